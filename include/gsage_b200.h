@@ -1,0 +1,224 @@
+/*
+ * gsage_b200.h -- C ABI of the B200-native GraphSAGE sample -> gather -> aggregate -> project engine.
+ *
+ * This header IS the drop-in boundary.  Every entry point is `extern "C"`, takes plain pointers and
+ * sizes (no torch / scipy / numpy types) and names the reference interface it stands in for
+ * (file:line under bkj/pytorch-graphsage).  The reference has no FFI of its own (it is 100 % Python);
+ * INTEGRATION.md shows the ctypes stub a maintainer would add to nn_modules.py / models.py.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative gsage_status otherwise; `gsage_last_error()`
+ *     returns a thread-local message (the Python host turns it into RuntimeError / IndexError, like
+ *     the reference's asserts, nn_modules.py:73,81);
+ *   - `*_dev` pointers are device pointers on the current device; `*_host` pointers are host pointers;
+ *   - `stream` is a `cudaStream_t` passed as void* (0 = legacy default stream).  Nothing synchronises
+ *     the stream unless the name ends in `_host` or the doc says so;
+ *   - ids are int64 in the reference's id space (sparse convention: row 0 = dummy node, node i = row i+1,
+ *     utils/convert.py:100-126);
+ *   - float tables/activations are row-major with an explicit leading dimension `ld` (in elements).
+ *     Rows must start 16-byte aligned (ld * sizeof(elem) % 16 == 0) and padding columns must be zero.
+ */
+#ifndef GSAGE_B200_H
+#define GSAGE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GSAGE_ABI_VERSION 1
+
+typedef enum gsage_status {
+    GSAGE_OK = 0,
+    GSAGE_ERR_INVALID = -1,     /* bad argument (shape / dtype / alignment / S <= 0)          */
+    GSAGE_ERR_CUDA = -2,        /* a CUDA runtime call failed                                   */
+    GSAGE_ERR_INDEX = -3,       /* an id outside the adjacency / table (scipy raises IndexError) */
+    GSAGE_ERR_RNG = -4,         /* the device stream ran out of look-ahead (never silently wrong) */
+    GSAGE_ERR_NOMEM = -5
+} gsage_status;
+
+typedef enum gsage_dtype { GSAGE_F32 = 0, GSAGE_BF16 = 1 } gsage_dtype;
+typedef enum gsage_act { GSAGE_ACT_NONE = 0, GSAGE_ACT_RELU = 1, GSAGE_ACT_TANH = 2 } gsage_act;
+typedef enum gsage_reduce { GSAGE_RED_MEAN = 0, GSAGE_RED_MAX = 1, GSAGE_RED_SUM = 2 } gsage_reduce;
+typedef enum gsage_aggregator {
+    GSAGE_AGG_MEAN = 0, GSAGE_AGG_MAX_POOL = 1, GSAGE_AGG_MEAN_POOL = 2, GSAGE_AGG_ATTENTION = 3
+} gsage_aggregator;
+typedef enum gsage_prep { GSAGE_PREP_IDENTITY = 0, GSAGE_PREP_NODE_EMBEDDING = 1, GSAGE_PREP_LINEAR = 2 } gsage_prep;
+
+typedef struct gsage_graph gsage_graph;     /* device-resident adjacency (both samplers' `adj`)      */
+typedef struct gsage_rng gsage_rng;         /* device-resident numpy-legacy MT19937 stream           */
+typedef struct gsage_engine gsage_engine;   /* GSSupervised.forward re-expressed over ids            */
+
+int gsage_abi_version(void);
+const char* gsage_last_error(void);
+/* name, SM count, HBM bytes of the current device */
+int gsage_device_info(char* name_out, int name_cap, int* sm_count, int64_t* hbm_bytes, int* cc_major, int* cc_minor);
+/* one process per GPU: bind this library's CUDA runtime to `device` (call before creating any object) */
+int gsage_set_device(int device);
+/* number of kernels this library has launched in this process (bench.py's `gpu_launches`) */
+int64_t gsage_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * Adjacency.  Replaces: `parse_csr_matrix` (problem.py:70-72) and
+ * `SparseUniformNeighborSampler.__init__` (nn_modules.py:72-78: scipy CSR + degree table).
+ * ------------------------------------------------------------------------------------------------ */
+
+/* From scipy-canonical CSR arrays on the host (sorted indices, duplicates summed).  `indices_host` may be
+ * NULL when the matrix follows the reference's file convention (columns of a row are 0..deg-1). */
+int gsage_graph_from_csr(const int64_t* indptr_host, const int64_t* indices_host, const int64_t* data_host,
+                         int64_t n_rows, int64_t n_cols, gsage_graph** out);
+/* From the 3 x nnz [v; r; c] triplets of a sparse problem file (problem.py:70-72 semantics: shape inferred
+ * as (max r + 1, max c + 1), duplicate (r, c) summed). */
+int gsage_graph_from_triplets(const int64_t* v_host, const int64_t* r_host, const int64_t* c_host, int64_t nnz,
+                              gsage_graph** out);
+void gsage_graph_destroy(gsage_graph* g);
+/* shape = (n_rows, n_cols); canonical = 1 when the column array is redundant and was dropped on device */
+int gsage_graph_info(const gsage_graph* g, int64_t* n_rows, int64_t* n_cols, int64_t* nnz, int* canonical,
+                     int64_t* device_bytes);
+/* the reference's `sampler.degrees` (nn_modules.py:76-78), copied to the host (n_rows int64) */
+int gsage_graph_degrees_host(const gsage_graph* g, int64_t* degrees_host);
+
+/* ------------------------------------------------------------------------------------------------
+ * Random stream.  Replaces the global numpy legacy RandomState the reference seeds in
+ * helpers.set_seeds (helpers.py:14-18) and draws from in nn_modules.py:88 / problem.py:146.
+ * ------------------------------------------------------------------------------------------------ */
+int gsage_rng_create(gsage_rng** out);
+void gsage_rng_destroy(gsage_rng* r);
+int gsage_rng_seed(gsage_rng* r, uint32_t seed, void* stream);                          /* np.random.seed    */
+int gsage_rng_set_state(gsage_rng* r, const uint32_t key_host[624], int pos, void* stream);   /* set_state  */
+int gsage_rng_get_state(gsage_rng* r, uint32_t key_host[624], int* pos, void* stream);  /* get_state; syncs  */
+/* next `count` raw tempered 32-bit words (== np.frombuffer(RandomState.bytes(4*count), '<u4')) */
+int gsage_rng_raw(gsage_rng* r, int64_t count, uint32_t* out_dev, void* stream);
+/* np.random.choice(hi, count) / legacy randint(0, hi, count): masked rejection, one word per attempt */
+int gsage_rng_randint(gsage_rng* r, uint32_t hi, int64_t count, uint32_t* out_dev, void* stream);
+/* np.random.permutation(np.arange(n)) (problem.py:146), int64 out */
+int gsage_rng_permutation(gsage_rng* r, int64_t n, int64_t* out_dev, void* stream);
+/* raises the sticky device error flag, if any (look-ahead exhausted); syncs the stream */
+int gsage_rng_check(gsage_rng* r, void* stream);
+/* total raw words consumed since the last seed / set_state; syncs the stream */
+int gsage_rng_consumed(gsage_rng* r, int64_t* words, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Samplers.  Replace SparseUniformNeighborSampler.__call__ (nn_modules.py:80-101) and
+ * UniformNeighborSampler.__call__ (nn_modules.py:42-49).
+ * ------------------------------------------------------------------------------------------------ */
+
+/* out[i*S + j] = A[ids[i], sel[i*S + j] % degree(ids[i])]  (0 when the row is empty).  `sel_dev` holds the
+ * n*S bounded draws in [0, n_cols) -- drawn by the host from np.random exactly like nn_modules.py:88
+ * ("mode A"), or by gsage_rng_randint.  Out-of-range ids raise the graph's sticky index-error flag. */
+int gsage_sample_sparse(gsage_graph* g, const int64_t* ids_dev, int64_t n, int S, const uint32_t* sel_dev,
+                        int64_t* out_dev, void* stream);
+/* same, drawing from the device stream ("mode B": no host round trip, same indices bit for bit) */
+int gsage_sample_sparse_rng(gsage_graph* g, gsage_rng* r, const int64_t* ids_dev, int64_t n, int S,
+                            int64_t* out_dev, void* stream);
+/* GSAGE_ERR_INDEX if any sampler call since the last check saw an id outside [0, n_rows); syncs */
+int gsage_graph_check(gsage_graph* g, void* stream);
+/* dense 2-D edgelist: out[i, j] = adj[ids[i], perm[j]] for j < S; one shared permutation (torch.randperm(K)) */
+int gsage_sample_dense(const int64_t* adj_dev, int64_t n_rows, int K, const int64_t* ids_dev, int64_t n,
+                       const int64_t* perm_dev, int S, int64_t* out_dev, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Gather / aggregate.  Replace `feats[ids]` (models.py:76,80), nn.Embedding lookups (nn_modules.py:146,149)
+ * and the reductions inside the aggregators (nn_modules.py:197-198, 225-226/240/252, 314-315).
+ * ------------------------------------------------------------------------------------------------ */
+
+/* out[i, :d] = table[ids[i], :d] (ids NULL -> identity).  out may be a column slice: out_dev + col, ld_out. */
+int gsage_gather_rows(const void* table_dev, int dtype, int64_t ld, int64_t n_table_rows, int d,
+                      const int64_t* ids_dev, int64_t n, void* out_dev, int out_dtype, int64_t ld_out, void* stream);
+/* THE fused gather+aggregate kernel: out[p, :] = reduce_j w[p*S+j] * table[ids[p*S + j], :]
+ *   ids NULL      -> rows p*S+j of `table` itself (the contiguous `neibs.view(N, S, d)` case)
+ *   weights NULL  -> 1 (MEAN divides by S including dummy rows; MAX ignores weights)
+ * fp32 accumulation whatever the table dtype. */
+int gsage_gather_reduce(const void* table_dev, int dtype, int64_t ld, int64_t n_table_rows, int d,
+                        const int64_t* ids_dev, int64_t n_parents, int S, int reduce, const float* weights_dev,
+                        void* out_dev, int out_dtype, int64_t ld_out, void* stream);
+/* attention weights (nn_modules.py:307-311): w[p, j] = softmax_j <na[p*S+j, :H], xa[p, :H]>, fp32 */
+int gsage_attention_weights(const void* na_dev, const void* xa_dev, int dtype, int64_t ld, int H,
+                            int64_t n_parents, int S, float* w_dev, void* stream);
+/* F.normalize(dim=1, eps=1e-12) (models.py:90), fp32 out */
+int gsage_l2_normalize(const void* x_dev, int dtype, int64_t ld, int64_t n, int d, float* out_dev, int64_t ld_out,
+                       void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Projection.  Replaces the nn.Linear calls of the aggregators and preps
+ * (nn_modules.py:150,166,200,224,228,307-308,317; models.py:91).
+ *   out[:, col0 : col0+O] = act( A[ids] (n x d) . W^T (O x d, row-major, ldw) + bias )
+ * `ids` NULL -> A read in place.  A / W / out dtypes independent (fp32 or bf16); fp32 accumulate.
+ * `exact` != 0 forces the fp32 FFMA kernel; 0 lets bf16 operands run on the tcgen05 tensor-core kernel.
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct gsage_linear_seg {
+    const void* a_dev; int a_dtype; int64_t lda; const int64_t* ids_dev;    /* A source (+ optional gather) */
+    const void* w_dev; int w_dtype; int64_t ldw; int d; int O;               /* W (O x d)                    */
+    const float* bias_dev;                                                   /* O floats or NULL             */
+    int64_t col0;                                                            /* output column offset         */
+} gsage_linear_seg;
+
+/* up to two segments writing disjoint column ranges of one output: the "concat-with-self" of
+ * nn_modules.py:200 ([fc_x(x) | fc_neib(agg)]) is ONE launch */
+int gsage_linear(const gsage_linear_seg* segs, int n_segs, int64_t n, int act, void* out_dev, int out_dtype,
+                 int64_t ld_out, int exact, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Engine.  Replaces GSSupervised.forward (models.py:71-91) for 2-layer stacks: owns the hop buffers, the
+ * workspace and the kernel order (hop-0 draws before hop-1 draws).
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct gsage_engine_config {
+    int aggregator;                 /* gsage_aggregator                                                  */
+    int prep;                       /* gsage_prep                                                        */
+    int n_layers;                   /* must be 2 (train.py:105-118 hard-codes two)                        */
+    int fanout[2];                  /* n_samples per hop                                                  */
+    int out_dim[2];                 /* O per layer (aggregator output is 2*O)                             */
+    int act[2];                     /* gsage_act per layer (train.py:110,116: relu, identity)             */
+    int n_classes;
+    int compute_dtype;              /* GSAGE_F32: every kernel fp32-exact.  GSAGE_BF16: bf16 tables/activations,
+                                       fp32 accumulate, tensor-core projections                           */
+    /* node features (`feats`, problem.py:118-121); NULL for feats=None (Pokec) */
+    const void* feats_dev; int feats_dtype; int64_t feats_ld; int feats_dim; int64_t feats_rows;
+    /* NodeEmbeddingPrep (nn_modules.py:126-155): table (n_nodes+1, 64), fc 64x64 + bias; n_nodes = adj.shape[0] */
+    const void* emb_dev; int emb_dtype; int64_t emb_ld; int emb_dim; int64_t n_nodes;
+    int hidden_dim;                 /* pool MLP width (512) / attention width (32)                        */
+    int64_t max_batch;              /* workspace is sized for this many seeds                             */
+} gsage_engine_config;
+
+/* fp32 weights, named after the reference's state_dict keys; unused ones NULL. All row-major (out, in). */
+typedef struct gsage_layer_weights {
+    const float* fc_x;              /* agg_layers.k.fc_x.weight    (O, d_in)                              */
+    const float* fc_neib;           /* agg_layers.k.fc_neib.weight (O, d_in | hidden)                     */
+    const float* mlp_w;             /* agg_layers.k.mlp.0.weight   (hidden, d_in)   pool                  */
+    const float* mlp_b;             /* agg_layers.k.mlp.0.bias     (hidden)         pool                  */
+    const float* att_w1;            /* agg_layers.k.att.0.weight   (hidden, d_in)   attention             */
+    const float* att_w2;            /* agg_layers.k.att.2.weight   (hidden, hidden) attention             */
+} gsage_layer_weights;
+
+typedef struct gsage_weights {
+    gsage_layer_weights layer[2];
+    const float* fc_w;              /* fc.weight (n_classes, 2*O_last)                                    */
+    const float* fc_b;              /* fc.bias                                                            */
+    const float* prep_fc_w;         /* prep.fc.weight: (64,64) node_embedding | (32, d) linear            */
+    const float* prep_fc_b;         /* prep.fc.bias   (node_embedding only)                               */
+    int prep_out_dim;               /* LinearPrep output_dim (32)                                         */
+} gsage_weights;
+
+int gsage_engine_create(const gsage_engine_config* cfg, gsage_engine** out);
+void gsage_engine_destroy(gsage_engine* e);
+/* (re)loads weights: converts to the compute dtype / padded layouts the kernels want */
+int gsage_engine_set_weights(gsage_engine* e, const gsage_weights* w, void* stream);
+/* logits[B, n_classes] (fp32) = fc(normalize(agg2(agg1(...))))  for seeds ids_dev[0:B].
+ * Sampling draws from `rng` (device stream), hop 0 then hop 1. */
+int gsage_engine_forward(gsage_engine* e, gsage_graph* g, gsage_rng* rng, const int64_t* ids_dev, int64_t B,
+                         float* logits_dev, void* stream);
+/* the same call for host buffers: H2D of the seed ids, forward, D2H of the logits, stream-synchronised.
+ * This is the end-to-end entry a reference-side caller binds (ids and logits are what models.py:71 takes/returns). */
+int gsage_engine_forward_host(gsage_engine* e, gsage_graph* g, gsage_rng* rng, const int64_t* ids_host, int64_t B,
+                              float* logits_host, void* stream);
+/* device views of the last forward's intermediates (valid until the next forward): hop ids and layer outputs.
+ * what: 0 ids0, 1 ids1, 2 ids2 (int64) ; 10 layer-1 output (26B x 2*O1) ; 11 layer-2 output (B x 2*O2) */
+int gsage_engine_peek(gsage_engine* e, int what, const void** ptr_dev, int64_t* rows, int64_t* cols, int64_t* ld,
+                      int* dtype);
+int64_t gsage_engine_workspace_bytes(const gsage_engine* e);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GSAGE_B200_H */

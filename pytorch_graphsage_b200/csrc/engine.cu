@@ -1,0 +1,339 @@
+// engine.cu -- GSSupervised.forward re-expressed over ids (the "wide" drop-in entry).
+//
+// Replaces  GSSupervised.forward  (/root/reference/models.py:71-91): sample both hops, prep every hop,
+// apply aggregator layer 1 to the pairs (x0,x1) and (x1,x2), layer 2 to the result pair, L2-normalise, fc.
+//
+// What changes versus the reference's dataflow (results identical up to fp32 rounding):
+//   * ids never leave the device: hop-0 draws, then hop-1 draws, from the device MT19937 stream (same order
+//     as the reference consumes np.random); the three hop id arrays live back to back in one
+//     buffer so "all parents of layer 1" is a prefix of it;
+//   * with the identity prep the neighbour rows are never materialised: every consumer (reduce kernel,
+//     projection kernels) takes (table, ids) and gathers on the fly;
+//   * `torch.cat([fc_x(x), fc_neib(agg)])` is one launch writing two column ranges.
+#include "graph.cuh"
+#include "mt19937.cuh"
+#include "linear.cuh"
+
+#include <vector>
+#include <algorithm>
+
+namespace gsage {
+int sample_sparse_launch(gsage_graph* g, const int64_t* ids, int64_t n, int S, const uint32_t* sel, int64_t* out,
+                         cudaStream_t s);
+int gather_reduce_launch(const void* table, int dtype, int64_t ld, int64_t rows, int d, const int64_t* ids,
+                         int64_t n_parents, int S, int reduce, const float* weights, void* out, int out_dtype,
+                         int64_t ld_out, cudaStream_t s);
+
+// a set of rows some kernel will read: either (table, ids) gathered on the fly or a materialised buffer
+struct RowSrc {
+    const void* base; int dtype; int64_t ld; int64_t table_rows; const int64_t* ids; int d;
+    RowSrc shifted(int64_t rows) const {       // the same source starting `rows` further down
+        RowSrc r = *this;
+        if (ids) r.ids = ids + rows;
+        else { r.base = (const char*)base + rows * ld * (int64_t)dtype_size(dtype); r.table_rows = table_rows - rows; }
+        return r;
+    }
+};
+
+__global__ void __launch_bounds__(256) fill_i64_kernel(int64_t* p, int64_t n, int64_t v) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+
+}  // namespace gsage
+
+using namespace gsage;
+
+struct gsage_engine {
+    gsage_engine_config cfg;
+    gsage_weights w;
+    bool have_weights = false;
+    int T = GSAGE_F32;                 // compute dtype of tables / activations
+    int d_prep = 0, ld_prep = 0;       // row width after prep (+ padded ld)
+    int hid = 0;
+    int64_t maxB = 0, n0 = 0, n1 = 0, n2 = 0;   // capacities in rows per hop
+    int64_t B = 0;                      // batch of the last forward
+    char* ws = nullptr; int64_t ws_bytes = 0;
+    // carved views
+    int64_t* ids = nullptr; uint32_t* sel = nullptr; int64_t* look0 = nullptr;
+    void* X = nullptr;                  // materialised prepped rows (non-identity preps)
+    void* M = nullptr;                  // reduced neighbour rows, one application at a time
+    void* HN = nullptr; void* Pp = nullptr;          // pool: hidden rows / pooled rows
+    void* T1 = nullptr; void* NA = nullptr; void* T1x = nullptr; void* XA = nullptr; float* AW = nullptr;   // attention
+    void* H1 = nullptr;                 // layer-1 output (n0 + n1, 2*O1)
+    float* Z = nullptr; float* ZN = nullptr; float* LG = nullptr;
+    int64_t ld_h1 = 0;
+};
+
+static int64_t pad_to(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
+
+static int linear_call(const RowSrc& a, const float* W, int64_t ldw, int O, const float* bias, int64_t n, int act,
+                       void* out, int out_dtype, int64_t ld_out, int64_t col0, int exact, cudaStream_t s) {
+    LinearParams P;
+    P.n_segs = 1; P.n = n; P.act = act; P.out = out; P.out_dtype = out_dtype; P.ld_out = ld_out;
+    P.seg[0] = LinearSeg{a.base, a.dtype, a.ld, a.ids, W, GSAGE_F32, ldw, a.d, O, bias, col0};
+    if (n == 0) return GSAGE_OK;
+    return linear_dispatch(P, exact, s);
+}
+
+static int combine_call(const RowSrc& x, const float* Wx, const RowSrc& m, const float* Wn, int O, int64_t n, int act,
+                        void* out, int out_dtype, int64_t ld_out, int exact, cudaStream_t s) {
+    LinearParams P;
+    P.n_segs = 2; P.n = n; P.act = act; P.out = out; P.out_dtype = out_dtype; P.ld_out = ld_out;
+    P.seg[0] = LinearSeg{x.base, x.dtype, x.ld, x.ids, Wx, GSAGE_F32, (int64_t)x.d, x.d, O, nullptr, 0};
+    P.seg[1] = LinearSeg{m.base, m.dtype, m.ld, m.ids, Wn, GSAGE_F32, (int64_t)m.d, m.d, O, nullptr, (int64_t)O};
+    if (n == 0) return GSAGE_OK;
+    return linear_dispatch(P, exact, s);
+}
+
+// one aggregator application: out[n, 2*O] = act([fc_x(x) | fc_neib(reduce(nb))])   (nn_modules.py:196-204 etc.)
+static int apply_aggregator(gsage_engine* e, int layer, const RowSrc& x, const RowSrc& nb, int64_t n, int S, void* out,
+                            int out_dtype, int64_t ld_out, cudaStream_t s) {
+    const gsage_layer_weights& L = e->w.layer[layer];
+    const int O = e->cfg.out_dim[layer], act = e->cfg.act[layer], T = e->T;
+    const int exact = (T == GSAGE_F32);
+    const int d = x.d;
+    const int64_t ldm = pad_to(d, 16 / (int64_t)dtype_size(T) * 2);
+    switch (e->cfg.aggregator) {
+    case GSAGE_AGG_MEAN: {
+        GS_TRY(gather_reduce_launch(nb.base, nb.dtype, nb.ld, nb.table_rows, d, nb.ids, n, S, GSAGE_RED_MEAN, nullptr, e->M, T, ldm, s));
+        RowSrc m{e->M, T, ldm, n, nullptr, d};
+        return combine_call(x, L.fc_x, m, L.fc_neib, O, n, act, out, out_dtype, ld_out, exact, s);
+    }
+    case GSAGE_AGG_MAX_POOL:
+    case GSAGE_AGG_MEAN_POOL: {
+        const int H = e->hid;
+        GS_TRY(linear_call(nb, L.mlp_w, d, H, L.mlp_b, n * S, GSAGE_ACT_RELU, e->HN, T, H, 0, exact, s));
+        GS_TRY(gather_reduce_launch(e->HN, T, H, n * S, H, nullptr, n, S,
+                                    e->cfg.aggregator == GSAGE_AGG_MAX_POOL ? GSAGE_RED_MAX : GSAGE_RED_MEAN, nullptr,
+                                    e->Pp, T, H, s));
+        RowSrc p{e->Pp, T, H, n, nullptr, H};
+        return combine_call(x, L.fc_x, p, L.fc_neib, O, n, act, out, out_dtype, ld_out, exact, s);
+    }
+    case GSAGE_AGG_ATTENTION: {
+        const int H = e->hid;
+        GS_CHECK_ARG(S > 1, "attention aggregator: S must be > 1");
+        GS_TRY(linear_call(nb, L.att_w1, d, H, nullptr, n * S, GSAGE_ACT_TANH, e->T1, GSAGE_F32, H, 0, exact, s));
+        RowSrc t1{e->T1, GSAGE_F32, H, n * S, nullptr, H};
+        GS_TRY(linear_call(t1, L.att_w2, H, H, nullptr, n * S, GSAGE_ACT_NONE, e->NA, GSAGE_F32, H, 0, 1, s));
+        GS_TRY(linear_call(x, L.att_w1, d, H, nullptr, n, GSAGE_ACT_TANH, e->T1x, GSAGE_F32, H, 0, exact, s));
+        RowSrc t1x{e->T1x, GSAGE_F32, H, n, nullptr, H};
+        GS_TRY(linear_call(t1x, L.att_w2, H, H, nullptr, n, GSAGE_ACT_NONE, e->XA, GSAGE_F32, H, 0, 1, s));
+        GS_TRY(gsage_attention_weights(e->NA, e->XA, GSAGE_F32, H, H, n, S, e->AW, s));
+        GS_TRY(gather_reduce_launch(nb.base, nb.dtype, nb.ld, nb.table_rows, d, nb.ids, n, S, GSAGE_RED_SUM, e->AW, e->M, T, ldm, s));
+        RowSrc m{e->M, T, ldm, n, nullptr, d};
+        return combine_call(x, L.fc_x, m, L.fc_neib, O, n, act, out, out_dtype, ld_out, exact, s);
+    }
+    }
+    set_error("engine: unknown aggregator %d", e->cfg.aggregator);
+    return GSAGE_ERR_INVALID;
+}
+
+extern "C" {
+
+int gsage_engine_create(const gsage_engine_config* cfg, gsage_engine** out) {
+    GS_CHECK_ARG(cfg && out, "engine_create: NULL argument");
+    GS_CHECK_ARG(cfg->n_layers == 2, "engine_create: exactly two layers (train.py:105-118)");
+    GS_CHECK_ARG(cfg->fanout[0] > 0 && cfg->fanout[1] > 0, "engine_create: fanouts must be > 0");
+    GS_CHECK_ARG(cfg->out_dim[0] > 0 && cfg->out_dim[1] > 0 && cfg->n_classes > 0, "engine_create: bad dims");
+    GS_CHECK_ARG(cfg->max_batch > 0, "engine_create: max_batch must be > 0");
+    GS_CHECK_ARG(cfg->compute_dtype == GSAGE_F32 || cfg->compute_dtype == GSAGE_BF16, "engine_create: bad compute dtype");
+    GS_CHECK_ARG(cfg->aggregator >= GSAGE_AGG_MEAN && cfg->aggregator <= GSAGE_AGG_ATTENTION, "engine_create: bad aggregator");
+    GS_CHECK_ARG(cfg->prep >= GSAGE_PREP_IDENTITY && cfg->prep <= GSAGE_PREP_LINEAR, "engine_create: bad prep");
+    const bool has_feats = cfg->feats_dev != nullptr;
+    if (cfg->prep == GSAGE_PREP_IDENTITY || cfg->prep == GSAGE_PREP_LINEAR)
+        GS_CHECK_ARG(has_feats, "engine_create: this prep needs node features");
+    if (cfg->prep == GSAGE_PREP_NODE_EMBEDDING)
+        GS_CHECK_ARG(cfg->emb_dev && cfg->emb_dim > 0 && cfg->n_nodes > 0, "engine_create: node_embedding needs the table");
+    if (has_feats) GS_CHECK_ARG(cfg->feats_dtype == cfg->compute_dtype, "engine_create: feats dtype must equal compute dtype");
+
+    gsage_engine* e = new gsage_engine();
+    e->cfg = *cfg;
+    e->T = cfg->compute_dtype;
+    const int64_t es = (int64_t)dtype_size(e->T);
+    const int64_t vec = 16 / es;
+    switch (cfg->prep) {
+    case GSAGE_PREP_IDENTITY: e->d_prep = cfg->feats_dim; break;
+    case GSAGE_PREP_LINEAR: e->d_prep = 32; break;            // overwritten by weights.prep_out_dim at set_weights
+    case GSAGE_PREP_NODE_EMBEDDING: e->d_prep = (has_feats ? cfg->feats_dim : 0) + cfg->emb_dim; break;
+    }
+    e->ld_prep = (int)pad_to(e->d_prep, vec * 2);
+    e->hid = cfg->hidden_dim > 0 ? cfg->hidden_dim : (cfg->aggregator == GSAGE_AGG_ATTENTION ? 32 : 512);
+    e->maxB = cfg->max_batch;
+    e->n0 = e->maxB; e->n1 = e->n0 * cfg->fanout[0]; e->n2 = e->n1 * cfg->fanout[1];
+    const int64_t O1 = cfg->out_dim[0], O2 = cfg->out_dim[1];
+    e->ld_h1 = pad_to(2 * O1, vec * 2);
+
+    // carve the workspace
+    int64_t off = 0;
+    auto carve = [&](int64_t bytes) { int64_t at = off; off += pad_to(std::max<int64_t>(bytes, 16), 256); return at; };
+    const int64_t o_ids = carve(8 * (e->n0 + e->n1 + e->n2));
+    const int64_t o_sel = carve(4 * e->n2);
+    const int64_t o_look = carve(8 * e->n0);
+    const int64_t o_X = cfg->prep == GSAGE_PREP_IDENTITY ? -1 : carve(es * e->ld_prep * (e->n0 + e->n1 + e->n2));
+    const int64_t dmax = std::max<int64_t>(e->ld_prep, e->ld_h1);
+    const int64_t o_M = carve(es * pad_to(dmax, vec * 2) * e->n1);
+    int64_t o_HN = -1, o_P = -1, o_T1 = -1, o_NA = -1, o_T1x = -1, o_XA = -1, o_AW = -1;
+    if (cfg->aggregator == GSAGE_AGG_MAX_POOL || cfg->aggregator == GSAGE_AGG_MEAN_POOL) {
+        o_HN = carve(es * e->hid * e->n2);
+        o_P = carve(es * e->hid * e->n1);
+    }
+    if (cfg->aggregator == GSAGE_AGG_ATTENTION) {
+        o_T1 = carve(4 * e->hid * e->n2); o_NA = carve(4 * e->hid * e->n2);
+        o_T1x = carve(4 * e->hid * e->n1); o_XA = carve(4 * e->hid * e->n1);
+        o_AW = carve(4 * e->n2);
+    }
+    const int64_t o_H1 = carve(es * e->ld_h1 * (e->n0 + e->n1));
+    const int64_t o_Z = carve(4 * 2 * O2 * e->n0);
+    const int64_t o_ZN = carve(4 * 2 * O2 * e->n0);
+    const int64_t o_LG = carve(4 * (int64_t)cfg->n_classes * e->n0);
+    e->ws_bytes = off;
+    if (cudaMalloc((void**)&e->ws, (size_t)off) != cudaSuccess) {
+        set_error("engine_create: cudaMalloc of %lld workspace bytes failed", (long long)off);
+        delete e;
+        return GSAGE_ERR_NOMEM;
+    }
+    cudaMemset(e->ws, 0, (size_t)off);      // padding columns of every intermediate stay zero forever
+    auto at = [&](int64_t o) -> char* { return o < 0 ? nullptr : e->ws + o; };
+    e->ids = (int64_t*)at(o_ids); e->sel = (uint32_t*)at(o_sel); e->look0 = (int64_t*)at(o_look);
+    e->X = at(o_X); e->M = at(o_M); e->HN = at(o_HN); e->Pp = at(o_P);
+    e->T1 = at(o_T1); e->NA = at(o_NA); e->T1x = at(o_T1x); e->XA = at(o_XA); e->AW = (float*)at(o_AW);
+    e->H1 = at(o_H1); e->Z = (float*)at(o_Z); e->ZN = (float*)at(o_ZN); e->LG = (float*)at(o_LG);
+    *out = e;
+    return GSAGE_OK;
+}
+
+void gsage_engine_destroy(gsage_engine* e) {
+    if (!e) return;
+    cudaFree(e->ws);
+    delete e;
+}
+
+int64_t gsage_engine_workspace_bytes(const gsage_engine* e) { return e ? e->ws_bytes : 0; }
+
+int gsage_engine_set_weights(gsage_engine* e, const gsage_weights* w, void* stream) {
+    (void)stream;
+    GS_CHECK_ARG(e && w, "engine_set_weights: NULL argument");
+    for (int l = 0; l < 2; ++l) {
+        GS_CHECK_ARG(w->layer[l].fc_x && w->layer[l].fc_neib, "engine_set_weights: fc_x / fc_neib missing (layer %d)", l);
+        if (e->cfg.aggregator == GSAGE_AGG_MAX_POOL || e->cfg.aggregator == GSAGE_AGG_MEAN_POOL)
+            GS_CHECK_ARG(w->layer[l].mlp_w && w->layer[l].mlp_b, "engine_set_weights: pool MLP missing (layer %d)", l);
+        if (e->cfg.aggregator == GSAGE_AGG_ATTENTION)
+            GS_CHECK_ARG(w->layer[l].att_w1 && w->layer[l].att_w2, "engine_set_weights: attention MLP missing (layer %d)", l);
+    }
+    GS_CHECK_ARG(w->fc_w && w->fc_b, "engine_set_weights: classifier missing");
+    if (e->cfg.prep == GSAGE_PREP_NODE_EMBEDDING) GS_CHECK_ARG(w->prep_fc_w && w->prep_fc_b, "engine_set_weights: prep.fc missing");
+    if (e->cfg.prep == GSAGE_PREP_LINEAR) {
+        GS_CHECK_ARG(w->prep_fc_w && w->prep_out_dim > 0, "engine_set_weights: prep.fc missing");
+        GS_CHECK_ARG(w->prep_out_dim <= e->ld_prep, "engine_set_weights: LinearPrep wider than the workspace rows");
+        e->d_prep = w->prep_out_dim;
+    }
+    e->w = *w;
+    e->have_weights = true;
+    return GSAGE_OK;
+}
+
+int gsage_engine_forward(gsage_engine* e, gsage_graph* g, gsage_rng* rng, const int64_t* ids_dev, int64_t B,
+                         float* logits_dev, void* stream) {
+    GS_CHECK_ARG(e && g && rng && ids_dev && logits_dev, "engine_forward: NULL argument");
+    GS_CHECK_ARG(e->have_weights, "engine_forward: call gsage_engine_set_weights first");
+    GS_CHECK_ARG(B > 0 && B <= e->maxB, "engine_forward: batch %lld outside (0, max_batch=%lld]", (long long)B, (long long)e->maxB);
+    GS_CHECK_ARG(g->n_cols >= 1 && g->n_cols <= 0xFFFFFFFFLL, "engine_forward: adjacency width out of range");
+    cudaStream_t s = as_stream(stream);
+    const gsage_engine_config& c = e->cfg;
+    const int S1 = c.fanout[0], S2 = c.fanout[1], T = e->T;
+    const int64_t n0 = B, n1 = B * S1, n2 = n1 * S2;
+    const int64_t es = (int64_t)dtype_size(T);
+    e->B = B;
+
+    // ---- sample: hop 0 draws first, then hop 1 (models.py:78-79) ------------------------------------
+    int64_t* ids0 = e->ids; int64_t* ids1 = ids0 + n0; int64_t* ids2 = ids1 + n1;
+    if (ids_dev != ids0) GS_CUDA(cudaMemcpyAsync(ids0, ids_dev, 8 * n0, cudaMemcpyDeviceToDevice, s));
+    GS_TRY(rng_randint_internal(rng, (uint32_t)g->n_cols, n1, e->sel, s));
+    GS_TRY(sample_sparse_launch(g, ids0, n0, S1, e->sel, ids1, s));
+    GS_TRY(rng_randint_internal(rng, (uint32_t)g->n_cols, n2, e->sel, s));
+    GS_TRY(sample_sparse_launch(g, ids1, n1, S2, e->sel, ids2, s));
+
+    // ---- prep (models.py:76-81) ------------------------------------------------------------------------
+    RowSrc lvl;       // all three hops, hop k starts `offset_k` rows in
+    if (c.prep == GSAGE_PREP_IDENTITY) {
+        lvl = RowSrc{c.feats_dev, c.feats_dtype, c.feats_ld, c.feats_rows, ids0, c.feats_dim};
+    } else {
+        const int64_t ntot = n0 + n1 + n2;
+        const int64_t ldx = e->ld_prep;
+        if (c.prep == GSAGE_PREP_LINEAR) {
+            RowSrc f{c.feats_dev, c.feats_dtype, c.feats_ld, c.feats_rows, ids0, c.feats_dim};
+            GS_TRY(linear_call(f, e->w.prep_fc_w, c.feats_dim, e->d_prep, nullptr, ntot, GSAGE_ACT_NONE, e->X, T, ldx, 0,
+                               T == GSAGE_F32, s));
+        } else {
+            const int dfe = c.feats_dev ? c.feats_dim : 0;
+            if (c.feats_dev)
+                GS_TRY(gather_reduce_launch(c.feats_dev, c.feats_dtype, c.feats_ld, c.feats_rows, c.feats_dim, ids0, ntot, 1,
+                                            GSAGE_RED_SUM, nullptr, e->X, T, ldx, s));
+            // seeds look up the masked row n_nodes (nn_modules.py:149); deeper hops their own id
+            fill_i64_kernel<<<(unsigned)ceil_div(n0, 256), 256, 0, s>>>(e->look0, n0, c.n_nodes);
+            GS_LAUNCHED();
+            RowSrc e0{c.emb_dev, c.emb_dtype, c.emb_ld, c.n_nodes + 1, e->look0, c.emb_dim};
+            GS_TRY(linear_call(e0, e->w.prep_fc_w, c.emb_dim, c.emb_dim, e->w.prep_fc_b, n0, GSAGE_ACT_NONE, e->X, T, ldx,
+                               dfe, T == GSAGE_F32, s));
+            RowSrc e12{c.emb_dev, c.emb_dtype, c.emb_ld, c.n_nodes + 1, ids1, c.emb_dim};
+            GS_TRY(linear_call(e12, e->w.prep_fc_w, c.emb_dim, c.emb_dim, e->w.prep_fc_b, n1 + n2, GSAGE_ACT_NONE,
+                               (char*)e->X + n0 * ldx * es, T, ldx, dfe, T == GSAGE_F32, s));
+        }
+        lvl = RowSrc{e->X, T, ldx, ntot, nullptr, e->d_prep};
+    }
+
+    // ---- layer 1 on (x0, x1) and (x1, x2) with shared weights (models.py:85-86) ---------------------------
+    const int64_t ldh = e->ld_h1;
+    const int O1 = c.out_dim[0], O2 = c.out_dim[1];
+    GS_TRY(apply_aggregator(e, 0, lvl, lvl.shifted(n0), n0, S1, e->H1, T, ldh, s));
+    GS_TRY(apply_aggregator(e, 0, lvl.shifted(n0), lvl.shifted(n0 + n1), n1, S2, (char*)e->H1 + n0 * ldh * es, T, ldh, s));
+
+    // ---- layer 2 on (h0, h1) ----------------------------------------------------------------------------------
+    RowSrc h{e->H1, T, ldh, n0 + n1, nullptr, 2 * O1};
+    GS_TRY(apply_aggregator(e, 1, h, h.shifted(n0), n0, S1, e->Z, GSAGE_F32, 2 * O2, s));
+
+    // ---- normalise + classifier (models.py:90-91) -----------------------------------------------------------------
+    GS_TRY(gsage_l2_normalize(e->Z, GSAGE_F32, 2 * O2, n0, 2 * O2, e->ZN, 2 * O2, s));
+    RowSrc zn{e->ZN, GSAGE_F32, 2 * O2, n0, nullptr, 2 * O2};
+    return linear_call(zn, e->w.fc_w, 2 * O2, c.n_classes, e->w.fc_b, n0, GSAGE_ACT_NONE, logits_dev, GSAGE_F32, c.n_classes,
+                       0, 1, s);
+}
+
+int gsage_engine_forward_host(gsage_engine* e, gsage_graph* g, gsage_rng* rng, const int64_t* ids_host, int64_t B,
+                              float* logits_host, void* stream) {
+    GS_CHECK_ARG(e && ids_host && logits_host, "engine_forward_host: NULL argument");
+    GS_CHECK_ARG(B > 0 && B <= e->maxB, "engine_forward_host: batch outside (0, max_batch]");
+    cudaStream_t s = as_stream(stream);
+    // the seed ids go straight into the hop-0 slot of the id buffer; the logits come back from a dedicated view
+    int64_t* ids_stage = e->ids;
+    float* logits_dev = e->LG;
+    GS_CUDA(cudaMemcpyAsync(ids_stage, ids_host, 8 * B, cudaMemcpyHostToDevice, s));
+    int st = gsage_engine_forward(e, g, rng, ids_stage, B, logits_dev, stream);
+    if (st == GSAGE_OK) {
+        if (cudaMemcpyAsync(logits_host, logits_dev, 4 * B * e->cfg.n_classes, cudaMemcpyDeviceToHost, s) != cudaSuccess ||
+            cudaStreamSynchronize(s) != cudaSuccess) {
+            set_error("engine_forward_host: D2H copy failed: %s", cudaGetErrorString(cudaGetLastError()));
+            st = GSAGE_ERR_CUDA;
+        }
+    }
+    if (st == GSAGE_OK) st = gsage_rng_check(rng, stream);
+    if (st == GSAGE_OK) st = gsage_graph_check(g, stream);
+    return st;
+}
+
+int gsage_engine_peek(gsage_engine* e, int what, const void** ptr, int64_t* rows, int64_t* cols, int64_t* ld, int* dtype) {
+    GS_CHECK_ARG(e && ptr && rows && cols && ld && dtype, "engine_peek: NULL argument");
+    const int64_t B = e->B, n1 = B * e->cfg.fanout[0], n2 = n1 * e->cfg.fanout[1];
+    switch (what) {
+    case 0: *ptr = e->ids; *rows = B; *cols = 1; *ld = 1; *dtype = -1; return GSAGE_OK;
+    case 1: *ptr = e->ids + B; *rows = n1; *cols = 1; *ld = 1; *dtype = -1; return GSAGE_OK;
+    case 2: *ptr = e->ids + B + n1; *rows = n2; *cols = 1; *ld = 1; *dtype = -1; return GSAGE_OK;
+    case 10: *ptr = e->H1; *rows = B + n1; *cols = 2 * e->cfg.out_dim[0]; *ld = e->ld_h1; *dtype = e->T; return GSAGE_OK;
+    case 11: *ptr = e->Z; *rows = B; *cols = 2 * e->cfg.out_dim[1]; *ld = 2 * e->cfg.out_dim[1]; *dtype = GSAGE_F32; return GSAGE_OK;
+    }
+    set_error("engine_peek: unknown view %d", what);
+    return GSAGE_ERR_INVALID;
+}
+
+}  // extern "C"

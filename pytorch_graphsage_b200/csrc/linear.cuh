@@ -1,0 +1,23 @@
+// linear.cuh -- parameter block shared by the projection kernels (linear_simt.cu, linear_umma.cu)
+#pragma once
+#include "common.cuh"
+
+namespace gsage {
+
+struct LinearSeg {
+    const void* a; int a_dtype; int64_t lda; const int64_t* ids;
+    const void* w; int w_dtype; int64_t ldw; int d; int O;
+    const float* bias; int64_t col0;
+};
+
+struct LinearParams {
+    LinearSeg seg[2];
+    int n_segs; int64_t n; int act;
+    void* out; int out_dtype; int64_t ld_out;
+};
+
+int linear_simt_launch(const LinearParams& P, cudaStream_t s);
+// picks the tensor-core kernel when every operand qualifies and `exact` == 0, else the FFMA kernel
+int linear_dispatch(const LinearParams& P, int exact, cudaStream_t s);
+
+}  // namespace gsage

@@ -1,0 +1,133 @@
+// linear_simt.cu -- fp32-exact projection kernel (FFMA, fp32 accumulate): the parity-grade path.
+//
+// Replaces the nn.Linear calls on the hot path: fc_x / fc_neib + concat (/root/reference/nn_modules.py:200,
+// 228, 317), the pool MLP (:224), the attention MLP (:307-308), the prep affines (:150,166) and the final
+// classifier (/root/reference/models.py:91).
+//
+//   out[r, col0 + o] = act( sum_k A[row(r), k] * W[o, k] + bias[o] ),   row(r) = ids ? ids[r] : r
+//
+// Up to two segments per launch (blockIdx.z): the reference's `torch.cat([fc_x(x), fc_neib(agg)], dim=1)`
+// is one launch writing two column ranges of one buffer -- the concat never exists as a copy.
+// 64x64 output tile per CTA, 16-wide k steps through shared memory, 4x4 register tile per thread.
+// The self rows are gathered straight from the feature table by id inside the A-tile load.
+#include "linear.cuh"
+
+namespace gsage {
+
+static constexpr int BM = 64, BN = 64, BK = 16;
+
+template <typename T>
+__device__ __forceinline__ float load_elem(const void* base, int64_t idx) {
+    return ElemTraits<T>::load(reinterpret_cast<const T*>(base) + idx);
+}
+
+__device__ __forceinline__ float load_any(const void* base, int dtype, int64_t idx) {
+    return dtype == GSAGE_BF16 ? load_elem<__nv_bfloat16>(base, idx) : load_elem<float>(base, idx);
+}
+
+__global__ void __launch_bounds__(256) linear_simt_kernel(LinearParams P) {
+    const LinearSeg& sg = P.seg[blockIdx.z];
+    if ((int)(blockIdx.y * BN) >= sg.O) return;
+    __shared__ float As[BK][BM + 4];
+    __shared__ float Ws[BK][BN + 4];
+    const int tid = threadIdx.x;
+    const int tx = tid & 15, ty = tid >> 4;              // 16 x 16 threads, 4x4 outputs each
+    const int64_t row0 = (int64_t)blockIdx.x * BM;
+    const int col0 = blockIdx.y * BN;
+
+    // loader mapping: 64 rows x 16 k = 1024 elements, 4 per thread (same k-quad)
+    const int lrow = tid >> 2, lk = (tid & 3) * 4;
+    int64_t a_row = -1;
+    if (row0 + lrow < P.n) {
+        a_row = row0 + lrow;
+        if (sg.ids) a_row = sg.ids[a_row];
+    }
+    const int w_row = col0 + lrow;
+
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.0f;
+
+    for (int k0 = 0; k0 < sg.d; k0 += BK) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int k = k0 + lk + q;
+            float a = 0.0f, w = 0.0f;
+            if (a_row >= 0 && k < sg.d) a = load_any(sg.a, sg.a_dtype, a_row * sg.lda + k);
+            if (w_row < sg.O && k < sg.d) w = load_any(sg.w, sg.w_dtype, (int64_t)w_row * sg.ldw + k);
+            As[lk + q][lrow] = a;
+            Ws[lk + q][lrow] = w;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < BK; ++k) {
+            const float4 a4 = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
+            const float4 w4 = *reinterpret_cast<const float4*>(&Ws[k][tx * 4]);
+            const float a[4] = {a4.x, a4.y, a4.z, a4.w};
+            const float w[4] = {w4.x, w4.y, w4.z, w4.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], w[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int64_t r = row0 + ty * 4 + i;
+        if (r >= P.n) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int o = col0 + tx * 4 + j;
+            if (o >= sg.O) continue;
+            float v = acc[i][j];
+            if (sg.bias) v += sg.bias[o];
+            v = apply_act(v, P.act);
+            const int64_t at = r * P.ld_out + sg.col0 + o;
+            if (P.out_dtype == GSAGE_BF16) reinterpret_cast<__nv_bfloat16*>(P.out)[at] = __float2bfloat16_rn(v);
+            else reinterpret_cast<float*>(P.out)[at] = v;
+        }
+    }
+}
+
+int linear_simt_launch(const LinearParams& P, cudaStream_t s) {
+    int maxO = 0;
+    for (int i = 0; i < P.n_segs; ++i) maxO = P.seg[i].O > maxO ? P.seg[i].O : maxO;
+    dim3 grid((unsigned)ceil_div(P.n, BM), (unsigned)ceil_div(maxO, BN), (unsigned)P.n_segs);
+    linear_simt_kernel<<<grid, 256, 0, s>>>(P);
+    GS_LAUNCHED();
+    return GSAGE_OK;
+}
+
+}  // namespace gsage
+
+using namespace gsage;
+
+extern "C" int gsage_linear(const gsage_linear_seg* segs, int n_segs, int64_t n, int act, void* out_dev, int out_dtype,
+                            int64_t ld_out, int exact, void* stream) {
+    GS_CHECK_ARG(segs && (n_segs == 1 || n_segs == 2) && n >= 0 && out_dev, "linear: bad arguments");
+    GS_CHECK_ARG(out_dtype == GSAGE_F32 || out_dtype == GSAGE_BF16, "linear: bad out dtype");
+    GS_CHECK_ARG(act == GSAGE_ACT_NONE || act == GSAGE_ACT_RELU || act == GSAGE_ACT_TANH, "linear: bad activation");
+    LinearParams P;
+    P.n_segs = n_segs; P.n = n; P.act = act; P.out = out_dev; P.out_dtype = out_dtype; P.ld_out = ld_out;
+    for (int i = 0; i < n_segs; ++i) {
+        const gsage_linear_seg& g = segs[i];
+        GS_CHECK_ARG(g.a_dev && g.w_dev && g.d > 0 && g.O > 0 && g.lda >= g.d && g.ldw >= g.d && g.col0 >= 0 &&
+                     g.col0 + g.O <= ld_out, "linear: bad segment %d", i);
+        P.seg[i].a = g.a_dev; P.seg[i].a_dtype = g.a_dtype; P.seg[i].lda = g.lda; P.seg[i].ids = g.ids_dev;
+        P.seg[i].w = g.w_dev; P.seg[i].w_dtype = g.w_dtype; P.seg[i].ldw = g.ldw; P.seg[i].d = g.d; P.seg[i].O = g.O;
+        P.seg[i].bias = g.bias_dev; P.seg[i].col0 = g.col0;
+    }
+    if (n == 0) return GSAGE_OK;
+    return linear_dispatch(P, exact, as_stream(stream));
+}
+
+namespace gsage {
+int linear_dispatch(const LinearParams& P, int exact, cudaStream_t s) {
+    (void)exact;   // the tcgen05 kernel (linear_umma.cu) hooks in here once it is parity-green
+    return linear_simt_launch(P, s);
+}
+}  // namespace gsage

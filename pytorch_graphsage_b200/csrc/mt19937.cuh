@@ -1,0 +1,23 @@
+// mt19937.cuh -- the device MT19937 stream object (see mt19937.cu for the layout)
+#pragma once
+#include "common.cuh"
+
+struct gsage_rng {
+    uint32_t* ring = nullptr;      // device, cap untempered words
+    int64_t cap = 0;               // power of two
+    int64_t* cursor = nullptr;     // device int64[2], double-buffered
+    int* err_flag = nullptr;       // device, sticky
+    int* tile_count = nullptr;     // device scratch
+    int64_t* tile_off = nullptr;   // device scratch
+    int tiles_cap = 0;
+    int parity = 0;                // host: which cursor slot is current
+    int64_t gen_end = 0;           // host: words [.., gen_end) are generated
+    int64_t cursor_lb = 0, cursor_ub = 0;   // host bounds on the device cursor
+    int64_t origin = 0;            // cursor value at the last seed / set_state
+    int64_t prefetch_blocks = 256; // generate at least this many 624-word blocks per refill
+};
+
+namespace gsage {
+// bounded draws into a device buffer (gsage_rng_randint without the argument checks)
+int rng_randint_internal(gsage_rng* r, uint32_t hi, int64_t count, uint32_t* out, cudaStream_t s);
+}

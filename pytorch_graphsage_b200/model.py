@@ -1,0 +1,220 @@
+"""
+GSSupervised -- the reference's model class (/root/reference/models.py:21-104) over the fused engine.
+
+Same constructor signature, same submodule / parameter names (`prep.*`, `agg_layers.k.*`, `fc.*`), so a
+reference `state_dict` loads with `load_state_dict` and vice versa.  `forward(ids, feats, train)` returns the
+same logits; what differs is *who calls whom*: the reference's Python loop gathers rows and hands them to
+the aggregators, here the ids go to the library's engine (gsage_engine_forward) which samples, gathers,
+aggregates and projects on the device.  `forward_reference_order` keeps the reference's call order through
+the narrow operator API for parity debugging.
+"""
+
+import ctypes as C
+from functools import partial
+
+import torch
+from torch import nn
+from torch.nn import functional as F
+
+from . import _lib, ops
+from ._lib import check, lib
+from .graph import GraphCSR
+from .operators import (AttentionAggregator, MeanAggregator, MeanPoolAggregator, MaxPoolAggregator, NodeEmbeddingPrep,
+                        IdentityPrep, LinearPrep, SparseUniformNeighborSampler, _act_name)
+from .rng import default_rng
+
+
+def _agg_name(cls):
+    for name, k in (('mean', MeanAggregator), ('max_pool', MaxPoolAggregator), ('mean_pool', MeanPoolAggregator),
+                    ('attention', AttentionAggregator)):
+        if cls is k:
+            return name
+    raise ValueError('gsage engine: unsupported aggregator class %r' % (cls,))
+
+
+def _prep_name(cls):
+    for name, k in (('identity', IdentityPrep), ('node_embedding', NodeEmbeddingPrep), ('linear', LinearPrep)):
+        if cls is k:
+            return name
+    raise ValueError('gsage engine: unsupported prep class %r' % (cls,))
+
+
+class FeatureTable(object):
+    """`problem.feats` on the device in the layout the kernels want: 32-byte-aligned zero-padded rows,
+    fp32 or bf16.  `.view` is the logical (rows, d) tensor."""
+
+    def __init__(self, feats, dtype=torch.float32):
+        self.store, self.d = ops.pad_table(feats, dtype)
+        self.view = self.store[:, :self.d]
+        self.ld = self.store.shape[1]
+        self.rows = self.store.shape[0]
+        self.dtype = dtype
+
+
+class GSSupervised(nn.Module):
+    def __init__(self, input_dim, n_nodes, n_classes, layer_specs, aggregator_class, prep_class, sampler_class,
+                 adj, train_adj, lr_init=0.01, weight_decay=0.0, lr_schedule='constant', epochs=10,
+                 compute_dtype=torch.float32, max_batch=512, rng=None):
+        super(GSSupervised, self).__init__()
+        assert len(layer_specs) == 2, 'GSSupervised: the engine implements the two-layer stack of train.py:105-118'
+        self.layer_specs = layer_specs
+        self.n_nodes, self.n_classes = n_nodes, n_classes
+        self.compute_dtype = compute_dtype
+        self.max_batch = max_batch
+        self.rng = rng
+
+        # Sampler (models.py:41-44) -- one device graph per adjacency, shared when they are the same object
+        self.train_sampler = sampler_class(adj=train_adj)
+        self.val_sampler = self.train_sampler if adj is train_adj else sampler_class(adj=adj)
+        self.train_sample_fns = [partial(self.train_sampler, n_samples=s['n_train_samples']) for s in layer_specs]
+        self.val_sample_fns = [partial(self.val_sampler, n_samples=s['n_val_samples']) for s in layer_specs]
+
+        # Prep (models.py:47-48)
+        self.prep = prep_class(input_dim=input_dim, n_nodes=n_nodes)
+        self.input_dim = input_dim
+        input_dim = self.prep.output_dim
+
+        # Network (models.py:50-62)
+        agg_layers = []
+        for spec in layer_specs:
+            agg = aggregator_class(input_dim=input_dim, output_dim=spec['output_dim'], activation=spec['activation'])
+            agg_layers.append(agg)
+            input_dim = agg.output_dim
+        self.agg_layers = nn.Sequential(*agg_layers)
+        self.fc = nn.Linear(input_dim, n_classes, bias=True)
+
+        self._agg_name, self._prep_name = _agg_name(aggregator_class), _prep_name(prep_class)
+        self._engines = {}
+        self._tables = {}
+
+    # -- engine plumbing --------------------------------------------------------------------------
+    def _table(self, feats):
+        if feats is None:
+            return None
+        if isinstance(feats, FeatureTable):
+            return feats
+        key = (feats.data_ptr() if torch.is_tensor(feats) else id(feats), self.compute_dtype)
+        if key not in self._tables:
+            self._tables[key] = FeatureTable(feats, self.compute_dtype)
+        return self._tables[key]
+
+    def _engine(self, table, fanout, batch):
+        key = (None if table is None else table.store.data_ptr(), tuple(fanout))
+        eng = self._engines.get(key)
+        if eng is not None and eng['max_batch'] >= batch:
+            return eng
+        if eng is not None:
+            lib().gsage_engine_destroy(eng['h'])
+        ops._bind_device()
+        cfg = _lib.EngineConfig()
+        cfg.aggregator, cfg.prep, cfg.n_layers = _lib.AGGREGATOR[self._agg_name], _lib.PREP[self._prep_name], 2
+        for k, spec in enumerate(self.layer_specs):
+            cfg.fanout[k] = int(fanout[k])
+            cfg.out_dim[k] = int(spec['output_dim'])
+            cfg.act[k] = _lib.ACT[_act_name(spec['activation'])]
+        cfg.n_classes = self.n_classes
+        cfg.compute_dtype = _lib.BF16 if self.compute_dtype == torch.bfloat16 else _lib.F32
+        if table is not None:
+            cfg.feats_dev, cfg.feats_dtype = table.store.data_ptr(), ops.dt(table.store)
+            cfg.feats_ld, cfg.feats_dim, cfg.feats_rows = table.ld, table.d, table.rows
+        emb_keep = None
+        if self._prep_name == 'node_embedding':
+            emb = self.prep.embedding.weight.data
+            if self.compute_dtype == torch.bfloat16:
+                emb_keep = FeatureTable(emb, torch.bfloat16)
+                cfg.emb_dev, cfg.emb_dtype, cfg.emb_ld = emb_keep.store.data_ptr(), _lib.BF16, emb_keep.ld
+            else:
+                cfg.emb_dev, cfg.emb_dtype, cfg.emb_ld = emb.data_ptr(), _lib.F32, emb.stride(0)
+            cfg.emb_dim, cfg.n_nodes = self.prep.embedding_dim, self.n_nodes
+        agg0 = self.agg_layers[0]
+        cfg.hidden_dim = agg0.mlp[0].out_features if hasattr(agg0, 'mlp') else (agg0.att[0].out_features if hasattr(agg0, 'att') else 0)
+        cfg.max_batch = max(batch, self.max_batch)
+        h = C.c_void_p()
+        check(lib().gsage_engine_create(C.byref(cfg), C.byref(h)))
+        eng = dict(h=h, max_batch=cfg.max_batch, emb_keep=emb_keep, cfg=cfg)
+        self._engines[key] = eng
+        return eng
+
+    def _weights(self):
+        w = _lib.Weights()
+        p = lambda t: t.data.data_ptr()
+        for k, agg in enumerate(self.agg_layers.children()):
+            for t in agg.parameters():
+                assert t.is_cuda and t.dtype == torch.float32 and t.is_contiguous(), 'GSSupervised: move the model to CUDA (fp32)'
+            w.layer[k].fc_x, w.layer[k].fc_neib = p(agg.fc_x.weight), p(agg.fc_neib.weight)
+            if hasattr(agg, 'mlp'):
+                w.layer[k].mlp_w, w.layer[k].mlp_b = p(agg.mlp[0].weight), p(agg.mlp[0].bias)
+            if hasattr(agg, 'att'):
+                w.layer[k].att_w1, w.layer[k].att_w2 = p(agg.att[0].weight), p(agg.att[2].weight)
+        w.fc_w, w.fc_b = p(self.fc.weight), p(self.fc.bias)
+        if self._prep_name == 'node_embedding':
+            w.prep_fc_w, w.prep_fc_b = p(self.prep.fc.weight), p(self.prep.fc.bias)
+        if self._prep_name == 'linear':
+            w.prep_fc_w, w.prep_out_dim = p(self.prep.fc.weight), self.prep.output_dim
+        return w
+
+    # -- the reference's public surface ---------------------------------------------------------------
+    def forward(self, ids, feats, train=True):
+        """models.py:71-91.  `ids`: int64 tensor of seed ids (CUDA, or CPU -> copied); `feats`: the node feature
+        table (tensor / FeatureTable) or None.  Returns fp32 logits (B, n_classes) on the GPU."""
+        sampler = self.train_sampler if train else self.val_sampler
+        assert isinstance(sampler, SparseUniformNeighborSampler), \
+            'GSSupervised: the fused engine samples from the sparse adjacency; use forward_reference_order for the dense sampler'
+        fanout = [s['n_train_samples' if train else 'n_val_samples'] for s in self.layer_specs]
+        ids = torch.as_tensor(ids).to(device='cuda', dtype=torch.int64).contiguous().view(-1)
+        table = self._table(feats)
+        eng = self._engine(table, fanout, ids.shape[0])
+        w = self._weights()
+        check(lib().gsage_engine_set_weights(eng['h'], C.byref(w), ops.stream()))
+        rng = sampler.rng or self.rng or default_rng()
+        out = torch.empty((ids.shape[0], self.n_classes), dtype=torch.float32, device='cuda')
+        check(lib().gsage_engine_forward(eng['h'], sampler.graph._h, rng._h, ops.ptr(ids), ids.shape[0], ops.ptr(out), ops.stream()))
+        self._last = eng
+        return out
+
+    def forward_host(self, ids_host, feats, logits_host, train=True):
+        """End-to-end entry for host buffers (pinned numpy / torch CPU tensors): H2D ids, forward, D2H logits."""
+        sampler = self.train_sampler if train else self.val_sampler
+        fanout = [s['n_train_samples' if train else 'n_val_samples'] for s in self.layer_specs]
+        table = self._table(feats)
+        B = ids_host.shape[0]
+        eng = self._engine(table, fanout, B)
+        w = self._weights()
+        check(lib().gsage_engine_set_weights(eng['h'], C.byref(w), ops.stream()))
+        rng = sampler.rng or self.rng or default_rng()
+        check(lib().gsage_engine_forward_host(eng['h'], sampler.graph._h, rng._h, C.c_void_p(ids_host.data_ptr()), B,
+                                              C.c_void_p(logits_host.data_ptr()), ops.stream()))
+        self._last = eng
+        return logits_host
+
+    def peek(self, what):
+        """Device view of an intermediate of the last forward: 'ids0' 'ids1' 'ids2' 'layer1' 'layer2'."""
+        code = {'ids0': 0, 'ids1': 1, 'ids2': 2, 'layer1': 10, 'layer2': 11}[what]
+        ptr, rows, cols, ld, dtype = C.c_void_p(), C.c_int64(), C.c_int64(), C.c_int64(), C.c_int()
+        check(lib().gsage_engine_peek(self._last['h'], code, C.byref(ptr), C.byref(rows), C.byref(cols), C.byref(ld), C.byref(dtype)))
+        view = ops.device_view(ptr.value, rows.value * ld.value, dtype.value).clone().view(rows.value, ld.value)
+        return view[:, :cols.value] if cols.value > 1 else view.view(-1)
+
+    def forward_reference_order(self, ids, feats, train=True):
+        """The reference's own loop (models.py:71-91) over the narrow operator API: sample -> feats[ids] -> prep ->
+        aggregators on pre-gathered rows.  Slower (rows are materialised); exists for parity debugging."""
+        sample_fns = self.train_sample_fns if train else self.val_sample_fns
+        ids = torch.as_tensor(ids).to(device='cuda', dtype=torch.int64).contiguous().view(-1)
+        table = self._table(feats)
+        rows = lambda i: ops.gather_rows(table.view, i, out_dtype=torch.float32) if table is not None else None
+        all_feats = [self.prep(ids, rows(ids), layer_idx=0)]
+        for layer_idx, sampler_fn in enumerate(sample_fns):
+            ids = sampler_fn(ids=ids).contiguous().view(-1)
+            all_feats.append(self.prep(ids, rows(ids), layer_idx=layer_idx + 1))
+        for agg_layer in self.agg_layers.children():
+            all_feats = [agg_layer(all_feats[k], all_feats[k + 1]) for k in range(len(all_feats) - 1)]
+        assert len(all_feats) == 1, "len(all_feats) != 1"
+        out = ops.l2_normalize(all_feats[0])
+        return ops.linear([dict(a=out, w=self.fc.weight.data, bias=self.fc.bias.data)], out.shape[0])
+
+    def __del__(self):
+        try:
+            for eng in self._engines.values():
+                lib().gsage_engine_destroy(eng['h'])
+        except Exception:
+            pass

@@ -1,0 +1,284 @@
+"""
+The reference's plug-in operators, re-implemented over libgsage_b200 -- same class names, constructor
+arguments, call signatures, parameter names and registries as /root/reference/nn_modules.py, so that
+
+    from pytorch_graphsage_b200.operators import sampler_lookup, prep_lookup, aggregator_lookup
+
+is a drop-in for the three dicts train.py resolves its CLI strings through (train.py:95,99,100), and a
+reference `state_dict` loads into these modules unchanged.
+
+Two entry points per aggregator:
+  * `forward(x, neibs)`           -- the reference's narrow contract (rows already gathered): reduce + both
+                                     projections + concat + activation run in the library;
+  * `forward_ids(table, ids_self, ids_neib, S)` -- the wide contract: the gather is fused into the reduce
+                                     and projection kernels, neighbour rows are never materialised.
+These modules are inference/forward operators (no autograd graph is recorded through the library calls).
+"""
+
+import numpy as np
+import torch
+from torch import nn
+from torch.nn import functional as F
+
+from . import ops
+from .graph import GraphCSR
+from .rng import default_rng
+from ._lib import check, lib
+
+
+def _act_name(fn):
+    """Map the callables train.py passes (F.relu, `lambda x: x`) onto the library's activation enum."""
+    if fn is None:
+        return None
+    if fn in (F.relu, torch.relu):
+        return 'relu'
+    if fn in (torch.tanh, F.tanh):
+        return 'tanh'
+    if isinstance(fn, str):
+        return fn
+    probe = torch.tensor([-2.0, 0.5])
+    res = fn(probe)
+    if torch.equal(res, probe):
+        return None
+    if torch.equal(res, torch.relu(probe)):
+        return 'relu'
+    if torch.allclose(res, torch.tanh(probe)):
+        return 'tanh'
+    raise ValueError('gsage: unsupported activation %r (identity / relu / tanh)' % (fn,))
+
+
+def _cuda_ids(ids):
+    ids = torch.as_tensor(ids)
+    was_cuda = ids.is_cuda
+    ids = ids.to(device='cuda', dtype=torch.int64).contiguous().view(-1)
+    return ids, was_cuda
+
+
+# --
+# Samplers
+
+class UniformNeighborSampler(object):
+    """Dense 2-D edgelist sampler (nn_modules.py:19-49): `adj[ids][:, randperm(K)][:, :n_samples]`,
+    ONE permutation per call shared by all rows, drawn from torch's CPU generator like the reference."""
+
+    def __init__(self, adj):
+        self.adj = torch.as_tensor(adj).to(device='cuda', dtype=torch.int64).contiguous()
+
+    def __call__(self, ids, n_samples=-1):
+        ids, was_cuda = _cuda_ids(ids)
+        K = self.adj.size(1)
+        perm = torch.randperm(K).cuda()                      # CPU generator, as nn_modules.py:44
+        S = n_samples if n_samples >= 0 else max(0, K + n_samples)
+        S = min(S, K)
+        out = torch.empty((ids.shape[0], S), dtype=torch.int64, device='cuda')
+        check(lib().gsage_sample_dense(ops.ptr(self.adj), self.adj.size(0), K, ops.ptr(ids), ids.shape[0], ops.ptr(perm),
+                                       n_samples, ops.ptr(out), ops.stream()))
+        return out if was_cuda else out.cpu()
+
+
+class SparseUniformNeighborSampler(object):
+    """Sparse CSR sampler (nn_modules.py:52-101), bit-exact with the reference under the same seed.
+
+    mode='device' (default): draws come from the device-resident MT19937 stream (`rng`, default the global
+        one seeded by `set_seeds`) -- no host round trip.
+    mode='host': draws are made on the host with the very call the reference makes
+        (`np.random.choice(adj.shape[1], (n, S))` on the global numpy stream) and shipped to the kernel."""
+
+    def __init__(self, adj, rng=None, mode='device'):
+        if isinstance(adj, GraphCSR):
+            self.graph = adj
+        else:
+            self.graph = GraphCSR.from_scipy(adj)            # asserts sparse.issparse(adj), like :73
+        self.adj = adj
+        self.rng = rng
+        self.mode = mode
+
+    @property
+    def degrees(self):
+        return self.graph.degrees
+
+    def __call__(self, ids, n_samples=128):
+        assert n_samples > 0, 'SparseUniformNeighborSampler: n_samples must be set explicitly'
+        ids, was_cuda = _cuda_ids(ids)
+        n = ids.shape[0]
+        out = torch.empty((n * n_samples,), dtype=torch.int64, device='cuda')
+        if self.mode == 'host':
+            sel = np.random.choice(self.graph.shape[1], (n, n_samples))          # nn_modules.py:88, global stream
+            sel = torch.from_numpy(sel.astype(np.uint32).view(np.int32).reshape(-1)).cuda()
+            check(lib().gsage_sample_sparse(self.graph._h, ops.ptr(ids), n, n_samples, ops.ptr(sel), ops.ptr(out), ops.stream()))
+        else:
+            rng = self.rng or default_rng()
+            check(lib().gsage_sample_sparse_rng(self.graph._h, rng._h, ops.ptr(ids), n, n_samples, ops.ptr(out), ops.stream()))
+        return out if was_cuda else out.cpu()
+
+
+sampler_lookup = {
+    "uniform_neighbor_sampler": UniformNeighborSampler,
+    "sparse_uniform_neighbor_sampler": SparseUniformNeighborSampler,
+}
+
+
+# --
+# Preprocessers
+
+class IdentityPrep(nn.Module):
+    def __init__(self, input_dim, n_nodes=None):
+        super(IdentityPrep, self).__init__()
+        self.input_dim = input_dim
+
+    @property
+    def output_dim(self):
+        return self.input_dim
+
+    def forward(self, ids, feats, layer_idx=0):
+        return feats
+
+
+class NodeEmbeddingPrep(nn.Module):
+    """nn_modules.py:126-155: learned (n_nodes+1, 64) table + 64x64 affine; seeds (layer_idx == 0) all look up
+    the masked row `n_nodes`."""
+
+    def __init__(self, input_dim, n_nodes, embedding_dim=64):
+        super(NodeEmbeddingPrep, self).__init__()
+        self.n_nodes = n_nodes
+        self.input_dim = input_dim
+        self.embedding_dim = embedding_dim
+        self.embedding = nn.Embedding(num_embeddings=n_nodes + 1, embedding_dim=embedding_dim)
+        self.fc = nn.Linear(embedding_dim, embedding_dim)
+
+    @property
+    def output_dim(self):
+        return (self.input_dim + self.embedding_dim) if self.input_dim else self.embedding_dim
+
+    def forward(self, ids, feats, layer_idx=0):
+        ids, _ = _cuda_ids(ids)
+        look = ids if layer_idx > 0 else torch.full_like(ids, self.n_nodes)
+        n, dfe = ids.shape[0], (self.input_dim or 0)
+        out = torch.empty((n, dfe + self.embedding_dim), dtype=torch.float32, device='cuda')
+        ops.linear([dict(a=self.embedding.weight.data, ids=look, w=self.fc.weight.data, bias=self.fc.bias.data, col0=dfe)],
+                   n, out=out)
+        if self.input_dim:
+            out[:, :dfe] = feats
+        return out
+
+
+class LinearPrep(nn.Module):
+    def __init__(self, input_dim, n_nodes, output_dim=32):
+        super(LinearPrep, self).__init__()
+        self.fc = nn.Linear(input_dim, output_dim, bias=False)
+        self.output_dim = output_dim
+
+    def forward(self, ids, feats, layer_idx=0):
+        return ops.linear([dict(a=feats.contiguous(), w=self.fc.weight.data)], feats.shape[0])
+
+
+prep_lookup = {
+    "identity": IdentityPrep,
+    "node_embedding": NodeEmbeddingPrep,
+    "linear": LinearPrep,
+}
+
+
+# --
+# Aggregators
+
+_cat = lambda x: torch.cat(x, dim=1)
+
+
+class AggregatorMixin(object):
+    @property
+    def output_dim(self):
+        tmp = torch.zeros((1, self.output_dim_))
+        return self.combine_fn([tmp, tmp]).size(1)
+
+    def _combine(self, x, x_ids, agg, n):
+        """act([fc_x(x) | fc_neib(agg)]) -- one launch writing both halves of the concat buffer."""
+        if self.combine_fn is not _cat:
+            raise NotImplementedError('gsage: only the default concat combine_fn is fused')
+        return ops.linear([dict(a=x, ids=x_ids, w=self.fc_x.weight.data, col0=0),
+                           dict(a=agg, w=self.fc_neib.weight.data, col0=self.output_dim_)],
+                          n, act=_act_name(self.activation))
+
+    def forward(self, x, neibs):
+        x, neibs = x.contiguous(), neibs.contiguous()
+        return self._apply(x, None, neibs, None, x.size(0), neibs.size(0) // x.size(0))
+
+    def forward_ids(self, table, ids_self, ids_neib, S):
+        return self._apply(table, ids_self, table, ids_neib, ids_self.shape[0], S)
+
+
+class MeanAggregator(nn.Module, AggregatorMixin):
+    def __init__(self, input_dim, output_dim, activation, combine_fn=_cat):
+        super(MeanAggregator, self).__init__()
+        self.fc_x = nn.Linear(input_dim, output_dim, bias=False)
+        self.fc_neib = nn.Linear(input_dim, output_dim, bias=False)
+        self.output_dim_ = output_dim
+        self.activation = activation
+        self.combine_fn = combine_fn
+
+    def _apply(self, x, x_ids, nb, nb_ids, n, S):
+        agg = ops.gather_reduce(nb, nb_ids, n, S, 'mean', d=self.fc_neib.in_features, out_dtype=torch.float32)
+        return self._combine(x, x_ids, agg, n)
+
+
+class PoolAggregator(nn.Module, AggregatorMixin):
+    def __init__(self, input_dim, output_dim, pool_fn, activation, hidden_dim=512, combine_fn=_cat):
+        super(PoolAggregator, self).__init__()
+        self.mlp = nn.Sequential(*[nn.Linear(input_dim, hidden_dim, bias=True), nn.ReLU()])
+        self.fc_x = nn.Linear(input_dim, output_dim, bias=False)
+        self.fc_neib = nn.Linear(hidden_dim, output_dim, bias=False)
+        self.output_dim_ = output_dim
+        self.activation = activation
+        self.pool_fn = pool_fn                          # 'max' | 'mean' (the reference passes lambdas)
+        self.combine_fn = combine_fn
+
+    def _apply(self, x, x_ids, nb, nb_ids, n, S):
+        h = ops.linear([dict(a=nb, ids=nb_ids, w=self.mlp[0].weight.data, bias=self.mlp[0].bias.data)], n * S, act='relu')
+        agg = ops.gather_reduce(h, None, n, S, self.pool_fn)
+        return self._combine(x, x_ids, agg, n)
+
+
+class MaxPoolAggregator(PoolAggregator):
+    def __init__(self, input_dim, output_dim, activation, hidden_dim=512, combine_fn=_cat):
+        super(MaxPoolAggregator, self).__init__(input_dim=input_dim, output_dim=output_dim, pool_fn='max',
+                                                activation=activation, hidden_dim=hidden_dim, combine_fn=combine_fn)
+
+
+class MeanPoolAggregator(PoolAggregator):
+    def __init__(self, input_dim, output_dim, activation, hidden_dim=512, combine_fn=_cat):
+        super(MeanPoolAggregator, self).__init__(input_dim=input_dim, output_dim=output_dim, pool_fn='mean',
+                                                 activation=activation, hidden_dim=hidden_dim, combine_fn=combine_fn)
+
+
+class AttentionAggregator(nn.Module, AggregatorMixin):
+    def __init__(self, input_dim, output_dim, activation, hidden_dim=32, combine_fn=_cat):
+        super(AttentionAggregator, self).__init__()
+        self.att = nn.Sequential(*[
+            nn.Linear(input_dim, hidden_dim, bias=False),
+            nn.Tanh(),
+            nn.Linear(hidden_dim, hidden_dim, bias=False),
+        ])
+        self.fc_x = nn.Linear(input_dim, output_dim, bias=False)
+        self.fc_neib = nn.Linear(input_dim, output_dim, bias=False)
+        self.output_dim_ = output_dim
+        self.activation = activation
+        self.combine_fn = combine_fn
+
+    def _att(self, a, ids, n):
+        t = ops.linear([dict(a=a, ids=ids, w=self.att[0].weight.data)], n, act='tanh')
+        return ops.linear([dict(a=t, w=self.att[2].weight.data)], n)
+
+    def _apply(self, x, x_ids, nb, nb_ids, n, S):
+        assert S > 1, 'AttentionAggregator: S must be > 1'
+        w = ops.attention_weights(self._att(nb, nb_ids, n * S), self._att(x, x_ids, n), n, S)
+        agg = ops.gather_reduce(nb, nb_ids, n, S, 'sum', weights=w, d=self.fc_neib.in_features, out_dtype=torch.float32)
+        return self._combine(x, x_ids, agg, n)
+
+
+aggregator_lookup = {
+    "mean": MeanAggregator,
+    "max_pool": MaxPoolAggregator,
+    "mean_pool": MeanPoolAggregator,
+    "attention": AttentionAggregator,
+    # "lstm": out of scope (sequential RNN over an arbitrary neighbour order, not a reduction)
+}

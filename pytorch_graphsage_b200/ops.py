@@ -1,0 +1,160 @@
+"""
+Tensor-level wrappers over the C ABI (include/gsage_b200.h).  torch is plumbing only: it owns the device
+memory and the stream; every arithmetic step happens inside libgsage_b200.so.
+"""
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import F32, BF16, check, lib
+
+_bound_device = [None]
+
+
+def _bind_device(t=None):
+    """One process per GPU: point the library's CUDA runtime at torch's current device."""
+    if not torch.cuda.is_available():
+        raise _lib.GsageError('pytorch_graphsage_b200 needs a CUDA device (B200, sm_100a); there is no CPU path')
+    dev = t.device.index if (t is not None and t.is_cuda and t.device.index is not None) else torch.cuda.current_device()
+    if _bound_device[0] != dev:
+        check(lib().gsage_set_device(dev))
+        _bound_device[0] = dev
+    return dev
+
+
+def stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def dt(t):
+    if t.dtype == torch.float32:
+        return F32
+    if t.dtype == torch.bfloat16:
+        return BF16
+    raise TypeError('gsage: only float32 / bfloat16 tensors are supported, got %s' % t.dtype)
+
+
+def ptr(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _rows2d(t):
+    assert t.dim() == 2 and t.stride(1) == 1, 'gsage: expected a row-major 2-D tensor'
+    return t.stride(0) if t.shape[0] > 1 else max(t.stride(0), t.shape[1])
+
+
+def pad_table(t, dtype=None):
+    """(rows, d) -> device tensor whose rows start 16-byte aligned with zero padding (a view of width d is returned
+    together with the leading dimension).  Returns (storage (rows, ld), d)."""
+    t = torch.as_tensor(t)
+    dtype = dtype or (t.dtype if t.dtype in (torch.float32, torch.bfloat16) else torch.float32)
+    per = 16 // (2 if dtype == torch.bfloat16 else 4)
+    d = t.shape[1]
+    ld = (d + 2 * per - 1) // (2 * per) * (2 * per)            # 32-byte rows: whole DRAM sectors
+    out = torch.zeros((t.shape[0], ld), dtype=dtype, device='cuda')
+    out[:, :d] = t.to(device='cuda', dtype=dtype)
+    return out, d
+
+
+def aligned_rows(t):
+    """The library streams rows with 16-byte loads: rows must start 16-byte aligned and be zero-padded to a whole
+    chunk.  Tensors that already qualify pass through; anything else gets one padded copy."""
+    es = t.element_size()
+    per = 16 // es
+    if t.dim() == 2 and t.stride(1) == 1 and t.data_ptr() % 16 == 0 and (t.stride(0) * es) % 16 == 0 \
+            and (t.shape[1] % per == 0 or t.stride(0) >= (t.shape[1] + per - 1) // per * per):
+        return t
+    store, d = pad_table(t, t.dtype)
+    return store[:, :d]
+
+
+def _ids_arg(ids):
+    if ids is None:
+        return None
+    assert ids.is_cuda and ids.dtype == torch.int64 and ids.is_contiguous(), 'gsage: ids must be a contiguous CUDA int64 tensor'
+    return ptr(ids)
+
+
+def gather_reduce(table, ids, n_parents, S, reduce='mean', weights=None, d=None, out_dtype=None, out=None):
+    """out[p] = reduce_j w[p*S+j] * table[ids[p*S+j]]  (ids None: rows p*S+j of `table`)."""
+    _bind_device(table)
+    d = table.shape[1] if d is None else d
+    table = aligned_rows(table)
+    out_dtype = out_dtype or table.dtype
+    if out is None:
+        per = 16 // (2 if out_dtype == torch.bfloat16 else 4)
+        ld_out = (d + per - 1) // per * per
+        store = torch.zeros((n_parents, ld_out), dtype=out_dtype, device=table.device)
+        out = store[:, :d]
+    if weights is not None:
+        assert weights.is_cuda and weights.dtype == torch.float32 and weights.is_contiguous()
+    check(lib().gsage_gather_reduce(ptr(table), dt(table), _rows2d(table), table.shape[0], d, _ids_arg(ids), n_parents, S,
+                                    _lib.REDUCE[reduce], ptr(weights), ptr(out), dt(out), _rows2d(out), stream()))
+    return out
+
+
+def gather_rows(table, ids, d=None, out_dtype=None):
+    return gather_reduce(table, ids, ids.shape[0], 1, 'sum', d=d, out_dtype=out_dtype)
+
+
+def linear(segments, n, act=None, out=None, out_dtype=torch.float32, exact=True):
+    """segments: list of dicts(a=, w=, ids=None, bias=None, col0=0, d=None).  One launch, <= 2 column ranges."""
+    segs = (_lib.LinearSeg * len(segments))()
+    width = 0
+    for i, sgm in enumerate(segments):
+        a, w = sgm['a'], sgm['w']
+        _bind_device(a)
+        d = sgm.get('d') or w.shape[1]
+        assert w.is_cuda and w.dim() == 2 and w.stride(1) == 1
+        bias = sgm.get('bias')
+        segs[i] = _lib.LinearSeg(ptr(a), dt(a), _rows2d(a), _ids_arg(sgm.get('ids')), ptr(w), dt(w), _rows2d(w), d,
+                                 w.shape[0], ptr(bias), sgm.get('col0', 0))
+        width = max(width, sgm.get('col0', 0) + w.shape[0])
+    if out is None:
+        out = torch.empty((n, width), dtype=out_dtype, device=segments[0]['a'].device)
+    check(lib().gsage_linear(segs, len(segments), n, _lib.ACT[act], ptr(out), dt(out), _rows2d(out), 1 if exact else 0, stream()))
+    return out
+
+
+def attention_weights(na, xa, n_parents, S):
+    _bind_device(na)
+    w = torch.empty((n_parents * S,), dtype=torch.float32, device=na.device)
+    check(lib().gsage_attention_weights(ptr(na), ptr(xa), dt(na), _rows2d(na), na.shape[1], n_parents, S, ptr(w), stream()))
+    return w
+
+
+def l2_normalize(x):
+    _bind_device(x)
+    out = torch.empty(x.shape, dtype=torch.float32, device=x.device)
+    check(lib().gsage_l2_normalize(ptr(x), dt(x), _rows2d(x), x.shape[0], x.shape[1], ptr(out), _rows2d(out), stream()))
+    return out
+
+
+def device_info():
+    _bind_device()
+    name = C.create_string_buffer(128)
+    sms, cc1, cc2, mem = C.c_int(), C.c_int(), C.c_int(), C.c_int64()
+    check(lib().gsage_device_info(name, 128, C.byref(sms), C.byref(mem), C.byref(cc1), C.byref(cc2)))
+    return dict(name=name.value.decode(), sm_count=sms.value, hbm_bytes=mem.value, cc=(cc1.value, cc2.value))
+
+
+def u32_to_numpy(t):
+    """int32-typed device tensor holding uint32 bit patterns -> numpy uint32."""
+    return t.cpu().numpy().view(np.uint32)
+
+
+class _DevView(object):
+    def __init__(self, ptr_value, n, typestr):
+        self.__cuda_array_interface__ = dict(shape=(n,), typestr=typestr, data=(ptr_value, False), version=2, strides=None)
+
+
+def device_view(ptr_value, n, dtype_code):
+    """Zero-copy torch view of `n` elements of library-owned device memory (dtype_code: -1 int64, 0 f32, 1 bf16)."""
+    if dtype_code == -1:
+        return torch.as_tensor(_DevView(ptr_value, n, '<i8'), device='cuda')
+    if dtype_code == F32:
+        return torch.as_tensor(_DevView(ptr_value, n, '<f4'), device='cuda')
+    return torch.as_tensor(_DevView(ptr_value, n, '<i2'), device='cuda').view(torch.bfloat16)

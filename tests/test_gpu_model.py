@@ -1,0 +1,113 @@
+"""End-to-end parity of the engine (C ABI gsage_engine_forward) with GSSupervised.forward of the reference,
+on the golden fixtures the reference itself produced.  GPU only.
+
+Bars: sampled ids bit-exact (and the RNG stream position after the batch); fp32 activations/logits within
+rtol 1e-4 / atol 1e-5 of the reference's fp32 values (the reference itself sits ~1e-5 from fp64, see
+tests/test_oracle_golden.py); bf16 compute within rtol 3e-2 / atol 3e-2 of the fp32 reference."""
+import numpy as np
+import pytest
+import torch
+from torch.nn import functional as F
+
+from tests import util
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope='module')
+def g():
+    import pytorch_graphsage_b200 as g
+    return g
+
+
+def build_model(g, fix, agg, prep, with_feats, compute_dtype=torch.float32, **kw):
+    graph = g.GraphCSR.from_triplets(fix['trip'])
+    S1, S2 = [int(s) for s in fix['fanout']]
+    O1, O2 = [int(s) for s in fix['out_dims']]
+    d = fix['feats'].shape[1] if with_feats else None
+    model = g.GSSupervised(
+        input_dim=d, n_nodes=int(fix['n_nodes']), n_classes=fix['logits'].shape[1],
+        layer_specs=[dict(n_train_samples=S1, n_val_samples=S1, output_dim=O1, activation=F.relu),
+                     dict(n_train_samples=S2, n_val_samples=S2, output_dim=O2, activation=lambda x: x)],
+        aggregator_class=g.aggregator_lookup[agg], prep_class=g.prep_lookup[prep],
+        sampler_class=g.sampler_lookup['sparse_uniform_neighbor_sampler'], adj=graph, train_adj=graph,
+        compute_dtype=compute_dtype, **kw)
+    missing = model.load_state_dict(util.params_of(fix), strict=True)      # the reference's own state_dict
+    assert not missing.missing_keys and not missing.unexpected_keys
+    return model.cuda()
+
+
+@pytest.mark.parametrize('agg,prep,with_feats', util.MODEL_CASES)
+def test_engine_matches_reference_fp32(g, agg, prep, with_feats):
+    fix = util.load(util.case_name(agg, prep, with_feats))
+    model = build_model(g, fix, agg, prep, with_feats)
+    feats = torch.from_numpy(fix['feats']) if with_feats else None
+    g.set_seeds(int(fix['seed']))                                         # train.py:133
+    logits = model(torch.from_numpy(fix['ids0']), feats, train=True)
+    # sampled indices: bit-exact, and the stream ends where numpy's ended
+    assert np.array_equal(model.peek('ids1').cpu().numpy(), fix['ids1'])
+    assert np.array_equal(model.peek('ids2').cpu().numpy(), fix['ids2'])
+    st = g.default_rng().get_state()
+    assert np.array_equal(st[1], fix['key_after']) and st[2] == int(fix['pos_after'])
+    tol = dict(rtol=1e-4, atol=1e-5)
+    B = fix['ids0'].shape[0]
+    l1 = model.peek('layer1').float().cpu().numpy()
+    np.testing.assert_allclose(l1[:B], fix['l1_a'], **tol)
+    np.testing.assert_allclose(l1[B:], fix['l1_b'], **tol)
+    np.testing.assert_allclose(model.peek('layer2').cpu().numpy(), fix['l2'], **tol)
+    np.testing.assert_allclose(logits.cpu().numpy(), fix['logits'], **tol)
+
+
+@pytest.mark.parametrize('agg,prep,with_feats', util.MODEL_CASES)
+def test_narrow_operator_api_matches_reference(g, agg, prep, with_feats):
+    """The reference's own call order through sampler(ids) / prep(ids, feats) / agg(x, neibs)."""
+    fix = util.load(util.case_name(agg, prep, with_feats))
+    model = build_model(g, fix, agg, prep, with_feats)
+    feats = torch.from_numpy(fix['feats']) if with_feats else None
+    g.set_seeds(int(fix['seed']))
+    logits = model.forward_reference_order(torch.from_numpy(fix['ids0']), feats, train=True)
+    np.testing.assert_allclose(logits.cpu().numpy(), fix['logits'], rtol=1e-4, atol=1e-5)
+
+
+@pytest.mark.parametrize('agg,prep,with_feats', [('mean', 'identity', True), ('max_pool', 'identity', True),
+                                                 ('attention', 'identity', True), ('mean', 'node_embedding', False)])
+def test_engine_bf16_compute(g, agg, prep, with_feats):
+    fix = util.load(util.case_name(agg, prep, with_feats))
+    model = build_model(g, fix, agg, prep, with_feats, compute_dtype=torch.bfloat16)
+    feats = torch.from_numpy(fix['feats']) if with_feats else None
+    g.set_seeds(int(fix['seed']))
+    logits = model(torch.from_numpy(fix['ids0']), feats, train=True)
+    assert np.array_equal(model.peek('ids2').cpu().numpy(), fix['ids2'])       # sampling is dtype independent
+    np.testing.assert_allclose(logits.cpu().numpy(), fix['logits'], rtol=3e-2, atol=3e-2)
+
+
+def test_host_buffer_entry_point(g):
+    """gsage_engine_forward_host: pinned host ids in, pinned host logits out (the e2e path bench.py times)."""
+    fix = util.load('model_mean_identity')
+    model = build_model(g, fix, 'mean', 'identity', True)
+    ids = torch.from_numpy(fix['ids0']).pin_memory()
+    out = torch.empty(fix['logits'].shape, dtype=torch.float32).pin_memory()
+    g.set_seeds(int(fix['seed']))
+    model.forward_host(ids, torch.from_numpy(fix['feats']), out)
+    np.testing.assert_allclose(out.numpy(), fix['logits'], rtol=1e-4, atol=1e-5)
+
+
+def test_consecutive_batches_continue_the_stream(g):
+    """Two batches back to back == the reference's two consecutive forward calls (same global stream)."""
+    fix = util.load('model_mean_identity')
+    model = build_model(g, fix, 'mean', 'identity', True)
+    feats = torch.from_numpy(fix['feats'])
+    from oracle import layers, sampler as osampler
+    from oracle.mt19937 import MT19937Oracle
+    indptr, indices, data, shape = osampler.csr_from_triplets(*fix['trip'])
+    deg = osampler.row_degrees(indptr, data)
+    o = MT19937Oracle(int(fix['seed']))
+    g.set_seeds(int(fix['seed']))
+    params = util.params_of(fix)
+    for batch in (fix['ids0'], fix['ids0'][::-1].copy(), fix['ids0'][:5]):
+        ids1 = osampler.sparse_sample(indptr, indices, data, shape, deg, batch, 25, o.randint)
+        ids2 = osampler.sparse_sample(indptr, indices, data, shape, deg, ids1, 10, o.randint)
+        want = layers.forward_stack([torch.from_numpy(a) for a in (batch, ids1, ids2)], feats, params)
+        got = model(torch.from_numpy(batch), feats)
+        assert np.array_equal(model.peek('ids2').cpu().numpy(), ids2)
+        np.testing.assert_allclose(got.cpu().numpy(), want.numpy(), rtol=1e-4, atol=1e-5)

@@ -1,0 +1,125 @@
+"""Kernel-level parity of the C-ABI ops against plain torch fp32 / fp64 on the same inputs.  GPU only.
+
+Tolerances (stated, per op):
+  gather_reduce fp32 table        rtol 1e-5  atol 1e-6   (fp32 sums of <= 40 terms, different association)
+  gather_reduce bf16 table        exact inputs (bf16 -> fp32 is exact), fp32 accumulate: same as above vs the
+                                  upcast table; bf16 OUTPUT adds one rounding: rtol 8e-3 (2^-7)
+  linear fp32 (FFMA kernel)       rtol 1e-4  atol 1e-5 vs fp64 (k up to 1433 products)
+"""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope='module')
+def g():
+    import pytorch_graphsage_b200 as g
+    return g
+
+
+def _table(rows, d, dtype, seed=0):
+    gen = torch.Generator().manual_seed(seed)
+    t = torch.randn((rows, d), generator=gen)
+    t[0] = 0
+    if dtype == torch.bfloat16:
+        t = t.to(torch.bfloat16).float()          # values exactly representable in bf16
+    return t
+
+
+@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize('d', [3, 20, 64, 100, 256, 602, 1433])
+@pytest.mark.parametrize('S', [1, 10, 25, 40])
+def test_gather_mean(g, dtype, d, S):
+    rows, n = 977, 301
+    host = _table(rows, d, dtype)
+    store, _ = g.ops.pad_table(host, dtype)
+    table = store[:, :d]
+    ids = torch.randint(0, rows, (n * S,), generator=torch.Generator().manual_seed(d * S))
+    want = host[ids].double().view(n, S, d).mean(dim=1)
+    got = g.ops.gather_reduce(table, ids.cuda(), n, S, 'mean', out_dtype=torch.float32)
+    np.testing.assert_allclose(got.cpu().numpy(), want.numpy(), rtol=1e-5, atol=1e-6)
+    if dtype == torch.bfloat16:
+        got16 = g.ops.gather_reduce(table, ids.cuda(), n, S, 'mean', out_dtype=torch.bfloat16)
+        np.testing.assert_allclose(got16.float().cpu().numpy(), want.numpy(), rtol=8e-3, atol=1e-3)
+
+
+@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize('d', [32, 512])
+def test_contiguous_reduce_max_and_mean(g, dtype, d):
+    """ids=None: the `neibs.view(N, S, d)` case (pool aggregators reduce the MLP output)."""
+    n, S = 130, 10
+    host = _table(n * S, d, dtype, seed=5)
+    h = g.ops.pad_table(host, dtype)[0][:, :d]
+    got_max = g.ops.gather_reduce(h, None, n, S, 'max', out_dtype=torch.float32)
+    got_mean = g.ops.gather_reduce(h, None, n, S, 'mean', out_dtype=torch.float32)
+    assert torch.equal(got_max.cpu(), host.view(n, S, d).max(dim=1)[0])          # max is exact
+    np.testing.assert_allclose(got_mean.cpu().numpy(), host.double().view(n, S, d).mean(dim=1).numpy(), rtol=1e-5, atol=1e-6)
+
+
+def test_weighted_sum(g):
+    rows, n, S, d = 500, 77, 25, 48
+    host = _table(rows, d, torch.float32, seed=9)
+    ids = torch.randint(0, rows, (n * S,))
+    w = torch.softmax(torch.randn(n, S), dim=1)
+    want = (host[ids].double().view(n, S, d) * w.double().unsqueeze(-1)).sum(dim=1)
+    got = g.ops.gather_reduce(g.ops.pad_table(host)[0][:, :d], ids.cuda(), n, S, 'sum', weights=w.view(-1).cuda().contiguous())
+    np.testing.assert_allclose(got.cpu().numpy(), want.numpy(), rtol=1e-5, atol=1e-6)
+
+
+def test_gather_rows_and_unaligned_input(g):
+    host = _table(300, 602, torch.float32, seed=2)              # 2408-byte rows: not 16-byte aligned -> padded copy
+    ids = torch.randint(0, 300, (1000,))
+    got = g.ops.gather_rows(host.cuda(), ids.cuda())
+    assert torch.equal(got.cpu(), host[ids])
+
+
+def test_out_of_range_ids_read_as_zero_rows(g):
+    host = _table(10, 8, torch.float32)
+    got = g.ops.gather_reduce(g.ops.pad_table(host)[0][:, :8], torch.tensor([1, 99, 2, -5]).cuda(), 2, 2, 'sum')
+    assert torch.equal(got.cpu(), torch.stack([host[1], host[2]]))
+
+
+@pytest.mark.parametrize('a_dtype', [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize('n,d,O', [(1, 7, 5), (64, 64, 128), (301, 602, 128), (130, 1433, 16), (1000, 256, 41), (77, 512, 130)])
+def test_linear(g, a_dtype, n, d, O):
+    gen = torch.Generator().manual_seed(n + d + O)
+    a = _table(n + 40, d, a_dtype, seed=n)
+    w = torch.randn((O, d), generator=gen) / d ** 0.5
+    b = torch.randn((O,), generator=gen)
+    ids = torch.randint(0, n + 40, (n,), generator=gen)
+    a_dev = g.ops.pad_table(a, a_dtype)[0][:, :d]
+    for act, fn in ((None, lambda t: t), ('relu', torch.relu), ('tanh', torch.tanh)):
+        want = fn(a[ids].double() @ w.double().t() + b.double())
+        got = g.ops.linear([dict(a=a_dev, ids=ids.cuda(), w=w.cuda(), bias=b.cuda())], n, act=act)
+        np.testing.assert_allclose(got.cpu().numpy(), want.numpy(), rtol=1e-4, atol=1e-5)
+    want = a[:n].double() @ w.double().t()                       # no gather, no bias
+    got = g.ops.linear([dict(a=a_dev, w=w.cuda())], n)
+    np.testing.assert_allclose(got.cpu().numpy(), want.numpy(), rtol=1e-4, atol=1e-5)
+
+
+def test_linear_two_segments_concat(g):
+    """[fc_x(x) | fc_neib(m)] in one launch (nn_modules.py:200)."""
+    n, d, O = 257, 100, 24
+    x, m = torch.randn(n, d), torch.randn(n, d)
+    wx, wn = torch.randn(O, d) / 10, torch.randn(O, d) / 10
+    want = torch.relu(torch.cat([x.double() @ wx.double().t(), m.double() @ wn.double().t()], dim=1))
+    got = g.ops.linear([dict(a=g.ops.aligned_rows(x.cuda()), w=wx.cuda(), col0=0),
+                        dict(a=g.ops.aligned_rows(m.cuda()), w=wn.cuda(), col0=O)], n, act='relu')
+    assert got.shape == (n, 2 * O)
+    np.testing.assert_allclose(got.cpu().numpy(), want.numpy(), rtol=1e-4, atol=1e-5)
+
+
+def test_attention_weights_and_l2norm(g):
+    n, S, H = 99, 10, 32
+    na, xa = torch.randn(n * S, H), torch.randn(n, H)
+    want = torch.softmax(torch.einsum('nsh,nh->ns', na.double().view(n, S, H), xa.double()), dim=1)
+    got = g.ops.attention_weights(na.cuda(), xa.cuda(), n, S)
+    np.testing.assert_allclose(got.view(n, S).cpu().numpy(), want.numpy(), rtol=1e-5, atol=1e-7)
+    z = torch.randn(50, 256)
+    z[3] = 0                                                        # F.normalize eps path
+    got = g.ops.l2_normalize(z.cuda())
+    np.testing.assert_allclose(got.cpu().numpy(), torch.nn.functional.normalize(z.double(), dim=1).numpy(), rtol=1e-5, atol=1e-7)
+    with pytest.raises(ValueError):
+        g.ops.attention_weights(na.cuda(), xa.cuda(), n * S, 1)     # S == 1 is out of contract
