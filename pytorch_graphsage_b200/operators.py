@@ -199,15 +199,19 @@ class AggregatorMixin(object):
                            dict(a=agg, w=self.fc_neib.weight.data, col0=self.output_dim_)],
                           n, act=_act_name(self.activation))
 
-    def forward(self, x, neibs):
+    def _forward_rows(self, x, neibs):
         x, neibs = x.contiguous(), neibs.contiguous()
-        return self._apply(x, None, neibs, None, x.size(0), neibs.size(0) // x.size(0))
+        return self._run(x, None, neibs, None, x.size(0), neibs.size(0) // x.size(0))
 
     def forward_ids(self, table, ids_self, ids_neib, S):
-        return self._apply(table, ids_self, table, ids_neib, ids_self.shape[0], S)
+        return self._run(table, ids_self, table, ids_neib, ids_self.shape[0], S)
 
 
 class MeanAggregator(nn.Module, AggregatorMixin):
+    def forward(self, x, neibs):
+        """x (N, d), neibs (N*S, d) row-major grouped by parent -> (N, 2*output_dim)."""
+        return self._forward_rows(x, neibs)
+
     def __init__(self, input_dim, output_dim, activation, combine_fn=_cat):
         super(MeanAggregator, self).__init__()
         self.fc_x = nn.Linear(input_dim, output_dim, bias=False)
@@ -216,12 +220,16 @@ class MeanAggregator(nn.Module, AggregatorMixin):
         self.activation = activation
         self.combine_fn = combine_fn
 
-    def _apply(self, x, x_ids, nb, nb_ids, n, S):
+    def _run(self, x, x_ids, nb, nb_ids, n, S):
         agg = ops.gather_reduce(nb, nb_ids, n, S, 'mean', d=self.fc_neib.in_features, out_dtype=torch.float32)
         return self._combine(x, x_ids, agg, n)
 
 
 class PoolAggregator(nn.Module, AggregatorMixin):
+    def forward(self, x, neibs):
+        """x (N, d), neibs (N*S, d) row-major grouped by parent -> (N, 2*output_dim)."""
+        return self._forward_rows(x, neibs)
+
     def __init__(self, input_dim, output_dim, pool_fn, activation, hidden_dim=512, combine_fn=_cat):
         super(PoolAggregator, self).__init__()
         self.mlp = nn.Sequential(*[nn.Linear(input_dim, hidden_dim, bias=True), nn.ReLU()])
@@ -232,7 +240,7 @@ class PoolAggregator(nn.Module, AggregatorMixin):
         self.pool_fn = pool_fn                          # 'max' | 'mean' (the reference passes lambdas)
         self.combine_fn = combine_fn
 
-    def _apply(self, x, x_ids, nb, nb_ids, n, S):
+    def _run(self, x, x_ids, nb, nb_ids, n, S):
         h = ops.linear([dict(a=nb, ids=nb_ids, w=self.mlp[0].weight.data, bias=self.mlp[0].bias.data)], n * S, act='relu')
         agg = ops.gather_reduce(h, None, n, S, self.pool_fn)
         return self._combine(x, x_ids, agg, n)
@@ -251,6 +259,10 @@ class MeanPoolAggregator(PoolAggregator):
 
 
 class AttentionAggregator(nn.Module, AggregatorMixin):
+    def forward(self, x, neibs):
+        """x (N, d), neibs (N*S, d) row-major grouped by parent -> (N, 2*output_dim)."""
+        return self._forward_rows(x, neibs)
+
     def __init__(self, input_dim, output_dim, activation, hidden_dim=32, combine_fn=_cat):
         super(AttentionAggregator, self).__init__()
         self.att = nn.Sequential(*[
@@ -268,7 +280,7 @@ class AttentionAggregator(nn.Module, AggregatorMixin):
         t = ops.linear([dict(a=a, ids=ids, w=self.att[0].weight.data)], n, act='tanh')
         return ops.linear([dict(a=t, w=self.att[2].weight.data)], n)
 
-    def _apply(self, x, x_ids, nb, nb_ids, n, S):
+    def _run(self, x, x_ids, nb, nb_ids, n, S):
         assert S > 1, 'AttentionAggregator: S must be > 1'
         w = ops.attention_weights(self._att(nb, nb_ids, n * S), self._att(x, x_ids, n), n, S)
         agg = ops.gather_reduce(nb, nb_ids, n, S, 'sum', weights=w, d=self.fc_neib.in_features, out_dtype=torch.float32)
