@@ -1,0 +1,380 @@
+#!/usr/bin/env python
+"""
+bench.py -- the headline measurement (BASELINE.json metric: sampled+aggregated nodes/sec; gather HBM GB/s vs peak).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload reddit] [--batch B]
+
+A "step" is one pass of the hot path (sample both hops -> gather -> aggregate -> project, two layers, normalise,
+classifier) over one batch of B seed nodes per GPU on a synthetic problem of the named shape.  Default workload =
+BASELINE.json configs[1]: Reddit-shape (232,965 nodes / 11 M edges / d=602), mean aggregator, bf16 table,
+fanout [25,10], on 1 x B200.
+
+Ours (`--impl ours`):
+  value   sampled neighbour rows consumed by aggregation per second (= seeds/s x 275), whole job over N GPUs,
+          ids already resident in HBM, device-timed (CUDA events, max over ranks)
+  e2e     same metric through the host-buffer entry (pinned host ids in, pinned host logits out every step)
+  roofline  the fused gather+aggregate kernel: algorithmic bytes / live CUDA-event time vs measured HBM peak
+  cpu_baseline  the oracle port of the reference's CPU path, bounded sample, timed here on the host cores
+Reference arm (`--impl reference`): the oracle port of the reference's CPU implementation (the reference is
+Python-2-era and cannot travel to the GPU box; oracle/ restates it and is pinned against it by the golden
+fixtures) timed on the host cores with all torch threads.
+"""
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+RANK = int(os.environ.get('RANK', '0'))
+LOCAL_RANK = int(os.environ.get('LOCAL_RANK', '0'))
+WORLD = int(os.environ.get('WORLD_SIZE', '1'))
+
+FANOUT = (25, 10)
+OUT_DIMS = (128, 128)
+ROWS_PER_SEED = FANOUT[0] + FANOUT[0] * FANOUT[1]          # 275 sampled neighbour rows per seed
+METRIC = 'sampled+aggregated nodes/sec'
+UNIT = 'nodes/s'
+
+WORKLOADS = {
+    # name -> (synth shape, aggregator, prep, table dtype, with_feats)
+    'reddit': ('reddit', 'mean', 'identity', 'bf16', True),          # BASELINE.json configs[1]  (default)
+    'reddit-fp32': ('reddit', 'mean', 'identity', 'f32', True),
+    'pokec-mean': ('pokec', 'mean', 'node_embedding', 'f32', False),  # north-star 60 % target shape
+    'pokec-maxpool': ('pokec', 'max_pool', 'node_embedding', 'f32', False),   # configs[2]
+    'plaw2m-attention': ('plaw2m', 'attention', 'identity', 'bf16', True),   # configs[3]
+    'big10m': ('big10m', 'mean', 'identity', 'bf16', True),                   # configs[4]
+    'tiny': ('tiny', 'mean', 'identity', 'f32', True),
+}
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=30)
+    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--workload', default='reddit', choices=sorted(WORKLOADS))
+    ap.add_argument('--batch', type=int, default=8192, help='seed nodes per step per GPU')
+    ap.add_argument('--cpu-batch', type=int, default=512, help='seed nodes per CPU-baseline step (train.py:48)')
+    ap.add_argument('--cpu-seconds', type=float, default=12.0, help='budget of the cpu_baseline leg')
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--scale', type=float, default=1.0, help='shrink the graph (debug only; reported in config)')
+    return ap.parse_args()
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(path):
+        try:
+            p = json.load(open(path))
+            return float(p['hbm_gbs']), 'measured (MEASURED_PEAKS.json hbm_gbs)'
+        except Exception:
+            pass
+    return 6650.0, 'fallback (B200_PROFILING.md 6.65 TB/s)'
+
+
+class ClockSampler(object):
+    """nvidia-smi clocks + throttle reasons DURING the timed region (B200_PROFILING.md clocks line)."""
+    Q = 'index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,' \
+        'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
+
+    def __init__(self, index):
+        self.index, self.proc, self.path = index, None, '/tmp/gsage_clocks_%d_%d.csv' % (os.getpid(), index)
+
+    def start(self):
+        try:
+            self.fh = open(self.path, 'w')
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q, '--format=csv,noheader,nounits',
+                                          '-lms', '100'], stdout=self.fh, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        self.fh.close()
+        sm, mx, reasons, power = [], [], set(), []
+        for line in open(self.path):
+            f = [x.strip() for x in line.split(',')]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); power.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, val in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), f[5:9]):
+                if val.lower().startswith('active'):
+                    reasons.add(name)
+        os.remove(self.path)
+        sm.sort()
+        return {'sm_mhz': (sm[len(sm) // 2] if sm else None), 'sm_max_mhz': (max(mx) if mx else None),
+                'power_w_max': (max(power) if power else None), 'samples': len(sm), 'reasons': sorted(reasons)}
+
+
+# ---------------------------------------------------------------------------------------------------
+def make_problem(args):
+    from pytorch_graphsage_b200 import synth
+    shape, agg, prep, dtype, with_feats = WORKLOADS[args.workload]
+    t0 = time.time()
+    prob = synth.make_problem(shape, seed=0, with_feats=with_feats, scale=args.scale)
+    prob.update(aggregator=agg, prep=prep, table_dtype=dtype, build_s=time.time() - t0)
+    return prob
+
+
+def layer_specs():
+    from torch.nn import functional as F
+    return [dict(n_train_samples=FANOUT[0], n_val_samples=FANOUT[0], output_dim=OUT_DIMS[0], activation=F.relu),
+            dict(n_train_samples=FANOUT[1], n_val_samples=FANOUT[1], output_dim=OUT_DIMS[1], activation=lambda x: x)]
+
+
+def workload_config(args, prob):
+    s = prob['adj']
+    return {'workload': '%s: %d nodes / %d edges / d=%s, %s aggregator, %s prep, fanout [25,10], out 128,128, %s table' %
+                        (args.workload, s['n_nodes'], s['nnz'], prob['feats_dim'] or 64, prob['aggregator'], prob['prep'],
+                         prob['table_dtype']),
+            'batch_seeds_per_gpu': args.batch, 'rows_per_seed': ROWS_PER_SEED, 'graph_scale': args.scale,
+            'sampler': 'sparse_uniform_neighbor_sampler (device MT19937, bit-exact numpy legacy stream)',
+            'l2_policy': 'inputs larger than L2 (table %.0f MB + per-step gather footprint); no flush' %
+                         ((s['n_nodes'] + 1) * (prob['feats_dim'] or 64) * (2 if prob['table_dtype'] == 'bf16' else 4) / 1e6),
+            'parallelism': 'seed-sharded dp%d, graph+table replicated, no data-path collective' % max(1, args.gpus)}
+
+
+# ---------------------------------------------------------------------------------------------------
+def cpu_reference_throughput(prob, batch, steps, warmup, seconds=None):
+    """The reference's CPU path (oracle port: numpy legacy RNG + CSR lookup + torch-CPU fp32 layers) on `batch`
+    seeds per step.  Returns (rows_per_s, ms_per_step, steps_done).  bf16 workloads use the bf16-rounded table
+    upcast to fp32 (the reference has no bf16 path)."""
+    import numpy as np
+    import torch
+    from oracle import layers, sampler as osampler
+    from pytorch_graphsage_b200 import synth
+    adj = prob['adj']
+    indptr, data, shape = adj['indptr'], adj['data'], adj['shape']
+    indices = np.arange(data.shape[0], dtype=np.int64) - np.repeat(indptr[:-1], np.diff(indptr))
+    deg = np.diff(indptr)
+    feats = None
+    if prob['feats'] is not None:
+        feats = torch.from_numpy(prob['feats'])
+        if prob['table_dtype'] == 'bf16':
+            feats = feats.to(torch.bfloat16).float()
+    params = reference_params(prob)
+    rs = np.random.RandomState(123 ** 2)
+    draw = lambda hi, n: rs.choice(hi, n)
+    done, t_start, times = 0, time.perf_counter(), []
+    with torch.no_grad():
+        while True:
+            ids0 = synth.seed_batch(prob, batch, seed=1000 + done)
+            t0 = time.perf_counter()
+            ids1 = osampler.sparse_sample(indptr, indices, data, shape, deg, ids0, FANOUT[0], draw)
+            ids2 = osampler.sparse_sample(indptr, indices, data, shape, deg, ids1, FANOUT[1], draw)
+            layers.forward_stack([torch.from_numpy(a) for a in (ids0, ids1, ids2)], feats, params,
+                                 aggregator=prob['aggregator'], prep=prob['prep'], n_nodes=prob['n_nodes'])
+            dt = time.perf_counter() - t0
+            done += 1
+            if done > warmup:
+                times.append(dt)
+            if seconds is not None:
+                if len(times) >= 3 and time.perf_counter() - t_start > seconds:
+                    break
+            elif len(times) >= steps:
+                break
+    ms = 1e3 * sum(times) / len(times)
+    return batch * ROWS_PER_SEED / (ms / 1e3), ms, len(times)
+
+
+def reference_params(prob, seed=123):
+    """Random-init weights of the reference architecture (torch.manual_seed(123), train.py:81), keyed like its state_dict."""
+    import torch
+    from torch import nn
+    torch.manual_seed(seed)
+    d = prob['feats_dim']
+    params = {}
+    if prob['prep'] == 'node_embedding':
+        params['prep.embedding.weight'] = nn.Embedding(prob['n_nodes'] + 1, 64).weight.data
+        fc = nn.Linear(64, 64)
+        params['prep.fc.weight'], params['prep.fc.bias'] = fc.weight.data, fc.bias.data
+        d = (d or 0) + 64
+    elif prob['prep'] == 'linear':
+        params['prep.fc.weight'] = nn.Linear(d, 32, bias=False).weight.data
+        d = 32
+    for k, O in enumerate(OUT_DIMS):
+        pre = 'agg_layers.%d.' % k
+        hid = d
+        if prob['aggregator'] in ('max_pool', 'mean_pool'):
+            mlp = nn.Linear(d, 512)
+            params[pre + 'mlp.0.weight'], params[pre + 'mlp.0.bias'] = mlp.weight.data, mlp.bias.data
+            hid = 512
+        if prob['aggregator'] == 'attention':
+            params[pre + 'att.0.weight'] = nn.Linear(d, 32, bias=False).weight.data
+            params[pre + 'att.2.weight'] = nn.Linear(32, 32, bias=False).weight.data
+        params[pre + 'fc_x.weight'] = nn.Linear(d, O, bias=False).weight.data
+        params[pre + 'fc_neib.weight'] = nn.Linear(hid, O, bias=False).weight.data
+        d = 2 * O
+    fc = nn.Linear(d, prob['n_classes'])
+    params['fc.weight'], params['fc.bias'] = fc.weight.data, fc.bias.data
+    return params
+
+
+def run_reference(args):
+    """`--impl reference`: rank 0 alone times the CPU path; other ranks exit 0 without work."""
+    if RANK != 0:
+        return
+    import torch
+    prob = make_problem(args)
+    value, ms, steps = cpu_reference_throughput(prob, args.cpu_batch, args.steps, args.warmup)
+    cores = torch.get_num_threads()
+    line = {'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': steps,
+            'warmup': args.warmup, 'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+            'dtype': 'f32', 'data': 'synthetic', 'config': dict(workload_config(args, prob), batch_seeds_per_step=args.cpu_batch),
+            'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': cores, 'kind': 'port',
+                             'sample': '%d steps x %d seeds (oracle port of nn_modules.py/models.py CPU path, torch %d threads of %d cpus)' %
+                                       (steps, args.cpu_batch, cores, os.cpu_count())},
+            'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+            'seeds_per_s': value / ROWS_PER_SEED, 'gpu_launches': 0}
+    print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------------------------------
+def run_ours(args):
+    if WORLD > 1:
+        os.environ.setdefault('CUDA_VISIBLE_DEVICES', str(LOCAL_RANK))        # one process per GPU, device 0 in-process
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import pytorch_graphsage_b200 as g
+    from pytorch_graphsage_b200 import synth
+
+    torch.cuda.set_device(0 if WORLD > 1 else LOCAL_RANK)
+    if WORLD > 1:
+        dist.init_process_group('nccl', device_id=torch.device('cuda', 0))
+
+    prob = make_problem(args)
+    B = args.batch
+    dtype = torch.bfloat16 if prob['table_dtype'] == 'bf16' else torch.float32
+    graph = g.GraphCSR.from_synth(prob['adj'])
+    table = g.FeatureTable(prob['feats'], dtype) if prob['feats'] is not None else None
+    model = g.GSSupervised(
+        input_dim=prob['feats_dim'], n_nodes=prob['n_nodes'], n_classes=prob['n_classes'], layer_specs=layer_specs(),
+        aggregator_class=g.aggregator_lookup[prob['aggregator']], prep_class=g.prep_lookup[prob['prep']],
+        sampler_class=g.sampler_lookup['sparse_uniform_neighbor_sampler'], adj=graph, train_adj=graph,
+        compute_dtype=dtype, max_batch=B)
+    model.load_state_dict(reference_params(prob))
+    model = model.cuda()
+    g.set_seeds(123 ** 2 + RANK)                                              # train.py:133 (+ rank: disjoint streams)
+
+    n_batches = 8                                                               # rotate seed batches: no step reuses hot rows
+    dev_ids = [torch.from_numpy(synth.seed_batch(prob, B, seed=17 * RANK + i)).cuda() for i in range(n_batches)]
+    host_ids = [torch.from_numpy(synth.seed_batch(prob, B, seed=17 * RANK + i)).pin_memory() for i in range(n_batches)]
+    host_out = torch.empty((B, prob['n_classes']), dtype=torch.float32).pin_memory()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if WORLD > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if WORLD == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device='cuda')
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- device-resident timing -----------------------------------------------------------------------------
+    for i in range(max(3, args.warmup)):
+        model(dev_ids[i % n_batches], table)
+    g.default_rng().check()
+    graph.check()
+    model.profile(True)
+    clocks = ClockSampler(LOCAL_RANK)
+    barrier()
+    clocks.start()
+    launches0 = g.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for i in range(args.steps):
+        model(dev_ids[i % n_batches], table)
+    ev1.record()
+    barrier()
+    launches = g.launch_count() - launches0
+    clk = clocks.stop()
+    ms_total = max_over_ranks(ev0.elapsed_time(ev1))
+    prof = model.profile_read()
+    model.profile(False)
+    g.default_rng().check()
+    ms_step = ms_total / args.steps
+    value = WORLD * B * ROWS_PER_SEED / (ms_step / 1e3)
+
+    # ---- end to end through the host-buffer entry -----------------------------------------------------------------
+    for i in range(3):
+        model.forward_host(host_ids[i % n_batches], table, host_out)
+    barrier()
+    t0 = time.perf_counter()
+    ev0.record()
+    for i in range(args.steps):
+        model.forward_host(host_ids[i % n_batches], table, host_out)           # synchronises every step (D2H result)
+    ev1.record()
+    barrier()
+    e2e_ms = max_over_ranks(max(ev0.elapsed_time(ev1), 0.0)) / args.steps
+    e2e_wall_ms = max_over_ranks((time.perf_counter() - t0) * 1e3) / args.steps
+    e2e_ms = max(e2e_ms, e2e_wall_ms)
+    e2e_value = WORLD * B * ROWS_PER_SEED / (e2e_ms / 1e3)
+
+    if RANK != 0:
+        if WORLD > 1:
+            dist.destroy_process_group()
+        return
+
+    peak, peak_src = measured_peaks()
+    red_ms, red_n, red_bytes = prof['reduce']
+    prj_ms, prj_n, prj_flops = prof['project']
+    achieved = (red_bytes / 1e9) / (red_ms / 1e3) if red_ms > 0 else None
+    traffic = None
+    tpath = os.path.join(ROOT, 'profiles', 'traffic.json')
+    if os.path.exists(tpath):
+        traffic = json.load(open(tpath)).get('%s:%d' % (args.workload, B))
+    line = {
+        'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': WORLD, 'steps': args.steps, 'warmup': max(3, args.warmup),
+        'ms_per_step': ms_step, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+        'dtype': 'bf16' if dtype == torch.bfloat16 else 'f32', 'data': 'synthetic',
+        'config': workload_config(args, prob), 'clocks': clk,
+        'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': 8 * B, 'd2h_bytes_per_step': 4 * B * prob['n_classes'],
+                'ms_per_step': e2e_ms},
+        'gpu_launches': int(launches) * WORLD,
+        'seeds_per_s': value / ROWS_PER_SEED,
+        'roofline': {'bound': 'hbm', 'kernel': 'gather_reduce_kernel (fused gather+mean, both layer-1 applications + layer 2)',
+                     'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': (achieved / peak if achieved else None),
+                     'traffic': traffic, 'peak_source': peak_src, 'launches': int(red_n),
+                     'algorithmic_bytes_per_launch_avg': (red_bytes / red_n if red_n else None),
+                     'avg_launch_ms': (red_ms / red_n if red_n else None)},
+        'breakdown_ms_per_step': {'forward': prof['forward'][0] / args.steps, 'sample': prof['sample'][0] / args.steps,
+                                  'gather_reduce': red_ms / args.steps, 'project': prj_ms / args.steps,
+                                  'project_tflops': (prj_flops / 1e12) / (prj_ms / 1e3) if prj_ms > 0 else None},
+    }
+    if not args.no_cpu_baseline:
+        v, ms, steps = cpu_reference_throughput(prob, args.cpu_batch, None, 2, seconds=args.cpu_seconds)
+        line['cpu_baseline'] = {'value': v, 'unit': UNIT, 'cores': torch.get_num_threads(), 'kind': 'port',
+                                'sample': '%d steps x %d seeds in %.0f s budget (oracle port, torch %d threads of %d cpus)' %
+                                          (steps, args.cpu_batch, args.cpu_seconds, torch.get_num_threads(), os.cpu_count()),
+                                'ms_per_step': ms}
+    print(json.dumps(line))
+    if WORLD > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    a = parse_args()
+    if a.impl == 'reference':
+        run_reference(a)
+    else:
+        run_ours(a)

@@ -218,6 +218,14 @@ int gsage_engine_peek(gsage_engine* e, int what, const void** ptr_dev, int64_t* 
                       int* dtype);
 int64_t gsage_engine_workspace_bytes(const gsage_engine* e);
 
+/* Live stopwatch (CUDA events on the launching stream) around kernel groups of the forward, for bench.py:
+ *   FORWARD  the whole gsage_engine_forward        SAMPLE   rng draws + sample kernels, both hops
+ *   REDUCE   the fused gather+aggregate launches   PROJECT  the concat-with-self projection launches
+ * `work_out`: algorithmic bytes (REDUCE) / flops (PROJECT) of the recorded launches.  Reading synchronises. */
+enum { GSAGE_PROF_FORWARD = 0, GSAGE_PROF_SAMPLE = 1, GSAGE_PROF_REDUCE = 2, GSAGE_PROF_PROJECT = 3, GSAGE_PROF_CATS = 4 };
+int gsage_engine_profile(gsage_engine* e, int enable);
+int gsage_engine_profile_read(gsage_engine* e, double* ms_out, int64_t* launches_out, double* work_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

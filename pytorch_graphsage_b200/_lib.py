@@ -83,6 +83,8 @@ _SIGNATURES = {
     'gsage_engine_forward_host': (C.c_int, [c_p, c_p, c_p, c_p, c_i64, c_p, c_p]),
     'gsage_engine_peek': (C.c_int, [c_p, C.c_int, C.POINTER(c_p), C.POINTER(c_i64), C.POINTER(c_i64), C.POINTER(c_i64), C.POINTER(C.c_int)]),
     'gsage_engine_workspace_bytes': (c_i64, [c_p]),
+    'gsage_engine_profile': (C.c_int, [c_p, C.c_int]),
+    'gsage_engine_profile_read': (C.c_int, [c_p, C.POINTER(C.c_double), C.POINTER(c_i64), C.POINTER(C.c_double), c_p]),
 }
 
 EXPORTS = sorted(_SIGNATURES)

@@ -44,7 +44,30 @@ __global__ void __launch_bounds__(256) fill_i64_kernel(int64_t* p, int64_t n, in
 
 using namespace gsage;
 
+// CUDA-event stopwatch around kernel groups of one forward (bench.py's live roofline / breakdown numbers)
+struct EngineProf {
+    bool on = false;
+    std::vector<cudaEvent_t> pool;
+    struct Rec { int cat; int a, b; };
+    std::vector<Rec> recs;
+    int used = 0;
+    double bytes[GSAGE_PROF_CATS] = {0, 0, 0, 0};
+    int begin(int cat, cudaStream_t s) {
+        if (!on) return -1;
+        if (used + 2 > (int)pool.size()) {
+            if (pool.size() >= 16384) return -1;
+            for (int i = 0; i < 64; ++i) { cudaEvent_t e; cudaEventCreate(&e); pool.push_back(e); }
+        }
+        recs.push_back(Rec{cat, used, used + 1});
+        cudaEventRecord(pool[used], s);
+        used += 2;
+        return (int)recs.size() - 1;
+    }
+    void end(int rec, cudaStream_t s) { if (rec >= 0) cudaEventRecord(pool[recs[rec].b], s); }
+};
+
 struct gsage_engine {
+    EngineProf prof;
     gsage_engine_config cfg;
     gsage_weights w;
     bool have_weights = false;
@@ -96,9 +119,17 @@ static int apply_aggregator(gsage_engine* e, int layer, const RowSrc& x, const R
     const int64_t ldm = pad_to(d, 16 / (int64_t)dtype_size(T) * 2);
     switch (e->cfg.aggregator) {
     case GSAGE_AGG_MEAN: {
+        const int p_red = e->prof.begin(GSAGE_PROF_REDUCE, s);
         GS_TRY(gather_reduce_launch(nb.base, nb.dtype, nb.ld, nb.table_rows, d, nb.ids, n, S, GSAGE_RED_MEAN, nullptr, e->M, T, ldm, s));
+        e->prof.end(p_red, s);
+        // algorithmic bytes of the fused gather+mean launch: S rows + S ids in, one row out
+        if (p_red >= 0) e->prof.bytes[GSAGE_PROF_REDUCE] += (double)n * ((double)S * d * dtype_size(nb.dtype) + (nb.ids ? 8.0 * S : 0.0) + (double)d * dtype_size(T));
         RowSrc m{e->M, T, ldm, n, nullptr, d};
-        return combine_call(x, L.fc_x, m, L.fc_neib, O, n, act, out, out_dtype, ld_out, exact, s);
+        const int p_prj = e->prof.begin(GSAGE_PROF_PROJECT, s);
+        const int st = combine_call(x, L.fc_x, m, L.fc_neib, O, n, act, out, out_dtype, ld_out, exact, s);
+        e->prof.end(p_prj, s);
+        if (p_prj >= 0) e->prof.bytes[GSAGE_PROF_PROJECT] += 4.0 * (double)n * d * O;      // flops, not bytes
+        return st;
     }
     case GSAGE_AGG_MAX_POOL:
     case GSAGE_AGG_MEAN_POOL: {
@@ -205,11 +236,37 @@ int gsage_engine_create(const gsage_engine_config* cfg, gsage_engine** out) {
 
 void gsage_engine_destroy(gsage_engine* e) {
     if (!e) return;
+    for (cudaEvent_t ev : e->prof.pool) cudaEventDestroy(ev);
     cudaFree(e->ws);
     delete e;
 }
 
 int64_t gsage_engine_workspace_bytes(const gsage_engine* e) { return e ? e->ws_bytes : 0; }
+
+int gsage_engine_profile(gsage_engine* e, int enable) {
+    GS_CHECK_ARG(e, "engine_profile: NULL engine");
+    e->prof.on = enable != 0;
+    e->prof.recs.clear();
+    e->prof.used = 0;
+    for (int i = 0; i < GSAGE_PROF_CATS; ++i) e->prof.bytes[i] = 0;
+    return GSAGE_OK;
+}
+
+int gsage_engine_profile_read(gsage_engine* e, double* ms_out, int64_t* launches_out, double* work_out, void* stream) {
+    GS_CHECK_ARG(e && ms_out && launches_out && work_out, "engine_profile_read: NULL argument");
+    GS_CUDA(cudaStreamSynchronize(as_stream(stream)));
+    for (int i = 0; i < GSAGE_PROF_CATS; ++i) { ms_out[i] = 0; launches_out[i] = 0; work_out[i] = e->prof.bytes[i]; }
+    for (const EngineProf::Rec& r : e->prof.recs) {
+        float ms = 0;
+        GS_CUDA(cudaEventElapsedTime(&ms, e->prof.pool[r.a], e->prof.pool[r.b]));
+        ms_out[r.cat] += ms;
+        launches_out[r.cat] += 1;
+    }
+    e->prof.recs.clear();
+    e->prof.used = 0;
+    for (int i = 0; i < GSAGE_PROF_CATS; ++i) e->prof.bytes[i] = 0;
+    return GSAGE_OK;
+}
 
 int gsage_engine_set_weights(gsage_engine* e, const gsage_weights* w, void* stream) {
     (void)stream;
@@ -246,6 +303,8 @@ int gsage_engine_forward(gsage_engine* e, gsage_graph* g, gsage_rng* rng, const 
     const int64_t es = (int64_t)dtype_size(T);
     e->B = B;
 
+    const int p_all = e->prof.begin(GSAGE_PROF_FORWARD, s);
+    const int p_smp = e->prof.begin(GSAGE_PROF_SAMPLE, s);
     // ---- sample: hop 0 draws first, then hop 1 (models.py:78-79) ------------------------------------
     int64_t* ids0 = e->ids; int64_t* ids1 = ids0 + n0; int64_t* ids2 = ids1 + n1;
     if (ids_dev != ids0) GS_CUDA(cudaMemcpyAsync(ids0, ids_dev, 8 * n0, cudaMemcpyDeviceToDevice, s));
@@ -253,6 +312,7 @@ int gsage_engine_forward(gsage_engine* e, gsage_graph* g, gsage_rng* rng, const 
     GS_TRY(sample_sparse_launch(g, ids0, n0, S1, e->sel, ids1, s));
     GS_TRY(rng_randint_internal(rng, (uint32_t)g->n_cols, n2, e->sel, s));
     GS_TRY(sample_sparse_launch(g, ids1, n1, S2, e->sel, ids2, s));
+    e->prof.end(p_smp, s);
 
     // ---- prep (models.py:76-81) ------------------------------------------------------------------------
     RowSrc lvl;       // all three hops, hop k starts `offset_k` rows in
@@ -296,8 +356,10 @@ int gsage_engine_forward(gsage_engine* e, gsage_graph* g, gsage_rng* rng, const 
     // ---- normalise + classifier (models.py:90-91) -----------------------------------------------------------------
     GS_TRY(gsage_l2_normalize(e->Z, GSAGE_F32, 2 * O2, n0, 2 * O2, e->ZN, 2 * O2, s));
     RowSrc zn{e->ZN, GSAGE_F32, 2 * O2, n0, nullptr, 2 * O2};
-    return linear_call(zn, e->w.fc_w, 2 * O2, c.n_classes, e->w.fc_b, n0, GSAGE_ACT_NONE, logits_dev, GSAGE_F32, c.n_classes,
-                       0, 1, s);
+    GS_TRY(linear_call(zn, e->w.fc_w, 2 * O2, c.n_classes, e->w.fc_b, n0, GSAGE_ACT_NONE, logits_dev, GSAGE_F32, c.n_classes,
+                       0, 1, s));
+    e->prof.end(p_all, s);
+    return GSAGE_OK;
 }
 
 int gsage_engine_forward_host(gsage_engine* e, gsage_graph* g, gsage_rng* rng, const int64_t* ids_host, int64_t B,

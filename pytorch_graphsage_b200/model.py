@@ -187,6 +187,18 @@ class GSSupervised(nn.Module):
         self._last = eng
         return logits_host
 
+    def profile(self, enable=True):
+        """Switch the engine's CUDA-event stopwatch on/off (all engines of this model)."""
+        for eng in self._engines.values():
+            check(lib().gsage_engine_profile(eng['h'], 1 if enable else 0))
+
+    def profile_read(self):
+        """{category: (ms, launches, work)} accumulated since the last read, for the last-used engine; synchronises."""
+        ms, cnt, work = (C.c_double * 4)(), (C.c_int64 * 4)(), (C.c_double * 4)()
+        check(lib().gsage_engine_profile_read(self._last['h'], ms, cnt, work, ops.stream()))
+        names = ('forward', 'sample', 'reduce', 'project')
+        return {n: (ms[i], cnt[i], work[i]) for i, n in enumerate(names)}
+
     def peek(self, what):
         """Device view of an intermediate of the last forward: 'ids0' 'ids1' 'ids2' 'layer1' 'layer2'."""
         code = {'ids0': 0, 'ids1': 1, 'ids2': 2, 'layer1': 10, 'layer2': 11}[what]
