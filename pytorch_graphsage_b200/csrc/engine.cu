@@ -35,6 +35,18 @@ struct RowSrc {
     }
 };
 
+// a weight matrix as a kernel will read it: the caller's fp32 tensor, or the engine's padded bf16 copy
+struct WRef { const void* p; int dtype; int64_t ld; };
+
+// fp32 (rows, cols) -> bf16 (rows, ld) with zero padding (the tcgen05 kernel wants 16-byte aligned bf16 rows)
+__global__ void __launch_bounds__(256) to_bf16_padded_kernel(const float* __restrict__ src, int rows, int cols,
+                                                             __nv_bfloat16* __restrict__ dst, int64_t ld) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (int64_t)rows * ld) return;
+    const int r = (int)(i / ld), c = (int)(i % ld);
+    dst[i] = __float2bfloat16_rn(c < cols ? src[(int64_t)r * cols + c] : 0.0f);
+}
+
 __global__ void __launch_bounds__(256) fill_i64_kernel(int64_t* p, int64_t n, int64_t v) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) p[i] = v;
@@ -86,25 +98,30 @@ struct gsage_engine {
     void* H1 = nullptr;                 // layer-1 output (n0 + n1, 2*O1)
     float* Z = nullptr; float* ZN = nullptr; float* LG = nullptr;
     int64_t ld_h1 = 0;
+    // weights as the kernels read them (fp32 originals, or bf16 copies when compute dtype is bf16)
+    char* wb = nullptr; int64_t wb_bytes = 0;
+    WRef w_x[2], w_n[2], w_mlp[2], w_att1[2];
 };
 
 static int64_t pad_to(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
 
-static int linear_call(const RowSrc& a, const float* W, int64_t ldw, int O, const float* bias, int64_t n, int act,
+static WRef f32w(const float* p, int64_t ld) { return WRef{p, GSAGE_F32, ld}; }
+
+static int linear_call(const RowSrc& a, const WRef& W, int O, const float* bias, int64_t n, int act,
                        void* out, int out_dtype, int64_t ld_out, int64_t col0, int exact, cudaStream_t s) {
     LinearParams P;
     P.n_segs = 1; P.n = n; P.act = act; P.out = out; P.out_dtype = out_dtype; P.ld_out = ld_out;
-    P.seg[0] = LinearSeg{a.base, a.dtype, a.ld, a.ids, W, GSAGE_F32, ldw, a.d, O, bias, col0};
+    P.seg[0] = LinearSeg{a.base, a.dtype, a.ld, a.ids, W.p, W.dtype, W.ld, a.d, O, bias, col0};
     if (n == 0) return GSAGE_OK;
     return linear_dispatch(P, exact, s);
 }
 
-static int combine_call(const RowSrc& x, const float* Wx, const RowSrc& m, const float* Wn, int O, int64_t n, int act,
+static int combine_call(const RowSrc& x, const WRef& Wx, const RowSrc& m, const WRef& Wn, int O, int64_t n, int act,
                         void* out, int out_dtype, int64_t ld_out, int exact, cudaStream_t s) {
     LinearParams P;
     P.n_segs = 2; P.n = n; P.act = act; P.out = out; P.out_dtype = out_dtype; P.ld_out = ld_out;
-    P.seg[0] = LinearSeg{x.base, x.dtype, x.ld, x.ids, Wx, GSAGE_F32, (int64_t)x.d, x.d, O, nullptr, 0};
-    P.seg[1] = LinearSeg{m.base, m.dtype, m.ld, m.ids, Wn, GSAGE_F32, (int64_t)m.d, m.d, O, nullptr, (int64_t)O};
+    P.seg[0] = LinearSeg{x.base, x.dtype, x.ld, x.ids, Wx.p, Wx.dtype, Wx.ld, x.d, O, nullptr, 0};
+    P.seg[1] = LinearSeg{m.base, m.dtype, m.ld, m.ids, Wn.p, Wn.dtype, Wn.ld, m.d, O, nullptr, (int64_t)O};
     if (n == 0) return GSAGE_OK;
     return linear_dispatch(P, exact, s);
 }
@@ -126,7 +143,7 @@ static int apply_aggregator(gsage_engine* e, int layer, const RowSrc& x, const R
         if (p_red >= 0) e->prof.bytes[GSAGE_PROF_REDUCE] += (double)n * ((double)S * d * dtype_size(nb.dtype) + (nb.ids ? 8.0 * S : 0.0) + (double)d * dtype_size(T));
         RowSrc m{e->M, T, ldm, n, nullptr, d};
         const int p_prj = e->prof.begin(GSAGE_PROF_PROJECT, s);
-        const int st = combine_call(x, L.fc_x, m, L.fc_neib, O, n, act, out, out_dtype, ld_out, exact, s);
+        const int st = combine_call(x, e->w_x[layer], m, e->w_n[layer], O, n, act, out, out_dtype, ld_out, exact, s);
         e->prof.end(p_prj, s);
         if (p_prj >= 0) e->prof.bytes[GSAGE_PROF_PROJECT] += 4.0 * (double)n * d * O;      // flops, not bytes
         return st;
@@ -134,26 +151,26 @@ static int apply_aggregator(gsage_engine* e, int layer, const RowSrc& x, const R
     case GSAGE_AGG_MAX_POOL:
     case GSAGE_AGG_MEAN_POOL: {
         const int H = e->hid;
-        GS_TRY(linear_call(nb, L.mlp_w, d, H, L.mlp_b, n * S, GSAGE_ACT_RELU, e->HN, T, H, 0, exact, s));
+        GS_TRY(linear_call(nb, e->w_mlp[layer], H, L.mlp_b, n * S, GSAGE_ACT_RELU, e->HN, T, H, 0, exact, s));
         GS_TRY(gather_reduce_launch(e->HN, T, H, n * S, H, nullptr, n, S,
                                     e->cfg.aggregator == GSAGE_AGG_MAX_POOL ? GSAGE_RED_MAX : GSAGE_RED_MEAN, nullptr,
                                     e->Pp, T, H, s));
         RowSrc p{e->Pp, T, H, n, nullptr, H};
-        return combine_call(x, L.fc_x, p, L.fc_neib, O, n, act, out, out_dtype, ld_out, exact, s);
+        return combine_call(x, e->w_x[layer], p, e->w_n[layer], O, n, act, out, out_dtype, ld_out, exact, s);
     }
     case GSAGE_AGG_ATTENTION: {
         const int H = e->hid;
         GS_CHECK_ARG(S > 1, "attention aggregator: S must be > 1");
-        GS_TRY(linear_call(nb, L.att_w1, d, H, nullptr, n * S, GSAGE_ACT_TANH, e->T1, GSAGE_F32, H, 0, exact, s));
+        GS_TRY(linear_call(nb, e->w_att1[layer], H, nullptr, n * S, GSAGE_ACT_TANH, e->T1, GSAGE_F32, H, 0, exact, s));
         RowSrc t1{e->T1, GSAGE_F32, H, n * S, nullptr, H};
-        GS_TRY(linear_call(t1, L.att_w2, H, H, nullptr, n * S, GSAGE_ACT_NONE, e->NA, GSAGE_F32, H, 0, 1, s));
-        GS_TRY(linear_call(x, L.att_w1, d, H, nullptr, n, GSAGE_ACT_TANH, e->T1x, GSAGE_F32, H, 0, exact, s));
+        GS_TRY(linear_call(t1, f32w(L.att_w2, H), H, nullptr, n * S, GSAGE_ACT_NONE, e->NA, GSAGE_F32, H, 0, 1, s));
+        GS_TRY(linear_call(x, e->w_att1[layer], H, nullptr, n, GSAGE_ACT_TANH, e->T1x, GSAGE_F32, H, 0, exact, s));
         RowSrc t1x{e->T1x, GSAGE_F32, H, n, nullptr, H};
-        GS_TRY(linear_call(t1x, L.att_w2, H, H, nullptr, n, GSAGE_ACT_NONE, e->XA, GSAGE_F32, H, 0, 1, s));
+        GS_TRY(linear_call(t1x, f32w(L.att_w2, H), H, nullptr, n, GSAGE_ACT_NONE, e->XA, GSAGE_F32, H, 0, 1, s));
         GS_TRY(gsage_attention_weights(e->NA, e->XA, GSAGE_F32, H, H, n, S, e->AW, s));
         GS_TRY(gather_reduce_launch(nb.base, nb.dtype, nb.ld, nb.table_rows, d, nb.ids, n, S, GSAGE_RED_SUM, e->AW, e->M, T, ldm, s));
         RowSrc m{e->M, T, ldm, n, nullptr, d};
-        return combine_call(x, L.fc_x, m, L.fc_neib, O, n, act, out, out_dtype, ld_out, exact, s);
+        return combine_call(x, e->w_x[layer], m, e->w_n[layer], O, n, act, out, out_dtype, ld_out, exact, s);
     }
     }
     set_error("engine: unknown aggregator %d", e->cfg.aggregator);
@@ -225,6 +242,16 @@ int gsage_engine_create(const gsage_engine_config* cfg, gsage_engine** out) {
         return GSAGE_ERR_NOMEM;
     }
     cudaMemset(e->ws, 0, (size_t)off);      // padding columns of every intermediate stay zero forever
+    if (e->T == GSAGE_BF16) {                // arena for the padded bf16 weight copies the tensor-core kernel reads
+        const int64_t dmax0 = std::max<int64_t>(e->ld_prep, 2 * O1) + 8;
+        e->wb_bytes = 2 * 2 * ((O1 + O2) * 2 * (dmax0 + e->hid) + 2 * (int64_t)e->hid * dmax0) + 16 * 256;
+        if (cudaMalloc((void**)&e->wb, (size_t)e->wb_bytes) != cudaSuccess) {
+            set_error("engine_create: cudaMalloc of the weight arena failed");
+            cudaFree(e->ws);
+            delete e;
+            return GSAGE_ERR_NOMEM;
+        }
+    }
     auto at = [&](int64_t o) -> char* { return o < 0 ? nullptr : e->ws + o; };
     e->ids = (int64_t*)at(o_ids); e->sel = (uint32_t*)at(o_sel); e->look0 = (int64_t*)at(o_look);
     e->X = at(o_X); e->M = at(o_M); e->HN = at(o_HN); e->Pp = at(o_P);
@@ -238,6 +265,7 @@ void gsage_engine_destroy(gsage_engine* e) {
     if (!e) return;
     for (cudaEvent_t ev : e->prof.pool) cudaEventDestroy(ev);
     cudaFree(e->ws);
+    cudaFree(e->wb);
     delete e;
 }
 
@@ -269,7 +297,6 @@ int gsage_engine_profile_read(gsage_engine* e, double* ms_out, int64_t* launches
 }
 
 int gsage_engine_set_weights(gsage_engine* e, const gsage_weights* w, void* stream) {
-    (void)stream;
     GS_CHECK_ARG(e && w, "engine_set_weights: NULL argument");
     for (int l = 0; l < 2; ++l) {
         GS_CHECK_ARG(w->layer[l].fc_x && w->layer[l].fc_neib, "engine_set_weights: fc_x / fc_neib missing (layer %d)", l);
@@ -286,6 +313,30 @@ int gsage_engine_set_weights(gsage_engine* e, const gsage_weights* w, void* stre
         e->d_prep = w->prep_out_dim;
     }
     e->w = *w;
+    cudaStream_t s = as_stream(stream);
+    const bool pool = e->cfg.aggregator == GSAGE_AGG_MAX_POOL || e->cfg.aggregator == GSAGE_AGG_MEAN_POOL;
+    const bool att = e->cfg.aggregator == GSAGE_AGG_ATTENTION;
+    int64_t off = 0;
+    for (int l = 0; l < 2; ++l) {
+        const int d_in = l == 0 ? e->d_prep : 2 * e->cfg.out_dim[0];
+        const int d_nb = pool ? e->hid : d_in;
+        const int O = e->cfg.out_dim[l];
+        struct Item { const float* src; int rows, cols; WRef* dst; } items[4] = {
+            {w->layer[l].fc_x, O, d_in, &e->w_x[l]}, {w->layer[l].fc_neib, O, d_nb, &e->w_n[l]},
+            {pool ? w->layer[l].mlp_w : nullptr, e->hid, d_in, &e->w_mlp[l]}, {att ? w->layer[l].att_w1 : nullptr, e->hid, d_in, &e->w_att1[l]}};
+        for (const Item& it : items) {
+            if (!it.src) { *it.dst = WRef{nullptr, GSAGE_F32, 0}; continue; }
+            if (e->T != GSAGE_BF16) { *it.dst = f32w(it.src, it.cols); continue; }
+            const int64_t ld = pad_to(it.cols, 8);
+            const int64_t bytes = pad_to(2 * ld * it.rows, 256);
+            GS_CHECK_ARG(off + bytes <= e->wb_bytes, "engine_set_weights: bf16 weight arena too small");
+            __nv_bfloat16* dst = (__nv_bfloat16*)(e->wb + off);
+            to_bf16_padded_kernel<<<(unsigned)ceil_div((int64_t)it.rows * ld, 256), 256, 0, s>>>(it.src, it.rows, it.cols, dst, ld);
+            GS_LAUNCHED();
+            *it.dst = WRef{dst, GSAGE_BF16, ld};
+            off += bytes;
+        }
+    }
     e->have_weights = true;
     return GSAGE_OK;
 }
@@ -323,7 +374,7 @@ int gsage_engine_forward(gsage_engine* e, gsage_graph* g, gsage_rng* rng, const 
         const int64_t ldx = e->ld_prep;
         if (c.prep == GSAGE_PREP_LINEAR) {
             RowSrc f{c.feats_dev, c.feats_dtype, c.feats_ld, c.feats_rows, ids0, c.feats_dim};
-            GS_TRY(linear_call(f, e->w.prep_fc_w, c.feats_dim, e->d_prep, nullptr, ntot, GSAGE_ACT_NONE, e->X, T, ldx, 0,
+            GS_TRY(linear_call(f, f32w(e->w.prep_fc_w, c.feats_dim), e->d_prep, nullptr, ntot, GSAGE_ACT_NONE, e->X, T, ldx, 0,
                                T == GSAGE_F32, s));
         } else {
             const int dfe = c.feats_dev ? c.feats_dim : 0;
@@ -334,10 +385,10 @@ int gsage_engine_forward(gsage_engine* e, gsage_graph* g, gsage_rng* rng, const 
             fill_i64_kernel<<<(unsigned)ceil_div(n0, 256), 256, 0, s>>>(e->look0, n0, c.n_nodes);
             GS_LAUNCHED();
             RowSrc e0{c.emb_dev, c.emb_dtype, c.emb_ld, c.n_nodes + 1, e->look0, c.emb_dim};
-            GS_TRY(linear_call(e0, e->w.prep_fc_w, c.emb_dim, c.emb_dim, e->w.prep_fc_b, n0, GSAGE_ACT_NONE, e->X, T, ldx,
+            GS_TRY(linear_call(e0, f32w(e->w.prep_fc_w, c.emb_dim), c.emb_dim, e->w.prep_fc_b, n0, GSAGE_ACT_NONE, e->X, T, ldx,
                                dfe, T == GSAGE_F32, s));
             RowSrc e12{c.emb_dev, c.emb_dtype, c.emb_ld, c.n_nodes + 1, ids1, c.emb_dim};
-            GS_TRY(linear_call(e12, e->w.prep_fc_w, c.emb_dim, c.emb_dim, e->w.prep_fc_b, n1 + n2, GSAGE_ACT_NONE,
+            GS_TRY(linear_call(e12, f32w(e->w.prep_fc_w, c.emb_dim), c.emb_dim, e->w.prep_fc_b, n1 + n2, GSAGE_ACT_NONE,
                                (char*)e->X + n0 * ldx * es, T, ldx, dfe, T == GSAGE_F32, s));
         }
         lvl = RowSrc{e->X, T, ldx, ntot, nullptr, e->d_prep};
@@ -356,7 +407,7 @@ int gsage_engine_forward(gsage_engine* e, gsage_graph* g, gsage_rng* rng, const 
     // ---- normalise + classifier (models.py:90-91) -----------------------------------------------------------------
     GS_TRY(gsage_l2_normalize(e->Z, GSAGE_F32, 2 * O2, n0, 2 * O2, e->ZN, 2 * O2, s));
     RowSrc zn{e->ZN, GSAGE_F32, 2 * O2, n0, nullptr, 2 * O2};
-    GS_TRY(linear_call(zn, e->w.fc_w, 2 * O2, c.n_classes, e->w.fc_b, n0, GSAGE_ACT_NONE, logits_dev, GSAGE_F32, c.n_classes,
+    GS_TRY(linear_call(zn, f32w(e->w.fc_w, 2 * O2), c.n_classes, e->w.fc_b, n0, GSAGE_ACT_NONE, logits_dev, GSAGE_F32, c.n_classes,
                        0, 1, s));
     e->prof.end(p_all, s);
     return GSAGE_OK;

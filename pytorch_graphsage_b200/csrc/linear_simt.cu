@@ -126,8 +126,33 @@ extern "C" int gsage_linear(const gsage_linear_seg* segs, int n_segs, int64_t n,
 }
 
 namespace gsage {
+// bf16 x bf16 segments go to the tcgen05 kernel (<= 256 accumulator columns per launch: wide segments are
+// split into column blocks, two-segment calls that do not fit are issued one segment at a time);
+// anything else -- and everything when `exact` is set -- runs on the fp32 FFMA kernel.
 int linear_dispatch(const LinearParams& P, int exact, cudaStream_t s) {
-    (void)exact;   // the tcgen05 kernel (linear_umma.cu) hooks in here once it is parity-green
-    return linear_simt_launch(P, s);
+    bool tc = !exact;
+    for (int i = 0; i < P.n_segs && tc; ++i) {
+        LinearParams one = P;
+        one.n_segs = 1; one.seg[0] = P.seg[i];
+        if (one.seg[0].O > 256) one.seg[0].O = 256;
+        tc = linear_umma_eligible(one);
+    }
+    if (!tc) return linear_simt_launch(P, s);
+    if (linear_umma_eligible(P)) return linear_umma_launch(P, s);
+    for (int i = 0; i < P.n_segs; ++i) {
+        const LinearSeg& g = P.seg[i];
+        for (int c = 0; c < g.O; c += 256) {
+            LinearParams one = P;
+            one.n_segs = 1;
+            one.seg[0] = g;
+            one.seg[0].O = g.O - c < 256 ? g.O - c : 256;
+            one.seg[0].w = (const char*)g.w + (size_t)c * g.ldw * dtype_size(g.w_dtype);
+            one.seg[0].bias = g.bias ? g.bias + c : nullptr;
+            one.seg[0].col0 = g.col0 + c;
+            if (linear_umma_eligible(one)) GS_TRY(linear_umma_launch(one, s));
+            else GS_TRY(linear_simt_launch(one, s));
+        }
+    }
+    return GSAGE_OK;
 }
 }  // namespace gsage

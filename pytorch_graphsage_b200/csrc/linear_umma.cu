@@ -1,0 +1,353 @@
+// linear_umma.cu -- the dense W projection on the 5th-gen tensor cores (tcgen05.mma, accumulators in TMEM).
+//
+// Replaces the same nn.Linear calls as linear_simt.cu (nn_modules.py:200,224,228,307-308,317) when every
+// operand is bf16: out[r, col0_s + o] = act( sum_k A_s[row_s(r), k] * W_s[o, k] + bias_s[o] ) for up to two
+// segments s (the reference's concat-with-self, [fc_x(x) | fc_neib(agg)], is two accumulators of one tile).
+//
+// B200 design
+//   * persistent CTAs (one per SM), 128-row output tiles, 9 warps with fixed roles:
+//       warps 0-3  epilogue   TMEM -> registers (tcgen05.ld 32x32b) -> bias/activation -> bf16/fp32 -> HBM
+//       warp  4    MMA issue  one elected lane issues tcgen05.mma (M=128, N=O, K=16) + tcgen05.commit
+//       warps 5-8  loaders    gather the A rows *by id* (self rows come straight from the feature table)
+//                             and the W rows with 16-byte cp.async into 128B-swizzled K-major smem tiles
+//   * smem ring of (A 128x64, W Ox64) bf16 chunk pairs; full/empty mbarriers; the gather is free-form because
+//     the loader, not TMA, owns the smem layout (TMA cannot gather arbitrary rows);
+//   * two TMEM accumulator buffers (2 x 256 fp32 columns = all 512 columns): the epilogue of tile i overlaps
+//     the loads and MMAs of tile i+1.
+// Every mbarrier wait is bounded (a stuck pipeline traps instead of hanging the GPU).
+#include "linear.cuh"
+#include <string.h>
+
+namespace gsage {
+
+static constexpr int UM = 128;            // rows per tile (UMMA M)
+static constexpr int UK = 64;             // bf16 elements per smem chunk row = 128 bytes (one swizzle atom row)
+static constexpr int kEpiWarps = 4, kLoadWarps = 4;
+static constexpr int kThreads = 32 * (kEpiWarps + 1 + kLoadWarps);
+static constexpr int kABytes = UM * UK * 2;                   // 16 KB
+static constexpr int kMaxO = 256;
+
+struct UmmaSeg {
+    const __nv_bfloat16* a; int64_t lda; const int64_t* ids;
+    const __nv_bfloat16* w; int64_t ldw; int d; int O;
+    const float* bias; int64_t col0;
+    int kchunks;          // ceil(d / 64)
+    int acc_col;          // first TMEM column of this segment's accumulator inside a buffer
+};
+
+struct UmmaParams {
+    UmmaSeg seg[2];
+    int n_segs; int64_t n; int act;
+    void* out; int out_bf16; int64_t ld_out;
+    int n_tiles; int stages; int stage_bytes; int w_bytes;
+    int* err;
+};
+
+// ---- PTX helpers -----------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
+// bounded wait: a pipeline bug must not hang the box
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* err) {
+    if (mbar_try(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try(bar, parity)) {
+        if (clock64() - t0 > 4000000000LL) {       // ~2 s at 1.9 GHz
+            if (err) atomicExch(err, 1);
+            __trap();
+        }
+    }
+}
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// K-major, SWIZZLE_128B operand tile: rows 128 B apart, 8-row atoms 1024 B apart (cute::UMMA::SmemDescriptor)
+__device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);          // start address, 16-byte units
+    d |= (uint64_t)1 << 16;                                // leading byte offset (unused for swizzled K-major)
+    d |= (uint64_t)(1024 >> 4) << 32;                      // stride byte offset: 8 rows x 128 B
+    d |= (uint64_t)1 << 46;                                // descriptor version (Blackwell)
+    d |= (uint64_t)2 << 61;                                // SWIZZLE_128B
+    return d;
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// ---- the kernel ----------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads, 1) linear_umma_kernel(const UmmaParams P) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    // carve: [stages x (A 16 KB | W w_bytes)] then barriers
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint64_t* bars = (uint64_t*)(smem + (size_t)P.stages * P.stage_bytes);
+    uint32_t* tmem_slot = (uint32_t*)(bars + 2 * 8 + 4);
+    const uint32_t bar_base = smem_u32(bars);
+    auto full_bar = [&](int s) { return bar_base + 8u * s; };
+    auto empty_bar = [&](int s) { return bar_base + 8u * (8 + s); };
+    auto tfull_bar = [&](int b) { return bar_base + 8u * (16 + b); };
+    auto tempty_bar = [&](int b) { return bar_base + 8u * (18 + b); };
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < P.stages; ++s) { mbar_init(full_bar(s), 32 * kLoadWarps); mbar_init(empty_bar(s), 1); }
+        for (int b = 0; b < 2; ++b) { mbar_init(tfull_bar(b), 1); mbar_init(tempty_bar(b), 32 * kEpiWarps); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == kEpiWarps) {                                 // the MMA warp owns the TMEM allocation
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    int items_per_tile = 0;
+    for (int s = 0; s < P.n_segs; ++s) items_per_tile += P.seg[s].kchunks;
+
+    if (warp < kEpiWarps) {
+        // =========================== EPILOGUE ===========================
+        const int row_in_tile = warp * 32 + lane;            // TMEM lane == tile row; warp w may touch lanes 32w..32w+31
+        int it = 0;
+        for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x, ++it) {
+            const int buf = it & 1;
+            mbar_wait(tfull_bar(buf), (it >> 1) & 1, P.err);
+            tc_fence_after();
+            const int64_t row = (int64_t)tile * UM + row_in_tile;
+            for (int s = 0; s < P.n_segs; ++s) {
+                const UmmaSeg& sg = P.seg[s];
+                for (int c0 = 0; c0 < sg.O; c0 += 32) {
+                    uint32_t r[32];
+                    tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(buf * 256 + sg.acc_col + c0), r);
+                    tmem_ld_wait();
+                    if (row < P.n) {
+                        float v[32];
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            float f = __uint_as_float(r[j]);
+                            if (sg.bias && c0 + j < sg.O) f += sg.bias[c0 + j];
+                            v[j] = apply_act(f, P.act);
+                        }
+                        const int valid = min(32, sg.O - c0);
+                        const int64_t at = row * P.ld_out + sg.col0 + c0;
+                        if (P.out_bf16) {
+                            __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(P.out) + at;
+                            if (valid == 32 && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
+#pragma unroll
+                                for (int q = 0; q < 4; ++q)
+                                    reinterpret_cast<uint4*>(o)[q] = make_uint4(pack_bf16(v[8 * q], v[8 * q + 1]), pack_bf16(v[8 * q + 2], v[8 * q + 3]),
+                                                                                pack_bf16(v[8 * q + 4], v[8 * q + 5]), pack_bf16(v[8 * q + 6], v[8 * q + 7]));
+                            } else {
+                                for (int j = 0; j < valid; ++j) o[j] = __float2bfloat16_rn(v[j]);
+                            }
+                        } else {
+                            float* o = reinterpret_cast<float*>(P.out) + at;
+                            if (valid == 32 && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
+#pragma unroll
+                                for (int q = 0; q < 8; ++q)
+                                    reinterpret_cast<float4*>(o)[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+                            } else {
+                                for (int j = 0; j < valid; ++j) o[j] = v[j];
+                            }
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(tempty_bar(buf));
+        }
+    } else if (warp == kEpiWarps) {
+        // =========================== MMA ISSUER ===========================
+        int item = 0, it = 0;
+        for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x, ++it) {
+            const int buf = it & 1;
+            mbar_wait(tempty_bar(buf), ((it >> 1) & 1) ^ 1, P.err);     // first use of each buffer passes immediately
+            tc_fence_after();
+            for (int s = 0; s < P.n_segs; ++s) {
+                const UmmaSeg& sg = P.seg[s];
+                // instruction descriptor: D=f32, A=B=bf16, K-major both, N = O, M = 128
+                const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(sg.O >> 3) << 17) | ((uint32_t)(UM >> 4) << 24);
+                const uint32_t d_tmem = tmem_base + (uint32_t)(buf * 256 + sg.acc_col);
+                for (int kc = 0; kc < sg.kchunks; ++kc, ++item) {
+                    const int stage = item % P.stages;
+                    mbar_wait(full_bar(stage), (item / P.stages) & 1, P.err);
+                    tc_fence_after();
+                    if (lane == 0) {
+                        const uint32_t a_addr = smem_u32(smem + (size_t)stage * P.stage_bytes);
+                        const uint32_t b_addr = a_addr + kABytes;
+                        const uint64_t adesc = umma_desc(a_addr), bdesc = umma_desc(b_addr);
+#pragma unroll
+                        for (int k = 0; k < UK / 16; ++k)                // 4 x (K = 16): +32 bytes inside the swizzle atom
+                            umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kc | k) ? 1u : 0u);
+                        umma_commit(empty_bar(stage));                   // smem slot reusable once these MMAs retire
+                    }
+                    __syncwarp();
+                }
+            }
+            if (lane == 0) umma_commit(tfull_bar(buf));                  // accumulators of this tile complete
+            __syncwarp();
+        }
+    } else {
+        // =========================== LOADERS ===========================
+        const int t = threadIdx.x - 32 * (kEpiWarps + 1);    // 0..127
+        const int sub_row = t >> 3, chunk = t & 7;            // 8 threads cover one 128-byte row segment
+        int item = 0;
+        const int total_items = ((P.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x) * items_per_tile;
+        constexpr int LAG = 2;                                 // cp.async groups in flight before the oldest is published
+        int issued = 0;
+        int tile = blockIdx.x, s = 0, kc = 0;
+        const __nv_bfloat16* a_rows[8];
+        bool rows_ready = false;
+        for (int step = 0; step < total_items + LAG; ++step) {
+            if (step < total_items) {
+                const UmmaSeg& sg = P.seg[s];
+                if (!rows_ready) {                                // row pointers of this (tile, segment): gathered by id
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const int64_t r = (int64_t)tile * UM + i * 16 + sub_row;
+                        a_rows[i] = nullptr;
+                        if (r < P.n) {
+                            const int64_t src = sg.ids ? sg.ids[r] : r;
+                            a_rows[i] = sg.a + src * sg.lda;
+                        }
+                    }
+                    rows_ready = true;
+                }
+                const int stage = item % P.stages;
+                mbar_wait(empty_bar(stage), ((item / P.stages) & 1) ^ 1, P.err);
+                uint8_t* sa = smem + (size_t)stage * P.stage_bytes;
+                const int k0 = kc * UK + chunk * 8;               // first element of this thread's 16-byte chunk
+                const uint32_t kbytes = (k0 < sg.d) ? (uint32_t)min(16, (sg.d - k0) * 2) : 0u;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int r = i * 16 + sub_row;
+                    const uint32_t dst = smem_u32(sa + r * 128 + ((chunk ^ (r & 7)) << 4));
+                    const bool live = a_rows[i] != nullptr && kbytes;
+                    cp_async16(dst, live ? (const void*)(a_rows[i] + k0) : (const void*)sg.a, live ? kbytes : 0u);
+                }
+                uint8_t* sw = sa + kABytes;
+                for (int r = sub_row; r < sg.O; r += 16) {
+                    const uint32_t dst = smem_u32(sw + r * 128 + ((chunk ^ (r & 7)) << 4));
+                    cp_async16(dst, kbytes ? (const void*)(sg.w + (int64_t)r * sg.ldw + k0) : (const void*)sg.w, kbytes);
+                }
+                ++item;
+                if (++kc == sg.kchunks) {
+                    kc = 0; rows_ready = false;
+                    if (++s == P.n_segs) { s = 0; tile += gridDim.x; }
+                }
+            }
+            cp_async_commit();
+            if (step >= LAG) {
+                cp_async_wait<LAG>();                             // the group issued LAG steps ago has landed
+                fence_proxy_async();                              // generic-proxy writes -> visible to the tensor core
+                mbar_arrive(full_bar(issued % P.stages));
+                ++issued;
+            }
+        }
+    }
+
+    // teardown: everyone done with TMEM before it is freed
+    tc_fence_before();
+    __syncthreads();
+    if (warp == kEpiWarps) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    }
+}
+
+// ---- host -------------------------------------------------------------------------------------------------
+static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+bool linear_umma_eligible(const LinearParams& P) {
+    if (P.n < 1) return false;
+    int cols = 0;
+    for (int i = 0; i < P.n_segs; ++i) {
+        const LinearSeg& s = P.seg[i];
+        if (s.a_dtype != GSAGE_BF16 || s.w_dtype != GSAGE_BF16) return false;
+        if (s.O % 16 != 0 || s.O < 16 || s.O > kMaxO) return false;
+        if (!aligned16(s.a) || !aligned16(s.w) || (s.lda * 2) % 16 != 0 || (s.ldw * 2) % 16 != 0) return false;
+        if (s.lda < (s.d + 7) / 8 * 8 || s.ldw < (s.d + 7) / 8 * 8) return false;      // whole 16-byte chunks readable
+        cols += s.O;
+    }
+    return cols <= 256;
+}
+
+static int* g_umma_err = nullptr;
+
+int linear_umma_launch(const LinearParams& P, cudaStream_t s) {
+    UmmaParams U;
+    memset(&U, 0, sizeof(U));
+    int col = 0, maxO = 0;
+    for (int i = 0; i < P.n_segs; ++i) {
+        const LinearSeg& g = P.seg[i];
+        U.seg[i].a = (const __nv_bfloat16*)g.a; U.seg[i].lda = g.lda; U.seg[i].ids = g.ids;
+        U.seg[i].w = (const __nv_bfloat16*)g.w; U.seg[i].ldw = g.ldw; U.seg[i].d = g.d; U.seg[i].O = g.O;
+        U.seg[i].bias = g.bias; U.seg[i].col0 = g.col0;
+        U.seg[i].kchunks = (g.d + UK - 1) / UK;
+        U.seg[i].acc_col = col;
+        col += (g.O + 31) / 32 * 32;
+        maxO = g.O > maxO ? g.O : maxO;
+    }
+    GS_CHECK_ARG(col <= 256, "linear_umma: accumulators need %d TMEM columns (max 256 per buffer)", col);
+    U.n_segs = P.n_segs; U.n = P.n; U.act = P.act; U.out = P.out; U.out_bf16 = P.out_dtype == GSAGE_BF16; U.ld_out = P.ld_out;
+    U.n_tiles = (int)ceil_div(P.n, UM);
+    U.w_bytes = maxO * UK * 2;
+    U.stage_bytes = (kABytes + U.w_bytes + 1023) / 1024 * 1024;
+    const int budget = 200 * 1024;
+    U.stages = budget / U.stage_bytes;
+    if (U.stages > 8) U.stages = 8;
+    GS_CHECK_ARG(U.stages >= 3, "linear_umma: tile too large for shared memory");
+    if (!g_umma_err) {
+        GS_CUDA(cudaMalloc((void**)&g_umma_err, sizeof(int)));
+        GS_CUDA(cudaMemset(g_umma_err, 0, sizeof(int)));
+    }
+    U.err = g_umma_err;
+    const size_t smem = (size_t)U.stages * U.stage_bytes + 1024 /*align slack*/ + 256 /*barriers*/;
+    static bool attr_set = false;
+    if (!attr_set) {
+        GS_CUDA(cudaFuncSetAttribute(linear_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        attr_set = true;
+    }
+    const int grid = U.n_tiles < sm_count() ? U.n_tiles : sm_count();
+    linear_umma_kernel<<<grid, kThreads, smem, s>>>(U);
+    GS_LAUNCHED();
+    return GSAGE_OK;
+}
+
+}  // namespace gsage

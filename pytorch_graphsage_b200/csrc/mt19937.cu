@@ -18,6 +18,8 @@
 // far ahead to generate; they are re-tightened with one 8-byte read-back only when they drift apart by
 // more than the ring can hold.
 #include "mt19937.cuh"
+#include "mt_jump.h"
+#include <vector>
 
 #include <math.h>
 #include <string.h>
@@ -66,6 +68,87 @@ __global__ void __launch_bounds__(256) mt_generate_kernel(uint32_t* __restrict__
         __syncthreads();
         const int64_t base = start + (int64_t)b * kN;
         for (int i = tid; i < kN; i += 256) ring[(uint64_t)(base + i) & cap_mask] = n[i];
+        cur ^= 1;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// lane-parallel refill (jump-ahead).  Lane l generates blocks [l*K, (l+1)*K) of the refill; its start
+// window is the head window H jumped ahead by l*K*624 words:  g_l(F) H = XOR_{i: g_l[i]=1} x[i .. i+624)
+// where x is the stream continuing H (mt_jump.cpp).  The XOR is split over kJumpSlices CTAs per lane
+// (each takes 2496 of the 19968 polynomial bits) and the partial windows are combined by the lane.
+// ---------------------------------------------------------------------------------------------
+static constexpr int kJumpSlices = 8;
+static constexpr int kSliceWords = 78;                   // 78 x 32 = 2496 bits; 8 x 78 = 624 words
+static constexpr int kSeqWords = 19968 + kN;             // words of x a slice may touch
+
+__device__ __forceinline__ void mt_next_block(const uint32_t* o, uint32_t* n, int tid) {
+    if (tid < 227) n[tid] = o[tid + kM] ^ mt_mix(o[tid], o[tid + 1]);
+    __syncthreads();
+    if (tid < 227) n[tid + 227] = n[tid] ^ mt_mix(o[tid + 227], o[tid + 228]);
+    __syncthreads();
+    if (tid < 169) n[tid + 454] = n[tid + 227] ^ mt_mix(o[tid + 454], o[tid + 455]);
+    else if (tid == 169) n[623] = n[396] ^ mt_mix(o[623], n[0]);
+    __syncthreads();
+}
+
+// grid (lanes-1, kJumpSlices): partial[(lane-1)*kJumpSlices + slice][624]
+__global__ void __launch_bounds__(256) mt_jump_kernel(const uint32_t* __restrict__ ring, uint64_t cap_mask, int64_t start,
+                                                      const uint32_t* __restrict__ polys, uint32_t* __restrict__ partial) {
+    extern __shared__ uint32_t x[];                       // kSeqWords
+    __shared__ uint32_t gw[kSliceWords];
+    const int tid = threadIdx.x, lane = blockIdx.x + 1, slice = blockIdx.y;
+    for (int i = tid; i < kN; i += 256) x[i] = ring[(uint64_t)(start - kN + i) & cap_mask];
+    if (tid < kSliceWords) gw[tid] = polys[(size_t)(lane - 1) * kN + slice * kSliceWords + tid];
+    __syncthreads();
+    // this slice touches x[slice*2496 .. slice*2496 + 2496 + 624): generate just far enough
+    const int need = (slice + 1) * kSliceWords * 32 + kN;
+    for (int b = 0; (b + 1) * kN < need; ++b) mt_next_block(x + b * kN, x + (b + 1) * kN, tid);
+    uint32_t a0 = 0, a1 = 0, a2 = 0;
+    const uint32_t* xs = x + slice * kSliceWords * 32;
+    const bool third = tid + 512 < kN;
+    for (int w = 0; w < kSliceWords; ++w) {
+        uint32_t bits = gw[w];                             // uniform across the CTA: no divergence
+        while (bits) {
+            const int b = __ffs(bits) - 1;
+            bits &= bits - 1;
+            const uint32_t* p = xs + w * 32 + b + tid;
+            a0 ^= p[0];
+            a1 ^= p[256];
+            if (third) a2 ^= p[512];
+        }
+    }
+    uint32_t* out = partial + ((size_t)(lane - 1) * kJumpSlices + slice) * kN;
+    out[tid] = a0;
+    out[tid + 256] = a1;
+    if (third) out[tid + 512] = a2;
+}
+
+// grid (lanes): lane l writes stream words [start + l*K*624, start + (l+1)*K*624)
+__global__ void __launch_bounds__(256) mt_generate_lanes_kernel(uint32_t* __restrict__ ring, uint64_t cap_mask,
+                                                                int64_t start, int blocks_per_lane,
+                                                                const uint32_t* __restrict__ partial) {
+    __shared__ uint32_t st[2][kN];
+    const int tid = threadIdx.x, lane = blockIdx.x;
+    for (int i = tid; i < kN; i += 256) {
+        uint32_t v;
+        if (lane == 0) {
+            v = ring[(uint64_t)(start - kN + i) & cap_mask];
+        } else {
+            v = 0;
+            const uint32_t* p = partial + (size_t)(lane - 1) * kJumpSlices * kN + i;
+#pragma unroll
+            for (int s = 0; s < kJumpSlices; ++s) v ^= p[s * kN];
+        }
+        st[0][i] = v;
+    }
+    __syncthreads();
+    int cur = 0;
+    const int64_t base0 = start + (int64_t)lane * blocks_per_lane * kN;
+    for (int b = 0; b < blocks_per_lane; ++b) {
+        mt_next_block(st[cur], st[cur ^ 1], tid);
+        const int64_t base = base0 + (int64_t)b * kN;
+        for (int i = tid; i < kN; i += 256) ring[(uint64_t)(base + i) & cap_mask] = st[cur ^ 1][i];
         cur ^= 1;
     }
 }
@@ -257,24 +340,55 @@ static int rng_resync(gsage_rng* r, cudaStream_t s) {
     return GSAGE_OK;
 }
 
+// lazily computed jump polynomials (host, ~0.1 s once per process) + device scratch for the lane refill
+static int rng_init_lanes(gsage_rng* r) {
+    if (r->lanes_ready) return GSAGE_OK;
+    std::vector<uint32_t> polys((size_t)(r->lanes - 1) * kN);
+    if (mt_jump_poly_series((uint64_t)r->lane_blocks * kN, r->lanes - 1, polys.data()) != 0) {
+        set_error("rng: MT19937 characteristic polynomial computation failed");
+        return GSAGE_ERR_RNG;
+    }
+    GS_CUDA(cudaMalloc((void**)&r->polys, sizeof(uint32_t) * polys.size()));
+    GS_CUDA(cudaMemcpy(r->polys, polys.data(), sizeof(uint32_t) * polys.size(), cudaMemcpyHostToDevice));
+    GS_CUDA(cudaMalloc((void**)&r->partial, sizeof(uint32_t) * (size_t)(r->lanes - 1) * kJumpSlices * kN));
+    GS_CUDA(cudaFuncSetAttribute(mt_jump_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(uint32_t) * kSeqWords)));
+    r->lanes_ready = true;
+    return GSAGE_OK;
+}
+
 // make sure stream words [.., upto) exist in the ring without overwriting anything still needed
 int rng_ensure(gsage_rng* r, int64_t upto, cudaStream_t s) {
-    if (upto <= r->gen_end) return GSAGE_OK;
-    int64_t blocks = ceil_div(upto - r->gen_end, kN);
-    blocks = std::max<int64_t>(blocks, r->prefetch_blocks);
-    // words from (cursor_lb - 624) must survive: the block under the cursor is the numpy `key`
-    if (r->gen_end + blocks * kN - (r->cursor_lb - kN) > r->cap) {
-        GS_TRY(rng_resync(r, s));
-        blocks = std::min(blocks, (r->cap - (r->gen_end - (r->cursor_lb - kN))) / kN);
-        if (r->gen_end + blocks * kN < upto) {
-            set_error("rng: ring of %lld words cannot hold a look-ahead of %lld", (long long)r->cap,
-                      (long long)(upto - r->cursor_lb));
-            return GSAGE_ERR_RNG;
+    while (upto > r->gen_end) {
+        const int64_t need = ceil_div(upto - r->gen_end, kN);
+        const int64_t lane_refill = (int64_t)r->lanes * r->lane_blocks;
+        const bool use_lanes = r->lanes > 1 && need >= r->lane_threshold;
+        int64_t blocks = use_lanes ? lane_refill : std::max<int64_t>(need, r->prefetch_blocks);
+        // words from (cursor_lb - 624) must survive: the block under the cursor is the numpy `key`
+        if (r->gen_end + blocks * kN - (r->cursor_lb - kN) > r->cap) {
+            GS_TRY(rng_resync(r, s));
+            const int64_t room = (r->cap - (r->gen_end - (r->cursor_lb - kN))) / kN;
+            if (room < need) {
+                set_error("rng: ring of %lld words cannot hold a look-ahead of %lld", (long long)r->cap,
+                          (long long)(upto - r->cursor_lb));
+                return GSAGE_ERR_RNG;
+            }
+            if (blocks > room) blocks = use_lanes ? -1 : room;
         }
+        if (use_lanes && blocks == lane_refill) {
+            GS_TRY(rng_init_lanes(r));
+            mt_jump_kernel<<<dim3(r->lanes - 1, kJumpSlices), 256, sizeof(uint32_t) * kSeqWords, s>>>(
+                r->ring, (uint64_t)(r->cap - 1), r->gen_end, r->polys, r->partial);
+            GS_LAUNCHED();
+            mt_generate_lanes_kernel<<<r->lanes, 256, 0, s>>>(r->ring, (uint64_t)(r->cap - 1), r->gen_end, r->lane_blocks,
+                                                              r->partial);
+            GS_LAUNCHED();
+        } else {
+            if (blocks < 0) blocks = std::min<int64_t>(need, (r->cap - (r->gen_end - (r->cursor_lb - kN))) / kN);
+            mt_generate_kernel<<<1, 256, 0, s>>>(r->ring, (uint64_t)(r->cap - 1), r->gen_end, (int)blocks);
+            GS_LAUNCHED();
+        }
+        r->gen_end += blocks * kN;
     }
-    mt_generate_kernel<<<1, 256, 0, s>>>(r->ring, (uint64_t)(r->cap - 1), r->gen_end, (int)blocks);
-    GS_LAUNCHED();
-    r->gen_end += blocks * kN;
     return GSAGE_OK;
 }
 
@@ -344,7 +458,11 @@ int gsage_rng_create(gsage_rng** out) {
     int log2cap = 24;                                           // 16 Mi words = 64 MiB of look-ahead
     if (const char* e = getenv("GSAGE_RNG_LOG2_WORDS")) log2cap = std::max(14, std::min(30, atoi(e)));
     r->cap = (int64_t)1 << log2cap;
-    r->prefetch_blocks = std::max<int64_t>(1, std::min<int64_t>(512, r->cap / kN / 8));
+    r->prefetch_blocks = std::max<int64_t>(1, std::min<int64_t>(64, r->cap / kN / 8));
+    // lane refill = lanes x lane_blocks x 624 words (default 32 x 256 -> 5.1 M words); rings too small for it stay sequential
+    r->lanes = 32; r->lane_blocks = 256; r->lane_threshold = 128;
+    if (const char* e = getenv("GSAGE_RNG_LANES")) r->lanes = std::max(1, std::min(148, atoi(e)));
+    if ((int64_t)r->lanes * r->lane_blocks * kN > r->cap / 3) r->lanes = 1;
     r->tiles_cap = (int)(r->cap / kTile + 2);
     cudaError_t e1 = cudaMalloc((void**)&r->ring, sizeof(uint32_t) * r->cap);
     cudaError_t e2 = cudaMalloc((void**)&r->cursor, sizeof(int64_t) * 2);
@@ -363,6 +481,7 @@ int gsage_rng_create(gsage_rng** out) {
 void gsage_rng_destroy(gsage_rng* r) {
     if (!r) return;
     cudaFree(r->ring); cudaFree(r->cursor); cudaFree(r->err_flag); cudaFree(r->tile_count); cudaFree(r->tile_off);
+    cudaFree(r->polys); cudaFree(r->partial);
     delete r;
 }
 

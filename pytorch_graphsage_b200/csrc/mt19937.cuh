@@ -14,7 +14,13 @@ struct gsage_rng {
     int64_t gen_end = 0;           // host: words [.., gen_end) are generated
     int64_t cursor_lb = 0, cursor_ub = 0;   // host bounds on the device cursor
     int64_t origin = 0;            // cursor value at the last seed / set_state
-    int64_t prefetch_blocks = 256; // generate at least this many 624-word blocks per refill
+    int64_t prefetch_blocks = 64;  // sequential refill: generate at least this many 624-word blocks
+    // lane-parallel refill (jump-ahead): lanes x lane_blocks blocks per refill
+    int lanes = 32, lane_blocks = 256;
+    int64_t lane_threshold = 128;  // refills needing fewer blocks than this stay on the sequential kernel
+    bool lanes_ready = false;
+    uint32_t* polys = nullptr;     // device, (lanes-1) x 624 words: t^(l*lane_blocks*624) mod phi
+    uint32_t* partial = nullptr;   // device, (lanes-1) x 8 x 624 words
 };
 
 namespace gsage {

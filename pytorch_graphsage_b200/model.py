@@ -153,6 +153,15 @@ class GSSupervised(nn.Module):
             w.prep_fc_w, w.prep_out_dim = p(self.prep.fc.weight), self.prep.output_dim
         return w
 
+    def _push_weights(self, eng):
+        """Hand the current parameters to the engine -- only when a parameter moved or was updated in place
+        (torch bumps `_version` on every in-place write, e.g. an optimiser step)."""
+        stamp = tuple((p.data_ptr(), p._version) for p in self.parameters())
+        if eng.get('stamp') != stamp:
+            w = self._weights()
+            check(lib().gsage_engine_set_weights(eng['h'], C.byref(w), ops.stream()))
+            eng['stamp'] = stamp
+
     # -- the reference's public surface ---------------------------------------------------------------
     def forward(self, ids, feats, train=True):
         """models.py:71-91.  `ids`: int64 tensor of seed ids (CUDA, or CPU -> copied); `feats`: the node feature
@@ -164,8 +173,7 @@ class GSSupervised(nn.Module):
         ids = torch.as_tensor(ids).to(device='cuda', dtype=torch.int64).contiguous().view(-1)
         table = self._table(feats)
         eng = self._engine(table, fanout, ids.shape[0])
-        w = self._weights()
-        check(lib().gsage_engine_set_weights(eng['h'], C.byref(w), ops.stream()))
+        self._push_weights(eng)
         rng = sampler.rng or self.rng or default_rng()
         out = torch.empty((ids.shape[0], self.n_classes), dtype=torch.float32, device='cuda')
         check(lib().gsage_engine_forward(eng['h'], sampler.graph._h, rng._h, ops.ptr(ids), ids.shape[0], ops.ptr(out), ops.stream()))
@@ -179,8 +187,7 @@ class GSSupervised(nn.Module):
         table = self._table(feats)
         B = ids_host.shape[0]
         eng = self._engine(table, fanout, B)
-        w = self._weights()
-        check(lib().gsage_engine_set_weights(eng['h'], C.byref(w), ops.stream()))
+        self._push_weights(eng)
         rng = sampler.rng or self.rng or default_rng()
         check(lib().gsage_engine_forward_host(eng['h'], sampler.graph._h, rng._h, C.c_void_p(ids_host.data_ptr()), B,
                                               C.c_void_p(logits_host.data_ptr()), ops.stream()))

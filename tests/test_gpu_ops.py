@@ -123,3 +123,60 @@ def test_attention_weights_and_l2norm(g):
     np.testing.assert_allclose(got.cpu().numpy(), torch.nn.functional.normalize(z.double(), dim=1).numpy(), rtol=1e-5, atol=1e-7)
     with pytest.raises(ValueError):
         g.ops.attention_weights(na.cuda(), xa.cuda(), n * S, 1)     # S == 1 is out of contract (SURVEY A.2)
+
+
+# ---- tcgen05 projection kernel (bf16 x bf16 -> fp32 accumulate in TMEM) -------------------------------------
+# Tolerance: operands are exactly representable in bf16, products are exact in fp32, only the accumulation
+# order differs from fp64: rtol 2e-4 / atol 2e-4 for fp32 output; bf16 output adds one rounding (2^-8 rel).
+
+def _bf16(t):
+    return t.to(torch.bfloat16)
+
+
+@pytest.mark.parametrize('n,d,O', [(128, 64, 128), (1, 64, 16), (129, 100, 128), (1000, 602, 128), (4097, 256, 256),
+                                   (300, 1433, 32), (640, 512, 48)])
+@pytest.mark.parametrize('out_dtype', [torch.float32, torch.bfloat16])
+def test_umma_linear_single_segment(g, n, d, O, out_dtype):
+    gen = torch.Generator().manual_seed(n * 7 + d + O)
+    rows = n + 50
+    a = _bf16(torch.randn((rows, d), generator=gen))
+    w = _bf16(torch.randn((O, d), generator=gen) / d ** 0.5)
+    b = torch.randn((O,), generator=gen)
+    ids = torch.randint(0, rows, (n,), generator=gen)
+    a_dev = g.ops.pad_table(a.float(), torch.bfloat16)[0][:, :d]
+    w_dev = g.ops.pad_table(w.float(), torch.bfloat16)[0][:, :d]
+    tol = dict(rtol=2e-4, atol=2e-4) if out_dtype == torch.float32 else dict(rtol=1e-2, atol=1e-2)
+    for act, fn in ((None, lambda t: t), ('relu', torch.relu)):
+        want = fn(a[ids].double() @ w.double().t() + b.double())
+        got = g.ops.linear([dict(a=a_dev, ids=ids.cuda(), w=w_dev, bias=b.cuda())], n, act=act, out_dtype=out_dtype, exact=False)
+        np.testing.assert_allclose(got.float().cpu().numpy(), want.numpy(), **tol)
+    want = a[:n].double() @ w.double().t()
+    got = g.ops.linear([dict(a=a_dev, w=w_dev)], n, out_dtype=out_dtype, exact=False)
+    np.testing.assert_allclose(got.float().cpu().numpy(), want.numpy(), **tol)
+
+
+@pytest.mark.parametrize('n,d,O', [(777, 602, 128), (128 * 150 + 3, 64, 64), (50, 256, 128)])
+def test_umma_concat_with_self(g, n, d, O):
+    """[fc_x(table[ids]) | fc_neib(m)] + relu in one tensor-core launch (two TMEM accumulators per tile)."""
+    gen = torch.Generator().manual_seed(n)
+    table = _bf16(torch.randn((n + 99, d), generator=gen))
+    m = _bf16(torch.randn((n, d), generator=gen))
+    wx, wn = _bf16(torch.randn((O, d), generator=gen) / d ** 0.5), _bf16(torch.randn((O, d), generator=gen) / d ** 0.5)
+    ids = torch.randint(0, n + 99, (n,), generator=gen)
+    pad = lambda t: g.ops.pad_table(t.float(), torch.bfloat16)[0][:, :t.shape[1]]
+    want = torch.relu(torch.cat([table[ids].double() @ wx.double().t(), m.double() @ wn.double().t()], dim=1))
+    got = g.ops.linear([dict(a=pad(table), ids=ids.cuda(), w=pad(wx), col0=0), dict(a=pad(m), w=pad(wn), col0=O)], n,
+                       act='relu', out_dtype=torch.float32, exact=False)
+    assert got.shape == (n, 2 * O)
+    np.testing.assert_allclose(got.cpu().numpy(), want.numpy(), rtol=2e-4, atol=2e-4)
+
+
+def test_umma_wide_output_is_split(g):
+    """O = 512 (the pool MLP) does not fit one 256-column accumulator: the dispatcher issues column blocks."""
+    n, d, O = 1500, 64, 512
+    gen = torch.Generator().manual_seed(3)
+    a, w, b = _bf16(torch.randn((n, d), generator=gen)), _bf16(torch.randn((O, d), generator=gen) / 8), torch.randn((O,), generator=gen)
+    pad = lambda t: g.ops.pad_table(t.float(), torch.bfloat16)[0][:, :t.shape[1]]
+    want = torch.relu(a.double() @ w.double().t() + b.double())
+    got = g.ops.linear([dict(a=pad(a), w=pad(w), bias=b.cuda())], n, act='relu', exact=False)
+    np.testing.assert_allclose(got.cpu().numpy(), want.numpy(), rtol=2e-4, atol=2e-4)

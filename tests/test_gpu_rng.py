@@ -102,3 +102,16 @@ def test_permutation(g, n):
     r, rs = g.DeviceMT19937(123), np.random.RandomState(123)
     assert np.array_equal(r.permutation(n).cpu().numpy(), rs.permutation(np.arange(n)))
     assert np.array_equal(g.ops.u32_to_numpy(r.raw(5)), np.frombuffer(rs.bytes(20), dtype='<u4'))
+
+
+def test_lane_parallel_refill_matches_numpy(g):
+    """Big requests go through the jump-ahead lane refill (32 lanes x 256 blocks): still the same stream."""
+    r, rs = g.DeviceMT19937(2024), np.random.RandomState(2024)
+    got = g.ops.u32_to_numpy(r.raw(7000000))                       # > one 5.1 M-word lane refill
+    assert np.array_equal(got, np.frombuffer(rs.bytes(28000000), dtype='<u4'))
+    for hi, count in ((20000, 2252800), (129, 1000000), (20000, 204800)):
+        got = g.ops.u32_to_numpy(r.randint(hi, count)).astype(np.int64)
+        assert np.array_equal(got, rs.choice(hi, count)), (hi, count)
+    st, want = r.get_state(), rs.get_state()
+    assert np.array_equal(st[1], want[1]) and st[2] == want[2]
+    r.check()
