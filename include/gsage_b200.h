@@ -152,6 +152,8 @@ typedef struct gsage_linear_seg {
     const void* w_dev; int w_dtype; int64_t ldw; int d; int O;               /* W (O x d)                    */
     const float* bias_dev;                                                   /* O floats or NULL             */
     int64_t col0;                                                            /* output column offset         */
+    int reduce_S;   /* <= 1: A row r = A[ids[r]].  S > 1: A row r = mean_j A[ids[r*S + j]] -- the neighbour gather+mean
+                       (nn_modules.py:197-198) fused into the projection's operand load; the mean never touches HBM */
 } gsage_linear_seg;
 
 /* up to two segments writing disjoint column ranges of one output: the "concat-with-self" of

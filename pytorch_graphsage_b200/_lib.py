@@ -24,7 +24,7 @@ c_p = C.c_void_p
 class LinearSeg(C.Structure):
     _fields_ = [('a_dev', c_p), ('a_dtype', C.c_int), ('lda', c_i64), ('ids_dev', c_p),
                 ('w_dev', c_p), ('w_dtype', C.c_int), ('ldw', c_i64), ('d', C.c_int), ('O', C.c_int),
-                ('bias_dev', c_p), ('col0', c_i64)]
+                ('bias_dev', c_p), ('col0', c_i64), ('reduce_S', C.c_int)]
 
 
 class EngineConfig(C.Structure):

@@ -136,6 +136,27 @@ static int apply_aggregator(gsage_engine* e, int layer, const RowSrc& x, const R
     const int64_t ldm = pad_to(d, 16 / (int64_t)dtype_size(T) * 2);
     switch (e->cfg.aggregator) {
     case GSAGE_AGG_MEAN: {
+        if (T == GSAGE_BF16 && e->w_x[layer].dtype == GSAGE_BF16) {
+            // one kernel: gather self rows + gather-and-mean the S neighbour rows in the loader warps, both
+            // projections on tcgen05, activation in the epilogue -- the aggregated rows never exist in HBM
+            LinearParams P;
+            P.n_segs = 2; P.n = n; P.act = act; P.out = out; P.out_dtype = out_dtype; P.ld_out = ld_out;
+            P.seg[0] = LinearSeg{x.base, x.dtype, x.ld, x.ids, e->w_x[layer].p, GSAGE_BF16, e->w_x[layer].ld, d, O, nullptr, 0};
+            P.seg[1] = LinearSeg{nb.base, nb.dtype, nb.ld, nb.ids, e->w_n[layer].p, GSAGE_BF16, e->w_n[layer].ld, d, O, nullptr, (int64_t)O};
+            P.seg[1].S = S;
+            if (linear_umma_eligible(P)) {
+                const int p_f = e->prof.begin(GSAGE_PROF_REDUCE, s);
+                const int st = linear_umma_launch(P, s);
+                e->prof.end(p_f, s);
+                if (p_f >= 0) {
+                    const double es_in = (double)dtype_size(nb.dtype), es_out = (double)dtype_size(out_dtype);
+                    e->prof.bytes[GSAGE_PROF_REDUCE] += (double)n * ((double)S * d * es_in + (nb.ids ? 8.0 * S : 0.0) + d * es_in +
+                                                                     (x.ids ? 8.0 : 0.0) + 2.0 * O * es_out);
+                    e->prof.bytes[GSAGE_PROF_PROJECT] += 4.0 * (double)n * d * O;
+                }
+                return st;
+            }
+        }
         const int p_red = e->prof.begin(GSAGE_PROF_REDUCE, s);
         GS_TRY(gather_reduce_launch(nb.base, nb.dtype, nb.ld, nb.table_rows, d, nb.ids, n, S, GSAGE_RED_MEAN, nullptr, e->M, T, ldm, s));
         e->prof.end(p_red, s);

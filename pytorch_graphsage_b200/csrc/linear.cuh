@@ -8,6 +8,7 @@ struct LinearSeg {
     const void* a; int a_dtype; int64_t lda; const int64_t* ids;
     const void* w; int w_dtype; int64_t ldw; int d; int O;
     const float* bias; int64_t col0;
+    int S = 1;      // > 1: A row r = mean_j A[ids[r*S + j]] (fused gather+mean; tensor-core kernel only)
 };
 
 struct LinearParams {

@@ -38,10 +38,12 @@ __global__ void __launch_bounds__(256) linear_simt_kernel(LinearParams P) {
     // loader mapping: 64 rows x 16 k = 1024 elements, 4 per thread (same k-quad)
     const int lrow = tid >> 2, lk = (tid & 3) * 4;
     int64_t a_row = -1;
+    const int S = sg.S > 1 ? sg.S : 1;
     if (row0 + lrow < P.n) {
         a_row = row0 + lrow;
-        if (sg.ids) a_row = sg.ids[a_row];
+        if (S == 1 && sg.ids) a_row = sg.ids[a_row];
     }
+    const float inv_S = 1.0f / (float)S;
     const int w_row = col0 + lrow;
 
     float acc[4][4];
@@ -55,7 +57,17 @@ __global__ void __launch_bounds__(256) linear_simt_kernel(LinearParams P) {
         for (int q = 0; q < 4; ++q) {
             const int k = k0 + lk + q;
             float a = 0.0f, w = 0.0f;
-            if (a_row >= 0 && k < sg.d) a = load_any(sg.a, sg.a_dtype, a_row * sg.lda + k);
+            if (a_row >= 0 && k < sg.d) {
+                if (S == 1) {
+                    a = load_any(sg.a, sg.a_dtype, a_row * sg.lda + k);
+                } else {                                       // fused gather+mean operand (fp32, same order as gather_reduce)
+                    for (int j = 0; j < S; ++j) {
+                        const int64_t q = a_row * S + j;
+                        a += load_any(sg.a, sg.a_dtype, (sg.ids ? sg.ids[q] : q) * sg.lda + k);
+                    }
+                    a *= inv_S;
+                }
+            }
             if (w_row < sg.O && k < sg.d) w = load_any(sg.w, sg.w_dtype, (int64_t)w_row * sg.ldw + k);
             As[lk + q][lrow] = a;
             Ws[lk + q][lrow] = w;
@@ -119,7 +131,7 @@ extern "C" int gsage_linear(const gsage_linear_seg* segs, int n_segs, int64_t n,
                      g.col0 + g.O <= ld_out, "linear: bad segment %d", i);
         P.seg[i].a = g.a_dev; P.seg[i].a_dtype = g.a_dtype; P.seg[i].lda = g.lda; P.seg[i].ids = g.ids_dev;
         P.seg[i].w = g.w_dev; P.seg[i].w_dtype = g.w_dtype; P.seg[i].ldw = g.ldw; P.seg[i].d = g.d; P.seg[i].O = g.O;
-        P.seg[i].bias = g.bias_dev; P.seg[i].col0 = g.col0;
+        P.seg[i].bias = g.bias_dev; P.seg[i].col0 = g.col0; P.seg[i].S = g.reduce_S > 1 ? g.reduce_S : 1;
     }
     if (n == 0) return GSAGE_OK;
     return linear_dispatch(P, exact, as_stream(stream));

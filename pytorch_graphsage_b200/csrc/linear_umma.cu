@@ -8,10 +8,14 @@
 //   * persistent CTAs (one per SM), 128-row output tiles, 9 warps with fixed roles:
 //       warps 0-3  epilogue   TMEM -> registers (tcgen05.ld 32x32b) -> bias/activation -> bf16/fp32 -> HBM
 //       warp  4    MMA issue  one elected lane issues tcgen05.mma (M=128, N=O, K=16) + tcgen05.commit
-//       warps 5-8  loaders    gather the A rows *by id* (self rows come straight from the feature table)
-//                             and the W rows with 16-byte cp.async into 128B-swizzled K-major smem tiles
+//       warps 5-12 loaders    four independent groups of 64 threads, each filling whole smem stages: A rows are
+//                             gathered *by id* with 16-byte read-only loads -- and, for a segment with S > 1,
+//                             the S neighbour rows of every parent are summed in fp32 registers on the way
+//                             (the fused gather+mean: the aggregated rows never exist in HBM) -- then stored
+//                             as bf16 into the 128B-swizzled K-major tile; W rows likewise
 //   * smem ring of (A 128x64, W Ox64) bf16 chunk pairs; full/empty mbarriers; the gather is free-form because
-//     the loader, not TMA, owns the smem layout (TMA cannot gather arbitrary rows);
+//     the loader, not TMA, owns the smem layout (plain stores + one fence.proxy.async per thread per stage:
+//     cp.async would need the same fence, which drains every copy in flight and serialises the ring);
 //   * two TMEM accumulator buffers (2 x 256 fp32 columns = all 512 columns): the epilogue of tile i overlaps
 //     the loads and MMAs of tile i+1.
 // Every mbarrier wait is bounded (a stuck pipeline traps instead of hanging the GPU).
@@ -22,7 +26,9 @@ namespace gsage {
 
 static constexpr int UM = 128;            // rows per tile (UMMA M)
 static constexpr int UK = 64;             // bf16 elements per smem chunk row = 128 bytes (one swizzle atom row)
-static constexpr int kEpiWarps = 4, kLoadWarps = 4;
+static constexpr int kEpiWarps = 4;
+static constexpr int kLoadGroups = 4, kGroupThreads = 64;           // loader groups fill different stages concurrently
+static constexpr int kLoadWarps = kLoadGroups * kGroupThreads / 32;
 static constexpr int kThreads = 32 * (kEpiWarps + 1 + kLoadWarps);
 static constexpr int kABytes = UM * UK * 2;                   // 16 KB
 static constexpr int kMaxO = 256;
@@ -33,6 +39,9 @@ struct UmmaSeg {
     const float* bias; int64_t col0;
     int kchunks;          // ceil(d / 64)
     int acc_col;          // first TMEM column of this segment's accumulator inside a buffer
+    int S;                // rows reduced into one A row (1 = plain gather; > 1 = fused gather+mean)
+    float scale;          // 1/S for the mean
+    int kvalid;           // d rounded up to a whole 16-byte chunk: elements that may be read
 };
 
 struct UmmaParams {
@@ -126,7 +135,7 @@ __global__ void __launch_bounds__(kThreads, 1) linear_umma_kernel(const UmmaPara
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < P.stages; ++s) { mbar_init(full_bar(s), 32 * kLoadWarps); mbar_init(empty_bar(s), 1); }
+        for (int s = 0; s < P.stages; ++s) { mbar_init(full_bar(s), kGroupThreads); mbar_init(empty_bar(s), 1); }
         for (int b = 0; b < 2; ++b) { mbar_init(tfull_bar(b), 1); mbar_init(tempty_bar(b), 32 * kEpiWarps); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -226,60 +235,78 @@ __global__ void __launch_bounds__(kThreads, 1) linear_umma_kernel(const UmmaPara
         }
     } else {
         // =========================== LOADERS ===========================
-        const int t = threadIdx.x - 32 * (kEpiWarps + 1);    // 0..127
-        const int sub_row = t >> 3, chunk = t & 7;            // 8 threads cover one 128-byte row segment
-        int item = 0;
-        const int total_items = ((P.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x) * items_per_tile;
-        constexpr int LAG = 2;                                 // cp.async groups in flight before the oldest is published
-        int issued = 0;
-        int tile = blockIdx.x, s = 0, kc = 0;
-        const __nv_bfloat16* a_rows[8];
-        bool rows_ready = false;
-        for (int step = 0; step < total_items + LAG; ++step) {
-            if (step < total_items) {
-                const UmmaSeg& sg = P.seg[s];
-                if (!rows_ready) {                                // row pointers of this (tile, segment): gathered by id
+        // group g fills items g, g+G, g+2G, ... (an item = one (tile, segment, k-chunk) stage); the MMA warp consumes
+        // items in order.  Thread (rg, c): 16-byte chunk c of rows rg, rg+8, ... of the 128-row tile.
+        const int lt = (threadIdx.x - 32 * (kEpiWarps + 1)) % kGroupThreads;
+        const int group = (threadIdx.x - 32 * (kEpiWarps + 1)) / kGroupThreads;
+        const int rg = lt >> 3, c = lt & 7;
+        const int my_tiles = (P.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+        const int total_items = my_tiles * items_per_tile;
+        for (int item = group; item < total_items; item += kLoadGroups) {
+            const int tile = blockIdx.x + (item / items_per_tile) * gridDim.x;
+            int rem = item % items_per_tile, sidx = 0;
+            while (rem >= P.seg[sidx].kchunks) { rem -= P.seg[sidx].kchunks; ++sidx; }
+            const UmmaSeg& sg = P.seg[sidx];
+            const int k0 = rem * UK + c * 8;                       // first element of this thread's chunk
+            const bool live_k = k0 < sg.kvalid;
+            const int stage = item % P.stages;
+            mbar_wait(empty_bar(stage), ((item / P.stages) & 1) ^ 1, P.err);
+            uint8_t* sa = smem + (size_t)stage * P.stage_bytes;
+            const __nv_bfloat16* abase = sg.a + k0;
+            const int S = sg.S;
+            // ---- A: 16 row slots per thread, two at a time so 2 x 8 independent 16-byte loads are in flight ----
+#pragma unroll 1
+            for (int i = 0; i < UM / 8; i += 2) {
+                const int r0 = rg + 8 * i, r1 = r0 + 8;
+                const int64_t row0 = (int64_t)tile * UM + r0, row1 = row0 + 8;
+                const bool ok0 = live_k && row0 < P.n, ok1 = live_k && row1 < P.n;
+                uint4 out0 = make_uint4(0, 0, 0, 0), out1 = make_uint4(0, 0, 0, 0);
+                if (S == 1) {
+                    if (ok0) out0 = ldg_nc_v4(abase + (sg.ids ? sg.ids[row0] : row0) * sg.lda);
+                    if (ok1) out1 = ldg_nc_v4(abase + (sg.ids ? sg.ids[row1] : row1) * sg.lda);
+                } else {
+                    float acc0[8], acc1[8];
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const int64_t r = (int64_t)tile * UM + i * 16 + sub_row;
-                        a_rows[i] = nullptr;
-                        if (r < P.n) {
-                            const int64_t src = sg.ids ? sg.ids[r] : r;
-                            a_rows[i] = sg.a + src * sg.lda;
+                    for (int e = 0; e < 8; ++e) { acc0[e] = 0.0f; acc1[e] = 0.0f; }
+                    for (int j0 = 0; j0 < S; j0 += 8) {
+                        uint4 v0[8], v1[8];
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) {
+                            const bool in = j0 + u < S;
+                            v0[u] = make_uint4(0, 0, 0, 0); v1[u] = make_uint4(0, 0, 0, 0);
+                            if (ok0 && in) { const int64_t q = row0 * S + j0 + u; v0[u] = ldg_nc_v4(abase + (sg.ids ? sg.ids[q] : q) * sg.lda); }
+                            if (ok1 && in) { const int64_t q = row1 * S + j0 + u; v1[u] = ldg_nc_v4(abase + (sg.ids ? sg.ids[q] : q) * sg.lda); }
+                        }
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) {
+                            float f[8];
+                            ElemTraits<__nv_bfloat16>::unpack(v0[u], f);
+#pragma unroll
+                            for (int e = 0; e < 8; ++e) acc0[e] += f[e];
+                            ElemTraits<__nv_bfloat16>::unpack(v1[u], f);
+#pragma unroll
+                            for (int e = 0; e < 8; ++e) acc1[e] += f[e];
                         }
                     }
-                    rows_ready = true;
-                }
-                const int stage = item % P.stages;
-                mbar_wait(empty_bar(stage), ((item / P.stages) & 1) ^ 1, P.err);
-                uint8_t* sa = smem + (size_t)stage * P.stage_bytes;
-                const int k0 = kc * UK + chunk * 8;               // first element of this thread's 16-byte chunk
-                const uint32_t kbytes = (k0 < sg.d) ? (uint32_t)min(16, (sg.d - k0) * 2) : 0u;
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const int r = i * 16 + sub_row;
-                    const uint32_t dst = smem_u32(sa + r * 128 + ((chunk ^ (r & 7)) << 4));
-                    const bool live = a_rows[i] != nullptr && kbytes;
-                    cp_async16(dst, live ? (const void*)(a_rows[i] + k0) : (const void*)sg.a, live ? kbytes : 0u);
+                    for (int e = 0; e < 8; ++e) { acc0[e] *= sg.scale; acc1[e] *= sg.scale; }
+                    out0 = ElemTraits<__nv_bfloat16>::pack(acc0);
+                    out1 = ElemTraits<__nv_bfloat16>::pack(acc1);
                 }
-                uint8_t* sw = sa + kABytes;
-                for (int r = sub_row; r < sg.O; r += 16) {
-                    const uint32_t dst = smem_u32(sw + r * 128 + ((chunk ^ (r & 7)) << 4));
-                    cp_async16(dst, kbytes ? (const void*)(sg.w + (int64_t)r * sg.ldw + k0) : (const void*)sg.w, kbytes);
-                }
-                ++item;
-                if (++kc == sg.kchunks) {
-                    kc = 0; rows_ready = false;
-                    if (++s == P.n_segs) { s = 0; tile += gridDim.x; }
-                }
+                *reinterpret_cast<uint4*>(sa + r0 * 128 + ((c ^ (r0 & 7)) << 4)) = out0;
+                *reinterpret_cast<uint4*>(sa + r1 * 128 + ((c ^ (r1 & 7)) << 4)) = out1;
             }
-            cp_async_commit();
-            if (step >= LAG) {
-                cp_async_wait<LAG>();                             // the group issued LAG steps ago has landed
-                fence_proxy_async();                              // generic-proxy writes -> visible to the tensor core
-                mbar_arrive(full_bar(issued % P.stages));
-                ++issued;
+            // ---- W: O rows x this k-chunk (L2-resident after the first tile) ----
+            uint8_t* sw = sa + kABytes;
+            const __nv_bfloat16* wbase = sg.w + k0;
+#pragma unroll 4
+            for (int r = rg; r < sg.O; r += 8) {
+                uint4 v = make_uint4(0, 0, 0, 0);
+                if (live_k) v = ldg_nc_v4(wbase + (int64_t)r * sg.ldw);
+                *reinterpret_cast<uint4*>(sw + r * 128 + ((c ^ (r & 7)) << 4)) = v;
             }
+            fence_proxy_async();                                  // generic-proxy stores -> visible to the tensor core
+            mbar_arrive(full_bar(stage));
         }
     }
 
@@ -321,6 +348,9 @@ int linear_umma_launch(const LinearParams& P, cudaStream_t s) {
         U.seg[i].bias = g.bias; U.seg[i].col0 = g.col0;
         U.seg[i].kchunks = (g.d + UK - 1) / UK;
         U.seg[i].acc_col = col;
+        U.seg[i].S = g.S > 1 ? g.S : 1;
+        U.seg[i].scale = g.S > 1 ? 1.0f / (float)g.S : 1.0f;
+        U.seg[i].kvalid = (g.d + 7) / 8 * 8;
         col += (g.O + 31) / 32 * 32;
         maxO = g.O > maxO ? g.O : maxO;
     }

@@ -101,7 +101,8 @@ def gather_rows(table, ids, d=None, out_dtype=None):
 
 
 def linear(segments, n, act=None, out=None, out_dtype=torch.float32, exact=True):
-    """segments: list of dicts(a=, w=, ids=None, bias=None, col0=0, d=None).  One launch, <= 2 column ranges."""
+    """segments: list of dicts(a=, w=, ids=None, bias=None, col0=0, d=None, S=1).  One launch, <= 2 column ranges.
+    S > 1: row r of that segment's operand is mean_j a[ids[r*S + j]] (fused gather+mean)."""
     segs = (_lib.LinearSeg * len(segments))()
     width = 0
     for i, sgm in enumerate(segments):
@@ -111,7 +112,7 @@ def linear(segments, n, act=None, out=None, out_dtype=torch.float32, exact=True)
         assert w.is_cuda and w.dim() == 2 and w.stride(1) == 1
         bias = sgm.get('bias')
         segs[i] = _lib.LinearSeg(ptr(a), dt(a), _rows2d(a), _ids_arg(sgm.get('ids')), ptr(w), dt(w), _rows2d(w), d,
-                                 w.shape[0], ptr(bias), sgm.get('col0', 0))
+                                 w.shape[0], ptr(bias), sgm.get('col0', 0), int(sgm.get('S', 1)))
         width = max(width, sgm.get('col0', 0) + w.shape[0])
     if out is None:
         out = torch.empty((n, width), dtype=out_dtype, device=segments[0]['a'].device)

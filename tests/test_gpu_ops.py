@@ -180,3 +180,41 @@ def test_umma_wide_output_is_split(g):
     want = torch.relu(a.double() @ w.double().t() + b.double())
     got = g.ops.linear([dict(a=pad(a), w=pad(w), bias=b.cuda())], n, act='relu', exact=False)
     np.testing.assert_allclose(got.cpu().numpy(), want.numpy(), rtol=2e-4, atol=2e-4)
+
+
+@pytest.mark.parametrize('n,d,O,S', [(300, 602, 128, 10), (129, 64, 64, 25), (1000, 256, 128, 3), (50, 100, 16, 40)])
+def test_fused_gather_mean_projection(g, n, d, O, S):
+    """[fc_x(table[ids]) | fc_neib(mean_j table[nb_ids])]: the gather+mean happens inside the projection kernel's
+    operand load (tcgen05 path, bf16) -- compared with fp64 on the same bf16 operands, and with the fp32 FFMA path."""
+    gen = torch.Generator().manual_seed(n + S)
+    rows = 2000
+    table = _bf16(torch.randn((rows, d), generator=gen))
+    wx, wn = _bf16(torch.randn((O, d), generator=gen) / d ** 0.5), _bf16(torch.randn((O, d), generator=gen) / d ** 0.5)
+    ids = torch.randint(0, rows, (n,), generator=gen)
+    nb = torch.randint(0, rows, (n * S,), generator=gen)
+    pad = lambda t: g.ops.pad_table(t.float(), torch.bfloat16)[0][:, :t.shape[1]]
+    mean = table[nb].float().view(n, S, d).sum(dim=1) * (1.0 / S)               # fp32 sum in j order, like the kernel
+    mean_bf16 = mean.to(torch.bfloat16)                                         # the kernel rounds the mean to bf16 in smem
+    want = torch.relu(torch.cat([table[ids].double() @ wx.double().t(), mean_bf16.double() @ wn.double().t()], dim=1))
+    segs = [dict(a=pad(table), ids=ids.cuda(), w=pad(wx), col0=0), dict(a=pad(table), ids=nb.cuda(), w=pad(wn), col0=O, S=S)]
+    got = g.ops.linear(segs, n, act='relu', out_dtype=torch.float32, exact=False)
+    # bf16 rounding of the mean can flip by one ulp vs the torch emulation (summation order): 2^-8 relative on that operand
+    np.testing.assert_allclose(got.cpu().numpy(), want.numpy(), rtol=2e-3, atol=2e-3)
+    exact = torch.relu(torch.cat([table[ids].double() @ wx.double().t(),
+                                  table[nb].double().view(n, S, d).mean(dim=1) @ wn.double().t()], dim=1))
+    got32 = g.ops.linear(segs, n, act='relu', out_dtype=torch.float32, exact=True)   # FFMA path: mean kept in fp32
+    np.testing.assert_allclose(got32.cpu().numpy(), exact.numpy(), rtol=1e-4, atol=1e-5)
+
+
+def test_fused_contiguous_mean_projection(g):
+    """ids=None, S>1: the layer-2 case -- neighbours are rows r*S+j of the previous layer's output."""
+    n, d, O, S = 200, 256, 128, 25
+    gen = torch.Generator().manual_seed(8)
+    h = _bf16(torch.randn((n + n * S, d), generator=gen))
+    wx, wn = _bf16(torch.randn((O, d), generator=gen) / 16), _bf16(torch.randn((O, d), generator=gen) / 16)
+    pad = lambda t: g.ops.pad_table(t.float(), torch.bfloat16)[0][:, :t.shape[1]]
+    hd = pad(h)
+    mean = (h[n:].float().view(n, S, d).sum(dim=1) * (1.0 / S)).to(torch.bfloat16)
+    want = torch.cat([h[:n].double() @ wx.double().t(), mean.double() @ wn.double().t()], dim=1)
+    got = g.ops.linear([dict(a=hd[:n], w=pad(wx), col0=0), dict(a=hd[n:], w=pad(wn), col0=O, S=S)], n, exact=False)
+    np.testing.assert_allclose(got.cpu().numpy(), want.numpy(), rtol=2e-3, atol=2e-3)
