@@ -16,6 +16,7 @@
 
 #include <vector>
 #include <algorithm>
+#include <stdlib.h>
 
 namespace gsage {
 int sample_sparse_launch(gsage_graph* g, const int64_t* ids, int64_t n, int S, const uint32_t* sel, int64_t* out,
@@ -101,6 +102,7 @@ struct gsage_engine {
     // weights as the kernels read them (fp32 originals, or bf16 copies when compute dtype is bf16)
     char* wb = nullptr; int64_t wb_bytes = 0;
     WRef w_x[2], w_n[2], w_mlp[2], w_att1[2];
+    bool fuse_mean = false;   // GSAGE_FUSE_MEAN=1: route the mean aggregator through the one-kernel fused layer (experimental)
 };
 
 static int64_t pad_to(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
@@ -136,7 +138,7 @@ static int apply_aggregator(gsage_engine* e, int layer, const RowSrc& x, const R
     const int64_t ldm = pad_to(d, 16 / (int64_t)dtype_size(T) * 2);
     switch (e->cfg.aggregator) {
     case GSAGE_AGG_MEAN: {
-        if (T == GSAGE_BF16 && e->w_x[layer].dtype == GSAGE_BF16) {
+        if (T == GSAGE_BF16 && e->w_x[layer].dtype == GSAGE_BF16 && e->fuse_mean) {
             // one kernel: gather self rows + gather-and-mean the S neighbour rows in the loader warps, both
             // projections on tcgen05, activation in the epilogue -- the aggregated rows never exist in HBM
             LinearParams P;
@@ -219,6 +221,7 @@ int gsage_engine_create(const gsage_engine_config* cfg, gsage_engine** out) {
     gsage_engine* e = new gsage_engine();
     e->cfg = *cfg;
     e->T = cfg->compute_dtype;
+    if (const char* f = getenv("GSAGE_FUSE_MEAN")) e->fuse_mean = atoi(f) != 0;
     const int64_t es = (int64_t)dtype_size(e->T);
     const int64_t vec = 16 / es;
     switch (cfg->prep) {

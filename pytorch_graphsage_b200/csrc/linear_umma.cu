@@ -254,17 +254,32 @@ __global__ void __launch_bounds__(kThreads, 1) linear_umma_kernel(const UmmaPara
             uint8_t* sa = smem + (size_t)stage * P.stage_bytes;
             const __nv_bfloat16* abase = sg.a + k0;
             const int S = sg.S;
-            // ---- A: 16 row slots per thread, two at a time so 2 x 8 independent 16-byte loads are in flight ----
+            if (S == 1) {
+                // ---- A, plain gather: all 16 row slots of this thread in flight at once ----
+                uint4 v[UM / 8];
+#pragma unroll
+                for (int i = 0; i < UM / 8; ++i) {
+                    const int64_t row = (int64_t)tile * UM + rg + 8 * i;
+                    v[i] = make_uint4(0, 0, 0, 0);
+                    if (live_k && row < P.n) v[i] = ldg_nc_v4(abase + (sg.ids ? sg.ids[row] : row) * sg.lda);
+                }
+#pragma unroll
+                for (int i = 0; i < UM / 8; ++i) {
+                    const int r = rg + 8 * i;
+                    *reinterpret_cast<uint4*>(sa + r * 128 + ((c ^ (r & 7)) << 4)) = v[i];
+                }
+            } else {
+            // ---- A, fused gather+mean: two row slots at a time so 2 x 8 independent 16-byte loads are in flight ----
+            // (correct but latency-bound: 256 loader threads cannot keep enough loads in flight through registers;
+            //  the engine uses the standalone gather_reduce kernel + this kernel with S == 1 until the TMA-staged
+            //  variant lands -- see DESIGN.md)
 #pragma unroll 1
             for (int i = 0; i < UM / 8; i += 2) {
                 const int r0 = rg + 8 * i, r1 = r0 + 8;
                 const int64_t row0 = (int64_t)tile * UM + r0, row1 = row0 + 8;
                 const bool ok0 = live_k && row0 < P.n, ok1 = live_k && row1 < P.n;
                 uint4 out0 = make_uint4(0, 0, 0, 0), out1 = make_uint4(0, 0, 0, 0);
-                if (S == 1) {
-                    if (ok0) out0 = ldg_nc_v4(abase + (sg.ids ? sg.ids[row0] : row0) * sg.lda);
-                    if (ok1) out1 = ldg_nc_v4(abase + (sg.ids ? sg.ids[row1] : row1) * sg.lda);
-                } else {
+                {
                     float acc0[8], acc1[8];
 #pragma unroll
                     for (int e = 0; e < 8; ++e) { acc0[e] = 0.0f; acc1[e] = 0.0f; }
@@ -296,14 +311,23 @@ __global__ void __launch_bounds__(kThreads, 1) linear_umma_kernel(const UmmaPara
                 *reinterpret_cast<uint4*>(sa + r0 * 128 + ((c ^ (r0 & 7)) << 4)) = out0;
                 *reinterpret_cast<uint4*>(sa + r1 * 128 + ((c ^ (r1 & 7)) << 4)) = out1;
             }
+            }
             // ---- W: O rows x this k-chunk (L2-resident after the first tile) ----
             uint8_t* sw = sa + kABytes;
             const __nv_bfloat16* wbase = sg.w + k0;
-#pragma unroll 4
-            for (int r = rg; r < sg.O; r += 8) {
-                uint4 v = make_uint4(0, 0, 0, 0);
-                if (live_k) v = ldg_nc_v4(wbase + (int64_t)r * sg.ldw);
-                *reinterpret_cast<uint4*>(sw + r * 128 + ((c ^ (r & 7)) << 4)) = v;
+            for (int rb = rg; rb < sg.O; rb += 64) {              // 8 row slots per batch: 8 loads in flight, then 8 stores
+                uint4 wv[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int r = rb + 8 * i;
+                    wv[i] = make_uint4(0, 0, 0, 0);
+                    if (live_k && r < sg.O) wv[i] = ldg_nc_v4(wbase + (int64_t)r * sg.ldw);
+                }
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int r = rb + 8 * i;
+                    if (r < sg.O) *reinterpret_cast<uint4*>(sw + r * 128 + ((c ^ (r & 7)) << 4)) = wv[i];
+                }
             }
             fence_proxy_async();                                  // generic-proxy stores -> visible to the tensor core
             mbar_arrive(full_bar(stage));

@@ -356,8 +356,14 @@ static int rng_init_lanes(gsage_rng* r) {
     return GSAGE_OK;
 }
 
-// make sure stream words [.., upto) exist in the ring without overwriting anything still needed
-int rng_ensure(gsage_rng* r, int64_t upto, cudaStream_t s) {
+// Enqueue generation of stream words up to (at least) `upto` on the rng's own side stream.  The refill first waits
+// for everything already queued on the caller's stream (those kernels may still read ring slots the refill is
+// about to recycle), then runs concurrently with whatever the caller queues next -- the generator is independent
+// of the graph data, so it overlaps the HBM-bound gather/aggregate kernels of the same step.
+// `may_sync`: allowed to read the true cursor back (synchronises the caller's stream) when the host bounds are too
+// loose to prove the ring has room; a prefetch passes false and simply gives up.
+static int rng_generate(gsage_rng* r, int64_t upto, cudaStream_t s, bool may_sync) {
+    bool fenced = false;
     while (upto > r->gen_end) {
         const int64_t need = ceil_div(upto - r->gen_end, kN);
         const int64_t lane_refill = (int64_t)r->lanes * r->lane_blocks;
@@ -365,6 +371,7 @@ int rng_ensure(gsage_rng* r, int64_t upto, cudaStream_t s) {
         int64_t blocks = use_lanes ? lane_refill : std::max<int64_t>(need, r->prefetch_blocks);
         // words from (cursor_lb - 624) must survive: the block under the cursor is the numpy `key`
         if (r->gen_end + blocks * kN - (r->cursor_lb - kN) > r->cap) {
+            if (!may_sync) return GSAGE_OK;
             GS_TRY(rng_resync(r, s));
             const int64_t room = (r->cap - (r->gen_end - (r->cursor_lb - kN))) / kN;
             if (room < need) {
@@ -374,22 +381,44 @@ int rng_ensure(gsage_rng* r, int64_t upto, cudaStream_t s) {
             }
             if (blocks > room) blocks = use_lanes ? -1 : room;
         }
+        if (!fenced) {
+            GS_CUDA(cudaEventRecord(r->ev_main, s));
+            GS_CUDA(cudaStreamWaitEvent(r->side, r->ev_main, 0));
+            fenced = true;
+        }
         if (use_lanes && blocks == lane_refill) {
             GS_TRY(rng_init_lanes(r));
-            mt_jump_kernel<<<dim3(r->lanes - 1, kJumpSlices), 256, sizeof(uint32_t) * kSeqWords, s>>>(
+            mt_jump_kernel<<<dim3(r->lanes - 1, kJumpSlices), 256, sizeof(uint32_t) * kSeqWords, r->side>>>(
                 r->ring, (uint64_t)(r->cap - 1), r->gen_end, r->polys, r->partial);
             GS_LAUNCHED();
-            mt_generate_lanes_kernel<<<r->lanes, 256, 0, s>>>(r->ring, (uint64_t)(r->cap - 1), r->gen_end, r->lane_blocks,
-                                                              r->partial);
+            mt_generate_lanes_kernel<<<r->lanes, 256, 0, r->side>>>(r->ring, (uint64_t)(r->cap - 1), r->gen_end, r->lane_blocks,
+                                                                    r->partial);
             GS_LAUNCHED();
         } else {
             if (blocks < 0) blocks = std::min<int64_t>(need, (r->cap - (r->gen_end - (r->cursor_lb - kN))) / kN);
-            mt_generate_kernel<<<1, 256, 0, s>>>(r->ring, (uint64_t)(r->cap - 1), r->gen_end, (int)blocks);
+            mt_generate_kernel<<<1, 256, 0, r->side>>>(r->ring, (uint64_t)(r->cap - 1), r->gen_end, (int)blocks);
             GS_LAUNCHED();
         }
         r->gen_end += blocks * kN;
     }
+    if (fenced) GS_CUDA(cudaEventRecord(r->ev_refill, r->side));
     return GSAGE_OK;
+}
+
+// make sure stream words [.., upto) exist in the ring AND are visible to kernels queued on `s` from now on
+int rng_ensure(gsage_rng* r, int64_t upto, cudaStream_t s) {
+    GS_TRY(rng_generate(r, upto, s, true));
+    if (upto > r->gen_visible) {
+        GS_CUDA(cudaStreamWaitEvent(s, r->ev_refill, 0));       // ev_refill covers everything generated so far
+        r->gen_visible = r->gen_end;
+    }
+    return GSAGE_OK;
+}
+
+// top the ring up for the next calls without making the caller's stream wait for it
+static int rng_prefetch(gsage_rng* r, cudaStream_t s) {
+    const int64_t ahead = r->max_window + r->max_window / 4 + kN;
+    return rng_generate(r, r->cursor_ub + ahead, s, false);
 }
 
 // window of raw words that holds `count` accepted draws with overwhelming probability (12 sigma)
@@ -438,8 +467,9 @@ static int rng_draw(gsage_rng* r, uint32_t hi, int64_t count, uint32_t* out, cud
         r->parity ^= 1;
         r->cursor_lb += n;
         r->cursor_ub += window;
+        r->max_window = std::max(r->max_window, window);
     }
-    return GSAGE_OK;
+    return rng_prefetch(r, s);
 }
 
 int rng_randint_internal(gsage_rng* r, uint32_t hi, int64_t count, uint32_t* out, cudaStream_t s) {
@@ -474,6 +504,13 @@ int gsage_rng_create(gsage_rng** out) {
         gsage_rng_destroy(r);
         return GSAGE_ERR_NOMEM;
     }
+    if (cudaStreamCreateWithFlags(&r->side, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&r->ev_main, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&r->ev_refill, cudaEventDisableTiming) != cudaSuccess) {
+        set_error("rng_create: stream / event creation failed");
+        gsage_rng_destroy(r);
+        return GSAGE_ERR_CUDA;
+    }
     *out = r;
     return gsage_rng_seed(r, 5489u, nullptr);
 }
@@ -482,13 +519,17 @@ void gsage_rng_destroy(gsage_rng* r) {
     if (!r) return;
     cudaFree(r->ring); cudaFree(r->cursor); cudaFree(r->err_flag); cudaFree(r->tile_count); cudaFree(r->tile_off);
     cudaFree(r->polys); cudaFree(r->partial);
+    if (r->side) { cudaStreamSynchronize(r->side); cudaStreamDestroy(r->side); }
+    if (r->ev_main) cudaEventDestroy(r->ev_main);
+    if (r->ev_refill) cudaEventDestroy(r->ev_refill);
     delete r;
 }
 
 int gsage_rng_set_state(gsage_rng* r, const uint32_t* key, int pos, void* stream) {
     GS_CHECK_ARG(r && key && pos >= 0 && pos <= kN, "rng_set_state: bad arguments (pos must be in [0, 624])");
     cudaStream_t s = as_stream(stream);
-    // the given key becomes stream block 0; earlier launches on this stream may still read the ring
+    // the given key becomes stream block 0; earlier launches (either stream) may still touch the ring
+    GS_CUDA(cudaStreamSynchronize(r->side));
     GS_CUDA(cudaStreamSynchronize(s));
     GS_CUDA(cudaMemcpyAsync(r->ring, key, sizeof(uint32_t) * kN, cudaMemcpyHostToDevice, s));
     const int64_t c[2] = {pos, pos};
@@ -496,6 +537,8 @@ int gsage_rng_set_state(gsage_rng* r, const uint32_t* key, int pos, void* stream
     GS_CUDA(cudaMemsetAsync(r->err_flag, 0, sizeof(int), s));
     GS_CUDA(cudaStreamSynchronize(s));                          // `key` / `c` are pageable host memory
     r->gen_end = kN;
+    r->gen_visible = kN;
+    r->max_window = 0;
     r->parity = 0;
     r->cursor_lb = r->cursor_ub = pos;
     r->origin = pos;

@@ -11,7 +11,11 @@ struct gsage_rng {
     int64_t* tile_off = nullptr;   // device scratch
     int tiles_cap = 0;
     int parity = 0;                // host: which cursor slot is current
-    int64_t gen_end = 0;           // host: words [.., gen_end) are generated
+    int64_t gen_end = 0;           // host: generation of words [.., gen_end) is queued (on `side`)
+    int64_t gen_visible = 0;       // host: words the caller's stream has already been ordered after
+    int64_t max_window = 0;        // host: largest look-ahead window requested since the last seed (prefetch size)
+    cudaStream_t side = nullptr;   // refills run here, overlapping the caller's compute
+    cudaEvent_t ev_main = nullptr, ev_refill = nullptr;
     int64_t cursor_lb = 0, cursor_ub = 0;   // host bounds on the device cursor
     int64_t origin = 0;            // cursor value at the last seed / set_state
     int64_t prefetch_blocks = 64;  // sequential refill: generate at least this many 624-word blocks
