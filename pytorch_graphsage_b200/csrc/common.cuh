@@ -65,10 +65,14 @@ int sm_count();   // cached cudaDevAttrMultiProcessorCount of the current device
 // 16-byte read-only load that does not pollute L1 (rows of the feature table are touched once per CTA)
 __device__ __forceinline__ uint4 ldg_nc_v4(const void* p) {
     uint4 r;
-    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
+    asm("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
                  : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
                  : "l"(p));
     return r;
+}
+
+__device__ __forceinline__ void st_shared_v4(uint32_t smem_addr, const uint4& v) {
+    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(smem_addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 
 __device__ __forceinline__ float bf16_lo(uint32_t u) { return __uint_as_float(u << 16); }

@@ -254,66 +254,79 @@ __global__ void __launch_bounds__(kThreads, 1) linear_umma_kernel(const UmmaPara
             uint8_t* sa = smem + (size_t)stage * P.stage_bytes;
             const __nv_bfloat16* abase = sg.a + k0;
             const int S = sg.S;
+            const uint32_t sa_u = smem_u32(sa);
             if (S == 1) {
-                // ---- A, plain gather: all 16 row slots of this thread in flight at once ----
-                uint4 v[UM / 8];
+                // ---- A, plain gather: ids first, then all 16 row slots of this thread in flight at once ----
+                int64_t src[UM / 8];
 #pragma unroll
                 for (int i = 0; i < UM / 8; ++i) {
                     const int64_t row = (int64_t)tile * UM + rg + 8 * i;
+                    src[i] = -1;
+                    if (live_k && row < P.n) src[i] = sg.ids ? __ldg(sg.ids + row) : row;
+                }
+                uint4 v[UM / 8];
+#pragma unroll
+                for (int i = 0; i < UM / 8; ++i) {
                     v[i] = make_uint4(0, 0, 0, 0);
-                    if (live_k && row < P.n) v[i] = ldg_nc_v4(abase + (sg.ids ? sg.ids[row] : row) * sg.lda);
+                    if (src[i] >= 0) v[i] = ldg_nc_v4(abase + src[i] * sg.lda);
                 }
 #pragma unroll
                 for (int i = 0; i < UM / 8; ++i) {
                     const int r = rg + 8 * i;
-                    *reinterpret_cast<uint4*>(sa + r * 128 + ((c ^ (r & 7)) << 4)) = v[i];
+                    st_shared_v4(sa_u + r * 128 + ((c ^ (r & 7)) << 4), v[i]);
                 }
             } else {
-            // ---- A, fused gather+mean: two row slots at a time so 2 x 8 independent 16-byte loads are in flight ----
-            // (correct but latency-bound: 256 loader threads cannot keep enough loads in flight through registers;
-            //  the engine uses the standalone gather_reduce kernel + this kernel with S == 1 until the TMA-staged
-            //  variant lands -- see DESIGN.md)
-#pragma unroll 1
-            for (int i = 0; i < UM / 8; i += 2) {
-                const int r0 = rg + 8 * i, r1 = r0 + 8;
-                const int64_t row0 = (int64_t)tile * UM + r0, row1 = row0 + 8;
-                const bool ok0 = live_k && row0 < P.n, ok1 = live_k && row1 < P.n;
-                uint4 out0 = make_uint4(0, 0, 0, 0), out1 = make_uint4(0, 0, 0, 0);
-                {
-                    float acc0[8], acc1[8];
+                // ---- A, fused gather+mean.  The thread walks its 16 row slots x S neighbours as one flat sequence in
+                // batches of 16: the ids of batch b+1 are fetched while the 16 row loads of batch b are in flight.
+                const int total = (UM / 8) * S;
+                int64_t nxt[16];
+                auto fetch_ids = [&](int q0) {
 #pragma unroll
-                    for (int e = 0; e < 8; ++e) { acc0[e] = 0.0f; acc1[e] = 0.0f; }
-                    for (int j0 = 0; j0 < S; j0 += 8) {
-                        uint4 v0[8], v1[8];
-#pragma unroll
-                        for (int u = 0; u < 8; ++u) {
-                            const bool in = j0 + u < S;
-                            v0[u] = make_uint4(0, 0, 0, 0); v1[u] = make_uint4(0, 0, 0, 0);
-                            if (ok0 && in) { const int64_t q = row0 * S + j0 + u; v0[u] = ldg_nc_v4(abase + (sg.ids ? sg.ids[q] : q) * sg.lda); }
-                            if (ok1 && in) { const int64_t q = row1 * S + j0 + u; v1[u] = ldg_nc_v4(abase + (sg.ids ? sg.ids[q] : q) * sg.lda); }
-                        }
-#pragma unroll
-                        for (int u = 0; u < 8; ++u) {
-                            float f[8];
-                            ElemTraits<__nv_bfloat16>::unpack(v0[u], f);
-#pragma unroll
-                            for (int e = 0; e < 8; ++e) acc0[e] += f[e];
-                            ElemTraits<__nv_bfloat16>::unpack(v1[u], f);
-#pragma unroll
-                            for (int e = 0; e < 8; ++e) acc1[e] += f[e];
+                    for (int u = 0; u < 16; ++u) {
+                        const int q = q0 + u;
+                        nxt[u] = -1;
+                        if (q < total) {
+                            const int slot = q / S, j = q - slot * S;
+                            const int64_t row = (int64_t)tile * UM + rg + 8 * slot;
+                            if (live_k && row < P.n) { const int64_t at = row * S + j; nxt[u] = sg.ids ? __ldg(sg.ids + at) : at; }
                         }
                     }
+                };
+                fetch_ids(0);
+                float acc[8];
 #pragma unroll
-                    for (int e = 0; e < 8; ++e) { acc0[e] *= sg.scale; acc1[e] *= sg.scale; }
-                    out0 = ElemTraits<__nv_bfloat16>::pack(acc0);
-                    out1 = ElemTraits<__nv_bfloat16>::pack(acc1);
+                for (int e = 0; e < 8; ++e) acc[e] = 0.0f;
+                int slot = 0, j = 0;
+                for (int q0 = 0; q0 < total; q0 += 16) {
+                    uint4 v[16];
+#pragma unroll
+                    for (int u = 0; u < 16; ++u) {
+                        v[u] = make_uint4(0, 0, 0, 0);
+                        if (nxt[u] >= 0) v[u] = ldg_nc_v4(abase + nxt[u] * sg.lda);
+                    }
+                    fetch_ids(q0 + 16);
+#pragma unroll
+                    for (int u = 0; u < 16; ++u) {
+                        if (q0 + u < total) {
+                            float f[8];
+                            ElemTraits<__nv_bfloat16>::unpack(v[u], f);
+#pragma unroll
+                            for (int e = 0; e < 8; ++e) acc[e] += f[e];
+                            if (++j == S) {                      // slot complete: scale, round to bf16, park in the swizzled tile
+#pragma unroll
+                                for (int e = 0; e < 8; ++e) acc[e] *= sg.scale;
+                                const int r = rg + 8 * slot;
+                                st_shared_v4(sa_u + r * 128 + ((c ^ (r & 7)) << 4), ElemTraits<__nv_bfloat16>::pack(acc));
+#pragma unroll
+                                for (int e = 0; e < 8; ++e) acc[e] = 0.0f;
+                                j = 0; ++slot;
+                            }
+                        }
+                    }
                 }
-                *reinterpret_cast<uint4*>(sa + r0 * 128 + ((c ^ (r0 & 7)) << 4)) = out0;
-                *reinterpret_cast<uint4*>(sa + r1 * 128 + ((c ^ (r1 & 7)) << 4)) = out1;
-            }
             }
             // ---- W: O rows x this k-chunk (L2-resident after the first tile) ----
-            uint8_t* sw = sa + kABytes;
+            const uint32_t sw_u = sa_u + kABytes;
             const __nv_bfloat16* wbase = sg.w + k0;
             for (int rb = rg; rb < sg.O; rb += 64) {              // 8 row slots per batch: 8 loads in flight, then 8 stores
                 uint4 wv[8];
@@ -326,7 +339,7 @@ __global__ void __launch_bounds__(kThreads, 1) linear_umma_kernel(const UmmaPara
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
                     const int r = rb + 8 * i;
-                    if (r < sg.O) *reinterpret_cast<uint4*>(sw + r * 128 + ((c ^ (r & 7)) << 4)) = wv[i];
+                    if (r < sg.O) st_shared_v4(sw_u + r * 128 + ((c ^ (r & 7)) << 4), wv[i]);
                 }
             }
             fence_proxy_async();                                  // generic-proxy stores -> visible to the tensor core

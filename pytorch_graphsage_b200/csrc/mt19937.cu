@@ -382,26 +382,30 @@ static int rng_generate(gsage_rng* r, int64_t upto, cudaStream_t s, bool may_syn
             if (blocks > room) blocks = use_lanes ? -1 : room;
         }
         if (!fenced) {
-            GS_CUDA(cudaEventRecord(r->ev_main, s));
-            GS_CUDA(cudaStreamWaitEvent(r->side, r->ev_main, 0));
+            if (!r->overlap) r->side_now = s;                    // GSAGE_RNG_OVERLAP=0: refill in line on the caller's stream
+            else {
+                r->side_now = r->side;
+                GS_CUDA(cudaEventRecord(r->ev_main, s));
+                GS_CUDA(cudaStreamWaitEvent(r->side, r->ev_main, 0));
+            }
             fenced = true;
         }
         if (use_lanes && blocks == lane_refill) {
             GS_TRY(rng_init_lanes(r));
-            mt_jump_kernel<<<dim3(r->lanes - 1, kJumpSlices), 256, sizeof(uint32_t) * kSeqWords, r->side>>>(
+            mt_jump_kernel<<<dim3(r->lanes - 1, kJumpSlices), 256, sizeof(uint32_t) * kSeqWords, r->side_now>>>(
                 r->ring, (uint64_t)(r->cap - 1), r->gen_end, r->polys, r->partial);
             GS_LAUNCHED();
-            mt_generate_lanes_kernel<<<r->lanes, 256, 0, r->side>>>(r->ring, (uint64_t)(r->cap - 1), r->gen_end, r->lane_blocks,
+            mt_generate_lanes_kernel<<<r->lanes, 256, 0, r->side_now>>>(r->ring, (uint64_t)(r->cap - 1), r->gen_end, r->lane_blocks,
                                                                     r->partial);
             GS_LAUNCHED();
         } else {
             if (blocks < 0) blocks = std::min<int64_t>(need, (r->cap - (r->gen_end - (r->cursor_lb - kN))) / kN);
-            mt_generate_kernel<<<1, 256, 0, r->side>>>(r->ring, (uint64_t)(r->cap - 1), r->gen_end, (int)blocks);
+            mt_generate_kernel<<<1, 256, 0, r->side_now>>>(r->ring, (uint64_t)(r->cap - 1), r->gen_end, (int)blocks);
             GS_LAUNCHED();
         }
         r->gen_end += blocks * kN;
     }
-    if (fenced) GS_CUDA(cudaEventRecord(r->ev_refill, r->side));
+    if (fenced) GS_CUDA(cudaEventRecord(r->ev_refill, r->side_now));
     return GSAGE_OK;
 }
 
@@ -491,6 +495,7 @@ int gsage_rng_create(gsage_rng** out) {
     r->prefetch_blocks = std::max<int64_t>(1, std::min<int64_t>(64, r->cap / kN / 8));
     // lane refill = lanes x lane_blocks x 624 words (default 32 x 256 -> 5.1 M words); rings too small for it stay sequential
     r->lanes = 32; r->lane_blocks = 256; r->lane_threshold = 128;
+    if (const char* e = getenv("GSAGE_RNG_OVERLAP")) r->overlap = atoi(e) != 0;
     if (const char* e = getenv("GSAGE_RNG_LANES")) r->lanes = std::max(1, std::min(148, atoi(e)));
     if ((int64_t)r->lanes * r->lane_blocks * kN > r->cap / 3) r->lanes = 1;
     r->tiles_cap = (int)(r->cap / kTile + 2);

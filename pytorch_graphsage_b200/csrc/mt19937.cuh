@@ -15,6 +15,8 @@ struct gsage_rng {
     int64_t gen_visible = 0;       // host: words the caller's stream has already been ordered after
     int64_t max_window = 0;        // host: largest look-ahead window requested since the last seed (prefetch size)
     cudaStream_t side = nullptr;   // refills run here, overlapping the caller's compute
+    cudaStream_t side_now = nullptr;
+    bool overlap = true;           // GSAGE_RNG_OVERLAP=0 keeps refills on the caller's stream
     cudaEvent_t ev_main = nullptr, ev_refill = nullptr;
     int64_t cursor_lb = 0, cursor_ub = 0;   // host bounds on the device cursor
     int64_t origin = 0;            // cursor value at the last seed / set_state
