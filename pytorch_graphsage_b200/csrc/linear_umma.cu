@@ -49,6 +49,8 @@ struct UmmaParams {
     int n_segs; int64_t n; int act;
     void* out; int out_bf16; int64_t ld_out;
     int n_tiles; int stages; int stage_bytes; int w_bytes;
+    int any_reduce;       // some segment has S > 1: loaders take the register path (fused gather+mean)
+    int full_count;       // arrivals that complete a `full` barrier phase
     int* err;
 };
 
@@ -80,6 +82,12 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* er
 }
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+// the mbarrier completes its phase only after every cp.async this thread has issued so far has landed (pending
+// count +1 now, -1 when the copies complete); the pattern CUTLASS' sm100 cp.async->UMMA mainloop uses -- no
+// proxy fence, no blocking wait in the producer
+__device__ __forceinline__ void cp_async_arrive_on(uint32_t bar) {
+    asm volatile("cp.async.mbarrier.arrive.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
@@ -135,7 +143,7 @@ __global__ void __launch_bounds__(kThreads, 1) linear_umma_kernel(const UmmaPara
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < P.stages; ++s) { mbar_init(full_bar(s), kGroupThreads); mbar_init(empty_bar(s), 1); }
+        for (int s = 0; s < P.stages; ++s) { mbar_init(full_bar(s), P.full_count); mbar_init(empty_bar(s), 1); }
         for (int b = 0; b < 2; ++b) { mbar_init(tfull_bar(b), 1); mbar_init(tempty_bar(b), 32 * kEpiWarps); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -235,6 +243,47 @@ __global__ void __launch_bounds__(kThreads, 1) linear_umma_kernel(const UmmaPara
         }
     } else {
         // =========================== LOADERS ===========================
+        if (!P.any_reduce) {
+            // ---- plain operands: 16-byte cp.async straight into the swizzled tiles, completion tracked by the
+            // stage's mbarrier.  Nothing blocks until the ring is full: up to `stages` x 32 KB in flight per SM.
+            const int t = threadIdx.x - 32 * (kEpiWarps + 1);
+            if (t < 128) {
+                const int sub_row = t >> 3, chunk = t & 7;      // 8 threads cover one 128-byte row segment
+                int item = 0;
+                for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x) {
+                    for (int sidx = 0; sidx < P.n_segs; ++sidx) {
+                        const UmmaSeg& sg = P.seg[sidx];
+                        const __nv_bfloat16* a_rows[8];           // this thread's 8 rows of the tile, gathered by id
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const int64_t r = (int64_t)tile * UM + i * 16 + sub_row;
+                            a_rows[i] = nullptr;
+                            if (r < P.n) a_rows[i] = sg.a + (sg.ids ? __ldg(sg.ids + r) : r) * sg.lda;
+                        }
+                        for (int kc = 0; kc < sg.kchunks; ++kc, ++item) {
+                            const int stage = item % P.stages;
+                            mbar_wait(empty_bar(stage), ((item / P.stages) & 1) ^ 1, P.err);
+                            const uint32_t sa_u = smem_u32(smem + (size_t)stage * P.stage_bytes);
+                            const int k0 = kc * UK + chunk * 8;
+                            const uint32_t kbytes = (k0 < sg.kvalid) ? 16u : 0u;
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) {
+                                const int r = i * 16 + sub_row;
+                                const bool live = a_rows[i] != nullptr && kbytes;
+                                cp_async16(sa_u + r * 128 + ((chunk ^ (r & 7)) << 4), live ? (const void*)(a_rows[i] + k0) : (const void*)sg.a,
+                                           live ? 16u : 0u);
+                            }
+                            const uint32_t sw_u = sa_u + kABytes;
+                            for (int r = sub_row; r < sg.O; r += 16)
+                                cp_async16(sw_u + r * 128 + ((chunk ^ (r & 7)) << 4),
+                                           kbytes ? (const void*)(sg.w + (int64_t)r * sg.ldw + k0) : (const void*)sg.w, kbytes);
+                            cp_async_arrive_on(full_bar(stage));
+                            mbar_arrive(full_bar(stage));
+                        }
+                    }
+                }
+            }
+        } else {
         // group g fills items g, g+G, g+2G, ... (an item = one (tile, segment, k-chunk) stage); the MMA warp consumes
         // items in order.  Thread (rg, c): 16-byte chunk c of rows rg, rg+8, ... of the 128-row tile.
         const int lt = (threadIdx.x - 32 * (kEpiWarps + 1)) % kGroupThreads;
@@ -345,6 +394,7 @@ __global__ void __launch_bounds__(kThreads, 1) linear_umma_kernel(const UmmaPara
             fence_proxy_async();                                  // generic-proxy stores -> visible to the tensor core
             mbar_arrive(full_bar(stage));
         }
+        }
     }
 
     // teardown: everyone done with TMEM before it is freed
@@ -394,6 +444,8 @@ int linear_umma_launch(const LinearParams& P, cudaStream_t s) {
     GS_CHECK_ARG(col <= 256, "linear_umma: accumulators need %d TMEM columns (max 256 per buffer)", col);
     U.n_segs = P.n_segs; U.n = P.n; U.act = P.act; U.out = P.out; U.out_bf16 = P.out_dtype == GSAGE_BF16; U.ld_out = P.ld_out;
     U.n_tiles = (int)ceil_div(P.n, UM);
+    for (int i = 0; i < P.n_segs; ++i) U.any_reduce |= (U.seg[i].S > 1) ? 1 : 0;
+    U.full_count = U.any_reduce ? kGroupThreads : 128;
     U.w_bytes = maxO * UK * 2;
     U.stage_bytes = (kABytes + U.w_bytes + 1023) / 1024 * 1024;
     const int budget = 200 * 1024;
