@@ -21,6 +21,7 @@
 // Every mbarrier wait is bounded (a stuck pipeline traps instead of hanging the GPU).
 #include "linear.cuh"
 #include <string.h>
+#include <stdlib.h>
 
 namespace gsage {
 
@@ -51,6 +52,7 @@ struct UmmaParams {
     int n_tiles; int stages; int stage_bytes; int w_bytes;
     int any_reduce;       // some segment has S > 1: loaders take the register path (fused gather+mean)
     int full_count;       // arrivals that complete a `full` barrier phase
+    int debug;            // GSAGE_UMMA_DEBUG bit0: no A reads, bit1: no W reads, bit2: no MMA issue (timing experiments only)
     int* err;
 };
 
@@ -127,6 +129,44 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// 32 accumulator columns of one row: bias, activation (compile-time), convert, 16-byte stores when aligned
+template <int ACT>
+__device__ __forceinline__ void epilogue_store(const uint32_t* r, const float* bias, int valid, void* out, int out_bf16) {
+    float v[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+    if (bias) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) if (j < valid) v[j] += __ldg(bias + j);
+    }
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+        if (ACT == GSAGE_ACT_RELU) v[j] = fmaxf(v[j], 0.0f);
+        if (ACT == GSAGE_ACT_TANH) v[j] = tanhf(v[j]);
+    }
+    const bool vec = valid == 32 && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
+    if (out_bf16) {
+        if (vec) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                reinterpret_cast<uint4*>(out)[q] = make_uint4(pack_bf16(v[8 * q], v[8 * q + 1]), pack_bf16(v[8 * q + 2], v[8 * q + 3]),
+                                                              pack_bf16(v[8 * q + 4], v[8 * q + 5]), pack_bf16(v[8 * q + 6], v[8 * q + 7]));
+        } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) if (j < valid) reinterpret_cast<__nv_bfloat16*>(out)[j] = __float2bfloat16_rn(v[j]);
+        }
+    } else {
+        if (vec) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+                reinterpret_cast<float4*>(out)[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+        } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) if (j < valid) reinterpret_cast<float*>(out)[j] = v[j];
+        }
+    }
+}
+
 // ---- the kernel ----------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kThreads, 1) linear_umma_kernel(const UmmaParams P) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -175,35 +215,12 @@ __global__ void __launch_bounds__(kThreads, 1) linear_umma_kernel(const UmmaPara
                     tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(buf * 256 + sg.acc_col + c0), r);
                     tmem_ld_wait();
                     if (row < P.n) {
-                        float v[32];
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) {
-                            float f = __uint_as_float(r[j]);
-                            if (sg.bias && c0 + j < sg.O) f += sg.bias[c0 + j];
-                            v[j] = apply_act(f, P.act);
-                        }
+                        void* o = (char*)P.out + (row * P.ld_out + sg.col0 + c0) * (P.out_bf16 ? 2 : 4);
+                        const float* bias = sg.bias ? sg.bias + c0 : nullptr;
                         const int valid = min(32, sg.O - c0);
-                        const int64_t at = row * P.ld_out + sg.col0 + c0;
-                        if (P.out_bf16) {
-                            __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(P.out) + at;
-                            if (valid == 32 && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
-#pragma unroll
-                                for (int q = 0; q < 4; ++q)
-                                    reinterpret_cast<uint4*>(o)[q] = make_uint4(pack_bf16(v[8 * q], v[8 * q + 1]), pack_bf16(v[8 * q + 2], v[8 * q + 3]),
-                                                                                pack_bf16(v[8 * q + 4], v[8 * q + 5]), pack_bf16(v[8 * q + 6], v[8 * q + 7]));
-                            } else {
-                                for (int j = 0; j < valid; ++j) o[j] = __float2bfloat16_rn(v[j]);
-                            }
-                        } else {
-                            float* o = reinterpret_cast<float*>(P.out) + at;
-                            if (valid == 32 && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
-#pragma unroll
-                                for (int q = 0; q < 8; ++q)
-                                    reinterpret_cast<float4*>(o)[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
-                            } else {
-                                for (int j = 0; j < valid; ++j) o[j] = v[j];
-                            }
-                        }
+                        if (P.act == GSAGE_ACT_RELU) epilogue_store<GSAGE_ACT_RELU>(r, bias, valid, o, P.out_bf16);
+                        else if (P.act == GSAGE_ACT_TANH) epilogue_store<GSAGE_ACT_TANH>(r, bias, valid, o, P.out_bf16);
+                        else epilogue_store<GSAGE_ACT_NONE>(r, bias, valid, o, P.out_bf16);
                     }
                 }
             }
@@ -226,7 +243,8 @@ __global__ void __launch_bounds__(kThreads, 1) linear_umma_kernel(const UmmaPara
                     const int stage = item % P.stages;
                     mbar_wait(full_bar(stage), (item / P.stages) & 1, P.err);
                     tc_fence_after();
-                    if (lane == 0) {
+                    if (lane == 0 && (P.debug & 4)) umma_commit(empty_bar(stage));
+                    if (lane == 0 && !(P.debug & 4)) {
                         const uint32_t a_addr = smem_u32(smem + (size_t)stage * P.stage_bytes);
                         const uint32_t b_addr = a_addr + kABytes;
                         const uint64_t adesc = umma_desc(a_addr), bdesc = umma_desc(b_addr);
@@ -269,14 +287,15 @@ __global__ void __launch_bounds__(kThreads, 1) linear_umma_kernel(const UmmaPara
 #pragma unroll
                             for (int i = 0; i < 8; ++i) {
                                 const int r = i * 16 + sub_row;
-                                const bool live = a_rows[i] != nullptr && kbytes;
+                                const bool live = a_rows[i] != nullptr && kbytes && !(P.debug & 1);
                                 cp_async16(sa_u + r * 128 + ((chunk ^ (r & 7)) << 4), live ? (const void*)(a_rows[i] + k0) : (const void*)sg.a,
                                            live ? 16u : 0u);
                             }
                             const uint32_t sw_u = sa_u + kABytes;
                             for (int r = sub_row; r < sg.O; r += 16)
                                 cp_async16(sw_u + r * 128 + ((chunk ^ (r & 7)) << 4),
-                                           kbytes ? (const void*)(sg.w + (int64_t)r * sg.ldw + k0) : (const void*)sg.w, kbytes);
+                                           (kbytes && !(P.debug & 2)) ? (const void*)(sg.w + (int64_t)r * sg.ldw + k0) : (const void*)sg.w,
+                                           (P.debug & 2) ? 0u : kbytes);
                             cp_async_arrive_on(full_bar(stage));
                             mbar_arrive(full_bar(stage));
                         }
@@ -446,6 +465,7 @@ int linear_umma_launch(const LinearParams& P, cudaStream_t s) {
     U.n_tiles = (int)ceil_div(P.n, UM);
     for (int i = 0; i < P.n_segs; ++i) U.any_reduce |= (U.seg[i].S > 1) ? 1 : 0;
     U.full_count = U.any_reduce ? kGroupThreads : 128;
+    if (const char* e = getenv("GSAGE_UMMA_DEBUG")) U.debug = atoi(e);
     U.w_bytes = maxO * UK * 2;
     U.stage_bytes = (kABytes + U.w_bytes + 1023) / 1024 * 1024;
     const int budget = 200 * 1024;
