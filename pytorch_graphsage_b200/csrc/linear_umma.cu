@@ -20,6 +20,8 @@
 //     the loads and MMAs of tile i+1.
 // Every mbarrier wait is bounded (a stuck pipeline traps instead of hanging the GPU).
 #include "linear.cuh"
+#include <cuda.h>
+#include <cudaTypedefs.h>
 #include <string.h>
 #include <stdlib.h>
 
@@ -30,7 +32,9 @@ static constexpr int UK = 64;             // bf16 elements per smem chunk row = 
 static constexpr int kEpiWarps = 4;
 static constexpr int kLoadGroups = 4, kGroupThreads = 64;           // loader groups fill different stages concurrently
 static constexpr int kLoadWarps = kLoadGroups * kGroupThreads / 32;
-static constexpr int kThreads = 32 * (kEpiWarps + 1 + kLoadWarps);
+static constexpr int kTmaWarp = kEpiWarps + 1;                       // one lane issues the TMA tile loads (W, contiguous A)
+static constexpr int kFirstLoadWarp = kEpiWarps + 2;
+static constexpr int kThreads = 32 * (kEpiWarps + 2 + kLoadWarps);
 static constexpr int kABytes = UM * UK * 2;                   // 16 KB
 static constexpr int kMaxO = 256;
 
@@ -52,9 +56,15 @@ struct UmmaParams {
     int n_tiles; int stages; int stage_bytes; int w_bytes;
     int any_reduce;       // some segment has S > 1: loaders take the register path (fused gather+mean)
     int full_count;       // arrivals that complete a `full` barrier phase
+    int cp_threads;       // copy threads of the cp.async loader (64 | 128)
     int debug;            // GSAGE_UMMA_DEBUG bit0: no A reads, bit1: no W reads, bit2: no MMA issue (timing experiments only)
     int* err;
 };
+
+// TMA descriptors (cuTensorMapEncodeTiled): per segment the W matrix, and the A matrix when it is read in place
+// (no ids).  Boxes are 64 columns (128 bytes, SWIZZLE_128B) x 128 | O rows; out-of-bounds rows / columns read as
+// zero, which is what pads the K tail (d = 602 -> 640) and the last row tile.
+struct UmmaMaps { CUtensorMap w[2]; CUtensorMap a[2]; };
 
 // ---- PTX helpers -----------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -85,11 +95,19 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* er
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
 }
-// the mbarrier completes its phase only after every cp.async this thread has issued so far has landed (pending
-// count +1 now, -1 when the copies complete); the pattern CUTLASS' sm100 cp.async->UMMA mainloop uses -- no
-// proxy fence, no blocking wait in the producer
+// the thread's arrival on the mbarrier is performed by the hardware once every cp.async it has issued so far has
+// landed (.noinc: it counts as one of the expected arrivals) -- the completion mechanism of CUTLASS' sm100
+// cp.async->UMMA mainloop: no proxy fence, no blocking wait in the producer
 __device__ __forceinline__ void cp_async_arrive_on(uint32_t bar) {
-    asm volatile("cp.async.mbarrier.arrive.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+// one 2-D tile (box of the descriptor) starting at (col, row) -> swizzled smem tile; bytes are credited to `bar`
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int col, int row, uint32_t bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 ::"r"(dst), "l"(map), "r"(col), "r"(row), "r"(bar) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
@@ -168,7 +186,7 @@ __device__ __forceinline__ void epilogue_store(const uint32_t* r, const float* b
 }
 
 // ---- the kernel ----------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kThreads, 1) linear_umma_kernel(const UmmaParams P) {
+__global__ void __launch_bounds__(kThreads, 1) linear_umma_kernel(const UmmaParams P, const __grid_constant__ UmmaMaps M) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     // carve: [stages x (A 16 KB | W w_bytes)] then barriers
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -259,24 +277,49 @@ __global__ void __launch_bounds__(kThreads, 1) linear_umma_kernel(const UmmaPara
             if (lane == 0) umma_commit(tfull_bar(buf));                  // accumulators of this tile complete
             __syncwarp();
         }
+    } else if (warp == kTmaWarp) {
+        // =========================== TMA ISSUER ===========================
+        // W tile of every item, and the A tile of items whose segment is read in place: one instruction each,
+        // completion (byte count) credited to the stage's `full` barrier
+        if (!P.any_reduce && lane == 0) {
+            int item = 0;
+            for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x) {
+                for (int sidx = 0; sidx < P.n_segs; ++sidx) {
+                    const UmmaSeg& sg = P.seg[sidx];
+                    const uint32_t w_bytes = (uint32_t)sg.O * 128u;
+                    for (int kc = 0; kc < sg.kchunks; ++kc, ++item) {
+                        const int stage = item % P.stages;
+                        mbar_wait(empty_bar(stage), ((item / P.stages) & 1) ^ 1, P.err);
+                        const uint32_t sa_u = smem_u32(smem + (size_t)stage * P.stage_bytes);
+                        mbar_arrive_expect_tx(full_bar(stage), w_bytes + (sg.ids ? 0u : (uint32_t)kABytes));
+                        if (!sg.ids) tma_load_2d(sa_u, &M.a[sidx], kc * UK, tile * UM, full_bar(stage));
+                        tma_load_2d(sa_u + kABytes, &M.w[sidx], kc * UK, 0, full_bar(stage));
+                    }
+                }
+            }
+        }
     } else {
         // =========================== LOADERS ===========================
         if (!P.any_reduce) {
             // ---- plain operands: 16-byte cp.async straight into the swizzled tiles, completion tracked by the
             // stage's mbarrier.  Nothing blocks until the ring is full: up to `stages` x 32 KB in flight per SM.
-            const int t = threadIdx.x - 32 * (kEpiWarps + 1);
-            if (t < 128) {
-                const int sub_row = t >> 3, chunk = t & 7;      // 8 threads cover one 128-byte row segment
+            const int t = threadIdx.x - 32 * kFirstLoadWarp;
+            const int CT = P.cp_threads;                        // 64 or 128 copy threads; fewer threads = fewer mbarrier arrivals
+            if (t < CT) {
+                const int slots = 1024 / CT;                     // (row, chunk) slots of the 128 x 8 A tile per thread: 8 or 16
+                const int chunk = t & 7, row_step = CT >> 3, sub_row = t >> 3;
                 int item = 0;
                 for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x) {
                     for (int sidx = 0; sidx < P.n_segs; ++sidx) {
                         const UmmaSeg& sg = P.seg[sidx];
-                        const __nv_bfloat16* a_rows[8];           // this thread's 8 rows of the tile, gathered by id
+                        const __nv_bfloat16* a_rows[16];          // this thread's rows of the tile, gathered by id
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) {
-                            const int64_t r = (int64_t)tile * UM + i * 16 + sub_row;
+                        for (int i = 0; i < 16; ++i) {
                             a_rows[i] = nullptr;
-                            if (r < P.n) a_rows[i] = sg.a + (sg.ids ? __ldg(sg.ids + r) : r) * sg.lda;
+                            if (i < slots && sg.ids) {
+                                const int64_t r = (int64_t)tile * UM + i * row_step + sub_row;
+                                if (r < P.n) a_rows[i] = sg.a + (sg.ids ? __ldg(sg.ids + r) : r) * sg.lda;
+                            }
                         }
                         for (int kc = 0; kc < sg.kchunks; ++kc, ++item) {
                             const int stage = item % P.stages;
@@ -284,20 +327,19 @@ __global__ void __launch_bounds__(kThreads, 1) linear_umma_kernel(const UmmaPara
                             const uint32_t sa_u = smem_u32(smem + (size_t)stage * P.stage_bytes);
                             const int k0 = kc * UK + chunk * 8;
                             const uint32_t kbytes = (k0 < sg.kvalid) ? 16u : 0u;
+                            if (sg.ids) {
 #pragma unroll
-                            for (int i = 0; i < 8; ++i) {
-                                const int r = i * 16 + sub_row;
-                                const bool live = a_rows[i] != nullptr && kbytes && !(P.debug & 1);
-                                cp_async16(sa_u + r * 128 + ((chunk ^ (r & 7)) << 4), live ? (const void*)(a_rows[i] + k0) : (const void*)sg.a,
-                                           live ? 16u : 0u);
+                                for (int i = 0; i < 16; ++i) {
+                                    if (i < slots) {
+                                        const int r = i * row_step + sub_row;
+                                        const bool live = a_rows[i] != nullptr && kbytes && !(P.debug & 1);
+                                        cp_async16(sa_u + r * 128 + ((chunk ^ (r & 7)) << 4),
+                                                   live ? (const void*)(a_rows[i] + k0) : (const void*)sg.a, live ? 16u : 0u);
+                                    }
+                                }
                             }
-                            const uint32_t sw_u = sa_u + kABytes;
-                            for (int r = sub_row; r < sg.O; r += 16)
-                                cp_async16(sw_u + r * 128 + ((chunk ^ (r & 7)) << 4),
-                                           (kbytes && !(P.debug & 2)) ? (const void*)(sg.w + (int64_t)r * sg.ldw + k0) : (const void*)sg.w,
-                                           (P.debug & 2) ? 0u : kbytes);
-                            cp_async_arrive_on(full_bar(stage));
-                            mbar_arrive(full_bar(stage));
+                            if (sg.ids) cp_async_arrive_on(full_bar(stage));   // .noinc: the async arrival IS one of the expected arrivals
+                            else mbar_arrive(full_bar(stage));               // TMA-only item: keep the arrival count uniform
                         }
                     }
                 }
@@ -305,8 +347,8 @@ __global__ void __launch_bounds__(kThreads, 1) linear_umma_kernel(const UmmaPara
         } else {
         // group g fills items g, g+G, g+2G, ... (an item = one (tile, segment, k-chunk) stage); the MMA warp consumes
         // items in order.  Thread (rg, c): 16-byte chunk c of rows rg, rg+8, ... of the 128-row tile.
-        const int lt = (threadIdx.x - 32 * (kEpiWarps + 1)) % kGroupThreads;
-        const int group = (threadIdx.x - 32 * (kEpiWarps + 1)) / kGroupThreads;
+        const int lt = (threadIdx.x - 32 * kFirstLoadWarp) % kGroupThreads;
+        const int group = (threadIdx.x - 32 * kFirstLoadWarp) / kGroupThreads;
         const int rg = lt >> 3, c = lt & 7;
         const int my_tiles = (P.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
         const int total_items = my_tiles * items_per_tile;
@@ -443,6 +485,32 @@ bool linear_umma_eligible(const LinearParams& P) {
 
 static int* g_umma_err = nullptr;
 
+static PFN_cuTensorMapEncodeTiled_v12000 tensor_map_encoder() {
+    static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = (PFN_cuTensorMapEncodeTiled_v12000)p;
+    }
+    return fn;
+}
+
+// bf16 (rows, cols) row-major with `ld` elements between rows; box = 64 columns x box_rows, 128-byte swizzle
+static int make_map(CUtensorMap* m, const void* base, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
+    PFN_cuTensorMapEncodeTiled_v12000 enc = tensor_map_encoder();
+    GS_CHECK_ARG(enc, "linear_umma: cuTensorMapEncodeTiled is not available from this driver");
+    const cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    const cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+    const cuuint32_t box[2] = {(cuuint32_t)UK, (cuuint32_t)box_rows};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    GS_CHECK_ARG(r == CUDA_SUCCESS, "linear_umma: cuTensorMapEncodeTiled failed (%d)", (int)r);
+    return GSAGE_OK;
+}
+
 int linear_umma_launch(const LinearParams& P, cudaStream_t s) {
     UmmaParams U;
     memset(&U, 0, sizeof(U));
@@ -464,7 +532,9 @@ int linear_umma_launch(const LinearParams& P, cudaStream_t s) {
     U.n_segs = P.n_segs; U.n = P.n; U.act = P.act; U.out = P.out; U.out_bf16 = P.out_dtype == GSAGE_BF16; U.ld_out = P.ld_out;
     U.n_tiles = (int)ceil_div(P.n, UM);
     for (int i = 0; i < P.n_segs; ++i) U.any_reduce |= (U.seg[i].S > 1) ? 1 : 0;
-    U.full_count = U.any_reduce ? kGroupThreads : 128;
+    U.cp_threads = 128;
+    if (const char* e = getenv("GSAGE_UMMA_CPT")) U.cp_threads = atoi(e) == 64 ? 64 : 128;
+    U.full_count = U.any_reduce ? kGroupThreads : U.cp_threads + 1;      // copy threads + the TMA thread's expect_tx arrival
     if (const char* e = getenv("GSAGE_UMMA_DEBUG")) U.debug = atoi(e);
     U.w_bytes = maxO * UK * 2;
     U.stage_bytes = (kABytes + U.w_bytes + 1023) / 1024 * 1024;
@@ -484,7 +554,14 @@ int linear_umma_launch(const LinearParams& P, cudaStream_t s) {
         attr_set = true;
     }
     const int grid = U.n_tiles < sm_count() ? U.n_tiles : sm_count();
-    linear_umma_kernel<<<grid, kThreads, smem, s>>>(U);
+    UmmaMaps maps;
+    memset(&maps, 0, sizeof(maps));
+    for (int i = 0; i < P.n_segs; ++i) {
+        const LinearSeg& g = P.seg[i];
+        GS_TRY(make_map(&maps.w[i], g.w, g.O, g.d, g.ldw, g.O));
+        if (!g.ids && U.seg[i].S == 1) GS_TRY(make_map(&maps.a[i], g.a, P.n, g.d, g.lda, UM));
+    }
+    linear_umma_kernel<<<grid, kThreads, smem, s>>>(U, maps);
     GS_LAUNCHED();
     return GSAGE_OK;
 }
