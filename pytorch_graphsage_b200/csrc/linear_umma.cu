@@ -64,7 +64,7 @@ struct UmmaParams {
 // TMA descriptors (cuTensorMapEncodeTiled): per segment the W matrix, and the A matrix when it is read in place
 // (no ids).  Boxes are 64 columns (128 bytes, SWIZZLE_128B) x 128 | O rows; out-of-bounds rows / columns read as
 // zero, which is what pads the K tail (d = 602 -> 640) and the last row tile.
-struct UmmaMaps { CUtensorMap w[2]; CUtensorMap a[2]; };
+struct UmmaMaps { CUtensorMap w[2]; CUtensorMap a[2]; CUtensorMap g[2]; };   // g: 64 x 1 box for tile::gather4 (rows by id)
 
 // ---- PTX helpers -----------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -108,6 +108,11 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t byt
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int col, int row, uint32_t bar) {
     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
                  ::"r"(dst), "l"(map), "r"(col), "r"(row), "r"(bar) : "memory");
+}
+// four rows of the table, picked by id, 64 columns each -> four consecutive 128-byte rows of the swizzled tile
+__device__ __forceinline__ void tma_gather4(uint32_t dst, const CUtensorMap* map, int col, int r0, int r1, int r2, int r3, uint32_t bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cta.global.tile::gather4.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5, %6}], [%7];"
+                 ::"r"(dst), "l"(map), "r"(col), "r"(r0), "r"(r1), "r"(r2), "r"(r3), "r"(bar) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
@@ -229,10 +234,11 @@ __global__ void __launch_bounds__(kThreads, 1) linear_umma_kernel(const UmmaPara
             for (int s = 0; s < P.n_segs; ++s) {
                 const UmmaSeg& sg = P.seg[s];
                 for (int c0 = 0; c0 < sg.O; c0 += 32) {
+                    if (P.debug & 16) continue;                      // timing experiment: no epilogue work at all
                     uint32_t r[32];
                     tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(buf * 256 + sg.acc_col + c0), r);
                     tmem_ld_wait();
-                    if (row < P.n) {
+                    if (row < P.n && !(P.debug & 8)) {
                         void* o = (char*)P.out + (row * P.ld_out + sg.col0 + c0) * (P.out_bf16 ? 2 : 4);
                         const float* bias = sg.bias ? sg.bias + c0 : nullptr;
                         const int valid = min(32, sg.O - c0);
@@ -281,70 +287,38 @@ __global__ void __launch_bounds__(kThreads, 1) linear_umma_kernel(const UmmaPara
         // =========================== TMA ISSUER ===========================
         // W tile of every item, and the A tile of items whose segment is read in place: one instruction each,
         // completion (byte count) credited to the stage's `full` barrier
-        if (!P.any_reduce && lane == 0) {
+        if (!P.any_reduce) {
             int item = 0;
             for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x) {
                 for (int sidx = 0; sidx < P.n_segs; ++sidx) {
                     const UmmaSeg& sg = P.seg[sidx];
                     const uint32_t w_bytes = (uint32_t)sg.O * 128u;
+                    int r0 = 0, r1 = 0, r2 = 0, r3 = 0;            // lane l gathers tile rows 4l .. 4l+3 by id
+                    if (sg.ids) {
+                        const int64_t base = (int64_t)tile * UM + 4 * lane;
+                        if (base + 0 < P.n) r0 = (int)__ldg(sg.ids + base + 0);
+                        if (base + 1 < P.n) r1 = (int)__ldg(sg.ids + base + 1);
+                        if (base + 2 < P.n) r2 = (int)__ldg(sg.ids + base + 2);
+                        if (base + 3 < P.n) r3 = (int)__ldg(sg.ids + base + 3);
+                    }
                     for (int kc = 0; kc < sg.kchunks; ++kc, ++item) {
                         const int stage = item % P.stages;
                         mbar_wait(empty_bar(stage), ((item / P.stages) & 1) ^ 1, P.err);
                         const uint32_t sa_u = smem_u32(smem + (size_t)stage * P.stage_bytes);
-                        mbar_arrive_expect_tx(full_bar(stage), w_bytes + (sg.ids ? 0u : (uint32_t)kABytes));
-                        if (!sg.ids) tma_load_2d(sa_u, &M.a[sidx], kc * UK, tile * UM, full_bar(stage));
-                        tma_load_2d(sa_u + kABytes, &M.w[sidx], kc * UK, 0, full_bar(stage));
+                        if (lane == 0) {
+                            mbar_arrive_expect_tx(full_bar(stage), w_bytes + (uint32_t)kABytes);
+                            tma_load_2d(sa_u + kABytes, &M.w[sidx], kc * UK, 0, full_bar(stage));
+                            if (!sg.ids) tma_load_2d(sa_u, &M.a[sidx], kc * UK, tile * UM, full_bar(stage));
+                        }
+                        __syncwarp();                              // expect_tx is posted before any lane's copy can complete
+                        if (sg.ids && !(P.debug & 1)) tma_gather4(sa_u + lane * 512, &M.g[sidx], kc * UK, r0, r1, r2, r3, full_bar(stage));
                     }
                 }
             }
         }
     } else {
         // =========================== LOADERS ===========================
-        if (!P.any_reduce) {
-            // ---- plain operands: 16-byte cp.async straight into the swizzled tiles, completion tracked by the
-            // stage's mbarrier.  Nothing blocks until the ring is full: up to `stages` x 32 KB in flight per SM.
-            const int t = threadIdx.x - 32 * kFirstLoadWarp;
-            const int CT = P.cp_threads;                        // 64 or 128 copy threads; fewer threads = fewer mbarrier arrivals
-            if (t < CT) {
-                const int slots = 1024 / CT;                     // (row, chunk) slots of the 128 x 8 A tile per thread: 8 or 16
-                const int chunk = t & 7, row_step = CT >> 3, sub_row = t >> 3;
-                int item = 0;
-                for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x) {
-                    for (int sidx = 0; sidx < P.n_segs; ++sidx) {
-                        const UmmaSeg& sg = P.seg[sidx];
-                        const __nv_bfloat16* a_rows[16];          // this thread's rows of the tile, gathered by id
-#pragma unroll
-                        for (int i = 0; i < 16; ++i) {
-                            a_rows[i] = nullptr;
-                            if (i < slots && sg.ids) {
-                                const int64_t r = (int64_t)tile * UM + i * row_step + sub_row;
-                                if (r < P.n) a_rows[i] = sg.a + (sg.ids ? __ldg(sg.ids + r) : r) * sg.lda;
-                            }
-                        }
-                        for (int kc = 0; kc < sg.kchunks; ++kc, ++item) {
-                            const int stage = item % P.stages;
-                            mbar_wait(empty_bar(stage), ((item / P.stages) & 1) ^ 1, P.err);
-                            const uint32_t sa_u = smem_u32(smem + (size_t)stage * P.stage_bytes);
-                            const int k0 = kc * UK + chunk * 8;
-                            const uint32_t kbytes = (k0 < sg.kvalid) ? 16u : 0u;
-                            if (sg.ids) {
-#pragma unroll
-                                for (int i = 0; i < 16; ++i) {
-                                    if (i < slots) {
-                                        const int r = i * row_step + sub_row;
-                                        const bool live = a_rows[i] != nullptr && kbytes && !(P.debug & 1);
-                                        cp_async16(sa_u + r * 128 + ((chunk ^ (r & 7)) << 4),
-                                                   live ? (const void*)(a_rows[i] + k0) : (const void*)sg.a, live ? 16u : 0u);
-                                    }
-                                }
-                            }
-                            if (sg.ids) cp_async_arrive_on(full_bar(stage));   // .noinc: the async arrival IS one of the expected arrivals
-                            else mbar_arrive(full_bar(stage));               // TMA-only item: keep the arrival count uniform
-                        }
-                    }
-                }
-            }
-        } else {
+        if (P.any_reduce) {
         // group g fills items g, g+G, g+2G, ... (an item = one (tile, segment, k-chunk) stage); the MMA warp consumes
         // items in order.  Thread (rg, c): 16-byte chunk c of rows rg, rg+8, ... of the 128-row tile.
         const int lt = (threadIdx.x - 32 * kFirstLoadWarp) % kGroupThreads;
@@ -534,7 +508,7 @@ int linear_umma_launch(const LinearParams& P, cudaStream_t s) {
     for (int i = 0; i < P.n_segs; ++i) U.any_reduce |= (U.seg[i].S > 1) ? 1 : 0;
     U.cp_threads = 128;
     if (const char* e = getenv("GSAGE_UMMA_CPT")) U.cp_threads = atoi(e) == 64 ? 64 : 128;
-    U.full_count = U.any_reduce ? kGroupThreads : U.cp_threads + 1;      // copy threads + the TMA thread's expect_tx arrival
+    U.full_count = U.any_reduce ? kGroupThreads : 1;                      // plain mode: the TMA lane's expect_tx arrival + byte count
     if (const char* e = getenv("GSAGE_UMMA_DEBUG")) U.debug = atoi(e);
     U.w_bytes = maxO * UK * 2;
     U.stage_bytes = (kABytes + U.w_bytes + 1023) / 1024 * 1024;
@@ -560,6 +534,7 @@ int linear_umma_launch(const LinearParams& P, cudaStream_t s) {
         const LinearSeg& g = P.seg[i];
         GS_TRY(make_map(&maps.w[i], g.w, g.O, g.d, g.ldw, g.O));
         if (!g.ids && U.seg[i].S == 1) GS_TRY(make_map(&maps.a[i], g.a, P.n, g.d, g.lda, UM));
+        if (g.ids && U.seg[i].S == 1) GS_TRY(make_map(&maps.g[i], g.a, 0x7FFFFFFF, g.d, g.lda, 1));   // rows by id: no row bound known here
     }
     linear_umma_kernel<<<grid, kThreads, smem, s>>>(U, maps);
     GS_LAUNCHED();
