@@ -5,20 +5,25 @@
 // segments s (the reference's concat-with-self, [fc_x(x) | fc_neib(agg)], is two accumulators of one tile).
 //
 // B200 design
-//   * persistent CTAs (one per SM), 128-row output tiles, 9 warps with fixed roles:
-//       warps 0-3  epilogue   TMEM -> registers (tcgen05.ld 32x32b) -> bias/activation -> bf16/fp32 -> HBM
-//       warp  4    MMA issue  one elected lane issues tcgen05.mma (M=128, N=O, K=16) + tcgen05.commit
-//       warps 5-12 loaders    four independent groups of 64 threads, each filling whole smem stages: A rows are
-//                             gathered *by id* with 16-byte read-only loads -- and, for a segment with S > 1,
-//                             the S neighbour rows of every parent are summed in fp32 registers on the way
-//                             (the fused gather+mean: the aggregated rows never exist in HBM) -- then stored
-//                             as bf16 into the 128B-swizzled K-major tile; W rows likewise
-//   * smem ring of (A 128x64, W Ox64) bf16 chunk pairs; full/empty mbarriers; the gather is free-form because
-//     the loader, not TMA, owns the smem layout (plain stores + one fence.proxy.async per thread per stage:
-//     cp.async would need the same fence, which drains every copy in flight and serialises the ring);
+//   * persistent CTAs (one per SM), 128-row output tiles, warps with fixed roles:
+//       warps 0-3   epilogue    TMEM -> registers (tcgen05.ld 32x32b) -> bias/activation -> bf16/fp32 -> HBM
+//       warp  4     MMA issue   one elected lane issues tcgen05.mma (M=128, N=O, K=16) + tcgen05.commit
+//       warp  5     TMA issue   every operand tile arrives by TMA into 128B-swizzled K-major smem:
+//                                 W chunk (O x 64) and in-place A chunk (128 x 64): cp.async.bulk.tensor.2d
+//                                 A rows gathered BY ID (self rows straight from the feature table):
+//                                 cp.async.bulk.tensor.2d ... tile::gather4, lane l owns rows 4l..4l+3 of the tile
+//                               completion = byte count on the stage's `full` mbarrier (one expect_tx arrival)
+//       warps 6-13  register-path loaders, used only for a segment with reduce_S > 1 (fused gather+mean: S
+//                   neighbour rows summed in fp32 registers on the way into the tile -- correct, but 256 threads
+//                   cannot keep enough loads in flight, so the engine keeps the standalone gather_reduce kernel)
+//   * smem ring of (A 128x64, W Ox64) bf16 chunk pairs, full/empty mbarriers, out-of-bounds rows/columns
+//     zero-filled by the TMA unit (K tail 602 -> 640, last row tile);
 //   * two TMEM accumulator buffers (2 x 256 fp32 columns = all 512 columns): the epilogue of tile i overlaps
 //     the loads and MMAs of tile i+1.
 // Every mbarrier wait is bounded (a stuck pipeline traps instead of hanging the GPU).
+// Measured history of the loader (reddit layer-1 shape, 204800 x 602 -> 2 x 128, profiles/README.md):
+//   cp.async + wait_group + fence.proxy.async 326 us -> LDG/STS register path 640 us -> cp.async + mbarrier
+//   arrive-on 287 us (LDGSTS issue bound, ~16 B/clk/SM) -> TMA for W and in-place A 177 us -> all-TMA 197 us.
 #include "linear.cuh"
 #include <cuda.h>
 #include <cudaTypedefs.h>
@@ -56,7 +61,7 @@ struct UmmaParams {
     int n_tiles; int stages; int stage_bytes; int w_bytes;
     int any_reduce;       // some segment has S > 1: loaders take the register path (fused gather+mean)
     int full_count;       // arrivals that complete a `full` barrier phase
-    int cp_threads;       // copy threads of the cp.async loader (64 | 128)
+    int prefetch;         // L2-prefetch whole rows of the next tile (GSAGE_UMMA_PREFETCH=1; off by default)
     int debug;            // GSAGE_UMMA_DEBUG bit0: no A reads, bit1: no W reads, bit2: no MMA issue (timing experiments only)
     int* err;
 };
@@ -113,6 +118,11 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
 __device__ __forceinline__ void tma_gather4(uint32_t dst, const CUtensorMap* map, int col, int r0, int r1, int r2, int r3, uint32_t bar) {
     asm volatile("cp.async.bulk.tensor.2d.shared::cta.global.tile::gather4.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5, %6}], [%7];"
                  ::"r"(dst), "l"(map), "r"(col), "r"(r0), "r"(r1), "r"(r2), "r"(r3), "r"(bar) : "memory");
+}
+// pull `bytes` (multiple of 16) starting at p into L2: used to fetch WHOLE rows of the next tile from DRAM in one
+// contiguous burst each, so the 128-byte-per-row tile loads that follow hit L2 instead of re-opening DRAM pages
+__device__ __forceinline__ void l2_prefetch(const void* p, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
@@ -293,6 +303,17 @@ __global__ void __launch_bounds__(kThreads, 1) linear_umma_kernel(const UmmaPara
                 for (int sidx = 0; sidx < P.n_segs; ++sidx) {
                     const UmmaSeg& sg = P.seg[sidx];
                     const uint32_t w_bytes = (uint32_t)sg.O * 128u;
+                    if (P.prefetch) {                               // whole rows of the NEXT tile of this segment -> L2
+                        const int64_t nbase = ((int64_t)tile + gridDim.x) * UM + 4 * lane;
+                        const uint32_t row_bytes = (uint32_t)sg.kvalid * 2u;
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            if (nbase + q < P.n) {
+                                const int64_t src = sg.ids ? __ldg(sg.ids + nbase + q) : nbase + q;
+                                l2_prefetch(sg.a + src * sg.lda, row_bytes);
+                            }
+                        }
+                    }
                     int r0 = 0, r1 = 0, r2 = 0, r3 = 0;            // lane l gathers tile rows 4l .. 4l+3 by id
                     if (sg.ids) {
                         const int64_t base = (int64_t)tile * UM + 4 * lane;
@@ -306,7 +327,7 @@ __global__ void __launch_bounds__(kThreads, 1) linear_umma_kernel(const UmmaPara
                         mbar_wait(empty_bar(stage), ((item / P.stages) & 1) ^ 1, P.err);
                         const uint32_t sa_u = smem_u32(smem + (size_t)stage * P.stage_bytes);
                         if (lane == 0) {
-                            mbar_arrive_expect_tx(full_bar(stage), w_bytes + (uint32_t)kABytes);
+                            mbar_arrive_expect_tx(full_bar(stage), w_bytes + ((sg.ids && (P.debug & 1)) ? 0u : (uint32_t)kABytes));
                             tma_load_2d(sa_u + kABytes, &M.w[sidx], kc * UK, 0, full_bar(stage));
                             if (!sg.ids) tma_load_2d(sa_u, &M.a[sidx], kc * UK, tile * UM, full_bar(stage));
                         }
@@ -506,8 +527,8 @@ int linear_umma_launch(const LinearParams& P, cudaStream_t s) {
     U.n_segs = P.n_segs; U.n = P.n; U.act = P.act; U.out = P.out; U.out_bf16 = P.out_dtype == GSAGE_BF16; U.ld_out = P.ld_out;
     U.n_tiles = (int)ceil_div(P.n, UM);
     for (int i = 0; i < P.n_segs; ++i) U.any_reduce |= (U.seg[i].S > 1) ? 1 : 0;
-    U.cp_threads = 128;
-    if (const char* e = getenv("GSAGE_UMMA_CPT")) U.cp_threads = atoi(e) == 64 ? 64 : 128;
+    U.prefetch = 0;      // measured: 275 us with, 198 us without (reddit layer-1 shape) -- the prefetches queue behind the tile loads
+    if (const char* e = getenv("GSAGE_UMMA_PREFETCH")) U.prefetch = atoi(e) != 0;
     U.full_count = U.any_reduce ? kGroupThreads : 1;                      // plain mode: the TMA lane's expect_tx arrival + byte count
     if (const char* e = getenv("GSAGE_UMMA_DEBUG")) U.debug = atoi(e);
     U.w_bytes = maxO * UK * 2;
