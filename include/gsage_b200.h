@@ -154,6 +154,7 @@ typedef struct gsage_linear_seg {
     int64_t col0;                                                            /* output column offset         */
     int reduce_S;   /* <= 1: A row r = A[ids[r]].  S > 1: A row r = mean_j A[ids[r*S + j]] -- the neighbour gather+mean
                        (nn_modules.py:197-198) fused into the projection's operand load; the mean never touches HBM */
+    int w_transposed; /* != 0: W is stored (d x O) row-major, i.e. out = A . W (the data-gradient form of a Linear) */
 } gsage_linear_seg;
 
 /* up to two segments writing disjoint column ranges of one output: the "concat-with-self" of
@@ -219,6 +220,24 @@ int gsage_engine_forward_host(gsage_engine* e, gsage_graph* g, gsage_rng* rng, c
 int gsage_engine_peek(gsage_engine* e, int what, const void** ptr_dev, int64_t* rows, int64_t* cols, int64_t* ld,
                       int* dtype);
 int64_t gsage_engine_workspace_bytes(const gsage_engine* e);
+
+/* ------------------------------------------------------------------------------------------------
+ * Backward (mean aggregator + identity prep).  Replaces `loss.backward()` (models.py:101) for the parameters of
+ * the hot path; must follow a gsage_engine_forward of the same batch (reads its ids and activations).
+ * `dlogits_dev`: d loss / d logits (B x n_classes, fp32).  `grads`: fp32 device buffers laid out like the
+ * weights (same shapes, contiguous), overwritten.  The two halves let the caller start the gradient
+ * all-reduce of the head (fc + layer 2, tiny) while the big layer-1 weight gradients are still being computed:
+ *   _head    fc.weight, fc.bias, layer-2 fc_x / fc_neib, and the layer-1 output gradient (kept internally)
+ *   _layer1  layer-1 fc_x / fc_neib (reduction over all 26*B parent rows)
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct gsage_grads {
+    float* fc_x[2];                 /* agg_layers.k.fc_x.weight.grad    */
+    float* fc_neib[2];              /* agg_layers.k.fc_neib.weight.grad */
+    float* fc_w;                    /* fc.weight.grad                   */
+    float* fc_b;                    /* fc.bias.grad                     */
+} gsage_grads;
+int gsage_engine_backward_head(gsage_engine* e, const float* dlogits_dev, const gsage_grads* grads, void* stream);
+int gsage_engine_backward_layer1(gsage_engine* e, const gsage_grads* grads, void* stream);
 
 /* Live stopwatch (CUDA events on the launching stream) around kernel groups of the forward, for bench.py:
  *   FORWARD  the whole gsage_engine_forward        SAMPLE   rng draws + sample kernels, both hops

@@ -24,7 +24,7 @@ c_p = C.c_void_p
 class LinearSeg(C.Structure):
     _fields_ = [('a_dev', c_p), ('a_dtype', C.c_int), ('lda', c_i64), ('ids_dev', c_p),
                 ('w_dev', c_p), ('w_dtype', C.c_int), ('ldw', c_i64), ('d', C.c_int), ('O', C.c_int),
-                ('bias_dev', c_p), ('col0', c_i64), ('reduce_S', C.c_int)]
+                ('bias_dev', c_p), ('col0', c_i64), ('reduce_S', C.c_int), ('w_transposed', C.c_int)]
 
 
 class EngineConfig(C.Structure):
@@ -39,6 +39,10 @@ class EngineConfig(C.Structure):
 
 class LayerWeights(C.Structure):
     _fields_ = [('fc_x', c_p), ('fc_neib', c_p), ('mlp_w', c_p), ('mlp_b', c_p), ('att_w1', c_p), ('att_w2', c_p)]
+
+
+class Grads(C.Structure):
+    _fields_ = [('fc_x', c_p * 2), ('fc_neib', c_p * 2), ('fc_w', c_p), ('fc_b', c_p)]
 
 
 class Weights(C.Structure):
@@ -83,6 +87,8 @@ _SIGNATURES = {
     'gsage_engine_forward_host': (C.c_int, [c_p, c_p, c_p, c_p, c_i64, c_p, c_p]),
     'gsage_engine_peek': (C.c_int, [c_p, C.c_int, C.POINTER(c_p), C.POINTER(c_i64), C.POINTER(c_i64), C.POINTER(c_i64), C.POINTER(C.c_int)]),
     'gsage_engine_workspace_bytes': (c_i64, [c_p]),
+    'gsage_engine_backward_head': (C.c_int, [c_p, c_p, C.POINTER(Grads), c_p]),
+    'gsage_engine_backward_layer1': (C.c_int, [c_p, C.POINTER(Grads), c_p]),
     'gsage_engine_profile': (C.c_int, [c_p, C.c_int]),
     'gsage_engine_profile_read': (C.c_int, [c_p, C.POINTER(C.c_double), C.POINTER(c_i64), C.POINTER(C.c_double), c_p]),
 }

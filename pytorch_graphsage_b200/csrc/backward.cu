@@ -1,0 +1,172 @@
+// backward.cu -- gradient kernels of the hot path (fp32 accumulate; the exact, FFMA generation).
+//
+// The reference gets these from autograd through `loss.backward()` (/root/reference/models.py:101); the
+// gradients are the payload of the one collective of the seed-sharded multi-GPU run.
+//   wgrad_simt_kernel        dW[o, k] += sum_r G[r, o] * A[row(r), k]      (fc_x / fc_neib / fc weight gradients;
+//                            the self rows are gathered by id straight from the feature table, like the forward)
+//   l2_normalize_bwd_kernel  gradient through F.normalize(dim=1)            (models.py:90)
+//   layer1_grad_kernel       dH = [dh0 ; broadcast(dm2)/S] * act'(H)       (mean over S + concat + relu, backwards)
+//   colsum_kernel            bias gradient
+// Tensor-core (tcgen05, MN-major operands) versions of wgrad are the next step; these are correct first.
+#include "backward.cuh"
+
+namespace gsage {
+
+__device__ __forceinline__ float ld_any(const void* base, int dtype, int64_t idx) {
+    return dtype == GSAGE_BF16 ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(base)[idx])
+                               : reinterpret_cast<const float*>(base)[idx];
+}
+
+// 64 (o) x 64 (k) tile of dW per CTA, a chunk of rows per CTA (grid.z), fp32 atomics into dW
+static constexpr int WT = 64, WR = 16;
+
+__global__ void __launch_bounds__(256) wgrad_simt_kernel(const float* __restrict__ G, int64_t ldg, int O,
+                                                         const void* __restrict__ A, int a_dtype, int64_t lda,
+                                                         const int64_t* __restrict__ ids, int d, int64_t n, int64_t rows_per_cta,
+                                                         float* __restrict__ dW, int64_t lddw) {
+    __shared__ float Gs[WR][WT + 4];
+    __shared__ float As[WR][WT + 4];
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    const int o0 = blockIdx.y * WT, k0 = blockIdx.x * WT;
+    const int64_t r_begin = (int64_t)blockIdx.z * rows_per_cta;
+    const int64_t r_end = min(n, r_begin + rows_per_cta);
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.0f;
+    // loader mapping: 16 rows x 64 cols = 1024 elements, 4 per thread
+    const int lr = tid >> 4, lc = (tid & 15) * 4;
+    for (int64_t r0 = r_begin; r0 < r_end; r0 += WR) {
+        const int64_t r = r0 + lr;
+        int64_t src = -1;
+        if (r < r_end) src = ids ? ids[r] : r;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            float g = 0.0f, a = 0.0f;
+            if (r < r_end) {
+                if (o0 + lc + q < O) g = G[r * ldg + o0 + lc + q];
+                if (k0 + lc + q < d) a = ld_any(A, a_dtype, src * lda + k0 + lc + q);
+            }
+            Gs[lr][lc + q] = g;
+            As[lr][lc + q] = a;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int rr = 0; rr < WR; ++rr) {
+            const float4 g4 = *reinterpret_cast<const float4*>(&Gs[rr][ty * 4]);
+            const float4 a4 = *reinterpret_cast<const float4*>(&As[rr][tx * 4]);
+            const float g[4] = {g4.x, g4.y, g4.z, g4.w}, a[4] = {a4.x, a4.y, a4.z, a4.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(g[i], a[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int o = o0 + ty * 4 + i;
+        if (o >= O) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int k = k0 + tx * 4 + j;
+            if (k < d) atomicAdd(dW + (int64_t)o * lddw + k, acc[i][j]);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) l2_normalize_bwd_kernel(const float* __restrict__ z, const float* __restrict__ dzn,
+                                                               int64_t n, int d, int act, float* __restrict__ dz) {
+    const int lane = threadIdx.x & 31;
+    const int64_t r = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (r >= n) return;
+    float ss = 0.0f, dot = 0.0f;
+    for (int c = lane; c < d; c += 32) {
+        const float v = z[r * d + c];
+        ss = fmaf(v, v, ss);
+        dot = fmaf(v, dzn[r * d + c], dot);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        ss += __shfl_xor_sync(0xFFFFFFFFu, ss, o);
+        dot += __shfl_xor_sync(0xFFFFFFFFu, dot, o);
+    }
+    const float inv = 1.0f / fmaxf(sqrtf(ss), 1e-12f);
+    const float proj = dot * inv * inv;                       // <zn, dzn> / ||z||
+    for (int c = lane; c < d; c += 32) {
+        const float v = z[r * d + c];
+        float g = (dzn[r * d + c] - v * proj) * inv;
+        if (act == GSAGE_ACT_RELU) g = v > 0.0f ? g : 0.0f;   // z is the post-activation output of layer 2
+        else if (act == GSAGE_ACT_TANH) g *= (1.0f - v * v);
+        dz[r * d + c] = g;
+    }
+}
+
+// dH[r, c]: r < n0 -> dh0[r, c];  r >= n0 -> dm2[(r - n0) / S, c] / S;  times act'(H[r, c])
+__global__ void __launch_bounds__(256) layer1_grad_kernel(const float* __restrict__ dh0, const float* __restrict__ dm2,
+                                                          const void* __restrict__ H, int h_dtype, int64_t ldh, int64_t n0,
+                                                          int64_t n1, int S, int width, int act, float* __restrict__ dH) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (n0 + n1) * width) return;
+    const int64_t r = i / width;
+    const int c = (int)(i - r * width);
+    float g = r < n0 ? dh0[r * width + c] : dm2[((r - n0) / S) * width + c] * (1.0f / (float)S);
+    const float h = ld_any(H, h_dtype, r * ldh + c);
+    if (act == GSAGE_ACT_RELU) g = h > 0.0f ? g : 0.0f;
+    else if (act == GSAGE_ACT_TANH) g *= (1.0f - h * h);
+    dH[i] = g;
+}
+
+__global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ x, int64_t n, int d, float* __restrict__ out) {
+    const int c = blockIdx.x;
+    float s = 0.0f;
+    for (int64_t r = threadIdx.x; r < n; r += blockDim.x) s += x[r * d + c];
+    __shared__ float sm[256];
+    sm[threadIdx.x] = s;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (threadIdx.x < o) sm[threadIdx.x] += sm[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) out[c] = sm[0];
+}
+
+int wgrad_launch(const float* G, int64_t ldg, int O, const void* A, int a_dtype, int64_t lda, const int64_t* ids, int d,
+                 int64_t n, float* dW, int64_t lddw, cudaStream_t s) {
+    GS_CUDA(cudaMemsetAsync(dW, 0, sizeof(float) * (size_t)O * lddw, s));
+    if (n == 0) return GSAGE_OK;
+    // enough row chunks to fill the machine a few times over, at least 256 rows each
+    const int64_t tiles = ceil_div(O, WT) * ceil_div(d, WT);
+    int64_t chunks = std::max<int64_t>(1, std::min<int64_t>(ceil_div(n, 256), (4 * 148 + tiles - 1) / tiles));
+    const int64_t rows_per_cta = ceil_div(ceil_div(n, chunks), WR) * WR;
+    chunks = ceil_div(n, rows_per_cta);
+    dim3 grid((unsigned)ceil_div(d, WT), (unsigned)ceil_div(O, WT), (unsigned)chunks);
+    wgrad_simt_kernel<<<grid, 256, 0, s>>>(G, ldg, O, A, a_dtype, lda, ids, d, n, rows_per_cta, dW, lddw);
+    GS_LAUNCHED();
+    return GSAGE_OK;
+}
+
+int l2_normalize_bwd_launch(const float* z, const float* dzn, int64_t n, int d, int act, float* dz, cudaStream_t s) {
+    if (n == 0) return GSAGE_OK;
+    l2_normalize_bwd_kernel<<<(unsigned)ceil_div(n, 8), 256, 0, s>>>(z, dzn, n, d, act, dz);
+    GS_LAUNCHED();
+    return GSAGE_OK;
+}
+
+int layer1_grad_launch(const float* dh0, const float* dm2, const void* H, int h_dtype, int64_t ldh, int64_t n0, int64_t n1, int S,
+                       int width, int act, float* dH, cudaStream_t s) {
+    const int64_t total = (n0 + n1) * width;
+    if (total == 0) return GSAGE_OK;
+    layer1_grad_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, s>>>(dh0, dm2, H, h_dtype, ldh, n0, n1, S, width, act, dH);
+    GS_LAUNCHED();
+    return GSAGE_OK;
+}
+
+int colsum_launch(const float* x, int64_t n, int d, float* out, cudaStream_t s) {
+    colsum_kernel<<<d, 256, 0, s>>>(x, n, d, out);
+    GS_LAUNCHED();
+    return GSAGE_OK;
+}
+
+}  // namespace gsage

@@ -13,6 +13,7 @@
 #include "graph.cuh"
 #include "mt19937.cuh"
 #include "linear.cuh"
+#include "backward.cuh"
 
 #include <vector>
 #include <algorithm>
@@ -93,7 +94,8 @@ struct gsage_engine {
     // carved views
     int64_t* ids = nullptr; uint32_t* sel = nullptr; int64_t* look0 = nullptr;
     void* X = nullptr;                  // materialised prepped rows (non-identity preps)
-    void* M = nullptr;                  // reduced neighbour rows, one application at a time
+    void* M = nullptr;                  // reduced neighbour rows: [layer-1 app 1 (n0) | layer-1 app 2 (n1) | layer 2 (n0)] x ld_m
+    int64_t ld_m = 0;                   // (kept after the forward: the backward pass reads them)
     void* HN = nullptr; void* Pp = nullptr;          // pool: hidden rows / pooled rows
     void* T1 = nullptr; void* NA = nullptr; void* T1x = nullptr; void* XA = nullptr; float* AW = nullptr;   // attention
     void* H1 = nullptr;                 // layer-1 output (n0 + n1, 2*O1)
@@ -102,6 +104,8 @@ struct gsage_engine {
     // weights as the kernels read them (fp32 originals, or bf16 copies when compute dtype is bf16)
     char* wb = nullptr; int64_t wb_bytes = 0;
     WRef w_x[2], w_n[2], w_mlp[2], w_att1[2];
+    // backward scratch (fp32): d zn / d z (B x 2*O2), d h0 / d m2 (B x 2*O1), d H (26B x 2*O1)
+    float* DZN = nullptr; float* DZ = nullptr; float* DH0 = nullptr; float* DM2 = nullptr; float* DH = nullptr;
     bool fuse_mean = false;   // GSAGE_FUSE_MEAN=1: route the mean aggregator through the one-kernel fused layer (experimental)
 };
 
@@ -130,12 +134,13 @@ static int combine_call(const RowSrc& x, const WRef& Wx, const RowSrc& m, const 
 
 // one aggregator application: out[n, 2*O] = act([fc_x(x) | fc_neib(reduce(nb))])   (nn_modules.py:196-204 etc.)
 static int apply_aggregator(gsage_engine* e, int layer, const RowSrc& x, const RowSrc& nb, int64_t n, int S, void* out,
-                            int out_dtype, int64_t ld_out, cudaStream_t s) {
+                            int out_dtype, int64_t ld_out, int64_t m_row0, cudaStream_t s) {
     const gsage_layer_weights& L = e->w.layer[layer];
     const int O = e->cfg.out_dim[layer], act = e->cfg.act[layer], T = e->T;
     const int exact = (T == GSAGE_F32);
     const int d = x.d;
-    const int64_t ldm = pad_to(d, 16 / (int64_t)dtype_size(T) * 2);
+    const int64_t ldm = e->ld_m;
+    void* const Mb = (char*)e->M + m_row0 * ldm * (int64_t)dtype_size(T);
     switch (e->cfg.aggregator) {
     case GSAGE_AGG_MEAN: {
         if (T == GSAGE_BF16 && e->w_x[layer].dtype == GSAGE_BF16 && e->fuse_mean) {
@@ -160,11 +165,11 @@ static int apply_aggregator(gsage_engine* e, int layer, const RowSrc& x, const R
             }
         }
         const int p_red = e->prof.begin(GSAGE_PROF_REDUCE, s);
-        GS_TRY(gather_reduce_launch(nb.base, nb.dtype, nb.ld, nb.table_rows, d, nb.ids, n, S, GSAGE_RED_MEAN, nullptr, e->M, T, ldm, s));
+        GS_TRY(gather_reduce_launch(nb.base, nb.dtype, nb.ld, nb.table_rows, d, nb.ids, n, S, GSAGE_RED_MEAN, nullptr, Mb, T, ldm, s));
         e->prof.end(p_red, s);
         // algorithmic bytes of the fused gather+mean launch: S rows + S ids in, one row out
         if (p_red >= 0) e->prof.bytes[GSAGE_PROF_REDUCE] += (double)n * ((double)S * d * dtype_size(nb.dtype) + (nb.ids ? 8.0 * S : 0.0) + (double)d * dtype_size(T));
-        RowSrc m{e->M, T, ldm, n, nullptr, d};
+        RowSrc m{Mb, T, ldm, n, nullptr, d};
         const int p_prj = e->prof.begin(GSAGE_PROF_PROJECT, s);
         const int st = combine_call(x, e->w_x[layer], m, e->w_n[layer], O, n, act, out, out_dtype, ld_out, exact, s);
         e->prof.end(p_prj, s);
@@ -191,8 +196,8 @@ static int apply_aggregator(gsage_engine* e, int layer, const RowSrc& x, const R
         RowSrc t1x{e->T1x, GSAGE_F32, H, n, nullptr, H};
         GS_TRY(linear_call(t1x, f32w(L.att_w2, H), H, nullptr, n, GSAGE_ACT_NONE, e->XA, GSAGE_F32, H, 0, 1, s));
         GS_TRY(gsage_attention_weights(e->NA, e->XA, GSAGE_F32, H, H, n, S, e->AW, s));
-        GS_TRY(gather_reduce_launch(nb.base, nb.dtype, nb.ld, nb.table_rows, d, nb.ids, n, S, GSAGE_RED_SUM, e->AW, e->M, T, ldm, s));
-        RowSrc m{e->M, T, ldm, n, nullptr, d};
+        GS_TRY(gather_reduce_launch(nb.base, nb.dtype, nb.ld, nb.table_rows, d, nb.ids, n, S, GSAGE_RED_SUM, e->AW, Mb, T, ldm, s));
+        RowSrc m{Mb, T, ldm, n, nullptr, d};
         return combine_call(x, e->w_x[layer], m, e->w_n[layer], O, n, act, out, out_dtype, ld_out, exact, s);
     }
     }
@@ -244,7 +249,8 @@ int gsage_engine_create(const gsage_engine_config* cfg, gsage_engine** out) {
     const int64_t o_look = carve(8 * e->n0);
     const int64_t o_X = cfg->prep == GSAGE_PREP_IDENTITY ? -1 : carve(es * e->ld_prep * (e->n0 + e->n1 + e->n2));
     const int64_t dmax = std::max<int64_t>(e->ld_prep, e->ld_h1);
-    const int64_t o_M = carve(es * pad_to(dmax, vec * 2) * e->n1);
+    e->ld_m = pad_to(dmax, vec * 2);
+    const int64_t o_M = carve(es * e->ld_m * (e->n0 + e->n1 + e->n0));
     int64_t o_HN = -1, o_P = -1, o_T1 = -1, o_NA = -1, o_T1x = -1, o_XA = -1, o_AW = -1;
     if (cfg->aggregator == GSAGE_AGG_MAX_POOL || cfg->aggregator == GSAGE_AGG_MEAN_POOL) {
         o_HN = carve(es * e->hid * e->n2);
@@ -259,6 +265,9 @@ int gsage_engine_create(const gsage_engine_config* cfg, gsage_engine** out) {
     const int64_t o_Z = carve(4 * 2 * O2 * e->n0);
     const int64_t o_ZN = carve(4 * 2 * O2 * e->n0);
     const int64_t o_LG = carve(4 * (int64_t)cfg->n_classes * e->n0);
+    const int64_t o_DZN = carve(4 * 2 * O2 * e->n0), o_DZ = carve(4 * 2 * O2 * e->n0);
+    const int64_t o_DH0 = carve(4 * 2 * O1 * e->n0), o_DM2 = carve(4 * 2 * O1 * e->n0);
+    const int64_t o_DH = carve(4 * 2 * O1 * (e->n0 + e->n1));
     e->ws_bytes = off;
     if (cudaMalloc((void**)&e->ws, (size_t)off) != cudaSuccess) {
         set_error("engine_create: cudaMalloc of %lld workspace bytes failed", (long long)off);
@@ -281,6 +290,7 @@ int gsage_engine_create(const gsage_engine_config* cfg, gsage_engine** out) {
     e->X = at(o_X); e->M = at(o_M); e->HN = at(o_HN); e->Pp = at(o_P);
     e->T1 = at(o_T1); e->NA = at(o_NA); e->T1x = at(o_T1x); e->XA = at(o_XA); e->AW = (float*)at(o_AW);
     e->H1 = at(o_H1); e->Z = (float*)at(o_Z); e->ZN = (float*)at(o_ZN); e->LG = (float*)at(o_LG);
+    e->DZN = (float*)at(o_DZN); e->DZ = (float*)at(o_DZ); e->DH0 = (float*)at(o_DH0); e->DM2 = (float*)at(o_DM2); e->DH = (float*)at(o_DH);
     *out = e;
     return GSAGE_OK;
 }
@@ -421,12 +431,12 @@ int gsage_engine_forward(gsage_engine* e, gsage_graph* g, gsage_rng* rng, const 
     // ---- layer 1 on (x0, x1) and (x1, x2) with shared weights (models.py:85-86) ---------------------------
     const int64_t ldh = e->ld_h1;
     const int O1 = c.out_dim[0], O2 = c.out_dim[1];
-    GS_TRY(apply_aggregator(e, 0, lvl, lvl.shifted(n0), n0, S1, e->H1, T, ldh, s));
-    GS_TRY(apply_aggregator(e, 0, lvl.shifted(n0), lvl.shifted(n0 + n1), n1, S2, (char*)e->H1 + n0 * ldh * es, T, ldh, s));
+    GS_TRY(apply_aggregator(e, 0, lvl, lvl.shifted(n0), n0, S1, e->H1, T, ldh, 0, s));
+    GS_TRY(apply_aggregator(e, 0, lvl.shifted(n0), lvl.shifted(n0 + n1), n1, S2, (char*)e->H1 + n0 * ldh * es, T, ldh, n0, s));
 
     // ---- layer 2 on (h0, h1) ----------------------------------------------------------------------------------
     RowSrc h{e->H1, T, ldh, n0 + n1, nullptr, 2 * O1};
-    GS_TRY(apply_aggregator(e, 1, h, h.shifted(n0), n0, S1, e->Z, GSAGE_F32, 2 * O2, s));
+    GS_TRY(apply_aggregator(e, 1, h, h.shifted(n0), n0, S1, e->Z, GSAGE_F32, 2 * O2, n0 + n1, s));
 
     // ---- normalise + classifier (models.py:90-91) -----------------------------------------------------------------
     GS_TRY(gsage_l2_normalize(e->Z, GSAGE_F32, 2 * O2, n0, 2 * O2, e->ZN, 2 * O2, s));
@@ -457,6 +467,60 @@ int gsage_engine_forward_host(gsage_engine* e, gsage_graph* g, gsage_rng* rng, c
     if (st == GSAGE_OK) st = gsage_rng_check(rng, stream);
     if (st == GSAGE_OK) st = gsage_graph_check(g, stream);
     return st;
+}
+
+static int linear_trans_call(const float* a, int64_t lda, int d, const float* W, int64_t ldw, int O, int64_t n, float* out,
+                             int64_t ld_out, cudaStream_t s) {
+    LinearParams P;                                  // out (n x O) = a (n x d) . W (d x O): the data gradient of a Linear
+    P.n_segs = 1; P.n = n; P.act = GSAGE_ACT_NONE; P.out = out; P.out_dtype = GSAGE_F32; P.ld_out = ld_out;
+    P.seg[0] = LinearSeg{a, GSAGE_F32, lda, nullptr, W, GSAGE_F32, ldw, d, O, nullptr, 0};
+    P.seg[0].w_trans = 1;
+    if (n == 0) return GSAGE_OK;
+    return linear_simt_launch(P, s);
+}
+
+static int backward_supported(gsage_engine* e) {
+    GS_CHECK_ARG(e && e->have_weights && e->B > 0, "engine_backward: run gsage_engine_forward first");
+    GS_CHECK_ARG(e->cfg.aggregator == GSAGE_AGG_MEAN && e->cfg.prep == GSAGE_PREP_IDENTITY,
+                 "engine_backward: implemented for the mean aggregator with the identity prep (the other plug-ins are forward-only this round)");
+    GS_CHECK_ARG(!e->fuse_mean, "engine_backward: needs the reduced rows the fused (GSAGE_FUSE_MEAN) layer never writes");
+    return GSAGE_OK;
+}
+
+int gsage_engine_backward_head(gsage_engine* e, const float* dlogits, const gsage_grads* g, void* stream) {
+    GS_TRY(backward_supported(e));
+    GS_CHECK_ARG(dlogits && g && g->fc_w && g->fc_b && g->fc_x[1] && g->fc_neib[1], "engine_backward_head: NULL argument");
+    cudaStream_t s = as_stream(stream);
+    const gsage_engine_config& c = e->cfg;
+    const int64_t n0 = e->B, n1 = n0 * c.fanout[0];
+    const int O1 = c.out_dim[0], O2 = c.out_dim[1], C = c.n_classes, S1 = c.fanout[0];
+    const int64_t es = (int64_t)dtype_size(e->T);
+    // classifier: logits = zn . Wfc^T + b
+    GS_TRY(wgrad_launch(dlogits, C, C, e->ZN, GSAGE_F32, 2 * O2, nullptr, 2 * O2, n0, g->fc_w, 2 * O2, s));
+    GS_TRY(colsum_launch(dlogits, n0, C, g->fc_b, s));
+    GS_TRY(linear_trans_call(dlogits, C, C, e->w.fc_w, 2 * O2, 2 * O2, n0, e->DZN, 2 * O2, s));
+    // F.normalize + layer-2 activation
+    GS_TRY(l2_normalize_bwd_launch(e->Z, e->DZN, n0, 2 * O2, c.act[1], e->DZ, s));
+    // layer 2: z = [h0 Wx2^T | m2 Wn2^T]
+    const void* m2 = (const char*)e->M + (n0 + n1) * e->ld_m * es;
+    GS_TRY(wgrad_launch(e->DZ, 2 * O2, O2, e->H1, e->T, e->ld_h1, nullptr, 2 * O1, n0, g->fc_x[1], 2 * O1, s));
+    GS_TRY(wgrad_launch(e->DZ + O2, 2 * O2, O2, m2, e->T, e->ld_m, nullptr, 2 * O1, n0, g->fc_neib[1], 2 * O1, s));
+    GS_TRY(linear_trans_call(e->DZ, 2 * O2, O2, e->w.layer[1].fc_x, 2 * O1, 2 * O1, n0, e->DH0, 2 * O1, s));
+    GS_TRY(linear_trans_call(e->DZ + O2, 2 * O2, O2, e->w.layer[1].fc_neib, 2 * O1, 2 * O1, n0, e->DM2, 2 * O1, s));
+    // mean over S1 children + concat + layer-1 activation, backwards
+    return layer1_grad_launch(e->DH0, e->DM2, e->H1, e->T, e->ld_h1, n0, n1, S1, 2 * O1, c.act[0], e->DH, s);
+}
+
+int gsage_engine_backward_layer1(gsage_engine* e, const gsage_grads* g, void* stream) {
+    GS_TRY(backward_supported(e));
+    GS_CHECK_ARG(g && g->fc_x[0] && g->fc_neib[0], "engine_backward_layer1: NULL argument");
+    cudaStream_t s = as_stream(stream);
+    const gsage_engine_config& c = e->cfg;
+    const int64_t n0 = e->B, n1 = n0 * c.fanout[0];
+    const int O1 = c.out_dim[0], d = c.feats_dim;
+    // h = act([table[ids01] Wx1^T | M01 Wn1^T]): both weight gradients reduce over all n0 + n1 parent rows
+    GS_TRY(wgrad_launch(e->DH, 2 * O1, O1, c.feats_dev, c.feats_dtype, c.feats_ld, e->ids, d, n0 + n1, g->fc_x[0], d, s));
+    return wgrad_launch(e->DH + O1, 2 * O1, O1, e->M, e->T, e->ld_m, nullptr, d, n0 + n1, g->fc_neib[0], d, s);
 }
 
 int gsage_engine_peek(gsage_engine* e, int what, const void** ptr, int64_t* rows, int64_t* cols, int64_t* ld, int* dtype) {

@@ -8,7 +8,8 @@ struct LinearSeg {
     const void* a; int a_dtype; int64_t lda; const int64_t* ids;
     const void* w; int w_dtype; int64_t ldw; int d; int O;
     const float* bias; int64_t col0;
-    int S = 1;      // > 1: A row r = mean_j A[ids[r*S + j]] (fused gather+mean; tensor-core kernel only)
+    int S = 1;      // > 1: A row r = mean_j A[ids[r*S + j]] (fused gather+mean)
+    int w_trans = 0;   // 1: W is stored (d x O): element (o, k) at w[k * ldw + o]  (backward: dX = dY . W; FFMA kernel only)
 };
 
 struct LinearParams {

@@ -68,7 +68,7 @@ __global__ void __launch_bounds__(256) linear_simt_kernel(LinearParams P) {
                     a *= inv_S;
                 }
             }
-            if (w_row < sg.O && k < sg.d) w = load_any(sg.w, sg.w_dtype, (int64_t)w_row * sg.ldw + k);
+            if (w_row < sg.O && k < sg.d) w = load_any(sg.w, sg.w_dtype, sg.w_trans ? (int64_t)k * sg.ldw + w_row : (int64_t)w_row * sg.ldw + k);
             As[lk + q][lrow] = a;
             Ws[lk + q][lrow] = w;
         }
@@ -127,11 +127,11 @@ extern "C" int gsage_linear(const gsage_linear_seg* segs, int n_segs, int64_t n,
     P.n_segs = n_segs; P.n = n; P.act = act; P.out = out_dev; P.out_dtype = out_dtype; P.ld_out = ld_out;
     for (int i = 0; i < n_segs; ++i) {
         const gsage_linear_seg& g = segs[i];
-        GS_CHECK_ARG(g.a_dev && g.w_dev && g.d > 0 && g.O > 0 && g.lda >= g.d && g.ldw >= g.d && g.col0 >= 0 &&
+        GS_CHECK_ARG(g.a_dev && g.w_dev && g.d > 0 && g.O > 0 && g.lda >= g.d && g.ldw >= (g.w_transposed ? g.O : g.d) && g.col0 >= 0 &&
                      g.col0 + g.O <= ld_out, "linear: bad segment %d", i);
         P.seg[i].a = g.a_dev; P.seg[i].a_dtype = g.a_dtype; P.seg[i].lda = g.lda; P.seg[i].ids = g.ids_dev;
         P.seg[i].w = g.w_dev; P.seg[i].w_dtype = g.w_dtype; P.seg[i].ldw = g.ldw; P.seg[i].d = g.d; P.seg[i].O = g.O;
-        P.seg[i].bias = g.bias_dev; P.seg[i].col0 = g.col0; P.seg[i].S = g.reduce_S > 1 ? g.reduce_S : 1;
+        P.seg[i].bias = g.bias_dev; P.seg[i].col0 = g.col0; P.seg[i].S = g.reduce_S > 1 ? g.reduce_S : 1; P.seg[i].w_trans = g.w_transposed ? 1 : 0;
     }
     if (n == 0) return GSAGE_OK;
     return linear_dispatch(P, exact, as_stream(stream));
@@ -143,6 +143,7 @@ namespace gsage {
 // anything else -- and everything when `exact` is set -- runs on the fp32 FFMA kernel.
 int linear_dispatch(const LinearParams& P, int exact, cudaStream_t s) {
     bool tc = !exact;
+    for (int i = 0; i < P.n_segs; ++i) tc = tc && !P.seg[i].w_trans;
     for (int i = 0; i < P.n_segs && tc; ++i) {
         LinearParams one = P;
         one.n_segs = 1; one.seg[0] = P.seg[i];

@@ -194,6 +194,56 @@ class GSSupervised(nn.Module):
         self._last = eng
         return logits_host
 
+    # -- training (models.py:97-104) ---------------------------------------------------------------------
+    def _bucket(self):
+        from .parallel import FlatGradBucket
+        if getattr(self, '_grad_bucket', None) is None:
+            head = list(self.fc.parameters()) + list(self.agg_layers[1].parameters())
+            self._grad_bucket = FlatGradBucket(self.parameters(), head=head)
+            self._grad_bucket.attach()
+        return self._grad_bucket
+
+    def backward(self, dlogits, grad_scale=1.0, overlap_stream=None):
+        """Parameter gradients of the last forward into the flat bucket (p.grad are views of it), summed over the
+        ranks of the default process group.  `dlogits` = d loss / d logits (B, n_classes) fp32 on the GPU.
+        `grad_scale` weights this rank's contribution (local_batch / global_batch for a mean loss).
+        The head (fc + layer 2) is all-reduced on `overlap_stream` while layer 1's weight gradients are computed."""
+        bucket = self._bucket()
+        g = _lib.Grads()
+        aggs = list(self.agg_layers.children())
+        for k in range(2):
+            g.fc_x[k] = bucket.grad_of(aggs[k].fc_x.weight).data_ptr()
+            g.fc_neib[k] = bucket.grad_of(aggs[k].fc_neib.weight).data_ptr()
+        g.fc_w, g.fc_b = bucket.grad_of(self.fc.weight).data_ptr(), bucket.grad_of(self.fc.bias).data_ptr()
+        dlogits = dlogits.contiguous().float()
+        check(lib().gsage_engine_backward_head(self._last['h'], ops.ptr(dlogits), C.byref(g), ops.stream()))
+        main = torch.cuda.current_stream()
+        if overlap_stream is not None:
+            overlap_stream.wait_stream(main)
+            with torch.cuda.stream(overlap_stream):
+                bucket.all_reduce_head(grad_scale)
+        check(lib().gsage_engine_backward_layer1(self._last['h'], C.byref(g), ops.stream()))
+        if overlap_stream is None:
+            bucket.all_reduce(grad_scale)
+        else:
+            bucket.all_reduce_tail(grad_scale)
+            main.wait_stream(overlap_stream)
+        return bucket
+
+    def train_step(self, ids, feats, targets, loss_fn, optimizer=None, clip=5.0, grad_scale=1.0, overlap_stream=None):
+        """models.py:97-104: forward, loss, backward, clip-norm 5, optimiser step.  The loss and the optimiser are
+        stock torch (out of scope); forward and parameter gradients run in the library."""
+        preds = self(ids, feats, train=True)
+        leaf = preds.detach().requires_grad_(True)
+        loss = loss_fn(leaf, targets.squeeze())
+        dlogits, = torch.autograd.grad(loss, leaf)
+        self.backward(dlogits, grad_scale=grad_scale, overlap_stream=overlap_stream)
+        if clip:
+            torch.nn.utils.clip_grad_norm_(self.parameters(), clip)
+        if optimizer is not None:
+            optimizer.step()
+        return preds, loss.detach()
+
     def profile(self, enable=True):
         """Switch the engine's CUDA-event stopwatch on/off (all engines of this model)."""
         for eng in self._engines.values():

@@ -112,7 +112,7 @@ def linear(segments, n, act=None, out=None, out_dtype=torch.float32, exact=True)
         assert w.is_cuda and w.dim() == 2 and w.stride(1) == 1
         bias = sgm.get('bias')
         segs[i] = _lib.LinearSeg(ptr(a), dt(a), _rows2d(a), _ids_arg(sgm.get('ids')), ptr(w), dt(w), _rows2d(w), d,
-                                 w.shape[0], ptr(bias), sgm.get('col0', 0), int(sgm.get('S', 1)))
+                                 w.shape[0], ptr(bias), sgm.get('col0', 0), int(sgm.get('S', 1)), 0)
         width = max(width, sgm.get('col0', 0) + w.shape[0])
     if out is None:
         out = torch.empty((n, width), dtype=out_dtype, device=segments[0]['a'].device)

@@ -1,0 +1,70 @@
+"""
+Seed-node data parallelism: one process per GPU, graph + feature table replicated, every rank
+samples / gathers / aggregates its own slice of the seed batch, and the ONLY collective is a sum all-reduce of the
+parameter gradients, carried in one flat bucket so it is a single NCCL call (two when the head is overlapped with
+the layer-1 weight gradients).  Works on any torch.distributed backend (NCCL on the GPUs, gloo in the CPU tests).
+"""
+
+import torch
+import torch.distributed as dist
+
+
+def shard_seeds(ids, rank, world):
+    """This rank's contiguous slice of the (already shuffled) global seed batch; slices partition the batch and
+    differ in length by at most one (np.array_split semantics, like problem.py:148)."""
+    n = ids.shape[0]
+    base, extra = divmod(n, world)
+    lo = rank * base + min(rank, extra)
+    hi = lo + base + (1 if rank < extra else 0)
+    return ids[lo:hi]
+
+
+class FlatGradBucket(object):
+    """All parameter gradients of a model as views into ONE contiguous fp32 buffer.
+
+    `head` parameters (the small late layers whose gradients exist first) sit at the front so that
+    `all_reduce_head()` can start while the big layer-1 weight gradients are still being computed."""
+
+    def __init__(self, params, head=(), device=None):
+        params = list(params)
+        head_ids = set(id(p) for p in head)
+        order = [p for p in params if id(p) in head_ids] + [p for p in params if id(p) not in head_ids]
+        device = device or order[0].device
+        self.flat = torch.zeros(sum(p.numel() for p in order), dtype=torch.float32, device=device)
+        self.views, off = {}, 0
+        for p in order:
+            self.views[id(p)] = self.flat[off:off + p.numel()].view_as(p)
+            off += p.numel()
+            if id(p) in head_ids:
+                self.head_numel = off
+        if not head_ids:
+            self.head_numel = 0
+        self.params = order
+
+    def grad_of(self, p):
+        return self.views[id(p)]
+
+    def attach(self):
+        """Point every parameter's .grad at its slice (the optimiser then reads the reduced values in place)."""
+        for p in self.params:
+            p.grad = self.views[id(p)]
+
+    def _reduce(self, t, scale, async_op=False):
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            work = dist.all_reduce(t, op=dist.ReduceOp.SUM, async_op=async_op)
+            if async_op:
+                return work
+        if scale != 1.0:
+            t.mul_(scale)
+        return None
+
+    def all_reduce(self, scale=1.0):
+        """Sum over ranks, then `scale` (local/global batch weighting so the result equals the single-process
+        gradient of the mean loss over the GLOBAL batch, problem.py:33)."""
+        self._reduce(self.flat, scale)
+
+    def all_reduce_head(self, scale=1.0):
+        self._reduce(self.flat[:self.head_numel], scale)
+
+    def all_reduce_tail(self, scale=1.0):
+        self._reduce(self.flat[self.head_numel:], scale)
