@@ -63,6 +63,7 @@ def parse_args():
     ap.add_argument('--cpu-batch', type=int, default=512, help='seed nodes per CPU-baseline step (train.py:48)')
     ap.add_argument('--cpu-seconds', type=float, default=12.0, help='budget of the cpu_baseline leg')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-train', action='store_true', help='skip the train-step leg')
     ap.add_argument('--scale', type=float, default=1.0, help='shrink the graph (debug only; reported in config)')
     return ap.parse_args()
 
@@ -330,6 +331,32 @@ def run_ours(args):
     e2e_ms = max(e2e_ms, e2e_wall_ms)
     e2e_value = WORLD * B * ROWS_PER_SEED / (e2e_ms / 1e3)
 
+    # ---- one optimiser step per batch (forward + loss + backward + gradient all-reduce + clip + Adam) ---------------
+    train = None
+    if prob['aggregator'] == 'mean' and prob['prep'] == 'identity' and not args.no_train:
+        from torch.nn import functional as F
+        tgt_all = torch.from_numpy(prob['targets'].reshape(-1)).cuda()
+        tgts = [tgt_all[i] for i in dev_ids]
+        opt = torch.optim.Adam(model.parameters(), lr=0.01)
+        side = torch.cuda.Stream()
+        k_train = max(3, min(args.steps, 30))
+        for i in range(3):
+            model.train_step(dev_ids[i % n_batches], table, tgts[i % n_batches], F.cross_entropy, optimizer=opt, grad_scale=1.0 / WORLD,
+                             overlap_stream=side)
+        barrier()
+        ev0.record()
+        for i in range(k_train):
+            model.train_step(dev_ids[i % n_batches], table, tgts[i % n_batches], F.cross_entropy, optimizer=opt, grad_scale=1.0 / WORLD,
+                             overlap_stream=side)
+        ev1.record()
+        barrier()
+        t_ms = max_over_ranks(ev0.elapsed_time(ev1)) / k_train
+        train = {'ms_per_step': t_ms, 'seeds_per_s': WORLD * B / (t_ms / 1e3), 'steps': k_train,
+                 'allreduce_bytes_per_step': int(model._bucket().flat.numel()) * 4,
+                 'collective': 'one flat fp32 gradient bucket, NCCL all-reduce in two pieces (fc + layer-2 head overlapped with the '
+                               'layer-1 weight-gradient kernels)' if WORLD > 1 else 'none (1 GPU)',
+                 'note': 'backward = fp32 FFMA wgrad kernels (tensor-core wgrad is a next-round item); loss + Adam are stock torch'}
+
     if RANK != 0:
         if WORLD > 1:
             dist.destroy_process_group()
@@ -362,6 +389,8 @@ def run_ours(args):
                                   # fused build: the projection runs inside the gather+aggregate kernel (no time of its own)
                                   'project_tflops': (prj_flops / 1e12) / ((prj_ms if prj_ms > 0 else red_ms) / 1e3) if (prj_ms + red_ms) > 0 else None},
     }
+    if train is not None:
+        line['train'] = train
     if not args.no_cpu_baseline:
         v, ms, steps = cpu_reference_throughput(prob, args.cpu_batch, None, 2, seconds=args.cpu_seconds)
         line['cpu_baseline'] = {'value': v, 'unit': UNIT, 'cores': torch.get_num_threads(), 'kind': 'port',

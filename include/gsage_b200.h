@@ -211,6 +211,11 @@ int gsage_engine_set_weights(gsage_engine* e, const gsage_weights* w, void* stre
  * Sampling draws from `rng` (device stream), hop 0 then hop 1. */
 int gsage_engine_forward(gsage_engine* e, gsage_graph* g, gsage_rng* rng, const int64_t* ids_dev, int64_t B,
                          float* logits_dev, void* stream);
+/* Seed-sharded forward that stays bit-exact with the single-process run: `ids_dev` holds seeds [first, first+B) of a
+ * global batch of `global_B` seeds; the rank consumes the whole global batch's draws from its (identically seeded)
+ * stream and samples with its slice of them.  global_B == B, first == 0 is gsage_engine_forward. */
+int gsage_engine_forward_sharded(gsage_engine* e, gsage_graph* g, gsage_rng* rng, const int64_t* ids_dev, int64_t B,
+                                 int64_t global_B, int64_t first, float* logits_dev, void* stream);
 /* the same call for host buffers: H2D of the seed ids, forward, D2H of the logits, stream-synchronised.
  * This is the end-to-end entry a reference-side caller binds (ids and logits are what models.py:71 takes/returns). */
 int gsage_engine_forward_host(gsage_engine* e, gsage_graph* g, gsage_rng* rng, const int64_t* ids_host, int64_t B,

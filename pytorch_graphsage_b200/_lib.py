@@ -84,6 +84,7 @@ _SIGNATURES = {
     'gsage_engine_destroy': (None, [c_p]),
     'gsage_engine_set_weights': (C.c_int, [c_p, C.POINTER(Weights), c_p]),
     'gsage_engine_forward': (C.c_int, [c_p, c_p, c_p, c_p, c_i64, c_p, c_p]),
+    'gsage_engine_forward_sharded': (C.c_int, [c_p, c_p, c_p, c_p, c_i64, c_i64, c_i64, c_p, c_p]),
     'gsage_engine_forward_host': (C.c_int, [c_p, c_p, c_p, c_p, c_i64, c_p, c_p]),
     'gsage_engine_peek': (C.c_int, [c_p, C.c_int, C.POINTER(c_p), C.POINTER(c_i64), C.POINTER(c_i64), C.POINTER(c_i64), C.POINTER(C.c_int)]),
     'gsage_engine_workspace_bytes': (c_i64, [c_p]),

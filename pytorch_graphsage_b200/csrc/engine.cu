@@ -377,7 +377,14 @@ int gsage_engine_set_weights(gsage_engine* e, const gsage_weights* w, void* stre
 
 int gsage_engine_forward(gsage_engine* e, gsage_graph* g, gsage_rng* rng, const int64_t* ids_dev, int64_t B,
                          float* logits_dev, void* stream) {
+    return gsage_engine_forward_sharded(e, g, rng, ids_dev, B, B, 0, logits_dev, stream);
+}
+
+int gsage_engine_forward_sharded(gsage_engine* e, gsage_graph* g, gsage_rng* rng, const int64_t* ids_dev, int64_t B,
+                                 int64_t global_B, int64_t first, float* logits_dev, void* stream) {
     GS_CHECK_ARG(e && g && rng && ids_dev && logits_dev, "engine_forward: NULL argument");
+    GS_CHECK_ARG(global_B >= B && first >= 0 && first + B <= global_B, "engine_forward_sharded: slice [%lld, %lld) outside the global batch of %lld",
+                 (long long)first, (long long)(first + B), (long long)global_B);
     GS_CHECK_ARG(e->have_weights, "engine_forward: call gsage_engine_set_weights first");
     GS_CHECK_ARG(B > 0 && B <= e->maxB, "engine_forward: batch %lld outside (0, max_batch=%lld]", (long long)B, (long long)e->maxB);
     GS_CHECK_ARG(g->n_cols >= 1 && g->n_cols <= 0xFFFFFFFFLL, "engine_forward: adjacency width out of range");
@@ -393,10 +400,25 @@ int gsage_engine_forward(gsage_engine* e, gsage_graph* g, gsage_rng* rng, const 
     // ---- sample: hop 0 draws first, then hop 1 (models.py:78-79) ------------------------------------
     int64_t* ids0 = e->ids; int64_t* ids1 = ids0 + n0; int64_t* ids2 = ids1 + n1;
     if (ids_dev != ids0) GS_CUDA(cudaMemcpyAsync(ids0, ids_dev, 8 * n0, cudaMemcpyDeviceToDevice, s));
-    GS_TRY(rng_randint_internal(rng, (uint32_t)g->n_cols, n1, e->sel, s));
-    GS_TRY(sample_sparse_launch(g, ids0, n0, S1, e->sel, ids1, s));
-    GS_TRY(rng_randint_internal(rng, (uint32_t)g->n_cols, n2, e->sel, s));
-    GS_TRY(sample_sparse_launch(g, ids1, n1, S2, e->sel, ids2, s));
+    if (global_B == B) {
+        GS_TRY(rng_randint_internal(rng, (uint32_t)g->n_cols, n1, e->sel, s));
+        GS_TRY(sample_sparse_launch(g, ids0, n0, S1, e->sel, ids1, s));
+        GS_TRY(rng_randint_internal(rng, (uint32_t)g->n_cols, n2, e->sel, s));
+        GS_TRY(sample_sparse_launch(g, ids1, n1, S2, e->sel, ids2, s));
+    } else {
+        // seed-sharded, still bit-exact with the single-process run: every rank consumes the draws of the WHOLE
+        // global batch (hop-0 block, then hop-1 block -- the cheap part) and uses the slice that belongs to its seeds;
+        // the gather / aggregate / project work is what is sharded
+        const int64_t g1 = global_B * S1, g2 = g1 * S2;
+        uint32_t* gsel = nullptr;
+        GS_CUDA(cudaMallocAsync((void**)&gsel, sizeof(uint32_t) * g2, s));
+        int st = rng_randint_internal(rng, (uint32_t)g->n_cols, g1, gsel, s);
+        if (st == GSAGE_OK) st = sample_sparse_launch(g, ids0, n0, S1, gsel + first * S1, ids1, s);
+        if (st == GSAGE_OK) st = rng_randint_internal(rng, (uint32_t)g->n_cols, g2, gsel, s);
+        if (st == GSAGE_OK) st = sample_sparse_launch(g, ids1, n1, S2, gsel + first * S1 * S2, ids2, s);
+        cudaFreeAsync(gsel, s);
+        GS_TRY(st);
+    }
     e->prof.end(p_smp, s);
 
     // ---- prep (models.py:76-81) ------------------------------------------------------------------------

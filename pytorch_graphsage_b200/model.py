@@ -163,7 +163,7 @@ class GSSupervised(nn.Module):
             eng['stamp'] = stamp
 
     # -- the reference's public surface ---------------------------------------------------------------
-    def forward(self, ids, feats, train=True):
+    def forward(self, ids, feats, train=True, shard=None):
         """models.py:71-91.  `ids`: int64 tensor of seed ids (CUDA, or CPU -> copied); `feats`: the node feature
         table (tensor / FeatureTable) or None.  Returns fp32 logits (B, n_classes) on the GPU."""
         sampler = self.train_sampler if train else self.val_sampler
@@ -176,7 +176,11 @@ class GSSupervised(nn.Module):
         self._push_weights(eng)
         rng = sampler.rng or self.rng or default_rng()
         out = torch.empty((ids.shape[0], self.n_classes), dtype=torch.float32, device='cuda')
-        check(lib().gsage_engine_forward(eng['h'], sampler.graph._h, rng._h, ops.ptr(ids), ids.shape[0], ops.ptr(out), ops.stream()))
+        if shard is None:
+            check(lib().gsage_engine_forward(eng['h'], sampler.graph._h, rng._h, ops.ptr(ids), ids.shape[0], ops.ptr(out), ops.stream()))
+        else:                                  # (global_batch, first): this rank holds seeds [first, first + len(ids))
+            check(lib().gsage_engine_forward_sharded(eng['h'], sampler.graph._h, rng._h, ops.ptr(ids), ids.shape[0], int(shard[0]),
+                                                     int(shard[1]), ops.ptr(out), ops.stream()))
         self._last = eng
         return out
 
@@ -230,10 +234,10 @@ class GSSupervised(nn.Module):
             main.wait_stream(overlap_stream)
         return bucket
 
-    def train_step(self, ids, feats, targets, loss_fn, optimizer=None, clip=5.0, grad_scale=1.0, overlap_stream=None):
+    def train_step(self, ids, feats, targets, loss_fn, optimizer=None, clip=5.0, grad_scale=1.0, overlap_stream=None, shard=None):
         """models.py:97-104: forward, loss, backward, clip-norm 5, optimiser step.  The loss and the optimiser are
         stock torch (out of scope); forward and parameter gradients run in the library."""
-        preds = self(ids, feats, train=True)
+        preds = self(ids, feats, train=True, shard=shard)
         leaf = preds.detach().requires_grad_(True)
         loss = loss_fn(leaf, targets.squeeze())
         dlogits, = torch.autograd.grad(loss, leaf)
