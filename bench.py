@@ -85,7 +85,7 @@ class ClockSampler(object):
         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
 
     def __init__(self, index):
-        self.index, self.proc, self.path = index, None, '/tmp/gsage_clocks_%d_%d.csv' % (os.getpid(), index)
+        self.index, self.proc, self.path = index, None, '/tmp/gsage_clocks_%d.csv' % os.getpid()
 
     def start(self):
         try:
@@ -247,17 +247,15 @@ def run_reference(args):
 
 # ---------------------------------------------------------------------------------------------------
 def run_ours(args):
-    if WORLD > 1:
-        os.environ.setdefault('CUDA_VISIBLE_DEVICES', str(LOCAL_RANK))        # one process per GPU, device 0 in-process
     import numpy as np
     import torch
     import torch.distributed as dist
     import pytorch_graphsage_b200 as g
     from pytorch_graphsage_b200 import synth
 
-    torch.cuda.set_device(0 if WORLD > 1 else LOCAL_RANK)
+    torch.cuda.set_device(LOCAL_RANK)                                         # one process per GPU
     if WORLD > 1:
-        dist.init_process_group('nccl', device_id=torch.device('cuda', 0))
+        dist.init_process_group('nccl', device_id=torch.device('cuda', LOCAL_RANK))
 
     prob = make_problem(args)
     B = args.batch
@@ -297,7 +295,11 @@ def run_ours(args):
     g.default_rng().check()
     graph.check()
     model.profile(True)
-    clocks = ClockSampler(LOCAL_RANK)
+    try:
+        gpu_sel = 'GPU-' + str(torch.cuda.get_device_properties(LOCAL_RANK).uuid)
+    except Exception:
+        gpu_sel = str(LOCAL_RANK)
+    clocks = ClockSampler(gpu_sel)
     barrier()
     clocks.start()
     launches0 = g.launch_count()
