@@ -159,6 +159,7 @@ def cpu_reference_throughput(prob, batch, steps, warmup, seconds=None):
     import torch
     from oracle import layers, sampler as osampler
     from pytorch_graphsage_b200 import synth
+    host_threads()
     adj = prob['adj']
     indptr, data, shape = adj['indptr'], adj['data'], adj['shape']
     indices = np.arange(data.shape[0], dtype=np.int64) - np.repeat(indptr[:-1], np.diff(indptr))
@@ -191,6 +192,16 @@ def cpu_reference_throughput(prob, batch, steps, warmup, seconds=None):
                 break
     ms = 1e3 * sum(times) / len(times)
     return batch * ROWS_PER_SEED / (ms / 1e3), ms, len(times)
+
+
+def host_threads():
+    """All the host threads the CPU path can use.  torchrun exports OMP_NUM_THREADS=1 to every rank; the CPU legs
+    run on rank 0 alone, so give them the box (physical cores = half the logical CPUs, torch's own default)."""
+    import torch
+    want = max(1, (os.cpu_count() or 2) // 2)
+    if torch.get_num_threads() < want:
+        torch.set_num_threads(want)
+    return torch.get_num_threads()
 
 
 def reference_params(prob, seed=123):
@@ -255,6 +266,8 @@ def run_ours(args):
 
     torch.cuda.set_device(LOCAL_RANK)                                         # one process per GPU
     if WORLD > 1:
+        if os.environ.get('NCCL_DEBUG', '').upper() not in ('INFO', 'TRACE'):
+            os.environ['NCCL_DEBUG'] = 'WARN'                                  # keep stdout to the one JSON line
         dist.init_process_group('nccl', device_id=torch.device('cuda', LOCAL_RANK))
 
     prob = make_problem(args)
