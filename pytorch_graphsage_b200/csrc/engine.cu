@@ -49,6 +49,11 @@ __global__ void __launch_bounds__(256) to_bf16_padded_kernel(const float* __rest
     dst[i] = __float2bfloat16_rn(c < cols ? src[(int64_t)r * cols + c] : 0.0f);
 }
 
+__global__ void __launch_bounds__(256) axpy_kernel(float* y, const float* x, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) y[i] += x[i];
+}
+
 __global__ void __launch_bounds__(256) fill_i64_kernel(int64_t* p, int64_t n, int64_t v) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) p[i] = v;
@@ -106,6 +111,14 @@ struct gsage_engine {
     WRef w_x[2], w_n[2], w_mlp[2], w_att1[2];
     // backward scratch (fp32): d zn / d z (B x 2*O2), d h0 / d m2 (B x 2*O1), d H (26B x 2*O1)
     float* DZN = nullptr; float* DZ = nullptr; float* DH0 = nullptr; float* DM2 = nullptr; float* DH = nullptr;
+    // NodeEmbeddingPrep without feats is an affine map of the gathered embedding row; every consumer of layer 1 is
+    // linear in its input, so the affine is FOLDED into the layer-1 weights (W' = W.Wp, b' = W.bp [+ b]) at
+    // set_weights time: the aggregators then read the raw (n_nodes+1, 64) table by id and the prepped rows are
+    // never materialised (algebraically identical; fp32 rounding differs at the 1e-6 level)
+    bool fold_prep = false;
+    float* fold = nullptr; int64_t fold_floats = 0;
+    const float* b_x[2] = {nullptr, nullptr}; const float* b_n[2] = {nullptr, nullptr};
+    const float* b_mlp[2] = {nullptr, nullptr}; const float* b_att[2] = {nullptr, nullptr};
     bool fuse_mean = false;   // GSAGE_FUSE_MEAN=1: route the mean aggregator through the one-kernel fused layer (experimental)
 };
 
@@ -123,13 +136,24 @@ static int linear_call(const RowSrc& a, const WRef& W, int O, const float* bias,
 }
 
 static int combine_call(const RowSrc& x, const WRef& Wx, const RowSrc& m, const WRef& Wn, int O, int64_t n, int act,
-                        void* out, int out_dtype, int64_t ld_out, int exact, cudaStream_t s) {
+                        void* out, int out_dtype, int64_t ld_out, int exact, cudaStream_t s, const float* bx = nullptr,
+                        const float* bn = nullptr) {
     LinearParams P;
     P.n_segs = 2; P.n = n; P.act = act; P.out = out; P.out_dtype = out_dtype; P.ld_out = ld_out;
-    P.seg[0] = LinearSeg{x.base, x.dtype, x.ld, x.ids, Wx.p, Wx.dtype, Wx.ld, x.d, O, nullptr, 0};
-    P.seg[1] = LinearSeg{m.base, m.dtype, m.ld, m.ids, Wn.p, Wn.dtype, Wn.ld, m.d, O, nullptr, (int64_t)O};
+    P.seg[0] = LinearSeg{x.base, x.dtype, x.ld, x.ids, Wx.p, Wx.dtype, Wx.ld, x.d, O, bx, 0};
+    P.seg[1] = LinearSeg{m.base, m.dtype, m.ld, m.ids, Wn.p, Wn.dtype, Wn.ld, m.d, O, bn, (int64_t)O};
     if (n == 0) return GSAGE_OK;
     return linear_dispatch(P, exact, s);
+}
+
+static int linear_trans_call(const float* a, int64_t lda, int d, const float* W, int64_t ldw, int O, int64_t n, float* out,
+                             int64_t ld_out, cudaStream_t s) {
+    LinearParams P;                                  // out (n x O) = a (n x d) . W (d x O): the data gradient of a Linear
+    P.n_segs = 1; P.n = n; P.act = GSAGE_ACT_NONE; P.out = out; P.out_dtype = GSAGE_F32; P.ld_out = ld_out;
+    P.seg[0] = LinearSeg{a, GSAGE_F32, lda, nullptr, W, GSAGE_F32, ldw, d, O, nullptr, 0};
+    P.seg[0].w_trans = 1;
+    if (n == 0) return GSAGE_OK;
+    return linear_simt_launch(P, s);
 }
 
 // one aggregator application: out[n, 2*O] = act([fc_x(x) | fc_neib(reduce(nb))])   (nn_modules.py:196-204 etc.)
@@ -164,14 +188,16 @@ static int apply_aggregator(gsage_engine* e, int layer, const RowSrc& x, const R
                 return st;
             }
         }
-        const int p_red = e->prof.begin(GSAGE_PROF_REDUCE, s);
+        // the stopwatch covers the dominant launch only (layer 1 on the (x1, x2) pair: n = B*S1 parents)
+        const bool dominant = layer == 0 && n > e->B;
+        const int p_red = dominant ? e->prof.begin(GSAGE_PROF_REDUCE, s) : -1;
         GS_TRY(gather_reduce_launch(nb.base, nb.dtype, nb.ld, nb.table_rows, d, nb.ids, n, S, GSAGE_RED_MEAN, nullptr, Mb, T, ldm, s));
         e->prof.end(p_red, s);
         // algorithmic bytes of the fused gather+mean launch: S rows + S ids in, one row out
         if (p_red >= 0) e->prof.bytes[GSAGE_PROF_REDUCE] += (double)n * ((double)S * d * dtype_size(nb.dtype) + (nb.ids ? 8.0 * S : 0.0) + (double)d * dtype_size(T));
         RowSrc m{Mb, T, ldm, n, nullptr, d};
-        const int p_prj = e->prof.begin(GSAGE_PROF_PROJECT, s);
-        const int st = combine_call(x, e->w_x[layer], m, e->w_n[layer], O, n, act, out, out_dtype, ld_out, exact, s);
+        const int p_prj = dominant ? e->prof.begin(GSAGE_PROF_PROJECT, s) : -1;
+        const int st = combine_call(x, e->w_x[layer], m, e->w_n[layer], O, n, act, out, out_dtype, ld_out, exact, s, e->b_x[layer], e->b_n[layer]);
         e->prof.end(p_prj, s);
         if (p_prj >= 0) e->prof.bytes[GSAGE_PROF_PROJECT] += 4.0 * (double)n * d * O;      // flops, not bytes
         return st;
@@ -179,26 +205,26 @@ static int apply_aggregator(gsage_engine* e, int layer, const RowSrc& x, const R
     case GSAGE_AGG_MAX_POOL:
     case GSAGE_AGG_MEAN_POOL: {
         const int H = e->hid;
-        GS_TRY(linear_call(nb, e->w_mlp[layer], H, L.mlp_b, n * S, GSAGE_ACT_RELU, e->HN, T, H, 0, exact, s));
+        GS_TRY(linear_call(nb, e->w_mlp[layer], H, e->b_mlp[layer], n * S, GSAGE_ACT_RELU, e->HN, T, H, 0, exact, s));
         GS_TRY(gather_reduce_launch(e->HN, T, H, n * S, H, nullptr, n, S,
                                     e->cfg.aggregator == GSAGE_AGG_MAX_POOL ? GSAGE_RED_MAX : GSAGE_RED_MEAN, nullptr,
                                     e->Pp, T, H, s));
         RowSrc p{e->Pp, T, H, n, nullptr, H};
-        return combine_call(x, e->w_x[layer], p, e->w_n[layer], O, n, act, out, out_dtype, ld_out, exact, s);
+        return combine_call(x, e->w_x[layer], p, e->w_n[layer], O, n, act, out, out_dtype, ld_out, exact, s, e->b_x[layer], nullptr);
     }
     case GSAGE_AGG_ATTENTION: {
         const int H = e->hid;
         GS_CHECK_ARG(S > 1, "attention aggregator: S must be > 1");
-        GS_TRY(linear_call(nb, e->w_att1[layer], H, nullptr, n * S, GSAGE_ACT_TANH, e->T1, GSAGE_F32, H, 0, exact, s));
+        GS_TRY(linear_call(nb, e->w_att1[layer], H, e->b_att[layer], n * S, GSAGE_ACT_TANH, e->T1, GSAGE_F32, H, 0, exact, s));
         RowSrc t1{e->T1, GSAGE_F32, H, n * S, nullptr, H};
         GS_TRY(linear_call(t1, f32w(L.att_w2, H), H, nullptr, n * S, GSAGE_ACT_NONE, e->NA, GSAGE_F32, H, 0, 1, s));
-        GS_TRY(linear_call(x, e->w_att1[layer], H, nullptr, n, GSAGE_ACT_TANH, e->T1x, GSAGE_F32, H, 0, exact, s));
+        GS_TRY(linear_call(x, e->w_att1[layer], H, e->b_att[layer], n, GSAGE_ACT_TANH, e->T1x, GSAGE_F32, H, 0, exact, s));
         RowSrc t1x{e->T1x, GSAGE_F32, H, n, nullptr, H};
         GS_TRY(linear_call(t1x, f32w(L.att_w2, H), H, nullptr, n, GSAGE_ACT_NONE, e->XA, GSAGE_F32, H, 0, 1, s));
         GS_TRY(gsage_attention_weights(e->NA, e->XA, GSAGE_F32, H, H, n, S, e->AW, s));
         GS_TRY(gather_reduce_launch(nb.base, nb.dtype, nb.ld, nb.table_rows, d, nb.ids, n, S, GSAGE_RED_SUM, e->AW, Mb, T, ldm, s));
         RowSrc m{Mb, T, ldm, n, nullptr, d};
-        return combine_call(x, e->w_x[layer], m, e->w_n[layer], O, n, act, out, out_dtype, ld_out, exact, s);
+        return combine_call(x, e->w_x[layer], m, e->w_n[layer], O, n, act, out, out_dtype, ld_out, exact, s, e->b_x[layer], e->b_n[layer]);
     }
     }
     set_error("engine: unknown aggregator %d", e->cfg.aggregator);
@@ -234,6 +260,8 @@ int gsage_engine_create(const gsage_engine_config* cfg, gsage_engine** out) {
     case GSAGE_PREP_LINEAR: e->d_prep = 32; break;            // overwritten by weights.prep_out_dim at set_weights
     case GSAGE_PREP_NODE_EMBEDDING: e->d_prep = (has_feats ? cfg->feats_dim : 0) + cfg->emb_dim; break;
     }
+    e->fold_prep = cfg->prep == GSAGE_PREP_NODE_EMBEDDING && !has_feats;
+    if (const char* f = getenv("GSAGE_FOLD_PREP")) e->fold_prep = e->fold_prep && atoi(f) != 0;
     e->ld_prep = (int)pad_to(e->d_prep, vec * 2);
     e->hid = cfg->hidden_dim > 0 ? cfg->hidden_dim : (cfg->aggregator == GSAGE_AGG_ATTENTION ? 32 : 512);
     e->maxB = cfg->max_batch;
@@ -247,7 +275,7 @@ int gsage_engine_create(const gsage_engine_config* cfg, gsage_engine** out) {
     const int64_t o_ids = carve(8 * (e->n0 + e->n1 + e->n2));
     const int64_t o_sel = carve(4 * e->n2);
     const int64_t o_look = carve(8 * e->n0);
-    const int64_t o_X = cfg->prep == GSAGE_PREP_IDENTITY ? -1 : carve(es * e->ld_prep * (e->n0 + e->n1 + e->n2));
+    const int64_t o_X = (cfg->prep == GSAGE_PREP_IDENTITY || e->fold_prep) ? -1 : carve(es * e->ld_prep * (e->n0 + e->n1 + e->n2));
     const int64_t dmax = std::max<int64_t>(e->ld_prep, e->ld_h1);
     e->ld_m = pad_to(dmax, vec * 2);
     const int64_t o_M = carve(es * e->ld_m * (e->n0 + e->n1 + e->n0));
@@ -275,6 +303,13 @@ int gsage_engine_create(const gsage_engine_config* cfg, gsage_engine** out) {
         return GSAGE_ERR_NOMEM;
     }
     cudaMemset(e->ws, 0, (size_t)off);      // padding columns of every intermediate stay zero forever
+    if (e->fold_prep) {
+        e->fold_floats = 4 * ((int64_t)(2 * O1 + e->hid) * (cfg->emb_dim + 1) + 64);
+        if (cudaMalloc((void**)&e->fold, sizeof(float) * (size_t)e->fold_floats) != cudaSuccess) {
+            set_error("engine_create: cudaMalloc of the folded-weight arena failed");
+            cudaFree(e->ws); delete e; return GSAGE_ERR_NOMEM;
+        }
+    }
     if (e->T == GSAGE_BF16) {                // arena for the padded bf16 weight copies the tensor-core kernel reads
         const int64_t dmax0 = std::max<int64_t>(e->ld_prep, 2 * O1) + 8;
         e->wb_bytes = 2 * 2 * ((O1 + O2) * 2 * (dmax0 + e->hid) + 2 * (int64_t)e->hid * dmax0) + 16 * 256;
@@ -300,6 +335,7 @@ void gsage_engine_destroy(gsage_engine* e) {
     for (cudaEvent_t ev : e->prof.pool) cudaEventDestroy(ev);
     cudaFree(e->ws);
     cudaFree(e->wb);
+    cudaFree(e->fold);
     delete e;
 }
 
@@ -348,6 +384,32 @@ int gsage_engine_set_weights(gsage_engine* e, const gsage_weights* w, void* stre
     }
     e->w = *w;
     cudaStream_t s = as_stream(stream);
+    gsage_weights eff = *w;                                   // the weights the kernels will actually use
+    for (int l = 0; l < 2; ++l) { e->b_x[l] = e->b_n[l] = e->b_att[l] = nullptr; e->b_mlp[l] = w->layer[l].mlp_b; }
+    if (e->fold_prep) {
+        // W' = W . Wp (rows x de), b' = W . bp (+ b): three or four tiny FFMA launches per set_weights
+        const int de = e->cfg.emb_dim, O = e->cfg.out_dim[0], H = e->hid;
+        float* at = e->fold;
+        auto fold_w = [&](const float* W, int rows, const float* extra_bias, const float** w_out, const float** b_out) -> int {
+            float* Wf = at; at += (int64_t)rows * de;
+            float* bf = at; at += rows;
+            GS_TRY(linear_trans_call(W, de, de, w->prep_fc_w, de, de, rows, Wf, de, s));               // W . Wp
+            LinearParams P;                                                                             // W . bp
+            P.n_segs = 1; P.n = rows; P.act = GSAGE_ACT_NONE; P.out = bf; P.out_dtype = GSAGE_F32; P.ld_out = 1;
+            P.seg[0] = LinearSeg{W, GSAGE_F32, (int64_t)de, nullptr, w->prep_fc_b, GSAGE_F32, (int64_t)de, de, 1, nullptr, 0};
+            GS_TRY(linear_simt_launch(P, s));
+            if (extra_bias) { axpy_kernel<<<(unsigned)ceil_div(rows, 256), 256, 0, s>>>(bf, extra_bias, rows); GS_LAUNCHED(); }
+            *w_out = Wf; *b_out = bf;
+            return GSAGE_OK;
+        };
+        const bool pool0 = e->cfg.aggregator == GSAGE_AGG_MAX_POOL || e->cfg.aggregator == GSAGE_AGG_MEAN_POOL;
+        GS_TRY(fold_w(w->layer[0].fc_x, O, nullptr, &eff.layer[0].fc_x, &e->b_x[0]));
+        if (!pool0) GS_TRY(fold_w(w->layer[0].fc_neib, O, nullptr, &eff.layer[0].fc_neib, &e->b_n[0]));
+        if (pool0) GS_TRY(fold_w(w->layer[0].mlp_w, H, w->layer[0].mlp_b, &eff.layer[0].mlp_w, &e->b_mlp[0]));
+        if (e->cfg.aggregator == GSAGE_AGG_ATTENTION) GS_TRY(fold_w(w->layer[0].att_w1, H, nullptr, &eff.layer[0].att_w1, &e->b_att[0]));
+        GS_CHECK_ARG(at - e->fold <= e->fold_floats, "engine_set_weights: folded-weight arena too small");
+    }
+    w = &eff;
     const bool pool = e->cfg.aggregator == GSAGE_AGG_MAX_POOL || e->cfg.aggregator == GSAGE_AGG_MEAN_POOL;
     const bool att = e->cfg.aggregator == GSAGE_AGG_ATTENTION;
     int64_t off = 0;
@@ -423,8 +485,14 @@ int gsage_engine_forward_sharded(gsage_engine* e, gsage_graph* g, gsage_rng* rng
 
     // ---- prep (models.py:76-81) ------------------------------------------------------------------------
     RowSrc lvl;       // all three hops, hop k starts `offset_k` rows in
+    RowSrc x_seed;    // the self rows of the seeds (layer_idx == 0); differs from `lvl` only under the folded prep
     if (c.prep == GSAGE_PREP_IDENTITY) {
         lvl = RowSrc{c.feats_dev, c.feats_dtype, c.feats_ld, c.feats_rows, ids0, c.feats_dim};
+    } else if (e->fold_prep) {
+        // aggregators read the raw embedding table by id; seeds look up the masked row n_nodes (nn_modules.py:149)
+        fill_i64_kernel<<<(unsigned)ceil_div(n0, 256), 256, 0, s>>>(e->look0, n0, c.n_nodes);
+        GS_LAUNCHED();
+        lvl = RowSrc{c.emb_dev, c.emb_dtype, c.emb_ld, c.n_nodes + 1, ids0, c.emb_dim};
     } else {
         const int64_t ntot = n0 + n1 + n2;
         const int64_t ldx = e->ld_prep;
@@ -453,7 +521,9 @@ int gsage_engine_forward_sharded(gsage_engine* e, gsage_graph* g, gsage_rng* rng
     // ---- layer 1 on (x0, x1) and (x1, x2) with shared weights (models.py:85-86) ---------------------------
     const int64_t ldh = e->ld_h1;
     const int O1 = c.out_dim[0], O2 = c.out_dim[1];
-    GS_TRY(apply_aggregator(e, 0, lvl, lvl.shifted(n0), n0, S1, e->H1, T, ldh, 0, s));
+    x_seed = lvl;
+    if (e->fold_prep) x_seed.ids = e->look0;
+    GS_TRY(apply_aggregator(e, 0, x_seed, lvl.shifted(n0), n0, S1, e->H1, T, ldh, 0, s));
     GS_TRY(apply_aggregator(e, 0, lvl.shifted(n0), lvl.shifted(n0 + n1), n1, S2, (char*)e->H1 + n0 * ldh * es, T, ldh, n0, s));
 
     // ---- layer 2 on (h0, h1) ----------------------------------------------------------------------------------
@@ -489,16 +559,6 @@ int gsage_engine_forward_host(gsage_engine* e, gsage_graph* g, gsage_rng* rng, c
     if (st == GSAGE_OK) st = gsage_rng_check(rng, stream);
     if (st == GSAGE_OK) st = gsage_graph_check(g, stream);
     return st;
-}
-
-static int linear_trans_call(const float* a, int64_t lda, int d, const float* W, int64_t ldw, int O, int64_t n, float* out,
-                             int64_t ld_out, cudaStream_t s) {
-    LinearParams P;                                  // out (n x O) = a (n x d) . W (d x O): the data gradient of a Linear
-    P.n_segs = 1; P.n = n; P.act = GSAGE_ACT_NONE; P.out = out; P.out_dtype = GSAGE_F32; P.ld_out = ld_out;
-    P.seg[0] = LinearSeg{a, GSAGE_F32, lda, nullptr, W, GSAGE_F32, ldw, d, O, nullptr, 0};
-    P.seg[0].w_trans = 1;
-    if (n == 0) return GSAGE_OK;
-    return linear_simt_launch(P, s);
 }
 
 static int backward_supported(gsage_engine* e) {
