@@ -45,6 +45,7 @@ WORKLOADS = {
     'reddit': ('reddit', 'mean', 'identity', 'bf16', True),          # BASELINE.json configs[1]  (default)
     'reddit-fp32': ('reddit', 'mean', 'identity', 'f32', True),
     'pokec-mean': ('pokec', 'mean', 'node_embedding', 'f32', False),  # north-star 60 % target shape
+    'pokec-mean-tf32': ('pokec', 'mean', 'node_embedding', 'tf32', False),    # same, projections as TF32 on tcgen05
     'pokec-maxpool': ('pokec', 'max_pool', 'node_embedding', 'bf16', False),  # configs[2] (bf16 compute: the MLP is tensor-bound)
     'plaw2m-attention': ('plaw2m', 'attention', 'identity', 'bf16', True),   # configs[3]
     'big10m': ('big10m', 'mean', 'identity', 'bf16', True),                   # configs[4]
@@ -273,13 +274,14 @@ def run_ours(args):
     prob = make_problem(args)
     B = args.batch
     dtype = torch.bfloat16 if prob['table_dtype'] == 'bf16' else torch.float32
+    tf32 = prob['table_dtype'] == 'tf32'
     graph = g.GraphCSR.from_synth(prob['adj'])
     table = g.FeatureTable(prob['feats'], dtype) if prob['feats'] is not None else None
     model = g.GSSupervised(
         input_dim=prob['feats_dim'], n_nodes=prob['n_nodes'], n_classes=prob['n_classes'], layer_specs=layer_specs(),
         aggregator_class=g.aggregator_lookup[prob['aggregator']], prep_class=g.prep_lookup[prob['prep']],
         sampler_class=g.sampler_lookup['sparse_uniform_neighbor_sampler'], adj=graph, train_adj=graph,
-        compute_dtype=dtype, max_batch=B)
+        compute_dtype=dtype, max_batch=B, allow_tf32=tf32)
     model.load_state_dict(reference_params(prob))
     model = model.cuda()
     g.set_seeds(123 ** 2 + RANK)                                              # train.py:133 (+ rank: disjoint streams)
@@ -388,7 +390,7 @@ def run_ours(args):
     line = {
         'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': WORLD, 'steps': args.steps, 'warmup': max(3, args.warmup),
         'ms_per_step': ms_step, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
-        'dtype': 'bf16' if dtype == torch.bfloat16 else 'f32', 'data': 'synthetic',
+        'dtype': 'bf16' if dtype == torch.bfloat16 else ('tf32' if tf32 else 'f32'), 'data': 'synthetic',
         'config': workload_config(args, prob), 'clocks': clk,
         'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': 8 * B, 'd2h_bytes_per_step': 4 * B * prob['n_classes'],
                 'ms_per_step': e2e_ms},

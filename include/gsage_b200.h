@@ -145,7 +145,8 @@ int gsage_l2_normalize(const void* x_dev, int dtype, int64_t ld, int64_t n, int 
  * (nn_modules.py:150,166,200,224,228,307-308,317; models.py:91).
  *   out[:, col0 : col0+O] = act( A[ids] (n x d) . W^T (O x d, row-major, ldw) + bias )
  * `ids` NULL -> A read in place.  A / W / out dtypes independent (fp32 or bf16); fp32 accumulate.
- * `exact` != 0 forces the fp32 FFMA kernel; 0 lets bf16 operands run on the tcgen05 tensor-core kernel.
+ * `exact` != 0 forces the fp32 FFMA kernel; 0 lets bf16 operands (or fp32 operands, as TF32) run on the tcgen05
+ * tensor-core kernel when they qualify (16-byte aligned rows, O % 16 == 0).
  * ------------------------------------------------------------------------------------------------ */
 typedef struct gsage_linear_seg {
     const void* a_dev; int a_dtype; int64_t lda; const int64_t* ids_dev;    /* A source (+ optional gather) */
@@ -182,6 +183,8 @@ typedef struct gsage_engine_config {
     const void* emb_dev; int emb_dtype; int64_t emb_ld; int emb_dim; int64_t n_nodes;
     int hidden_dim;                 /* pool MLP width (512) / attention width (32)                        */
     int64_t max_batch;              /* workspace is sized for this many seeds                             */
+    int allow_tf32;                 /* fp32 mode only: run the projections on the tensor cores as TF32 (10-bit mantissa
+                                       products, fp32 accumulate; ~1e-3 relative) instead of the exact FFMA kernel */
 } gsage_engine_config;
 
 /* fp32 weights, named after the reference's state_dict keys; unused ones NULL. All row-major (out, in). */

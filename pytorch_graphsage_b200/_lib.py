@@ -34,7 +34,7 @@ class EngineConfig(C.Structure):
                 ('feats_dev', c_p), ('feats_dtype', C.c_int), ('feats_ld', c_i64), ('feats_dim', C.c_int),
                 ('feats_rows', c_i64),
                 ('emb_dev', c_p), ('emb_dtype', C.c_int), ('emb_ld', c_i64), ('emb_dim', C.c_int), ('n_nodes', c_i64),
-                ('hidden_dim', C.c_int), ('max_batch', c_i64)]
+                ('hidden_dim', C.c_int), ('max_batch', c_i64), ('allow_tf32', C.c_int)]
 
 
 class LayerWeights(C.Structure):

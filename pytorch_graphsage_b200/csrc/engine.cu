@@ -161,7 +161,7 @@ static int apply_aggregator(gsage_engine* e, int layer, const RowSrc& x, const R
                             int out_dtype, int64_t ld_out, int64_t m_row0, cudaStream_t s) {
     const gsage_layer_weights& L = e->w.layer[layer];
     const int O = e->cfg.out_dim[layer], act = e->cfg.act[layer], T = e->T;
-    const int exact = (T == GSAGE_F32);
+    const int exact = (T == GSAGE_F32 && !e->cfg.allow_tf32);
     const int d = x.d;
     const int64_t ldm = e->ld_m;
     void* const Mb = (char*)e->M + m_row0 * ldm * (int64_t)dtype_size(T);

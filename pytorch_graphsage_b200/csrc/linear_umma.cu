@@ -61,6 +61,8 @@ struct UmmaParams {
     int n_tiles; int stages; int stage_bytes; int w_bytes;
     int any_reduce;       // some segment has S > 1: loaders take the register path (fused gather+mean)
     int full_count;       // arrivals that complete a `full` barrier phase
+    int tf32;             // operands are fp32 read as TF32 (kind::tf32, 32 elements per 128-byte chunk row) instead of bf16
+    int uk;               // elements per 128-byte chunk row: 64 (bf16) | 32 (tf32)
     int prefetch;         // L2-prefetch whole rows of the next tile (GSAGE_UMMA_PREFETCH=1; off by default)
     int debug;            // GSAGE_UMMA_DEBUG bit0: no A reads, bit1: no W reads, bit2: no MMA issue (timing experiments only)
     int* err;
@@ -134,6 +136,12 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t a_desc, uint
     asm volatile(
         "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
         "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
         ::"r"(tmem_d), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
 }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
@@ -271,7 +279,8 @@ __global__ void __launch_bounds__(kThreads, 1) linear_umma_kernel(const UmmaPara
             for (int s = 0; s < P.n_segs; ++s) {
                 const UmmaSeg& sg = P.seg[s];
                 // instruction descriptor: D=f32, A=B=bf16, K-major both, N = O, M = 128
-                const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(sg.O >> 3) << 17) | ((uint32_t)(UM >> 4) << 24);
+                const uint32_t fmt = P.tf32 ? 2u : 1u;      // a/b format: 1 = bf16, 2 = tf32
+                const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(sg.O >> 3) << 17) | ((uint32_t)(UM >> 4) << 24);
                 const uint32_t d_tmem = tmem_base + (uint32_t)(buf * 256 + sg.acc_col);
                 for (int kc = 0; kc < sg.kchunks; ++kc, ++item) {
                     const int stage = item % P.stages;
@@ -283,8 +292,10 @@ __global__ void __launch_bounds__(kThreads, 1) linear_umma_kernel(const UmmaPara
                         const uint32_t b_addr = a_addr + kABytes;
                         const uint64_t adesc = umma_desc(a_addr), bdesc = umma_desc(b_addr);
 #pragma unroll
-                        for (int k = 0; k < UK / 16; ++k)                // 4 x (K = 16): +32 bytes inside the swizzle atom
-                            umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kc | k) ? 1u : 0u);
+                        for (int k = 0; k < 4; ++k) {                    // 4 x (K = 16 bf16 | 8 tf32): +32 bytes inside the swizzle atom
+                            if (P.tf32) umma_tf32(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kc | k) ? 1u : 0u);
+                            else umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kc | k) ? 1u : 0u);
+                        }
                         umma_commit(empty_bar(stage));                   // smem slot reusable once these MMAs retire
                     }
                     __syncwarp();
@@ -328,11 +339,11 @@ __global__ void __launch_bounds__(kThreads, 1) linear_umma_kernel(const UmmaPara
                         const uint32_t sa_u = smem_u32(smem + (size_t)stage * P.stage_bytes);
                         if (lane == 0) {
                             mbar_arrive_expect_tx(full_bar(stage), w_bytes + ((sg.ids && (P.debug & 1)) ? 0u : (uint32_t)kABytes));
-                            tma_load_2d(sa_u + kABytes, &M.w[sidx], kc * UK, 0, full_bar(stage));
-                            if (!sg.ids) tma_load_2d(sa_u, &M.a[sidx], kc * UK, tile * UM, full_bar(stage));
+                            tma_load_2d(sa_u + kABytes, &M.w[sidx], kc * P.uk, 0, full_bar(stage));
+                            if (!sg.ids) tma_load_2d(sa_u, &M.a[sidx], kc * P.uk, tile * UM, full_bar(stage));
                         }
                         __syncwarp();                              // expect_tx is posted before any lane's copy can complete
-                        if (sg.ids && !(P.debug & 1)) tma_gather4(sa_u + lane * 512, &M.g[sidx], kc * UK, r0, r1, r2, r3, full_bar(stage));
+                        if (sg.ids && !(P.debug & 1)) tma_gather4(sa_u + lane * 512, &M.g[sidx], kc * P.uk, r0, r1, r2, r3, full_bar(stage));
                     }
                 }
             }
@@ -469,10 +480,12 @@ bool linear_umma_eligible(const LinearParams& P) {
     int cols = 0;
     for (int i = 0; i < P.n_segs; ++i) {
         const LinearSeg& s = P.seg[i];
-        if (s.a_dtype != GSAGE_BF16 || s.w_dtype != GSAGE_BF16) return false;
+        if (s.a_dtype != P.seg[0].a_dtype || s.w_dtype != s.a_dtype) return false;         // all bf16, or all fp32 (run as TF32)
+        if (s.a_dtype == GSAGE_F32 && s.S > 1) return false;                              // the register path is bf16 only
         if (s.O % 16 != 0 || s.O < 16 || s.O > kMaxO) return false;
-        if (!aligned16(s.a) || !aligned16(s.w) || (s.lda * 2) % 16 != 0 || (s.ldw * 2) % 16 != 0) return false;
-        if (s.lda < (s.d + 7) / 8 * 8 || s.ldw < (s.d + 7) / 8 * 8) return false;      // whole 16-byte chunks readable
+        const int es = s.a_dtype == GSAGE_BF16 ? 2 : 4, per = 16 / es;
+        if (!aligned16(s.a) || !aligned16(s.w) || (s.lda * es) % 16 != 0 || (s.ldw * es) % 16 != 0) return false;
+        if (s.lda < (s.d + per - 1) / per * per || s.ldw < (s.d + per - 1) / per * per) return false;   // whole 16-byte chunks readable
         cols += s.O;
     }
     return cols <= 256;
@@ -492,14 +505,14 @@ static PFN_cuTensorMapEncodeTiled_v12000 tensor_map_encoder() {
 }
 
 // bf16 (rows, cols) row-major with `ld` elements between rows; box = 64 columns x box_rows, 128-byte swizzle
-static int make_map(CUtensorMap* m, const void* base, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
+static int make_map(CUtensorMap* m, const void* base, int64_t rows, int64_t cols, int64_t ld, int box_rows, int es) {
     PFN_cuTensorMapEncodeTiled_v12000 enc = tensor_map_encoder();
     GS_CHECK_ARG(enc, "linear_umma: cuTensorMapEncodeTiled is not available from this driver");
     const cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-    const cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
-    const cuuint32_t box[2] = {(cuuint32_t)UK, (cuuint32_t)box_rows};
+    const cuuint64_t strides[1] = {(cuuint64_t)ld * es};
+    const cuuint32_t box[2] = {(cuuint32_t)(128 / es), (cuuint32_t)box_rows};
     const cuuint32_t estr[2] = {1, 1};
-    const CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+    const CUresult r = enc(m, es == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), dims, strides, box, estr,
                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     GS_CHECK_ARG(r == CUDA_SUCCESS, "linear_umma: cuTensorMapEncodeTiled failed (%d)", (int)r);
@@ -510,12 +523,14 @@ int linear_umma_launch(const LinearParams& P, cudaStream_t s) {
     UmmaParams U;
     memset(&U, 0, sizeof(U));
     int col = 0, maxO = 0;
+    U.tf32 = P.seg[0].a_dtype == GSAGE_F32 ? 1 : 0;
+    U.uk = U.tf32 ? 32 : 64;
     for (int i = 0; i < P.n_segs; ++i) {
         const LinearSeg& g = P.seg[i];
         U.seg[i].a = (const __nv_bfloat16*)g.a; U.seg[i].lda = g.lda; U.seg[i].ids = g.ids;
         U.seg[i].w = (const __nv_bfloat16*)g.w; U.seg[i].ldw = g.ldw; U.seg[i].d = g.d; U.seg[i].O = g.O;
         U.seg[i].bias = g.bias; U.seg[i].col0 = g.col0;
-        U.seg[i].kchunks = (g.d + UK - 1) / UK;
+        U.seg[i].kchunks = (g.d + U.uk - 1) / U.uk;
         U.seg[i].acc_col = col;
         U.seg[i].S = g.S > 1 ? g.S : 1;
         U.seg[i].scale = g.S > 1 ? 1.0f / (float)g.S : 1.0f;
@@ -551,11 +566,12 @@ int linear_umma_launch(const LinearParams& P, cudaStream_t s) {
     const int grid = U.n_tiles < sm_count() ? U.n_tiles : sm_count();
     UmmaMaps maps;
     memset(&maps, 0, sizeof(maps));
+    const int es = U.tf32 ? 4 : 2;
     for (int i = 0; i < P.n_segs; ++i) {
         const LinearSeg& g = P.seg[i];
-        GS_TRY(make_map(&maps.w[i], g.w, g.O, g.d, g.ldw, g.O));
-        if (!g.ids && U.seg[i].S == 1) GS_TRY(make_map(&maps.a[i], g.a, P.n, g.d, g.lda, UM));
-        if (g.ids && U.seg[i].S == 1) GS_TRY(make_map(&maps.g[i], g.a, 0x7FFFFFFF, g.d, g.lda, 1));   // rows by id: no row bound known here
+        GS_TRY(make_map(&maps.w[i], g.w, g.O, g.d, g.ldw, g.O, es));
+        if (!g.ids && U.seg[i].S == 1) GS_TRY(make_map(&maps.a[i], g.a, P.n, g.d, g.lda, UM, es));
+        if (g.ids && U.seg[i].S == 1) GS_TRY(make_map(&maps.g[i], g.a, 0x7FFFFFFF, g.d, g.lda, 1, es));   // rows by id: no row bound known here
     }
     linear_umma_kernel<<<grid, kThreads, smem, s>>>(U, maps);
     GS_LAUNCHED();

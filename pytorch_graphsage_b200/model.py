@@ -54,13 +54,14 @@ class FeatureTable(object):
 class GSSupervised(nn.Module):
     def __init__(self, input_dim, n_nodes, n_classes, layer_specs, aggregator_class, prep_class, sampler_class,
                  adj, train_adj, lr_init=0.01, weight_decay=0.0, lr_schedule='constant', epochs=10,
-                 compute_dtype=torch.float32, max_batch=512, rng=None):
+                 compute_dtype=torch.float32, max_batch=512, rng=None, allow_tf32=False):
         super(GSSupervised, self).__init__()
         assert len(layer_specs) == 2, 'GSSupervised: the engine implements the two-layer stack of train.py:105-118'
         self.layer_specs = layer_specs
         self.n_nodes, self.n_classes = n_nodes, n_classes
         self.compute_dtype = compute_dtype
         self.max_batch = max_batch
+        self.allow_tf32 = allow_tf32          # fp32 tables, projections as TF32 on the tensor cores (~1e-3 relative)
         self.rng = rng
 
         # Sampler (models.py:41-44) -- one device graph per adjacency, shared when they are the same object
@@ -129,6 +130,7 @@ class GSSupervised(nn.Module):
         agg0 = self.agg_layers[0]
         cfg.hidden_dim = agg0.mlp[0].out_features if hasattr(agg0, 'mlp') else (agg0.att[0].out_features if hasattr(agg0, 'att') else 0)
         cfg.max_batch = max(batch, self.max_batch)
+        cfg.allow_tf32 = 1 if self.allow_tf32 else 0
         h = C.c_void_p()
         check(lib().gsage_engine_create(C.byref(cfg), C.byref(h)))
         eng = dict(h=h, max_batch=cfg.max_batch, emb_keep=emb_keep, cfg=cfg)

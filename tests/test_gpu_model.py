@@ -111,3 +111,13 @@ def test_consecutive_batches_continue_the_stream(g):
         got = model(torch.from_numpy(batch), feats)
         assert np.array_equal(model.peek('ids2').cpu().numpy(), ids2)
         np.testing.assert_allclose(got.cpu().numpy(), want.numpy(), rtol=1e-4, atol=1e-5)
+
+
+def test_engine_tf32_projection_mode(g):
+    """fp32 tables, projections on the tensor cores as TF32 (allow_tf32=True): ids still bit-exact, logits within 5e-3."""
+    fix = util.load('model_mean_node_embedding_nofeats')
+    model = build_model(g, fix, 'mean', 'node_embedding', False, allow_tf32=True)
+    g.set_seeds(int(fix['seed']))
+    logits = model(torch.from_numpy(fix['ids0']), None)
+    assert np.array_equal(model.peek('ids2').cpu().numpy(), fix['ids2'])
+    np.testing.assert_allclose(logits.cpu().numpy(), fix['logits'], rtol=5e-3, atol=5e-3)

@@ -218,3 +218,23 @@ def test_fused_contiguous_mean_projection(g):
     want = torch.cat([h[:n].double() @ wx.double().t(), mean.double() @ wn.double().t()], dim=1)
     got = g.ops.linear([dict(a=hd[:n], w=pad(wx), col0=0), dict(a=hd[n:], w=pad(wn), col0=O, S=S)], n, exact=False)
     np.testing.assert_allclose(got.cpu().numpy(), want.numpy(), rtol=2e-3, atol=2e-3)
+
+
+@pytest.mark.parametrize('n,d,O', [(300, 64, 128), (1000, 256, 64), (129, 100, 16)])
+def test_umma_tf32_projection(g, n, d, O):
+    """fp32 operands on the tensor cores as TF32 (exact=False): products carry a 10-bit mantissa, fp32 accumulate.
+    Stated tolerance: 2e-3 * sqrt(d) absolute on unit-variance operands (measured errors are ~10x smaller)."""
+    gen = torch.Generator().manual_seed(d)
+    table = torch.randn((n + 77, d), generator=gen)
+    m = torch.randn((n, d), generator=gen)
+    wx, wn = torch.randn((O, d), generator=gen) / d ** 0.5, torch.randn((O, d), generator=gen) / d ** 0.5
+    ids = torch.randint(0, n + 77, (n,), generator=gen)
+    pad = lambda t: g.ops.pad_table(t, torch.float32)[0][:, :t.shape[1]]
+    segs = [dict(a=pad(table), ids=ids.cuda(), w=pad(wx), col0=0), dict(a=pad(m), w=pad(wn), col0=O)]
+    want = torch.relu(torch.cat([table[ids].double() @ wx.double().t(), m.double() @ wn.double().t()], dim=1))
+    got = g.ops.linear(segs, n, act='relu', out_dtype=torch.float32, exact=False)
+    err = (got.cpu().double() - want).abs().max().item()
+    assert err < 2e-3 * d ** 0.5, err
+    assert err > 0 or d < 8                       # it really ran in reduced precision (the FFMA path would be ~1e-6)
+    exact = g.ops.linear(segs, n, act='relu', out_dtype=torch.float32, exact=True)
+    np.testing.assert_allclose(exact.cpu().numpy(), want.numpy(), rtol=1e-4, atol=1e-5)
