@@ -110,3 +110,20 @@ def test_sparse_vs_oracle_random_graphs(g, trial):
     assert np.array_equal(got1.cpu().numpy(), want1) and np.array_equal(got2.cpu().numpy(), want2)
     st = rng.get_state()
     assert np.array_equal(st[1], o.key) and st[2] == o.pos
+
+
+def test_epoch_iterator_matches_reference_shuffle(g):
+    """problem.py:141-153: the epoch shuffle comes from the same stream, before the sampler draws."""
+    from pytorch_graphsage_b200.problem import iterate
+    nodes = np.arange(1, 1338)
+    targets = np.arange(2000)
+    g.set_seeds(99)
+    got = [(ids.cpu().numpy(), t.cpu().numpy(), p) for ids, t, p in iterate(nodes, targets, batch_size=512, shuffle=True)]
+    rs = np.random.RandomState(99)
+    idx = rs.permutation(np.arange(nodes.shape[0]))                  # what NodeProblem.iterate does
+    chunks = np.array_split(idx, nodes.shape[0] // 512 + 1)
+    assert len(got) == len(chunks)
+    for (ids, t, p), (k, c) in zip(got, enumerate(chunks)):
+        assert np.array_equal(ids, nodes[c]) and np.array_equal(t, targets[nodes[c]]) and p == k / len(chunks)
+    # the stream continues where numpy's would: the next sampler draw matches
+    assert np.array_equal(g.ops.u32_to_numpy(g.default_rng().randint(1000, 50)).astype(np.int64), rs.choice(1000, 50))
