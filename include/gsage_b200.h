@@ -247,6 +247,10 @@ typedef struct gsage_grads {
 int gsage_engine_backward_head(gsage_engine* e, const float* dlogits_dev, const gsage_grads* grads, void* stream);
 int gsage_engine_backward_layer1(gsage_engine* e, const gsage_grads* grads, void* stream);
 
+/* keep != 0: the next forwards keep every activation the backward pass needs (training).  0 (default): forward-only
+ * streaming -- intermediates may be processed in L2-sized chunks that reuse their buffers. */
+int gsage_engine_keep_activations(gsage_engine* e, int keep);
+
 /* Live stopwatch (CUDA events on the launching stream) around kernel groups of the forward, for bench.py:
  *   FORWARD  the whole gsage_engine_forward        SAMPLE   rng draws + sample kernels, both hops
  *   REDUCE   the fused gather+aggregate launches   PROJECT  the concat-with-self projection launches

@@ -71,6 +71,28 @@ __device__ __forceinline__ uint4 ldg_nc_v4(const void* p) {
     return r;
 }
 
+// L2 eviction-priority policies (createpolicy): streaming table rows should leave L2 first, the small reduced-row
+// buffer that the projection kernel re-reads right away should stay
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ uint4 ldg_nc_v4_hint(const void* p, uint64_t policy) {
+    uint4 r;
+    asm("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.u32 {%0, %1, %2, %3}, [%4], %5;"
+        : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p), "l"(policy));
+    return r;
+}
+__device__ __forceinline__ void stg_v4_hint(void* p, const uint4& v, uint64_t policy) {
+    asm volatile("st.global.L2::cache_hint.v4.u32 [%0], {%1, %2, %3, %4}, %5;" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "l"(policy) : "memory");
+}
+
 __device__ __forceinline__ void st_shared_v4(uint32_t smem_addr, const uint4& v) {
     asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(smem_addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }

@@ -24,7 +24,7 @@ int sample_sparse_launch(gsage_graph* g, const int64_t* ids, int64_t n, int S, c
                          cudaStream_t s);
 int gather_reduce_launch(const void* table, int dtype, int64_t ld, int64_t rows, int d, const int64_t* ids,
                          int64_t n_parents, int S, int reduce, const float* weights, void* out, int out_dtype,
-                         int64_t ld_out, cudaStream_t s);
+                         int64_t ld_out, cudaStream_t s, int l2_hint = 0);
 
 // a set of rows some kernel will read: either (table, ids) gathered on the fly or a materialised buffer
 struct RowSrc {
@@ -119,6 +119,11 @@ struct gsage_engine {
     float* fold = nullptr; int64_t fold_floats = 0;
     const float* b_x[2] = {nullptr, nullptr}; const float* b_n[2] = {nullptr, nullptr};
     const float* b_mlp[2] = {nullptr, nullptr}; const float* b_att[2] = {nullptr, nullptr};
+    // forward-only streaming (keep_activations == false): the big layer-1 application runs in chunks of `chunk_parents`
+    // parents that reuse ONE small reduced-row buffer, so the rows the reduce kernel writes are still in L2 (126 MB) when
+    // the projection kernel reads them, and are overwritten there before they are ever written back to HBM
+    bool keep_activations = false;
+    int64_t chunk_parents = 0; int l2_hint = 0;
     bool fuse_mean = false;   // GSAGE_FUSE_MEAN=1: route the mean aggregator through the one-kernel fused layer (experimental)
 };
 
@@ -191,7 +196,8 @@ static int apply_aggregator(gsage_engine* e, int layer, const RowSrc& x, const R
         // the stopwatch covers the dominant launch only (layer 1 on the (x1, x2) pair: n = B*S1 parents)
         const bool dominant = layer == 0 && n > e->B;
         const int p_red = dominant ? e->prof.begin(GSAGE_PROF_REDUCE, s) : -1;
-        GS_TRY(gather_reduce_launch(nb.base, nb.dtype, nb.ld, nb.table_rows, d, nb.ids, n, S, GSAGE_RED_MEAN, nullptr, Mb, T, ldm, s));
+        GS_TRY(gather_reduce_launch(nb.base, nb.dtype, nb.ld, nb.table_rows, d, nb.ids, n, S, GSAGE_RED_MEAN, nullptr, Mb, T, ldm, s,
+                                    (e->l2_hint && !e->keep_activations) ? 1 : 0));
         e->prof.end(p_red, s);
         // algorithmic bytes of the fused gather+mean launch: S rows + S ids in, one row out
         if (p_red >= 0) e->prof.bytes[GSAGE_PROF_REDUCE] += (double)n * ((double)S * d * dtype_size(nb.dtype) + (nb.ids ? 8.0 * S : 0.0) + (double)d * dtype_size(T));
@@ -253,6 +259,8 @@ int gsage_engine_create(const gsage_engine_config* cfg, gsage_engine** out) {
     e->cfg = *cfg;
     e->T = cfg->compute_dtype;
     if (const char* f = getenv("GSAGE_FUSE_MEAN")) e->fuse_mean = atoi(f) != 0;
+    if (const char* f = getenv("GSAGE_CHUNK")) e->chunk_parents = atoll(f);
+    if (const char* f = getenv("GSAGE_L2HINT")) e->l2_hint = atoi(f);
     const int64_t es = (int64_t)dtype_size(e->T);
     const int64_t vec = 16 / es;
     switch (cfg->prep) {
@@ -340,6 +348,12 @@ void gsage_engine_destroy(gsage_engine* e) {
 }
 
 int64_t gsage_engine_workspace_bytes(const gsage_engine* e) { return e ? e->ws_bytes : 0; }
+
+int gsage_engine_keep_activations(gsage_engine* e, int keep) {
+    GS_CHECK_ARG(e, "engine_keep_activations: NULL engine");
+    e->keep_activations = keep != 0;
+    return GSAGE_OK;
+}
 
 int gsage_engine_profile(gsage_engine* e, int enable) {
     GS_CHECK_ARG(e, "engine_profile: NULL engine");
@@ -524,7 +538,15 @@ int gsage_engine_forward_sharded(gsage_engine* e, gsage_graph* g, gsage_rng* rng
     x_seed = lvl;
     if (e->fold_prep) x_seed.ids = e->look0;
     GS_TRY(apply_aggregator(e, 0, x_seed, lvl.shifted(n0), n0, S1, e->H1, T, ldh, 0, s));
-    GS_TRY(apply_aggregator(e, 0, lvl.shifted(n0), lvl.shifted(n0 + n1), n1, S2, (char*)e->H1 + n0 * ldh * es, T, ldh, n0, s));
+    if (!e->keep_activations && e->chunk_parents > 0 && c.aggregator == GSAGE_AGG_MEAN && n1 > e->chunk_parents) {
+        for (int64_t p0 = 0; p0 < n1; p0 += e->chunk_parents) {
+            const int64_t np = std::min(e->chunk_parents, n1 - p0);
+            GS_TRY(apply_aggregator(e, 0, lvl.shifted(n0 + p0), lvl.shifted(n0 + n1 + p0 * S2), np, S2,
+                                    (char*)e->H1 + (n0 + p0) * ldh * es, T, ldh, n0, s));      // same M rows every chunk
+        }
+    } else {
+        GS_TRY(apply_aggregator(e, 0, lvl.shifted(n0), lvl.shifted(n0 + n1), n1, S2, (char*)e->H1 + n0 * ldh * es, T, ldh, n0, s));
+    }
 
     // ---- layer 2 on (h0, h1) ----------------------------------------------------------------------------------
     RowSrc h{e->H1, T, ldh, n0 + n1, nullptr, 2 * O1};
@@ -566,6 +588,7 @@ static int backward_supported(gsage_engine* e) {
     GS_CHECK_ARG(e->cfg.aggregator == GSAGE_AGG_MEAN && e->cfg.prep == GSAGE_PREP_IDENTITY,
                  "engine_backward: implemented for the mean aggregator with the identity prep (the other plug-ins are forward-only this round)");
     GS_CHECK_ARG(!e->fuse_mean, "engine_backward: needs the reduced rows the fused (GSAGE_FUSE_MEAN) layer never writes");
+    GS_CHECK_ARG(e->keep_activations || e->chunk_parents == 0, "engine_backward: call gsage_engine_keep_activations(e, 1) before the forward");
     return GSAGE_OK;
 }
 

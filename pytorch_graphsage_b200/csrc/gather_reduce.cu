@@ -24,8 +24,9 @@ template <typename T, int LPR, int CPL, int RED>
 __global__ void __launch_bounds__(256)
 gather_reduce_kernel(const T* __restrict__ table, int64_t ld, int64_t n_table_rows, int d,
                      const int64_t* __restrict__ ids, int64_t n_parents, int S, const float* __restrict__ weights,
-                     float scale, void* __restrict__ out, int out_bf16, int64_t ld_out, int vec_store) {
+                     float scale, void* __restrict__ out, int out_bf16, int64_t ld_out, int vec_store, int l2_hint) {
     constexpr int VEC = ElemTraits<T>::kPerVec;
+    const uint64_t pol_in = l2_hint ? l2_policy_evict_first() : 0, pol_out = l2_hint ? l2_policy_evict_last() : 0;
     constexpr int U = (CPL == 1) ? 8 : (CPL == 2 ? 4 : 2);
     constexpr int GROUPS = 256 / LPR;
     const int lane_g = threadIdx.x & (LPR - 1);
@@ -64,7 +65,7 @@ gather_reduce_kernel(const T* __restrict__ table, int64_t ld, int64_t n_table_ro
 #pragma unroll
                 for (int c = 0; c < CPL; ++c) {
                     const int ch = chunk0 + c * LPR;
-                    v[u][c] = (live && ch < nchunks) ? ldg_nc_v4(row + (int64_t)ch * VEC) : make_uint4(0, 0, 0, 0);
+                    v[u][c] = (live && ch < nchunks) ? (l2_hint ? ldg_nc_v4_hint(row + (int64_t)ch * VEC, pol_in) : ldg_nc_v4(row + (int64_t)ch * VEC)) : make_uint4(0, 0, 0, 0);
                 }
             }
 #pragma unroll
@@ -96,7 +97,8 @@ gather_reduce_kernel(const T* __restrict__ table, int64_t ld, int64_t n_table_ro
             if (out_bf16) {
                 __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out) + parent * ld_out + col;
                 if (VEC == 8) {
-                    *reinterpret_cast<uint4*>(o) = ElemTraits<__nv_bfloat16>::pack(f);
+                    if (l2_hint) stg_v4_hint(o, ElemTraits<__nv_bfloat16>::pack(f), pol_out);
+                    else *reinterpret_cast<uint4*>(o) = ElemTraits<__nv_bfloat16>::pack(f);
                 } else {
                     *reinterpret_cast<uint2*>(o) = make_uint2(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]));
                 }
@@ -120,16 +122,16 @@ gather_reduce_kernel(const T* __restrict__ table, int64_t ld, int64_t n_table_ro
 template <typename T, int LPR, int CPL>
 static int launch_shape(const void* table, int64_t ld, int64_t rows, int d, const int64_t* ids, int64_t n_parents, int S,
                         int red, const float* weights, float scale, void* out, int out_bf16, int64_t ld_out,
-                        int vec_store, cudaStream_t s) {
+                        int vec_store, int l2_hint, cudaStream_t s) {
     constexpr int VEC = ElemTraits<T>::kPerVec;
     const int nchunks = (d + VEC - 1) / VEC;
     dim3 grid((unsigned)ceil_div(n_parents, 256 / LPR), (unsigned)ceil_div(nchunks, LPR * CPL));
     if (red == kRedMax)
         gather_reduce_kernel<T, LPR, CPL, kRedMax><<<grid, 256, 0, s>>>((const T*)table, ld, rows, d, ids, n_parents, S,
-                                                                        weights, scale, out, out_bf16, ld_out, vec_store);
+                                                                        weights, scale, out, out_bf16, ld_out, vec_store, l2_hint);
     else
         gather_reduce_kernel<T, LPR, CPL, kRedSum><<<grid, 256, 0, s>>>((const T*)table, ld, rows, d, ids, n_parents, S,
-                                                                        weights, scale, out, out_bf16, ld_out, vec_store);
+                                                                        weights, scale, out, out_bf16, ld_out, vec_store, l2_hint);
     GS_LAUNCHED();
     return GSAGE_OK;
 }
@@ -137,10 +139,10 @@ static int launch_shape(const void* table, int64_t ld, int64_t rows, int d, cons
 template <typename T>
 static int launch_dtype(const void* table, int64_t ld, int64_t rows, int d, const int64_t* ids, int64_t n_parents, int S,
                         int red, const float* weights, float scale, void* out, int out_bf16, int64_t ld_out,
-                        int vec_store, cudaStream_t s) {
+                        int vec_store, int l2_hint, cudaStream_t s) {
     constexpr int VEC = ElemTraits<T>::kPerVec;
     const int nchunks = (d + VEC - 1) / VEC;
-#define GS_SHAPE(L, C) return launch_shape<T, L, C>(table, ld, rows, d, ids, n_parents, S, red, weights, scale, out, out_bf16, ld_out, vec_store, s)
+#define GS_SHAPE(L, C) return launch_shape<T, L, C>(table, ld, rows, d, ids, n_parents, S, red, weights, scale, out, out_bf16, ld_out, vec_store, l2_hint, s)
     if (nchunks <= 4) GS_SHAPE(4, 1);
     if (nchunks <= 8) GS_SHAPE(8, 1);
     if (nchunks <= 16) GS_SHAPE(16, 1);
@@ -209,7 +211,7 @@ static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 
 
 int gather_reduce_launch(const void* table, int dtype, int64_t ld, int64_t rows, int d, const int64_t* ids,
                          int64_t n_parents, int S, int reduce, const float* weights, void* out, int out_dtype,
-                         int64_t ld_out, cudaStream_t s) {
+                         int64_t ld_out, cudaStream_t s, int l2_hint) {
     const int vec = dtype == GSAGE_BF16 ? 8 : 4;
     GS_CHECK_ARG(table && out && d > 0 && S > 0 && n_parents >= 0, "gather_reduce: bad arguments");
     GS_CHECK_ARG(dtype == GSAGE_F32 || dtype == GSAGE_BF16, "gather_reduce: dtype must be f32 or bf16");
@@ -225,9 +227,9 @@ int gather_reduce_launch(const void* table, int dtype, int64_t ld, int64_t rows,
     const int red = (reduce == GSAGE_RED_MAX) ? kRedMax : kRedSum;
     if (dtype == GSAGE_BF16)
         return launch_dtype<__nv_bfloat16>(table, ld, rows, d, ids, n_parents, S, red, weights, scale, out,
-                                           out_dtype == GSAGE_BF16, ld_out, vec_store, s);
+                                           out_dtype == GSAGE_BF16, ld_out, vec_store, l2_hint, s);
     return launch_dtype<float>(table, ld, rows, d, ids, n_parents, S, red, weights, scale, out, out_dtype == GSAGE_BF16,
-                               ld_out, vec_store, s);
+                               ld_out, vec_store, l2_hint, s);
 }
 
 }  // namespace gsage

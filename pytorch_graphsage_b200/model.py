@@ -165,7 +165,7 @@ class GSSupervised(nn.Module):
             eng['stamp'] = stamp
 
     # -- the reference's public surface ---------------------------------------------------------------
-    def forward(self, ids, feats, train=True, shard=None):
+    def forward(self, ids, feats, train=True, shard=None, keep_activations=False):
         """models.py:71-91.  `ids`: int64 tensor of seed ids (CUDA, or CPU -> copied); `feats`: the node feature
         table (tensor / FeatureTable) or None.  Returns fp32 logits (B, n_classes) on the GPU."""
         sampler = self.train_sampler if train else self.val_sampler
@@ -176,6 +176,7 @@ class GSSupervised(nn.Module):
         table = self._table(feats)
         eng = self._engine(table, fanout, ids.shape[0])
         self._push_weights(eng)
+        check(lib().gsage_engine_keep_activations(eng['h'], 1 if keep_activations else 0))
         rng = sampler.rng or self.rng or default_rng()
         out = torch.empty((ids.shape[0], self.n_classes), dtype=torch.float32, device='cuda')
         if shard is None:
@@ -239,7 +240,7 @@ class GSSupervised(nn.Module):
     def train_step(self, ids, feats, targets, loss_fn, optimizer=None, clip=5.0, grad_scale=1.0, overlap_stream=None, shard=None):
         """models.py:97-104: forward, loss, backward, clip-norm 5, optimiser step.  The loss and the optimiser are
         stock torch (out of scope); forward and parameter gradients run in the library."""
-        preds = self(ids, feats, train=True, shard=shard)
+        preds = self(ids, feats, train=True, shard=shard, keep_activations=True)
         leaf = preds.detach().requires_grad_(True)
         loss = loss_fn(leaf, targets.squeeze())
         dlogits, = torch.autograd.grad(loss, leaf)
