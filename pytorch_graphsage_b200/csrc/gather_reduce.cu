@@ -243,13 +243,13 @@ int gsage_gather_reduce(const void* table_dev, int dtype, int64_t ld, int64_t n_
                         int64_t ld_out, void* stream) {
     GS_CHECK_ARG(reduce == GSAGE_RED_MEAN || reduce == GSAGE_RED_MAX || reduce == GSAGE_RED_SUM, "gather_reduce: bad reduce op");
     return gather_reduce_launch(table_dev, dtype, ld, n_table_rows, d, ids_dev, n_parents, S, reduce, weights_dev, out_dev,
-                                out_dtype, ld_out, as_stream(stream));
+                                out_dtype, ld_out, as_stream(stream), 0);
 }
 
 int gsage_gather_rows(const void* table_dev, int dtype, int64_t ld, int64_t n_table_rows, int d, const int64_t* ids_dev,
                       int64_t n, void* out_dev, int out_dtype, int64_t ld_out, void* stream) {
     return gather_reduce_launch(table_dev, dtype, ld, n_table_rows, d, ids_dev, n, 1, GSAGE_RED_SUM, nullptr, out_dev,
-                                out_dtype, ld_out, as_stream(stream));
+                                out_dtype, ld_out, as_stream(stream), 0);
 }
 
 int gsage_attention_weights(const void* na_dev, const void* xa_dev, int dtype, int64_t ld, int H, int64_t n_parents, int S,
