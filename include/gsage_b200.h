@@ -163,6 +163,13 @@ typedef struct gsage_linear_seg {
 int gsage_linear(const gsage_linear_seg* segs, int n_segs, int64_t n, int act, void* out_dev, int out_dtype,
                  int64_t ld_out, int exact, void* stream);
 
+/* Pool aggregators (nn_modules.py:223-226,240,252): out[p, col0+o] = reduce_{j<S} act(A[ids[p*S+j]] . W[o] + bias[o]),
+ * reduce = GSAGE_RED_MAX | GSAGE_RED_MEAN.  The per-neighbour MLP runs on the tensor cores and the pool over the S
+ * rows of a parent happens in the kernel's epilogue: the (n*S, O) hidden rows never reach HBM.  Requires operands that
+ * qualify for the tensor-core kernel (bf16, or fp32 run as TF32; 16-byte aligned rows; O % 16 == 0), S <= 128. */
+int gsage_linear_pooled(const gsage_linear_seg* seg, int64_t n_parents, int S, int reduce, int act, void* out_dev,
+                        int out_dtype, int64_t ld_out, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Engine.  Replaces GSSupervised.forward (models.py:71-91) for 2-layer stacks: owns the hop buffers, the
  * workspace and the kernel order (hop-0 draws before hop-1 draws).

@@ -16,6 +16,8 @@ struct LinearParams {
     LinearSeg seg[2];
     int n_segs; int64_t n; int act;
     void* out; int out_dtype; int64_t ld_out;
+    int pool_S = 1;    // > 1 (tensor-core kernel only): reduce every S consecutive output rows, store one row per parent
+    int pool_max = 1;  // 1 = max, 0 = mean
 };
 
 int linear_simt_launch(const LinearParams& P, cudaStream_t s);

@@ -144,13 +144,14 @@ namespace gsage {
 int linear_dispatch(const LinearParams& P, int exact, cudaStream_t s) {
     bool tc = !exact;
     for (int i = 0; i < P.n_segs; ++i) tc = tc && !P.seg[i].w_trans;
+    if (P.pool_S > 1) GS_CHECK_ARG(tc, "linear: the pooled epilogue exists on the tensor-core kernel only");
     for (int i = 0; i < P.n_segs && tc; ++i) {
         LinearParams one = P;
         one.n_segs = 1; one.seg[0] = P.seg[i];
         if (one.seg[0].O > 256) one.seg[0].O = 256;
         tc = linear_umma_eligible(one);
     }
-    if (!tc) return linear_simt_launch(P, s);
+    if (!tc) { GS_CHECK_ARG(P.pool_S <= 1, "linear: operands do not qualify for the tensor-core kernel (pooled epilogue)"); return linear_simt_launch(P, s); }
     if (linear_umma_eligible(P)) return linear_umma_launch(P, s);
     for (int i = 0; i < P.n_segs; ++i) {
         const LinearSeg& g = P.seg[i];
@@ -163,9 +164,25 @@ int linear_dispatch(const LinearParams& P, int exact, cudaStream_t s) {
             one.seg[0].bias = g.bias ? g.bias + c : nullptr;
             one.seg[0].col0 = g.col0 + c;
             if (linear_umma_eligible(one)) GS_TRY(linear_umma_launch(one, s));
-            else GS_TRY(linear_simt_launch(one, s));
+            else { GS_CHECK_ARG(P.pool_S <= 1, "linear: column block does not qualify for the tensor-core kernel (pooled epilogue)"); GS_TRY(linear_simt_launch(one, s)); }
         }
     }
     return GSAGE_OK;
 }
 }  // namespace gsage
+
+// out[p, col0 + o] = reduce_{j<S} act( A[row(p*S+j)] . W[o] + bias[o] )   -- the pool aggregators' MLP + pool in one launch
+// (tensor-core kernel only: bf16 or fp32-as-TF32 operands with 16-byte aligned rows, O % 16 == 0)
+extern "C" int gsage_linear_pooled(const gsage_linear_seg* seg, int64_t n_parents, int S, int reduce, int act, void* out_dev,
+                                   int out_dtype, int64_t ld_out, void* stream) {
+    GS_CHECK_ARG(seg && out_dev && n_parents >= 0 && S >= 1, "linear_pooled: bad arguments");
+    GS_CHECK_ARG(reduce == GSAGE_RED_MAX || reduce == GSAGE_RED_MEAN, "linear_pooled: reduce must be max or mean");
+    LinearParams P;
+    P.n_segs = 1; P.n = n_parents * S; P.act = act; P.out = out_dev; P.out_dtype = out_dtype; P.ld_out = ld_out;
+    P.seg[0] = LinearSeg{seg->a_dev, seg->a_dtype, seg->lda, seg->ids_dev, seg->w_dev, seg->w_dtype, seg->ldw, seg->d, seg->O,
+                         seg->bias_dev, seg->col0};
+    P.pool_S = S; P.pool_max = reduce == GSAGE_RED_MAX ? 1 : 0;
+    if (P.n == 0) return GSAGE_OK;
+    if (S == 1) { P.pool_S = 1; return linear_dispatch(P, 0, as_stream(stream)); }
+    return linear_dispatch(P, 0, as_stream(stream));
+}

@@ -61,6 +61,9 @@ struct UmmaParams {
     int n_tiles; int stages; int stage_bytes; int w_bytes;
     int any_reduce;       // some segment has S > 1: loaders take the register path (fused gather+mean)
     int full_count;       // arrivals that complete a `full` barrier phase
+    int tile_rows;        // rows of the input each tile covers: 128, or floor(128/S)*S with the pooled epilogue
+    int pool_S;           // > 1: the epilogue reduces every S consecutive rows (one parent) and stores ONE row per parent
+    int pool_max;         // 1 = max, 0 = mean
     int tf32;             // operands are fp32 read as TF32 (kind::tf32, 32 elements per 128-byte chunk row) instead of bf16
     int uk;               // elements per 128-byte chunk row: 64 (bf16) | 32 (tf32)
     int prefetch;         // L2-prefetch whole rows of the next tile (GSAGE_UMMA_PREFETCH=1; off by default)
@@ -215,6 +218,7 @@ __global__ void __launch_bounds__(kThreads, 1) linear_umma_kernel(const UmmaPara
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint64_t* bars = (uint64_t*)(smem + (size_t)P.stages * P.stage_bytes);
     uint32_t* tmem_slot = (uint32_t*)(bars + 2 * 8 + 4);
+    float* pool_scratch = (float*)(bars + 32);              // 128 x 33 floats, used only by the pooled epilogue
     const uint32_t bar_base = smem_u32(bars);
     auto full_bar = [&](int s) { return bar_base + 8u * s; };
     auto empty_bar = [&](int s) { return bar_base + 8u * (8 + s); };
@@ -248,7 +252,7 @@ __global__ void __launch_bounds__(kThreads, 1) linear_umma_kernel(const UmmaPara
             const int buf = it & 1;
             mbar_wait(tfull_bar(buf), (it >> 1) & 1, P.err);
             tc_fence_after();
-            const int64_t row = (int64_t)tile * UM + row_in_tile;
+            const int64_t row = (int64_t)tile * P.tile_rows + row_in_tile;
             for (int s = 0; s < P.n_segs; ++s) {
                 const UmmaSeg& sg = P.seg[s];
                 for (int c0 = 0; c0 < sg.O; c0 += 32) {
@@ -256,7 +260,33 @@ __global__ void __launch_bounds__(kThreads, 1) linear_umma_kernel(const UmmaPara
                     uint32_t r[32];
                     tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(buf * 256 + sg.acc_col + c0), r);
                     tmem_ld_wait();
-                    if (row < P.n && !(P.debug & 8)) {
+                    if (P.pool_S > 1) {
+                        // segmented reduce over the S rows of each parent (nn_modules.py:225-226,240): rows -> smem, then
+                        // (parent, column) pairs; the MLP output of the neighbour rows never goes to HBM
+                        const int S = P.pool_S, parents = P.tile_rows / S, valid = min(32, sg.O - c0);
+                        float* mine = pool_scratch + row_in_tile * 33;
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            float f = __uint_as_float(r[j]);
+                            if (sg.bias && j < valid) f += __ldg(sg.bias + c0 + j);
+                            mine[j] = apply_act(f, P.act);
+                        }
+                        asm volatile("bar.sync 1, 128;" ::: "memory");
+                        const int64_t parent0 = (int64_t)tile * parents, n_parents = P.n / S;
+                        for (int o = threadIdx.x; o < parents * 32; o += 128) {
+                            const int pp = o >> 5, c = o & 31;
+                            if (parent0 + pp < n_parents && c < valid) {
+                                const float* src = pool_scratch + pp * S * 33 + c;
+                                float a = src[0];
+                                if (P.pool_max) { for (int j = 1; j < S; ++j) a = fmaxf(a, src[j * 33]); }
+                                else { for (int j = 1; j < S; ++j) a += src[j * 33]; a *= 1.0f / (float)S; }
+                                const int64_t at = (parent0 + pp) * P.ld_out + sg.col0 + c0 + c;
+                                if (P.out_bf16) reinterpret_cast<__nv_bfloat16*>(P.out)[at] = __float2bfloat16_rn(a);
+                                else reinterpret_cast<float*>(P.out)[at] = a;
+                            }
+                        }
+                        asm volatile("bar.sync 1, 128;" ::: "memory");
+                    } else if (row < P.n && !(P.debug & 8)) {
                         void* o = (char*)P.out + (row * P.ld_out + sg.col0 + c0) * (P.out_bf16 ? 2 : 4);
                         const float* bias = sg.bias ? sg.bias + c0 : nullptr;
                         const int valid = min(32, sg.O - c0);
@@ -315,7 +345,7 @@ __global__ void __launch_bounds__(kThreads, 1) linear_umma_kernel(const UmmaPara
                     const UmmaSeg& sg = P.seg[sidx];
                     const uint32_t w_bytes = (uint32_t)sg.O * 128u;
                     if (P.prefetch) {                               // whole rows of the NEXT tile of this segment -> L2
-                        const int64_t nbase = ((int64_t)tile + gridDim.x) * UM + 4 * lane;
+                        const int64_t nbase = ((int64_t)tile + gridDim.x) * P.tile_rows + 4 * lane;
                         const uint32_t row_bytes = (uint32_t)sg.kvalid * 2u;
 #pragma unroll
                         for (int q = 0; q < 4; ++q) {
@@ -327,7 +357,7 @@ __global__ void __launch_bounds__(kThreads, 1) linear_umma_kernel(const UmmaPara
                     }
                     int r0 = 0, r1 = 0, r2 = 0, r3 = 0;            // lane l gathers tile rows 4l .. 4l+3 by id
                     if (sg.ids) {
-                        const int64_t base = (int64_t)tile * UM + 4 * lane;
+                        const int64_t base = (int64_t)tile * P.tile_rows + 4 * lane;
                         if (base + 0 < P.n) r0 = (int)__ldg(sg.ids + base + 0);
                         if (base + 1 < P.n) r1 = (int)__ldg(sg.ids + base + 1);
                         if (base + 2 < P.n) r2 = (int)__ldg(sg.ids + base + 2);
@@ -340,7 +370,7 @@ __global__ void __launch_bounds__(kThreads, 1) linear_umma_kernel(const UmmaPara
                         if (lane == 0) {
                             mbar_arrive_expect_tx(full_bar(stage), w_bytes + ((sg.ids && (P.debug & 1)) ? 0u : (uint32_t)kABytes));
                             tma_load_2d(sa_u + kABytes, &M.w[sidx], kc * P.uk, 0, full_bar(stage));
-                            if (!sg.ids) tma_load_2d(sa_u, &M.a[sidx], kc * P.uk, tile * UM, full_bar(stage));
+                            if (!sg.ids) tma_load_2d(sa_u, &M.a[sidx], kc * P.uk, tile * P.tile_rows, full_bar(stage));
                         }
                         __syncwarp();                              // expect_tx is posted before any lane's copy can complete
                         if (sg.ids && !(P.debug & 1)) tma_gather4(sa_u + lane * 512, &M.g[sidx], kc * P.uk, r0, r1, r2, r3, full_bar(stage));
@@ -540,7 +570,12 @@ int linear_umma_launch(const LinearParams& P, cudaStream_t s) {
     }
     GS_CHECK_ARG(col <= 256, "linear_umma: accumulators need %d TMEM columns (max 256 per buffer)", col);
     U.n_segs = P.n_segs; U.n = P.n; U.act = P.act; U.out = P.out; U.out_bf16 = P.out_dtype == GSAGE_BF16; U.ld_out = P.ld_out;
-    U.n_tiles = (int)ceil_div(P.n, UM);
+    U.pool_S = P.pool_S > 1 ? P.pool_S : 1;
+    U.pool_max = P.pool_max;
+    GS_CHECK_ARG(U.pool_S <= UM, "linear_umma: pooled epilogue needs S <= 128");
+    GS_CHECK_ARG(U.pool_S == 1 || P.n % U.pool_S == 0, "linear_umma: pooled epilogue needs n to be a multiple of S");
+    U.tile_rows = U.pool_S > 1 ? (UM / U.pool_S) * U.pool_S : UM;
+    U.n_tiles = (int)ceil_div(P.n, U.tile_rows);
     for (int i = 0; i < P.n_segs; ++i) U.any_reduce |= (U.seg[i].S > 1) ? 1 : 0;
     U.prefetch = 0;      // measured: 275 us with, 198 us without (reddit layer-1 shape) -- the prefetches queue behind the tile loads
     if (const char* e = getenv("GSAGE_UMMA_PREFETCH")) U.prefetch = atoi(e) != 0;
@@ -548,7 +583,7 @@ int linear_umma_launch(const LinearParams& P, cudaStream_t s) {
     if (const char* e = getenv("GSAGE_UMMA_DEBUG")) U.debug = atoi(e);
     U.w_bytes = maxO * UK * 2;
     U.stage_bytes = (kABytes + U.w_bytes + 1023) / 1024 * 1024;
-    const int budget = 200 * 1024;
+    const int budget = (P.pool_S > 1 ? 180 : 200) * 1024;
     U.stages = budget / U.stage_bytes;
     if (U.stages > 8) U.stages = 8;
     GS_CHECK_ARG(U.stages >= 3, "linear_umma: tile too large for shared memory");
@@ -557,7 +592,7 @@ int linear_umma_launch(const LinearParams& P, cudaStream_t s) {
         GS_CUDA(cudaMemset(g_umma_err, 0, sizeof(int)));
     }
     U.err = g_umma_err;
-    const size_t smem = (size_t)U.stages * U.stage_bytes + 1024 /*align slack*/ + 256 /*barriers*/;
+    const size_t smem = (size_t)U.stages * U.stage_bytes + 1024 /*align slack*/ + 256 /*barriers*/ + (U.pool_S > 1 ? 128 * 33 * 4 : 0);
     static bool attr_set = false;
     if (!attr_set) {
         GS_CUDA(cudaFuncSetAttribute(linear_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));

@@ -120,6 +120,15 @@ def linear(segments, n, act=None, out=None, out_dtype=torch.float32, exact=True)
     return out
 
 
+def linear_pooled(a, w, n_parents, S, reduce='max', ids=None, bias=None, act='relu', out_dtype=torch.float32):
+    """reduce_j act(a[ids[p*S+j]] . w^T + bias): the pool aggregators' per-neighbour MLP with the pool fused in the epilogue."""
+    _bind_device(a)
+    seg = _lib.LinearSeg(ptr(a), dt(a), _rows2d(a), _ids_arg(ids), ptr(w), dt(w), _rows2d(w), w.shape[1], w.shape[0], ptr(bias), 0, 1, 0)
+    out = torch.empty((n_parents, w.shape[0]), dtype=out_dtype, device=a.device)
+    check(lib().gsage_linear_pooled(C.byref(seg), n_parents, S, _lib.REDUCE[reduce], _lib.ACT[act], ptr(out), dt(out), _rows2d(out), stream()))
+    return out
+
+
 def attention_weights(na, xa, n_parents, S):
     _bind_device(na)
     w = torch.empty((n_parents * S,), dtype=torch.float32, device=na.device)

@@ -238,3 +238,25 @@ def test_umma_tf32_projection(g, n, d, O):
     assert err > 0 or d < 8                       # it really ran in reduced precision (the FFMA path would be ~1e-6)
     exact = g.ops.linear(segs, n, act='relu', out_dtype=torch.float32, exact=True)
     np.testing.assert_allclose(exact.cpu().numpy(), want.numpy(), rtol=1e-4, atol=1e-5)
+
+
+@pytest.mark.parametrize('n,S,d,H', [(100, 10, 64, 512), (37, 25, 64, 512), (513, 3, 100, 32), (8, 128, 64, 48)])
+@pytest.mark.parametrize('reduce', ['max', 'mean'])
+def test_umma_pooled_epilogue(g, n, S, d, H, reduce):
+    """relu(MLP) on tcgen05 with the max / mean over the S neighbour rows of each parent done in the epilogue."""
+    gen = torch.Generator().manual_seed(n * S + d)
+    rows = 3000
+    table = _bf16(torch.randn((rows, d), generator=gen))
+    w, b = _bf16(torch.randn((H, d), generator=gen) / d ** 0.5), torch.randn((H,), generator=gen)
+    ids = torch.randint(0, rows, (n * S,), generator=gen)
+    pad = lambda t: g.ops.pad_table(t.float(), torch.bfloat16)[0][:, :t.shape[1]]
+    h = torch.relu(table[ids].double() @ w.double().t() + b.double()).view(n, S, H)
+    want = h.max(dim=1)[0] if reduce == 'max' else h.mean(dim=1)
+    got = g.ops.linear_pooled(pad(table), pad(w), n, S, reduce, ids=ids.cuda(), bias=b.cuda())
+    np.testing.assert_allclose(got.cpu().numpy(), want.numpy(), rtol=2e-4, atol=2e-4)
+    # contiguous neighbours (ids=None): rows p*S+j of the operand itself
+    nb = _bf16(torch.randn((n * S, d), generator=gen))
+    h = torch.relu(nb.double() @ w.double().t() + b.double()).view(n, S, H)
+    want = h.max(dim=1)[0] if reduce == 'max' else h.mean(dim=1)
+    got = g.ops.linear_pooled(pad(nb), pad(w), n, S, reduce, bias=b.cuda(), out_dtype=torch.bfloat16)
+    np.testing.assert_allclose(got.float().cpu().numpy(), want.numpy(), rtol=1e-2, atol=1e-2)
