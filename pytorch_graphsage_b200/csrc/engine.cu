@@ -211,7 +211,7 @@ static int apply_aggregator(gsage_engine* e, int layer, const RowSrc& x, const R
     case GSAGE_AGG_MAX_POOL:
     case GSAGE_AGG_MEAN_POOL: {
         const int H = e->hid;
-        if (!exact && S <= 128 && H % 16 == 0) {
+        if (!exact) {
             // MLP on tcgen05 with the pool (max / mean over the S neighbour rows) done in the epilogue: the (n*S, 512)
             // hidden rows never exist in HBM
             LinearParams P;
@@ -219,8 +219,7 @@ static int apply_aggregator(gsage_engine* e, int layer, const RowSrc& x, const R
             P.seg[0] = LinearSeg{nb.base, nb.dtype, nb.ld, nb.ids, e->w_mlp[layer].p, e->w_mlp[layer].dtype, e->w_mlp[layer].ld, d, H,
                                  e->b_mlp[layer], 0};
             P.pool_S = S; P.pool_max = e->cfg.aggregator == GSAGE_AGG_MAX_POOL ? 1 : 0;
-            LinearParams probe = P; probe.seg[0].O = std::min(H, 256);
-            if (linear_umma_eligible(probe)) {
+            if (linear_pool_umma_eligible(P)) {
                 GS_TRY(linear_dispatch(P, 0, s));
                 RowSrc p{e->Pp, T, H, n, nullptr, H};
                 return combine_call(x, e->w_x[layer], p, e->w_n[layer], O, n, act, out, out_dtype, ld_out, exact, s, e->b_x[layer], nullptr);

@@ -24,6 +24,9 @@ int linear_simt_launch(const LinearParams& P, cudaStream_t s);
 // tcgen05 kernel (linear_umma.cu): bf16 operands, 16-byte aligned rows, O % 16 == 0, <= 256 accumulator columns
 bool linear_umma_eligible(const LinearParams& P);
 int linear_umma_launch(const LinearParams& P, cudaStream_t s);
+// pool aggregators: MLP + pool over the S rows of a parent in one tcgen05 kernel (linear_pool_umma.cu, swap-AB)
+bool linear_pool_umma_eligible(const LinearParams& P);
+int linear_pool_umma_launch(const LinearParams& P, cudaStream_t s);
 // picks the tensor-core kernel when every operand qualifies and `exact` == 0, else the FFMA kernel
 int linear_dispatch(const LinearParams& P, int exact, cudaStream_t s);
 

@@ -142,9 +142,13 @@ namespace gsage {
 // split into column blocks, two-segment calls that do not fit are issued one segment at a time);
 // anything else -- and everything when `exact` is set -- runs on the fp32 FFMA kernel.
 int linear_dispatch(const LinearParams& P, int exact, cudaStream_t s) {
+    if (P.pool_S > 1) {
+        GS_CHECK_ARG(!exact && linear_pool_umma_eligible(P), "linear: the fused MLP+pool needs operands that qualify for the tensor-core kernel "
+                     "(bf16 or fp32-as-TF32, 16-byte aligned rows, one segment)");
+        return linear_pool_umma_launch(P, s);
+    }
     bool tc = !exact;
     for (int i = 0; i < P.n_segs; ++i) tc = tc && !P.seg[i].w_trans;
-    if (P.pool_S > 1) GS_CHECK_ARG(tc, "linear: the pooled epilogue exists on the tensor-core kernel only");
     for (int i = 0; i < P.n_segs && tc; ++i) {
         LinearParams one = P;
         one.n_segs = 1; one.seg[0] = P.seg[i];
