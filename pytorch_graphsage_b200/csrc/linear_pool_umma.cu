@@ -42,6 +42,7 @@ struct PoolParams {
 
 struct PoolMaps { CUtensorMap w; CUtensorMap a; CUtensorMap g; };
 
+template <int ACT, bool POOL_MAX>
 __global__ void __launch_bounds__(kPoolThreads, 1) linear_pool_umma_kernel(const PoolParams P, const __grid_constant__ PoolMaps M) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -84,7 +85,7 @@ __global__ void __launch_bounds__(kPoolThreads, 1) linear_pool_umma_kernel(const
                 if (hb >= P.h_blocks) break;
                 const int h = hb * PM + quarter * 32 + lane;
                 const float bias = (P.bias && h < P.H) ? __ldg(P.bias + h) : 0.0f;
-                float acc = P.pool_max ? -3.0e38f : 0.0f;
+                float acc = POOL_MAX ? -3.0e38f : 0.0f;
                 int cnt = 0;
                 int64_t parent = (int64_t)rb * parents_per_block;
                 for (int c0 = 0; c0 < cols; c0 += 32) {
@@ -94,17 +95,19 @@ __global__ void __launch_bounds__(kPoolThreads, 1) linear_pool_umma_kernel(const
 #pragma unroll
                     for (int q = 0; q < 32; ++q) {
                         if (c0 + q < cols) {
-                            const float v = apply_act(__uint_as_float(r[q]) + bias, P.act);
-                            acc = P.pool_max ? fmaxf(acc, v) : acc + v;
+                            float v = __uint_as_float(r[q]) + bias;
+                            if (ACT == GSAGE_ACT_RELU) v = fmaxf(v, 0.0f);
+                            if (ACT == GSAGE_ACT_TANH) v = tanhf(v);
+                            acc = POOL_MAX ? fmaxf(acc, v) : acc + v;
                             if (++cnt == P.S) {
                                 if (h < P.H) {
-                                    const float o = P.pool_max ? acc : acc * (1.0f / (float)P.S);
+                                    const float o = POOL_MAX ? acc : acc * (1.0f / (float)P.S);
                                     const int64_t at = parent * P.ld_out + P.col0 + h;
                                     if (P.out_bf16) reinterpret_cast<__nv_bfloat16*>(P.out)[at] = __float2bfloat16_rn(o);
                                     else reinterpret_cast<float*>(P.out)[at] = o;
                                 }
                                 ++parent; cnt = 0;
-                                acc = P.pool_max ? -3.0e38f : 0.0f;
+                                acc = POOL_MAX ? -3.0e38f : 0.0f;
                             }
                         }
                     }
@@ -230,14 +233,21 @@ int linear_pool_umma_launch(const LinearParams& P, cudaStream_t s) {
     if (g.ids) GS_TRY(make_map(&maps.g, g.a, 0x7FFFFFFF, g.d, g.lda, 1, es));
     else GS_TRY(make_map(&maps.a, g.a, P.n, g.d, g.lda, 128, es));
     const size_t smem = (size_t)U.stages * U.stage_bytes + 1024 + 256;
-    static bool attr_set = false;
-    if (!attr_set) {
-        GS_CUDA(cudaFuncSetAttribute(linear_pool_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        attr_set = true;
-    }
     const int tiles = U.row_blocks * U.passes;
     const int grid = tiles < sm_count() ? tiles : sm_count();
-    linear_pool_umma_kernel<<<grid, kPoolThreads, smem, s>>>(U, maps);
+#define GS_POOL_LAUNCH(A, MX)                                                                                                   \
+    do {                                                                                                                        \
+        static bool attr_set = false;                                                                                           \
+        if (!attr_set) {                                                                                                        \
+            GS_CUDA(cudaFuncSetAttribute(linear_pool_umma_kernel<A, MX>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); \
+            attr_set = true;                                                                                                    \
+        }                                                                                                                       \
+        linear_pool_umma_kernel<A, MX><<<grid, kPoolThreads, smem, s>>>(U, maps);                                               \
+    } while (0)
+    if (U.act == GSAGE_ACT_RELU) { if (U.pool_max) GS_POOL_LAUNCH(GSAGE_ACT_RELU, true); else GS_POOL_LAUNCH(GSAGE_ACT_RELU, false); }
+    else if (U.act == GSAGE_ACT_TANH) { if (U.pool_max) GS_POOL_LAUNCH(GSAGE_ACT_TANH, true); else GS_POOL_LAUNCH(GSAGE_ACT_TANH, false); }
+    else { if (U.pool_max) GS_POOL_LAUNCH(GSAGE_ACT_NONE, true); else GS_POOL_LAUNCH(GSAGE_ACT_NONE, false); }
+#undef GS_POOL_LAUNCH
     GS_LAUNCHED();
     return GSAGE_OK;
 }
