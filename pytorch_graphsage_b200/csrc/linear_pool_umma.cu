@@ -15,8 +15,8 @@
 // Tiles: one row block of R = floor(128/S)*S neighbour rows against up to FOUR blocks of 128 hidden units at once
 // (4 x 128 fp32 accumulator columns = the whole TMEM), so every neighbour row is gathered exactly once per pass
 // (a first version with one hidden block per tile re-gathered every row block 4x and was TMA-request bound:
-// 5.5 ms/step on pokec max-pool; unfused 2.76 ms).  Eight epilogue warps (two per TMEM lane quarter) split the
-// hidden blocks.  Warp roles, smem ring and all-TMA operand loads (tile::gather4 for rows by id) as in linear_umma.cu.
+// 5.5 ms/step on pokec max-pool; unfused 2.76 ms).  Sixteen epilogue warps (four per TMEM lane quarter, one hidden
+// block each).  Warp roles, smem ring and all-TMA operand loads (tile::gather4 for rows by id) as in linear_umma.cu.
 #include "linear.cuh"
 #include "umma_ptx.cuh"
 #include <string.h>
@@ -25,7 +25,7 @@ namespace gsage {
 
 static constexpr int PM = 128;            // hidden units per block (UMMA M)
 static constexpr int kHB = 4;             // hidden blocks per pass: 4 x 128 accumulator columns = all of TMEM
-static constexpr int kPoolEpiWarps = 8;
+static constexpr int kPoolEpiWarps = 16;          // four warps per TMEM lane quarter: one hidden block each
 static constexpr int kPoolThreads = 32 * (kPoolEpiWarps + 2);
 static constexpr int kMBytes = PM * 128;                      // 16 KB: 128 W rows x one 128-byte chunk
 static constexpr int kNBytes = 128 * 128;                     // 16 KB: up to 128 neighbour rows x one chunk
@@ -73,14 +73,14 @@ __global__ void __launch_bounds__(kPoolThreads, 1) linear_pool_umma_kernel(const
         // ============ EPILOGUE: one hidden unit per thread, pool along the columns (warps w and w+4 share a lane quarter) ============
         int it = 0;
         const int parents_per_block = P.R / P.S;
-        const int quarter = warp & 3, half = warp >> 2;
+        const int quarter = warp & 3, first = warp >> 2;
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
             const int rb = tile / P.passes, pass = tile - rb * P.passes;
             mbar_wait(tfull_bar, it & 1, P.err);
             tc_fence_after();
             const int64_t row0 = (int64_t)rb * P.R;
             const int cols = (int)min((int64_t)P.R, P.n_rows - row0);          // valid neighbour rows of this block
-            for (int j = half; j < kHB; j += 2) {                               // this warp's hidden blocks of the pass
+            for (int j = first; j < kHB; j += kPoolEpiWarps / 4) {              // this warp's hidden block(s) of the pass
                 const int hb = pass * kHB + j;
                 if (hb >= P.h_blocks) break;
                 const int h = hb * PM + quarter * 32 + lane;
