@@ -60,7 +60,7 @@ def parse_args():
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--workload', default='reddit', choices=sorted(WORKLOADS))
-    ap.add_argument('--batch', type=int, default=8192, help='seed nodes per step per GPU')
+    ap.add_argument('--batch', type=int, default=16384, help='seed nodes per step per GPU')
     ap.add_argument('--cpu-batch', type=int, default=512, help='seed nodes per CPU-baseline step (train.py:48)')
     ap.add_argument('--cpu-seconds', type=float, default=12.0, help='budget of the cpu_baseline leg')
     ap.add_argument('--no-cpu-baseline', action='store_true')
