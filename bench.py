@@ -65,6 +65,7 @@ def parse_args():
     ap.add_argument('--cpu-seconds', type=float, default=12.0, help='budget of the cpu_baseline leg')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-train', action='store_true', help='skip the train-step leg')
+    ap.add_argument('--no-ahead', action='store_true', help='sample inside each forward instead of one batch ahead on the sampler stream')
     ap.add_argument('--scale', type=float, default=1.0, help='shrink the graph (debug only; reported in config)')
     return ap.parse_args()
 
@@ -148,6 +149,9 @@ def workload_config(args, prob):
             'sampler': 'sparse_uniform_neighbor_sampler (device MT19937, bit-exact numpy legacy stream)',
             'l2_policy': 'inputs larger than L2 (table %.0f MB + per-step gather footprint); no flush' %
                          ((s['n_nodes'] + 1) * (prob['feats_dim'] or 64) * (2 if prob['table_dtype'] == 'bf16' else 4) / 1e6),
+            'pipeline': ('none: every forward samples its own batch' if getattr(args, 'no_ahead', False) else
+                         'sample-ahead: the draws + CSR lookups of batch i+1 run on a second stream under the aggregation of batch i; '
+                         'every timed step still samples one batch and aggregates one batch'),
             'parallelism': 'seed-sharded dp%d, graph+table replicated, no data-path collective' % max(1, args.gpus)}
 
 
@@ -305,8 +309,21 @@ def run_ours(args):
         return float(t.item())
 
     # ---- device-resident timing -----------------------------------------------------------------------------
+    ahead = not args.no_ahead
+    step_no = [0]
+
+    def step():
+        i = step_no[0]
+        step_no[0] += 1
+        out = model(dev_ids[i % n_batches], table)
+        if ahead:                                                                # batch i+1 is drawn while batch i aggregates
+            model.sample_ahead(dev_ids[(i + 1) % n_batches], table)
+        return out
+
+    if ahead:
+        model.sample_ahead(dev_ids[0], table)
     for i in range(max(3, args.warmup)):
-        model(dev_ids[i % n_batches], table)
+        step()
     g.default_rng().check()
     graph.check()
     model.profile(True)
@@ -321,7 +338,7 @@ def run_ours(args):
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
     for i in range(args.steps):
-        model(dev_ids[i % n_batches], table)
+        step()
     ev1.record()
     barrier()
     launches = g.launch_count() - launches0
@@ -334,15 +351,24 @@ def run_ours(args):
     value = WORLD * B * ROWS_PER_SEED / (ms_step / 1e3)
 
     # ---- end to end through the host-buffer entry -----------------------------------------------------------------
+    if ahead:
+        model(dev_ids[step_no[0] % n_batches], table)                          # consume the batch the last timed step drew ahead
+
+    def host_step(i):                                                          # synchronises every step (D2H of the logits)
+        nxt = host_ids[(i + 1) % n_batches] if ahead else None
+        model.forward_host(host_ids[i % n_batches], table, host_out, next_ids_host=nxt)
+
     for i in range(3):
-        model.forward_host(host_ids[i % n_batches], table, host_out)
+        host_step(i)
     barrier()
     t0 = time.perf_counter()
     ev0.record()
-    for i in range(args.steps):
-        model.forward_host(host_ids[i % n_batches], table, host_out)           # synchronises every step (D2H result)
+    for i in range(3, 3 + args.steps):
+        host_step(i)
     ev1.record()
     barrier()
+    if ahead:
+        model.forward_host(host_ids[(3 + args.steps) % n_batches], table, host_out)   # drain the pending batch
     e2e_ms = max_over_ranks(max(ev0.elapsed_time(ev1), 0.0)) / args.steps
     e2e_wall_ms = max_over_ranks((time.perf_counter() - t0) * 1e3) / args.steps
     e2e_ms = max(e2e_ms, e2e_wall_ms)
@@ -357,22 +383,26 @@ def run_ours(args):
         opt = torch.optim.Adam(model.parameters(), lr=0.01)
         side = torch.cuda.Stream()
         k_train = max(3, min(args.steps, 30))
-        for i in range(3):
+        def train_step(i):
             model.train_step(dev_ids[i % n_batches], table, tgts[i % n_batches], F.cross_entropy, optimizer=opt, grad_scale=1.0 / WORLD,
-                             overlap_stream=side)
+                             overlap_stream=side, next_ids=dev_ids[(i + 1) % n_batches] if ahead else None)
+
+        for i in range(3):
+            train_step(i)
         barrier()
         ev0.record()
-        for i in range(k_train):
-            model.train_step(dev_ids[i % n_batches], table, tgts[i % n_batches], F.cross_entropy, optimizer=opt, grad_scale=1.0 / WORLD,
-                             overlap_stream=side)
+        for i in range(3, 3 + k_train):
+            train_step(i)
         ev1.record()
         barrier()
+        if ahead:
+            model(dev_ids[(3 + k_train) % n_batches], table)                       # drain the pending batch
         t_ms = max_over_ranks(ev0.elapsed_time(ev1)) / k_train
         train = {'ms_per_step': t_ms, 'seeds_per_s': WORLD * B / (t_ms / 1e3), 'steps': k_train,
                  'allreduce_bytes_per_step': int(model._bucket().flat.numel()) * 4,
                  'collective': 'one flat fp32 gradient bucket, NCCL all-reduce in two pieces (fc + layer-2 head overlapped with the '
                                'layer-1 weight-gradient kernels)' if WORLD > 1 else 'none (1 GPU)',
-                 'note': 'backward = fp32 FFMA wgrad kernels (tensor-core wgrad is a next-round item); loss + Adam are stock torch'}
+                 'note': 'loss + clip + Adam are stock torch'}
 
     if RANK != 0:
         if WORLD > 1:

@@ -230,6 +230,26 @@ int gsage_engine_forward_sharded(gsage_engine* e, gsage_graph* g, gsage_rng* rng
  * This is the end-to-end entry a reference-side caller binds (ids and logits are what models.py:71 takes/returns). */
 int gsage_engine_forward_host(gsage_engine* e, gsage_graph* g, gsage_rng* rng, const int64_t* ids_host, int64_t B,
                               float* logits_host, void* stream);
+/* Sample-ahead.  Draws and samples both hops of a batch NOW, on the engine's own high-priority stream, into a spare id
+ * buffer; the next gsage_engine_forward[_sharded|_host] call -- which must name the same batch: same ids pointer, B,
+ * (global_B, first), graph and rng -- skips its sampling section and only waits for that stream.  The (latency-bound)
+ * sampling of batch i+1 then runs underneath the HBM-bound aggregation of batch i.  The draw order on the RNG stream is
+ * the call order, exactly as if the sampling had happened inside the forwards (models.py:78-79), so the sampled ids are
+ * bit-identical with and without it.  Call it right AFTER queueing the forward (and backward) it should overlap with:
+ * the sampler stream only waits for the batch BEFORE that one (the last reader of the spare id buffer).  The ids are
+ * copied when the call executes on the device: keep `ids_dev` / `ids_host` (pinned) alive until the matching forward.
+ * Other state the forward reads (weights, tables) is not touched. */
+int gsage_engine_sample_ahead(gsage_engine* e, gsage_graph* g, gsage_rng* rng, const int64_t* ids_dev, int64_t B,
+                              int64_t global_B, int64_t first, void* stream);
+int gsage_engine_sample_ahead_host(gsage_engine* e, gsage_graph* g, gsage_rng* rng, const int64_t* ids_host, int64_t B,
+                                   void* stream);
+/* gsage_engine_forward_host that also queues the sample-ahead of the NEXT host batch (H2D of its ids + both hops) before
+ * it blocks on its own logits: the end-to-end loop of a caller that knows its next batch (problem.py:141-153 does).
+ * `next_ids_host` NULL = plain gsage_engine_forward_host. */
+int gsage_engine_forward_host_next(gsage_engine* e, gsage_graph* g, gsage_rng* rng, const int64_t* ids_host, int64_t B,
+                                   const int64_t* next_ids_host, int64_t next_B, float* logits_host, void* stream);
+/* 1 while a sampled-ahead batch waits for its forward */
+int gsage_engine_sample_ahead_pending(const gsage_engine* e);
 /* device views of the last forward's intermediates (valid until the next forward): hop ids and layer outputs.
  * what: 0 ids0, 1 ids1, 2 ids2 (int64) ; 10 layer-1 output (26B x 2*O1) ; 11 layer-2 output (B x 2*O2) */
 int gsage_engine_peek(gsage_engine* e, int what, const void** ptr_dev, int64_t* rows, int64_t* cols, int64_t* ld,

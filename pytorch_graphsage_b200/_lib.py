@@ -87,6 +87,10 @@ _SIGNATURES = {
     'gsage_engine_forward': (C.c_int, [c_p, c_p, c_p, c_p, c_i64, c_p, c_p]),
     'gsage_engine_forward_sharded': (C.c_int, [c_p, c_p, c_p, c_p, c_i64, c_i64, c_i64, c_p, c_p]),
     'gsage_engine_forward_host': (C.c_int, [c_p, c_p, c_p, c_p, c_i64, c_p, c_p]),
+    'gsage_engine_forward_host_next': (C.c_int, [c_p, c_p, c_p, c_p, c_i64, c_p, c_i64, c_p, c_p]),
+    'gsage_engine_sample_ahead': (C.c_int, [c_p, c_p, c_p, c_p, c_i64, c_i64, c_i64, c_p]),
+    'gsage_engine_sample_ahead_host': (C.c_int, [c_p, c_p, c_p, c_p, c_i64, c_p]),
+    'gsage_engine_sample_ahead_pending': (C.c_int, [c_p]),
     'gsage_engine_peek': (C.c_int, [c_p, C.c_int, C.POINTER(c_p), C.POINTER(c_i64), C.POINTER(c_i64), C.POINTER(c_i64), C.POINTER(C.c_int)]),
     'gsage_engine_workspace_bytes': (c_i64, [c_p]),
     'gsage_engine_backward_head': (C.c_int, [c_p, c_p, C.POINTER(Grads), c_p]),

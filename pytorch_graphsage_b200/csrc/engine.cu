@@ -98,6 +98,13 @@ struct gsage_engine {
     char* ws = nullptr; int64_t ws_bytes = 0;
     // carved views
     int64_t* ids = nullptr; uint32_t* sel = nullptr; int64_t* look0 = nullptr;
+    // sample-ahead (gsage_engine_sample_ahead): the hop ids of the NEXT batch are drawn on the engine's own high-priority
+    // stream into the spare id buffer while the current batch aggregates; `ids` always points at the slot in use
+    int64_t* ids_slot[2] = {nullptr, nullptr}; int cur = 0; uint32_t* sel_ahead = nullptr;
+    cudaStream_t ss = nullptr; cudaEvent_t ev_ahead = nullptr;
+    cudaEvent_t ev_done[2] = {nullptr, nullptr}; bool done_valid[2] = {false, false};   // last reader of each id slot (forward / backward) finished
+    struct Ahead { bool valid = false; const void* src = nullptr; int64_t B = 0, global_B = 0, first = 0;
+                   gsage_graph* g = nullptr; gsage_rng* rng = nullptr; } ahead;
     void* X = nullptr;                  // materialised prepped rows (non-identity preps)
     void* M = nullptr;                  // reduced neighbour rows: [layer-1 app 1 (n0) | layer-1 app 2 (n1) | layer 2 (n0)] x ld_m
     int64_t ld_m = 0;                   // (kept after the forward: the backward pass reads them)
@@ -295,7 +302,9 @@ int gsage_engine_create(const gsage_engine_config* cfg, gsage_engine** out) {
     int64_t off = 0;
     auto carve = [&](int64_t bytes) { int64_t at = off; off += pad_to(std::max<int64_t>(bytes, 16), 256); return at; };
     const int64_t o_ids = carve(8 * (e->n0 + e->n1 + e->n2));
+    const int64_t o_ids1 = carve(8 * (e->n0 + e->n1 + e->n2));
     const int64_t o_sel = carve(4 * e->n2);
+    const int64_t o_sel1 = carve(4 * e->n2);
     const int64_t o_look = carve(8 * e->n0);
     const int64_t o_X = (cfg->prep == GSAGE_PREP_IDENTITY || e->fold_prep) ? -1 : carve(es * e->ld_prep * (e->n0 + e->n1 + e->n2));
     const int64_t dmax = std::max<int64_t>(e->ld_prep, e->ld_h1);
@@ -344,6 +353,7 @@ int gsage_engine_create(const gsage_engine_config* cfg, gsage_engine** out) {
     }
     auto at = [&](int64_t o) -> char* { return o < 0 ? nullptr : e->ws + o; };
     e->ids = (int64_t*)at(o_ids); e->sel = (uint32_t*)at(o_sel); e->look0 = (int64_t*)at(o_look);
+    e->ids_slot[0] = e->ids; e->ids_slot[1] = (int64_t*)at(o_ids1); e->cur = 0; e->sel_ahead = (uint32_t*)at(o_sel1);
     e->X = at(o_X); e->M = at(o_M); e->HN = at(o_HN); e->Pp = at(o_P);
     e->T1 = at(o_T1); e->NA = at(o_NA); e->T1x = at(o_T1x); e->XA = at(o_XA); e->AW = (float*)at(o_AW);
     e->H1 = at(o_H1); e->Z = (float*)at(o_Z); e->ZN = (float*)at(o_ZN); e->LG = (float*)at(o_LG);
@@ -355,6 +365,9 @@ int gsage_engine_create(const gsage_engine_config* cfg, gsage_engine** out) {
 void gsage_engine_destroy(gsage_engine* e) {
     if (!e) return;
     for (cudaEvent_t ev : e->prof.pool) cudaEventDestroy(ev);
+    if (e->ss) { cudaStreamSynchronize(e->ss); cudaStreamDestroy(e->ss); }
+    for (int i = 0; i < 2; ++i) if (e->ev_done[i]) cudaEventDestroy(e->ev_done[i]);
+    if (e->ev_ahead) cudaEventDestroy(e->ev_ahead);
     cudaFree(e->ws);
     cudaFree(e->wb);
     cudaFree(e->fold);
@@ -465,36 +478,19 @@ int gsage_engine_set_weights(gsage_engine* e, const gsage_weights* w, void* stre
     return GSAGE_OK;
 }
 
-int gsage_engine_forward(gsage_engine* e, gsage_graph* g, gsage_rng* rng, const int64_t* ids_dev, int64_t B,
-                         float* logits_dev, void* stream) {
-    return gsage_engine_forward_sharded(e, g, rng, ids_dev, B, B, 0, logits_dev, stream);
-}
-
-int gsage_engine_forward_sharded(gsage_engine* e, gsage_graph* g, gsage_rng* rng, const int64_t* ids_dev, int64_t B,
-                                 int64_t global_B, int64_t first, float* logits_dev, void* stream) {
-    GS_CHECK_ARG(e && g && rng && ids_dev && logits_dev, "engine_forward: NULL argument");
-    GS_CHECK_ARG(global_B >= B && first >= 0 && first + B <= global_B, "engine_forward_sharded: slice [%lld, %lld) outside the global batch of %lld",
-                 (long long)first, (long long)(first + B), (long long)global_B);
-    GS_CHECK_ARG(e->have_weights, "engine_forward: call gsage_engine_set_weights first");
-    GS_CHECK_ARG(B > 0 && B <= e->maxB, "engine_forward: batch %lld outside (0, max_batch=%lld]", (long long)B, (long long)e->maxB);
-    GS_CHECK_ARG(g->n_cols >= 1 && g->n_cols <= 0xFFFFFFFFLL, "engine_forward: adjacency width out of range");
-    cudaStream_t s = as_stream(stream);
-    const gsage_engine_config& c = e->cfg;
-    const int S1 = c.fanout[0], S2 = c.fanout[1], T = e->T;
+// ---- sample: hop 0 draws first, then hop 1 (models.py:78-79), into `ids` = [ids0 | ids1 | ids2] -----------------
+static int sample_hops(gsage_engine* e, gsage_graph* g, gsage_rng* rng, int64_t* ids, uint32_t* sel, const int64_t* ids_src,
+                       bool src_host, int64_t B, int64_t global_B, int64_t first, cudaStream_t s) {
+    const int S1 = e->cfg.fanout[0], S2 = e->cfg.fanout[1];
     const int64_t n0 = B, n1 = B * S1, n2 = n1 * S2;
-    const int64_t es = (int64_t)dtype_size(T);
-    e->B = B;
-
-    const int p_all = e->prof.begin(GSAGE_PROF_FORWARD, s);
     const int p_smp = e->prof.begin(GSAGE_PROF_SAMPLE, s);
-    // ---- sample: hop 0 draws first, then hop 1 (models.py:78-79) ------------------------------------
-    int64_t* ids0 = e->ids; int64_t* ids1 = ids0 + n0; int64_t* ids2 = ids1 + n1;
-    if (ids_dev != ids0) GS_CUDA(cudaMemcpyAsync(ids0, ids_dev, 8 * n0, cudaMemcpyDeviceToDevice, s));
+    int64_t* ids0 = ids; int64_t* ids1 = ids0 + n0; int64_t* ids2 = ids1 + n1;
+    if (ids_src != ids0) GS_CUDA(cudaMemcpyAsync(ids0, ids_src, 8 * n0, src_host ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, s));
     if (global_B == B) {
-        GS_TRY(rng_randint_internal(rng, (uint32_t)g->n_cols, n1, e->sel, s));
-        GS_TRY(sample_sparse_launch(g, ids0, n0, S1, e->sel, ids1, s));
-        GS_TRY(rng_randint_internal(rng, (uint32_t)g->n_cols, n2, e->sel, s));
-        GS_TRY(sample_sparse_launch(g, ids1, n1, S2, e->sel, ids2, s));
+        GS_TRY(rng_randint_internal(rng, (uint32_t)g->n_cols, n1, sel, s));
+        GS_TRY(sample_sparse_launch(g, ids0, n0, S1, sel, ids1, s));
+        GS_TRY(rng_randint_internal(rng, (uint32_t)g->n_cols, n2, sel, s));
+        GS_TRY(sample_sparse_launch(g, ids1, n1, S2, sel, ids2, s));
     } else {
         // seed-sharded, still bit-exact with the single-process run: every rank consumes the draws of the WHOLE
         // global batch (hop-0 block, then hop-1 block -- the cheap part) and uses the slice that belongs to its seeds;
@@ -510,6 +506,99 @@ int gsage_engine_forward_sharded(gsage_engine* e, gsage_graph* g, gsage_rng* rng
         GS_TRY(st);
     }
     e->prof.end(p_smp, s);
+    return GSAGE_OK;
+}
+
+// the id slot in use has been read by everything queued on `s` so far (sample-ahead may recycle it after this point)
+static int mark_slot_done(gsage_engine* e, cudaStream_t s) {
+    if (!e->ev_done[e->cur]) GS_CUDA(cudaEventCreateWithFlags(&e->ev_done[e->cur], cudaEventDisableTiming));
+    GS_CUDA(cudaEventRecord(e->ev_done[e->cur], s));
+    e->done_valid[e->cur] = true;
+    return GSAGE_OK;
+}
+
+static int check_batch_args(gsage_engine* e, gsage_graph* g, gsage_rng* rng, const void* ids, int64_t B, int64_t global_B, int64_t first) {
+    GS_CHECK_ARG(e && g && rng && ids, "engine_forward: NULL argument");
+    GS_CHECK_ARG(global_B >= B && first >= 0 && first + B <= global_B, "engine_forward_sharded: slice [%lld, %lld) outside the global batch of %lld",
+                 (long long)first, (long long)(first + B), (long long)global_B);
+    GS_CHECK_ARG(B > 0 && B <= e->maxB, "engine_forward: batch %lld outside (0, max_batch=%lld]", (long long)B, (long long)e->maxB);
+    GS_CHECK_ARG(g->n_cols >= 1 && g->n_cols <= 0xFFFFFFFFLL, "engine_forward: adjacency width out of range");
+    return GSAGE_OK;
+}
+
+static int sample_ahead_impl(gsage_engine* e, gsage_graph* g, gsage_rng* rng, const int64_t* ids_src, bool src_host, int64_t B,
+                             int64_t global_B, int64_t first, cudaStream_t main) {
+    GS_TRY(check_batch_args(e, g, rng, ids_src, B, global_B, first));
+    GS_CHECK_ARG(!e->ahead.valid, "engine_sample_ahead: a sampled-ahead batch is already pending (run its forward first)");
+    if (!e->ss) {
+        int lo = 0, hi = 0;
+        GS_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));          // hi = numerically lowest = greatest priority
+        GS_CUDA(cudaStreamCreateWithPriority(&e->ss, cudaStreamNonBlocking, hi));
+        GS_CUDA(cudaEventCreateWithFlags(&e->ev_ahead, cudaEventDisableTiming));
+    }
+    // the spare slot was last read by the forward (and backward) BEFORE the one in flight: wait for that one only, so
+    // the draws run underneath the forward that was queued just before this call
+    (void)main;
+    if (e->done_valid[e->cur ^ 1]) GS_CUDA(cudaStreamWaitEvent(e->ss, e->ev_done[e->cur ^ 1], 0));
+    GS_TRY(sample_hops(e, g, rng, e->ids_slot[e->cur ^ 1], e->sel_ahead, ids_src, src_host, B, global_B, first, e->ss));
+    GS_CUDA(cudaEventRecord(e->ev_ahead, e->ss));
+    e->ahead.valid = true; e->ahead.src = ids_src; e->ahead.B = B; e->ahead.global_B = global_B; e->ahead.first = first;
+    e->ahead.g = g; e->ahead.rng = rng;
+    return GSAGE_OK;
+}
+
+int gsage_engine_sample_ahead(gsage_engine* e, gsage_graph* g, gsage_rng* rng, const int64_t* ids_dev, int64_t B,
+                              int64_t global_B, int64_t first, void* stream) {
+    return sample_ahead_impl(e, g, rng, ids_dev, false, B, global_B, first, as_stream(stream));
+}
+
+int gsage_engine_sample_ahead_host(gsage_engine* e, gsage_graph* g, gsage_rng* rng, const int64_t* ids_host, int64_t B,
+                                   void* stream) {
+    return sample_ahead_impl(e, g, rng, ids_host, true, B, B, 0, as_stream(stream));
+}
+
+int gsage_engine_sample_ahead_pending(const gsage_engine* e) { return (e && e->ahead.valid) ? 1 : 0; }
+
+static int forward_impl(gsage_engine* e, gsage_graph* g, gsage_rng* rng, const int64_t* ids_src, bool src_host, int64_t B,
+                        int64_t global_B, int64_t first, float* logits_dev, cudaStream_t s);
+
+int gsage_engine_forward(gsage_engine* e, gsage_graph* g, gsage_rng* rng, const int64_t* ids_dev, int64_t B,
+                         float* logits_dev, void* stream) {
+    return forward_impl(e, g, rng, ids_dev, false, B, B, 0, logits_dev, as_stream(stream));
+}
+
+int gsage_engine_forward_sharded(gsage_engine* e, gsage_graph* g, gsage_rng* rng, const int64_t* ids_dev, int64_t B,
+                                 int64_t global_B, int64_t first, float* logits_dev, void* stream) {
+    return forward_impl(e, g, rng, ids_dev, false, B, global_B, first, logits_dev, as_stream(stream));
+}
+
+static int forward_impl(gsage_engine* e, gsage_graph* g, gsage_rng* rng, const int64_t* ids_src, bool src_host, int64_t B,
+                        int64_t global_B, int64_t first, float* logits_dev, cudaStream_t s) {
+    GS_TRY(check_batch_args(e, g, rng, ids_src, B, global_B, first));
+    GS_CHECK_ARG(logits_dev, "engine_forward: NULL argument");
+    GS_CHECK_ARG(e->have_weights, "engine_forward: call gsage_engine_set_weights first");
+    const gsage_engine_config& c = e->cfg;
+    const int S1 = c.fanout[0], S2 = c.fanout[1], T = e->T;
+    const int64_t n0 = B, n1 = B * S1, n2 = n1 * S2;
+    const int64_t es = (int64_t)dtype_size(T);
+
+    const int p_all = e->prof.begin(GSAGE_PROF_FORWARD, s);
+    if (e->ahead.valid) {
+        // this batch was sampled ahead: same draws, same order on the RNG stream -- only wait for the sampler stream
+        GS_CHECK_ARG(e->ahead.src == ids_src && e->ahead.B == B && e->ahead.global_B == global_B && e->ahead.first == first &&
+                     e->ahead.g == g && e->ahead.rng == rng,
+                     "engine_forward: a different batch was sampled ahead (its draws are already consumed): run the forward of "
+                     "that batch (same ids pointer, batch size, graph and rng) first");
+        GS_CUDA(cudaStreamWaitEvent(s, e->ev_ahead, 0));
+        e->cur ^= 1;
+        e->ids = e->ids_slot[e->cur];
+        e->ahead.valid = false;
+    } else {
+        GS_TRY(sample_hops(e, g, rng, e->ids, e->sel, ids_src, src_host, B, global_B, first, s));
+    }
+    e->B = B;
+    int64_t* ids0 = e->ids; int64_t* ids1 = ids0 + n0;
+    (void)n2; (void)S2;
 
     // ---- prep (models.py:76-81) ------------------------------------------------------------------------
     RowSrc lvl;       // all three hops, hop k starts `offset_k` rows in
@@ -572,19 +661,21 @@ int gsage_engine_forward_sharded(gsage_engine* e, gsage_graph* g, gsage_rng* rng
     GS_TRY(linear_call(zn, f32w(e->w.fc_w, 2 * O2), c.n_classes, e->w.fc_b, n0, GSAGE_ACT_NONE, logits_dev, GSAGE_F32, c.n_classes,
                        0, 1, s));
     e->prof.end(p_all, s);
+    GS_TRY(mark_slot_done(e, s));
     return GSAGE_OK;
 }
 
-int gsage_engine_forward_host(gsage_engine* e, gsage_graph* g, gsage_rng* rng, const int64_t* ids_host, int64_t B,
-                              float* logits_host, void* stream) {
+int gsage_engine_forward_host_next(gsage_engine* e, gsage_graph* g, gsage_rng* rng, const int64_t* ids_host, int64_t B,
+                                   const int64_t* next_ids_host, int64_t next_B, float* logits_host, void* stream) {
     GS_CHECK_ARG(e && ids_host && logits_host, "engine_forward_host: NULL argument");
     GS_CHECK_ARG(B > 0 && B <= e->maxB, "engine_forward_host: batch outside (0, max_batch]");
     cudaStream_t s = as_stream(stream);
-    // the seed ids go straight into the hop-0 slot of the id buffer; the logits come back from a dedicated view
-    int64_t* ids_stage = e->ids;
+    // the seed ids go straight into the hop-0 slot of the id buffer (H2D inside sample_hops, or already done by
+    // gsage_engine_sample_ahead_host); the logits come back from a dedicated view
     float* logits_dev = e->LG;
-    GS_CUDA(cudaMemcpyAsync(ids_stage, ids_host, 8 * B, cudaMemcpyHostToDevice, s));
-    int st = gsage_engine_forward(e, g, rng, ids_stage, B, logits_dev, stream);
+    int st = forward_impl(e, g, rng, ids_host, true, B, B, 0, logits_dev, s);
+    // the next batch's H2D + sampling are queued BEFORE this call blocks on its own result: they overlap the forward
+    if (st == GSAGE_OK && next_ids_host) st = sample_ahead_impl(e, g, rng, next_ids_host, true, next_B, next_B, 0, s);
     if (st == GSAGE_OK) {
         if (cudaMemcpyAsync(logits_host, logits_dev, 4 * B * e->cfg.n_classes, cudaMemcpyDeviceToHost, s) != cudaSuccess ||
             cudaStreamSynchronize(s) != cudaSuccess) {
@@ -595,6 +686,11 @@ int gsage_engine_forward_host(gsage_engine* e, gsage_graph* g, gsage_rng* rng, c
     if (st == GSAGE_OK) st = gsage_rng_check(rng, stream);
     if (st == GSAGE_OK) st = gsage_graph_check(g, stream);
     return st;
+}
+
+int gsage_engine_forward_host(gsage_engine* e, gsage_graph* g, gsage_rng* rng, const int64_t* ids_host, int64_t B,
+                              float* logits_host, void* stream) {
+    return gsage_engine_forward_host_next(e, g, rng, ids_host, B, nullptr, 0, logits_host, stream);
 }
 
 static int backward_supported(gsage_engine* e) {
@@ -627,7 +723,8 @@ int gsage_engine_backward_head(gsage_engine* e, const float* dlogits, const gsag
     GS_TRY(linear_trans_call(e->DZ, 2 * O2, O2, e->w.layer[1].fc_x, 2 * O1, 2 * O1, n0, e->DH0, 2 * O1, s));
     GS_TRY(linear_trans_call(e->DZ + O2, 2 * O2, O2, e->w.layer[1].fc_neib, 2 * O1, 2 * O1, n0, e->DM2, 2 * O1, s));
     // mean over S1 children + concat + layer-1 activation, backwards
-    return layer1_grad_launch(e->DH0, e->DM2, e->H1, e->T, e->ld_h1, n0, n1, S1, 2 * O1, c.act[0], e->DH, s);
+    GS_TRY(layer1_grad_launch(e->DH0, e->DM2, e->H1, e->T, e->ld_h1, n0, n1, S1, 2 * O1, c.act[0], e->DH, s));
+    return mark_slot_done(e, s);
 }
 
 int gsage_engine_backward_layer1(gsage_engine* e, const gsage_grads* g, void* stream) {
@@ -639,7 +736,8 @@ int gsage_engine_backward_layer1(gsage_engine* e, const gsage_grads* g, void* st
     const int O1 = c.out_dim[0], d = c.feats_dim;
     // h = act([table[ids01] Wx1^T | M01 Wn1^T]): both weight gradients reduce over all n0 + n1 parent rows
     GS_TRY(wgrad_launch(e->DH, 2 * O1, O1, c.feats_dev, c.feats_dtype, c.feats_ld, e->ids, d, n0 + n1, g->fc_x[0], d, s));
-    return wgrad_launch(e->DH + O1, 2 * O1, O1, e->M, e->T, e->ld_m, nullptr, d, n0 + n1, g->fc_neib[0], d, s);
+    GS_TRY(wgrad_launch(e->DH + O1, 2 * O1, O1, e->M, e->T, e->ld_m, nullptr, d, n0 + n1, g->fc_neib[0], d, s));
+    return mark_slot_done(e, s);          // the weight gradients gather self rows by id: the slot is busy until here
 }
 
 int gsage_engine_peek(gsage_engine* e, int what, const void** ptr, int64_t* rows, int64_t* cols, int64_t* ld, int* dtype) {

@@ -24,6 +24,9 @@ int linear_simt_launch(const LinearParams& P, cudaStream_t s);
 // tcgen05 kernel (linear_umma.cu): bf16 operands, 16-byte aligned rows, O % 16 == 0, <= 256 accumulator columns
 bool linear_umma_eligible(const LinearParams& P);
 int linear_umma_launch(const LinearParams& P, cudaStream_t s);
+// weight-stationary tcgen05 kernel (linear_ws_umma.cu): same operands, W of a phase resident in shared memory (preferred when it fits)
+bool linear_ws_umma_eligible(const LinearParams& P);
+int linear_ws_umma_launch(const LinearParams& P, cudaStream_t s);
 // pool aggregators: MLP + pool over the S rows of a parent in one tcgen05 kernel (linear_pool_umma.cu, swap-AB)
 bool linear_pool_umma_eligible(const LinearParams& P);
 int linear_pool_umma_launch(const LinearParams& P, cudaStream_t s);

@@ -156,6 +156,7 @@ int linear_dispatch(const LinearParams& P, int exact, cudaStream_t s) {
         tc = linear_umma_eligible(one);
     }
     if (!tc) { GS_CHECK_ARG(P.pool_S <= 1, "linear: operands do not qualify for the tensor-core kernel (pooled epilogue)"); return linear_simt_launch(P, s); }
+    if (linear_ws_umma_eligible(P)) return linear_ws_umma_launch(P, s);      // weights stationary in smem: half the L2 -> SM bytes
     if (linear_umma_eligible(P)) return linear_umma_launch(P, s);
     for (int i = 0; i < P.n_segs; ++i) {
         const LinearSeg& g = P.seg[i];

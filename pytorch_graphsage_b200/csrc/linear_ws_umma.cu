@@ -1,0 +1,350 @@
+// linear_ws_umma.cu -- the dense W projection on tcgen05 with the WEIGHTS STATIONARY in shared memory.
+//
+// Same contract as linear_umma.cu (nn_modules.py:200,228,317: out[r, col0_s + o] = act(A_s[row_s(r)] . W_s[o] + bias_s[o])
+// for up to two segments s, the reference's concat-with-self), different data movement.  The streaming kernel
+// re-reads the W chunk of every (tile, k-chunk) stage from L2, so for the layer-1 shape (d = 602, O = 128) half of
+// the bytes an SM ingests are weights -- and the L2 -> SM fabric (~6.5 TB/s chip-wide, B300_MICROARCH.md "LTS
+// throughput cap") is what bounds that kernel, not HBM.  Here a CTA loads the W of a *phase* once
+// (kchunks x O x 128 B, 160 KB for layer 1) and keeps it for all of its row tiles; only A rows stream:
+//   phase = the segments whose weights fit in shared memory together (both for d <= 256; one at a time for
+//           d = 602: all row tiles with Wx, then all row tiles again with Wn -- each phase writes its own column
+//           range of the output, the activation is elementwise, so the result is identical)
+//   warps 0-3  epilogue   tcgen05.ld -> bias / activation -> bf16 | fp32 -> HBM
+//   warp  4    MMA issue  tcgen05.mma M=128, N=O, K=16 (bf16) | 8 (tf32); A from the stage ring, B from the resident W
+//   warp  5    TMA issue  W of the phase (one expect_tx for all of it), then per (tile, segment, k-chunk) one A stage:
+//                         cp.async.bulk.tensor.2d (in place) or 32 x tile::gather4 (rows by id)
+// Two TMEM accumulator buffers (2 x 256 columns): the epilogue of tile i overlaps the loads and MMAs of tile i+1.
+// Every mbarrier wait is bounded (a stuck pipeline traps instead of hanging the GPU).
+#include "linear.cuh"
+#include "umma_ptx.cuh"
+#include <string.h>
+#include <stdlib.h>
+
+namespace gsage {
+
+static constexpr int WM = 128;                 // rows per tile (UMMA M)
+static constexpr int kWsEpiWarps = 4;
+static constexpr int kWsThreads = 32 * (kWsEpiWarps + 2);
+static constexpr int kWsABytes = WM * 128;     // one A stage: 128 rows x 128 bytes
+static constexpr int kWsMaxStages = 8;
+static constexpr int kSmemLimit = 227 * 1024;
+
+struct WsSeg {
+    const void* a; int64_t lda; const int64_t* ids;
+    int d; int O; const float* bias; int64_t col0;
+    int kchunks;          // ceil(d / uk)
+    int acc_col;          // first TMEM column of this segment's accumulator inside a buffer
+    int w_off;            // byte offset of this segment's resident W inside the W area (kchunks slots of O x 128 B)
+};
+
+struct WsParams {
+    WsSeg seg[2];
+    int n_phases; int phase_first[2]; int phase_count[2];
+    int64_t n; int act;
+    void* out; int out_bf16; int64_t ld_out;
+    int n_tiles; int stages; int w_area;      // bytes reserved for the resident weights
+    int tf32; int uk;
+    int* err;
+};
+
+struct WsMaps { CUtensorMap w[2]; CUtensorMap a[2]; CUtensorMap g[2]; };
+
+template <int ACT>
+__device__ __forceinline__ void ws_store32(const uint32_t* r, const float* bias, int valid, void* out, int out_bf16) {
+    float v[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+    if (bias) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) if (j < valid) v[j] += __ldg(bias + j);
+    }
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+        if (ACT == GSAGE_ACT_RELU) v[j] = fmaxf(v[j], 0.0f);
+        if (ACT == GSAGE_ACT_TANH) v[j] = tanhf(v[j]);
+    }
+    const bool vec = valid == 32 && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
+    if (out_bf16) {
+        if (vec) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                reinterpret_cast<uint4*>(out)[q] = make_uint4(pack_bf16(v[8 * q], v[8 * q + 1]), pack_bf16(v[8 * q + 2], v[8 * q + 3]),
+                                                              pack_bf16(v[8 * q + 4], v[8 * q + 5]), pack_bf16(v[8 * q + 6], v[8 * q + 7]));
+        } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) if (j < valid) reinterpret_cast<__nv_bfloat16*>(out)[j] = __float2bfloat16_rn(v[j]);
+        }
+    } else {
+        if (vec) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+                reinterpret_cast<float4*>(out)[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+        } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) if (j < valid) reinterpret_cast<float*>(out)[j] = v[j];
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kWsThreads, 1) linear_ws_umma_kernel(const WsParams P, const __grid_constant__ WsMaps M) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    // carve: [resident W: w_area] [stages x A 16 KB] [barriers]
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint8_t* a_ring = smem + P.w_area;
+    uint64_t* bars = (uint64_t*)(a_ring + (size_t)P.stages * kWsABytes);
+    uint32_t* tmem_slot = (uint32_t*)(bars + 2 * kWsMaxStages + 6);
+    const uint32_t bar_base = smem_u32(bars);
+    auto full_bar = [&](int s) { return bar_base + 8u * s; };
+    auto empty_bar = [&](int s) { return bar_base + 8u * (kWsMaxStages + s); };
+    auto tfull_bar = [&](int b) { return bar_base + 8u * (2 * kWsMaxStages + b); };
+    auto tempty_bar = [&](int b) { return bar_base + 8u * (2 * kWsMaxStages + 2 + b); };
+    const uint32_t wfull_bar = bar_base + 8u * (2 * kWsMaxStages + 4);
+    const uint32_t wempty_bar = bar_base + 8u * (2 * kWsMaxStages + 5);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < P.stages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+        for (int b = 0; b < 2; ++b) { mbar_init(tfull_bar(b), 1); mbar_init(tempty_bar(b), 32 * kWsEpiWarps); }
+        mbar_init(wfull_bar, 1);
+        mbar_init(wempty_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == kWsEpiWarps) {                               // the MMA warp owns the TMEM allocation
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp < kWsEpiWarps) {
+        // =========================== EPILOGUE ===========================
+        const int row_in_tile = warp * 32 + lane;            // TMEM lane == tile row
+        int it = 0;
+        for (int ph = 0; ph < P.n_phases; ++ph) {
+            for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x, ++it) {
+                const int buf = it & 1;
+                mbar_wait(tfull_bar(buf), (it >> 1) & 1, P.err);
+                tc_fence_after();
+                const int64_t row = (int64_t)tile * WM + row_in_tile;
+                for (int si = 0; si < P.phase_count[ph]; ++si) {
+                    const WsSeg& sg = P.seg[P.phase_first[ph] + si];
+                    for (int c0 = 0; c0 < sg.O; c0 += 32) {
+                        uint32_t r[32];
+                        tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(buf * 256 + sg.acc_col + c0), r);
+                        tmem_ld_wait();
+                        if (row < P.n) {
+                            void* o = (char*)P.out + (row * P.ld_out + sg.col0 + c0) * (P.out_bf16 ? 2 : 4);
+                            const float* bias = sg.bias ? sg.bias + c0 : nullptr;
+                            const int valid = min(32, sg.O - c0);
+                            if (P.act == GSAGE_ACT_RELU) ws_store32<GSAGE_ACT_RELU>(r, bias, valid, o, P.out_bf16);
+                            else if (P.act == GSAGE_ACT_TANH) ws_store32<GSAGE_ACT_TANH>(r, bias, valid, o, P.out_bf16);
+                            else ws_store32<GSAGE_ACT_NONE>(r, bias, valid, o, P.out_bf16);
+                        }
+                    }
+                }
+                tc_fence_before();
+                mbar_arrive(tempty_bar(buf));
+            }
+        }
+    } else if (warp == kWsEpiWarps) {
+        // =========================== MMA ISSUER ===========================
+        int item = 0, it = 0;
+        const uint32_t fmt = P.tf32 ? 2u : 1u;              // a/b format: 1 = bf16, 2 = tf32
+        for (int ph = 0; ph < P.n_phases; ++ph) {
+            mbar_wait(wfull_bar, ph & 1, P.err);             // this phase's weights have landed
+            tc_fence_after();
+            for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x, ++it) {
+                const int buf = it & 1;
+                mbar_wait(tempty_bar(buf), ((it >> 1) & 1) ^ 1, P.err);     // first use of each buffer passes immediately
+                tc_fence_after();
+                for (int si = 0; si < P.phase_count[ph]; ++si) {
+                    const WsSeg& sg = P.seg[P.phase_first[ph] + si];
+                    // instruction descriptor: D = f32, A = B = bf16 | tf32, both K-major, N = O, M = 128
+                    const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(sg.O >> 3) << 17) | ((uint32_t)(WM >> 4) << 24);
+                    const uint32_t d_tmem = tmem_base + (uint32_t)(buf * 256 + sg.acc_col);
+                    const uint32_t w_base = smem_u32(smem + sg.w_off);
+                    const uint32_t w_slot = (uint32_t)sg.O * 128u;
+                    for (int kc = 0; kc < sg.kchunks; ++kc, ++item) {
+                        const int stage = item % P.stages;
+                        mbar_wait(full_bar(stage), (item / P.stages) & 1, P.err);
+                        tc_fence_after();
+                        if (lane == 0) {
+                            const uint64_t adesc = umma_desc(smem_u32(a_ring + (size_t)stage * kWsABytes));
+                            const uint64_t bdesc = umma_desc(w_base + (uint32_t)kc * w_slot);
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) {                // 4 x (K = 16 bf16 | 8 tf32): +32 bytes inside the swizzle atom
+                                if (P.tf32) umma_tf32(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kc | k) ? 1u : 0u);
+                                else umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kc | k) ? 1u : 0u);
+                            }
+                            umma_commit(empty_bar(stage));               // A slot reusable once these MMAs retire
+                        }
+                        __syncwarp();
+                    }
+                }
+                if (lane == 0) umma_commit(tfull_bar(buf));              // accumulators of this tile complete
+                __syncwarp();
+            }
+            if (lane == 0) umma_commit(wempty_bar);                      // every MMA that reads this phase's W has retired
+            __syncwarp();
+        }
+    } else {
+        // =========================== TMA ISSUER ===========================
+        int item = 0;
+        for (int ph = 0; ph < P.n_phases; ++ph) {
+            mbar_wait(wempty_bar, (ph & 1) ^ 1, P.err);      // phase 0 passes immediately; later phases wait for the MMAs
+            if (lane == 0) {
+                uint32_t total = 0;
+                for (int si = 0; si < P.phase_count[ph]; ++si) {
+                    const WsSeg& sg = P.seg[P.phase_first[ph] + si];
+                    total += (uint32_t)sg.kchunks * (uint32_t)sg.O * 128u;
+                }
+                mbar_arrive_expect_tx(wfull_bar, total);
+                for (int si = 0; si < P.phase_count[ph]; ++si) {
+                    const int sidx = P.phase_first[ph] + si;
+                    const WsSeg& sg = P.seg[sidx];
+                    const uint32_t w_base = smem_u32(smem + sg.w_off);
+                    for (int kc = 0; kc < sg.kchunks; ++kc)
+                        tma_load_2d(w_base + (uint32_t)kc * (uint32_t)sg.O * 128u, &M.w[sidx], kc * P.uk, 0, wfull_bar);
+                }
+            }
+            __syncwarp();
+            for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x) {
+                for (int si = 0; si < P.phase_count[ph]; ++si) {
+                    const int sidx = P.phase_first[ph] + si;
+                    const WsSeg& sg = P.seg[sidx];
+                    int r0 = 0, r1 = 0, r2 = 0, r3 = 0;            // lane l gathers tile rows 4l .. 4l+3 by id
+                    if (sg.ids) {
+                        const int64_t base = (int64_t)tile * WM + 4 * lane;
+                        if (base + 0 < P.n) r0 = (int)__ldg(sg.ids + base + 0);
+                        if (base + 1 < P.n) r1 = (int)__ldg(sg.ids + base + 1);
+                        if (base + 2 < P.n) r2 = (int)__ldg(sg.ids + base + 2);
+                        if (base + 3 < P.n) r3 = (int)__ldg(sg.ids + base + 3);
+                    }
+                    for (int kc = 0; kc < sg.kchunks; ++kc, ++item) {
+                        const int stage = item % P.stages;
+                        mbar_wait(empty_bar(stage), ((item / P.stages) & 1) ^ 1, P.err);
+                        const uint32_t sa_u = smem_u32(a_ring + (size_t)stage * kWsABytes);
+                        if (lane == 0) {
+                            mbar_arrive_expect_tx(full_bar(stage), (uint32_t)kWsABytes);
+                            if (!sg.ids) tma_load_2d(sa_u, &M.a[sidx], kc * P.uk, tile * WM, full_bar(stage));
+                        }
+                        __syncwarp();                              // expect_tx is posted before any lane's copy can complete
+                        if (sg.ids) tma_gather4(sa_u + lane * 512, &M.g[sidx], kc * P.uk, r0, r1, r2, r3, full_bar(stage));
+                    }
+                }
+            }
+        }
+    }
+
+    // teardown: everyone done with TMEM before it is freed
+    tc_fence_before();
+    __syncthreads();
+    if (warp == kWsEpiWarps) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    }
+}
+
+// ---- host -------------------------------------------------------------------------------------------------
+static bool ws_aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+static int ws_w_bytes(const LinearSeg& s) {
+    const int es = s.a_dtype == GSAGE_BF16 ? 2 : 4, uk = 128 / es;
+    return (s.d + uk - 1) / uk * s.O * 128;
+}
+
+// plan the phases: both segments resident together when they fit next to >= 4 A stages, else one segment per phase
+static bool ws_plan(const LinearParams& P, int* n_phases, int* w_area, int* stages) {
+    const int fixed = 1024 /*align slack*/ + 512 /*barriers*/;
+    int total = 0, widest = 0, cols = 0;
+    for (int i = 0; i < P.n_segs; ++i) {
+        const int wb = ws_w_bytes(P.seg[i]);
+        total += wb; widest = wb > widest ? wb : widest;
+        cols += (P.seg[i].O + 31) / 32 * 32;
+    }
+    int area, phases;
+    if (cols <= 256 && total + 4 * kWsABytes + fixed <= kSmemLimit) { area = total; phases = 1; }
+    else { area = widest; phases = P.n_segs; }
+    int st = (kSmemLimit - fixed - area) / kWsABytes;
+    if (st > kWsMaxStages) st = kWsMaxStages;
+    if (st < 3) return false;
+    *n_phases = phases; *w_area = area; *stages = st;
+    return true;
+}
+
+bool linear_ws_umma_eligible(const LinearParams& P) {
+    if (P.n < 1 || P.pool_S > 1 || P.n_segs < 1 || P.n_segs > 2) return false;
+    if (getenv("GSAGE_NO_WS")) return false;
+    for (int i = 0; i < P.n_segs; ++i) {
+        const LinearSeg& s = P.seg[i];
+        if (s.a_dtype != P.seg[0].a_dtype || s.w_dtype != s.a_dtype) return false;         // all bf16, or all fp32 (run as TF32)
+        if (s.S > 1 || s.w_trans) return false;
+        if (s.O % 16 != 0 || s.O < 16 || s.O > 256) return false;
+        const int es = s.a_dtype == GSAGE_BF16 ? 2 : 4, per = 16 / es;
+        if (!ws_aligned16(s.a) || !ws_aligned16(s.w) || (s.lda * es) % 16 != 0 || (s.ldw * es) % 16 != 0) return false;
+        if (s.lda < (s.d + per - 1) / per * per || s.ldw < (s.d + per - 1) / per * per) return false;   // whole 16-byte chunks readable
+    }
+    int ph, area, st;
+    return ws_plan(P, &ph, &area, &st);
+}
+
+static int* g_ws_err = nullptr;
+
+int linear_ws_umma_launch(const LinearParams& P, cudaStream_t s) {
+    WsParams U;
+    memset(&U, 0, sizeof(U));
+    U.tf32 = P.seg[0].a_dtype == GSAGE_F32 ? 1 : 0;
+    U.uk = U.tf32 ? 32 : 64;
+    int n_phases = 0, w_area = 0, stages = 0;
+    GS_CHECK_ARG(ws_plan(P, &n_phases, &w_area, &stages), "linear_ws_umma: weights do not fit in shared memory");
+    U.n_phases = n_phases; U.stages = stages;
+    U.w_area = (w_area + 1023) / 1024 * 1024;
+    for (int i = 0; i < P.n_segs; ++i) {
+        const LinearSeg& g = P.seg[i];
+        U.seg[i].a = g.a; U.seg[i].lda = g.lda; U.seg[i].ids = g.ids;
+        U.seg[i].d = g.d; U.seg[i].O = g.O; U.seg[i].bias = g.bias; U.seg[i].col0 = g.col0;
+        U.seg[i].kchunks = (g.d + U.uk - 1) / U.uk;
+    }
+    if (n_phases == 1) {
+        U.phase_first[0] = 0; U.phase_count[0] = P.n_segs;
+        int col = 0, off = 0;
+        for (int i = 0; i < P.n_segs; ++i) {
+            U.seg[i].acc_col = col; U.seg[i].w_off = off;
+            col += (P.seg[i].O + 31) / 32 * 32;
+            off += ws_w_bytes(P.seg[i]);
+        }
+    } else {
+        for (int i = 0; i < P.n_segs; ++i) { U.phase_first[i] = i; U.phase_count[i] = 1; U.seg[i].acc_col = 0; U.seg[i].w_off = 0; }
+    }
+    U.n = P.n; U.act = P.act; U.out = P.out; U.out_bf16 = P.out_dtype == GSAGE_BF16; U.ld_out = P.ld_out;
+    U.n_tiles = (int)ceil_div(P.n, WM);
+    if (!g_ws_err) {
+        GS_CUDA(cudaMalloc((void**)&g_ws_err, sizeof(int)));
+        GS_CUDA(cudaMemset(g_ws_err, 0, sizeof(int)));
+    }
+    U.err = g_ws_err;
+    const size_t smem = (size_t)U.w_area + (size_t)U.stages * kWsABytes + 1024 /*align slack*/ + 512 /*barriers*/;
+    GS_CHECK_ARG(smem <= (size_t)kSmemLimit, "linear_ws_umma: %zu bytes of shared memory needed", smem);
+    static bool attr_set = false;
+    if (!attr_set) {
+        GS_CUDA(cudaFuncSetAttribute(linear_ws_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
+        attr_set = true;
+    }
+    const int grid = U.n_tiles < sm_count() ? U.n_tiles : sm_count();
+    WsMaps maps;
+    memset(&maps, 0, sizeof(maps));
+    const int es = U.tf32 ? 4 : 2;
+    for (int i = 0; i < P.n_segs; ++i) {
+        const LinearSeg& g = P.seg[i];
+        GS_TRY(make_map(&maps.w[i], g.w, g.O, g.d, g.ldw, g.O, es));
+        if (!g.ids) GS_TRY(make_map(&maps.a[i], g.a, P.n, g.d, g.lda, WM, es));
+        else GS_TRY(make_map(&maps.g[i], g.a, 0x7FFFFFFF, g.d, g.lda, 1, es));       // rows by id: no row bound known here
+    }
+    linear_ws_umma_kernel<<<grid, kWsThreads, smem, s>>>(U, maps);
+    GS_LAUNCHED();
+    return GSAGE_OK;
+}
+
+}  // namespace gsage

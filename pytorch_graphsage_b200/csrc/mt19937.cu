@@ -433,9 +433,20 @@ static int64_t window_for(int64_t count, double p) {
     return (int64_t)(mean + 12.0 * sd + 64.0);
 }
 
+int rng_enter(gsage_rng* r, cudaStream_t s) {
+    if (r->have_last && r->last_stream != s) {
+        GS_CUDA(cudaEventRecord(r->ev_switch, r->last_stream));
+        GS_CUDA(cudaStreamWaitEvent(s, r->ev_switch, 0));
+    }
+    r->last_stream = s;
+    r->have_last = true;
+    return GSAGE_OK;
+}
+
 static int rng_draw(gsage_rng* r, uint32_t hi, int64_t count, uint32_t* out, cudaStream_t s) {
     const uint32_t rng_max = hi - 1u;
     if (count == 0) return GSAGE_OK;
+    GS_TRY(rng_enter(r, s));
     if (rng_max == 0) {                       // numpy: rng == 0 -> zeros, no word consumed
         GS_CUDA(cudaMemsetAsync(out, 0, sizeof(uint32_t) * count, s));
         return GSAGE_OK;
@@ -509,9 +520,12 @@ int gsage_rng_create(gsage_rng** out) {
         gsage_rng_destroy(r);
         return GSAGE_ERR_NOMEM;
     }
-    if (cudaStreamCreateWithFlags(&r->side, cudaStreamNonBlocking) != cudaSuccess ||
+    int prio_lo = 0, prio_hi = 0;                               // refills are tiny next to the gather kernels they overlap:
+    cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);       // highest priority, so their CTAs are placed as slots free up
+    if (cudaStreamCreateWithPriority(&r->side, cudaStreamNonBlocking, prio_hi) != cudaSuccess ||
         cudaEventCreateWithFlags(&r->ev_main, cudaEventDisableTiming) != cudaSuccess ||
-        cudaEventCreateWithFlags(&r->ev_refill, cudaEventDisableTiming) != cudaSuccess) {
+        cudaEventCreateWithFlags(&r->ev_refill, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&r->ev_switch, cudaEventDisableTiming) != cudaSuccess) {
         set_error("rng_create: stream / event creation failed");
         gsage_rng_destroy(r);
         return GSAGE_ERR_CUDA;
@@ -527,6 +541,7 @@ void gsage_rng_destroy(gsage_rng* r) {
     if (r->side) { cudaStreamSynchronize(r->side); cudaStreamDestroy(r->side); }
     if (r->ev_main) cudaEventDestroy(r->ev_main);
     if (r->ev_refill) cudaEventDestroy(r->ev_refill);
+    if (r->ev_switch) cudaEventDestroy(r->ev_switch);
     delete r;
 }
 
@@ -535,7 +550,9 @@ int gsage_rng_set_state(gsage_rng* r, const uint32_t* key, int pos, void* stream
     cudaStream_t s = as_stream(stream);
     // the given key becomes stream block 0; earlier launches (either stream) may still touch the ring
     GS_CUDA(cudaStreamSynchronize(r->side));
+    if (r->have_last && r->last_stream != s) GS_CUDA(cudaStreamSynchronize(r->last_stream));
     GS_CUDA(cudaStreamSynchronize(s));
+    r->last_stream = s; r->have_last = true;
     GS_CUDA(cudaMemcpyAsync(r->ring, key, sizeof(uint32_t) * kN, cudaMemcpyHostToDevice, s));
     const int64_t c[2] = {pos, pos};
     GS_CUDA(cudaMemcpyAsync(r->cursor, c, sizeof(c), cudaMemcpyHostToDevice, s));
@@ -560,6 +577,7 @@ int gsage_rng_seed(gsage_rng* r, uint32_t seed, void* stream) {
 int gsage_rng_get_state(gsage_rng* r, uint32_t* key, int* pos, void* stream) {
     GS_CHECK_ARG(r && key && pos, "rng_get_state: NULL argument");
     cudaStream_t s = as_stream(stream);
+    GS_TRY(rng_enter(r, s));
     GS_TRY(gsage_rng_check(r, stream));
     GS_TRY(rng_resync(r, s));
     const int64_t c = r->cursor_lb;
@@ -578,6 +596,7 @@ int gsage_rng_get_state(gsage_rng* r, uint32_t* key, int* pos, void* stream) {
 int gsage_rng_raw(gsage_rng* r, int64_t count, uint32_t* out_dev, void* stream) {
     GS_CHECK_ARG(r && count >= 0 && (out_dev || count == 0), "rng_raw: bad arguments");
     cudaStream_t s = as_stream(stream);
+    GS_TRY(rng_enter(r, s));
     const int64_t max_piece = r->cap / 4;
     for (int64_t done = 0; done < count; done += max_piece) {
         const int64_t n = std::min(max_piece, count - done);
@@ -602,6 +621,7 @@ int gsage_rng_permutation(gsage_rng* r, int64_t n, int64_t* out_dev, void* strea
     GS_CHECK_ARG(r && n >= 0 && (out_dev || n == 0), "rng_permutation: bad arguments");
     if (n == 0) return GSAGE_OK;
     cudaStream_t s = as_stream(stream);
+    GS_TRY(rng_enter(r, s));
     // every step needs < 2 words on average; 2n + 12 sigma + slack bounds the walk
     const int64_t window = std::min<int64_t>(2 * n + (int64_t)(12.0 * sqrt(2.0 * (double)n)) + 256, r->cap / 2);
     GS_TRY(rng_ensure(r, r->cursor_ub + window, s));
@@ -616,7 +636,7 @@ int gsage_rng_permutation(gsage_rng* r, int64_t n, int64_t* out_dev, void* strea
 
 int gsage_rng_check(gsage_rng* r, void* stream) {
     GS_CHECK_ARG(r, "rng_check: NULL rng");
-    int flag = 0;
+    int flag = 0;                       // sticky flag: reading it needs no ordering against the other consumer stream
     GS_CUDA(cudaMemcpyAsync(&flag, r->err_flag, sizeof(int), cudaMemcpyDeviceToHost, as_stream(stream)));
     GS_CUDA(cudaStreamSynchronize(as_stream(stream)));
     if (flag) {
@@ -629,6 +649,7 @@ int gsage_rng_check(gsage_rng* r, void* stream) {
 
 int gsage_rng_consumed(gsage_rng* r, int64_t* words, void* stream) {
     GS_CHECK_ARG(r && words, "rng_consumed: NULL argument");
+    GS_TRY(rng_enter(r, as_stream(stream)));
     GS_TRY(rng_resync(r, as_stream(stream)));
     *words = r->cursor_lb - r->origin;
     return GSAGE_OK;

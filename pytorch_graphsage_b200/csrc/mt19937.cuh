@@ -27,9 +27,15 @@ struct gsage_rng {
     bool lanes_ready = false;
     uint32_t* polys = nullptr;     // device, (lanes-1) x 624 words: t^(l*lane_blocks*624) mod phi
     uint32_t* partial = nullptr;   // device, (lanes-1) x 8 x 624 words
+    // consumers may alternate between streams (the engine's sample-ahead stream and the caller's): the first draw on a
+    // new stream is ordered after everything queued on the previous one, so the stream of draws stays one sequence
+    cudaStream_t last_stream = nullptr; bool have_last = false;
+    cudaEvent_t ev_switch = nullptr;
 };
 
 namespace gsage {
 // bounded draws into a device buffer (gsage_rng_randint without the argument checks)
 int rng_randint_internal(gsage_rng* r, uint32_t hi, int64_t count, uint32_t* out, cudaStream_t s);
+// order stream `s` after the stream that drew from `r` last (no-op when it is the same stream)
+int rng_enter(gsage_rng* r, cudaStream_t s);
 }

@@ -187,17 +187,43 @@ class GSSupervised(nn.Module):
         self._last = eng
         return out
 
-    def forward_host(self, ids_host, feats, logits_host, train=True):
-        """End-to-end entry for host buffers (pinned numpy / torch CPU tensors): H2D ids, forward, D2H logits."""
+    def sample_ahead(self, ids, feats, train=True, shard=None, host=False):
+        """Draw and sample both hops of the NEXT batch now, on the engine's own stream, so that it overlaps the
+        aggregation of the batch whose forward is queued right after this call (gsage_engine_sample_ahead).  The next
+        `forward` / `forward_host` must be given the same `ids` tensor.  Draw order on the RNG stream = call order, so
+        the sampled ids are bit-identical with and without it."""
+        sampler = self.train_sampler if train else self.val_sampler
+        fanout = [s['n_train_samples' if train else 'n_val_samples'] for s in self.layer_specs]
+        if not host:
+            ids = torch.as_tensor(ids).to(device='cuda', dtype=torch.int64).contiguous().view(-1)
+        table = self._table(feats)
+        eng = self._engine(table, fanout, ids.shape[0])
+        rng = sampler.rng or self.rng or default_rng()
+        B = ids.shape[0]
+        if host:
+            check(lib().gsage_engine_sample_ahead_host(eng['h'], sampler.graph._h, rng._h, C.c_void_p(ids.data_ptr()), B, ops.stream()))
+        else:
+            gB, first = (B, 0) if shard is None else (int(shard[0]), int(shard[1]))
+            check(lib().gsage_engine_sample_ahead(eng['h'], sampler.graph._h, rng._h, ops.ptr(ids), B, gB, first, ops.stream()))
+        self._ahead_ids = ids                 # the copy runs later on the sampler stream: keep the source alive
+        return ids
+
+    def forward_host(self, ids_host, feats, logits_host, train=True, next_ids_host=None):
+        """End-to-end entry for host buffers (pinned numpy / torch CPU tensors): H2D ids, forward, D2H logits.
+        `next_ids_host`: the batch after this one -- its H2D copy and sampling are queued before this call blocks on
+        its own result (sample-ahead); the next call must then be given that same tensor."""
         sampler = self.train_sampler if train else self.val_sampler
         fanout = [s['n_train_samples' if train else 'n_val_samples'] for s in self.layer_specs]
         table = self._table(feats)
         B = ids_host.shape[0]
-        eng = self._engine(table, fanout, B)
+        eng = self._engine(table, fanout, max(B, next_ids_host.shape[0] if next_ids_host is not None else 0))
         self._push_weights(eng)
         rng = sampler.rng or self.rng or default_rng()
-        check(lib().gsage_engine_forward_host(eng['h'], sampler.graph._h, rng._h, C.c_void_p(ids_host.data_ptr()), B,
-                                              C.c_void_p(logits_host.data_ptr()), ops.stream()))
+        nxt = C.c_void_p(next_ids_host.data_ptr()) if next_ids_host is not None else None
+        check(lib().gsage_engine_forward_host_next(eng['h'], sampler.graph._h, rng._h, C.c_void_p(ids_host.data_ptr()), B,
+                                                   nxt, next_ids_host.shape[0] if next_ids_host is not None else 0,
+                                                   C.c_void_p(logits_host.data_ptr()), ops.stream()))
+        self._ahead_ids = next_ids_host
         self._last = eng
         return logits_host
 
@@ -237,10 +263,14 @@ class GSSupervised(nn.Module):
             main.wait_stream(overlap_stream)
         return bucket
 
-    def train_step(self, ids, feats, targets, loss_fn, optimizer=None, clip=5.0, grad_scale=1.0, overlap_stream=None, shard=None):
+    def train_step(self, ids, feats, targets, loss_fn, optimizer=None, clip=5.0, grad_scale=1.0, overlap_stream=None, shard=None,
+                   next_ids=None, next_shard=None):
         """models.py:97-104: forward, loss, backward, clip-norm 5, optimiser step.  The loss and the optimiser are
-        stock torch (out of scope); forward and parameter gradients run in the library."""
+        stock torch (out of scope); forward and parameter gradients run in the library.
+        `next_ids`: the next batch, sampled ahead underneath this step (the next call must be given the same tensor)."""
         preds = self(ids, feats, train=True, shard=shard, keep_activations=True)
+        if next_ids is not None:
+            self.sample_ahead(next_ids, feats, train=True, shard=next_shard)
         leaf = preds.detach().requires_grad_(True)
         loss = loss_fn(leaf, targets.squeeze())
         dlogits, = torch.autograd.grad(loss, leaf)

@@ -121,3 +121,64 @@ def test_engine_tf32_projection_mode(g):
     logits = model(torch.from_numpy(fix['ids0']), None)
     assert np.array_equal(model.peek('ids2').cpu().numpy(), fix['ids2'])
     np.testing.assert_allclose(logits.cpu().numpy(), fix['logits'], rtol=5e-3, atol=5e-3)
+
+
+def test_sample_ahead_is_bit_identical(g):
+    """gsage_engine_sample_ahead: batch i+1 is drawn on the engine's own stream while batch i aggregates.  Draw order on
+    the RNG stream = call order, so ids and logits equal the plain back-to-back run (and the oracle's)."""
+    fix = util.load('model_mean_identity')
+    feats = torch.from_numpy(fix['feats'])
+    batches = [torch.from_numpy(b).cuda() for b in (fix['ids0'], fix['ids0'][::-1].copy(), fix['ids0'][:7].copy(), fix['ids0'])]
+    plain = build_model(g, fix, 'mean', 'identity', True)
+    g.set_seeds(int(fix['seed']))
+    want = []
+    for b in batches:
+        out = plain(b, feats)
+        want.append((plain.peek('ids1').cpu().numpy(), plain.peek('ids2').cpu().numpy(), out.cpu().numpy()))
+    state_plain = g.default_rng().get_state()
+
+    model = build_model(g, fix, 'mean', 'identity', True)
+    g.set_seeds(int(fix['seed']))
+    model.sample_ahead(batches[0], feats)
+    for i, b in enumerate(batches):
+        if i + 1 < len(batches):
+            # queue the forward of batch i right after the sample-ahead of batch i+1 is requested?  No: the engine holds
+            # ONE pending batch, so the order is forward(i) [consumes the pending sample] then sample_ahead(i+1)
+            pass
+        out = model(b, feats)
+        ids1, ids2 = model.peek('ids1').cpu().numpy(), model.peek('ids2').cpu().numpy()
+        if i + 1 < len(batches):
+            model.sample_ahead(batches[i + 1], feats)
+        assert np.array_equal(ids1, want[i][0]) and np.array_equal(ids2, want[i][1])
+        np.testing.assert_array_equal(out.cpu().numpy(), want[i][2])
+    st = g.default_rng().get_state()
+    assert np.array_equal(st[1], state_plain[1]) and st[2] == state_plain[2]
+    # the first batch also equals the reference's golden trace
+    assert np.array_equal(want[0][1], fix['ids2'])
+
+
+def test_sample_ahead_rejects_a_different_batch(g):
+    fix = util.load('model_mean_identity')
+    feats = torch.from_numpy(fix['feats'])
+    model = build_model(g, fix, 'mean', 'identity', True)
+    a = torch.from_numpy(fix['ids0']).cuda()
+    b = torch.from_numpy(fix['ids0'][::-1].copy()).cuda()
+    g.set_seeds(1)
+    model.sample_ahead(a, feats)
+    with pytest.raises(ValueError):
+        model.sample_ahead(b, feats)            # one pending batch at a time
+    with pytest.raises(ValueError):
+        model(b, feats)                         # its draws are already consumed: the forward must name the same batch
+    model(a, feats)
+
+
+def test_sample_ahead_host_entry(g):
+    fix = util.load('model_mean_identity')
+    model = build_model(g, fix, 'mean', 'identity', True)
+    ids = torch.from_numpy(fix['ids0']).pin_memory()
+    out = torch.empty(fix['logits'].shape, dtype=torch.float32).pin_memory()
+    g.set_seeds(int(fix['seed']))
+    model.sample_ahead(ids, torch.from_numpy(fix['feats']), host=True)
+    model.forward_host(ids, torch.from_numpy(fix['feats']), out)
+    assert np.array_equal(model.peek('ids2').cpu().numpy(), fix['ids2'])
+    np.testing.assert_allclose(out.numpy(), fix['logits'], rtol=1e-4, atol=1e-5)

@@ -260,3 +260,28 @@ def test_umma_pooled_epilogue(g, n, S, d, H, reduce):
     want = h.max(dim=1)[0] if reduce == 'max' else h.mean(dim=1)
     got = g.ops.linear_pooled(pad(nb), pad(w), n, S, reduce, bias=b.cuda(), out_dtype=torch.bfloat16)
     np.testing.assert_allclose(got.float().cpu().numpy(), want.numpy(), rtol=1e-2, atol=1e-2)
+
+
+@pytest.mark.parametrize('n,d,O', [(777, 602, 128), (128 * 150 + 3, 64, 64), (50, 256, 128), (128 * 300 + 1, 602, 128), (3000, 256, 256)])
+def test_weight_stationary_kernel_equals_streaming_kernel(g, n, d, O, monkeypatch):
+    """linear_ws_umma.cu (W of a phase resident in shared memory; d=602 runs as two phases, one segment each) against
+    linear_umma.cu (W streamed with every stage): same MMAs in the same k order -> bit-identical fp32 results, and
+    both within 2e-4 of fp64 on the bf16 operands."""
+    gen = torch.Generator().manual_seed(n + d)
+    table = _bf16(torch.randn((n + 99, d), generator=gen))
+    m = _bf16(torch.randn((n, d), generator=gen))
+    wx, wn = _bf16(torch.randn((O, d), generator=gen) / d ** 0.5), _bf16(torch.randn((O, d), generator=gen) / d ** 0.5)
+    bx = torch.randn((O,), generator=gen)
+    ids = torch.randint(0, n + 99, (n,), generator=gen)
+    pad = lambda t: g.ops.pad_table(t.float(), torch.bfloat16)[0][:, :t.shape[1]]
+    segs = [dict(a=pad(table), ids=ids.cuda(), w=pad(wx), col0=0, bias=bx.cuda()), dict(a=pad(m), w=pad(wn), col0=O)]
+    want = torch.relu(torch.cat([table[ids].double() @ wx.double().t() + bx.double(), m.double() @ wn.double().t()], dim=1))
+    got_ws = g.ops.linear(segs, n, act='relu', out_dtype=torch.float32, exact=False)
+    monkeypatch.setenv('GSAGE_NO_WS', '1')
+    got_stream = g.ops.linear(segs, n, act='relu', out_dtype=torch.float32, exact=False)
+    monkeypatch.delenv('GSAGE_NO_WS')
+    np.testing.assert_allclose(got_ws.cpu().numpy(), want.numpy(), rtol=2e-4, atol=2e-4)
+    if 2 * O <= 256:                       # wider pairs are split differently by the streaming dispatcher
+        np.testing.assert_array_equal(got_ws.cpu().numpy(), got_stream.cpu().numpy())
+    out16 = g.ops.linear(segs, n, act='relu', out_dtype=torch.bfloat16, exact=False)
+    np.testing.assert_allclose(out16.float().cpu().numpy(), want.numpy(), rtol=1e-2, atol=1e-2)
