@@ -345,15 +345,26 @@ def run_ours(args):
     clk = clocks.stop()
     ms_total = max_over_ranks(ev0.elapsed_time(ev1))
     prof = model.profile_read()
-    model.profile(False)
     g.default_rng().check()
     ms_step = ms_total / args.steps
     value = WORLD * B * ROWS_PER_SEED / (ms_step / 1e3)
 
-    # ---- end to end through the host-buffer entry -----------------------------------------------------------------
+    # the dominant kernel alone: a few steps WITHOUT sample-ahead, so that no sampler kernel shares the SMs with it
+    # (in the pipelined run above its launches overlap the next batch's draws: the step gets shorter, the kernel longer)
+    prof_iso = None
     if ahead:
         model(dev_ids[step_no[0] % n_batches], table)                          # consume the batch the last timed step drew ahead
+        step_no[0] += 1
+        torch.cuda.synchronize()
+        model.profile_read()
+        for i in range(20):
+            model(dev_ids[(step_no[0] + i) % n_batches], table)
+        torch.cuda.synchronize()
+        prof_iso = model.profile_read()
+        step_no[0] += 20
+    model.profile(False)
 
+    # ---- end to end through the host-buffer entry -----------------------------------------------------------------
     def host_step(i):                                                          # synchronises every step (D2H of the logits)
         nxt = host_ids[(i + 1) % n_batches] if ahead else None
         model.forward_host(host_ids[i % n_batches], table, host_out, next_ids_host=nxt)
@@ -430,12 +441,19 @@ def run_ours(args):
                      'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': (achieved / peak if achieved else None),
                      'traffic': traffic, 'peak_source': peak_src, 'launches': int(red_n),
                      'algorithmic_bytes_per_launch_avg': (red_bytes / red_n if red_n else None),
-                     'avg_launch_ms': (red_ms / red_n if red_n else None)},
+                     'avg_launch_ms': (red_ms / red_n if red_n else None),
+                     'timed_in': 'the pipelined steps above (its launches share the SMs with the next batch\'s sampling kernels)' if ahead
+                                 else 'the timed steps above'},
         'breakdown_ms_per_step': {'forward': prof['forward'][0] / args.steps, 'sample': prof['sample'][0] / args.steps,
                                   'gather_reduce': red_ms / args.steps, 'project': prj_ms / args.steps,
                                   # fused build: the projection runs inside the gather+aggregate kernel (no time of its own)
                                   'project_tflops': (prj_flops / 1e12) / ((prj_ms if prj_ms > 0 else red_ms) / 1e3) if (prj_ms + red_ms) > 0 else None},
     }
+    if prof_iso is not None and prof_iso['reduce'][0] > 0:
+        ims, inn, iby = prof_iso['reduce']
+        line['roofline']['isolated'] = {'achieved': (iby / 1e9) / (ims / 1e3), 'frac': (iby / 1e9) / (ims / 1e3) / peak, 'launches': int(inn),
+                                        'avg_launch_ms': ims / inn,
+                                        'note': 'same kernel, same inputs, 20 steps without sample-ahead (nothing else on the SMs)'}
     if train is not None:
         line['train'] = train
     if not args.no_cpu_baseline:

@@ -274,6 +274,12 @@ typedef struct gsage_grads {
 int gsage_engine_backward_head(gsage_engine* e, const float* dlogits_dev, const gsage_grads* grads, void* stream);
 int gsage_engine_backward_layer1(gsage_engine* e, const gsage_grads* grads, void* stream);
 
+/* The weight gradient of one projection on its own: dW (O x d, fp32, overwritten) = G^T . A[ids] (ids NULL: A in place),
+ * G = the (n, O) output gradient.  exact != 0: fp32 FFMA kernel, fp32 G.  exact == 0: split-K tcgen05 kernel reading both
+ * row-major operands as MN-major tiles (bf16 G and A, O == 128, 16-byte aligned rows; GSAGE_ERR_INVALID otherwise). */
+int gsage_wgrad(const void* g_dev, int g_dtype, int64_t ldg, int O, const void* a_dev, int a_dtype, int64_t lda,
+                const int64_t* ids_dev, int d, int64_t n, float* dw_dev, int64_t lddw, int exact, void* stream);
+
 /* keep != 0: the next forwards keep every activation the backward pass needs (training).  0 (default): forward-only
  * streaming -- intermediates may be processed in L2-sized chunks that reuse their buffers. */
 int gsage_engine_keep_activations(gsage_engine* e, int keep);

@@ -95,6 +95,7 @@ _SIGNATURES = {
     'gsage_engine_workspace_bytes': (c_i64, [c_p]),
     'gsage_engine_backward_head': (C.c_int, [c_p, c_p, C.POINTER(Grads), c_p]),
     'gsage_engine_backward_layer1': (C.c_int, [c_p, C.POINTER(Grads), c_p]),
+    'gsage_wgrad': (C.c_int, [c_p, C.c_int, c_i64, C.c_int, c_p, C.c_int, c_i64, c_p, C.c_int, c_i64, c_p, c_i64, C.c_int, c_p]),
     'gsage_engine_keep_activations': (C.c_int, [c_p, C.c_int]),
     'gsage_engine_profile': (C.c_int, [c_p, C.c_int]),
     'gsage_engine_profile_read': (C.c_int, [c_p, C.POINTER(C.c_double), C.POINTER(c_i64), C.POINTER(C.c_double), c_p]),

@@ -106,7 +106,7 @@ __global__ void __launch_bounds__(256) l2_normalize_bwd_kernel(const float* __re
 // dH[r, c]: r < n0 -> dh0[r, c];  r >= n0 -> dm2[(r - n0) / S, c] / S;  times act'(H[r, c])
 __global__ void __launch_bounds__(256) layer1_grad_kernel(const float* __restrict__ dh0, const float* __restrict__ dm2,
                                                           const void* __restrict__ H, int h_dtype, int64_t ldh, int64_t n0,
-                                                          int64_t n1, int S, int width, int act, float* __restrict__ dH) {
+                                                          int64_t n1, int S, int width, int act, void* __restrict__ dH, int dh_bf16) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (n0 + n1) * width) return;
     const int64_t r = i / width;
@@ -115,7 +115,8 @@ __global__ void __launch_bounds__(256) layer1_grad_kernel(const float* __restric
     const float h = ld_any(H, h_dtype, r * ldh + c);
     if (act == GSAGE_ACT_RELU) g = h > 0.0f ? g : 0.0f;
     else if (act == GSAGE_ACT_TANH) g *= (1.0f - h * h);
-    dH[i] = g;
+    if (dh_bf16) reinterpret_cast<__nv_bfloat16*>(dH)[i] = __float2bfloat16_rn(g);     // operand of the tensor-core wgrad
+    else reinterpret_cast<float*>(dH)[i] = g;
 }
 
 __global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ x, int64_t n, int d, float* __restrict__ out) {
@@ -155,10 +156,11 @@ int l2_normalize_bwd_launch(const float* z, const float* dzn, int64_t n, int d, 
 }
 
 int layer1_grad_launch(const float* dh0, const float* dm2, const void* H, int h_dtype, int64_t ldh, int64_t n0, int64_t n1, int S,
-                       int width, int act, float* dH, cudaStream_t s) {
+                       int width, int act, void* dH, int dh_dtype, cudaStream_t s) {
     const int64_t total = (n0 + n1) * width;
     if (total == 0) return GSAGE_OK;
-    layer1_grad_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, s>>>(dh0, dm2, H, h_dtype, ldh, n0, n1, S, width, act, dH);
+    layer1_grad_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, s>>>(dh0, dm2, H, h_dtype, ldh, n0, n1, S, width, act, dH,
+                                                                     dh_dtype == GSAGE_BF16 ? 1 : 0);
     GS_LAUNCHED();
     return GSAGE_OK;
 }
@@ -170,3 +172,21 @@ int colsum_launch(const float* x, int64_t n, int d, float* out, cudaStream_t s) 
 }
 
 }  // namespace gsage
+
+using namespace gsage;
+
+// dW (O x d, fp32) = G^T . A[ids]  -- the weight gradient of a Linear whose input rows are A[ids] (or A in place) and
+// whose output gradient is G.  exact != 0: fp32 FFMA kernel (G must be fp32).  exact == 0: tcgen05 kernel when the
+// operands qualify (bf16 G and A, O == 128, 16-byte aligned rows), else an error -- never a silent fallback in tests.
+extern "C" int gsage_wgrad(const void* g_dev, int g_dtype, int64_t ldg, int O, const void* a_dev, int a_dtype, int64_t lda,
+                           const int64_t* ids_dev, int d, int64_t n, float* dw_dev, int64_t lddw, int exact, void* stream) {
+    GS_CHECK_ARG(g_dev && a_dev && dw_dev && O > 0 && d > 0 && n >= 0 && lddw >= d && ldg >= O, "wgrad: bad arguments");
+    cudaStream_t s = as_stream(stream);
+    if (exact) {
+        GS_CHECK_ARG(g_dtype == GSAGE_F32, "wgrad: the exact (FFMA) kernel takes an fp32 output gradient");
+        return wgrad_launch((const float*)g_dev, ldg, O, a_dev, a_dtype, lda, ids_dev, d, n, dw_dev, lddw, s);
+    }
+    WgradJob j{g_dev, g_dtype, ldg, O, a_dev, a_dtype, lda, ids_dev, d, n, dw_dev, lddw};
+    GS_CHECK_ARG(wgrad_umma_eligible(j), "wgrad: operands do not qualify for the tensor-core kernel (bf16 G and A, O == 128, aligned rows)");
+    return wgrad_umma_launch(&j, 1, s);
+}

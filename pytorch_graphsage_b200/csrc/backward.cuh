@@ -7,8 +7,16 @@ namespace gsage {
 // dW[o, k] = sum_r G[r, o] * A[ids ? ids[r] : r, k]   (dW zeroed first; fp32)
 int wgrad_launch(const float* G, int64_t ldg, int O, const void* A, int a_dtype, int64_t lda, const int64_t* ids, int d,
                  int64_t n, float* dW, int64_t lddw, cudaStream_t s);
+// tensor-core version (wgrad_umma.cu): bf16 G and A, O == 128; up to two jobs (the fc_x / fc_neib pair) per launch
+struct WgradJob {
+    const void* G; int g_dtype; int64_t ldg; int O;       // G: (n, O) slice of the output gradient
+    const void* A; int a_dtype; int64_t lda; const int64_t* ids; int d;
+    int64_t n; float* dW; int64_t lddw;
+};
+bool wgrad_umma_eligible(const WgradJob& j);
+int wgrad_umma_launch(const WgradJob* jobs, int n_jobs, cudaStream_t s);
 int l2_normalize_bwd_launch(const float* z, const float* dzn, int64_t n, int d, int act, float* dz, cudaStream_t s);
 int layer1_grad_launch(const float* dh0, const float* dm2, const void* H, int h_dtype, int64_t ldh, int64_t n0, int64_t n1, int S,
-                       int width, int act, float* dH, cudaStream_t s);
+                       int width, int act, void* dH, int dh_dtype, cudaStream_t s);
 int colsum_launch(const float* x, int64_t n, int d, float* out, cudaStream_t s);
 }

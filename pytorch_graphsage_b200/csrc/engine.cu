@@ -693,6 +693,16 @@ int gsage_engine_forward_host(gsage_engine* e, gsage_graph* g, gsage_rng* rng, c
     return gsage_engine_forward_host_next(e, g, rng, ids_host, B, nullptr, 0, logits_host, stream);
 }
 
+// layer-1 weight gradients run on tcgen05 when everything is bf16 and O1 == 128 (wgrad_umma.cu); fp32 mode stays exact
+static bool layer1_wgrad_on_tensor_cores(const gsage_engine* e) {
+    if (e->T != GSAGE_BF16 || e->cfg.out_dim[0] != 128 || e->cfg.feats_dtype != GSAGE_BF16) return false;
+    WgradJob probe{e->DH, GSAGE_BF16, 2 * (int64_t)e->cfg.out_dim[0], 128, e->cfg.feats_dev, GSAGE_BF16, e->cfg.feats_ld, e->ids,
+                   e->cfg.feats_dim, 1, nullptr, e->cfg.feats_dim};
+    WgradJob probe2 = probe;
+    probe2.A = e->M; probe2.lda = e->ld_m; probe2.ids = nullptr;
+    return wgrad_umma_eligible(probe) && wgrad_umma_eligible(probe2);
+}
+
 static int backward_supported(gsage_engine* e) {
     GS_CHECK_ARG(e && e->have_weights && e->B > 0, "engine_backward: run gsage_engine_forward first");
     GS_CHECK_ARG(e->cfg.aggregator == GSAGE_AGG_MEAN && e->cfg.prep == GSAGE_PREP_IDENTITY,
@@ -723,7 +733,8 @@ int gsage_engine_backward_head(gsage_engine* e, const float* dlogits, const gsag
     GS_TRY(linear_trans_call(e->DZ, 2 * O2, O2, e->w.layer[1].fc_x, 2 * O1, 2 * O1, n0, e->DH0, 2 * O1, s));
     GS_TRY(linear_trans_call(e->DZ + O2, 2 * O2, O2, e->w.layer[1].fc_neib, 2 * O1, 2 * O1, n0, e->DM2, 2 * O1, s));
     // mean over S1 children + concat + layer-1 activation, backwards
-    GS_TRY(layer1_grad_launch(e->DH0, e->DM2, e->H1, e->T, e->ld_h1, n0, n1, S1, 2 * O1, c.act[0], e->DH, s));
+    GS_TRY(layer1_grad_launch(e->DH0, e->DM2, e->H1, e->T, e->ld_h1, n0, n1, S1, 2 * O1, c.act[0], e->DH,
+                              layer1_wgrad_on_tensor_cores(e) ? GSAGE_BF16 : GSAGE_F32, s));
     return mark_slot_done(e, s);
 }
 
@@ -735,6 +746,16 @@ int gsage_engine_backward_layer1(gsage_engine* e, const gsage_grads* g, void* st
     const int64_t n0 = e->B, n1 = n0 * c.fanout[0];
     const int O1 = c.out_dim[0], d = c.feats_dim;
     // h = act([table[ids01] Wx1^T | M01 Wn1^T]): both weight gradients reduce over all n0 + n1 parent rows
+    if (layer1_wgrad_on_tensor_cores(e)) {
+        // bf16 mode: split-K tcgen05 GEMMs straight from the row-major operands (MN-major), self rows gathered by id;
+        // the output gradient was written as bf16 by layer1_grad_kernel
+        const __nv_bfloat16* dh = (const __nv_bfloat16*)e->DH;
+        WgradJob jobs[2] = {
+            {dh, GSAGE_BF16, 2 * (int64_t)O1, O1, c.feats_dev, c.feats_dtype, c.feats_ld, e->ids, d, n0 + n1, g->fc_x[0], d},
+            {dh + O1, GSAGE_BF16, 2 * (int64_t)O1, O1, e->M, e->T, e->ld_m, nullptr, d, n0 + n1, g->fc_neib[0], d}};
+        GS_TRY(wgrad_umma_launch(jobs, 2, s));
+        return mark_slot_done(e, s);
+    }
     GS_TRY(wgrad_launch(e->DH, 2 * O1, O1, c.feats_dev, c.feats_dtype, c.feats_ld, e->ids, d, n0 + n1, g->fc_x[0], d, s));
     GS_TRY(wgrad_launch(e->DH + O1, 2 * O1, O1, e->M, e->T, e->ld_m, nullptr, d, n0 + n1, g->fc_neib[0], d, s));
     return mark_slot_done(e, s);          // the weight gradients gather self rows by id: the slot is busy until here

@@ -65,7 +65,8 @@ struct UmmaParams {
     int pool_max;         // 1 = max, 0 = mean
     int tf32;             // operands are fp32 read as TF32 (kind::tf32, 32 elements per 128-byte chunk row) instead of bf16
     int uk;               // elements per 128-byte chunk row: 64 (bf16) | 32 (tf32)
-    int prefetch;         // L2-prefetch whole rows of the next tile (GSAGE_UMMA_PREFETCH=1; off by default)
+    int prefetch;         // L2-prefetch whole rows of the next tile from the TMA warp (GSAGE_UMMA_PREFETCH=1; off by default)
+    int pf;               // tiles of LSU-path L2 prefetch distance from two otherwise idle warps (0 = off; GSAGE_PF)
     int debug;            // GSAGE_UMMA_DEBUG bit0: no A reads, bit1: no W reads, bit2: no MMA issue (timing experiments only)
     int* err;
 };
@@ -121,6 +122,7 @@ __global__ void __launch_bounds__(kThreads, 1) linear_umma_kernel(const UmmaPara
     uint64_t* bars = (uint64_t*)(smem + (size_t)P.stages * P.stage_bytes);
     uint32_t* tmem_slot = (uint32_t*)(bars + 2 * 8 + 4);
     float* pool_scratch = (float*)(bars + 32);              // 128 x 33 floats, used only by the pooled epilogue
+    volatile int* progress = (volatile int*)(tmem_slot + 1);
     const uint32_t bar_base = smem_u32(bars);
     auto full_bar = [&](int s) { return bar_base + 8u * s; };
     auto empty_bar = [&](int s) { return bar_base + 8u * (8 + s); };
@@ -132,6 +134,7 @@ __global__ void __launch_bounds__(kThreads, 1) linear_umma_kernel(const UmmaPara
     if (threadIdx.x == 0) {
         for (int s = 0; s < P.stages; ++s) { mbar_init(full_bar(s), P.full_count); mbar_init(empty_bar(s), 1); }
         for (int b = 0; b < 2; ++b) { mbar_init(tfull_bar(b), 1); mbar_init(tempty_bar(b), 32 * kEpiWarps); }
+        *progress = 0;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == kEpiWarps) {                                 // the MMA warp owns the TMEM allocation
@@ -233,7 +236,7 @@ __global__ void __launch_bounds__(kThreads, 1) linear_umma_kernel(const UmmaPara
                     __syncwarp();
                 }
             }
-            if (lane == 0) umma_commit(tfull_bar(buf));                  // accumulators of this tile complete
+            if (lane == 0) { umma_commit(tfull_bar(buf)); progress_publish(progress, it + 1); }   // accumulators of this tile complete
             __syncwarp();
         }
     } else if (warp == kTmaWarp) {
@@ -282,6 +285,19 @@ __global__ void __launch_bounds__(kThreads, 1) linear_umma_kernel(const UmmaPara
         }
     } else {
         // =========================== LOADERS ===========================
+        if (!P.any_reduce && P.pf > 0 && warp < kFirstLoadWarp + 2) {
+            // plain mode: two of these warps pull the A rows of the tile `pf` tiles ahead into L2 (LSU path, whole rows)
+            const int t = threadIdx.x - 32 * kFirstLoadWarp, nt = 64;
+            const int es = P.tf32 ? 4 : 2;
+            int it = 0;
+            for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x, ++it) {
+                if (it >= P.pf) progress_wait(progress, it - P.pf);
+                for (int sidx = 0; sidx < P.n_segs; ++sidx) {
+                    const UmmaSeg& sg = P.seg[sidx];
+                    prefetch_tile_rows(sg.a, sg.lda * es, sg.ids, (int64_t)tile * P.tile_rows, P.n, P.tile_rows, sg.kvalid * es, t, nt);
+                }
+            }
+        }
         if (P.any_reduce) {
         // group g fills items g, g+G, g+2G, ... (an item = one (tile, segment, k-chunk) stage); the MMA warp consumes
         // items in order.  Thread (rg, c): 16-byte chunk c of rows rg, rg+8, ... of the 128-row tile.
@@ -455,6 +471,8 @@ int linear_umma_launch(const LinearParams& P, cudaStream_t s) {
     for (int i = 0; i < P.n_segs; ++i) U.any_reduce |= (U.seg[i].S > 1) ? 1 : 0;
     U.prefetch = 0;      // measured: 275 us with, 198 us without (reddit layer-1 shape) -- the prefetches queue behind the tile loads
     if (const char* e = getenv("GSAGE_UMMA_PREFETCH")) U.prefetch = atoi(e) != 0;
+    U.pf = 1;
+    if (const char* e = getenv("GSAGE_PF")) U.pf = atoi(e);
     U.full_count = U.any_reduce ? kGroupThreads : 1;                      // plain mode: the TMA lane's expect_tx arrival + byte count
     if (const char* e = getenv("GSAGE_UMMA_DEBUG")) U.debug = atoi(e);
     U.w_bytes = maxO * UK * 2;

@@ -4,15 +4,18 @@
 // for up to two segments s, the reference's concat-with-self), different data movement.  The streaming kernel
 // re-reads the W chunk of every (tile, k-chunk) stage from L2, so for the layer-1 shape (d = 602, O = 128) half of
 // the bytes an SM ingests are weights -- and the L2 -> SM fabric (~6.5 TB/s chip-wide, B300_MICROARCH.md "LTS
-// throughput cap") is what bounds that kernel, not HBM.  Here a CTA loads the W of a *phase* once
-// (kchunks x O x 128 B, 160 KB for layer 1) and keeps it for all of its row tiles; only A rows stream:
+// throughput cap") is what bounds that kernel, not HBM.  Here a CTA loads (most of) the W of a *phase* once and keeps it
+// for all of its row tiles: the first `kres` k-chunks of W are resident (kres x O x 128 B), the rest -- whatever does not
+// fit next to a ring deep enough to cover the load latency -- streams through the ring with the A chunks.
+// Measured (reddit layer 1, B=16384): fully resident W (160 KB) leaves 4 x 16 KB stages = too few bytes in flight, 418 us
+// vs 391 us streaming; kres and the ring depth are therefore planned together (GSAGE_WS_STAGES, default 6).
 //   phase = the segments whose weights fit in shared memory together (both for d <= 256; one at a time for
 //           d = 602: all row tiles with Wx, then all row tiles again with Wn -- each phase writes its own column
 //           range of the output, the activation is elementwise, so the result is identical)
 //   warps 0-3  epilogue   tcgen05.ld -> bias / activation -> bf16 | fp32 -> HBM
 //   warp  4    MMA issue  tcgen05.mma M=128, N=O, K=16 (bf16) | 8 (tf32); A from the stage ring, B from the resident W
-//   warp  5    TMA issue  W of the phase (one expect_tx for all of it), then per (tile, segment, k-chunk) one A stage:
-//                         cp.async.bulk.tensor.2d (in place) or 32 x tile::gather4 (rows by id)
+//   warps 5-8  TMA issue  W of the phase (one expect_tx for all of it), then per (tile, segment, k-chunk) one A stage:
+//                         cp.async.bulk.tensor.2d (in place, producer 0) or 4 x 8 tile::gather4 (rows by id, all producers)
 // Two TMEM accumulator buffers (2 x 256 columns): the epilogue of tile i overlaps the loads and MMAs of tile i+1.
 // Every mbarrier wait is bounded (a stuck pipeline traps instead of hanging the GPU).
 #include "linear.cuh"
@@ -24,9 +27,10 @@ namespace gsage {
 
 static constexpr int WM = 128;                 // rows per tile (UMMA M)
 static constexpr int kWsEpiWarps = 4;
-static constexpr int kWsThreads = 32 * (kWsEpiWarps + 2);
+static constexpr int kWsTmaWarps = 4;             // producers: a lone warp issuing 32 gather4 per stage is the bottleneck (see below)
+static constexpr int kWsThreads = 32 * (kWsEpiWarps + 1 + kWsTmaWarps);
 static constexpr int kWsABytes = WM * 128;     // one A stage: 128 rows x 128 bytes
-static constexpr int kWsMaxStages = 8;
+static constexpr int kWsMaxStages = 12;
 static constexpr int kSmemLimit = 227 * 1024;
 
 struct WsSeg {
@@ -34,7 +38,8 @@ struct WsSeg {
     int d; int O; const float* bias; int64_t col0;
     int kchunks;          // ceil(d / uk)
     int acc_col;          // first TMEM column of this segment's accumulator inside a buffer
-    int w_off;            // byte offset of this segment's resident W inside the W area (kchunks slots of O x 128 B)
+    int w_off;            // byte offset of this segment's resident W inside the W area (kres slots of O x 128 B)
+    int kres;             // k-chunks of W resident in shared memory; chunks kres.. stream through the ring
 };
 
 struct WsParams {
@@ -43,6 +48,7 @@ struct WsParams {
     int64_t n; int act;
     void* out; int out_bf16; int64_t ld_out;
     int n_tiles; int stages; int w_area;      // bytes reserved for the resident weights
+    int stage_bytes;                          // one ring slot: an A chunk (128 x 128 B) or a streamed W chunk (O x 128 B)
     int tf32; int uk;
     int* err;
 };
@@ -91,7 +97,7 @@ __global__ void __launch_bounds__(kWsThreads, 1) linear_ws_umma_kernel(const WsP
     // carve: [resident W: w_area] [stages x A 16 KB] [barriers]
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint8_t* a_ring = smem + P.w_area;
-    uint64_t* bars = (uint64_t*)(a_ring + (size_t)P.stages * kWsABytes);
+    uint64_t* bars = (uint64_t*)(a_ring + (size_t)P.stages * P.stage_bytes);
     uint32_t* tmem_slot = (uint32_t*)(bars + 2 * kWsMaxStages + 6);
     const uint32_t bar_base = smem_u32(bars);
     auto full_bar = [&](int s) { return bar_base + 8u * s; };
@@ -151,88 +157,154 @@ __global__ void __launch_bounds__(kWsThreads, 1) linear_ws_umma_kernel(const WsP
         }
     } else if (warp == kWsEpiWarps) {
         // =========================== MMA ISSUER ===========================
-        int item = 0, it = 0;
-        const uint32_t fmt = P.tf32 ? 2u : 1u;              // a/b format: 1 = bf16, 2 = tf32
-        for (int ph = 0; ph < P.n_phases; ++ph) {
-            mbar_wait(wfull_bar, ph & 1, P.err);             // this phase's weights have landed
-            tc_fence_after();
-            for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x, ++it) {
-                const int buf = it & 1;
-                mbar_wait(tempty_bar(buf), ((it >> 1) & 1) ^ 1, P.err);     // first use of each buffer passes immediately
-                tc_fence_after();
-                for (int si = 0; si < P.phase_count[ph]; ++si) {
-                    const WsSeg& sg = P.seg[P.phase_first[ph] + si];
-                    // instruction descriptor: D = f32, A = B = bf16 | tf32, both K-major, N = O, M = 128
-                    const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(sg.O >> 3) << 17) | ((uint32_t)(WM >> 4) << 24);
-                    const uint32_t d_tmem = tmem_base + (uint32_t)(buf * 256 + sg.acc_col);
-                    const uint32_t w_base = smem_u32(smem + sg.w_off);
-                    const uint32_t w_slot = (uint32_t)sg.O * 128u;
-                    for (int kc = 0; kc < sg.kchunks; ++kc, ++item) {
-                        const int stage = item % P.stages;
-                        mbar_wait(full_bar(stage), (item / P.stages) & 1, P.err);
-                        tc_fence_after();
-                        if (lane == 0) {
-                            const uint64_t adesc = umma_desc(smem_u32(a_ring + (size_t)stage * kWsABytes));
-                            const uint64_t bdesc = umma_desc(w_base + (uint32_t)kc * w_slot);
-#pragma unroll
-                            for (int k = 0; k < 4; ++k) {                // 4 x (K = 16 bf16 | 8 tf32): +32 bytes inside the swizzle atom
-                                if (P.tf32) umma_tf32(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kc | k) ? 1u : 0u);
-                                else umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kc | k) ? 1u : 0u);
+        // ONE thread runs this loop, and it is the critical path of the kernel: every instruction between two stages is
+        // serial latency (a lone warp issues a dependent instruction every ~5 cycles).  Measured with ncu's source view:
+        // the first version (modulo / division by the runtime stage count, descriptors rebuilt per stage, parameter
+        // structs indexed dynamically) spent ~1300 cycles of instructions per 16 KB stage -- 2/3 of the kernel.  Hence:
+        // ring position and parity by increment, descriptors by addition, everything else hoisted.
+        if (lane == 0) {
+            const uint32_t fmt = P.tf32 ? 2u : 1u;              // a/b format: 1 = bf16, 2 = tf32
+            const uint32_t ring16 = (smem_u32(a_ring) & 0x3FFFF) >> 4, sb16 = (uint32_t)P.stage_bytes >> 4;
+            const uint64_t desc_hi = umma_desc(0);               // everything but the start address
+            const uint32_t n_stages = (uint32_t)P.stages;
+            uint32_t stage = 0, par = 0, a16 = ring16;           // ring slot, its parity, its address / 16
+            int it = 0;
+            for (int ph = 0; ph < P.n_phases; ++ph) {
+                mbar_wait(wfull_bar, ph & 1, P.err);             // this phase's resident weights have landed
+                const int s_first = P.phase_first[ph], s_count = P.phase_count[ph];
+                for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x, ++it) {
+                    const uint32_t buf = it & 1;
+                    mbar_wait(tempty_bar(buf), ((it >> 1) & 1) ^ 1, P.err);     // first use of each buffer passes immediately
+                    tc_fence_after();
+                    for (int si = 0; si < s_count; ++si) {
+                        const WsSeg& sg = P.seg[s_first + si];
+                        // instruction descriptor: D = f32, A = B = bf16 | tf32, both K-major, N = O, M = 128
+                        const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(sg.O >> 3) << 17) | ((uint32_t)(WM >> 4) << 24);
+                        const uint32_t d_tmem = tmem_base + buf * 256u + (uint32_t)sg.acc_col;
+                        const uint32_t w_slot16 = ((uint32_t)sg.O * 128u) >> 4;
+                        uint64_t wdesc = desc_hi | (uint64_t)((smem_u32(smem + sg.w_off) & 0x3FFFF) >> 4);
+                        const int kchunks = sg.kchunks, kres = sg.kres;
+                        for (int kc = 0; kc < kchunks; ++kc) {
+                            mbar_wait(full_bar(stage), par, P.err);
+                            const uint32_t a_stage = stage;
+                            const uint64_t adesc = desc_hi | (uint64_t)a16;
+                            if (++stage == n_stages) { stage = 0; par ^= 1; a16 = ring16; } else a16 += sb16;
+                            uint64_t bdesc = wdesc;
+                            uint32_t w_stage = 0;
+                            const bool streamed = kc >= kres;
+                            if (streamed) {                              // this W chunk came through the ring too
+                                mbar_wait(full_bar(stage), par, P.err);
+                                w_stage = stage;
+                                bdesc = desc_hi | (uint64_t)a16;
+                                if (++stage == n_stages) { stage = 0; par ^= 1; a16 = ring16; } else a16 += sb16;
+                            } else {
+                                wdesc += w_slot16;
                             }
-                            umma_commit(empty_bar(stage));               // A slot reusable once these MMAs retire
+                            tc_fence_after();
+                            if (P.tf32) {
+#pragma unroll
+                                for (int k = 0; k < 4; ++k) umma_tf32(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kc | k) ? 1u : 0u);
+                            } else {
+#pragma unroll
+                                for (int k = 0; k < 4; ++k) umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kc | k) ? 1u : 0u);
+                            }
+                            umma_commit(empty_bar(a_stage));             // slots reusable once these MMAs retire
+                            if (streamed) umma_commit(empty_bar(w_stage));
                         }
-                        __syncwarp();
                     }
+                    umma_commit(tfull_bar(buf));                         // accumulators of this tile complete
                 }
-                if (lane == 0) umma_commit(tfull_bar(buf));              // accumulators of this tile complete
-                __syncwarp();
+                umma_commit(wempty_bar);                                 // every MMA that reads this phase's W has retired
             }
-            if (lane == 0) umma_commit(wempty_bar);                      // every MMA that reads this phase's W has retired
-            __syncwarp();
         }
+        __syncwarp();
     } else {
-        // =========================== TMA ISSUER ===========================
-        int item = 0;
+        // =========================== TMA PRODUCERS ===========================
+        // Four warps walk the same stage sequence.  Producer 0 (lane 0) posts every expect_tx and issues the one-instruction
+        // loads (resident W, in-place A chunks, streamed W chunks).  A chunk gathered BY ID is 32 tile::gather4 instructions
+        // with per-instruction row coordinates; TMA operands live in uniform registers, so a warp issues them one lane at
+        // a time (~50 cycles each: ncu shows the R2UR / UTMALDG / BRA.U.ANY loop at 43 % of a lone producer warp's samples,
+        // ~1 us per 16 KB stage).  Each producer therefore gathers 32 of the 128 rows: 8 instructions per warp per stage,
+        // on four schedulers at once.  mbarrier transaction counts may go negative, so the byte completions of the other
+        // producers need no ordering against producer 0's expect_tx.
+        const int pw = warp - (kWsEpiWarps + 1);
+        const uint32_t ring_u = smem_u32(a_ring), sb = (uint32_t)P.stage_bytes;
+        const uint32_t n_stages = (uint32_t)P.stages;
+        const int uk = P.uk;
+        const bool lead = pw == 0 && lane == 0;
+        uint32_t stage = 0, par = 1, sa_u = ring_u;              // producer parity starts at 1: fresh slots are free
         for (int ph = 0; ph < P.n_phases; ++ph) {
-            mbar_wait(wempty_bar, (ph & 1) ^ 1, P.err);      // phase 0 passes immediately; later phases wait for the MMAs
-            if (lane == 0) {
+            const int s_first = P.phase_first[ph], s_count = P.phase_count[ph];
+            if (lead) {
+                mbar_wait(wempty_bar, (ph & 1) ^ 1, P.err);  // phase 0 passes immediately; later phases wait for the MMAs
                 uint32_t total = 0;
-                for (int si = 0; si < P.phase_count[ph]; ++si) {
-                    const WsSeg& sg = P.seg[P.phase_first[ph] + si];
-                    total += (uint32_t)sg.kchunks * (uint32_t)sg.O * 128u;
+                for (int si = 0; si < s_count; ++si) {
+                    const WsSeg& sg = P.seg[s_first + si];
+                    total += (uint32_t)sg.kres * (uint32_t)sg.O * 128u;
                 }
                 mbar_arrive_expect_tx(wfull_bar, total);
-                for (int si = 0; si < P.phase_count[ph]; ++si) {
-                    const int sidx = P.phase_first[ph] + si;
-                    const WsSeg& sg = P.seg[sidx];
+                for (int si = 0; si < s_count; ++si) {
+                    const WsSeg& sg = P.seg[s_first + si];
                     const uint32_t w_base = smem_u32(smem + sg.w_off);
-                    for (int kc = 0; kc < sg.kchunks; ++kc)
-                        tma_load_2d(w_base + (uint32_t)kc * (uint32_t)sg.O * 128u, &M.w[sidx], kc * P.uk, 0, wfull_bar);
+                    for (int kc = 0; kc < sg.kres; ++kc)
+                        tma_load_2d(w_base + (uint32_t)kc * (uint32_t)sg.O * 128u, &M.w[s_first + si], kc * uk, 0, wfull_bar);
                 }
             }
-            __syncwarp();
             for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x) {
-                for (int si = 0; si < P.phase_count[ph]; ++si) {
-                    const int sidx = P.phase_first[ph] + si;
+                for (int si = 0; si < s_count; ++si) {
+                    const int sidx = s_first + si;
                     const WsSeg& sg = P.seg[sidx];
-                    int r0 = 0, r1 = 0, r2 = 0, r3 = 0;            // lane l gathers tile rows 4l .. 4l+3 by id
-                    if (sg.ids) {
-                        const int64_t base = (int64_t)tile * WM + 4 * lane;
-                        if (base + 0 < P.n) r0 = (int)__ldg(sg.ids + base + 0);
-                        if (base + 1 < P.n) r1 = (int)__ldg(sg.ids + base + 1);
-                        if (base + 2 < P.n) r2 = (int)__ldg(sg.ids + base + 2);
-                        if (base + 3 < P.n) r3 = (int)__ldg(sg.ids + base + 3);
-                    }
-                    for (int kc = 0; kc < sg.kchunks; ++kc, ++item) {
-                        const int stage = item % P.stages;
-                        mbar_wait(empty_bar(stage), ((item / P.stages) & 1) ^ 1, P.err);
-                        const uint32_t sa_u = smem_u32(a_ring + (size_t)stage * kWsABytes);
-                        if (lane == 0) {
-                            mbar_arrive_expect_tx(full_bar(stage), (uint32_t)kWsABytes);
-                            if (!sg.ids) tma_load_2d(sa_u, &M.a[sidx], kc * P.uk, tile * WM, full_bar(stage));
+                    const int64_t* ids = sg.ids;
+                    const int kchunks = sg.kchunks, kres = sg.kres;
+                    const uint32_t w_chunk_bytes = (uint32_t)sg.O * 128u;
+                    const CUtensorMap* map_a = ids ? &M.g[sidx] : &M.a[sidx];
+                    const CUtensorMap* map_w = &M.w[sidx];
+                    const int tile_row = tile * WM;
+                    if (ids) {
+                        // ---- gathered operand: lanes 0..7 of producer pw own tile rows 32 pw + 4 lane .. + 3 ----
+                        int r0 = 0, r1 = 0, r2 = 0, r3 = 0;
+                        const int my_row = 32 * pw + 4 * lane;
+                        if (lane < 8) {
+                            const int64_t base = (int64_t)tile_row + my_row;
+                            if (base + 0 < P.n) r0 = (int)__ldg(ids + base + 0);
+                            if (base + 1 < P.n) r1 = (int)__ldg(ids + base + 1);
+                            if (base + 2 < P.n) r2 = (int)__ldg(ids + base + 2);
+                            if (base + 3 < P.n) r3 = (int)__ldg(ids + base + 3);
                         }
-                        __syncwarp();                              // expect_tx is posted before any lane's copy can complete
-                        if (sg.ids) tma_gather4(sa_u + lane * 512, &M.g[sidx], kc * P.uk, r0, r1, r2, r3, full_bar(stage));
+                        const uint32_t row_off = (uint32_t)my_row * 128u;
+                        for (int kc = 0, col = 0; kc < kchunks; ++kc, col += uk) {
+                            mbar_wait(empty_bar(stage), par, P.err);
+                            const uint32_t fb = full_bar(stage);
+                            if (lead) mbar_arrive_expect_tx(fb, (uint32_t)kWsABytes);
+                            if (lane < 8) tma_gather4(sa_u + row_off, map_a, col, r0, r1, r2, r3, fb);
+                            if (++stage == n_stages) { stage = 0; par ^= 1; sa_u = ring_u; } else sa_u += sb;
+                            if (kc >= kres) {                      // this W chunk is not resident: it streams through the ring too
+                                if (lead) {
+                                    mbar_wait(empty_bar(stage), par, P.err);
+                                    mbar_arrive_expect_tx(full_bar(stage), w_chunk_bytes);
+                                    tma_load_2d(sa_u, map_w, col, 0, full_bar(stage));
+                                }
+                                if (++stage == n_stages) { stage = 0; par ^= 1; sa_u = ring_u; } else sa_u += sb;
+                            }
+                        }
+                    } else {
+                        // ---- operand read in place: one instruction per chunk, producer 0 alone ----
+                        for (int kc = 0, col = 0; kc < kchunks; ++kc, col += uk) {
+                            if (lead) {
+                                mbar_wait(empty_bar(stage), par, P.err);
+                                mbar_arrive_expect_tx(full_bar(stage), (uint32_t)kWsABytes);
+                                tma_load_2d(sa_u, map_a, col, tile_row, full_bar(stage));
+                            }
+                            if (++stage == n_stages) { stage = 0; par ^= 1; sa_u = ring_u; } else sa_u += sb;
+                            if (kc >= kres) {
+                                if (lead) {
+                                    mbar_wait(empty_bar(stage), par, P.err);
+                                    mbar_arrive_expect_tx(full_bar(stage), w_chunk_bytes);
+                                    tma_load_2d(sa_u, map_w, col, 0, full_bar(stage));
+                                }
+                                if (++stage == n_stages) { stage = 0; par ^= 1; sa_u = ring_u; } else sa_u += sb;
+                            }
+                        }
                     }
                 }
             }
@@ -250,27 +322,49 @@ __global__ void __launch_bounds__(kWsThreads, 1) linear_ws_umma_kernel(const WsP
 // ---- host -------------------------------------------------------------------------------------------------
 static bool ws_aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
-static int ws_w_bytes(const LinearSeg& s) {
+static int ws_kchunks(const LinearSeg& s) {
     const int es = s.a_dtype == GSAGE_BF16 ? 2 : 4, uk = 128 / es;
-    return (s.d + uk - 1) / uk * s.O * 128;
+    return (s.d + uk - 1) / uk;
 }
 
-// plan the phases: both segments resident together when they fit next to >= 4 A stages, else one segment per phase
-static bool ws_plan(const LinearParams& P, int* n_phases, int* w_area, int* stages) {
+struct WsPlan { int n_phases, w_area, stages, stage_bytes, kres[2]; };
+
+// plan the phases: both segments fully resident together when they fit next to a deep enough ring, else one segment per
+// phase with as many resident k-chunks as the ring leaves room for
+static bool ws_plan(const LinearParams& P, WsPlan* out) {
     const int fixed = 1024 /*align slack*/ + 512 /*barriers*/;
-    int total = 0, widest = 0, cols = 0;
+    int total = 0, cols = 0, maxO = 0;
     for (int i = 0; i < P.n_segs; ++i) {
-        const int wb = ws_w_bytes(P.seg[i]);
-        total += wb; widest = wb > widest ? wb : widest;
+        total += ws_kchunks(P.seg[i]) * P.seg[i].O * 128;
         cols += (P.seg[i].O + 31) / 32 * 32;
+        maxO = P.seg[i].O > maxO ? P.seg[i].O : maxO;
     }
-    int area, phases;
-    if (cols <= 256 && total + 4 * kWsABytes + fixed <= kSmemLimit) { area = total; phases = 1; }
-    else { area = widest; phases = P.n_segs; }
-    int st = (kSmemLimit - fixed - area) / kWsABytes;
-    if (st > kWsMaxStages) st = kWsMaxStages;
-    if (st < 3) return false;
-    *n_phases = phases; *w_area = area; *stages = st;
+    WsPlan p;
+    p.stage_bytes = maxO * 128 > kWsABytes ? maxO * 128 : kWsABytes;
+    int min_stages = 6;
+    if (const char* e = getenv("GSAGE_WS_STAGES")) min_stages = atoi(e);
+    if (min_stages < 3) min_stages = 3;
+    if (min_stages > kWsMaxStages) min_stages = kWsMaxStages;
+    const int avail = kSmemLimit - fixed - min_stages * p.stage_bytes;
+    if (avail < 0) return false;
+    if (cols <= 256 && total <= avail) {
+        p.n_phases = 1; p.w_area = total;
+        for (int i = 0; i < P.n_segs; ++i) p.kres[i] = ws_kchunks(P.seg[i]);
+    } else {
+        p.n_phases = P.n_segs; p.w_area = 0;
+        for (int i = 0; i < P.n_segs; ++i) {
+            const int slot = P.seg[i].O * 128;
+            int k = avail / slot;
+            if (k > ws_kchunks(P.seg[i])) k = ws_kchunks(P.seg[i]);
+            p.kres[i] = k;
+            if (k * slot > p.w_area) p.w_area = k * slot;
+        }
+    }
+    p.w_area = (p.w_area + 1023) / 1024 * 1024;
+    p.stages = (kSmemLimit - fixed - p.w_area) / p.stage_bytes;
+    if (p.stages > kWsMaxStages) p.stages = kWsMaxStages;
+    if (p.stages < 3) return false;
+    *out = p;
     return true;
 }
 
@@ -286,8 +380,8 @@ bool linear_ws_umma_eligible(const LinearParams& P) {
         if (!ws_aligned16(s.a) || !ws_aligned16(s.w) || (s.lda * es) % 16 != 0 || (s.ldw * es) % 16 != 0) return false;
         if (s.lda < (s.d + per - 1) / per * per || s.ldw < (s.d + per - 1) / per * per) return false;   // whole 16-byte chunks readable
     }
-    int ph, area, st;
-    return ws_plan(P, &ph, &area, &st);
+    WsPlan plan;
+    return ws_plan(P, &plan);
 }
 
 static int* g_ws_err = nullptr;
@@ -297,15 +391,16 @@ int linear_ws_umma_launch(const LinearParams& P, cudaStream_t s) {
     memset(&U, 0, sizeof(U));
     U.tf32 = P.seg[0].a_dtype == GSAGE_F32 ? 1 : 0;
     U.uk = U.tf32 ? 32 : 64;
-    int n_phases = 0, w_area = 0, stages = 0;
-    GS_CHECK_ARG(ws_plan(P, &n_phases, &w_area, &stages), "linear_ws_umma: weights do not fit in shared memory");
-    U.n_phases = n_phases; U.stages = stages;
-    U.w_area = (w_area + 1023) / 1024 * 1024;
+    WsPlan plan;
+    GS_CHECK_ARG(ws_plan(P, &plan), "linear_ws_umma: operands do not fit in shared memory");
+    const int n_phases = plan.n_phases;
+    U.n_phases = n_phases; U.stages = plan.stages; U.w_area = plan.w_area; U.stage_bytes = plan.stage_bytes;
     for (int i = 0; i < P.n_segs; ++i) {
         const LinearSeg& g = P.seg[i];
         U.seg[i].a = g.a; U.seg[i].lda = g.lda; U.seg[i].ids = g.ids;
         U.seg[i].d = g.d; U.seg[i].O = g.O; U.seg[i].bias = g.bias; U.seg[i].col0 = g.col0;
         U.seg[i].kchunks = (g.d + U.uk - 1) / U.uk;
+        U.seg[i].kres = plan.kres[i];
     }
     if (n_phases == 1) {
         U.phase_first[0] = 0; U.phase_count[0] = P.n_segs;
@@ -313,7 +408,7 @@ int linear_ws_umma_launch(const LinearParams& P, cudaStream_t s) {
         for (int i = 0; i < P.n_segs; ++i) {
             U.seg[i].acc_col = col; U.seg[i].w_off = off;
             col += (P.seg[i].O + 31) / 32 * 32;
-            off += ws_w_bytes(P.seg[i]);
+            off += plan.kres[i] * P.seg[i].O * 128;
         }
     } else {
         for (int i = 0; i < P.n_segs; ++i) { U.phase_first[i] = i; U.phase_count[i] = 1; U.seg[i].acc_col = 0; U.seg[i].w_off = 0; }
@@ -325,7 +420,7 @@ int linear_ws_umma_launch(const LinearParams& P, cudaStream_t s) {
         GS_CUDA(cudaMemset(g_ws_err, 0, sizeof(int)));
     }
     U.err = g_ws_err;
-    const size_t smem = (size_t)U.w_area + (size_t)U.stages * kWsABytes + 1024 /*align slack*/ + 512 /*barriers*/;
+    const size_t smem = (size_t)U.w_area + (size_t)U.stages * U.stage_bytes + 1024 /*align slack*/ + 512 /*barriers*/;
     GS_CHECK_ARG(smem <= (size_t)kSmemLimit, "linear_ws_umma: %zu bytes of shared memory needed", smem);
     static bool attr_set = false;
     if (!attr_set) {

@@ -433,13 +433,17 @@ static int64_t window_for(int64_t count, double p) {
     return (int64_t)(mean + 12.0 * sd + 64.0);
 }
 
+// Consumers may alternate between streams.  Every consuming call ends with rng_leave (an event on its stream); the first
+// call on a different stream waits for that event -- no handle of the previous stream is kept (it may be gone by then).
 int rng_enter(gsage_rng* r, cudaStream_t s) {
-    if (r->have_last && r->last_stream != s) {
-        GS_CUDA(cudaEventRecord(r->ev_switch, r->last_stream));
-        GS_CUDA(cudaStreamWaitEvent(s, r->ev_switch, 0));
-    }
+    if (r->have_last && r->last_stream != s) GS_CUDA(cudaStreamWaitEvent(s, r->ev_switch, 0));
     r->last_stream = s;
     r->have_last = true;
+    return GSAGE_OK;
+}
+
+static int rng_leave(gsage_rng* r, cudaStream_t s) {
+    GS_CUDA(cudaEventRecord(r->ev_switch, s));
     return GSAGE_OK;
 }
 
@@ -484,6 +488,7 @@ static int rng_draw(gsage_rng* r, uint32_t hi, int64_t count, uint32_t* out, cud
         r->cursor_ub += window;
         r->max_window = std::max(r->max_window, window);
     }
+    GS_TRY(rng_leave(r, s));
     return rng_prefetch(r, s);
 }
 
@@ -550,9 +555,9 @@ int gsage_rng_set_state(gsage_rng* r, const uint32_t* key, int pos, void* stream
     cudaStream_t s = as_stream(stream);
     // the given key becomes stream block 0; earlier launches (either stream) may still touch the ring
     GS_CUDA(cudaStreamSynchronize(r->side));
-    if (r->have_last && r->last_stream != s) GS_CUDA(cudaStreamSynchronize(r->last_stream));
+    if (r->have_last && r->last_stream != s) GS_CUDA(cudaEventSynchronize(r->ev_switch));   // draws queued on another stream
     GS_CUDA(cudaStreamSynchronize(s));
-    r->last_stream = s; r->have_last = true;
+    r->last_stream = s; r->have_last = false;
     GS_CUDA(cudaMemcpyAsync(r->ring, key, sizeof(uint32_t) * kN, cudaMemcpyHostToDevice, s));
     const int64_t c[2] = {pos, pos};
     GS_CUDA(cudaMemcpyAsync(r->cursor, c, sizeof(c), cudaMemcpyHostToDevice, s));
@@ -609,7 +614,7 @@ int gsage_rng_raw(gsage_rng* r, int64_t count, uint32_t* out_dev, void* stream) 
         r->cursor_lb += n;
         r->cursor_ub += n;
     }
-    return GSAGE_OK;
+    return rng_leave(r, s);
 }
 
 int gsage_rng_randint(gsage_rng* r, uint32_t hi, int64_t count, uint32_t* out_dev, void* stream) {
@@ -631,6 +636,7 @@ int gsage_rng_permutation(gsage_rng* r, int64_t n, int64_t* out_dev, void* strea
     r->parity ^= 1;
     r->cursor_lb += 0;                       // n == 1 consumes nothing; the true value comes from resync
     r->cursor_ub += window;
+    GS_TRY(rng_leave(r, s));
     return rng_resync(r, s);                  // sequential kernel anyway: re-tighten immediately
 }
 

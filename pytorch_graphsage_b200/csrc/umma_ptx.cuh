@@ -60,6 +60,33 @@ __device__ __forceinline__ void tma_gather4(uint32_t dst, const CUtensorMap* map
 __device__ __forceinline__ void l2_prefetch(const void* p, uint32_t bytes) {
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
 }
+// LSU-path L2 prefetch of one 128-byte line (fire and forget: no register, no scoreboard)
+__device__ __forceinline__ void prefetch_l2_line(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+// `nthreads` threads (this one is `t`) pull `rows` whole rows of an operand tile into L2: row r of the tile is
+// a[ids ? ids[row0 + r] : row0 + r] (pitch bytes apart), `bytes` long.  Consecutive threads take consecutive lines of the
+// same row, so a row's DRAM page is opened once.  The TMA unit keeps only a few KB of requests in flight per SM
+// (measured: ~16 KB per microsecond-latency round trip), so the tile loads of the projection kernels run at DRAM
+// *latency* unless the lines are already in L2 when TMA asks for them -- this is what puts them there.
+__device__ __forceinline__ void prefetch_tile_rows(const void* a, int64_t pitch, const int64_t* ids, int64_t row0, int64_t n,
+                                                   int rows, int bytes, int t, int nthreads) {
+    const int lines = (bytes + 127) / 128 + 1;             // + 1: rows are not 128-byte aligned, the last line covers the tail
+    for (int i = t; i < rows * lines; i += nthreads) {
+        const int r = i / lines, l = i - r * lines;
+        const int64_t row = row0 + r;
+        if (row >= n) continue;
+        const int64_t src = ids ? __ldg(ids + row) : row;
+        int off = l * 128;
+        if (off >= bytes) off = bytes - 1;
+        prefetch_l2_line((const char*)a + src * pitch + off);
+    }
+}
+// pacing of the prefetch warps: the MMA warp publishes how many tiles it has issued; a prefetch warp waits (sleeping)
+// until `want` tiles have been issued.  Approximate on purpose (issue, not completion) -- it only has to keep the
+// prefetched lines within L2's reach of their use.
+__device__ __forceinline__ void progress_publish(volatile int* p, int v) { *p = v; }
+__device__ __forceinline__ void progress_wait(volatile int* p, int want) {
+    while (*p < want) __nanosleep(200);
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }

@@ -129,6 +129,16 @@ def linear_pooled(a, w, n_parents, S, reduce='max', ids=None, bias=None, act='re
     return out
 
 
+def wgrad(g, a, ids=None, n=None, exact=True):
+    """dW (O, d) fp32 = g[:n]^T . a[ids] (ids None: a[:n]) -- the weight gradient of a Linear (gsage_wgrad)."""
+    _bind_device(a)
+    n = g.shape[0] if n is None else n
+    O, d = g.shape[1], a.shape[1]
+    dw = torch.empty((O, d), dtype=torch.float32, device=a.device)
+    check(lib().gsage_wgrad(ptr(g), dt(g), _rows2d(g), O, ptr(a), dt(a), _rows2d(a), _ids_arg(ids), d, n, ptr(dw), d, 1 if exact else 0, stream()))
+    return dw
+
+
 def attention_weights(na, xa, n_parents, S):
     _bind_device(na)
     w = torch.empty((n_parents * S,), dtype=torch.float32, device=na.device)

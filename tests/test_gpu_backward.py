@@ -79,3 +79,43 @@ def test_backward_rejects_unsupported_plugins(g):
     preds = model(torch.from_numpy(fix['ids0']), torch.from_numpy(fix['feats']))
     with pytest.raises(ValueError):
         model.backward(torch.zeros_like(preds))
+
+
+# ---- tensor-core weight gradient (wgrad_umma.cu): dW = G^T . A[ids], both operands row-major = MN-major tiles --------
+# Tolerance: bf16 operands are exact, products exact in fp32, accumulation order (split-K + atomics) differs from fp64:
+# rtol 2e-4 / atol 2e-4 * sqrt(n / 1000) on unit-variance operands.
+
+@pytest.mark.parametrize('n,d', [(64, 64), (1000, 602), (4096 + 17, 256), (300, 1433), (20000, 100), (129, 8)])
+@pytest.mark.parametrize('gather', [False, True])
+def test_wgrad_tensor_core_kernel(g, n, d, gather, monkeypatch):
+    gen = torch.Generator().manual_seed(n + d)
+    O = 128
+    rows = n + 333 if gather else n
+    a = torch.randn((rows, d), generator=gen).to(torch.bfloat16)
+    G = (torch.randn((n, 2 * O), generator=gen) / 8).to(torch.bfloat16)        # the kernel reads a 128-column slice of it
+    ids = torch.randint(0, rows, (n,), generator=gen) if gather else None
+    a_dev = g.ops.pad_table(a.float(), torch.bfloat16)[0][:, :d]
+    G_dev = G.cuda()
+    src = a[ids] if gather else a[:n]
+    tol = dict(rtol=2e-4, atol=2e-4 * max(1.0, (n / 1000.0) ** 0.5))
+    for half in (0, 1):
+        Gs = G_dev[:, half * O:(half + 1) * O]
+        want = G[:, half * O:(half + 1) * O].double().t() @ src.double()
+        got = g.ops.wgrad(Gs, a_dev, ids=None if ids is None else ids.cuda(), n=n, exact=False).cpu().double()
+        if not np.allclose(got.numpy(), want.numpy(), **tol):
+            monkeypatch.setenv('GSAGE_WGRAD_SWAP', '1')
+            alt = g.ops.wgrad(Gs, a_dev, ids=None if ids is None else ids.cuda(), n=n, exact=False).cpu().double()
+            monkeypatch.delenv('GSAGE_WGRAD_SWAP')
+            ok_alt = np.allclose(alt.numpy(), want.numpy(), **tol)
+            raise AssertionError('wgrad_umma mismatch: max err %.3e (LBO/SBO swapped variant %s: max err %.3e)' %
+                                 ((got - want).abs().max().item(), 'MATCHES' if ok_alt else 'also wrong', (alt - want).abs().max().item()))
+        # and the exact FFMA kernel on the same operands (fp32 gradient)
+        exact = g.ops.wgrad(Gs.float().contiguous(), a_dev, ids=None if ids is None else ids.cuda(), n=n, exact=True).cpu().double()
+        np.testing.assert_allclose(exact.numpy(), want.numpy(), rtol=2e-4, atol=2e-4 * max(1.0, (n / 1000.0) ** 0.5))
+
+
+def test_wgrad_rejects_operands_the_tensor_core_kernel_cannot_take(g):
+    a = torch.randn((64, 64)).cuda()
+    G = torch.randn((64, 128)).cuda()
+    with pytest.raises(ValueError):
+        g.ops.wgrad(G, a, exact=False)              # fp32 operands: no silent fallback
