@@ -136,6 +136,15 @@ int gsage_gather_reduce(const void* table_dev, int dtype, int64_t ld, int64_t n_
 /* attention weights (nn_modules.py:307-311): w[p, j] = softmax_j <na[p*S+j, :H], xa[p, :H]>, fp32 */
 int gsage_attention_weights(const void* na_dev, const void* xa_dev, int dtype, int64_t ld, int H,
                             int64_t n_parents, int S, float* w_dev, void* stream);
+/* The whole reduction of the attention aggregator (nn_modules.py:307-315) in one launch:
+ *   out[p, :d] = sum_j softmax_j(<a(n_pj), xa[p]>) n_pj,   a(v) = W2 tanh(W1 v + b1),   n_pj = table[ids[p*S + j]]
+ * (ids NULL: row p*S + j of `table`).  Scores on the tensor cores, softmax and weighted sum from the same shared-memory
+ * tile: every neighbour row is read from HBM once.  `xa_dev` = a(x_p), (n_parents, 32) fp32, computed by the caller with
+ * gsage_linear.  bf16 table and W1 (32 x d), W2 (32 x 32) fp32, 2 <= S <= 128; dummy rows are not masked (their score is
+ * a(0)-dependent, exactly like the reference).  GSAGE_ERR_INVALID when the operands do not qualify. */
+int gsage_attention_aggregate(const void* table_dev, int dtype, int64_t ld, int d, const int64_t* ids_dev, int64_t n_parents, int S,
+                              const void* w1_dev, int w1_dtype, int64_t ldw, int H, const float* b1_dev, const float* w2_dev,
+                              const float* xa_dev, void* out_dev, int out_dtype, int64_t ld_out, void* stream);
 /* F.normalize(dim=1, eps=1e-12) (models.py:90), fp32 out */
 int gsage_l2_normalize(const void* x_dev, int dtype, int64_t ld, int64_t n, int d, float* out_dev, int64_t ld_out,
                        void* stream);

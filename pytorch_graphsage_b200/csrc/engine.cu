@@ -242,12 +242,21 @@ static int apply_aggregator(gsage_engine* e, int layer, const RowSrc& x, const R
     case GSAGE_AGG_ATTENTION: {
         const int H = e->hid;
         GS_CHECK_ARG(S > 1, "attention aggregator: S must be > 1");
-        GS_TRY(linear_call(nb, e->w_att1[layer], H, e->b_att[layer], n * S, GSAGE_ACT_TANH, e->T1, GSAGE_F32, H, 0, exact, s));
-        RowSrc t1{e->T1, GSAGE_F32, H, n * S, nullptr, H};
-        GS_TRY(linear_call(t1, f32w(L.att_w2, H), H, nullptr, n * S, GSAGE_ACT_NONE, e->NA, GSAGE_F32, H, 0, 1, s));
+        // a(x_i) for the n parents: two small projections (n rows, not n*S)
         GS_TRY(linear_call(x, e->w_att1[layer], H, e->b_att[layer], n, GSAGE_ACT_TANH, e->T1x, GSAGE_F32, H, 0, exact, s));
         RowSrc t1x{e->T1x, GSAGE_F32, H, n, nullptr, H};
         GS_TRY(linear_call(t1x, f32w(L.att_w2, H), H, nullptr, n, GSAGE_ACT_NONE, e->XA, GSAGE_F32, H, 0, 1, s));
+        if (!exact && attention_fused_eligible(nb.base, nb.dtype, nb.ld, d, e->w_att1[layer].p, e->w_att1[layer].dtype, e->w_att1[layer].ld, H, S,
+                                               n, Mb, ldm, T)) {
+            // bf16 mode: scores (tcgen05), softmax and the weighted sum in ONE kernel -- every neighbour row is read once
+            GS_TRY(attention_fused_launch(nb.base, nb.ld, nb.ids, d, e->w_att1[layer].p, e->w_att1[layer].ld, e->b_att[layer], L.att_w2,
+                                          (const float*)e->XA, n, S, Mb, T, ldm, s));
+            RowSrc mf{Mb, T, ldm, n, nullptr, d};
+            return combine_call(x, e->w_x[layer], mf, e->w_n[layer], O, n, act, out, out_dtype, ld_out, exact, s, e->b_x[layer], e->b_n[layer]);
+        }
+        GS_TRY(linear_call(nb, e->w_att1[layer], H, e->b_att[layer], n * S, GSAGE_ACT_TANH, e->T1, GSAGE_F32, H, 0, exact, s));
+        RowSrc t1{e->T1, GSAGE_F32, H, n * S, nullptr, H};
+        GS_TRY(linear_call(t1, f32w(L.att_w2, H), H, nullptr, n * S, GSAGE_ACT_NONE, e->NA, GSAGE_F32, H, 0, 1, s));
         GS_TRY(gsage_attention_weights(e->NA, e->XA, GSAGE_F32, H, H, n, S, e->AW, s));
         GS_TRY(gather_reduce_launch(nb.base, nb.dtype, nb.ld, nb.table_rows, d, nb.ids, n, S, GSAGE_RED_SUM, e->AW, Mb, T, ldm, s));
         RowSrc m{Mb, T, ldm, n, nullptr, d};

@@ -30,6 +30,12 @@ int linear_ws_umma_launch(const LinearParams& P, cudaStream_t s);
 // pool aggregators: MLP + pool over the S rows of a parent in one tcgen05 kernel (linear_pool_umma.cu, swap-AB)
 bool linear_pool_umma_eligible(const LinearParams& P);
 int linear_pool_umma_launch(const LinearParams& P, cudaStream_t s);
+// the attention aggregator's reduction in one kernel (attention_umma.cu): scores on tcgen05, softmax + weighted sum on chip
+bool attention_fused_eligible(const void* a, int a_dtype, int64_t lda, int d, const void* w1, int w1_dtype, int64_t ldw, int H, int S,
+                              int64_t n_parents, const void* out, int64_t ld_out, int out_dtype);
+int attention_fused_launch(const void* a, int64_t lda, const int64_t* ids, int d, const void* w1, int64_t ldw, const float* b1,
+                           const float* w2, const float* xa, int64_t n_parents, int S, void* out, int out_dtype, int64_t ld_out,
+                           cudaStream_t s);
 // picks the tensor-core kernel when every operand qualifies and `exact` == 0, else the FFMA kernel
 int linear_dispatch(const LinearParams& P, int exact, cudaStream_t s);
 

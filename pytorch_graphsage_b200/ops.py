@@ -146,6 +146,18 @@ def attention_weights(na, xa, n_parents, S):
     return w
 
 
+def attention_aggregate(table, ids, n_parents, S, w1, w2, xa, b1=None, out_dtype=None):
+    """sum_j softmax_j(<a(n_pj), xa[p]>) n_pj in one launch (gsage_attention_aggregate); returns (n_parents, d)."""
+    _bind_device(table)
+    d = table.shape[1]
+    out_dtype = out_dtype or table.dtype
+    store, _ = pad_table(torch.zeros((n_parents, d), dtype=torch.float32), out_dtype)
+    out = store[:, :d]
+    check(lib().gsage_attention_aggregate(ptr(table), dt(table), _rows2d(table), d, _ids_arg(ids), n_parents, S, ptr(w1), dt(w1), _rows2d(w1),
+                                          w1.shape[0], ptr(b1), ptr(w2), ptr(xa), ptr(out), dt(out), _rows2d(out), stream()))
+    return out
+
+
 def l2_normalize(x):
     _bind_device(x)
     out = torch.empty(x.shape, dtype=torch.float32, device=x.device)

@@ -285,3 +285,46 @@ def test_weight_stationary_kernel_equals_streaming_kernel(g, n, d, O, monkeypatc
         np.testing.assert_array_equal(got_ws.cpu().numpy(), got_stream.cpu().numpy())
     out16 = g.ops.linear(segs, n, act='relu', out_dtype=torch.bfloat16, exact=False)
     np.testing.assert_allclose(out16.float().cpu().numpy(), want.numpy(), rtol=1e-2, atol=1e-2)
+
+
+# ---- fused attention reduction (attention_umma.cu) -----------------------------------------------------------------
+# Tolerance: bf16 operands are exact; scores go through a bf16 tensor-core product (fp32 accumulate), tanh.approx.f32
+# (~5e-4 relative) and __expf; the weighted sum is fp32 over bf16 rows and is rounded to bf16 on store.  Against fp64 on
+# the same bf16 operands: rtol 2e-2 / atol 2e-2 on unit-variance rows (measured ~3e-3).
+
+@pytest.mark.parametrize('n,S,d,gather', [(300, 10, 256, True), (77, 25, 256, False), (1000, 10, 602, True), (64, 2, 64, True),
+                                          (5, 128, 100, True), (513, 3, 8, False)])
+def test_fused_attention_aggregate(g, n, S, d, gather):
+    gen = torch.Generator().manual_seed(n + S + d)
+    H = 32
+    rows = 3000 if gather else n * S
+    table = _bf16(torch.randn((rows, d), generator=gen))
+    table[0] = 0                                                  # the dummy node: a zero row that is NOT masked
+    w1 = _bf16(torch.randn((H, d), generator=gen) / d ** 0.5)
+    b1 = torch.randn((H,), generator=gen) * 0.1
+    w2 = torch.randn((H, H), generator=gen) / H ** 0.5
+    xa = torch.randn((n, H), generator=gen)
+    ids = torch.randint(0, rows, (n * S,), generator=gen) if gather else None
+    if gather:
+        ids[::7] = 0
+    nb = (table[ids] if gather else table).double().view(n, S, d)
+    a_n = torch.tanh(nb @ w1.double().t() + b1.double()) @ w2.double().t()          # (n, S, H)
+    sc = torch.softmax((a_n * xa.double().view(n, 1, H)).sum(-1), dim=1)            # (n, S)
+    want = (sc.unsqueeze(-1) * nb).sum(1)
+    pad = lambda t: g.ops.pad_table(t.float(), torch.bfloat16)[0][:, :t.shape[1]]
+    for out_dtype in (torch.float32, torch.bfloat16):
+        got = g.ops.attention_aggregate(pad(table), None if ids is None else ids.cuda(), n, S, pad(w1), w2.cuda(), xa.cuda(), b1=b1.cuda(),
+                                        out_dtype=out_dtype)
+        np.testing.assert_allclose(got.float().cpu().numpy(), want.numpy(), rtol=2e-2, atol=2e-2)
+    # no bias (the plain reference module has none)
+    a_n = torch.tanh(nb @ w1.double().t()) @ w2.double().t()
+    sc = torch.softmax((a_n * xa.double().view(n, 1, H)).sum(-1), dim=1)
+    want = (sc.unsqueeze(-1) * nb).sum(1)
+    got = g.ops.attention_aggregate(pad(table), None if ids is None else ids.cuda(), n, S, pad(w1), w2.cuda(), xa.cuda(), out_dtype=torch.float32)
+    np.testing.assert_allclose(got.cpu().numpy(), want.numpy(), rtol=2e-2, atol=2e-2)
+
+
+def test_fused_attention_rejects_fp32_tables(g):
+    with pytest.raises(ValueError):
+        g.ops.attention_aggregate(torch.randn(100, 64).cuda(), None, 10, 10, torch.randn(32, 64).cuda(), torch.randn(32, 32).cuda(),
+                                  torch.randn(10, 32).cuda())
