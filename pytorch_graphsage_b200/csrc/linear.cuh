@@ -36,6 +36,9 @@ bool attention_fused_eligible(const void* a, int a_dtype, int64_t lda, int d, co
 int attention_fused_launch(const void* a, int64_t lda, const int64_t* ids, int d, const void* w1, int64_t ldw, const float* b1,
                            const float* w2, const float* xa, int64_t n_parents, int S, void* out, int out_dtype, int64_t ld_out,
                            cudaStream_t s);
+// weight-stationary, double-buffered version of the pool kernel (linear_pool_ws_umma.cu): relu, S <= 64
+bool linear_pool_ws_umma_eligible(const LinearParams& P);
+int linear_pool_ws_umma_launch(const LinearParams& P, cudaStream_t s);
 // picks the tensor-core kernel when every operand qualifies and `exact` == 0, else the FFMA kernel
 int linear_dispatch(const LinearParams& P, int exact, cudaStream_t s);
 

@@ -1,0 +1,316 @@
+// linear_pool_ws_umma.cu -- the pool aggregators' per-neighbour MLP + pool on tcgen05, weights stationary.
+//
+// Replaces  h = relu(mlp(neibs)); h.view(N, S, H).max(dim=1)[0] | .mean(dim=1)   (nn_modules.py:224-226,240,252)
+//
+//   out[p, col0 + h] = reduce_{j < S} relu( A[row(p*S + j)] . W[h] + bias[h] )
+//
+// Same swap-AB orientation as linear_pool_umma.cu (hidden units on the M side, one hidden unit per TMEM lane, the S rows
+// of a parent are S consecutive accumulator COLUMNS, the pool is a running max / sum in registers; the (N*S, H) hidden
+// matrix never exists in HBM).  What changed after profiling that kernel (pokec max-pool, B = 8192: 78 % of the step,
+// ~8000 cycles per 120-row tile against ~1000 cycles of MMA):
+//   * W is RESIDENT in shared memory for a *phase* = as many 128-unit hidden blocks as fit (all four for d = 64; two for
+//     d = 256): it used to be re-read from L2 with every tile -- 64 KB of weights for 15 KB of rows;
+//   * row tiles are 64 accumulator columns wide, so four hidden blocks need 256 TMEM columns and there are TWO accumulator
+//     buffers: the epilogue of tile i overlaps the MMAs of tile i+1 (it used to own all 512 columns and serialise);
+//   * the epilogue is specialised at compile time for the fanouts the reference uses (S = 10, 25): parent boundaries are
+//     static, one FMNMX per element, bias + relu once per parent (max_j relu(v_j + b) = relu(max_j v_j + b));
+//   * four producer warps issue the tile::gather4 loads (a lone warp issues one per ~50 cycles, see linear_ws_umma.cu),
+//     and the MMA thread's loop carries its ring position / descriptors by increment.
+// Requires: relu, S <= 64, bf16 or fp32-as-TF32 operands, one hidden block's W (kchunks x 16 KB) <= 176 KB.
+#include "linear.cuh"
+#include "umma_ptx.cuh"
+#include <string.h>
+#include <stdlib.h>
+
+namespace gsage {
+
+static constexpr int QM = 128;                    // hidden units per block (UMMA M)
+static constexpr int QN = 64;                     // accumulator columns (neighbour rows) per tile (UMMA N)
+static constexpr int kQMaxBlocks = 4;             // hidden blocks per phase: 4 x 64 columns x 2 buffers = all of TMEM
+static constexpr int kQEpiWarps = 16;             // four per TMEM lane quarter: one hidden block each
+static constexpr int kQTmaWarps = 4;
+static constexpr int kQThreads = 32 * (kQEpiWarps + 1 + kQTmaWarps);
+static constexpr int kQWChunk = QM * 128;         // 16 KB: one hidden block x one k-chunk of W
+static constexpr int kQRChunk = QN * 128;         // 8 KB: one k-chunk of a row tile
+static constexpr int kQStages = 8;
+static constexpr int kQSmemLimit = 227 * 1024;
+
+struct QParams {
+    const void* a; int64_t lda; const int64_t* ids;
+    const float* bias; int64_t col0;
+    int d, H, S, R, PT;                           // R = PT * S rows of a tile are used
+    int64_t n_rows, n_parents;
+    int n_tiles, h_blocks, bpp, n_phases, kchunks, uk, tf32;
+    void* out; int out_bf16; int64_t ld_out;
+    int* err;
+};
+
+struct QMaps { CUtensorMap w; CUtensorMap a; };
+
+// one parent's pooled value -> HBM (relu applied here for the max pool: once per parent instead of once per element)
+template <bool POOL_MAX>
+__device__ __forceinline__ void q_store(const QParams& P, int64_t parent, int h, float acc, float bias) {
+    const float o = POOL_MAX ? fmaxf(acc + bias, 0.0f) : acc * (1.0f / (float)P.S);
+    const int64_t at = parent * P.ld_out + P.col0 + h;
+    if (P.out_bf16) reinterpret_cast<__nv_bfloat16*>(P.out)[at] = __float2bfloat16_rn(o);
+    else reinterpret_cast<float*>(P.out)[at] = o;
+}
+
+template <bool POOL_MAX, int S_CT>
+__global__ void __launch_bounds__(kQThreads, 1) linear_pool_ws_umma_kernel(const QParams P, const __grid_constant__ QMaps M) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    // carve: [W of a phase: bpp x kchunks x 16 KB] [ring: 8 x 8 KB row chunks] [barriers]
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint8_t* ring = smem + (size_t)P.bpp * P.kchunks * kQWChunk;
+    uint64_t* bars = (uint64_t*)(ring + kQStages * kQRChunk);
+    uint32_t* tmem_slot = (uint32_t*)(bars + 2 * kQStages + 6);
+    const uint32_t bar_base = smem_u32(bars);
+    auto full_bar = [&](int s) { return bar_base + 8u * s; };
+    auto empty_bar = [&](int s) { return bar_base + 8u * (kQStages + s); };
+    auto tfull_bar = [&](int b) { return bar_base + 8u * (2 * kQStages + b); };
+    auto tempty_bar = [&](int b) { return bar_base + 8u * (2 * kQStages + 2 + b); };
+    const uint32_t wfull_bar = bar_base + 8u * (2 * kQStages + 4), wempty_bar = bar_base + 8u * (2 * kQStages + 5);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kQStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+        for (int b = 0; b < 2; ++b) { mbar_init(tfull_bar(b), 1); mbar_init(tempty_bar(b), 32 * kQEpiWarps); }
+        mbar_init(wfull_bar, 1); mbar_init(wempty_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == kQEpiWarps) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp < kQEpiWarps) {
+        // ============ EPILOGUE: one hidden unit per thread, the pool runs along the accumulator columns ============
+        const int quarter = warp & 3, slot = warp >> 2;        // TMEM lane quarter; hidden block of the phase
+        const int S = S_CT > 0 ? S_CT : P.S;
+        const int PT = S_CT > 0 ? QN / S_CT : P.PT;
+        int it = 0;
+        for (int ph = 0; ph < P.n_phases; ++ph) {
+            const int hb = ph * P.bpp + slot;
+            const bool mine = slot < P.bpp && hb < P.h_blocks;
+            const int h = hb * QM + quarter * 32 + lane;
+            const bool h_ok = mine && h < P.H;
+            const float bias = (P.bias && h_ok) ? __ldg(P.bias + h) : 0.0f;
+            for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x, ++it) {
+                const int buf = it & 1;
+                mbar_wait(tfull_bar(buf), (it >> 1) & 1, P.err);
+                tc_fence_after();
+                if (mine) {
+                    const int64_t parent0 = (int64_t)tile * PT;
+                    const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * 256 + slot * QN);
+                    uint32_t r0[32], r1[32];
+                    tmem_ld32(taddr, r0);
+                    tmem_ld32(taddr + 32, r1);
+                    tmem_ld_wait();
+                    if (S_CT > 0) {
+                        // static parent boundaries: element i of the tile belongs to parent i / S_CT
+#pragma unroll
+                        for (int p = 0; p < QN / (S_CT > 0 ? S_CT : 1); ++p) {
+                            float acc = POOL_MAX ? -3.0e38f : 0.0f;
+#pragma unroll
+                            for (int j = 0; j < (S_CT > 0 ? S_CT : 1); ++j) {
+                                const int i = p * S_CT + j;
+                                const float v = __uint_as_float(i < 32 ? r0[i & 31] : r1[i & 31]);
+                                if (POOL_MAX) acc = fmaxf(acc, v);
+                                else acc += fmaxf(v + bias, 0.0f);
+                            }
+                            if (h_ok && parent0 + p < P.n_parents) q_store<POOL_MAX>(P, parent0 + p, h, acc, bias);
+                        }
+                    } else {
+                        float acc = POOL_MAX ? -3.0e38f : 0.0f;
+                        int cnt = 0, p = 0;
+#pragma unroll
+                        for (int i = 0; i < QN; ++i) {
+                            if (i < P.R) {
+                                const float v = __uint_as_float(i < 32 ? r0[i & 31] : r1[i & 31]);
+                                if (POOL_MAX) acc = fmaxf(acc, v);
+                                else acc += fmaxf(v + bias, 0.0f);
+                                if (++cnt == S) {
+                                    if (h_ok && parent0 + p < P.n_parents) q_store<POOL_MAX>(P, parent0 + p, h, acc, bias);
+                                    ++p; cnt = 0;
+                                    acc = POOL_MAX ? -3.0e38f : 0.0f;
+                                }
+                            }
+                        }
+                    }
+                }
+                tc_fence_before();
+                mbar_arrive(tempty_bar(buf));
+            }
+        }
+    } else if (warp == kQEpiWarps) {
+        // ============ MMA ISSUER: D[buf][blk][hidden, row] += W[blk][kc] . rows[kc]^T, one thread, lean loop ============
+        if (lane == 0) {
+            const uint32_t fmt = P.tf32 ? 2u : 1u;
+            const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(QN >> 3) << 17) | ((uint32_t)(QM >> 4) << 24);
+            const uint64_t desc_hi = umma_desc(0);
+            const uint32_t ring16 = (smem_u32(ring) & 0x3FFFF) >> 4, w16 = (smem_u32(smem) & 0x3FFFF) >> 4;
+            const int kchunks = P.kchunks;
+            uint32_t stage = 0, par = 0, b16 = ring16;
+            int it = 0;
+            for (int ph = 0; ph < P.n_phases; ++ph) {
+                const int nb = min(P.bpp, P.h_blocks - ph * P.bpp);
+                mbar_wait(wfull_bar, ph & 1, P.err);
+                for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x, ++it) {
+                    const uint32_t buf = it & 1;
+                    mbar_wait(tempty_bar(buf), ((it >> 1) & 1) ^ 1, P.err);
+                    tc_fence_after();
+                    const uint32_t d0 = tmem_base + buf * 256u;
+                    for (int kc = 0; kc < kchunks; ++kc) {
+                        mbar_wait(full_bar(stage), par, P.err);
+                        tc_fence_after();
+                        const uint64_t bdesc = desc_hi | (uint64_t)b16;
+                        for (int j = 0; j < nb; ++j) {
+                            const uint64_t adesc = desc_hi | (uint64_t)(w16 + (uint32_t)(j * kchunks + kc) * (kQWChunk >> 4));
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) {
+                                if (P.tf32) umma_tf32(d0 + j * QN, adesc + 2 * k, bdesc + 2 * k, idesc, (kc | k) ? 1u : 0u);
+                                else umma_bf16(d0 + j * QN, adesc + 2 * k, bdesc + 2 * k, idesc, (kc | k) ? 1u : 0u);
+                            }
+                        }
+                        umma_commit(empty_bar(stage));
+                        if (++stage == kQStages) { stage = 0; par ^= 1; b16 = ring16; } else b16 += (kQRChunk >> 4);
+                    }
+                    umma_commit(tfull_bar(buf));
+                }
+                umma_commit(wempty_bar);
+            }
+        }
+        __syncwarp();
+    } else {
+        // ============ TMA PRODUCERS ============
+        const int pw = warp - (kQEpiWarps + 1);
+        const bool lead = pw == 0 && lane == 0;
+        const uint32_t ring_u = smem_u32(ring);
+        const int uk = P.uk, kchunks = P.kchunks;
+        const int my_row = 16 * pw + 4 * lane;                 // gather: lanes 0..3 of producer pw own tile rows my_row .. + 3
+        uint32_t stage = 0, par = 1, sa_u = ring_u;
+        for (int ph = 0; ph < P.n_phases; ++ph) {
+            if (lead) {
+                const int nb = min(P.bpp, P.h_blocks - ph * P.bpp);
+                mbar_wait(wempty_bar, (ph & 1) ^ 1, P.err);
+                mbar_arrive_expect_tx(wfull_bar, (uint32_t)(nb * kchunks * kQWChunk));
+                for (int j = 0; j < nb; ++j)
+                    for (int kc = 0; kc < kchunks; ++kc)
+                        tma_load_2d(smem_u32(smem) + (uint32_t)(j * kchunks + kc) * kQWChunk, &M.w, kc * uk, (ph * P.bpp + j) * QM, wfull_bar);
+            }
+            for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x) {
+                const int64_t row0 = (int64_t)tile * P.R;
+                if (P.ids) {
+                    int r0 = 0, r1 = 0, r2 = 0, r3 = 0;
+                    const bool glane = lane < 4;
+                    if (glane) {
+                        const int64_t base = row0 + my_row;
+                        if (my_row + 0 < P.R && base + 0 < P.n_rows) r0 = (int)__ldg(P.ids + base + 0);
+                        if (my_row + 1 < P.R && base + 1 < P.n_rows) r1 = (int)__ldg(P.ids + base + 1);
+                        if (my_row + 2 < P.R && base + 2 < P.n_rows) r2 = (int)__ldg(P.ids + base + 2);
+                        if (my_row + 3 < P.R && base + 3 < P.n_rows) r3 = (int)__ldg(P.ids + base + 3);
+                    }
+                    const uint32_t row_off = (uint32_t)my_row * 128u;
+                    for (int kc = 0, col = 0; kc < kchunks; ++kc, col += uk) {
+                        mbar_wait(empty_bar(stage), par, P.err);
+                        const uint32_t fb = full_bar(stage);
+                        if (lead) mbar_arrive_expect_tx(fb, (uint32_t)kQRChunk);
+                        if (glane) tma_gather4(sa_u + row_off, &M.a, col, r0, r1, r2, r3, fb);
+                        if (++stage == kQStages) { stage = 0; par ^= 1; sa_u = ring_u; } else sa_u += kQRChunk;
+                    }
+                } else {
+                    for (int kc = 0, col = 0; kc < kchunks; ++kc, col += uk) {
+                        if (lead) {
+                            mbar_wait(empty_bar(stage), par, P.err);
+                            mbar_arrive_expect_tx(full_bar(stage), (uint32_t)kQRChunk);
+                            tma_load_2d(sa_u, &M.a, col, (int)row0, full_bar(stage));
+                        }
+                        if (++stage == kQStages) { stage = 0; par ^= 1; sa_u = ring_u; } else sa_u += kQRChunk;
+                    }
+                }
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == kQEpiWarps) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    }
+}
+
+// ---- host -------------------------------------------------------------------------------------------------
+static int q_blocks_per_phase(const LinearParams& P) {
+    const LinearSeg& s = P.seg[0];
+    const int es = s.a_dtype == GSAGE_BF16 ? 2 : 4, uk = 128 / es;
+    const int kchunks = (s.d + uk - 1) / uk;
+    const int budget = kQSmemLimit - 2048 - kQStages * kQRChunk;
+    int bpp = budget / (kchunks * kQWChunk);
+    const int h_blocks = (s.O + QM - 1) / QM;
+    if (bpp > kQMaxBlocks) bpp = kQMaxBlocks;
+    if (bpp > h_blocks) bpp = h_blocks;
+    return bpp;
+}
+
+bool linear_pool_ws_umma_eligible(const LinearParams& P) {
+    if (getenv("GSAGE_NO_POOL_WS")) return false;
+    if (!linear_pool_umma_eligible(P)) return false;
+    if (P.act != GSAGE_ACT_RELU || P.pool_S > QN) return false;
+    return q_blocks_per_phase(P) >= 1;
+}
+
+static int* g_q_err = nullptr;
+
+int linear_pool_ws_umma_launch(const LinearParams& P, cudaStream_t s) {
+    const LinearSeg& g = P.seg[0];
+    QParams U;
+    memset(&U, 0, sizeof(U));
+    U.a = g.a; U.lda = g.lda; U.ids = g.ids; U.bias = g.bias; U.col0 = g.col0;
+    U.d = g.d; U.H = g.O; U.S = P.pool_S;
+    U.PT = QN / U.S; U.R = U.PT * U.S;
+    U.n_rows = P.n; U.n_parents = P.n / P.pool_S;
+    U.tf32 = g.a_dtype == GSAGE_F32 ? 1 : 0;
+    U.uk = U.tf32 ? 32 : 64;
+    U.kchunks = (U.d + U.uk - 1) / U.uk;
+    U.n_tiles = (int)ceil_div(U.n_parents, U.PT);
+    U.h_blocks = (U.H + QM - 1) / QM;
+    U.bpp = q_blocks_per_phase(P);
+    GS_CHECK_ARG(U.bpp >= 1, "linear_pool_ws_umma: one hidden block of W does not fit in shared memory");
+    U.n_phases = (U.h_blocks + U.bpp - 1) / U.bpp;
+    U.out = P.out; U.out_bf16 = P.out_dtype == GSAGE_BF16; U.ld_out = P.ld_out;
+    if (!g_q_err) {
+        GS_CUDA(cudaMalloc((void**)&g_q_err, sizeof(int)));
+        GS_CUDA(cudaMemset(g_q_err, 0, sizeof(int)));
+    }
+    U.err = g_q_err;
+    const int es = U.tf32 ? 4 : 2;
+    QMaps maps;
+    memset(&maps, 0, sizeof(maps));
+    GS_TRY(make_map(&maps.w, g.w, g.O, g.d, g.ldw, QM, es));
+    if (g.ids) GS_TRY(make_map(&maps.a, g.a, 0x7FFFFFFF, g.d, g.lda, 1, es));
+    else GS_TRY(make_map(&maps.a, g.a, P.n, g.d, g.lda, QN, es));
+    const size_t smem = (size_t)U.bpp * U.kchunks * kQWChunk + (size_t)kQStages * kQRChunk + 1024 + 512;
+    const int grid = U.n_tiles < sm_count() ? U.n_tiles : sm_count();
+#define GS_Q_LAUNCH(MX, SCT)                                                                                                       \
+    do {                                                                                                                           \
+        static bool attr_set = false;                                                                                              \
+        if (!attr_set) {                                                                                                           \
+            GS_CUDA(cudaFuncSetAttribute(linear_pool_ws_umma_kernel<MX, SCT>, cudaFuncAttributeMaxDynamicSharedMemorySize, kQSmemLimit)); \
+            attr_set = true;                                                                                                       \
+        }                                                                                                                          \
+        linear_pool_ws_umma_kernel<MX, SCT><<<grid, kQThreads, smem, s>>>(U, maps);                                                \
+    } while (0)
+    const bool mx = P.pool_max != 0;
+    if (U.S == 10) { if (mx) GS_Q_LAUNCH(true, 10); else GS_Q_LAUNCH(false, 10); }
+    else if (U.S == 25) { if (mx) GS_Q_LAUNCH(true, 25); else GS_Q_LAUNCH(false, 25); }
+    else { if (mx) GS_Q_LAUNCH(true, 0); else GS_Q_LAUNCH(false, 0); }
+#undef GS_Q_LAUNCH
+    GS_LAUNCHED();
+    return GSAGE_OK;
+}
+
+}  // namespace gsage

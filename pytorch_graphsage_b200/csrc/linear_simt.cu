@@ -145,6 +145,7 @@ int linear_dispatch(const LinearParams& P, int exact, cudaStream_t s) {
     if (P.pool_S > 1) {
         GS_CHECK_ARG(!exact && linear_pool_umma_eligible(P), "linear: the fused MLP+pool needs operands that qualify for the tensor-core kernel "
                      "(bf16 or fp32-as-TF32, 16-byte aligned rows, one segment)");
+        if (linear_pool_ws_umma_eligible(P)) return linear_pool_ws_umma_launch(P, s);
         return linear_pool_umma_launch(P, s);
     }
     bool tc = !exact;

@@ -240,7 +240,8 @@ def test_umma_tf32_projection(g, n, d, O):
     np.testing.assert_allclose(exact.cpu().numpy(), want.numpy(), rtol=1e-4, atol=1e-5)
 
 
-@pytest.mark.parametrize('n,S,d,H', [(100, 10, 64, 512), (37, 25, 64, 512), (513, 3, 100, 32), (8, 128, 64, 48)])
+@pytest.mark.parametrize('n,S,d,H', [(100, 10, 64, 512), (37, 25, 64, 512), (513, 3, 100, 32), (8, 128, 64, 48), (3000, 10, 256, 512),
+                                     (257, 25, 256, 512), (1000, 10, 602, 512), (50, 64, 64, 200), (64, 2, 72, 136)])
 @pytest.mark.parametrize('reduce', ['max', 'mean'])
 def test_umma_pooled_epilogue(g, n, S, d, H, reduce):
     """relu(MLP) on tcgen05 with the max / mean over the S neighbour rows of each parent done in the epilogue."""
