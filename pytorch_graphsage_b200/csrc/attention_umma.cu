@@ -118,18 +118,25 @@ __global__ void __launch_bounds__(kAtThreads, 1) attention_fused_kernel(const At
                 float xa[16];
 #pragma unroll
                 for (int q = 0; q < 4; ++q) { const float4 v = __ldg(xav + q); xa[4 * q] = v.x; xa[4 * q + 1] = v.y; xa[4 * q + 2] = v.z; xa[4 * q + 3] = v.w; }
+                // 16 independent accumulators (the first version ran one 32-long dependent FFMA chain per output and was
+                // latency-bound: 60 % of the kernel's samples); W2 rows come from smem as warp-uniform broadcast LDS.128
+                float acc[16];
 #pragma unroll
-                for (int o = 0; o < 16; ++o) {
-                    const float4* wrow = reinterpret_cast<const float4*>(w2s + (half * 16 + o) * AH);     // warp-uniform: broadcast
-                    float acc = 0.0f;
+                for (int o = 0; o < 16; ++o) acc[o] = 0.0f;
+                const uint32_t w2_u = smem_u32(w2s) + (uint32_t)(half * 16 * AH * 4);
 #pragma unroll
-                    for (int q = 0; q < AH / 4; ++q) {
-                        const float4 w = wrow[q];
-                        acc = fmaf(w.x, t[4 * q], acc); acc = fmaf(w.y, t[4 * q + 1], acc);
-                        acc = fmaf(w.z, t[4 * q + 2], acc); acc = fmaf(w.w, t[4 * q + 3], acc);
+                for (int q = 0; q < AH / 4; ++q) {
+#pragma unroll
+                    for (int o = 0; o < 16; ++o) {
+                        float4 w;
+                        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(w.x), "=f"(w.y), "=f"(w.z), "=f"(w.w)
+                                     : "r"(w2_u + (uint32_t)((o * AH + 4 * q) * 4)));
+                        acc[o] = fmaf(w.x, t[4 * q], acc[o]); acc[o] = fmaf(w.y, t[4 * q + 1], acc[o]);
+                        acc[o] = fmaf(w.z, t[4 * q + 2], acc[o]); acc[o] = fmaf(w.w, t[4 * q + 3], acc[o]);
                     }
-                    part = fmaf(acc, xa[o], part);
                 }
+#pragma unroll
+                for (int o = 0; o < 16; ++o) part = fmaf(acc[o], xa[o], part);
             }
             sc[half * 128 + row] = part;
             asm volatile("bar.sync 1, 256;" ::: "memory");

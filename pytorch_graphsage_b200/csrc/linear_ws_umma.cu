@@ -14,8 +14,8 @@
 //           range of the output, the activation is elementwise, so the result is identical)
 //   warps 0-3  epilogue   tcgen05.ld -> bias / activation -> bf16 | fp32 -> HBM
 //   warp  4    MMA issue  tcgen05.mma M=128, N=O, K=16 (bf16) | 8 (tf32); A from the stage ring, B from the resident W
-//   warps 5-8  TMA issue  W of the phase (one expect_tx for all of it), then per (tile, segment, k-chunk) one A stage:
-//                         cp.async.bulk.tensor.2d (in place, producer 0) or 4 x 8 tile::gather4 (rows by id, all producers)
+//   warps 5-12 TMA issue  W of the phase (one expect_tx for all of it), then per (tile, segment, k-chunk) one A stage:
+//                         cp.async.bulk.tensor.2d (in place, producer 0) or 4 x 8 tile::gather4 (rows by id, 8 producers x 4)
 // Two TMEM accumulator buffers (2 x 256 columns): the epilogue of tile i overlaps the loads and MMAs of tile i+1.
 // Every mbarrier wait is bounded (a stuck pipeline traps instead of hanging the GPU).
 #include "linear.cuh"
@@ -27,7 +27,7 @@ namespace gsage {
 
 static constexpr int WM = 128;                 // rows per tile (UMMA M)
 static constexpr int kWsEpiWarps = 4;
-static constexpr int kWsTmaWarps = 4;             // producers: a lone warp issuing 32 gather4 per stage is the bottleneck (see below)
+static constexpr int kWsTmaWarps = 8;             // producers: a lone warp issuing 32 gather4 per stage is the bottleneck (see below)
 static constexpr int kWsThreads = 32 * (kWsEpiWarps + 1 + kWsTmaWarps);
 static constexpr int kWsABytes = WM * 128;     // one A stage: 128 rows x 128 bytes
 static constexpr int kWsMaxStages = 12;
@@ -220,12 +220,12 @@ __global__ void __launch_bounds__(kWsThreads, 1) linear_ws_umma_kernel(const WsP
         __syncwarp();
     } else {
         // =========================== TMA PRODUCERS ===========================
-        // Four warps walk the same stage sequence.  Producer 0 (lane 0) posts every expect_tx and issues the one-instruction
+        // Eight warps walk the same stage sequence.  Producer 0 (lane 0) posts every expect_tx and issues the one-instruction
         // loads (resident W, in-place A chunks, streamed W chunks).  A chunk gathered BY ID is 32 tile::gather4 instructions
         // with per-instruction row coordinates; TMA operands live in uniform registers, so a warp issues them one lane at
         // a time (~50 cycles each: ncu shows the R2UR / UTMALDG / BRA.U.ANY loop at 43 % of a lone producer warp's samples,
-        // ~1 us per 16 KB stage).  Each producer therefore gathers 32 of the 128 rows: 8 instructions per warp per stage,
-        // on four schedulers at once.  mbarrier transaction counts may go negative, so the byte completions of the other
+        // ~1 us per 16 KB stage).  Each of the eight producers therefore gathers 16 of the 128 rows: 4 instructions per warp
+        // per stage, two warps on each scheduler.  mbarrier transaction counts may go negative, so the byte completions of the other
         // producers need no ordering against producer 0's expect_tx.
         const int pw = warp - (kWsEpiWarps + 1);
         const uint32_t ring_u = smem_u32(a_ring), sb = (uint32_t)P.stage_bytes;
@@ -261,10 +261,11 @@ __global__ void __launch_bounds__(kWsThreads, 1) linear_ws_umma_kernel(const WsP
                     const CUtensorMap* map_w = &M.w[sidx];
                     const int tile_row = tile * WM;
                     if (ids) {
-                        // ---- gathered operand: lanes 0..7 of producer pw own tile rows 32 pw + 4 lane .. + 3 ----
+                        // ---- gathered operand: the first lanes of producer pw own tile rows kRowsPerProducer pw + 4 lane .. + 3 ----
+                        constexpr int kRowsPerProducer = WM / kWsTmaWarps, kGatherLanes = kRowsPerProducer / 4;
                         int r0 = 0, r1 = 0, r2 = 0, r3 = 0;
-                        const int my_row = 32 * pw + 4 * lane;
-                        if (lane < 8) {
+                        const int my_row = kRowsPerProducer * pw + 4 * lane;
+                        if (lane < kGatherLanes) {
                             const int64_t base = (int64_t)tile_row + my_row;
                             if (base + 0 < P.n) r0 = (int)__ldg(ids + base + 0);
                             if (base + 1 < P.n) r1 = (int)__ldg(ids + base + 1);
@@ -276,7 +277,7 @@ __global__ void __launch_bounds__(kWsThreads, 1) linear_ws_umma_kernel(const WsP
                             mbar_wait(empty_bar(stage), par, P.err);
                             const uint32_t fb = full_bar(stage);
                             if (lead) mbar_arrive_expect_tx(fb, (uint32_t)kWsABytes);
-                            if (lane < 8) tma_gather4(sa_u + row_off, map_a, col, r0, r1, r2, r3, fb);
+                            if (lane < kGatherLanes) tma_gather4(sa_u + row_off, map_a, col, r0, r1, r2, r3, fb);
                             if (++stage == n_stages) { stage = 0; par ^= 1; sa_u = ring_u; } else sa_u += sb;
                             if (kc >= kres) {                      // this W chunk is not resident: it streams through the ring too
                                 if (lead) {

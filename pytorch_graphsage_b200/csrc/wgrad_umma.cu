@@ -10,11 +10,12 @@
 // the layout the tensor core wants, and the self rows of fc_x are fetched BY ID from the feature table with
 // tile::gather4, exactly like the forward projection.
 //
-//   unit   = (gemm, N-tile of <= 512 dW columns, K-range of rows); one CTA per unit, grid ~ one wave of 148
+//   unit   = (N-tile of <= 512 dW columns, K-range of rows); one CTA per unit runs every gemm of the launch over it, one
+//            after the other (equal work per CTA); grid ~ one wave of 148
 //   warps 0-3  epilogue   TMEM -> registers -> red.global.add.f32 into dW (fp32; dW is zeroed by the launcher)
 //   warp  4    MMA issue  per 64-row stage: 4 k-steps x (N <= 256) tcgen05.mma.kind::f16, M = 128 = O
-//   warps 5-8  TMA issue  per stage: 2 boxes of G + q boxes of A (in place; producer 0) or 16 x q gather4 (rows by id; four
-//                         producers x 4 row groups -- a lone warp issues one gather4 per ~50 cycles, see linear_ws_umma.cu)
+//   warps 5-12 TMA issue  per stage: 2 boxes of G + q boxes of A (in place; producer 0) or 16 x q gather4 (rows by id; eight
+//                         producers x 2 row groups -- a lone warp issues one gather4 per ~50 cycles, see linear_ws_umma.cu)
 // HBM-bound: every G / A byte is read once per N-tile (G is re-read by the second N-tile when d > 512).
 // Requires bf16 operands, O == 128, 16-byte aligned rows.  Everything else stays on the FFMA kernel (backward.cu).
 #include "backward.cuh"
@@ -27,7 +28,7 @@ namespace gsage {
 static constexpr int GK = 64;                    // rows (reduction index) per stage
 static constexpr int kBox = GK * 128;            // one [64 rows x 64 bf16] box = 8 KB
 static constexpr int kWgEpiWarps = 4;
-static constexpr int kWgTmaWarps = 4;             // gather4 issue is serial per warp (operands in uniform registers): spread it
+static constexpr int kWgTmaWarps = 8;             // gather4 issue is serial per warp (operands in uniform registers): spread it
 static constexpr int kWgThreads = 32 * (kWgEpiWarps + 1 + kWgTmaWarps);
 static constexpr int kWgMaxStages = 6;
 static constexpr int kWgSmemLimit = 227 * 1024;
@@ -65,19 +66,19 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_umma_kernel(const WgParam
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint64_t* bars = (uint64_t*)(smem + (size_t)P.stages * P.stage_bytes);
-    uint32_t* tmem_slot = (uint32_t*)(bars + 2 * kWgMaxStages + 2);
+    uint32_t* tmem_slot = (uint32_t*)(bars + 2 * kWgMaxStages + 3);
     const uint32_t bar_base = smem_u32(bars);
     auto full_bar = [&](int s) { return bar_base + 8u * s; };
     auto empty_bar = [&](int s) { return bar_base + 8u * (kWgMaxStages + s); };
-    const uint32_t done_bar = bar_base + 8u * (2 * kWgMaxStages);
+    const uint32_t done_bar = bar_base + 8u * (2 * kWgMaxStages), drained_bar = bar_base + 8u * (2 * kWgMaxStages + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-    // unit decode: blockIdx.x = (gemm * n_tiles_n + ntile) * ksplit + kpart
+    // unit decode: blockIdx.x = ntile * ksplit + kpart; the CTA runs EVERY gemm of the launch over its K-range, one after
+    // the other (first version: one gemm per CTA -- the CTAs of the in-place gemm finished early and idled while the
+    // gather4-issue-bound CTAs of the by-id gemm were still running)
     const int kpart = blockIdx.x % P.ksplit;
-    const int gt = blockIdx.x / P.ksplit;
-    const int ntile = gt % P.n_tiles_n, gi = gt / P.n_tiles_n;
-    const WgGemm& G = P.gemm[gi];
+    const int ntile = blockIdx.x / P.ksplit;
     const int64_t kt0 = P.ktiles * kpart / P.ksplit, kt1 = P.ktiles * (kpart + 1) / P.ksplit;
     const int n_it = (int)(kt1 - kt0);
     const int col0 = ntile * P.q * 64;                       // first dW column (= A column) of this unit
@@ -85,6 +86,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_umma_kernel(const WgParam
     if (threadIdx.x == 0) {
         for (int s = 0; s < P.stages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
         mbar_init(done_bar, 1);
+        mbar_init(drained_bar, 32 * kWgEpiWarps);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == kWgEpiWarps) {
@@ -99,27 +101,32 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_umma_kernel(const WgParam
     if (warp < kWgEpiWarps) {
         // =========================== EPILOGUE ===========================
         if (n_it > 0) {
-            mbar_wait(done_bar, 0, P.err);
-            tc_fence_after();
-            const int o = warp * 32 + lane;                  // TMEM lane == dW row
-            float* row = G.dW + (int64_t)o * G.lddw;
-            for (int c0 = 0; c0 < P.q * 64; c0 += 32) {
-                if (col0 + c0 >= G.d) break;
-                uint32_t r[32];
-                tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, r);
-                tmem_ld_wait();
+            for (int gi = 0; gi < P.n_gemms; ++gi) {
+                const WgGemm& G = P.gemm[gi];
+                mbar_wait(done_bar, gi & 1, P.err);
+                tc_fence_after();
+                const int o = warp * 32 + lane;                  // TMEM lane == dW row
+                float* row = G.dW + (int64_t)o * G.lddw;
+                for (int c0 = 0; c0 < P.q * 64; c0 += 32) {
+                    if (col0 + c0 >= G.d) break;
+                    uint32_t r[32];
+                    tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, r);
+                    tmem_ld_wait();
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    const int c = col0 + c0 + j;
-                    if (c < G.d) atomicAdd(row + c, __uint_as_float(r[j]));
+                    for (int j = 0; j < 32; ++j) {
+                        const int c = col0 + c0 + j;
+                        if (c < G.d) atomicAdd(row + c, __uint_as_float(r[j]));
+                    }
                 }
+                tc_fence_before();
+                mbar_arrive(drained_bar);                        // the accumulator may be overwritten by the next gemm
             }
         }
     } else if (warp == kWgEpiWarps) {
         // =========================== MMA ISSUER ===========================
         // D (128 x 64q, fp32) += G_tile^T (M = 128, MN-major) . A_tile (N, MN-major); K = 16 rows per instruction.
         // One thread, nothing recomputed per stage (the issue loop is serial latency).
-        if (lane == 0) {
+        if (lane == 0 && n_it > 0) {
             const uint32_t lbo = P.swap_offsets ? 1024u : (uint32_t)kBox, sbo = P.swap_offsets ? (uint32_t)kBox : 1024u;
             const int n_first = P.q > 4 ? 4 : P.q, n_second = P.q - n_first;      // N = 64 * n_first (<= 256), then the rest
             const uint32_t base_idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(128 >> 4) << 24);
@@ -130,20 +137,23 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_umma_kernel(const WgParam
             const uint32_t a_off16 = (2 * kBox) >> 4, b2_off16 = (uint32_t)((2 + n_first) * kBox) >> 4;
             const uint32_t n_stages = (uint32_t)P.stages, d2 = tmem_base + (uint32_t)(64 * n_first);
             uint32_t stage = 0, par = 0, g16 = ring16;
-            for (int it = 0; it < n_it; ++it) {
-                mbar_wait(full_bar(stage), par, P.err);
-                tc_fence_after();
-                const uint64_t gdesc = desc_hi | (uint64_t)g16;
+            for (int gi = 0; gi < P.n_gemms; ++gi) {
+                if (gi > 0) { mbar_wait(drained_bar, (gi - 1) & 1, P.err); tc_fence_after(); }
+                for (int it = 0; it < n_it; ++it) {
+                    mbar_wait(full_bar(stage), par, P.err);
+                    tc_fence_after();
+                    const uint64_t gdesc = desc_hi | (uint64_t)g16;
 #pragma unroll
-                for (int j = 0; j < GK / 16; ++j) {          // 16 rows = two 8-row atoms = 2048 bytes (128 x 16 B) further down every box
-                    const uint32_t acc = (it | j) ? 1u : 0u;
-                    umma_bf16(tmem_base, gdesc + 128 * j, gdesc + a_off16 + 128 * j, idesc1, acc);
-                    if (n_second > 0) umma_bf16(d2, gdesc + 128 * j, gdesc + b2_off16 + 128 * j, idesc2, acc);
+                    for (int j = 0; j < GK / 16; ++j) {          // 16 rows = two 8-row atoms = 2048 bytes (128 x 16 B) further down every box
+                        const uint32_t acc = (it | j) ? 1u : 0u;
+                        umma_bf16(tmem_base, gdesc + 128 * j, gdesc + a_off16 + 128 * j, idesc1, acc);
+                        if (n_second > 0) umma_bf16(d2, gdesc + 128 * j, gdesc + b2_off16 + 128 * j, idesc2, acc);
+                    }
+                    umma_commit(empty_bar(stage));
+                    if (++stage == n_stages) { stage = 0; par ^= 1; g16 = ring16; } else g16 += sb16;
                 }
-                umma_commit(empty_bar(stage));
-                if (++stage == n_stages) { stage = 0; par ^= 1; g16 = ring16; } else g16 += sb16;
+                umma_commit(done_bar);
             }
-            if (n_it > 0) umma_commit(done_bar);
         }
         __syncwarp();
     } else {
@@ -152,33 +162,36 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_umma_kernel(const WgParam
         const bool lead = pw == 0 && lane == 0;
         const uint32_t ring_u = smem_u32(smem), sb = (uint32_t)P.stage_bytes;
         const uint32_t n_stages = (uint32_t)P.stages;
-        const int64_t* ids = G.ids;
-        // gather: lane -> (row group g of this producer's four, box b): rows r0 + 4 (4 pw + g) .. + 3, columns col0 + 64 b
+        // gather: lane -> (row group g of this producer's kGroups, box b): rows r0 + 4 (kGroups pw + g) .. + 3, columns col0 + 64 b
+        constexpr int kGroups = GK / 4 / kWgTmaWarps;
         const int gq = lane / P.q, gb = lane - gq * P.q;
-        const bool gather_lane = ids != nullptr && lane < 4 * P.q;
-        const int grp = 4 * pw + gq;
+        const int grp = kGroups * pw + gq;
         uint32_t stage = 0, par = 1, g_addr = ring_u;
-        for (int it = 0; it < n_it; ++it) {
-            const int64_t r0 = (kt0 + it) * GK;
-            int i0 = 0, i1 = 0, i2 = 0, i3 = 0;
-            if (gather_lane) {
-                const int64_t base = r0 + 4 * grp;
-                if (base + 0 < P.n) i0 = (int)__ldg(ids + base + 0);
-                if (base + 1 < P.n) i1 = (int)__ldg(ids + base + 1);
-                if (base + 2 < P.n) i2 = (int)__ldg(ids + base + 2);
-                if (base + 3 < P.n) i3 = (int)__ldg(ids + base + 3);
+        for (int gi = 0; gi < P.n_gemms; ++gi) {
+            const int64_t* ids = P.gemm[gi].ids;
+            const bool gather_lane = ids != nullptr && lane < kGroups * P.q;
+            for (int it = 0; it < n_it; ++it) {
+                const int64_t r0 = (kt0 + it) * GK;
+                int i0 = 0, i1 = 0, i2 = 0, i3 = 0;
+                if (gather_lane) {
+                    const int64_t base = r0 + 4 * grp;
+                    if (base + 0 < P.n) i0 = (int)__ldg(ids + base + 0);
+                    if (base + 1 < P.n) i1 = (int)__ldg(ids + base + 1);
+                    if (base + 2 < P.n) i2 = (int)__ldg(ids + base + 2);
+                    if (base + 3 < P.n) i3 = (int)__ldg(ids + base + 3);
+                }
+                if (ids || lead) mbar_wait(empty_bar(stage), par, P.err);
+                const uint32_t fb = full_bar(stage), a_addr = g_addr + 2 * kBox;
+                if (lead) {
+                    mbar_arrive_expect_tx(fb, (uint32_t)P.stage_bytes);
+                    tma_load_2d(g_addr, &M.g[gi], 0, (int)r0, fb);                        // rows past n read as zero
+                    tma_load_2d(g_addr + kBox, &M.g[gi], 64, (int)r0, fb);
+                    if (!ids)
+                        for (int b = 0; b < P.q; ++b) tma_load_2d(a_addr + b * kBox, &M.a[gi], col0 + 64 * b, (int)r0, fb);
+                }
+                if (gather_lane) tma_gather4(a_addr + gb * kBox + grp * 512, &M.a[gi], col0 + 64 * gb, i0, i1, i2, i3, fb);
+                if (++stage == n_stages) { stage = 0; par ^= 1; g_addr = ring_u; } else g_addr += sb;
             }
-            if (ids || lead) mbar_wait(empty_bar(stage), par, P.err);
-            const uint32_t fb = full_bar(stage), a_addr = g_addr + 2 * kBox;
-            if (lead) {
-                mbar_arrive_expect_tx(fb, (uint32_t)P.stage_bytes);
-                tma_load_2d(g_addr, &M.g[gi], 0, (int)r0, fb);                            // rows past n read as zero
-                tma_load_2d(g_addr + kBox, &M.g[gi], 64, (int)r0, fb);
-                if (!ids)
-                    for (int b = 0; b < P.q; ++b) tma_load_2d(a_addr + b * kBox, &M.a[gi], col0 + 64 * b, (int)r0, fb);
-            }
-            if (gather_lane) tma_gather4(a_addr + gb * kBox + grp * 512, &M.a[gi], col0 + 64 * gb, i0, i1, i2, i3, fb);
-            if (++stage == n_stages) { stage = 0; par ^= 1; g_addr = ring_u; } else g_addr += sb;
         }
     }
 
@@ -217,7 +230,7 @@ int wgrad_umma_launch(const WgradJob* jobs, int n_jobs, cudaStream_t s) {
     U.n_tiles_n = (boxes + 7) / 8;
     U.q = (boxes + U.n_tiles_n - 1) / U.n_tiles_n;
     U.n_gemms = n_jobs; U.n = jobs[0].n; U.ktiles = ceil_div(U.n, GK);
-    const int units = n_jobs * U.n_tiles_n;
+    const int units = U.n_tiles_n;                         // every CTA runs all jobs over its K-range
     int ksplit = sm_count() / units;
     if (ksplit < 1) ksplit = 1;
     if (ksplit > U.ktiles) ksplit = (int)U.ktiles;
