@@ -103,20 +103,56 @@ __global__ void __launch_bounds__(256) l2_normalize_bwd_kernel(const float* __re
     }
 }
 
-// dH[r, c]: r < n0 -> dh0[r, c];  r >= n0 -> dm2[(r - n0) / S, c] / S;  times act'(H[r, c])
+// dH[r, c]: r < n0 -> dh0[r, c];  r >= n0 -> dm2[(r - n0) / S, c] / S;  times act'(H[r, c]).
+// One warp per row, 8 columns per lane per pass (16-byte loads of H, 16- or 32-byte stores): the first version (one
+// element per thread, a 64-bit division each) ran at 0.8 TB/s -- 0.56 ms of the 3.1 ms train step.
 __global__ void __launch_bounds__(256) layer1_grad_kernel(const float* __restrict__ dh0, const float* __restrict__ dm2,
                                                           const void* __restrict__ H, int h_dtype, int64_t ldh, int64_t n0,
                                                           int64_t n1, int S, int width, int act, void* __restrict__ dH, int dh_bf16) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= (n0 + n1) * width) return;
-    const int64_t r = i / width;
-    const int c = (int)(i - r * width);
-    float g = r < n0 ? dh0[r * width + c] : dm2[((r - n0) / S) * width + c] * (1.0f / (float)S);
-    const float h = ld_any(H, h_dtype, r * ldh + c);
-    if (act == GSAGE_ACT_RELU) g = h > 0.0f ? g : 0.0f;
-    else if (act == GSAGE_ACT_TANH) g *= (1.0f - h * h);
-    if (dh_bf16) reinterpret_cast<__nv_bfloat16*>(dH)[i] = __float2bfloat16_rn(g);     // operand of the tensor-core wgrad
-    else reinterpret_cast<float*>(dH)[i] = g;
+    const int lane = threadIdx.x & 31;
+    const int64_t r = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (r >= n0 + n1) return;
+    const bool seed = r < n0;
+    const float* g_row = seed ? dh0 + r * width : dm2 + ((r - n0) / S) * width;
+    const float scale = seed ? 1.0f : 1.0f / (float)S;
+    for (int c = lane * 8; c < width; c += 256) {
+        float g[8], h[8];
+        if ((width & 7) == 0 && (ldh & 7) == 0) {
+            const float4 a = *reinterpret_cast<const float4*>(g_row + c), b = *reinterpret_cast<const float4*>(g_row + c + 4);
+            g[0] = a.x; g[1] = a.y; g[2] = a.z; g[3] = a.w; g[4] = b.x; g[5] = b.y; g[6] = b.z; g[7] = b.w;
+            if (h_dtype == GSAGE_BF16) {
+                const uint4 v = *reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(H) + r * ldh + c);
+                ElemTraits<__nv_bfloat16>::unpack(v, h);
+            } else {
+                const float* hp = reinterpret_cast<const float*>(H) + r * ldh + c;
+#pragma unroll
+                for (int e = 0; e < 8; ++e) h[e] = hp[e];
+            }
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                float v = g[e] * scale;
+                if (act == GSAGE_ACT_RELU) v = h[e] > 0.0f ? v : 0.0f;
+                else if (act == GSAGE_ACT_TANH) v *= (1.0f - h[e] * h[e]);
+                g[e] = v;
+            }
+            if (dh_bf16) {
+                *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(dH) + r * width + c) = ElemTraits<__nv_bfloat16>::pack(g);
+            } else {
+                float* o = reinterpret_cast<float*>(dH) + r * width + c;
+                *reinterpret_cast<float4*>(o) = make_float4(g[0], g[1], g[2], g[3]);
+                *reinterpret_cast<float4*>(o + 4) = make_float4(g[4], g[5], g[6], g[7]);
+            }
+        } else {
+            for (int e = 0; e < 8 && c + e < width; ++e) {        // rows that are not 16-byte aligned: scalar
+                float v = g_row[c + e] * scale;
+                const float hv = ld_any(H, h_dtype, r * ldh + c + e);
+                if (act == GSAGE_ACT_RELU) v = hv > 0.0f ? v : 0.0f;
+                else if (act == GSAGE_ACT_TANH) v *= (1.0f - hv * hv);
+                if (dh_bf16) reinterpret_cast<__nv_bfloat16*>(dH)[r * width + c + e] = __float2bfloat16_rn(v);
+                else reinterpret_cast<float*>(dH)[r * width + c + e] = v;
+            }
+        }
+    }
 }
 
 __global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ x, int64_t n, int d, float* __restrict__ out) {
@@ -159,7 +195,8 @@ int layer1_grad_launch(const float* dh0, const float* dm2, const void* H, int h_
                        int width, int act, void* dH, int dh_dtype, cudaStream_t s) {
     const int64_t total = (n0 + n1) * width;
     if (total == 0) return GSAGE_OK;
-    layer1_grad_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, s>>>(dh0, dm2, H, h_dtype, ldh, n0, n1, S, width, act, dH,
+    GS_CHECK_ARG(ldh >= width, "layer1_grad: ldh < width");
+    layer1_grad_kernel<<<(unsigned)ceil_div(n0 + n1, 8), 256, 0, s>>>(dh0, dm2, H, h_dtype, ldh, n0, n1, S, width, act, dH,
                                                                      dh_dtype == GSAGE_BF16 ? 1 : 0);
     GS_LAUNCHED();
     return GSAGE_OK;

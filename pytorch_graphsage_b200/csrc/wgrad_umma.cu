@@ -67,6 +67,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_umma_kernel(const WgParam
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint64_t* bars = (uint64_t*)(smem + (size_t)P.stages * P.stage_bytes);
     uint32_t* tmem_slot = (uint32_t*)(bars + 2 * kWgMaxStages + 3);
+    float* scratch = (float*)(bars + 2 * kWgMaxStages + 4);          // 128 x 33 floats: the epilogue's transpose buffer
     const uint32_t bar_base = smem_u32(bars);
     auto full_bar = [&](int s) { return bar_base + 8u * s; };
     auto empty_bar = [&](int s) { return bar_base + 8u * (kWgMaxStages + s); };
@@ -105,18 +106,26 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_umma_kernel(const WgParam
                 const WgGemm& G = P.gemm[gi];
                 mbar_wait(done_bar, gi & 1, P.err);
                 tc_fence_after();
-                const int o = warp * 32 + lane;                  // TMEM lane == dW row
-                float* row = G.dW + (int64_t)o * G.lddw;
+                // TMEM lane == dW row, so a thread holds 32 columns of ONE row: adding them straight to dW would make every
+                // warp-level RED touch 32 different 128-byte lines (12 M L2 atomic requests per launch, all CTAs on the same
+                // 300 KB).  Transpose each 128 x 32 chunk through shared memory instead: a warp then adds 32 consecutive
+                // floats of one row -- one line per request, 32x fewer requests.
+                const int o = warp * 32 + lane;
                 for (int c0 = 0; c0 < P.q * 64; c0 += 32) {
                     if (col0 + c0 >= G.d) break;
                     uint32_t r[32];
                     tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, r);
                     tmem_ld_wait();
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        const int c = col0 + c0 + j;
-                        if (c < G.d) atomicAdd(row + c, __uint_as_float(r[j]));
+                    for (int j = 0; j < 32; ++j) scratch[o * 33 + j] = __uint_as_float(r[j]);
+                    asm volatile("bar.sync 1, 128;" ::: "memory");
+                    const int c = col0 + c0 + lane;
+                    if (c < G.d) {
+#pragma unroll 8
+                        for (int rr = warp; rr < 128; rr += kWgEpiWarps)
+                            atomicAdd(G.dW + (int64_t)rr * G.lddw + c, scratch[rr * 33 + lane]);
                     }
+                    asm volatile("bar.sync 1, 128;" ::: "memory");
                 }
                 tc_fence_before();
                 mbar_arrive(drained_bar);                        // the accumulator may be overwritten by the next gemm
@@ -236,7 +245,8 @@ int wgrad_umma_launch(const WgradJob* jobs, int n_jobs, cudaStream_t s) {
     if (ksplit > U.ktiles) ksplit = (int)U.ktiles;
     U.ksplit = ksplit;
     U.stage_bytes = (2 + U.q) * kBox;
-    U.stages = (kWgSmemLimit - 2048) / U.stage_bytes;
+    const int kScratch = 128 * 33 * 4;
+    U.stages = (kWgSmemLimit - 2048 - kScratch) / U.stage_bytes;
     if (U.stages > kWgMaxStages) U.stages = kWgMaxStages;
     GS_CHECK_ARG(U.stages >= 2, "wgrad_umma: stage too large");
     if (const char* e = getenv("GSAGE_WGRAD_SWAP")) U.swap_offsets = atoi(e);
@@ -253,7 +263,7 @@ int wgrad_umma_launch(const WgradJob* jobs, int n_jobs, cudaStream_t s) {
         if (jobs[i].ids) GS_TRY(make_map(&maps.a[i], jobs[i].A, 0x7FFFFFFF, d, jobs[i].lda, 1, 2));       // rows by id (tile::gather4)
         else GS_TRY(make_map(&maps.a[i], jobs[i].A, U.n, d, jobs[i].lda, GK, 2));
     }
-    const size_t smem = (size_t)U.stages * U.stage_bytes + 1024 + 256;
+    const size_t smem = (size_t)U.stages * U.stage_bytes + 1024 + 256 + kScratch;
     static bool attr_set = false;
     if (!attr_set) {
         GS_CUDA(cudaFuncSetAttribute(wgrad_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWgSmemLimit));
