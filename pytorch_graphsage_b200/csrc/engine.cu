@@ -103,6 +103,9 @@ struct gsage_engine {
     int64_t* ids_slot[2] = {nullptr, nullptr}; int cur = 0; uint32_t* sel_ahead = nullptr;
     cudaStream_t ss = nullptr; cudaEvent_t ev_ahead = nullptr;
     cudaEvent_t ev_done[2] = {nullptr, nullptr}; bool done_valid[2] = {false, false};   // last reader of each id slot (forward / backward) finished
+    // mean aggregator: the sample-ahead stream starts AFTER the dominant (HBM-bound) gather+mean launch of the forward in
+    // flight, so its kernels share the SMs with the projection / layer-2 tail instead of slowing the bandwidth-bound kernel
+    cudaEvent_t ev_mid = nullptr; bool mid_valid = false; int ahead_after_gather = 1;
     struct Ahead { bool valid = false; const void* src = nullptr; int64_t B = 0, global_B = 0, first = 0;
                    gsage_graph* g = nullptr; gsage_rng* rng = nullptr; } ahead;
     void* X = nullptr;                  // materialised prepped rows (non-identity preps)
@@ -206,6 +209,11 @@ static int apply_aggregator(gsage_engine* e, int layer, const RowSrc& x, const R
         GS_TRY(gather_reduce_launch(nb.base, nb.dtype, nb.ld, nb.table_rows, d, nb.ids, n, S, GSAGE_RED_MEAN, nullptr, Mb, T, ldm, s,
                                     (e->l2_hint && !e->keep_activations) ? 1 : 0));
         e->prof.end(p_red, s);
+        if (dominant && e->ahead_after_gather) {
+            if (!e->ev_mid) GS_CUDA(cudaEventCreateWithFlags(&e->ev_mid, cudaEventDisableTiming));
+            GS_CUDA(cudaEventRecord(e->ev_mid, s));
+            e->mid_valid = true;
+        }
         // algorithmic bytes of the fused gather+mean launch: S rows + S ids in, one row out
         if (p_red >= 0) e->prof.bytes[GSAGE_PROF_REDUCE] += (double)n * ((double)S * d * dtype_size(nb.dtype) + (nb.ids ? 8.0 * S : 0.0) + (double)d * dtype_size(T));
         RowSrc m{Mb, T, ldm, n, nullptr, d};
@@ -291,6 +299,7 @@ int gsage_engine_create(const gsage_engine_config* cfg, gsage_engine** out) {
     if (const char* f = getenv("GSAGE_FUSE_MEAN")) e->fuse_mean = atoi(f) != 0;
     if (const char* f = getenv("GSAGE_CHUNK")) e->chunk_parents = atoll(f);
     if (const char* f = getenv("GSAGE_L2HINT")) e->l2_hint = atoi(f);
+    if (const char* f = getenv("GSAGE_AHEAD_AFTER_GATHER")) e->ahead_after_gather = atoi(f);
     const int64_t es = (int64_t)dtype_size(e->T);
     const int64_t vec = 16 / es;
     switch (cfg->prep) {
@@ -312,8 +321,8 @@ int gsage_engine_create(const gsage_engine_config* cfg, gsage_engine** out) {
     auto carve = [&](int64_t bytes) { int64_t at = off; off += pad_to(std::max<int64_t>(bytes, 16), 256); return at; };
     const int64_t o_ids = carve(8 * (e->n0 + e->n1 + e->n2));
     const int64_t o_ids1 = carve(8 * (e->n0 + e->n1 + e->n2));
-    const int64_t o_sel = carve(4 * e->n2);
-    const int64_t o_sel1 = carve(4 * e->n2);
+    const int64_t o_sel = carve(4 * (e->n1 + e->n2));
+    const int64_t o_sel1 = carve(4 * (e->n1 + e->n2));
     const int64_t o_look = carve(8 * e->n0);
     const int64_t o_X = (cfg->prep == GSAGE_PREP_IDENTITY || e->fold_prep) ? -1 : carve(es * e->ld_prep * (e->n0 + e->n1 + e->n2));
     const int64_t dmax = std::max<int64_t>(e->ld_prep, e->ld_h1);
@@ -376,6 +385,7 @@ void gsage_engine_destroy(gsage_engine* e) {
     for (cudaEvent_t ev : e->prof.pool) cudaEventDestroy(ev);
     if (e->ss) { cudaStreamSynchronize(e->ss); cudaStreamDestroy(e->ss); }
     for (int i = 0; i < 2; ++i) if (e->ev_done[i]) cudaEventDestroy(e->ev_done[i]);
+    if (e->ev_mid) cudaEventDestroy(e->ev_mid);
     if (e->ev_ahead) cudaEventDestroy(e->ev_ahead);
     cudaFree(e->ws);
     cudaFree(e->wb);
@@ -496,10 +506,12 @@ static int sample_hops(gsage_engine* e, gsage_graph* g, gsage_rng* rng, int64_t*
     int64_t* ids0 = ids; int64_t* ids1 = ids0 + n0; int64_t* ids2 = ids1 + n1;
     if (ids_src != ids0) GS_CUDA(cudaMemcpyAsync(ids0, ids_src, 8 * n0, src_host ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, s));
     if (global_B == B) {
-        GS_TRY(rng_randint_internal(rng, (uint32_t)g->n_cols, n1, sel, s));
+        // both hops draw from the same range [0, maxdeg) and the hop sizes do not depend on what was sampled, so the
+        // n1 hop-0 draws followed by the n2 hop-1 draws are ONE bounded draw of n1 + n2 values from the stream (same words,
+        // same order, same final position as two np.random.choice calls): one count / scan / scatter pass instead of two
+        GS_TRY(rng_randint_internal(rng, (uint32_t)g->n_cols, n1 + n2, sel, s));
         GS_TRY(sample_sparse_launch(g, ids0, n0, S1, sel, ids1, s));
-        GS_TRY(rng_randint_internal(rng, (uint32_t)g->n_cols, n2, sel, s));
-        GS_TRY(sample_sparse_launch(g, ids1, n1, S2, sel, ids2, s));
+        GS_TRY(sample_sparse_launch(g, ids1, n1, S2, sel + n1, ids2, s));
     } else {
         // seed-sharded, still bit-exact with the single-process run: every rank consumes the draws of the WHOLE
         // global batch (hop-0 block, then hop-1 block -- the cheap part) and uses the slice that belongs to its seeds;
@@ -549,6 +561,7 @@ static int sample_ahead_impl(gsage_engine* e, gsage_graph* g, gsage_rng* rng, co
     // the draws run underneath the forward that was queued just before this call
     (void)main;
     if (e->done_valid[e->cur ^ 1]) GS_CUDA(cudaStreamWaitEvent(e->ss, e->ev_done[e->cur ^ 1], 0));
+    if (e->mid_valid) { GS_CUDA(cudaStreamWaitEvent(e->ss, e->ev_mid, 0)); e->mid_valid = false; }
     GS_TRY(sample_hops(e, g, rng, e->ids_slot[e->cur ^ 1], e->sel_ahead, ids_src, src_host, B, global_B, first, e->ss));
     GS_CUDA(cudaEventRecord(e->ev_ahead, e->ss));
     e->ahead.valid = true; e->ahead.src = ids_src; e->ahead.B = B; e->ahead.global_B = global_B; e->ahead.first = first;

@@ -337,6 +337,7 @@ static int rng_resync(gsage_rng* r, cudaStream_t s) {
     GS_CUDA(cudaMemcpyAsync(&c, r->cursor + r->parity, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
     GS_CUDA(cudaStreamSynchronize(s));
     r->cursor_lb = r->cursor_ub = c;
+    for (auto& f : r->fb) f.pending = false;                   // older than this exact value
     return GSAGE_OK;
 }
 
@@ -356,6 +357,29 @@ static int rng_init_lanes(gsage_rng* r) {
     return GSAGE_OK;
 }
 
+// fold completed cursor read-backs into the host bounds (never blocks)
+static void rng_poll(gsage_rng* r) {
+    for (auto& f : r->fb) {
+        if (!f.pending || cudaEventQuery(f.ev) != cudaSuccess) continue;
+        const int64_t c = *f.host;
+        // draws queued after the read-back was posted consumed >= (acc_total - acc_at) and <= (win_total - win_at) words
+        r->cursor_lb = std::max(r->cursor_lb, c + (r->acc_total - f.acc_at));
+        r->cursor_ub = std::min(r->cursor_ub, c + (r->win_total - f.win_at));
+        f.pending = false;
+    }
+}
+
+// post a read-back of the cursor as it is after everything queued on `s` so far
+static void rng_post_feedback(gsage_rng* r, cudaStream_t s) {
+    for (auto& f : r->fb) {
+        if (f.pending || !f.host) continue;
+        if (cudaMemcpyAsync(f.host, r->cursor + r->parity, sizeof(int64_t), cudaMemcpyDeviceToHost, s) != cudaSuccess) return;
+        if (cudaEventRecord(f.ev, s) != cudaSuccess) return;
+        f.acc_at = r->acc_total; f.win_at = r->win_total; f.pending = true;
+        return;
+    }
+}
+
 // Enqueue generation of stream words up to (at least) `upto` on the rng's own side stream.  The refill first waits
 // for everything already queued on the caller's stream (those kernels may still read ring slots the refill is
 // about to recycle), then runs concurrently with whatever the caller queues next -- the generator is independent
@@ -364,6 +388,7 @@ static int rng_init_lanes(gsage_rng* r) {
 // loose to prove the ring has room; a prefetch passes false and simply gives up.
 static int rng_generate(gsage_rng* r, int64_t upto, cudaStream_t s, bool may_sync) {
     bool fenced = false;
+    rng_poll(r);
     while (upto > r->gen_end) {
         const int64_t need = ceil_div(upto - r->gen_end, kN);
         const int64_t lane_refill = (int64_t)r->lanes * r->lane_blocks;
@@ -421,7 +446,8 @@ int rng_ensure(gsage_rng* r, int64_t upto, cudaStream_t s) {
 
 // top the ring up for the next calls without making the caller's stream wait for it
 static int rng_prefetch(gsage_rng* r, cudaStream_t s) {
-    const int64_t ahead = r->max_window + r->max_window / 4 + kN;
+    // far enough ahead that the refill for the NEXT batch is already done when its draws are queued (ring permitting)
+    const int64_t ahead = std::min<int64_t>(2 * r->max_window + r->max_window / 2 + kN, r->cap / 2);
     return rng_generate(r, r->cursor_ub + ahead, s, false);
 }
 
@@ -486,9 +512,11 @@ static int rng_draw(gsage_rng* r, uint32_t hi, int64_t count, uint32_t* out, cud
         r->parity ^= 1;
         r->cursor_lb += n;
         r->cursor_ub += window;
+        r->acc_total += n; r->win_total += window;
         r->max_window = std::max(r->max_window, window);
     }
     GS_TRY(rng_leave(r, s));
+    rng_post_feedback(r, s);
     return rng_prefetch(r, s);
 }
 
@@ -505,7 +533,7 @@ extern "C" {
 int gsage_rng_create(gsage_rng** out) {
     GS_CHECK_ARG(out, "rng_create: NULL out");
     gsage_rng* r = new gsage_rng();
-    int log2cap = 24;                                           // 16 Mi words = 64 MiB of look-ahead
+    int log2cap = 25;                                           // 32 Mi words = 128 MiB of look-ahead
     if (const char* e = getenv("GSAGE_RNG_LOG2_WORDS")) log2cap = std::max(14, std::min(30, atoi(e)));
     r->cap = (int64_t)1 << log2cap;
     r->prefetch_blocks = std::max<int64_t>(1, std::min<int64_t>(64, r->cap / kN / 8));
@@ -535,6 +563,14 @@ int gsage_rng_create(gsage_rng** out) {
         gsage_rng_destroy(r);
         return GSAGE_ERR_CUDA;
     }
+    for (auto& f : r->fb) {
+        if (cudaHostAlloc((void**)&f.host, sizeof(int64_t), cudaHostAllocDefault) != cudaSuccess ||
+            cudaEventCreateWithFlags(&f.ev, cudaEventDisableTiming) != cudaSuccess) {
+            set_error("rng_create: pinned feedback slot allocation failed");
+            gsage_rng_destroy(r);
+            return GSAGE_ERR_NOMEM;
+        }
+    }
     *out = r;
     return gsage_rng_seed(r, 5489u, nullptr);
 }
@@ -547,6 +583,7 @@ void gsage_rng_destroy(gsage_rng* r) {
     if (r->ev_main) cudaEventDestroy(r->ev_main);
     if (r->ev_refill) cudaEventDestroy(r->ev_refill);
     if (r->ev_switch) cudaEventDestroy(r->ev_switch);
+    for (auto& f : r->fb) { if (f.ev) { cudaEventSynchronize(f.ev); cudaEventDestroy(f.ev); } if (f.host) cudaFreeHost(f.host); }
     delete r;
 }
 
@@ -569,6 +606,7 @@ int gsage_rng_set_state(gsage_rng* r, const uint32_t* key, int pos, void* stream
     r->parity = 0;
     r->cursor_lb = r->cursor_ub = pos;
     r->origin = pos;
+    for (auto& f : r->fb) { if (f.pending) cudaEventSynchronize(f.ev); f.pending = false; }
     return GSAGE_OK;
 }
 
@@ -613,6 +651,7 @@ int gsage_rng_raw(gsage_rng* r, int64_t count, uint32_t* out_dev, void* stream) 
         r->parity ^= 1;
         r->cursor_lb += n;
         r->cursor_ub += n;
+        r->acc_total += n; r->win_total += n;
     }
     return rng_leave(r, s);
 }
@@ -636,6 +675,7 @@ int gsage_rng_permutation(gsage_rng* r, int64_t n, int64_t* out_dev, void* strea
     r->parity ^= 1;
     r->cursor_lb += 0;                       // n == 1 consumes nothing; the true value comes from resync
     r->cursor_ub += window;
+    r->win_total += window;
     GS_TRY(rng_leave(r, s));
     return rng_resync(r, s);                  // sequential kernel anyway: re-tighten immediately
 }

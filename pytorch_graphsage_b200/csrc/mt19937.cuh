@@ -31,6 +31,13 @@ struct gsage_rng {
     // new stream is ordered after everything queued on the previous one, so the stream of draws stays one sequence
     cudaStream_t last_stream = nullptr; bool have_last = false;
     cudaEvent_t ev_switch = nullptr;
+    // asynchronous cursor feedback: after a draw the true cursor is copied to pinned host memory (8 bytes, stream ordered);
+    // once the copy has landed the host bounds are re-tightened from it WITHOUT synchronising anything.  Accepted draws are
+    // only a lower bound on words consumed (masked rejection), so without this the bounds drift apart by ~40 % of every
+    // draw and the ring-room check forces a blocking read-back every few batches.
+    static constexpr int kFeedback = 4;
+    struct Feedback { int64_t* host = nullptr; cudaEvent_t ev = nullptr; int64_t acc_at = 0, win_at = 0; bool pending = false; } fb[kFeedback];
+    int64_t acc_total = 0, win_total = 0;     // monotone: words certainly / at most consumed by all draws queued so far
 };
 
 namespace gsage {
