@@ -387,15 +387,21 @@ def run_ours(args):
 
     # ---- one optimiser step per batch (forward + loss + backward + gradient all-reduce + clip + Adam) ---------------
     train = None
-    if prob['aggregator'] == 'mean' and prob['prep'] == 'identity' and not args.no_train:
+    trainable = prob['aggregator'] == 'mean' and (prob['prep'] == 'identity' or (prob['prep'] == 'node_embedding' and dtype == torch.float32 and not tf32))
+    if trainable and not args.no_train:
         from torch.nn import functional as F
-        tgt_all = torch.from_numpy(prob['targets'].reshape(-1)).cuda()
+        if prob['task'] == 'regression_mae':                                       # problem.py:39-41: l1 loss on (B, 1) predictions
+            tgt_all = torch.from_numpy(prob['targets']).cuda()
+            loss_fn = lambda preds, t: F.l1_loss(preds, t.view_as(preds))
+        else:
+            tgt_all = torch.from_numpy(prob['targets'].reshape(-1)).cuda()
+            loss_fn = F.cross_entropy
         tgts = [tgt_all[i] for i in dev_ids]
         opt = torch.optim.Adam(model.parameters(), lr=0.01)
         side = torch.cuda.Stream()
         k_train = max(3, min(args.steps, 30))
         def train_step(i):
-            model.train_step(dev_ids[i % n_batches], table, tgts[i % n_batches], F.cross_entropy, optimizer=opt, grad_scale=1.0 / WORLD,
+            model.train_step(dev_ids[i % n_batches], table, tgts[i % n_batches], loss_fn, optimizer=opt, grad_scale=1.0 / WORLD,
                              overlap_stream=side, next_ids=dev_ids[(i + 1) % n_batches] if ahead else None)
 
         for i in range(3):

@@ -239,6 +239,12 @@ int gsage_engine_forward_sharded(gsage_engine* e, gsage_graph* g, gsage_rng* rng
  * This is the end-to-end entry a reference-side caller binds (ids and logits are what models.py:71 takes/returns). */
 int gsage_engine_forward_host(gsage_engine* e, gsage_graph* g, gsage_rng* rng, const int64_t* ids_host, int64_t B,
                               float* logits_host, void* stream);
+/* GSSupervised.forward with the DENSE 2-D edgelist sampler (nn_modules.py:19-49; `uniform_neighbor_sampler` is the default
+ * of train.py:55): hop k takes adj[ids][:, perm_k][:, :S_k], one permutation shared by all rows of the hop.  perm0 / perm1
+ * are the reference's two torch.randperm(K) draws (CPU generator, hop 0 first), made by the caller and passed as K int64
+ * each; `adj_dev` is the (n_rows, K) int64 table.  Everything after the sampling is gsage_engine_forward. */
+int gsage_engine_forward_dense(gsage_engine* e, const int64_t* adj_dev, int64_t n_rows, int K, const int64_t* perm0_dev,
+                               const int64_t* perm1_dev, const int64_t* ids_dev, int64_t B, float* logits_dev, void* stream);
 /* Sample-ahead.  Draws and samples both hops of a batch NOW, on the engine's own high-priority stream, into a spare id
  * buffer; the next gsage_engine_forward[_sharded|_host] call -- which must name the same batch: same ids pointer, B,
  * (global_B, first), graph and rng -- skips its sampling section and only waits for that stream.  The (latency-bound)
@@ -288,6 +294,15 @@ int gsage_engine_backward_layer1(gsage_engine* e, const gsage_grads* grads, void
  * row-major operands as MN-major tiles (bf16 G and A, O == 128, 16-byte aligned rows; GSAGE_ERR_INVALID otherwise). */
 int gsage_wgrad(const void* g_dev, int g_dtype, int64_t ldg, int O, const void* a_dev, int a_dtype, int64_t lda,
                 const int64_t* ids_dev, int d, int64_t n, float* dw_dev, int64_t lddw, int exact, void* stream);
+
+/* Layer-1 gradients of the Pokec recipe (utils/pokec.sh: mean aggregator + NodeEmbeddingPrep without features, fp32).
+ * Replaces gsage_engine_backward_layer1 for such models; same preconditions.  The library does every reduction over rows;
+ * the caller finishes with four (O x 64)(64 x 64) products (formulas in engine.cu, done by model.GSSupervised.backward):
+ *   gx_raw (O1, emb_dim) = Gx^T . E[self ids]        gn_raw (O1, emb_dim) = Gn^T . mean_j E[neighbour ids]
+ *   csum   (2 * O1)      = column sums of G           d_table (n_nodes + 1, emb_dim) = dense gradient of the embedding table
+ * where G = d loss / d (layer-1 pre-activation) of all 26*B parent rows.  All buffers fp32, overwritten. */
+typedef struct gsage_embedding_grads { float* gx_raw; float* gn_raw; float* csum; float* d_table; } gsage_embedding_grads;
+int gsage_engine_backward_layer1_embedding(gsage_engine* e, const gsage_embedding_grads* g, void* stream);
 
 /* keep != 0: the next forwards keep every activation the backward pass needs (training).  0 (default): forward-only
  * streaming -- intermediates may be processed in L2-sized chunks that reuse their buffers. */

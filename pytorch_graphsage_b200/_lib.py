@@ -45,6 +45,10 @@ class Grads(C.Structure):
     _fields_ = [('fc_x', c_p * 2), ('fc_neib', c_p * 2), ('fc_w', c_p), ('fc_b', c_p)]
 
 
+class EmbeddingGrads(C.Structure):
+    _fields_ = [('gx_raw', c_p), ('gn_raw', c_p), ('csum', c_p), ('d_table', c_p)]
+
+
 class Weights(C.Structure):
     _fields_ = [('layer', LayerWeights * 2), ('fc_w', c_p), ('fc_b', c_p), ('prep_fc_w', c_p), ('prep_fc_b', c_p),
                 ('prep_out_dim', C.c_int)]
@@ -89,6 +93,7 @@ _SIGNATURES = {
     'gsage_engine_forward': (C.c_int, [c_p, c_p, c_p, c_p, c_i64, c_p, c_p]),
     'gsage_engine_forward_sharded': (C.c_int, [c_p, c_p, c_p, c_p, c_i64, c_i64, c_i64, c_p, c_p]),
     'gsage_engine_forward_host': (C.c_int, [c_p, c_p, c_p, c_p, c_i64, c_p, c_p]),
+    'gsage_engine_forward_dense': (C.c_int, [c_p, c_p, c_i64, C.c_int, c_p, c_p, c_p, c_i64, c_p, c_p]),
     'gsage_engine_forward_host_next': (C.c_int, [c_p, c_p, c_p, c_p, c_i64, c_p, c_i64, c_p, c_p]),
     'gsage_engine_sample_ahead': (C.c_int, [c_p, c_p, c_p, c_p, c_i64, c_i64, c_i64, c_p]),
     'gsage_engine_sample_ahead_host': (C.c_int, [c_p, c_p, c_p, c_p, c_i64, c_p]),
@@ -97,6 +102,7 @@ _SIGNATURES = {
     'gsage_engine_workspace_bytes': (c_i64, [c_p]),
     'gsage_engine_backward_head': (C.c_int, [c_p, c_p, C.POINTER(Grads), c_p]),
     'gsage_engine_backward_layer1': (C.c_int, [c_p, C.POINTER(Grads), c_p]),
+    'gsage_engine_backward_layer1_embedding': (C.c_int, [c_p, C.POINTER(EmbeddingGrads), c_p]),
     'gsage_wgrad': (C.c_int, [c_p, C.c_int, c_i64, C.c_int, c_p, C.c_int, c_i64, c_p, C.c_int, c_i64, c_p, c_i64, C.c_int, c_p]),
     'gsage_engine_keep_activations': (C.c_int, [c_p, C.c_int]),
     'gsage_engine_profile': (C.c_int, [c_p, C.c_int]),

@@ -169,9 +169,31 @@ __global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ x
     if (threadIdx.x == 0) out[c] = sm[0];
 }
 
+// one warp per id: lanes stride over the d columns (coalesced RED requests, fire and forget)
+__global__ void __launch_bounds__(256) embedding_scatter_kernel(const float* __restrict__ rows, int64_t ld, int d,
+                                                                const int64_t* __restrict__ ids, int64_t n_ids, int S, float scale,
+                                                                float* __restrict__ table_grad, int64_t ld_table, int64_t table_rows) {
+    const int lane = threadIdx.x & 31;
+    const int64_t i = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (i >= n_ids) return;
+    const int64_t id = ids[i];
+    if ((uint64_t)id >= (uint64_t)table_rows) return;           // ids outside the table read as zero rows in the forward
+    const float* src = rows + (i / S) * ld;
+    float* dst = table_grad + id * ld_table;
+    for (int c = lane; c < d; c += 32) atomicAdd(dst + c, src[c] * scale);
+}
+
+int embedding_scatter_launch(const float* rows, int64_t ld, int d, const int64_t* ids, int64_t n_ids, int S, float scale,
+                             float* table_grad, int64_t ld_table, int64_t table_rows, cudaStream_t s) {
+    if (n_ids == 0) return GSAGE_OK;
+    embedding_scatter_kernel<<<(unsigned)ceil_div(n_ids, 8), 256, 0, s>>>(rows, ld, d, ids, n_ids, S, scale, table_grad, ld_table, table_rows);
+    GS_LAUNCHED();
+    return GSAGE_OK;
+}
+
 int wgrad_launch(const float* G, int64_t ldg, int O, const void* A, int a_dtype, int64_t lda, const int64_t* ids, int d,
-                 int64_t n, float* dW, int64_t lddw, cudaStream_t s) {
-    GS_CUDA(cudaMemsetAsync(dW, 0, sizeof(float) * (size_t)O * lddw, s));
+                 int64_t n, float* dW, int64_t lddw, cudaStream_t s, bool accumulate) {
+    if (!accumulate) GS_CUDA(cudaMemsetAsync(dW, 0, sizeof(float) * (size_t)O * lddw, s));
     if (n == 0) return GSAGE_OK;
     // enough row chunks to fill the machine a few times over, at least 256 rows each
     const int64_t tiles = ceil_div(O, WT) * ceil_div(d, WT);

@@ -127,6 +127,8 @@ struct gsage_engine {
     // never materialised (algebraically identical; fp32 rounding differs at the 1e-6 level)
     bool fold_prep = false;
     float* fold = nullptr; int64_t fold_floats = 0;
+    const float* fold_wx = nullptr; const float* fold_wn = nullptr;     // W'x = Wx.Wp, W'n = Wn.Wp (O1 x emb_dim, fp32): backward needs them
+    float* DXE = nullptr;               // backward scratch (node_embedding): d loss / d (raw embedding row), (n0 + n1) x emb_dim, fp32
     const float* b_x[2] = {nullptr, nullptr}; const float* b_n[2] = {nullptr, nullptr};
     const float* b_mlp[2] = {nullptr, nullptr}; const float* b_att[2] = {nullptr, nullptr};
     // forward-only streaming (keep_activations == false): the big layer-1 application runs in chunks of `chunk_parents`
@@ -345,6 +347,7 @@ int gsage_engine_create(const gsage_engine_config* cfg, gsage_engine** out) {
     const int64_t o_DZN = carve(4 * 2 * O2 * e->n0), o_DZ = carve(4 * 2 * O2 * e->n0);
     const int64_t o_DH0 = carve(4 * 2 * O1 * e->n0), o_DM2 = carve(4 * 2 * O1 * e->n0);
     const int64_t o_DH = carve(4 * 2 * O1 * (e->n0 + e->n1));
+    const int64_t o_DXE = e->fold_prep ? carve(4 * (int64_t)cfg->emb_dim * (e->n0 + e->n1)) : -1;
     e->ws_bytes = off;
     if (cudaMalloc((void**)&e->ws, (size_t)off) != cudaSuccess) {
         set_error("engine_create: cudaMalloc of %lld workspace bytes failed", (long long)off);
@@ -375,6 +378,7 @@ int gsage_engine_create(const gsage_engine_config* cfg, gsage_engine** out) {
     e->X = at(o_X); e->M = at(o_M); e->HN = at(o_HN); e->Pp = at(o_P);
     e->T1 = at(o_T1); e->NA = at(o_NA); e->T1x = at(o_T1x); e->XA = at(o_XA); e->AW = (float*)at(o_AW);
     e->H1 = at(o_H1); e->Z = (float*)at(o_Z); e->ZN = (float*)at(o_ZN); e->LG = (float*)at(o_LG);
+    e->DXE = (float*)at(o_DXE);
     e->DZN = (float*)at(o_DZN); e->DZ = (float*)at(o_DZ); e->DH0 = (float*)at(o_DH0); e->DM2 = (float*)at(o_DM2); e->DH = (float*)at(o_DH);
     *out = e;
     return GSAGE_OK;
@@ -465,6 +469,8 @@ int gsage_engine_set_weights(gsage_engine* e, const gsage_weights* w, void* stre
         const bool pool0 = e->cfg.aggregator == GSAGE_AGG_MAX_POOL || e->cfg.aggregator == GSAGE_AGG_MEAN_POOL;
         GS_TRY(fold_w(w->layer[0].fc_x, O, nullptr, &eff.layer[0].fc_x, &e->b_x[0]));
         if (!pool0) GS_TRY(fold_w(w->layer[0].fc_neib, O, nullptr, &eff.layer[0].fc_neib, &e->b_n[0]));
+        e->fold_wx = eff.layer[0].fc_x;
+        e->fold_wn = pool0 ? nullptr : eff.layer[0].fc_neib;
         if (pool0) GS_TRY(fold_w(w->layer[0].mlp_w, H, w->layer[0].mlp_b, &eff.layer[0].mlp_w, &e->b_mlp[0]));
         if (e->cfg.aggregator == GSAGE_AGG_ATTENTION) GS_TRY(fold_w(w->layer[0].att_w1, H, nullptr, &eff.layer[0].att_w1, &e->b_att[0]));
         GS_CHECK_ARG(at - e->fold <= e->fold_floats, "engine_set_weights: folded-weight arena too small");
@@ -583,6 +589,7 @@ int gsage_engine_sample_ahead_pending(const gsage_engine* e) { return (e && e->a
 
 static int forward_impl(gsage_engine* e, gsage_graph* g, gsage_rng* rng, const int64_t* ids_src, bool src_host, int64_t B,
                         int64_t global_B, int64_t first, float* logits_dev, cudaStream_t s);
+static int forward_layers(gsage_engine* e, int64_t B, float* logits_dev, cudaStream_t s, int p_all);
 
 int gsage_engine_forward(gsage_engine* e, gsage_graph* g, gsage_rng* rng, const int64_t* ids_dev, int64_t B,
                          float* logits_dev, void* stream) {
@@ -599,10 +606,6 @@ static int forward_impl(gsage_engine* e, gsage_graph* g, gsage_rng* rng, const i
     GS_TRY(check_batch_args(e, g, rng, ids_src, B, global_B, first));
     GS_CHECK_ARG(logits_dev, "engine_forward: NULL argument");
     GS_CHECK_ARG(e->have_weights, "engine_forward: call gsage_engine_set_weights first");
-    const gsage_engine_config& c = e->cfg;
-    const int S1 = c.fanout[0], S2 = c.fanout[1], T = e->T;
-    const int64_t n0 = B, n1 = B * S1, n2 = n1 * S2;
-    const int64_t es = (int64_t)dtype_size(T);
 
     const int p_all = e->prof.begin(GSAGE_PROF_FORWARD, s);
     if (e->ahead.valid) {
@@ -618,9 +621,17 @@ static int forward_impl(gsage_engine* e, gsage_graph* g, gsage_rng* rng, const i
     } else {
         GS_TRY(sample_hops(e, g, rng, e->ids, e->sel, ids_src, src_host, B, global_B, first, s));
     }
+    return forward_layers(e, B, logits_dev, s, p_all);
+}
+
+// everything after the sampling: prep, both aggregator layers, normalise, classifier -- reads the hop ids of e->ids
+static int forward_layers(gsage_engine* e, int64_t B, float* logits_dev, cudaStream_t s, int p_all) {
+    const gsage_engine_config& c = e->cfg;
+    const int S1 = c.fanout[0], S2 = c.fanout[1], T = e->T;
+    const int64_t n0 = B, n1 = B * S1, n2 = n1 * S2;
+    const int64_t es = (int64_t)dtype_size(T);
     e->B = B;
     int64_t* ids0 = e->ids; int64_t* ids1 = ids0 + n0;
-    (void)n2; (void)S2;
 
     // ---- prep (models.py:76-81) ------------------------------------------------------------------------
     RowSrc lvl;       // all three hops, hop k starts `offset_k` rows in
@@ -725,10 +736,33 @@ static bool layer1_wgrad_on_tensor_cores(const gsage_engine* e) {
     return wgrad_umma_eligible(probe) && wgrad_umma_eligible(probe2);
 }
 
+// GSSupervised.forward with the DENSE sampler (nn_modules.py:19-49, train.py:55's default): hop k is
+// adj[ids][:, perm_k][:, :S_k] with the caller's torch.randperm(K) draws; everything after the sampling is shared.
+int gsage_engine_forward_dense(gsage_engine* e, const int64_t* adj_dev, int64_t n_rows, int K, const int64_t* perm0_dev,
+                               const int64_t* perm1_dev, const int64_t* ids_dev, int64_t B, float* logits_dev, void* stream) {
+    GS_CHECK_ARG(e && adj_dev && perm0_dev && perm1_dev && ids_dev && logits_dev, "engine_forward_dense: NULL argument");
+    GS_CHECK_ARG(e->have_weights, "engine_forward_dense: call gsage_engine_set_weights first");
+    GS_CHECK_ARG(B > 0 && B <= e->maxB, "engine_forward_dense: batch %lld outside (0, max_batch=%lld]", (long long)B, (long long)e->maxB);
+    GS_CHECK_ARG(!e->ahead.valid, "engine_forward_dense: a sampled-ahead batch is pending (run its forward first)");
+    const int S1 = e->cfg.fanout[0], S2 = e->cfg.fanout[1];
+    GS_CHECK_ARG(K >= S1 && K >= S2, "engine_forward_dense: fanout larger than the table width K = %d", K);
+    cudaStream_t s = as_stream(stream);
+    const int p_all = e->prof.begin(GSAGE_PROF_FORWARD, s);
+    const int p_smp = e->prof.begin(GSAGE_PROF_SAMPLE, s);
+    int64_t* ids0 = e->ids; int64_t* ids1 = ids0 + B; int64_t* ids2 = ids1 + B * S1;
+    if (ids_dev != ids0) GS_CUDA(cudaMemcpyAsync(ids0, ids_dev, 8 * B, cudaMemcpyDeviceToDevice, s));
+    GS_TRY(gsage_sample_dense(adj_dev, n_rows, K, ids0, B, perm0_dev, S1, ids1, stream));
+    GS_TRY(gsage_sample_dense(adj_dev, n_rows, K, ids1, B * S1, perm1_dev, S2, ids2, stream));
+    e->prof.end(p_smp, s);
+    return forward_layers(e, B, logits_dev, s, p_all);
+}
+
 static int backward_supported(gsage_engine* e) {
     GS_CHECK_ARG(e && e->have_weights && e->B > 0, "engine_backward: run gsage_engine_forward first");
-    GS_CHECK_ARG(e->cfg.aggregator == GSAGE_AGG_MEAN && e->cfg.prep == GSAGE_PREP_IDENTITY,
-                 "engine_backward: implemented for the mean aggregator with the identity prep (the other plug-ins are forward-only this round)");
+    GS_CHECK_ARG(e->cfg.aggregator == GSAGE_AGG_MEAN &&
+                 (e->cfg.prep == GSAGE_PREP_IDENTITY || (e->cfg.prep == GSAGE_PREP_NODE_EMBEDDING && e->fold_prep && e->T == GSAGE_F32)),
+                 "engine_backward: implemented for the mean aggregator with the identity prep, or with the node_embedding prep "
+                 "without features in fp32 (the Pokec recipe); the other plug-ins are forward-only");
     GS_CHECK_ARG(!e->fuse_mean, "engine_backward: needs the reduced rows the fused (GSAGE_FUSE_MEAN) layer never writes");
     GS_CHECK_ARG(e->keep_activations || e->chunk_parents == 0, "engine_backward: call gsage_engine_keep_activations(e, 1) before the forward");
     return GSAGE_OK;
@@ -762,6 +796,7 @@ int gsage_engine_backward_head(gsage_engine* e, const float* dlogits, const gsag
 
 int gsage_engine_backward_layer1(gsage_engine* e, const gsage_grads* g, void* stream) {
     GS_TRY(backward_supported(e));
+    GS_CHECK_ARG(e->cfg.prep == GSAGE_PREP_IDENTITY, "engine_backward_layer1: node_embedding models use gsage_engine_backward_layer1_embedding");
     GS_CHECK_ARG(g && g->fc_x[0] && g->fc_neib[0], "engine_backward_layer1: NULL argument");
     cudaStream_t s = as_stream(stream);
     const gsage_engine_config& c = e->cfg;
@@ -781,6 +816,40 @@ int gsage_engine_backward_layer1(gsage_engine* e, const gsage_grads* g, void* st
     GS_TRY(wgrad_launch(e->DH, 2 * O1, O1, c.feats_dev, c.feats_dtype, c.feats_ld, e->ids, d, n0 + n1, g->fc_x[0], d, s));
     GS_TRY(wgrad_launch(e->DH + O1, 2 * O1, O1, e->M, e->T, e->ld_m, nullptr, d, n0 + n1, g->fc_neib[0], d, s));
     return mark_slot_done(e, s);          // the weight gradients gather self rows by id: the slot is busy until here
+}
+
+// Layer-1 gradients of the Pokec recipe (mean aggregator, NodeEmbeddingPrep without features, nn_modules.py:126-155):
+//   H_r = act([W'x e_self(r) + b'x | W'n mean_j e_nb(r,j) + b'n]),  W' = W.Wp, b' = W.bp  (the prep's affine folded into layer 1)
+// With G = d loss / d pre-activation (layer1_grad_kernel):
+//   gx_raw = Gx^T . E[self ids]     gn_raw = Gn^T . M     cx / cn = column sums of Gx / Gn       (all the row-reductions)
+//   d_table[id] += Gx[r] . W'x  for the self row of r,   += (1/S) Gn[r] . W'n  for each of its S sampled neighbours
+// The parameter gradients follow from these by (O x 64)(64 x 64) products, left to the caller:
+//   dWx = gx_raw.Wp^T + cx (x) bp,  dWn = gn_raw.Wp^T + cn (x) bp,  dWp = Wx^T.gx_raw + Wn^T.gn_raw,  dbp = Wx^T.cx + Wn^T.cn
+int gsage_engine_backward_layer1_embedding(gsage_engine* e, const gsage_embedding_grads* g, void* stream) {
+    GS_TRY(backward_supported(e));
+    GS_CHECK_ARG(e->cfg.prep == GSAGE_PREP_NODE_EMBEDDING && e->fold_prep, "engine_backward_layer1_embedding: not a node_embedding model");
+    GS_CHECK_ARG(g && g->gx_raw && g->gn_raw && g->csum && g->d_table, "engine_backward_layer1_embedding: NULL argument");
+    cudaStream_t s = as_stream(stream);
+    const gsage_engine_config& c = e->cfg;
+    const int64_t n0 = e->B, n1 = n0 * c.fanout[0], n2 = n1 * c.fanout[1];
+    const int O1 = c.out_dim[0], de = c.emb_dim, S1 = c.fanout[0], S2 = c.fanout[1];
+    const int64_t rows = n0 + n1, trows = c.n_nodes + 1;
+    const int64_t* ids0 = e->ids; const int64_t* ids1 = ids0 + n0; const int64_t* ids2 = ids1 + n1;
+    (void)ids0;
+    // row reductions: seeds read the masked row n_nodes (look0), hop-1 parents their own id
+    GS_TRY(wgrad_launch(e->DH, 2 * O1, O1, c.emb_dev, c.emb_dtype, c.emb_ld, e->look0, de, n0, g->gx_raw, de, s));
+    GS_TRY(wgrad_launch(e->DH + (int64_t)n0 * 2 * O1, 2 * O1, O1, c.emb_dev, c.emb_dtype, c.emb_ld, ids1, de, n1, g->gx_raw, de, s, true));
+    GS_TRY(wgrad_launch(e->DH + O1, 2 * O1, O1, e->M, e->T, e->ld_m, nullptr, de, rows, g->gn_raw, de, s));
+    GS_TRY(colsum_launch(e->DH, rows, 2 * O1, g->csum, s));
+    // table gradient: dense (n_nodes + 1, de), like nn.Embedding's
+    GS_CUDA(cudaMemsetAsync(g->d_table, 0, sizeof(float) * (size_t)trows * de, s));
+    GS_TRY(linear_trans_call(e->DH, 2 * O1, O1, e->fold_wx, de, de, rows, e->DXE, de, s));                 // Gx . W'x
+    GS_TRY(embedding_scatter_launch(e->DXE, de, de, e->look0, n0, 1, 1.0f, g->d_table, de, trows, s));
+    GS_TRY(embedding_scatter_launch(e->DXE + n0 * de, de, de, ids1, n1, 1, 1.0f, g->d_table, de, trows, s));
+    GS_TRY(linear_trans_call(e->DH + O1, 2 * O1, O1, e->fold_wn, de, de, rows, e->DXE, de, s));            // Gn . W'n
+    GS_TRY(embedding_scatter_launch(e->DXE, de, de, ids1, n1, S1, 1.0f / (float)S1, g->d_table, de, trows, s));
+    GS_TRY(embedding_scatter_launch(e->DXE + n0 * de, de, de, ids2, n2, S2, 1.0f / (float)S2, g->d_table, de, trows, s));
+    return mark_slot_done(e, s);
 }
 
 int gsage_engine_peek(gsage_engine* e, int what, const void** ptr, int64_t* rows, int64_t* cols, int64_t* ld, int* dtype) {

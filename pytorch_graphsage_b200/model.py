@@ -20,7 +20,7 @@ from . import _lib, ops
 from ._lib import check, lib
 from .graph import GraphCSR
 from .operators import (AttentionAggregator, MeanAggregator, MeanPoolAggregator, MaxPoolAggregator, NodeEmbeddingPrep,
-                        IdentityPrep, LinearPrep, SparseUniformNeighborSampler, _act_name)
+                        IdentityPrep, LinearPrep, SparseUniformNeighborSampler, UniformNeighborSampler, _act_name)
 from .rng import default_rng
 
 
@@ -169,14 +169,24 @@ class GSSupervised(nn.Module):
         """models.py:71-91.  `ids`: int64 tensor of seed ids (CUDA, or CPU -> copied); `feats`: the node feature
         table (tensor / FeatureTable) or None.  Returns fp32 logits (B, n_classes) on the GPU."""
         sampler = self.train_sampler if train else self.val_sampler
-        assert isinstance(sampler, SparseUniformNeighborSampler), \
-            'GSSupervised: the fused engine samples from the sparse adjacency; use forward_reference_order for the dense sampler'
         fanout = [s['n_train_samples' if train else 'n_val_samples'] for s in self.layer_specs]
         ids = torch.as_tensor(ids).to(device='cuda', dtype=torch.int64).contiguous().view(-1)
         table = self._table(feats)
         eng = self._engine(table, fanout, ids.shape[0])
         self._push_weights(eng)
         check(lib().gsage_engine_keep_activations(eng['h'], 1 if keep_activations else 0))
+        if isinstance(sampler, UniformNeighborSampler):
+            # the dense 2-D edgelist sampler (train.py:55's default): one torch.randperm(K) per hop from the CPU generator,
+            # hop 0 first -- exactly the draws nn_modules.py:44 makes -- then the same engine
+            assert shard is None, 'GSSupervised: seed sharding is implemented for the sparse sampler'
+            K = sampler.adj.size(1)
+            perms = [torch.randperm(K).cuda() for _ in fanout]
+            out = torch.empty((ids.shape[0], self.n_classes), dtype=torch.float32, device='cuda')
+            check(lib().gsage_engine_forward_dense(eng['h'], ops.ptr(sampler.adj), sampler.adj.size(0), K, ops.ptr(perms[0]), ops.ptr(perms[1]),
+                                                   ops.ptr(ids), ids.shape[0], ops.ptr(out), ops.stream()))
+            self._last = eng
+            return out
+        assert isinstance(sampler, SparseUniformNeighborSampler), 'GSSupervised: unknown sampler class %r' % (type(sampler),)
         rng = sampler.rng or self.rng or default_rng()
         out = torch.empty((ids.shape[0], self.n_classes), dtype=torch.float32, device='cuda')
         if shard is None:
@@ -255,13 +265,35 @@ class GSSupervised(nn.Module):
             overlap_stream.wait_stream(main)
             with torch.cuda.stream(overlap_stream):
                 bucket.all_reduce_head(grad_scale)
-        check(lib().gsage_engine_backward_layer1(self._last['h'], C.byref(g), ops.stream()))
+        if self._prep_name == 'node_embedding':
+            self._backward_layer1_embedding(bucket, aggs[0])
+        else:
+            check(lib().gsage_engine_backward_layer1(self._last['h'], C.byref(g), ops.stream()))
         if overlap_stream is None:
             bucket.all_reduce(grad_scale)
         else:
             bucket.all_reduce_tail(grad_scale)
             main.wait_stream(overlap_stream)
         return bucket
+
+    def _backward_layer1_embedding(self, bucket, agg0):
+        """The Pokec recipe (mean + NodeEmbeddingPrep without features): the library reduces over the 26*B parent rows and
+        scatters the table gradient; the four (O x 64)(64 x 64) products that turn those reductions into parameter
+        gradients are done here (gsage_engine_backward_layer1_embedding documents the formulas)."""
+        O, de = agg0.fc_x.weight.shape[0], self.prep.embedding_dim
+        raw = torch.empty((2 * O * de + 2 * O,), dtype=torch.float32, device='cuda')
+        gx_raw, gn_raw, csum = raw[:O * de].view(O, de), raw[O * de:2 * O * de].view(O, de), raw[2 * O * de:]
+        eg = _lib.EmbeddingGrads()
+        eg.gx_raw, eg.gn_raw, eg.csum = gx_raw.data_ptr(), gn_raw.data_ptr(), csum.data_ptr()
+        eg.d_table = bucket.grad_of(self.prep.embedding.weight).data_ptr()
+        check(lib().gsage_engine_backward_layer1_embedding(self._last['h'], C.byref(eg), ops.stream()))
+        Wp, bp = self.prep.fc.weight.data, self.prep.fc.bias.data
+        Wx, Wn = agg0.fc_x.weight.data, agg0.fc_neib.weight.data
+        cx, cn = csum[:O], csum[O:]
+        bucket.grad_of(agg0.fc_x.weight).copy_(gx_raw @ Wp.t() + torch.outer(cx, bp))
+        bucket.grad_of(agg0.fc_neib.weight).copy_(gn_raw @ Wp.t() + torch.outer(cn, bp))
+        bucket.grad_of(self.prep.fc.weight).copy_(Wx.t() @ gx_raw + Wn.t() @ gn_raw)
+        bucket.grad_of(self.prep.fc.bias).copy_(Wx.t() @ cx + Wn.t() @ cn)
 
     def train_step(self, ids, feats, targets, loss_fn, optimizer=None, clip=5.0, grad_scale=1.0, overlap_stream=None, shard=None,
                    next_ids=None, next_shard=None):

@@ -161,6 +161,49 @@ def gen_model(agg, prep, fanout=(25, 10), batch=12, d=20, n_nodes=400, with_feat
     save('model_%s_%s%s' % (agg, prep, '' if with_feats else '_nofeats'), **arrays)
 
 
+def gen_model_dense(agg='mean', prep='identity', fanout=(25, 10), batch=12, d=20, n=300, K=128, out_dims=(16, 12)):
+    """GSSupervised.forward with the DENSE sampler -- train.py:55's default (`uniform_neighbor_sampler`), dummy row last."""
+    rs = np.random.RandomState(9)
+    adj = rs.randint(0, n, (n + 1, K)).astype(np.int64)
+    adj[rs.rand(n + 1, K) < 0.2] = n                 # some slots point at the dummy node, like convert.py:77 leaves them
+    adj[n] = n
+    feats = np.vstack([synth.make_features(n, d, seed=2)[1:n + 1], np.zeros((1, d), dtype=np.float32)]).astype(np.float32)
+    n_classes = 5
+    torch.manual_seed(123)
+    model = ref_models.GSSupervised(
+        input_dim=d, n_nodes=n + 1, n_classes=n_classes,
+        layer_specs=[
+            dict(n_train_samples=fanout[0], n_val_samples=fanout[0], output_dim=out_dims[0], activation=F.relu),
+            dict(n_train_samples=fanout[1], n_val_samples=fanout[1], output_dim=out_dims[1], activation=lambda x: x),
+        ],
+        aggregator_class=ref_nn.aggregator_lookup[agg], prep_class=ref_nn.prep_lookup[prep],
+        sampler_class=ref_nn.sampler_lookup['uniform_neighbor_sampler'], adj=torch.LongTensor(adj), train_adj=torch.LongTensor(adj))
+    model.eval()
+    ids0 = np.concatenate([[n], rs.randint(0, n, batch - 1)]).astype(np.int64)
+    hops, layer_outs = [], []
+    real_sampler = model.train_sampler
+    from functools import partial
+
+    def spy(ids, n_samples):
+        out = real_sampler(ids=ids, n_samples=n_samples)
+        hops.append(out.numpy().copy())
+        return out
+    model.train_sample_fns = [partial(spy, n_samples=s) for s in fanout]
+    hooks = [m.register_forward_hook(lambda mod, inp, out: layer_outs.append(out.detach().numpy().copy()))
+             for m in model.agg_layers.children()]
+    torch.manual_seed(123 ** 2)                      # helpers.set_seeds at train.py:133 seeds torch as well
+    with torch.no_grad():
+        logits = model(torch.LongTensor(ids0), torch.FloatTensor(feats), train=True)
+    for h in hooks:
+        h.remove()
+    arrays = dict(adj=adj, feats=feats, ids0=ids0, ids1=hops[0], ids2=hops[1], fanout=np.array(fanout), out_dims=np.array(out_dims),
+                  logits=logits.numpy(), l1_a=layer_outs[0], l1_b=layer_outs[1], l2=layer_outs[2], seed=np.int64(123 ** 2),
+                  n_nodes=np.int64(n + 1))
+    for k, v in model.state_dict().items():
+        arrays['w:' + k] = v.numpy()
+    save('model_dense_%s_%s' % (agg, prep), **arrays)
+
+
 if __name__ == '__main__':
     gen_sampler_canonical()
     gen_sampler_general()
@@ -172,3 +215,4 @@ if __name__ == '__main__':
     gen_model('mean', 'node_embedding', with_feats=False)       # the Pokec recipe (run.sh:30-34)
     gen_model('max_pool', 'node_embedding', with_feats=False)   # BASELINE config C3
     gen_model('attention', 'node_embedding', with_feats=False)
+    gen_model_dense('mean', 'identity')                          # BASELINE config C1: train.py's default sampler

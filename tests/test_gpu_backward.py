@@ -72,6 +72,32 @@ def test_train_step_matches_reference_optimizer_step(g):
     np.testing.assert_allclose(after.cpu().numpy(), want.numpy(), rtol=2e-3, atol=2e-4)
 
 
+def test_gradients_of_the_pokec_recipe_match_autograd(g):
+    """utils/pokec.sh: mean aggregator + NodeEmbeddingPrep without features.  Every parameter gradient -- layer weights,
+    prep.fc, and the dense (n_nodes + 1, 64) embedding-table gradient -- against torch autograd through the CPU oracle on
+    the same sampled ids.  fp32: rtol 2e-3 / atol 2e-5 (atomics reorder the sums)."""
+    fix = util.load('model_mean_node_embedding_nofeats')
+    model = build_model(g, fix, 'mean', 'node_embedding', False)
+    targets = torch.from_numpy(np.random.RandomState(0).randint(0, fix['logits'].shape[1], fix['ids0'].shape[0]))
+    g.set_seeds(int(fix['seed']))
+    preds, loss = model.train_step(torch.from_numpy(fix['ids0']), None, targets.cuda(), F.cross_entropy, optimizer=None, clip=None)
+    assert np.array_equal(model.peek('ids2').cpu().numpy(), fix['ids2'])
+    hop_ids = [torch.from_numpy(fix[k]) for k in ('ids0', 'ids1', 'ids2')]
+    ps = {k: v.clone().requires_grad_(True) for k, v in util.params_of(fix).items()}
+    logits = layers.forward_stack(hop_ids, None, ps, aggregator='mean', prep='node_embedding', n_nodes=int(fix['n_nodes']))
+    want_loss = F.cross_entropy(logits, targets)
+    want_loss.backward()
+    assert abs(loss.item() - want_loss.item()) < 1e-4
+    for name, p in model.named_parameters():
+        np.testing.assert_allclose(p.grad.cpu().numpy(), ps[name].grad.numpy(), err_msg=name, rtol=2e-3, atol=2e-5)
+    # one Adam step moves the embedding rows that were touched, and the engine picks the new table up
+    opt = torch.optim.Adam(model.parameters(), lr=0.01)
+    before = model.prep.embedding.weight.detach().clone()
+    g.set_seeds(int(fix['seed']))
+    model.train_step(torch.from_numpy(fix['ids0']), None, targets.cuda(), F.cross_entropy, optimizer=opt, clip=5.0)
+    assert (model.prep.embedding.weight.detach() - before).abs().max().item() > 0
+
+
 def test_backward_rejects_unsupported_plugins(g):
     fix = util.load('model_max_pool_identity')
     model = build_model(g, fix, 'max_pool', 'identity', True)

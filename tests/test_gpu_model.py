@@ -182,3 +182,26 @@ def test_sample_ahead_host_entry(g):
     model.forward_host(ids, torch.from_numpy(fix['feats']), out)
     assert np.array_equal(model.peek('ids2').cpu().numpy(), fix['ids2'])
     np.testing.assert_allclose(out.numpy(), fix['logits'], rtol=1e-4, atol=1e-5)
+
+
+@pytest.mark.parametrize('dtype,tol', [(torch.float32, dict(rtol=1e-4, atol=1e-5)), (torch.bfloat16, dict(rtol=3e-2, atol=3e-2))])
+def test_engine_with_the_dense_sampler_matches_reference(g, dtype, tol):
+    """train.py's DEFAULT sampler (`uniform_neighbor_sampler`, nn_modules.py:19-49) through the engine: the two
+    torch.randperm(K) draws come from the CPU generator like the reference's, so ids are bit-exact under the same seed."""
+    fix = util.load('model_dense_mean_identity')
+    S1, S2 = [int(s) for s in fix['fanout']]
+    O1, O2 = [int(s) for s in fix['out_dims']]
+    adj = torch.from_numpy(fix['adj'])
+    model = g.GSSupervised(
+        input_dim=fix['feats'].shape[1], n_nodes=int(fix['n_nodes']), n_classes=fix['logits'].shape[1],
+        layer_specs=[dict(n_train_samples=S1, n_val_samples=S1, output_dim=O1, activation=F.relu),
+                     dict(n_train_samples=S2, n_val_samples=S2, output_dim=O2, activation=lambda x: x)],
+        aggregator_class=g.aggregator_lookup['mean'], prep_class=g.prep_lookup['identity'],
+        sampler_class=g.sampler_lookup['uniform_neighbor_sampler'], adj=adj, train_adj=adj, compute_dtype=dtype)
+    model.load_state_dict(util.params_of(fix), strict=True)
+    model = model.cuda()
+    g.set_seeds(int(fix['seed']))
+    logits = model(torch.from_numpy(fix['ids0']), torch.from_numpy(fix['feats']), train=True)
+    assert np.array_equal(model.peek('ids1').cpu().numpy(), fix['ids1'].reshape(-1))
+    assert np.array_equal(model.peek('ids2').cpu().numpy(), fix['ids2'].reshape(-1))
+    np.testing.assert_allclose(logits.cpu().numpy(), fix['logits'], **tol)

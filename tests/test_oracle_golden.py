@@ -93,6 +93,19 @@ def test_forward_stack_matches_reference(agg, prep, with_feats):
     np.testing.assert_allclose(out64.numpy(), fix['logits'], rtol=2e-4, atol=2e-5)
 
 
+def test_forward_stack_with_the_dense_sampler_matches_reference():
+    """BASELINE config C1's path: train.py's default `uniform_neighbor_sampler` (dense table, one torch.randperm per hop)."""
+    fix = util.load('model_dense_mean_identity')
+    torch.manual_seed(int(fix['seed']))
+    K = fix['adj'].shape[1]
+    ids1 = sampler.dense_sample(fix['adj'], fix['ids0'], int(fix['fanout'][0]), torch.randperm(K).numpy())
+    ids2 = sampler.dense_sample(fix['adj'], ids1.reshape(-1), int(fix['fanout'][1]), torch.randperm(K).numpy())
+    assert np.array_equal(ids1, fix['ids1']) and np.array_equal(ids2, fix['ids2'])
+    hop_ids = [torch.from_numpy(np.ascontiguousarray(a).reshape(-1)) for a in (fix['ids0'], ids1, ids2)]
+    out = layers.forward_stack(hop_ids, torch.from_numpy(fix['feats']), util.params_of(fix), n_nodes=int(fix['n_nodes']))
+    np.testing.assert_allclose(out.numpy(), fix['logits'], rtol=1e-5, atol=1e-6)
+
+
 @pytest.mark.skipif(not util.have_reference(), reason='live reference only exists in the build container')
 def test_oracle_against_live_reference_random_graphs():
     """Beyond the committed fixtures: fresh random graphs / seeds through the reference's sampler class."""
