@@ -47,6 +47,7 @@ WORKLOADS = {
     'pokec-mean': ('pokec', 'mean', 'node_embedding', 'f32', False),  # north-star 60 % target shape
     'pokec-mean-tf32': ('pokec', 'mean', 'node_embedding', 'tf32', False),    # same, projections as TF32 on tcgen05
     'pokec-maxpool': ('pokec', 'max_pool', 'node_embedding', 'bf16', False),  # configs[2] (bf16 compute: the MLP is tensor-bound)
+    'reddit-maxpool': ('reddit', 'max_pool', 'identity', 'bf16', True),      # max-pool on the reddit shape (trainable: identity prep)
     'plaw2m-attention': ('plaw2m', 'attention', 'identity', 'bf16', True),   # configs[3]
     'big10m': ('big10m', 'mean', 'identity', 'bf16', True),                   # configs[4]
     'tiny': ('tiny', 'mean', 'identity', 'f32', True),
@@ -387,7 +388,8 @@ def run_ours(args):
 
     # ---- one optimiser step per batch (forward + loss + backward + gradient all-reduce + clip + Adam) ---------------
     train = None
-    trainable = prob['aggregator'] == 'mean' and (prob['prep'] == 'identity' or (prob['prep'] == 'node_embedding' and dtype == torch.float32 and not tf32))
+    trainable = (prob['aggregator'] == 'mean' and (prob['prep'] == 'identity' or (prob['prep'] == 'node_embedding' and dtype == torch.float32 and not tf32))) or \
+                (prob['aggregator'] in ('max_pool', 'mean_pool') and prob['prep'] == 'identity' and dtype == torch.bfloat16)
     if trainable and not args.no_train:
         from torch.nn import functional as F
         if prob['task'] == 'regression_mae':                                       # problem.py:39-41: l1 loss on (B, 1) predictions

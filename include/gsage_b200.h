@@ -304,6 +304,13 @@ int gsage_wgrad(const void* g_dev, int g_dtype, int64_t ldg, int O, const void* 
 typedef struct gsage_embedding_grads { float* gx_raw; float* gn_raw; float* csum; float* d_table; } gsage_embedding_grads;
 int gsage_engine_backward_layer1_embedding(gsage_engine* e, const gsage_embedding_grads* g, void* stream);
 
+/* Every parameter gradient of a max / mean pool model (bf16 compute, identity prep, output_dim 128) in one call; replaces
+ * the _head / _layer1 pair for such models (nn_modules.py:207-256 through loss.backward(), models.py:101).  `pg`: gradients
+ * of agg_layers.k.mlp.0.weight (hidden, d_in) / .bias (hidden).  All buffers fp32, overwritten. */
+typedef struct gsage_pool_grads { float* mlp_w[2]; float* mlp_b[2]; } gsage_pool_grads;
+int gsage_engine_backward_pool(gsage_engine* e, const float* dlogits_dev, const gsage_grads* grads, const gsage_pool_grads* pool_grads,
+                               void* stream);
+
 /* keep != 0: the next forwards keep every activation the backward pass needs (training).  0 (default): forward-only
  * streaming -- intermediates may be processed in L2-sized chunks that reuse their buffers. */
 int gsage_engine_keep_activations(gsage_engine* e, int keep);

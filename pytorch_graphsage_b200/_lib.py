@@ -45,6 +45,10 @@ class Grads(C.Structure):
     _fields_ = [('fc_x', c_p * 2), ('fc_neib', c_p * 2), ('fc_w', c_p), ('fc_b', c_p)]
 
 
+class PoolGrads(C.Structure):
+    _fields_ = [('mlp_w', c_p * 2), ('mlp_b', c_p * 2)]
+
+
 class EmbeddingGrads(C.Structure):
     _fields_ = [('gx_raw', c_p), ('gn_raw', c_p), ('csum', c_p), ('d_table', c_p)]
 
@@ -102,6 +106,7 @@ _SIGNATURES = {
     'gsage_engine_workspace_bytes': (c_i64, [c_p]),
     'gsage_engine_backward_head': (C.c_int, [c_p, c_p, C.POINTER(Grads), c_p]),
     'gsage_engine_backward_layer1': (C.c_int, [c_p, C.POINTER(Grads), c_p]),
+    'gsage_engine_backward_pool': (C.c_int, [c_p, c_p, C.POINTER(Grads), C.POINTER(PoolGrads), c_p]),
     'gsage_engine_backward_layer1_embedding': (C.c_int, [c_p, C.POINTER(EmbeddingGrads), c_p]),
     'gsage_wgrad': (C.c_int, [c_p, C.c_int, c_i64, C.c_int, c_p, C.c_int, c_i64, c_p, C.c_int, c_i64, c_p, c_i64, C.c_int, c_p]),
     'gsage_engine_keep_activations': (C.c_int, [c_p, C.c_int]),

@@ -11,7 +11,7 @@ int wgrad_launch(const float* G, int64_t ldg, int O, const void* A, int a_dtype,
 // for i < n_ids (S consecutive ids share one source row: the mean aggregator's broadcast; S = 1 for self rows)
 int embedding_scatter_launch(const float* rows, int64_t ld, int d, const int64_t* ids, int64_t n_ids, int S, float scale,
                              float* table_grad, int64_t ld_table, int64_t table_rows, cudaStream_t s);
-// tensor-core version (wgrad_umma.cu): bf16 G and A, O == 128; up to two jobs (the fc_x / fc_neib pair) per launch
+// tensor-core version (wgrad_umma.cu): bf16 G and A, O == 128; up to four jobs per launch (all with the same n and d)
 struct WgradJob {
     const void* G; int g_dtype; int64_t ldg; int O;       // G: (n, O) slice of the output gradient
     const void* A; int a_dtype; int64_t lda; const int64_t* ids; int d;

@@ -49,6 +49,16 @@ __global__ void __launch_bounds__(256) to_bf16_padded_kernel(const float* __rest
     dst[i] = __float2bfloat16_rn(c < cols ? src[(int64_t)r * cols + c] : 0.0f);
 }
 
+// fp32 (rows, cols) -> bf16 TRANSPOSED (cols, ld) with zero padding: the K-major operand of a data-gradient projection
+// (dX = dY . W is `out = A . W'^T` with W' = W^T)
+__global__ void __launch_bounds__(256) transpose_to_bf16_kernel(const float* __restrict__ src, int rows, int cols,
+                                                                __nv_bfloat16* __restrict__ dst, int64_t ld) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (int64_t)cols * ld) return;
+    const int c = (int)(i / ld), r = (int)(i % ld);
+    dst[i] = __float2bfloat16_rn(r < rows ? src[(int64_t)r * cols + c] : 0.0f);
+}
+
 __global__ void __launch_bounds__(256) axpy_kernel(float* y, const float* x, int n) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) y[i] += x[i];
@@ -119,6 +129,10 @@ struct gsage_engine {
     // weights as the kernels read them (fp32 originals, or bf16 copies when compute dtype is bf16)
     char* wb = nullptr; int64_t wb_bytes = 0;
     WRef w_x[2], w_n[2], w_mlp[2], w_att1[2];
+    WRef w_nT[2], w_mlpT[2];            // pool backward (bf16): fc_neib^T (H x O) and mlp.0.weight^T (d_in x H), K-major
+    float* DP = nullptr;                // pool backward: d loss / d pooled rows, (n0 + n1) x H fp32
+    void* DHID = nullptr;               // pool backward: d loss / d hidden rows, (n1 + n2) x H bf16
+    float* DN2 = nullptr;               // pool backward: d loss / d (layer-2 neighbour rows), n1 x 2*O1 fp32
     // backward scratch (fp32): d zn / d z (B x 2*O2), d h0 / d m2 (B x 2*O1), d H (26B x 2*O1)
     float* DZN = nullptr; float* DZ = nullptr; float* DH0 = nullptr; float* DM2 = nullptr; float* DH = nullptr;
     // NodeEmbeddingPrep without feats is an affine map of the gathered embedding row; every consumer of layer 1 is
@@ -232,13 +246,14 @@ static int apply_aggregator(gsage_engine* e, int layer, const RowSrc& x, const R
             // MLP on tcgen05 with the pool (max / mean over the S neighbour rows) done in the epilogue: the (n*S, 512)
             // hidden rows never exist in HBM
             LinearParams P;
-            P.n_segs = 1; P.n = n * S; P.act = GSAGE_ACT_RELU; P.out = e->Pp; P.out_dtype = T; P.ld_out = H;
+            void* const Pb = (char*)e->Pp + m_row0 * (int64_t)H * (int64_t)dtype_size(T);       // this application's pooled rows
+            P.n_segs = 1; P.n = n * S; P.act = GSAGE_ACT_RELU; P.out = Pb; P.out_dtype = T; P.ld_out = H;
             P.seg[0] = LinearSeg{nb.base, nb.dtype, nb.ld, nb.ids, e->w_mlp[layer].p, e->w_mlp[layer].dtype, e->w_mlp[layer].ld, d, H,
                                  e->b_mlp[layer], 0};
             P.pool_S = S; P.pool_max = e->cfg.aggregator == GSAGE_AGG_MAX_POOL ? 1 : 0;
             if (linear_pool_umma_eligible(P)) {
                 GS_TRY(linear_dispatch(P, 0, s));
-                RowSrc p{e->Pp, T, H, n, nullptr, H};
+                RowSrc p{Pb, T, H, n, nullptr, H};
                 return combine_call(x, e->w_x[layer], p, e->w_n[layer], O, n, act, out, out_dtype, ld_out, exact, s, e->b_x[layer], nullptr);
             }
         }
@@ -333,7 +348,7 @@ int gsage_engine_create(const gsage_engine_config* cfg, gsage_engine** out) {
     int64_t o_HN = -1, o_P = -1, o_T1 = -1, o_NA = -1, o_T1x = -1, o_XA = -1, o_AW = -1;
     if (cfg->aggregator == GSAGE_AGG_MAX_POOL || cfg->aggregator == GSAGE_AGG_MEAN_POOL) {
         o_HN = carve(es * e->hid * e->n2);
-        o_P = carve(es * e->hid * e->n1);
+        o_P = carve(es * e->hid * (e->n0 + e->n1 + e->n0));       // pooled rows of all three applications (kept for the backward)
     }
     if (cfg->aggregator == GSAGE_AGG_ATTENTION) {
         o_T1 = carve(4 * e->hid * e->n2); o_NA = carve(4 * e->hid * e->n2);
@@ -348,6 +363,11 @@ int gsage_engine_create(const gsage_engine_config* cfg, gsage_engine** out) {
     const int64_t o_DH0 = carve(4 * 2 * O1 * e->n0), o_DM2 = carve(4 * 2 * O1 * e->n0);
     const int64_t o_DH = carve(4 * 2 * O1 * (e->n0 + e->n1));
     const int64_t o_DXE = e->fold_prep ? carve(4 * (int64_t)cfg->emb_dim * (e->n0 + e->n1)) : -1;
+    const bool pool_cfg = cfg->aggregator == GSAGE_AGG_MAX_POOL || cfg->aggregator == GSAGE_AGG_MEAN_POOL;
+    const bool pool_bwd = pool_cfg && e->T == GSAGE_BF16 && cfg->prep == GSAGE_PREP_IDENTITY && getenv("GSAGE_NO_POOL_BACKWARD") == nullptr;
+    const int64_t o_DP = pool_bwd ? carve(4 * (int64_t)e->hid * (e->n0 + e->n1)) : -1;
+    const int64_t o_DHID = pool_bwd ? carve(2 * (int64_t)e->hid * (e->n1 + e->n2)) : -1;
+    const int64_t o_DN2 = pool_bwd ? carve(4 * 2 * O1 * e->n1) : -1;
     e->ws_bytes = off;
     if (cudaMalloc((void**)&e->ws, (size_t)off) != cudaSuccess) {
         set_error("engine_create: cudaMalloc of %lld workspace bytes failed", (long long)off);
@@ -364,7 +384,7 @@ int gsage_engine_create(const gsage_engine_config* cfg, gsage_engine** out) {
     }
     if (e->T == GSAGE_BF16) {                // arena for the padded bf16 weight copies the tensor-core kernel reads
         const int64_t dmax0 = std::max<int64_t>(e->ld_prep, 2 * O1) + 8;
-        e->wb_bytes = 2 * 2 * ((O1 + O2) * 2 * (dmax0 + e->hid) + 2 * (int64_t)e->hid * dmax0) + 16 * 256;
+        e->wb_bytes = 2 * (2 * 2 * ((O1 + O2) * 2 * (dmax0 + e->hid) + 2 * (int64_t)e->hid * dmax0) + 16 * 256);   // + the transposed copies
         if (cudaMalloc((void**)&e->wb, (size_t)e->wb_bytes) != cudaSuccess) {
             set_error("engine_create: cudaMalloc of the weight arena failed");
             cudaFree(e->ws);
@@ -379,6 +399,7 @@ int gsage_engine_create(const gsage_engine_config* cfg, gsage_engine** out) {
     e->T1 = at(o_T1); e->NA = at(o_NA); e->T1x = at(o_T1x); e->XA = at(o_XA); e->AW = (float*)at(o_AW);
     e->H1 = at(o_H1); e->Z = (float*)at(o_Z); e->ZN = (float*)at(o_ZN); e->LG = (float*)at(o_LG);
     e->DXE = (float*)at(o_DXE);
+    e->DP = (float*)at(o_DP); e->DHID = at(o_DHID); e->DN2 = (float*)at(o_DN2);
     e->DZN = (float*)at(o_DZN); e->DZ = (float*)at(o_DZ); e->DH0 = (float*)at(o_DH0); e->DM2 = (float*)at(o_DM2); e->DH = (float*)at(o_DH);
     *out = e;
     return GSAGE_OK;
@@ -497,6 +518,21 @@ int gsage_engine_set_weights(gsage_engine* e, const gsage_weights* w, void* stre
             GS_LAUNCHED();
             *it.dst = WRef{dst, GSAGE_BF16, ld};
             off += bytes;
+        }
+        if (pool && e->T == GSAGE_BF16 && e->DP) {
+            // K-major transposed copies for the pool backward's data-gradient projections
+            struct TItem { const float* src; int rows, cols; WRef* dst; } titems[2] = {
+                {w->layer[l].fc_neib, O, e->hid, &e->w_nT[l]}, {w->layer[l].mlp_w, e->hid, d_in, &e->w_mlpT[l]}};
+            for (const TItem& it : titems) {
+                const int64_t ld = pad_to(it.rows, 8);
+                const int64_t bytes = pad_to(2 * ld * it.cols, 256);
+                GS_CHECK_ARG(off + bytes <= e->wb_bytes, "engine_set_weights: bf16 weight arena too small (transposed copies)");
+                __nv_bfloat16* dst = (__nv_bfloat16*)(e->wb + off);
+                transpose_to_bf16_kernel<<<(unsigned)ceil_div((int64_t)it.cols * ld, 256), 256, 0, s>>>(it.src, it.rows, it.cols, dst, ld);
+                GS_LAUNCHED();
+                *it.dst = WRef{dst, GSAGE_BF16, ld};
+                off += bytes;
+            }
         }
     }
     e->have_weights = true;
@@ -849,6 +885,97 @@ int gsage_engine_backward_layer1_embedding(gsage_engine* e, const gsage_embeddin
     GS_TRY(linear_trans_call(e->DH + O1, 2 * O1, O1, e->fold_wn, de, de, rows, e->DXE, de, s));            // Gn . W'n
     GS_TRY(embedding_scatter_launch(e->DXE, de, de, ids1, n1, S1, 1.0f / (float)S1, g->d_table, de, trows, s));
     GS_TRY(embedding_scatter_launch(e->DXE + n0 * de, de, de, ids2, n2, S2, 1.0f / (float)S2, g->d_table, de, trows, s));
+    return mark_slot_done(e, s);
+}
+
+// Full parameter-gradient pass for the pool aggregators (bf16 compute, identity prep; nn_modules.py:207-256).
+//   out = act([Wx x | Wn p]),  p = pool_j relu(W1 n_j + b1)
+// Per application, from G = d loss / d pre-activation:  dWx = Gx^T x,  dWn = Gn^T p,  dP = Gn Wn,
+//   dHid = pool'(dP) -- the forward's MLP is RECOMPUTED on the tensor cores and the gradient routed to the arg-max row (or
+//   spread over the open relus for the mean pool) by linear_pool_ws_umma_kernel<.., BWD>; it is the one large intermediate
+//   (rows x H bf16) --  dW1 = dHid^T n (wgrad_umma, 128-unit blocks as parallel jobs),  db1 = column sums (in the same kernel),
+//   and for layer 2 the input gradient dN = dHid W1 that flows into layer 1.
+int gsage_engine_backward_pool(gsage_engine* e, const float* dlogits, const gsage_grads* g, const gsage_pool_grads* pg, void* stream) {
+    GS_CHECK_ARG(e && e->have_weights && e->B > 0, "engine_backward_pool: run gsage_engine_forward first");
+    const gsage_engine_config& c = e->cfg;
+    const bool pool = c.aggregator == GSAGE_AGG_MAX_POOL || c.aggregator == GSAGE_AGG_MEAN_POOL;
+    GS_CHECK_ARG(pool && c.prep == GSAGE_PREP_IDENTITY && e->T == GSAGE_BF16 && e->DP,
+                 "engine_backward_pool: implemented for the max / mean pool aggregators with the identity prep in bf16 compute mode");
+    GS_CHECK_ARG(e->keep_activations, "engine_backward_pool: call gsage_engine_keep_activations(e, 1) before the forward");
+    GS_CHECK_ARG(dlogits && g && pg && g->fc_w && g->fc_b && g->fc_x[0] && g->fc_x[1] && g->fc_neib[0] && g->fc_neib[1] &&
+                 pg->mlp_w[0] && pg->mlp_w[1] && pg->mlp_b[0] && pg->mlp_b[1], "engine_backward_pool: NULL argument");
+    const int O1 = c.out_dim[0], O2 = c.out_dim[1], C = c.n_classes, S1 = c.fanout[0], S2 = c.fanout[1], H = e->hid, d = c.feats_dim;
+    GS_CHECK_ARG(O1 == 128 && O2 == 128 && H % 128 == 0, "engine_backward_pool: needs output_dim 128 and a hidden width that is a multiple of 128 "
+                 "(the tensor-core weight-gradient kernel works on 128-row blocks)");
+    cudaStream_t s = as_stream(stream);
+    const int64_t n0 = e->B, n1 = n0 * S1, n2 = n1 * S2, rows = n0 + n1;
+    const int pool_max = c.aggregator == GSAGE_AGG_MAX_POOL ? 1 : 0;
+    const __nv_bfloat16* H1 = (const __nv_bfloat16*)e->H1;
+    const __nv_bfloat16* Pp = (const __nv_bfloat16*)e->Pp;
+    __nv_bfloat16* DHID = (__nv_bfloat16*)e->DHID;
+    const int64_t* ids0 = e->ids; const int64_t* ids1 = ids0 + n0; const int64_t* ids2 = ids1 + n1;
+
+    auto pool_bwd = [&](int layer, const void* a, int64_t lda, const int64_t* ids, int d_in, int64_t n_rows, int S, const float* dP,
+                        __nv_bfloat16* dhid, float* db) -> int {
+        LinearParams P;
+        P.n_segs = 1; P.n = n_rows; P.act = GSAGE_ACT_RELU; P.out = nullptr; P.out_dtype = GSAGE_BF16; P.ld_out = H;
+        P.seg[0] = LinearSeg{a, GSAGE_BF16, lda, ids, e->w_mlp[layer].p, GSAGE_BF16, e->w_mlp[layer].ld, d_in, H, e->b_mlp[layer], 0};
+        P.pool_S = S; P.pool_max = pool_max;
+        return linear_pool_ws_umma_backward_launch(P, dP, H, dhid, H, db, s);
+    };
+    auto mlp_wgrad = [&](const __nv_bfloat16* dhid, const void* a, int64_t lda, const int64_t* ids, int d_in, int64_t n_rows, float* dW) -> int {
+        for (int b0 = 0; b0 < H / 128; b0 += 4) {                      // 128-unit blocks of the hidden layer as parallel jobs
+            WgradJob jobs[4];
+            const int nj = std::min(4, H / 128 - b0);
+            for (int j = 0; j < nj; ++j)
+                jobs[j] = WgradJob{dhid + (b0 + j) * 128, GSAGE_BF16, (int64_t)H, 128, a, GSAGE_BF16, lda, ids, d_in, n_rows,
+                                   dW + (int64_t)(b0 + j) * 128 * d_in, (int64_t)d_in};
+            GS_TRY(wgrad_umma_launch(jobs, nj, s));
+        }
+        return GSAGE_OK;
+    };
+
+    // ---- classifier + F.normalize (as gsage_engine_backward_head) --------------------------------------------------
+    GS_TRY(wgrad_launch(dlogits, C, C, e->ZN, GSAGE_F32, 2 * O2, nullptr, 2 * O2, n0, g->fc_w, 2 * O2, s));
+    GS_TRY(colsum_launch(dlogits, n0, C, g->fc_b, s));
+    GS_TRY(linear_trans_call(dlogits, C, C, e->w.fc_w, 2 * O2, 2 * O2, n0, e->DZN, 2 * O2, s));
+    GS_TRY(l2_normalize_bwd_launch(e->Z, e->DZN, n0, 2 * O2, c.act[1], e->DZ, s));
+    // ---- layer 2 on (h0, h1): x = H1[:n0], neighbours = H1[n0:] in place, pooled rows P2 ----------------------------
+    const __nv_bfloat16* P2 = Pp + (n0 + n1) * (int64_t)H;
+    GS_TRY(wgrad_launch(e->DZ, 2 * O2, O2, H1, GSAGE_BF16, e->ld_h1, nullptr, 2 * O1, n0, g->fc_x[1], 2 * O1, s));
+    GS_TRY(wgrad_launch(e->DZ + O2, 2 * O2, O2, P2, GSAGE_BF16, H, nullptr, H, n0, g->fc_neib[1], H, s));
+    GS_TRY(linear_trans_call(e->DZ, 2 * O2, O2, e->w.layer[1].fc_x, 2 * O1, 2 * O1, n0, e->DH0, 2 * O1, s));      // d h0
+    GS_TRY(linear_trans_call(e->DZ + O2, 2 * O2, O2, e->w.layer[1].fc_neib, H, H, n0, e->DP, H, s));              // d P2
+    GS_CUDA(cudaMemsetAsync(pg->mlp_b[1], 0, sizeof(float) * H, s));
+    GS_TRY(pool_bwd(1, H1 + n0 * e->ld_h1, e->ld_h1, nullptr, 2 * O1, n1, S1, e->DP, DHID, pg->mlp_b[1]));
+    GS_TRY(mlp_wgrad(DHID, H1 + n0 * e->ld_h1, e->ld_h1, nullptr, 2 * O1, n1, pg->mlp_w[1]));
+    {   // d H1[n0:] = dHid2 . W1_2  (n1 x H -> 2*O1): the projection kernel on the transposed weights
+        LinearParams P;
+        P.n_segs = 1; P.n = n1; P.act = GSAGE_ACT_NONE; P.out = e->DN2; P.out_dtype = GSAGE_F32; P.ld_out = 2 * O1;
+        P.seg[0] = LinearSeg{DHID, GSAGE_BF16, (int64_t)H, nullptr, e->w_mlpT[1].p, GSAGE_BF16, e->w_mlpT[1].ld, H, 2 * O1, nullptr, 0};
+        GS_TRY(linear_dispatch(P, 0, s));
+    }
+    // d (layer-1 pre-activation): [d h0 ; d H1[n0:]] * relu'(H1), bf16 (operand of the tensor-core weight gradients)
+    GS_TRY(layer1_grad_launch(e->DH0, e->DN2, e->H1, e->T, e->ld_h1, n0, n1, 1, 2 * O1, c.act[0], e->DH, GSAGE_BF16, s));
+    // ---- layer 1 on (x0, x1) and (x1, x2), shared weights ------------------------------------------------------------------
+    const __nv_bfloat16* dh = (const __nv_bfloat16*)e->DH;
+    {
+        WgradJob jx{dh, GSAGE_BF16, 2 * (int64_t)O1, O1, c.feats_dev, c.feats_dtype, c.feats_ld, ids0, d, rows, g->fc_x[0], (int64_t)d};
+        GS_CHECK_ARG(wgrad_umma_eligible(jx), "engine_backward_pool: the feature table does not qualify for the tensor-core weight gradient");
+        GS_TRY(wgrad_umma_launch(&jx, 1, s));
+        WgradJob jn{dh + O1, GSAGE_BF16, 2 * (int64_t)O1, O1, Pp, GSAGE_BF16, (int64_t)H, nullptr, H, rows, g->fc_neib[0], (int64_t)H};
+        GS_TRY(wgrad_umma_launch(&jn, 1, s));
+    }
+    {   // d P1 = Gn . Wn1  ((n0 + n1) x O1 -> H)
+        LinearParams P;
+        P.n_segs = 1; P.n = rows; P.act = GSAGE_ACT_NONE; P.out = e->DP; P.out_dtype = GSAGE_F32; P.ld_out = H;
+        P.seg[0] = LinearSeg{dh + O1, GSAGE_BF16, 2 * (int64_t)O1, nullptr, e->w_nT[0].p, GSAGE_BF16, e->w_nT[0].ld, O1, H, nullptr, 0};
+        GS_TRY(linear_dispatch(P, 0, s));
+    }
+    GS_CUDA(cudaMemsetAsync(pg->mlp_b[0], 0, sizeof(float) * H, s));
+    GS_TRY(pool_bwd(0, c.feats_dev, c.feats_ld, ids1, d, n1, S1, e->DP, DHID, pg->mlp_b[0]));                              // (x0, x1)
+    GS_TRY(pool_bwd(0, c.feats_dev, c.feats_ld, ids2, d, n2, S2, e->DP + n0 * (int64_t)H, DHID + n1 * (int64_t)H, pg->mlp_b[0]));   // (x1, x2)
+    GS_TRY(mlp_wgrad(DHID, c.feats_dev, c.feats_ld, ids1, d, n1 + n2, pg->mlp_w[0]));
     return mark_slot_done(e, s);
 }
 

@@ -39,6 +39,8 @@ int attention_fused_launch(const void* a, int64_t lda, const int64_t* ids, int d
 // weight-stationary, double-buffered version of the pool kernel (linear_pool_ws_umma.cu): relu, S <= 64
 bool linear_pool_ws_umma_eligible(const LinearParams& P);
 int linear_pool_ws_umma_launch(const LinearParams& P, cudaStream_t s);
+int linear_pool_ws_umma_backward_launch(const LinearParams& P, const float* dP, int64_t ld_dp, void* dhid, int64_t ld_dhid, float* db,
+                                        cudaStream_t s);
 // picks the tensor-core kernel when every operand qualifies and `exact` == 0, else the FFMA kernel
 int linear_dispatch(const LinearParams& P, int exact, cudaStream_t s);
 

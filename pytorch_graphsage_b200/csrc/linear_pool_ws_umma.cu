@@ -42,6 +42,9 @@ struct QParams {
     int64_t n_rows, n_parents;
     int n_tiles, h_blocks, bpp, n_phases, kchunks, uk, tf32;
     void* out; int out_bf16; int64_t ld_out;
+    // backward mode: recompute the hidden rows and emit d loss / d hidden (bf16) from d loss / d pooled
+    const float* dP; int64_t ld_dp; __nv_bfloat16* dhid; int64_t ld_dhid;
+    float* db;                                    // += column sums of d hidden (the MLP bias gradient); may be NULL
     int* err;
 };
 
@@ -56,7 +59,32 @@ __device__ __forceinline__ void q_store(const QParams& P, int64_t parent, int h,
     else reinterpret_cast<float*>(P.out)[at] = o;
 }
 
-template <bool POOL_MAX, int S_CT>
+// backward epilogue for one parent whose S accumulator values are v[0..S): gradient of the pooled value `g` goes to the FIRST
+// row that attains the max (torch.max's backward; rows drawn twice are identical, so which copy gets it does not change
+// dW) and only if relu let it through; the mean pool spreads g / S over the rows whose relu is open
+template <bool POOL_MAX, int S>
+__device__ __forceinline__ float q_backward_parent(const QParams& P, const float* v, float bias, float g, int64_t row0, int h, bool h_ok) {
+    float mx = -3.0e38f, total = 0.0f;
+#pragma unroll
+    for (int j = 0; j < S; ++j) mx = fmaxf(mx, v[j]);
+    const bool gate = mx + bias > 0.0f;
+    bool found = false;
+#pragma unroll
+    for (int j = 0; j < S; ++j) {
+        float o;
+        if (POOL_MAX) {
+            const bool hit = gate && !found && v[j] == mx;
+            found = found || hit;
+            o = hit ? g : 0.0f;
+        } else {
+            o = (v[j] + bias > 0.0f) ? g * (1.0f / (float)S) : 0.0f;
+        }
+        if (h_ok && row0 + j < P.n_rows) { P.dhid[(row0 + j) * P.ld_dhid + h] = __float2bfloat16_rn(o); total += o; }
+    }
+    return total;
+}
+
+template <bool POOL_MAX, int S_CT, bool BWD>
 __global__ void __launch_bounds__(kQThreads, 1) linear_pool_ws_umma_kernel(const QParams P, const __grid_constant__ QMaps M) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     // carve: [W of a phase: bpp x kchunks x 16 KB] [ring: 8 x 8 KB row chunks] [barriers]
@@ -99,6 +127,7 @@ __global__ void __launch_bounds__(kQThreads, 1) linear_pool_ws_umma_kernel(const
             const int h = hb * QM + quarter * 32 + lane;
             const bool h_ok = mine && h < P.H;
             const float bias = (P.bias && h_ok) ? __ldg(P.bias + h) : 0.0f;
+            float bsum = 0.0f;                                 // backward: this hidden unit's bias gradient over the CTA's tiles
             for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x, ++it) {
                 const int buf = it & 1;
                 mbar_wait(tfull_bar(buf), (it >> 1) & 1, P.err);
@@ -110,6 +139,37 @@ __global__ void __launch_bounds__(kQThreads, 1) linear_pool_ws_umma_kernel(const
                     tmem_ld32(taddr, r0);
                     tmem_ld32(taddr + 32, r1);
                     tmem_ld_wait();
+                    if (BWD) {
+                        // ---- backward: d hidden[row, h] from d pooled[parent, h] (the forward's MMAs recomputed) ----
+                        float v[QN];
+#pragma unroll
+                        for (int i = 0; i < QN; ++i) v[i] = __uint_as_float(i < 32 ? r0[i & 31] : r1[i & 31]);
+                        if (S_CT > 0) {
+#pragma unroll
+                            for (int p = 0; p < QN / (S_CT > 0 ? S_CT : 1); ++p) {
+                                const bool p_ok = parent0 + p < P.n_parents;
+                                const float g = (h_ok && p_ok) ? __ldg(P.dP + (parent0 + p) * P.ld_dp + h) : 0.0f;
+                                bsum += q_backward_parent<POOL_MAX, (S_CT > 0 ? S_CT : 1)>(P, v + p * S_CT, bias, g, (parent0 + p) * (int64_t)S_CT, h, h_ok && p_ok);
+                            }
+                        } else {
+                            for (int p = 0; p < PT; ++p) {               // odd fanouts: dynamic indexing (local memory), correctness first
+                                const bool p_ok = parent0 + p < P.n_parents;
+                                const float g = (h_ok && p_ok) ? __ldg(P.dP + (parent0 + p) * P.ld_dp + h) : 0.0f;
+                                float mx = -3.0e38f;
+                                for (int j = 0; j < S; ++j) mx = fmaxf(mx, v[p * S + j]);
+                                const bool gate = mx + bias > 0.0f;
+                                bool found = false;
+                                for (int j = 0; j < S; ++j) {
+                                    const float x = v[p * S + j];
+                                    float o;
+                                    if (POOL_MAX) { const bool hit = gate && !found && x == mx; found = found || hit; o = hit ? g : 0.0f; }
+                                    else o = (x + bias > 0.0f) ? g * (1.0f / (float)S) : 0.0f;
+                                    const int64_t row = (parent0 + p) * (int64_t)S + j;
+                                    if (h_ok && p_ok && row < P.n_rows) { P.dhid[row * P.ld_dhid + h] = __float2bfloat16_rn(o); bsum += o; }
+                                }
+                            }
+                        }
+                    } else
                     if (S_CT > 0) {
                         // static parent boundaries: element i of the tile belongs to parent i / S_CT
 #pragma unroll
@@ -145,6 +205,7 @@ __global__ void __launch_bounds__(kQThreads, 1) linear_pool_ws_umma_kernel(const
                 tc_fence_before();
                 mbar_arrive(tempty_bar(buf));
             }
+            if (BWD && P.db && h_ok) atomicAdd(P.db + h, bsum);
         }
     } else if (warp == kQEpiWarps) {
         // ============ MMA ISSUER: D[buf][blk][hidden, row] += W[blk][kc] . rows[kc]^T, one thread, lean loop ============
@@ -265,8 +326,9 @@ bool linear_pool_ws_umma_eligible(const LinearParams& P) {
 
 static int* g_q_err = nullptr;
 
-int linear_pool_ws_umma_launch(const LinearParams& P, cudaStream_t s) {
+static int q_launch(const LinearParams& P, const float* dP, int64_t ld_dp, void* dhid, int64_t ld_dhid, float* db, cudaStream_t s) {
     const LinearSeg& g = P.seg[0];
+    const bool bwd = dhid != nullptr;
     QParams U;
     memset(&U, 0, sizeof(U));
     U.a = g.a; U.lda = g.lda; U.ids = g.ids; U.bias = g.bias; U.col0 = g.col0;
@@ -282,6 +344,7 @@ int linear_pool_ws_umma_launch(const LinearParams& P, cudaStream_t s) {
     GS_CHECK_ARG(U.bpp >= 1, "linear_pool_ws_umma: one hidden block of W does not fit in shared memory");
     U.n_phases = (U.h_blocks + U.bpp - 1) / U.bpp;
     U.out = P.out; U.out_bf16 = P.out_dtype == GSAGE_BF16; U.ld_out = P.ld_out;
+    U.dP = dP; U.ld_dp = ld_dp; U.dhid = (__nv_bfloat16*)dhid; U.ld_dhid = ld_dhid; U.db = db;
     if (!g_q_err) {
         GS_CUDA(cudaMalloc((void**)&g_q_err, sizeof(int)));
         GS_CUDA(cudaMemset(g_q_err, 0, sizeof(int)));
@@ -295,22 +358,39 @@ int linear_pool_ws_umma_launch(const LinearParams& P, cudaStream_t s) {
     else GS_TRY(make_map(&maps.a, g.a, P.n, g.d, g.lda, QN, es));
     const size_t smem = (size_t)U.bpp * U.kchunks * kQWChunk + (size_t)kQStages * kQRChunk + 1024 + 512;
     const int grid = U.n_tiles < sm_count() ? U.n_tiles : sm_count();
-#define GS_Q_LAUNCH(MX, SCT)                                                                                                       \
+#define GS_Q_LAUNCH(MX, SCT, BW)                                                                                                   \
     do {                                                                                                                           \
         static bool attr_set = false;                                                                                              \
         if (!attr_set) {                                                                                                           \
-            GS_CUDA(cudaFuncSetAttribute(linear_pool_ws_umma_kernel<MX, SCT>, cudaFuncAttributeMaxDynamicSharedMemorySize, kQSmemLimit)); \
+            GS_CUDA(cudaFuncSetAttribute(linear_pool_ws_umma_kernel<MX, SCT, BW>, cudaFuncAttributeMaxDynamicSharedMemorySize, kQSmemLimit)); \
             attr_set = true;                                                                                                       \
         }                                                                                                                          \
-        linear_pool_ws_umma_kernel<MX, SCT><<<grid, kQThreads, smem, s>>>(U, maps);                                                \
+        linear_pool_ws_umma_kernel<MX, SCT, BW><<<grid, kQThreads, smem, s>>>(U, maps);                                            \
+    } while (0)
+#define GS_Q_PICK(SCT)                                                                                                             \
+    do {                                                                                                                           \
+        if (bwd) { if (mx) GS_Q_LAUNCH(true, SCT, true); else GS_Q_LAUNCH(false, SCT, true); }                                     \
+        else { if (mx) GS_Q_LAUNCH(true, SCT, false); else GS_Q_LAUNCH(false, SCT, false); }                                       \
     } while (0)
     const bool mx = P.pool_max != 0;
-    if (U.S == 10) { if (mx) GS_Q_LAUNCH(true, 10); else GS_Q_LAUNCH(false, 10); }
-    else if (U.S == 25) { if (mx) GS_Q_LAUNCH(true, 25); else GS_Q_LAUNCH(false, 25); }
-    else { if (mx) GS_Q_LAUNCH(true, 0); else GS_Q_LAUNCH(false, 0); }
+    if (U.S == 10) GS_Q_PICK(10);
+    else if (U.S == 25) GS_Q_PICK(25);
+    else GS_Q_PICK(0);
+#undef GS_Q_PICK
 #undef GS_Q_LAUNCH
     GS_LAUNCHED();
     return GSAGE_OK;
+}
+
+int linear_pool_ws_umma_launch(const LinearParams& P, cudaStream_t s) { return q_launch(P, nullptr, 0, nullptr, 0, nullptr, s); }
+
+// backward of the fused MLP + pool: dhid[(p*S + j), h] (bf16, ld_dhid) = d loss / d (pre-relu hidden) from dP[p, h] = d loss / d pooled;
+// db[h] += sum over rows of dhid[:, h] (the caller zeroes db)
+int linear_pool_ws_umma_backward_launch(const LinearParams& P, const float* dP, int64_t ld_dp, void* dhid, int64_t ld_dhid, float* db,
+                                        cudaStream_t s) {
+    GS_CHECK_ARG(dP && dhid && ld_dhid >= P.seg[0].O && ld_dp >= P.seg[0].O, "linear_pool_ws_umma_backward: bad arguments");
+    GS_CHECK_ARG(linear_pool_ws_umma_eligible(P), "linear_pool_ws_umma_backward: operands do not qualify for the weight-stationary pool kernel");
+    return q_launch(P, dP, ld_dp, dhid, ld_dhid, db, s);
 }
 
 }  // namespace gsage

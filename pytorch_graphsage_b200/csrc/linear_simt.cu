@@ -169,7 +169,8 @@ int linear_dispatch(const LinearParams& P, int exact, cudaStream_t s) {
             one.seg[0].w = (const char*)g.w + (size_t)c * g.ldw * dtype_size(g.w_dtype);
             one.seg[0].bias = g.bias ? g.bias + c : nullptr;
             one.seg[0].col0 = g.col0 + c;
-            if (linear_umma_eligible(one)) GS_TRY(linear_umma_launch(one, s));
+            if (linear_ws_umma_eligible(one)) GS_TRY(linear_ws_umma_launch(one, s));
+            else if (linear_umma_eligible(one)) GS_TRY(linear_umma_launch(one, s));
             else { GS_CHECK_ARG(P.pool_S <= 1, "linear: column block does not qualify for the tensor-core kernel (pooled epilogue)"); GS_TRY(linear_simt_launch(one, s)); }
         }
     }

@@ -38,8 +38,10 @@ struct WgGemm {
     float* dW; int64_t lddw; int d;
 };
 
+static constexpr int kWgMaxJobs = 4;
+
 struct WgParams {
-    WgGemm gemm[2];
+    WgGemm gemm[kWgMaxJobs];
     int n_gemms; int n_tiles_n; int ksplit;
     int q;                   // 64-column boxes of A per N-tile (tile width = 64 * q <= 512)
     int64_t n;               // rows to reduce over
@@ -49,7 +51,7 @@ struct WgParams {
     int* err;
 };
 
-struct WgMaps { CUtensorMap g[2]; CUtensorMap a[2]; };
+struct WgMaps { CUtensorMap g[kWgMaxJobs]; CUtensorMap a[kWgMaxJobs]; };
 
 // MN-major, SWIZZLE_128B operand: atoms of [8 k-rows x 128 bytes]; LBO = bytes between atoms along MN, SBO = along K
 __device__ __forceinline__ uint64_t umma_desc_mn(uint32_t smem_addr, uint32_t lbo, uint32_t sbo) {
@@ -224,9 +226,10 @@ bool wgrad_umma_eligible(const WgradJob& j) {
 
 static int* g_wg_err = nullptr;
 
-// all jobs of one launch share n (rows), O = 128 and d (they are the fc_x / fc_neib pair of one layer application)
+// all jobs of one launch share n (rows), O = 128 and d (the fc_x / fc_neib pair of one layer application, or the four
+// 128-unit blocks of a pool MLP's weight gradient)
 int wgrad_umma_launch(const WgradJob* jobs, int n_jobs, cudaStream_t s) {
-    GS_CHECK_ARG(n_jobs >= 1 && n_jobs <= 2, "wgrad_umma: one or two jobs per launch");
+    GS_CHECK_ARG(n_jobs >= 1 && n_jobs <= kWgMaxJobs, "wgrad_umma: one to four jobs per launch");
     for (int i = 0; i < n_jobs; ++i) {
         GS_CHECK_ARG(wgrad_umma_eligible(jobs[i]), "wgrad_umma: job %d does not qualify (bf16, O == 128, aligned rows)", i);
         GS_CHECK_ARG(jobs[i].n == jobs[0].n && jobs[i].d == jobs[0].d, "wgrad_umma: jobs of one launch must share n and d");

@@ -254,6 +254,19 @@ class GSSupervised(nn.Module):
         bucket = self._bucket()
         g = _lib.Grads()
         aggs = list(self.agg_layers.children())
+        if self._agg_name in ('max_pool', 'mean_pool'):
+            # one call computes every gradient (gsage_engine_backward_pool); no head / layer-1 split to overlap with
+            pg = _lib.PoolGrads()
+            for k in range(2):
+                g.fc_x[k] = bucket.grad_of(aggs[k].fc_x.weight).data_ptr()
+                g.fc_neib[k] = bucket.grad_of(aggs[k].fc_neib.weight).data_ptr()
+                pg.mlp_w[k] = bucket.grad_of(aggs[k].mlp[0].weight).data_ptr()
+                pg.mlp_b[k] = bucket.grad_of(aggs[k].mlp[0].bias).data_ptr()
+            g.fc_w, g.fc_b = bucket.grad_of(self.fc.weight).data_ptr(), bucket.grad_of(self.fc.bias).data_ptr()
+            dlogits = dlogits.contiguous().float()
+            check(lib().gsage_engine_backward_pool(self._last['h'], ops.ptr(dlogits), C.byref(g), C.byref(pg), ops.stream()))
+            bucket.all_reduce(grad_scale)
+            return bucket
         for k in range(2):
             g.fc_x[k] = bucket.grad_of(aggs[k].fc_x.weight).data_ptr()
             g.fc_neib[k] = bucket.grad_of(aggs[k].fc_neib.weight).data_ptr()
