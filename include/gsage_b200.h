@@ -142,7 +142,8 @@ int gsage_attention_weights(const void* na_dev, const void* xa_dev, int dtype, i
  * tile: every neighbour row is read from HBM once.  `xa_dev` = a(x_p), (n_parents, 32) fp32, computed by the caller with
  * gsage_linear.  bf16 table and W1 (32 x d), W2 (32 x 32) fp32, 2 <= S <= 128; dummy rows are not masked (their score is
  * a(0)-dependent, exactly like the reference).  GSAGE_ERR_INVALID when the operands do not qualify. */
-int gsage_attention_aggregate(const void* table_dev, int dtype, int64_t ld, int d, const int64_t* ids_dev, int64_t n_parents, int S,
+int gsage_attention_aggregate(const void* table_dev, int dtype, int64_t ld, int64_t n_table_rows, int d, const int64_t* ids_dev,
+                              int64_t n_parents, int S,
                               const void* w1_dev, int w1_dtype, int64_t ldw, int H, const float* b1_dev, const float* w2_dev,
                               const float* xa_dev, void* out_dev, int out_dtype, int64_t ld_out, void* stream);
 /* F.normalize(dim=1, eps=1e-12) (models.py:90), fp32 out */
@@ -165,6 +166,8 @@ typedef struct gsage_linear_seg {
     int reduce_S;   /* <= 1: A row r = A[ids[r]].  S > 1: A row r = mean_j A[ids[r*S + j]] -- the neighbour gather+mean
                        (nn_modules.py:197-198) fused into the projection's operand load; the mean never touches HBM */
     int w_transposed; /* != 0: W is stored (d x O) row-major, i.e. out = A . W (the data-gradient form of a Linear) */
+    int64_t a_rows;   /* rows of the table behind a_dev when ids_dev is given (0 = unknown): ids outside [0, a_rows) then read
+                         as ZERO rows, like gsage_gather_reduce; with 0 every id must be a valid row */
 } gsage_linear_seg;
 
 /* up to two segments writing disjoint column ranges of one output: the "concat-with-self" of
@@ -292,7 +295,7 @@ int gsage_engine_backward_layer1(gsage_engine* e, const gsage_grads* grads, void
 /* The weight gradient of one projection on its own: dW (O x d, fp32, overwritten) = G^T . A[ids] (ids NULL: A in place),
  * G = the (n, O) output gradient.  exact != 0: fp32 FFMA kernel, fp32 G.  exact == 0: split-K tcgen05 kernel reading both
  * row-major operands as MN-major tiles (bf16 G and A, O == 128, 16-byte aligned rows; GSAGE_ERR_INVALID otherwise). */
-int gsage_wgrad(const void* g_dev, int g_dtype, int64_t ldg, int O, const void* a_dev, int a_dtype, int64_t lda,
+int gsage_wgrad(const void* g_dev, int g_dtype, int64_t ldg, int O, const void* a_dev, int a_dtype, int64_t lda, int64_t n_table_rows,
                 const int64_t* ids_dev, int d, int64_t n, float* dw_dev, int64_t lddw, int exact, void* stream);
 
 /* Layer-1 gradients of the Pokec recipe (utils/pokec.sh: mean aggregator + NodeEmbeddingPrep without features, fp32).

@@ -24,7 +24,7 @@ c_p = C.c_void_p
 class LinearSeg(C.Structure):
     _fields_ = [('a_dev', c_p), ('a_dtype', C.c_int), ('lda', c_i64), ('ids_dev', c_p),
                 ('w_dev', c_p), ('w_dtype', C.c_int), ('ldw', c_i64), ('d', C.c_int), ('O', C.c_int),
-                ('bias_dev', c_p), ('col0', c_i64), ('reduce_S', C.c_int), ('w_transposed', C.c_int)]
+                ('bias_dev', c_p), ('col0', c_i64), ('reduce_S', C.c_int), ('w_transposed', C.c_int), ('a_rows', c_i64)]
 
 
 class EngineConfig(C.Structure):
@@ -86,7 +86,7 @@ _SIGNATURES = {
     'gsage_gather_rows': (C.c_int, [c_p, C.c_int, c_i64, c_i64, C.c_int, c_p, c_i64, c_p, C.c_int, c_i64, c_p]),
     'gsage_gather_reduce': (C.c_int, [c_p, C.c_int, c_i64, c_i64, C.c_int, c_p, c_i64, C.c_int, C.c_int, c_p, c_p, C.c_int, c_i64, c_p]),
     'gsage_attention_weights': (C.c_int, [c_p, c_p, C.c_int, c_i64, C.c_int, c_i64, C.c_int, c_p, c_p]),
-    'gsage_attention_aggregate': (C.c_int, [c_p, C.c_int, c_i64, C.c_int, c_p, c_i64, C.c_int, c_p, C.c_int, c_i64, C.c_int, c_p, c_p, c_p, c_p,
+    'gsage_attention_aggregate': (C.c_int, [c_p, C.c_int, c_i64, c_i64, C.c_int, c_p, c_i64, C.c_int, c_p, C.c_int, c_i64, C.c_int, c_p, c_p, c_p, c_p,
                                             C.c_int, c_i64, c_p]),
     'gsage_l2_normalize': (C.c_int, [c_p, C.c_int, c_i64, c_i64, C.c_int, c_p, c_i64, c_p]),
     'gsage_linear': (C.c_int, [C.POINTER(LinearSeg), C.c_int, c_i64, C.c_int, c_p, C.c_int, c_i64, C.c_int, c_p]),
@@ -108,7 +108,7 @@ _SIGNATURES = {
     'gsage_engine_backward_layer1': (C.c_int, [c_p, C.POINTER(Grads), c_p]),
     'gsage_engine_backward_pool': (C.c_int, [c_p, c_p, C.POINTER(Grads), C.POINTER(PoolGrads), c_p]),
     'gsage_engine_backward_layer1_embedding': (C.c_int, [c_p, C.POINTER(EmbeddingGrads), c_p]),
-    'gsage_wgrad': (C.c_int, [c_p, C.c_int, c_i64, C.c_int, c_p, C.c_int, c_i64, c_p, C.c_int, c_i64, c_p, c_i64, C.c_int, c_p]),
+    'gsage_wgrad': (C.c_int, [c_p, C.c_int, c_i64, C.c_int, c_p, C.c_int, c_i64, c_i64, c_p, C.c_int, c_i64, c_p, c_i64, C.c_int, c_p]),
     'gsage_engine_keep_activations': (C.c_int, [c_p, C.c_int]),
     'gsage_engine_profile': (C.c_int, [c_p, C.c_int]),
     'gsage_engine_profile_read': (C.c_int, [c_p, C.POINTER(C.c_double), C.POINTER(c_i64), C.POINTER(C.c_double), c_p]),

@@ -275,7 +275,7 @@ static int* g_att_err = nullptr;
 
 int attention_fused_launch(const void* a, int64_t lda, const int64_t* ids, int d, const void* w1, int64_t ldw, const float* b1,
                            const float* w2, const float* xa, int64_t n_parents, int S, void* out, int out_dtype, int64_t ld_out,
-                           cudaStream_t s) {
+                           cudaStream_t s, int64_t table_rows) {
     AttParams U;
     memset(&U, 0, sizeof(U));
     U.a = a; U.lda = lda; U.ids = ids; U.b1 = b1; U.w2 = w2; U.xa = xa;
@@ -295,7 +295,7 @@ int attention_fused_launch(const void* a, int64_t lda, const int64_t* ids, int d
     AttMaps maps;
     memset(&maps, 0, sizeof(maps));
     GS_TRY(make_map(&maps.w1, w1, AH, d, ldw, AH, 2));
-    if (ids) GS_TRY(make_map(&maps.a, a, 0x7FFFFFFF, d, lda, 1, 2));
+    if (ids) GS_TRY(make_map(&maps.a, a, table_rows > 0 ? table_rows : 0x7FFFFFFF, d, lda, 1, 2));
     else GS_TRY(make_map(&maps.a, a, U.n_rows, d, lda, 128, 2));
     const size_t smem = (size_t)U.nbuf * U.buf_bytes + fixed;
     static bool attr_set = false;
@@ -316,8 +316,8 @@ using namespace gsage;
 // m[p, :d] = sum_j softmax_j(<a(n_pj), xa[p]>) n_pj  with a(v) = W2 tanh(W1 v + b1): the attention aggregator's reduction
 // (nn_modules.py:307-315) in one launch.  n_pj = table[ids[p*S + j]] (ids NULL: row p*S + j of `table` itself).
 // bf16 table and W1, attention width 32; GSAGE_ERR_INVALID for anything else (no silent fallback).
-extern "C" int gsage_attention_aggregate(const void* table_dev, int dtype, int64_t ld, int d, const int64_t* ids_dev, int64_t n_parents,
-                                         int S, const void* w1_dev, int w1_dtype, int64_t ldw, int H, const float* b1_dev,
+extern "C" int gsage_attention_aggregate(const void* table_dev, int dtype, int64_t ld, int64_t n_table_rows, int d,
+                                         const int64_t* ids_dev, int64_t n_parents, int S, const void* w1_dev, int w1_dtype, int64_t ldw, int H, const float* b1_dev,
                                          const float* w2_dev, const float* xa_dev, void* out_dev, int out_dtype, int64_t ld_out,
                                          void* stream) {
     GS_CHECK_ARG(table_dev && w1_dev && w2_dev && xa_dev && out_dev, "attention_aggregate: NULL argument");
@@ -327,5 +327,5 @@ extern "C" int gsage_attention_aggregate(const void* table_dev, int dtype, int64
                  "attention_aggregate: needs a bf16 table and W1 with 16-byte aligned rows, attention width 32, 2 <= S <= 128, "
                  "an output whose rows hold whole 16-byte chunks");
     return attention_fused_launch(table_dev, ld, ids_dev, d, w1_dev, ldw, b1_dev, w2_dev, xa_dev, n_parents, S, out_dev, out_dtype,
-                                  ld_out, as_stream(stream));
+                                  ld_out, as_stream(stream), ids_dev ? n_table_rows : 0);
 }

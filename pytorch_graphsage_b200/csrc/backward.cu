@@ -238,14 +238,15 @@ using namespace gsage;
 // whose output gradient is G.  exact != 0: fp32 FFMA kernel (G must be fp32).  exact == 0: tcgen05 kernel when the
 // operands qualify (bf16 G and A, O == 128, 16-byte aligned rows), else an error -- never a silent fallback in tests.
 extern "C" int gsage_wgrad(const void* g_dev, int g_dtype, int64_t ldg, int O, const void* a_dev, int a_dtype, int64_t lda,
-                           const int64_t* ids_dev, int d, int64_t n, float* dw_dev, int64_t lddw, int exact, void* stream) {
+                           int64_t n_table_rows, const int64_t* ids_dev, int d, int64_t n, float* dw_dev, int64_t lddw, int exact,
+                           void* stream) {
     GS_CHECK_ARG(g_dev && a_dev && dw_dev && O > 0 && d > 0 && n >= 0 && lddw >= d && ldg >= O, "wgrad: bad arguments");
     cudaStream_t s = as_stream(stream);
     if (exact) {
         GS_CHECK_ARG(g_dtype == GSAGE_F32, "wgrad: the exact (FFMA) kernel takes an fp32 output gradient");
         return wgrad_launch((const float*)g_dev, ldg, O, a_dev, a_dtype, lda, ids_dev, d, n, dw_dev, lddw, s);
     }
-    WgradJob j{g_dev, g_dtype, ldg, O, a_dev, a_dtype, lda, ids_dev, d, n, dw_dev, lddw};
+    WgradJob j{g_dev, g_dtype, ldg, O, a_dev, a_dtype, lda, ids_dev, d, n, dw_dev, lddw, ids_dev ? n_table_rows : 0};
     GS_CHECK_ARG(wgrad_umma_eligible(j), "wgrad: operands do not qualify for the tensor-core kernel (bf16 G and A, O == 128, aligned rows)");
     return wgrad_umma_launch(&j, 1, s);
 }

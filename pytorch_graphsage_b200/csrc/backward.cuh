@@ -16,6 +16,7 @@ struct WgradJob {
     const void* G; int g_dtype; int64_t ldg; int O;       // G: (n, O) slice of the output gradient
     const void* A; int a_dtype; int64_t lda; const int64_t* ids; int d;
     int64_t n; float* dW; int64_t lddw;
+    int64_t a_rows = 0;                                   // rows of the table behind A when known (ids outside it read as zero rows)
 };
 bool wgrad_umma_eligible(const WgradJob& j);
 int wgrad_umma_launch(const WgradJob* jobs, int n_jobs, cudaStream_t s);

@@ -162,6 +162,7 @@ static int linear_call(const RowSrc& a, const WRef& W, int O, const float* bias,
     LinearParams P;
     P.n_segs = 1; P.n = n; P.act = act; P.out = out; P.out_dtype = out_dtype; P.ld_out = ld_out;
     P.seg[0] = LinearSeg{a.base, a.dtype, a.ld, a.ids, W.p, W.dtype, W.ld, a.d, O, bias, col0};
+    P.seg[0].a_rows = a.ids ? a.table_rows : 0;
     if (n == 0) return GSAGE_OK;
     return linear_dispatch(P, exact, s);
 }
@@ -173,6 +174,8 @@ static int combine_call(const RowSrc& x, const WRef& Wx, const RowSrc& m, const 
     P.n_segs = 2; P.n = n; P.act = act; P.out = out; P.out_dtype = out_dtype; P.ld_out = ld_out;
     P.seg[0] = LinearSeg{x.base, x.dtype, x.ld, x.ids, Wx.p, Wx.dtype, Wx.ld, x.d, O, bx, 0};
     P.seg[1] = LinearSeg{m.base, m.dtype, m.ld, m.ids, Wn.p, Wn.dtype, Wn.ld, m.d, O, bn, (int64_t)O};
+    P.seg[0].a_rows = x.ids ? x.table_rows : 0;
+    P.seg[1].a_rows = m.ids ? m.table_rows : 0;
     if (n == 0) return GSAGE_OK;
     return linear_dispatch(P, exact, s);
 }
@@ -251,6 +254,7 @@ static int apply_aggregator(gsage_engine* e, int layer, const RowSrc& x, const R
             P.seg[0] = LinearSeg{nb.base, nb.dtype, nb.ld, nb.ids, e->w_mlp[layer].p, e->w_mlp[layer].dtype, e->w_mlp[layer].ld, d, H,
                                  e->b_mlp[layer], 0};
             P.pool_S = S; P.pool_max = e->cfg.aggregator == GSAGE_AGG_MAX_POOL ? 1 : 0;
+            P.seg[0].a_rows = nb.ids ? nb.table_rows : 0;
             if (linear_pool_umma_eligible(P)) {
                 GS_TRY(linear_dispatch(P, 0, s));
                 RowSrc p{Pb, T, H, n, nullptr, H};
@@ -275,7 +279,7 @@ static int apply_aggregator(gsage_engine* e, int layer, const RowSrc& x, const R
                                                n, Mb, ldm, T)) {
             // bf16 mode: scores (tcgen05), softmax and the weighted sum in ONE kernel -- every neighbour row is read once
             GS_TRY(attention_fused_launch(nb.base, nb.ld, nb.ids, d, e->w_att1[layer].p, e->w_att1[layer].ld, e->b_att[layer], L.att_w2,
-                                          (const float*)e->XA, n, S, Mb, T, ldm, s));
+                                          (const float*)e->XA, n, S, Mb, T, ldm, s, nb.ids ? nb.table_rows : 0));
             RowSrc mf{Mb, T, ldm, n, nullptr, d};
             return combine_call(x, e->w_x[layer], mf, e->w_n[layer], O, n, act, out, out_dtype, ld_out, exact, s, e->b_x[layer], e->b_n[layer]);
         }
@@ -844,7 +848,7 @@ int gsage_engine_backward_layer1(gsage_engine* e, const gsage_grads* g, void* st
         // the output gradient was written as bf16 by layer1_grad_kernel
         const __nv_bfloat16* dh = (const __nv_bfloat16*)e->DH;
         WgradJob jobs[2] = {
-            {dh, GSAGE_BF16, 2 * (int64_t)O1, O1, c.feats_dev, c.feats_dtype, c.feats_ld, e->ids, d, n0 + n1, g->fc_x[0], d},
+            {dh, GSAGE_BF16, 2 * (int64_t)O1, O1, c.feats_dev, c.feats_dtype, c.feats_ld, e->ids, d, n0 + n1, g->fc_x[0], d, c.feats_rows},
             {dh + O1, GSAGE_BF16, 2 * (int64_t)O1, O1, e->M, e->T, e->ld_m, nullptr, d, n0 + n1, g->fc_neib[0], d}};
         GS_TRY(wgrad_umma_launch(jobs, 2, s));
         return mark_slot_done(e, s);
@@ -921,6 +925,7 @@ int gsage_engine_backward_pool(gsage_engine* e, const float* dlogits, const gsag
         P.n_segs = 1; P.n = n_rows; P.act = GSAGE_ACT_RELU; P.out = nullptr; P.out_dtype = GSAGE_BF16; P.ld_out = H;
         P.seg[0] = LinearSeg{a, GSAGE_BF16, lda, ids, e->w_mlp[layer].p, GSAGE_BF16, e->w_mlp[layer].ld, d_in, H, e->b_mlp[layer], 0};
         P.pool_S = S; P.pool_max = pool_max;
+        P.seg[0].a_rows = ids ? c.feats_rows : 0;
         return linear_pool_ws_umma_backward_launch(P, dP, H, dhid, H, db, s);
     };
     auto mlp_wgrad = [&](const __nv_bfloat16* dhid, const void* a, int64_t lda, const int64_t* ids, int d_in, int64_t n_rows, float* dW) -> int {
@@ -929,7 +934,7 @@ int gsage_engine_backward_pool(gsage_engine* e, const float* dlogits, const gsag
             const int nj = std::min(4, H / 128 - b0);
             for (int j = 0; j < nj; ++j)
                 jobs[j] = WgradJob{dhid + (b0 + j) * 128, GSAGE_BF16, (int64_t)H, 128, a, GSAGE_BF16, lda, ids, d_in, n_rows,
-                                   dW + (int64_t)(b0 + j) * 128 * d_in, (int64_t)d_in};
+                                   dW + (int64_t)(b0 + j) * 128 * d_in, (int64_t)d_in, ids ? c.feats_rows : 0};
             GS_TRY(wgrad_umma_launch(jobs, nj, s));
         }
         return GSAGE_OK;
@@ -960,7 +965,7 @@ int gsage_engine_backward_pool(gsage_engine* e, const float* dlogits, const gsag
     // ---- layer 1 on (x0, x1) and (x1, x2), shared weights ------------------------------------------------------------------
     const __nv_bfloat16* dh = (const __nv_bfloat16*)e->DH;
     {
-        WgradJob jx{dh, GSAGE_BF16, 2 * (int64_t)O1, O1, c.feats_dev, c.feats_dtype, c.feats_ld, ids0, d, rows, g->fc_x[0], (int64_t)d};
+        WgradJob jx{dh, GSAGE_BF16, 2 * (int64_t)O1, O1, c.feats_dev, c.feats_dtype, c.feats_ld, ids0, d, rows, g->fc_x[0], (int64_t)d, c.feats_rows};
         GS_CHECK_ARG(wgrad_umma_eligible(jx), "engine_backward_pool: the feature table does not qualify for the tensor-core weight gradient");
         GS_TRY(wgrad_umma_launch(&jx, 1, s));
         WgradJob jn{dh + O1, GSAGE_BF16, 2 * (int64_t)O1, O1, Pp, GSAGE_BF16, (int64_t)H, nullptr, H, rows, g->fc_neib[0], (int64_t)H};

@@ -10,6 +10,8 @@ struct LinearSeg {
     const float* bias; int64_t col0;
     int S = 1;      // > 1: A row r = mean_j A[ids[r*S + j]] (fused gather+mean)
     int w_trans = 0;   // 1: W is stored (d x O): element (o, k) at w[k * ldw + o]  (backward: dX = dY . W; FFMA kernel only)
+    int64_t a_rows = 0;   // rows of the table behind `a` when known (> 0): ids outside it then read as ZERO rows in the TMA
+                          // gathers (like gather_reduce.cu) instead of touching memory past the table
 };
 
 struct LinearParams {
@@ -35,7 +37,7 @@ bool attention_fused_eligible(const void* a, int a_dtype, int64_t lda, int d, co
                               int64_t n_parents, const void* out, int64_t ld_out, int out_dtype);
 int attention_fused_launch(const void* a, int64_t lda, const int64_t* ids, int d, const void* w1, int64_t ldw, const float* b1,
                            const float* w2, const float* xa, int64_t n_parents, int S, void* out, int out_dtype, int64_t ld_out,
-                           cudaStream_t s);
+                           cudaStream_t s, int64_t table_rows = 0);
 // weight-stationary, double-buffered version of the pool kernel (linear_pool_ws_umma.cu): relu, S <= 64
 bool linear_pool_ws_umma_eligible(const LinearParams& P);
 int linear_pool_ws_umma_launch(const LinearParams& P, cudaStream_t s);

@@ -230,7 +230,7 @@ int linear_pool_umma_launch(const LinearParams& P, cudaStream_t s) {
     PoolMaps maps;
     memset(&maps, 0, sizeof(maps));
     GS_TRY(make_map(&maps.w, g.w, g.O, g.d, g.ldw, PM, es));
-    if (g.ids) GS_TRY(make_map(&maps.g, g.a, 0x7FFFFFFF, g.d, g.lda, 1, es));
+    if (g.ids) GS_TRY(make_map(&maps.g, g.a, g.a_rows > 0 ? g.a_rows : 0x7FFFFFFF, g.d, g.lda, 1, es));
     else GS_TRY(make_map(&maps.a, g.a, P.n, g.d, g.lda, 128, es));
     const size_t smem = (size_t)U.stages * U.stage_bytes + 1024 + 256;
     const int tiles = U.row_blocks * U.passes;

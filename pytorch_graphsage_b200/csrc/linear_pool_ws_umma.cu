@@ -354,7 +354,7 @@ static int q_launch(const LinearParams& P, const float* dP, int64_t ld_dp, void*
     QMaps maps;
     memset(&maps, 0, sizeof(maps));
     GS_TRY(make_map(&maps.w, g.w, g.O, g.d, g.ldw, QM, es));
-    if (g.ids) GS_TRY(make_map(&maps.a, g.a, 0x7FFFFFFF, g.d, g.lda, 1, es));
+    if (g.ids) GS_TRY(make_map(&maps.a, g.a, g.a_rows > 0 ? g.a_rows : 0x7FFFFFFF, g.d, g.lda, 1, es));
     else GS_TRY(make_map(&maps.a, g.a, P.n, g.d, g.lda, QN, es));
     const size_t smem = (size_t)U.bpp * U.kchunks * kQWChunk + (size_t)kQStages * kQRChunk + 1024 + 512;
     const int grid = U.n_tiles < sm_count() ? U.n_tiles : sm_count();

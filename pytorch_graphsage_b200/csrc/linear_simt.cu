@@ -132,6 +132,7 @@ extern "C" int gsage_linear(const gsage_linear_seg* segs, int n_segs, int64_t n,
         P.seg[i].a = g.a_dev; P.seg[i].a_dtype = g.a_dtype; P.seg[i].lda = g.lda; P.seg[i].ids = g.ids_dev;
         P.seg[i].w = g.w_dev; P.seg[i].w_dtype = g.w_dtype; P.seg[i].ldw = g.ldw; P.seg[i].d = g.d; P.seg[i].O = g.O;
         P.seg[i].bias = g.bias_dev; P.seg[i].col0 = g.col0; P.seg[i].S = g.reduce_S > 1 ? g.reduce_S : 1; P.seg[i].w_trans = g.w_transposed ? 1 : 0;
+        P.seg[i].a_rows = g.ids_dev ? g.a_rows : 0;
     }
     if (n == 0) return GSAGE_OK;
     return linear_dispatch(P, exact, as_stream(stream));
@@ -188,6 +189,7 @@ extern "C" int gsage_linear_pooled(const gsage_linear_seg* seg, int64_t n_parent
     P.n_segs = 1; P.n = n_parents * S; P.act = act; P.out = out_dev; P.out_dtype = out_dtype; P.ld_out = ld_out;
     P.seg[0] = LinearSeg{seg->a_dev, seg->a_dtype, seg->lda, seg->ids_dev, seg->w_dev, seg->w_dtype, seg->ldw, seg->d, seg->O,
                          seg->bias_dev, seg->col0};
+    P.seg[0].a_rows = seg->ids_dev ? seg->a_rows : 0;
     P.pool_S = S; P.pool_max = reduce == GSAGE_RED_MAX ? 1 : 0;
     if (P.n == 0) return GSAGE_OK;
     if (S == 1) { P.pool_S = 1; return linear_dispatch(P, 0, as_stream(stream)); }

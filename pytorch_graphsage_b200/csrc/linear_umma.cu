@@ -500,7 +500,7 @@ int linear_umma_launch(const LinearParams& P, cudaStream_t s) {
         const LinearSeg& g = P.seg[i];
         GS_TRY(make_map(&maps.w[i], g.w, g.O, g.d, g.ldw, g.O, es));
         if (!g.ids && U.seg[i].S == 1) GS_TRY(make_map(&maps.a[i], g.a, P.n, g.d, g.lda, UM, es));
-        if (g.ids && U.seg[i].S == 1) GS_TRY(make_map(&maps.g[i], g.a, 0x7FFFFFFF, g.d, g.lda, 1, es));   // rows by id: no row bound known here
+        if (g.ids && U.seg[i].S == 1) GS_TRY(make_map(&maps.g[i], g.a, g.a_rows > 0 ? g.a_rows : 0x7FFFFFFF, g.d, g.lda, 1, es));   // rows by id
     }
     linear_umma_kernel<<<grid, kThreads, smem, s>>>(U, maps);
     GS_LAUNCHED();

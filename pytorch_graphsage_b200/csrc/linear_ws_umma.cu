@@ -436,7 +436,7 @@ int linear_ws_umma_launch(const LinearParams& P, cudaStream_t s) {
         const LinearSeg& g = P.seg[i];
         GS_TRY(make_map(&maps.w[i], g.w, g.O, g.d, g.ldw, g.O, es));
         if (!g.ids) GS_TRY(make_map(&maps.a[i], g.a, P.n, g.d, g.lda, WM, es));
-        else GS_TRY(make_map(&maps.g[i], g.a, 0x7FFFFFFF, g.d, g.lda, 1, es));       // rows by id: no row bound known here
+        else GS_TRY(make_map(&maps.g[i], g.a, g.a_rows > 0 ? g.a_rows : 0x7FFFFFFF, g.d, g.lda, 1, es));       // rows by id
     }
     linear_ws_umma_kernel<<<grid, kWsThreads, smem, s>>>(U, maps);
     GS_LAUNCHED();

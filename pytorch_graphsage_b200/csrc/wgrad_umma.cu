@@ -263,7 +263,7 @@ int wgrad_umma_launch(const WgradJob* jobs, int n_jobs, cudaStream_t s) {
     for (int i = 0; i < n_jobs; ++i) {
         U.gemm[i].ids = jobs[i].ids; U.gemm[i].dW = jobs[i].dW; U.gemm[i].lddw = jobs[i].lddw; U.gemm[i].d = d;
         GS_TRY(make_map(&maps.g[i], jobs[i].G, U.n, 128, jobs[i].ldg, GK, 2));
-        if (jobs[i].ids) GS_TRY(make_map(&maps.a[i], jobs[i].A, 0x7FFFFFFF, d, jobs[i].lda, 1, 2));       // rows by id (tile::gather4)
+        if (jobs[i].ids) GS_TRY(make_map(&maps.a[i], jobs[i].A, jobs[i].a_rows > 0 ? jobs[i].a_rows : 0x7FFFFFFF, d, jobs[i].lda, 1, 2));       // rows by id (tile::gather4)
         else GS_TRY(make_map(&maps.a[i], jobs[i].A, U.n, d, jobs[i].lda, GK, 2));
     }
     const size_t smem = (size_t)U.stages * U.stage_bytes + 1024 + 256 + kScratch;

@@ -112,7 +112,7 @@ def linear(segments, n, act=None, out=None, out_dtype=torch.float32, exact=True)
         assert w.is_cuda and w.dim() == 2 and w.stride(1) == 1
         bias = sgm.get('bias')
         segs[i] = _lib.LinearSeg(ptr(a), dt(a), _rows2d(a), _ids_arg(sgm.get('ids')), ptr(w), dt(w), _rows2d(w), d,
-                                 w.shape[0], ptr(bias), sgm.get('col0', 0), int(sgm.get('S', 1)), 0)
+                                 w.shape[0], ptr(bias), sgm.get('col0', 0), int(sgm.get('S', 1)), 0, a.shape[0])
         width = max(width, sgm.get('col0', 0) + w.shape[0])
     if out is None:
         out = torch.empty((n, width), dtype=out_dtype, device=segments[0]['a'].device)
@@ -123,7 +123,8 @@ def linear(segments, n, act=None, out=None, out_dtype=torch.float32, exact=True)
 def linear_pooled(a, w, n_parents, S, reduce='max', ids=None, bias=None, act='relu', out_dtype=torch.float32):
     """reduce_j act(a[ids[p*S+j]] . w^T + bias): the pool aggregators' per-neighbour MLP with the pool fused in the epilogue."""
     _bind_device(a)
-    seg = _lib.LinearSeg(ptr(a), dt(a), _rows2d(a), _ids_arg(ids), ptr(w), dt(w), _rows2d(w), w.shape[1], w.shape[0], ptr(bias), 0, 1, 0)
+    seg = _lib.LinearSeg(ptr(a), dt(a), _rows2d(a), _ids_arg(ids), ptr(w), dt(w), _rows2d(w), w.shape[1], w.shape[0], ptr(bias), 0, 1, 0,
+                         a.shape[0])
     out = torch.empty((n_parents, w.shape[0]), dtype=out_dtype, device=a.device)
     check(lib().gsage_linear_pooled(C.byref(seg), n_parents, S, _lib.REDUCE[reduce], _lib.ACT[act], ptr(out), dt(out), _rows2d(out), stream()))
     return out
@@ -135,7 +136,8 @@ def wgrad(g, a, ids=None, n=None, exact=True):
     n = g.shape[0] if n is None else n
     O, d = g.shape[1], a.shape[1]
     dw = torch.empty((O, d), dtype=torch.float32, device=a.device)
-    check(lib().gsage_wgrad(ptr(g), dt(g), _rows2d(g), O, ptr(a), dt(a), _rows2d(a), _ids_arg(ids), d, n, ptr(dw), d, 1 if exact else 0, stream()))
+    check(lib().gsage_wgrad(ptr(g), dt(g), _rows2d(g), O, ptr(a), dt(a), _rows2d(a), a.shape[0], _ids_arg(ids), d, n, ptr(dw), d,
+                            1 if exact else 0, stream()))
     return dw
 
 
@@ -153,7 +155,7 @@ def attention_aggregate(table, ids, n_parents, S, w1, w2, xa, b1=None, out_dtype
     out_dtype = out_dtype or table.dtype
     store, _ = pad_table(torch.zeros((n_parents, d), dtype=torch.float32), out_dtype)
     out = store[:, :d]
-    check(lib().gsage_attention_aggregate(ptr(table), dt(table), _rows2d(table), d, _ids_arg(ids), n_parents, S, ptr(w1), dt(w1), _rows2d(w1),
+    check(lib().gsage_attention_aggregate(ptr(table), dt(table), _rows2d(table), table.shape[0], d, _ids_arg(ids), n_parents, S, ptr(w1), dt(w1), _rows2d(w1),
                                           w1.shape[0], ptr(b1), ptr(w2), ptr(xa), ptr(out), dt(out), _rows2d(out), stream()))
     return out
 

@@ -329,3 +329,22 @@ def test_fused_attention_rejects_fp32_tables(g):
     with pytest.raises(ValueError):
         g.ops.attention_aggregate(torch.randn(100, 64).cuda(), None, 10, 10, torch.randn(32, 64).cuda(), torch.randn(32, 32).cuda(),
                                   torch.randn(10, 32).cuda())
+
+
+def test_tensor_core_gathers_read_out_of_range_ids_as_zero_rows(g):
+    """ids outside the table are zero rows in the TMA gathers too (the tensor maps are bounded by the table's rows):
+    same behaviour as gather_reduce.cu, and no access past the table's last row."""
+    gen = torch.Generator().manual_seed(1)
+    rows, d, O, n = 37, 64, 128, 300
+    table = _bf16(torch.randn((rows, d), generator=gen))
+    w = _bf16(torch.randn((O, d), generator=gen) / 8)
+    b = torch.randn((O,), generator=gen)
+    ids = torch.randint(0, rows, (n,), generator=gen)
+    ids[::5] = rows + 1000                                    # far past the table
+    ids[3] = -7                                               # negative: also outside
+    pad = lambda t: g.ops.pad_table(t.float(), torch.bfloat16)[0][:, :t.shape[1]]
+    src = table.double()[ids.clamp(0, rows - 1)]
+    src[(ids < 0) | (ids >= rows)] = 0
+    want = src @ w.double().t() + b.double()
+    got = g.ops.linear([dict(a=pad(table), ids=ids.cuda(), w=pad(w), bias=b.cuda())], n, exact=False)
+    np.testing.assert_allclose(got.cpu().numpy(), want.numpy(), rtol=2e-4, atol=2e-4)
