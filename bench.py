@@ -66,6 +66,7 @@ def parse_args():
     ap.add_argument('--cpu-seconds', type=float, default=12.0, help='budget of the cpu_baseline leg')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-train', action='store_true', help='skip the train-step leg')
+    ap.add_argument('--torch-adam', action='store_true', help='train leg: torch.optim.Adam + clip_grad_norm_ instead of the fused native step')
     ap.add_argument('--no-ahead', action='store_true', help='sample inside each forward instead of one batch ahead on the sampler stream')
     ap.add_argument('--scale', type=float, default=1.0, help='shrink the graph (debug only; reported in config)')
     return ap.parse_args()
@@ -399,7 +400,8 @@ def run_ours(args):
             tgt_all = torch.from_numpy(prob['targets'].reshape(-1)).cuda()
             loss_fn = F.cross_entropy
         tgts = [tgt_all[i] for i in dev_ids]
-        opt = torch.optim.Adam(model.parameters(), lr=0.01)
+        # clip_grad_norm 5 + Adam as one native call over flat buffers (parallel.FusedAdam); --torch-adam: the stock pair
+        opt = torch.optim.Adam(model.parameters(), lr=0.01) if args.torch_adam else g.FusedAdam(model, lr=0.01)
         side = torch.cuda.Stream()
         k_train = max(3, min(args.steps, 30))
         def train_step(i):
@@ -421,7 +423,7 @@ def run_ours(args):
                  'allreduce_bytes_per_step': int(model._bucket().flat.numel()) * 4,
                  'collective': 'one flat fp32 gradient bucket, NCCL all-reduce in two pieces (fc + layer-2 head overlapped with the '
                                'layer-1 weight-gradient kernels)' if WORLD > 1 else 'none (1 GPU)',
-                 'note': 'loss + clip + Adam are stock torch'}
+                 'note': 'loss is stock torch; clip + Adam are ' + ('stock torch' if args.torch_adam else 'one native call (gsage_adam_step)')}
 
     if RANK != 0:
         if WORLD > 1:

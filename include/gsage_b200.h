@@ -314,6 +314,12 @@ typedef struct gsage_pool_grads { float* mlp_w[2]; float* mlp_b[2]; } gsage_pool
 int gsage_engine_backward_pool(gsage_engine* e, const float* dlogits_dev, const gsage_grads* grads, const gsage_pool_grads* pool_grads,
                                void* stream);
 
+/* torch.nn.utils.clip_grad_norm(params, max_norm) + torch.optim.Adam.step() (models.py:102-103) on ONE flat fp32 parameter
+ * buffer and its flat gradient / moment buffers (two launches instead of ~25).  `step` is the 1-based step count of the bias
+ * corrections; max_norm <= 0 skips the clip; `scratch_dev` is one float of device memory. */
+int gsage_adam_step(float* param_dev, float* grad_dev, float* m_dev, float* v_dev, int64_t n, float lr, float beta1, float beta2,
+                    float eps, float weight_decay, int64_t step, float max_norm, float* scratch_dev, void* stream);
+
 /* keep != 0: the next forwards keep every activation the backward pass needs (training).  0 (default): forward-only
  * streaming -- intermediates may be processed in L2-sized chunks that reuse their buffers. */
 int gsage_engine_keep_activations(gsage_engine* e, int keep);

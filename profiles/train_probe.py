@@ -27,7 +27,7 @@ model = model.cuda()
 g.set_seeds(123 ** 2)
 ids = [torch.from_numpy(synth.seed_batch(prob, B, seed=i)).cuda() for i in range(4)]
 tgt = torch.from_numpy(prob['targets'].reshape(-1)).cuda()
-opt = torch.optim.Adam(model.parameters(), lr=0.01)
+opt = g.FusedAdam(model, lr=0.01)
 side = torch.cuda.Stream()
 ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 for i in range(steps + 2):

@@ -15,7 +15,9 @@ from .operators import (sampler_lookup, prep_lookup, aggregator_lookup, UniformN
                         SparseUniformNeighborSampler, IdentityPrep, NodeEmbeddingPrep, LinearPrep, MeanAggregator,
                         PoolAggregator, MaxPoolAggregator, MeanPoolAggregator, AttentionAggregator)
 from .model import GSSupervised, FeatureTable             # noqa: F401
+from .parallel import FusedAdam, FlatGradBucket            # noqa: F401
 from . import ops, synth, problem                          # noqa: F401
 
 __all__ = ['sampler_lookup', 'prep_lookup', 'aggregator_lookup', 'GSSupervised', 'FeatureTable', 'GraphCSR',
-           'DeviceMT19937', 'default_rng', 'set_seeds', 'ops', 'synth', 'lib', 'launch_count', 'GsageError']
+           'DeviceMT19937', 'default_rng', 'set_seeds', 'ops', 'synth', 'lib', 'launch_count', 'GsageError', 'FusedAdam',
+           'FlatGradBucket']

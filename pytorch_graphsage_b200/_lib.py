@@ -109,6 +109,7 @@ _SIGNATURES = {
     'gsage_engine_backward_pool': (C.c_int, [c_p, c_p, C.POINTER(Grads), C.POINTER(PoolGrads), c_p]),
     'gsage_engine_backward_layer1_embedding': (C.c_int, [c_p, C.POINTER(EmbeddingGrads), c_p]),
     'gsage_wgrad': (C.c_int, [c_p, C.c_int, c_i64, C.c_int, c_p, C.c_int, c_i64, c_i64, c_p, C.c_int, c_i64, c_p, c_i64, C.c_int, c_p]),
+    'gsage_adam_step': (C.c_int, [c_p, c_p, c_p, c_p, c_i64, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, c_i64, C.c_float, c_p, c_p]),
     'gsage_engine_keep_activations': (C.c_int, [c_p, C.c_int]),
     'gsage_engine_profile': (C.c_int, [c_p, C.c_int]),
     'gsage_engine_profile_read': (C.c_int, [c_p, C.POINTER(C.c_double), C.POINTER(c_i64), C.POINTER(C.c_double), c_p]),

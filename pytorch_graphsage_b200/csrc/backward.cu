@@ -77,7 +77,8 @@ __global__ void __launch_bounds__(256) wgrad_simt_kernel(const float* __restrict
 }
 
 __global__ void __launch_bounds__(256) l2_normalize_bwd_kernel(const float* __restrict__ z, const float* __restrict__ dzn,
-                                                               int64_t n, int d, int act, float* __restrict__ dz) {
+                                                               int64_t n, int d, int act, float* __restrict__ dz,
+                                                               __nv_bfloat16* __restrict__ dz_bf16) {
     const int lane = threadIdx.x & 31;
     const int64_t r = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
     if (r >= n) return;
@@ -100,6 +101,7 @@ __global__ void __launch_bounds__(256) l2_normalize_bwd_kernel(const float* __re
         if (act == GSAGE_ACT_RELU) g = v > 0.0f ? g : 0.0f;   // z is the post-activation output of layer 2
         else if (act == GSAGE_ACT_TANH) g *= (1.0f - v * v);
         dz[r * d + c] = g;
+        if (dz_bf16) dz_bf16[r * d + c] = __float2bfloat16_rn(g);     // operand copy for the tensor-core gradient kernels
     }
 }
 
@@ -206,9 +208,9 @@ int wgrad_launch(const float* G, int64_t ldg, int O, const void* A, int a_dtype,
     return GSAGE_OK;
 }
 
-int l2_normalize_bwd_launch(const float* z, const float* dzn, int64_t n, int d, int act, float* dz, cudaStream_t s) {
+int l2_normalize_bwd_launch(const float* z, const float* dzn, int64_t n, int d, int act, float* dz, cudaStream_t s, void* dz_bf16) {
     if (n == 0) return GSAGE_OK;
-    l2_normalize_bwd_kernel<<<(unsigned)ceil_div(n, 8), 256, 0, s>>>(z, dzn, n, d, act, dz);
+    l2_normalize_bwd_kernel<<<(unsigned)ceil_div(n, 8), 256, 0, s>>>(z, dzn, n, d, act, dz, (__nv_bfloat16*)dz_bf16);
     GS_LAUNCHED();
     return GSAGE_OK;
 }

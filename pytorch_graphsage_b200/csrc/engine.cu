@@ -130,6 +130,8 @@ struct gsage_engine {
     char* wb = nullptr; int64_t wb_bytes = 0;
     WRef w_x[2], w_n[2], w_mlp[2], w_att1[2];
     WRef w_nT[2], w_mlpT[2];            // pool backward (bf16): fc_neib^T (H x O) and mlp.0.weight^T (d_in x H), K-major
+    WRef w_x2T, w_n2T;                  // mean backward (bf16): layer-2 fc_x^T / fc_neib^T (2*O1 x O2), K-major, for the head's data gradients
+    void* DZB = nullptr;                // bf16 copy of d loss / d z (operand of the tensor-core head gradients)
     float* DP = nullptr;                // pool backward: d loss / d pooled rows, (n0 + n1) x H fp32
     void* DHID = nullptr;               // pool backward: d loss / d hidden rows, (n1 + n2) x H bf16
     float* DN2 = nullptr;               // pool backward: d loss / d (layer-2 neighbour rows), n1 x 2*O1 fp32
@@ -365,6 +367,7 @@ int gsage_engine_create(const gsage_engine_config* cfg, gsage_engine** out) {
     const int64_t o_LG = carve(4 * (int64_t)cfg->n_classes * e->n0);
     const int64_t o_DZN = carve(4 * 2 * O2 * e->n0), o_DZ = carve(4 * 2 * O2 * e->n0);
     const int64_t o_DH0 = carve(4 * 2 * O1 * e->n0), o_DM2 = carve(4 * 2 * O1 * e->n0);
+    const int64_t o_DZB = carve(2 * 2 * O2 * e->n0);
     const int64_t o_DH = carve(4 * 2 * O1 * (e->n0 + e->n1));
     const int64_t o_DXE = e->fold_prep ? carve(4 * (int64_t)cfg->emb_dim * (e->n0 + e->n1)) : -1;
     const bool pool_cfg = cfg->aggregator == GSAGE_AGG_MAX_POOL || cfg->aggregator == GSAGE_AGG_MEAN_POOL;
@@ -402,7 +405,7 @@ int gsage_engine_create(const gsage_engine_config* cfg, gsage_engine** out) {
     e->X = at(o_X); e->M = at(o_M); e->HN = at(o_HN); e->Pp = at(o_P);
     e->T1 = at(o_T1); e->NA = at(o_NA); e->T1x = at(o_T1x); e->XA = at(o_XA); e->AW = (float*)at(o_AW);
     e->H1 = at(o_H1); e->Z = (float*)at(o_Z); e->ZN = (float*)at(o_ZN); e->LG = (float*)at(o_LG);
-    e->DXE = (float*)at(o_DXE);
+    e->DXE = (float*)at(o_DXE); e->DZB = at(o_DZB);
     e->DP = (float*)at(o_DP); e->DHID = at(o_DHID); e->DN2 = (float*)at(o_DN2);
     e->DZN = (float*)at(o_DZN); e->DZ = (float*)at(o_DZ); e->DH0 = (float*)at(o_DH0); e->DM2 = (float*)at(o_DM2); e->DH = (float*)at(o_DH);
     *out = e;
@@ -522,6 +525,22 @@ int gsage_engine_set_weights(gsage_engine* e, const gsage_weights* w, void* stre
             GS_LAUNCHED();
             *it.dst = WRef{dst, GSAGE_BF16, ld};
             off += bytes;
+        }
+        if (l == 1 && e->cfg.aggregator == GSAGE_AGG_MEAN && e->T == GSAGE_BF16) {
+            // K-major transposed copies of the layer-2 weights: the head's data gradients d h0 = dz_x . Wx2, d m2 = dz_n . Wn2
+            // run on the projection kernel as out = A . W'^T with W' = W^T
+            struct TItem { const float* src; int rows, cols; WRef* dst; } titems[2] = {
+                {w->layer[1].fc_x, O, d_in, &e->w_x2T}, {w->layer[1].fc_neib, O, d_in, &e->w_n2T}};
+            for (const TItem& it : titems) {
+                const int64_t ld = pad_to(it.rows, 8);
+                const int64_t bytes = pad_to(2 * ld * it.cols, 256);
+                GS_CHECK_ARG(off + bytes <= e->wb_bytes, "engine_set_weights: bf16 weight arena too small (transposed copies)");
+                __nv_bfloat16* dst = (__nv_bfloat16*)(e->wb + off);
+                transpose_to_bf16_kernel<<<(unsigned)ceil_div((int64_t)it.cols * ld, 256), 256, 0, s>>>(it.src, it.rows, it.cols, dst, ld);
+                GS_LAUNCHED();
+                *it.dst = WRef{dst, GSAGE_BF16, ld};
+                off += bytes;
+            }
         }
         if (pool && e->T == GSAGE_BF16 && e->DP) {
             // K-major transposed copies for the pool backward's data-gradient projections
@@ -821,13 +840,33 @@ int gsage_engine_backward_head(gsage_engine* e, const float* dlogits, const gsag
     GS_TRY(colsum_launch(dlogits, n0, C, g->fc_b, s));
     GS_TRY(linear_trans_call(dlogits, C, C, e->w.fc_w, 2 * O2, 2 * O2, n0, e->DZN, 2 * O2, s));
     // F.normalize + layer-2 activation
-    GS_TRY(l2_normalize_bwd_launch(e->Z, e->DZN, n0, 2 * O2, c.act[1], e->DZ, s));
-    // layer 2: z = [h0 Wx2^T | m2 Wn2^T]
     const void* m2 = (const char*)e->M + (n0 + n1) * e->ld_m * es;
-    GS_TRY(wgrad_launch(e->DZ, 2 * O2, O2, e->H1, e->T, e->ld_h1, nullptr, 2 * O1, n0, g->fc_x[1], 2 * O1, s));
-    GS_TRY(wgrad_launch(e->DZ + O2, 2 * O2, O2, m2, e->T, e->ld_m, nullptr, 2 * O1, n0, g->fc_neib[1], 2 * O1, s));
-    GS_TRY(linear_trans_call(e->DZ, 2 * O2, O2, e->w.layer[1].fc_x, 2 * O1, 2 * O1, n0, e->DH0, 2 * O1, s));
-    GS_TRY(linear_trans_call(e->DZ + O2, 2 * O2, O2, e->w.layer[1].fc_neib, 2 * O1, 2 * O1, n0, e->DM2, 2 * O1, s));
+    WgradJob head_jobs[2] = {
+        {e->DZB, GSAGE_BF16, 2 * (int64_t)O2, O2, e->H1, e->T, e->ld_h1, nullptr, 2 * O1, n0, g->fc_x[1], 2 * (int64_t)O1},
+        {(const __nv_bfloat16*)e->DZB + O2, GSAGE_BF16, 2 * (int64_t)O2, O2, m2, e->T, e->ld_m, nullptr, 2 * O1, n0, g->fc_neib[1], 2 * (int64_t)O1}};
+    const bool head_tc = e->T == GSAGE_BF16 && e->cfg.aggregator == GSAGE_AGG_MEAN && e->w_x2T.p && O2 % 16 == 0 &&
+                         wgrad_umma_eligible(head_jobs[0]) && wgrad_umma_eligible(head_jobs[1]);
+    GS_TRY(l2_normalize_bwd_launch(e->Z, e->DZN, n0, 2 * O2, c.act[1], e->DZ, s, head_tc ? e->DZB : nullptr));
+    // layer 2: z = [h0 Wx2^T | m2 Wn2^T]
+    if (head_tc) {
+        // bf16 mode: both weight gradients as two jobs of one split-K tcgen05 launch, both data gradients on the projection
+        // kernel with the transposed weights (the FFMA generation of these four took 0.26 ms of a 2.4 ms train step)
+        GS_TRY(wgrad_umma_launch(head_jobs, 2, s));
+        const WRef* wt[2] = {&e->w_x2T, &e->w_n2T};
+        float* outs[2] = {e->DH0, e->DM2};
+        for (int k = 0; k < 2; ++k) {
+            LinearParams P;
+            P.n_segs = 1; P.n = n0; P.act = GSAGE_ACT_NONE; P.out = outs[k]; P.out_dtype = GSAGE_F32; P.ld_out = 2 * O1;
+            P.seg[0] = LinearSeg{(const __nv_bfloat16*)e->DZB + k * O2, GSAGE_BF16, 2 * (int64_t)O2, nullptr, wt[k]->p, GSAGE_BF16, wt[k]->ld,
+                                 O2, 2 * O1, nullptr, 0};
+            GS_TRY(linear_dispatch(P, 0, s));
+        }
+    } else {
+        GS_TRY(wgrad_launch(e->DZ, 2 * O2, O2, e->H1, e->T, e->ld_h1, nullptr, 2 * O1, n0, g->fc_x[1], 2 * O1, s));
+        GS_TRY(wgrad_launch(e->DZ + O2, 2 * O2, O2, m2, e->T, e->ld_m, nullptr, 2 * O1, n0, g->fc_neib[1], 2 * O1, s));
+        GS_TRY(linear_trans_call(e->DZ, 2 * O2, O2, e->w.layer[1].fc_x, 2 * O1, 2 * O1, n0, e->DH0, 2 * O1, s));
+        GS_TRY(linear_trans_call(e->DZ + O2, 2 * O2, O2, e->w.layer[1].fc_neib, 2 * O1, 2 * O1, n0, e->DM2, 2 * O1, s));
+    }
     // mean over S1 children + concat + layer-1 activation, backwards
     GS_TRY(layer1_grad_launch(e->DH0, e->DM2, e->H1, e->T, e->ld_h1, n0, n1, S1, 2 * O1, c.act[0], e->DH,
                               layer1_wgrad_on_tensor_cores(e) ? GSAGE_BF16 : GSAGE_F32, s));

@@ -137,6 +137,13 @@ class GSSupervised(nn.Module):
         self._engines[key] = eng
         return eng
 
+    def _reset_engines(self):
+        """Drop every engine (they hold raw pointers into parameter / table storage that is about to move)."""
+        for eng in self._engines.values():
+            lib().gsage_engine_destroy(eng['h'])
+        self._engines = {}
+        self._last = None
+
     def _weights(self):
         w = _lib.Weights()
         p = lambda t: t.data.data_ptr()
@@ -158,7 +165,7 @@ class GSSupervised(nn.Module):
     def _push_weights(self, eng):
         """Hand the current parameters to the engine -- only when a parameter moved or was updated in place
         (torch bumps `_version` on every in-place write, e.g. an optimiser step)."""
-        stamp = tuple((p.data_ptr(), p._version) for p in self.parameters())
+        stamp = tuple((p.data_ptr(), p._version) for p in self.parameters()) + (getattr(self, '_weights_epoch', 0),)
         if eng.get('stamp') != stamp:
             w = self._weights()
             check(lib().gsage_engine_set_weights(eng['h'], C.byref(w), ops.stream()))
@@ -320,10 +327,13 @@ class GSSupervised(nn.Module):
         loss = loss_fn(leaf, targets.squeeze())
         dlogits, = torch.autograd.grad(loss, leaf)
         self.backward(dlogits, grad_scale=grad_scale, overlap_stream=overlap_stream)
-        if clip:
-            torch.nn.utils.clip_grad_norm_(self.parameters(), clip)
-        if optimizer is not None:
-            optimizer.step()
+        if getattr(optimizer, 'fused_clip', False):
+            optimizer.step(clip=clip)                              # clip + Adam in one native call (parallel.FusedAdam)
+        else:
+            if clip:
+                torch.nn.utils.clip_grad_norm_(self.parameters(), clip)
+            if optimizer is not None:
+                optimizer.step()
         return preds, loss.detach()
 
     def profile(self, enable=True):

@@ -8,6 +8,9 @@ the layer-1 weight gradients).  Works on any torch.distributed backend (NCCL on 
 import torch
 import torch.distributed as dist
 
+from . import ops
+from ._lib import check, lib
+
 
 def shard_seeds(ids, rank, world):
     """This rank's contiguous slice of the (already shuffled) global seed batch; slices partition the batch and
@@ -68,3 +71,42 @@ class FlatGradBucket(object):
 
     def all_reduce_tail(self, scale=1.0):
         self._reduce(self.flat[self.head_numel:], scale)
+
+
+class FusedAdam(object):
+    """`clip_grad_norm(params, 5)` + `torch.optim.Adam.step()` (models.py:102-103) as ONE native call (gsage_adam_step: two
+    launches) over flat buffers: the model's parameters are re-pointed at slices of one contiguous fp32 buffer, laid out
+    like its FlatGradBucket, with flat first / second moment buffers beside it.  Same update as
+    torch.optim.Adam(lr, betas, eps, weight_decay) after clip_grad_norm_(max_norm=clip)."""
+
+    fused_clip = True
+
+    def __init__(self, model, lr=0.01, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0):
+        self.model = model
+        self.bucket = model._bucket()
+        order = self.bucket.params
+        dev = self.bucket.flat.device
+        self.flat = torch.empty(self.bucket.flat.numel(), dtype=torch.float32, device=dev)
+        off = 0
+        for p in order:
+            assert p.dtype == torch.float32 and p.is_cuda, 'FusedAdam: fp32 CUDA parameters'
+            n = p.numel()
+            self.flat[off:off + n].copy_(p.data.reshape(-1))
+            p.data = self.flat[off:off + n].view_as(p)            # the parameter now lives inside the flat buffer
+            off += n
+        self.m = torch.zeros_like(self.flat)
+        self.v = torch.zeros_like(self.flat)
+        self.scratch = torch.zeros(1, dtype=torch.float32, device=dev)
+        self.lr, self.betas, self.eps, self.weight_decay = lr, betas, eps, weight_decay
+        self.steps = 0
+        model._reset_engines()                                    # engines hold raw pointers of the old parameter storage
+
+    def step(self, clip=5.0):
+        self.steps += 1
+        check(lib().gsage_adam_step(ops.ptr(self.flat), ops.ptr(self.bucket.flat), ops.ptr(self.m), ops.ptr(self.v), self.flat.numel(),
+                                    float(self.lr), float(self.betas[0]), float(self.betas[1]), float(self.eps), float(self.weight_decay),
+                                    self.steps, float(clip or 0.0), ops.ptr(self.scratch), ops.stream()))
+        self.model._weights_epoch = getattr(self.model, '_weights_epoch', 0) + 1     # in-place update torch did not see
+
+    def zero_grad(self):
+        pass                                                      # every backward overwrites the whole bucket

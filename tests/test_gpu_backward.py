@@ -138,6 +138,57 @@ def test_pool_aggregator_gradients_match_autograd(g, agg):
         assert cos >= 0.995 and abs(ratio - 1.0) <= 2e-2, '%s: cosine %.5f, norm ratio %.4f' % (name, cos, ratio)
 
 
+def test_fused_clip_adam_equals_torch(g):
+    """parallel.FusedAdam (gsage_adam_step: clip_grad_norm 5 + Adam in two launches over flat buffers) against
+    torch.nn.utils.clip_grad_norm_ + torch.optim.Adam on the same model, three steps, weight decay on."""
+    fix = util.load('model_mean_identity')
+    feats = torch.from_numpy(fix['feats'])
+    targets = torch.from_numpy(np.random.RandomState(1).randint(0, fix['logits'].shape[1], fix['ids0'].shape[0])).cuda()
+    ids = torch.from_numpy(fix['ids0'])
+    a = build_model(g, fix, 'mean', 'identity', True)
+    b = build_model(g, fix, 'mean', 'identity', True)
+    opt_a = torch.optim.Adam(a.parameters(), lr=0.01, weight_decay=1e-3)
+    opt_b = g.FusedAdam(b, lr=0.01, weight_decay=1e-3)
+    for step in range(3):
+        g.set_seeds(int(fix['seed']) + step)
+        a.train_step(ids, feats, targets, F.cross_entropy, optimizer=opt_a, clip=0.05)      # small max_norm: the clip is active
+        g.set_seeds(int(fix['seed']) + step)
+        b.train_step(ids, feats, targets, F.cross_entropy, optimizer=opt_b, clip=0.05)
+        for (name, pa), (_, pb) in zip(a.named_parameters(), b.named_parameters()):
+            np.testing.assert_allclose(pb.detach().cpu().numpy(), pa.detach().cpu().numpy(), rtol=1e-4, atol=2e-6, err_msg='%s step %d' % (name, step))
+    # the engine sees the natively updated weights (no torch _version bump to rely on)
+    g.set_seeds(5)
+    la = a(ids, feats)
+    g.set_seeds(5)
+    lb = b(ids, feats)
+    np.testing.assert_allclose(lb.cpu().numpy(), la.cpu().numpy(), rtol=1e-4, atol=1e-5)
+
+
+def test_train_step_with_the_dense_sampler(g):
+    """train.py's default configuration (dense sampler, mean, identity): gradients against autograd through the oracle."""
+    fix = util.load('model_dense_mean_identity')
+    S1, S2 = [int(s) for s in fix['fanout']]
+    O1, O2 = [int(s) for s in fix['out_dims']]
+    adj = torch.from_numpy(fix['adj'])
+    model = g.GSSupervised(
+        input_dim=fix['feats'].shape[1], n_nodes=int(fix['n_nodes']), n_classes=fix['logits'].shape[1],
+        layer_specs=[dict(n_train_samples=S1, n_val_samples=S1, output_dim=O1, activation=F.relu),
+                     dict(n_train_samples=S2, n_val_samples=S2, output_dim=O2, activation=lambda x: x)],
+        aggregator_class=g.aggregator_lookup['mean'], prep_class=g.prep_lookup['identity'],
+        sampler_class=g.sampler_lookup['uniform_neighbor_sampler'], adj=adj, train_adj=adj)
+    model.load_state_dict(util.params_of(fix), strict=True)
+    model = model.cuda()
+    targets = torch.from_numpy(np.random.RandomState(0).randint(0, fix['logits'].shape[1], fix['ids0'].shape[0]))
+    g.set_seeds(int(fix['seed']))
+    feats = torch.from_numpy(fix['feats'])
+    model.train_step(torch.from_numpy(fix['ids0']), feats, targets.cuda(), F.cross_entropy, optimizer=None, clip=None)
+    hop_ids = [torch.from_numpy(np.ascontiguousarray(fix[k]).reshape(-1)) for k in ('ids0', 'ids1', 'ids2')]
+    ps = {k: v.clone().requires_grad_(True) for k, v in util.params_of(fix).items()}
+    F.cross_entropy(layers.forward_stack(hop_ids, feats, ps), targets).backward()
+    for name, p in model.named_parameters():
+        np.testing.assert_allclose(p.grad.cpu().numpy(), ps[name].grad.numpy(), rtol=2e-3, atol=2e-5, err_msg=name)
+
+
 def test_backward_rejects_unsupported_plugins(g):
     fix = util.load('model_attention_identity')
     model = build_model(g, fix, 'attention', 'identity', True)
