@@ -254,7 +254,8 @@ def run_reference(args):
     cores = torch.get_num_threads()
     line = {'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': steps,
             'warmup': args.warmup, 'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
-            'dtype': 'f32', 'data': 'synthetic', 'config': dict(workload_config(args, prob), batch_seeds_per_step=args.cpu_batch),
+            'dtype': 'f32', 'data': 'synthetic',
+            'config': dict(workload_config(args, prob), batch_seeds_per_step=args.cpu_batch, pipeline='n/a (the reference\'s CPU path)'),
             'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': cores, 'kind': 'port',
                              'sample': '%d steps x %d seeds (oracle port of nn_modules.py/models.py CPU path, torch %d threads of %d cpus)' %
                                        (steps, args.cpu_batch, cores, os.cpu_count())},
@@ -390,7 +391,7 @@ def run_ours(args):
     # ---- one optimiser step per batch (forward + loss + backward + gradient all-reduce + clip + Adam) ---------------
     train = None
     trainable = (prob['aggregator'] == 'mean' and (prob['prep'] == 'identity' or (prob['prep'] == 'node_embedding' and dtype == torch.float32 and not tf32))) or \
-                (prob['aggregator'] in ('max_pool', 'mean_pool') and prob['prep'] == 'identity' and dtype == torch.bfloat16)
+                (prob['aggregator'] in ('max_pool', 'mean_pool') and dtype == torch.bfloat16)
     if trainable and not args.no_train:
         from torch.nn import functional as F
         if prob['task'] == 'regression_mae':                                       # problem.py:39-41: l1 loss on (B, 1) predictions

@@ -313,6 +313,13 @@ int gsage_engine_backward_layer1_embedding(gsage_engine* e, const gsage_embeddin
 typedef struct gsage_pool_grads { float* mlp_w[2]; float* mlp_b[2]; } gsage_pool_grads;
 int gsage_engine_backward_pool(gsage_engine* e, const float* dlogits_dev, const gsage_grads* grads, const gsage_pool_grads* pool_grads,
                                void* stream);
+/* The same for BASELINE config C3 (Pokec: pool aggregator + NodeEmbeddingPrep without features, bf16).  The prep's affine is
+ * folded into layer 1 (W' = W.Wp), so grads->fc_x[0] (O1, emb_dim) and pool_grads->mlp_w[0] (hidden, emb_dim) receive the RAW
+ * reductions against the embedding rows; with csum_x (O1: column sums of Gx) and mlp_b[0] the caller unfolds them
+ * (dW = raw.Wp^T + csum (x) bp, dWp = sum W^T.raw, dbp = sum W^T.csum).  d_table: dense (n_nodes + 1, emb_dim) fp32 gradient. */
+typedef struct gsage_pool_embedding_grads { float* csum_x; float* d_table; } gsage_pool_embedding_grads;
+int gsage_engine_backward_pool_embedding(gsage_engine* e, const float* dlogits_dev, const gsage_grads* grads,
+                                         const gsage_pool_grads* pool_grads, const gsage_pool_embedding_grads* emb_grads, void* stream);
 
 /* torch.nn.utils.clip_grad_norm(params, max_norm) + torch.optim.Adam.step() (models.py:102-103) on ONE flat fp32 parameter
  * buffer and its flat gradient / moment buffers (two launches instead of ~25).  `step` is the 1-based step count of the bias

@@ -49,6 +49,10 @@ class PoolGrads(C.Structure):
     _fields_ = [('mlp_w', c_p * 2), ('mlp_b', c_p * 2)]
 
 
+class PoolEmbeddingGrads(C.Structure):
+    _fields_ = [('csum_x', c_p), ('d_table', c_p)]
+
+
 class EmbeddingGrads(C.Structure):
     _fields_ = [('gx_raw', c_p), ('gn_raw', c_p), ('csum', c_p), ('d_table', c_p)]
 
@@ -107,6 +111,7 @@ _SIGNATURES = {
     'gsage_engine_backward_head': (C.c_int, [c_p, c_p, C.POINTER(Grads), c_p]),
     'gsage_engine_backward_layer1': (C.c_int, [c_p, C.POINTER(Grads), c_p]),
     'gsage_engine_backward_pool': (C.c_int, [c_p, c_p, C.POINTER(Grads), C.POINTER(PoolGrads), c_p]),
+    'gsage_engine_backward_pool_embedding': (C.c_int, [c_p, c_p, C.POINTER(Grads), C.POINTER(PoolGrads), C.POINTER(PoolEmbeddingGrads), c_p]),
     'gsage_engine_backward_layer1_embedding': (C.c_int, [c_p, C.POINTER(EmbeddingGrads), c_p]),
     'gsage_wgrad': (C.c_int, [c_p, C.c_int, c_i64, C.c_int, c_p, C.c_int, c_i64, c_i64, c_p, C.c_int, c_i64, c_p, c_i64, C.c_int, c_p]),
     'gsage_adam_step': (C.c_int, [c_p, c_p, c_p, c_p, c_i64, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, c_i64, C.c_float, c_p, c_p]),

@@ -226,6 +226,26 @@ int layer1_grad_launch(const float* dh0, const float* dm2, const void* H, int h_
     return GSAGE_OK;
 }
 
+// bf16 rows: a block takes a strip of rows, a thread one column pair; fp32 atomics combine the strips
+__global__ void __launch_bounds__(256) colsum_bf16_kernel(const __nv_bfloat16* __restrict__ x, int64_t ld, int64_t n, int d,
+                                                          int64_t rows_per_block, float* __restrict__ out) {
+    const int64_t r0 = (int64_t)blockIdx.x * rows_per_block, r1 = min(n, r0 + rows_per_block);
+    for (int c = threadIdx.x; c < d; c += blockDim.x) {
+        float s = 0.0f;
+        for (int64_t r = r0; r < r1; ++r) s += __bfloat162float(x[r * ld + c]);
+        atomicAdd(out + c, s);
+    }
+}
+
+int colsum_bf16_launch(const void* x, int64_t ld, int64_t n, int d, float* out, cudaStream_t s) {
+    GS_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * d, s));
+    if (n == 0) return GSAGE_OK;
+    const int64_t rows_per_block = std::max<int64_t>(64, ceil_div(n, 148 * 8));
+    colsum_bf16_kernel<<<(unsigned)ceil_div(n, rows_per_block), 256, 0, s>>>((const __nv_bfloat16*)x, ld, n, d, rows_per_block, out);
+    GS_LAUNCHED();
+    return GSAGE_OK;
+}
+
 int colsum_launch(const float* x, int64_t n, int d, float* out, cudaStream_t s) {
     colsum_kernel<<<d, 256, 0, s>>>(x, n, d, out);
     GS_LAUNCHED();

@@ -19,9 +19,11 @@ struct WgradJob {
     int64_t a_rows = 0;                                   // rows of the table behind A when known (ids outside it read as zero rows)
 };
 bool wgrad_umma_eligible(const WgradJob& j);
-int wgrad_umma_launch(const WgradJob* jobs, int n_jobs, cudaStream_t s);
+int wgrad_umma_launch(const WgradJob* jobs, int n_jobs, cudaStream_t s, bool accumulate = false);   // accumulate: dW += instead of dW =
 int l2_normalize_bwd_launch(const float* z, const float* dzn, int64_t n, int d, int act, float* dz, cudaStream_t s, void* dz_bf16 = nullptr);
 int layer1_grad_launch(const float* dh0, const float* dm2, const void* H, int h_dtype, int64_t ldh, int64_t n0, int64_t n1, int S,
                        int width, int act, void* dH, int dh_dtype, cudaStream_t s);
 int colsum_launch(const float* x, int64_t n, int d, float* out, cudaStream_t s);
+// column sums of a bf16 (n, ld) matrix over its first d columns -> fp32
+int colsum_bf16_launch(const void* x, int64_t ld, int64_t n, int d, float* out, cudaStream_t s);
 }

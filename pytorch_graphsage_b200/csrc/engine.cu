@@ -130,6 +130,7 @@ struct gsage_engine {
     char* wb = nullptr; int64_t wb_bytes = 0;
     WRef w_x[2], w_n[2], w_mlp[2], w_att1[2];
     WRef w_nT[2], w_mlpT[2];            // pool backward (bf16): fc_neib^T (H x O) and mlp.0.weight^T (d_in x H), K-major
+    WRef w_xT0;                         // pool + folded node_embedding backward (bf16): (Wx.Wp)^T (emb_dim x O1), K-major
     WRef w_x2T, w_n2T;                  // mean backward (bf16): layer-2 fc_x^T / fc_neib^T (2*O1 x O2), K-major, for the head's data gradients
     void* DZB = nullptr;                // bf16 copy of d loss / d z (operand of the tensor-core head gradients)
     float* DP = nullptr;                // pool backward: d loss / d pooled rows, (n0 + n1) x H fp32
@@ -369,9 +370,11 @@ int gsage_engine_create(const gsage_engine_config* cfg, gsage_engine** out) {
     const int64_t o_DH0 = carve(4 * 2 * O1 * e->n0), o_DM2 = carve(4 * 2 * O1 * e->n0);
     const int64_t o_DZB = carve(2 * 2 * O2 * e->n0);
     const int64_t o_DH = carve(4 * 2 * O1 * (e->n0 + e->n1));
-    const int64_t o_DXE = e->fold_prep ? carve(4 * (int64_t)cfg->emb_dim * (e->n0 + e->n1)) : -1;
+    // (n0 + n1) self rows for the mean recipe; the pool recipe also needs one row per sampled neighbour (n1 + n2)
+    const int64_t o_DXE = e->fold_prep ? carve(4 * (int64_t)cfg->emb_dim * ((cfg->aggregator == GSAGE_AGG_MEAN ? 0 : e->n2) + e->n0 + e->n1)) : -1;
     const bool pool_cfg = cfg->aggregator == GSAGE_AGG_MAX_POOL || cfg->aggregator == GSAGE_AGG_MEAN_POOL;
-    const bool pool_bwd = pool_cfg && e->T == GSAGE_BF16 && cfg->prep == GSAGE_PREP_IDENTITY && getenv("GSAGE_NO_POOL_BACKWARD") == nullptr;
+    const bool pool_bwd = pool_cfg && e->T == GSAGE_BF16 && (cfg->prep == GSAGE_PREP_IDENTITY || e->fold_prep) &&
+                          getenv("GSAGE_NO_POOL_BACKWARD") == nullptr;
     const int64_t o_DP = pool_bwd ? carve(4 * (int64_t)e->hid * (e->n0 + e->n1)) : -1;
     const int64_t o_DHID = pool_bwd ? carve(2 * (int64_t)e->hid * (e->n1 + e->n2)) : -1;
     const int64_t o_DN2 = pool_bwd ? carve(4 * 2 * O1 * e->n1) : -1;
@@ -544,9 +547,11 @@ int gsage_engine_set_weights(gsage_engine* e, const gsage_weights* w, void* stre
         }
         if (pool && e->T == GSAGE_BF16 && e->DP) {
             // K-major transposed copies for the pool backward's data-gradient projections
-            struct TItem { const float* src; int rows, cols; WRef* dst; } titems[2] = {
-                {w->layer[l].fc_neib, O, e->hid, &e->w_nT[l]}, {w->layer[l].mlp_w, e->hid, d_in, &e->w_mlpT[l]}};
+            struct TItem { const float* src; int rows, cols; WRef* dst; } titems[3] = {
+                {w->layer[l].fc_neib, O, e->hid, &e->w_nT[l]}, {w->layer[l].mlp_w, e->hid, d_in, &e->w_mlpT[l]},
+                {(l == 0 && e->fold_prep) ? w->layer[0].fc_x : nullptr, O, d_in, &e->w_xT0}};
             for (const TItem& it : titems) {
+                if (!it.src) continue;
                 const int64_t ld = pad_to(it.rows, 8);
                 const int64_t bytes = pad_to(2 * ld * it.cols, 256);
                 GS_CHECK_ARG(off + bytes <= e->wb_bytes, "engine_set_weights: bf16 weight arena too small (transposed copies)");
@@ -938,16 +943,26 @@ int gsage_engine_backward_layer1_embedding(gsage_engine* e, const gsage_embeddin
 //   spread over the open relus for the mean pool) by linear_pool_ws_umma_kernel<.., BWD>; it is the one large intermediate
 //   (rows x H bf16) --  dW1 = dHid^T n (wgrad_umma, 128-unit blocks as parallel jobs),  db1 = column sums (in the same kernel),
 //   and for layer 2 the input gradient dN = dHid W1 that flows into layer 1.
-int gsage_engine_backward_pool(gsage_engine* e, const float* dlogits, const gsage_grads* g, const gsage_pool_grads* pg, void* stream) {
+static int backward_pool_impl(gsage_engine* e, const float* dlogits, const gsage_grads* g, const gsage_pool_grads* pg,
+                              const gsage_pool_embedding_grads* eg, void* stream) {
     GS_CHECK_ARG(e && e->have_weights && e->B > 0, "engine_backward_pool: run gsage_engine_forward first");
     const gsage_engine_config& c = e->cfg;
     const bool pool = c.aggregator == GSAGE_AGG_MAX_POOL || c.aggregator == GSAGE_AGG_MEAN_POOL;
-    GS_CHECK_ARG(pool && c.prep == GSAGE_PREP_IDENTITY && e->T == GSAGE_BF16 && e->DP,
-                 "engine_backward_pool: implemented for the max / mean pool aggregators with the identity prep in bf16 compute mode");
+    const bool fold = e->fold_prep;
+    GS_CHECK_ARG(pool && (c.prep == GSAGE_PREP_IDENTITY || fold) && e->T == GSAGE_BF16 && e->DP,
+                 "engine_backward_pool: implemented for the max / mean pool aggregators in bf16 compute mode, with the identity prep or "
+                 "the node_embedding prep without features");
+    GS_CHECK_ARG(fold == (eg != nullptr), fold ? "engine_backward_pool: node_embedding models use gsage_engine_backward_pool_embedding"
+                                               : "engine_backward_pool_embedding: not a node_embedding model");
+    if (eg) GS_CHECK_ARG(eg->csum_x && eg->d_table && c.emb_dtype == GSAGE_BF16, "engine_backward_pool_embedding: NULL argument / table not bf16");
     GS_CHECK_ARG(e->keep_activations, "engine_backward_pool: call gsage_engine_keep_activations(e, 1) before the forward");
     GS_CHECK_ARG(dlogits && g && pg && g->fc_w && g->fc_b && g->fc_x[0] && g->fc_x[1] && g->fc_neib[0] && g->fc_neib[1] &&
                  pg->mlp_w[0] && pg->mlp_w[1] && pg->mlp_b[0] && pg->mlp_b[1], "engine_backward_pool: NULL argument");
-    const int O1 = c.out_dim[0], O2 = c.out_dim[1], C = c.n_classes, S1 = c.fanout[0], S2 = c.fanout[1], H = e->hid, d = c.feats_dim;
+    const int O1 = c.out_dim[0], O2 = c.out_dim[1], C = c.n_classes, S1 = c.fanout[0], S2 = c.fanout[1], H = e->hid;
+    // layer 1 reads rows of the feature table, or (folded node_embedding prep) of the raw embedding table
+    const void* tab = fold ? c.emb_dev : c.feats_dev;
+    const int64_t tab_ld = fold ? c.emb_ld : c.feats_ld, tab_rows = fold ? c.n_nodes + 1 : c.feats_rows;
+    const int d = fold ? c.emb_dim : c.feats_dim;
     GS_CHECK_ARG(O1 == 128 && O2 == 128 && H % 128 == 0, "engine_backward_pool: needs output_dim 128 and a hidden width that is a multiple of 128 "
                  "(the tensor-core weight-gradient kernel works on 128-row blocks)");
     cudaStream_t s = as_stream(stream);
@@ -964,7 +979,7 @@ int gsage_engine_backward_pool(gsage_engine* e, const float* dlogits, const gsag
         P.n_segs = 1; P.n = n_rows; P.act = GSAGE_ACT_RELU; P.out = nullptr; P.out_dtype = GSAGE_BF16; P.ld_out = H;
         P.seg[0] = LinearSeg{a, GSAGE_BF16, lda, ids, e->w_mlp[layer].p, GSAGE_BF16, e->w_mlp[layer].ld, d_in, H, e->b_mlp[layer], 0};
         P.pool_S = S; P.pool_max = pool_max;
-        P.seg[0].a_rows = ids ? c.feats_rows : 0;
+        P.seg[0].a_rows = ids ? tab_rows : 0;
         return linear_pool_ws_umma_backward_launch(P, dP, H, dhid, H, db, s);
     };
     auto mlp_wgrad = [&](const __nv_bfloat16* dhid, const void* a, int64_t lda, const int64_t* ids, int d_in, int64_t n_rows, float* dW) -> int {
@@ -973,7 +988,7 @@ int gsage_engine_backward_pool(gsage_engine* e, const float* dlogits, const gsag
             const int nj = std::min(4, H / 128 - b0);
             for (int j = 0; j < nj; ++j)
                 jobs[j] = WgradJob{dhid + (b0 + j) * 128, GSAGE_BF16, (int64_t)H, 128, a, GSAGE_BF16, lda, ids, d_in, n_rows,
-                                   dW + (int64_t)(b0 + j) * 128 * d_in, (int64_t)d_in, ids ? c.feats_rows : 0};
+                                   dW + (int64_t)(b0 + j) * 128 * d_in, (int64_t)d_in, ids ? tab_rows : 0};
             GS_TRY(wgrad_umma_launch(jobs, nj, s));
         }
         return GSAGE_OK;
@@ -1004,9 +1019,18 @@ int gsage_engine_backward_pool(gsage_engine* e, const float* dlogits, const gsag
     // ---- layer 1 on (x0, x1) and (x1, x2), shared weights ------------------------------------------------------------------
     const __nv_bfloat16* dh = (const __nv_bfloat16*)e->DH;
     {
-        WgradJob jx{dh, GSAGE_BF16, 2 * (int64_t)O1, O1, c.feats_dev, c.feats_dtype, c.feats_ld, ids0, d, rows, g->fc_x[0], (int64_t)d, c.feats_rows};
-        GS_CHECK_ARG(wgrad_umma_eligible(jx), "engine_backward_pool: the feature table does not qualify for the tensor-core weight gradient");
-        GS_TRY(wgrad_umma_launch(&jx, 1, s));
+        if (!fold) {
+            WgradJob jx{dh, GSAGE_BF16, 2 * (int64_t)O1, O1, tab, GSAGE_BF16, tab_ld, ids0, d, rows, g->fc_x[0], (int64_t)d, tab_rows};
+            GS_CHECK_ARG(wgrad_umma_eligible(jx), "engine_backward_pool: the feature table does not qualify for the tensor-core weight gradient");
+            GS_TRY(wgrad_umma_launch(&jx, 1, s));
+        } else {
+            // seeds read the masked row n_nodes (look0), hop-1 parents their own id: two launches into the same buffer
+            WgradJob j0{dh, GSAGE_BF16, 2 * (int64_t)O1, O1, tab, GSAGE_BF16, tab_ld, e->look0, d, n0, g->fc_x[0], (int64_t)d, tab_rows};
+            WgradJob j1{dh + n0 * 2 * (int64_t)O1, GSAGE_BF16, 2 * (int64_t)O1, O1, tab, GSAGE_BF16, tab_ld, ids1, d, n1, g->fc_x[0], (int64_t)d, tab_rows};
+            GS_CHECK_ARG(wgrad_umma_eligible(j0), "engine_backward_pool: the embedding table does not qualify for the tensor-core weight gradient");
+            GS_TRY(wgrad_umma_launch(&j0, 1, s));
+            GS_TRY(wgrad_umma_launch(&j1, 1, s, true));
+        }
         WgradJob jn{dh + O1, GSAGE_BF16, 2 * (int64_t)O1, O1, Pp, GSAGE_BF16, (int64_t)H, nullptr, H, rows, g->fc_neib[0], (int64_t)H};
         GS_TRY(wgrad_umma_launch(&jn, 1, s));
     }
@@ -1017,10 +1041,38 @@ int gsage_engine_backward_pool(gsage_engine* e, const float* dlogits, const gsag
         GS_TRY(linear_dispatch(P, 0, s));
     }
     GS_CUDA(cudaMemsetAsync(pg->mlp_b[0], 0, sizeof(float) * H, s));
-    GS_TRY(pool_bwd(0, c.feats_dev, c.feats_ld, ids1, d, n1, S1, e->DP, DHID, pg->mlp_b[0]));                              // (x0, x1)
-    GS_TRY(pool_bwd(0, c.feats_dev, c.feats_ld, ids2, d, n2, S2, e->DP + n0 * (int64_t)H, DHID + n1 * (int64_t)H, pg->mlp_b[0]));   // (x1, x2)
-    GS_TRY(mlp_wgrad(DHID, c.feats_dev, c.feats_ld, ids1, d, n1 + n2, pg->mlp_w[0]));
+    GS_TRY(pool_bwd(0, tab, tab_ld, ids1, d, n1, S1, e->DP, DHID, pg->mlp_b[0]));                              // (x0, x1)
+    GS_TRY(pool_bwd(0, tab, tab_ld, ids2, d, n2, S2, e->DP + n0 * (int64_t)H, DHID + n1 * (int64_t)H, pg->mlp_b[0]));   // (x1, x2)
+    GS_TRY(mlp_wgrad(DHID, tab, tab_ld, ids1, d, n1 + n2, pg->mlp_w[0]));
+    if (fold) {
+        // With the prep folded in (W1' = W1.Wp, Wx' = Wx.Wp), fc_x[0] / mlp_w[0] above are the RAW reductions against the
+        // embedding rows (the caller unfolds them, see model.GSSupervised.backward); here the rest: column sums of Gx and
+        // the dense gradient of the embedding table = every row's d loss / d (raw embedding), scatter-added by id
+        GS_TRY(colsum_bf16_launch(dh, 2 * O1, rows, O1, eg->csum_x, s));
+        GS_CUDA(cudaMemsetAsync(eg->d_table, 0, sizeof(float) * (size_t)tab_rows * d, s));
+        LinearParams P;
+        P.n_segs = 1; P.act = GSAGE_ACT_NONE; P.out = e->DXE; P.out_dtype = GSAGE_F32; P.ld_out = d;
+        P.n = n1 + n2;                                                       // neighbours: dHid . W1'
+        P.seg[0] = LinearSeg{DHID, GSAGE_BF16, (int64_t)H, nullptr, e->w_mlpT[0].p, GSAGE_BF16, e->w_mlpT[0].ld, H, d, nullptr, 0};
+        GS_TRY(linear_dispatch(P, 0, s));
+        GS_TRY(embedding_scatter_launch(e->DXE, d, d, ids1, n1 + n2, 1, 1.0f, eg->d_table, d, tab_rows, s));
+        P.n = rows;                                                          // self rows: Gx . Wx'
+        P.seg[0] = LinearSeg{dh, GSAGE_BF16, 2 * (int64_t)O1, nullptr, e->w_xT0.p, GSAGE_BF16, e->w_xT0.ld, O1, d, nullptr, 0};
+        GS_TRY(linear_dispatch(P, 0, s));
+        GS_TRY(embedding_scatter_launch(e->DXE, d, d, e->look0, n0, 1, 1.0f, eg->d_table, d, tab_rows, s));
+        GS_TRY(embedding_scatter_launch(e->DXE + n0 * (int64_t)d, d, d, ids1, n1, 1, 1.0f, eg->d_table, d, tab_rows, s));
+    }
     return mark_slot_done(e, s);
+}
+
+int gsage_engine_backward_pool(gsage_engine* e, const float* dlogits, const gsage_grads* g, const gsage_pool_grads* pg, void* stream) {
+    return backward_pool_impl(e, dlogits, g, pg, nullptr, stream);
+}
+
+int gsage_engine_backward_pool_embedding(gsage_engine* e, const float* dlogits, const gsage_grads* g, const gsage_pool_grads* pg,
+                                         const gsage_pool_embedding_grads* eg, void* stream) {
+    GS_CHECK_ARG(eg, "engine_backward_pool_embedding: NULL argument");
+    return backward_pool_impl(e, dlogits, g, pg, eg, stream);
 }
 
 int gsage_engine_peek(gsage_engine* e, int what, const void** ptr, int64_t* rows, int64_t* cols, int64_t* ld, int* dtype) {

@@ -228,12 +228,12 @@ static int* g_wg_err = nullptr;
 
 // all jobs of one launch share n (rows), O = 128 and d (the fc_x / fc_neib pair of one layer application, or the four
 // 128-unit blocks of a pool MLP's weight gradient)
-int wgrad_umma_launch(const WgradJob* jobs, int n_jobs, cudaStream_t s) {
+int wgrad_umma_launch(const WgradJob* jobs, int n_jobs, cudaStream_t s, bool accumulate) {
     GS_CHECK_ARG(n_jobs >= 1 && n_jobs <= kWgMaxJobs, "wgrad_umma: one to four jobs per launch");
     for (int i = 0; i < n_jobs; ++i) {
         GS_CHECK_ARG(wgrad_umma_eligible(jobs[i]), "wgrad_umma: job %d does not qualify (bf16, O == 128, aligned rows)", i);
         GS_CHECK_ARG(jobs[i].n == jobs[0].n && jobs[i].d == jobs[0].d, "wgrad_umma: jobs of one launch must share n and d");
-        GS_CUDA(cudaMemsetAsync(jobs[i].dW, 0, sizeof(float) * (size_t)128 * jobs[i].lddw, s));
+        if (!accumulate) GS_CUDA(cudaMemsetAsync(jobs[i].dW, 0, sizeof(float) * (size_t)128 * jobs[i].lddw, s));
     }
     WgParams U;
     memset(&U, 0, sizeof(U));

@@ -167,6 +167,9 @@ class GSSupervised(nn.Module):
         (torch bumps `_version` on every in-place write, e.g. an optimiser step)."""
         stamp = tuple((p.data_ptr(), p._version) for p in self.parameters()) + (getattr(self, '_weights_epoch', 0),)
         if eng.get('stamp') != stamp:
+            if eng.get('emb_keep') is not None:                     # bf16 mode: the engine reads a bf16 copy of the learned table
+                keep = eng['emb_keep']
+                keep.store[:, :keep.d].copy_(self.prep.embedding.weight.data)
             w = self._weights()
             check(lib().gsage_engine_set_weights(eng['h'], C.byref(w), ops.stream()))
             eng['stamp'] = stamp
@@ -271,7 +274,26 @@ class GSSupervised(nn.Module):
                 pg.mlp_b[k] = bucket.grad_of(aggs[k].mlp[0].bias).data_ptr()
             g.fc_w, g.fc_b = bucket.grad_of(self.fc.weight).data_ptr(), bucket.grad_of(self.fc.bias).data_ptr()
             dlogits = dlogits.contiguous().float()
-            check(lib().gsage_engine_backward_pool(self._last['h'], ops.ptr(dlogits), C.byref(g), C.byref(pg), ops.stream()))
+            if self._prep_name == 'node_embedding':
+                # BASELINE config C3 (Pokec): the prep's affine is folded into layer 1, so the library returns the raw
+                # reductions against the embedding rows and the (O x 64)(64 x 64) unfolding products are done here
+                O = aggs[0].fc_x.weight.shape[0]
+                csum_x = torch.empty((O,), dtype=torch.float32, device='cuda')
+                eg = _lib.PoolEmbeddingGrads()
+                eg.csum_x, eg.d_table = csum_x.data_ptr(), bucket.grad_of(self.prep.embedding.weight).data_ptr()
+                check(lib().gsage_engine_backward_pool_embedding(self._last['h'], ops.ptr(dlogits), C.byref(g), C.byref(pg), C.byref(eg),
+                                                                 ops.stream()))
+                Wp, bp = self.prep.fc.weight.data, self.prep.fc.bias.data
+                Wx, W1 = aggs[0].fc_x.weight.data, aggs[0].mlp[0].weight.data
+                gx_raw = bucket.grad_of(aggs[0].fc_x.weight).clone()
+                g1_raw = bucket.grad_of(aggs[0].mlp[0].weight).clone()
+                c1 = bucket.grad_of(aggs[0].mlp[0].bias)
+                bucket.grad_of(aggs[0].fc_x.weight).copy_(gx_raw @ Wp.t() + torch.outer(csum_x, bp))
+                bucket.grad_of(aggs[0].mlp[0].weight).copy_(g1_raw @ Wp.t() + torch.outer(c1, bp))
+                bucket.grad_of(self.prep.fc.weight).copy_(Wx.t() @ gx_raw + W1.t() @ g1_raw)
+                bucket.grad_of(self.prep.fc.bias).copy_(Wx.t() @ csum_x + W1.t() @ c1)
+            else:
+                check(lib().gsage_engine_backward_pool(self._last['h'], ops.ptr(dlogits), C.byref(g), C.byref(pg), ops.stream()))
             bucket.all_reduce(grad_scale)
             return bucket
         for k in range(2):
