@@ -391,7 +391,8 @@ def run_ours(args):
     # ---- one optimiser step per batch (forward + loss + backward + gradient all-reduce + clip + Adam) ---------------
     train = None
     trainable = (prob['aggregator'] == 'mean' and (prob['prep'] == 'identity' or (prob['prep'] == 'node_embedding' and dtype == torch.float32 and not tf32))) or \
-                (prob['aggregator'] in ('max_pool', 'mean_pool') and dtype == torch.bfloat16)
+                (prob['aggregator'] in ('max_pool', 'mean_pool') and dtype == torch.bfloat16) or \
+                (prob['aggregator'] == 'attention' and prob['prep'] == 'identity' and dtype == torch.bfloat16)
     if trainable and not args.no_train:
         from torch.nn import functional as F
         if prob['task'] == 'regression_mae':                                       # problem.py:39-41: l1 loss on (B, 1) predictions

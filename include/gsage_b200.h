@@ -327,6 +327,13 @@ int gsage_engine_backward_pool_embedding(gsage_engine* e, const float* dlogits_d
 int gsage_adam_step(float* param_dev, float* grad_dev, float* m_dev, float* v_dev, int64_t n, float lr, float beta1, float beta2,
                     float eps, float weight_decay, int64_t step, float max_norm, float* scratch_dev, void* stream);
 
+/* Every parameter gradient of an attention model (bf16 compute, identity prep, output_dim 128, feature width % 16 == 0) in
+ * one call (nn_modules.py:289-321 through loss.backward(), models.py:101).  `ag`: gradients of agg_layers.k.att.0.weight
+ * (32, d_in) and agg_layers.k.att.2.weight (32, 32).  All buffers fp32, overwritten. */
+typedef struct gsage_attention_grads { float* att_w1[2]; float* att_w2[2]; } gsage_attention_grads;
+int gsage_engine_backward_attention(gsage_engine* e, const float* dlogits_dev, const gsage_grads* grads,
+                                    const gsage_attention_grads* att_grads, void* stream);
+
 /* keep != 0: the next forwards keep every activation the backward pass needs (training).  0 (default): forward-only
  * streaming -- intermediates may be processed in L2-sized chunks that reuse their buffers. */
 int gsage_engine_keep_activations(gsage_engine* e, int keep);

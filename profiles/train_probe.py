@@ -14,12 +14,13 @@ from pytorch_graphsage_b200 import synth         # noqa: E402
 
 steps = int(sys.argv[1]) if len(sys.argv) > 1 else 3
 B = int(sys.argv[2]) if len(sys.argv) > 2 else 16384
-args = type('A', (), dict(workload='reddit', scale=1.0))()
+workload = sys.argv[3] if len(sys.argv) > 3 else 'reddit'
+args = type('A', (), dict(workload=workload, scale=1.0))()
 prob = bench.make_problem(args)
 graph = g.GraphCSR.from_synth(prob['adj'])
 table = g.FeatureTable(prob['feats'], torch.bfloat16)
 model = g.GSSupervised(input_dim=prob['feats_dim'], n_nodes=prob['n_nodes'], n_classes=prob['n_classes'], layer_specs=bench.layer_specs(),
-                       aggregator_class=g.aggregator_lookup['mean'], prep_class=g.prep_lookup['identity'],
+                       aggregator_class=g.aggregator_lookup[prob['aggregator']], prep_class=g.prep_lookup[prob['prep']],
                        sampler_class=g.sampler_lookup['sparse_uniform_neighbor_sampler'], adj=graph, train_adj=graph,
                        compute_dtype=torch.bfloat16, max_batch=B)
 model.load_state_dict(bench.reference_params(prob))

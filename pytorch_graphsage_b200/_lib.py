@@ -49,6 +49,10 @@ class PoolGrads(C.Structure):
     _fields_ = [('mlp_w', c_p * 2), ('mlp_b', c_p * 2)]
 
 
+class AttentionGrads(C.Structure):
+    _fields_ = [('att_w1', c_p * 2), ('att_w2', c_p * 2)]
+
+
 class PoolEmbeddingGrads(C.Structure):
     _fields_ = [('csum_x', c_p), ('d_table', c_p)]
 
@@ -111,6 +115,7 @@ _SIGNATURES = {
     'gsage_engine_backward_head': (C.c_int, [c_p, c_p, C.POINTER(Grads), c_p]),
     'gsage_engine_backward_layer1': (C.c_int, [c_p, C.POINTER(Grads), c_p]),
     'gsage_engine_backward_pool': (C.c_int, [c_p, c_p, C.POINTER(Grads), C.POINTER(PoolGrads), c_p]),
+    'gsage_engine_backward_attention': (C.c_int, [c_p, c_p, C.POINTER(Grads), C.POINTER(AttentionGrads), c_p]),
     'gsage_engine_backward_pool_embedding': (C.c_int, [c_p, c_p, C.POINTER(Grads), C.POINTER(PoolGrads), C.POINTER(PoolEmbeddingGrads), c_p]),
     'gsage_engine_backward_layer1_embedding': (C.c_int, [c_p, C.POINTER(EmbeddingGrads), c_p]),
     'gsage_wgrad': (C.c_int, [c_p, C.c_int, c_i64, C.c_int, c_p, C.c_int, c_i64, c_i64, c_p, C.c_int, c_i64, c_p, c_i64, C.c_int, c_p]),

@@ -193,6 +193,127 @@ int embedding_scatter_launch(const float* rows, int64_t ld, int d, const int64_t
     return GSAGE_OK;
 }
 
+// ---- attention aggregator, backwards (nn_modules.py:307-315) ------------------------------------------------------------
+//   m_p = sum_j w_pj n_pj,  w_p = softmax_j(s_pj),  s_pj = <a(n_pj), a(x_p)>,  a(v) = W2 tanh(W1 v)
+
+// dw[p*S + j] = <dM[p], n_pj>  (gradient of the softmax weights), and optionally dN[p*S + j, :] = w_pj * dM[p, :] (the part of
+// the neighbour rows' gradient that does not go through the attention MLP; layer 2 only).  One warp per parent: every lane
+// keeps its 16-byte chunks of dM[p] in registers and streams the S neighbour rows once.
+__global__ void __launch_bounds__(256) attention_dw_kernel(const __nv_bfloat16* __restrict__ table, int64_t ld, int64_t n_table_rows, int d,
+                                                           const int64_t* __restrict__ ids, int64_t n_parents, int S,
+                                                           const float* __restrict__ dM, int64_t ld_dm, const float* __restrict__ w,
+                                                           float* __restrict__ dw, float* __restrict__ dN, int64_t ld_dn) {
+    const int lane = threadIdx.x & 31;
+    const int64_t p = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (p >= n_parents) return;
+    const int nch = (d + 7) / 8;
+    for (int j = 0; j < S; ++j) {
+        const int64_t r = p * S + j;
+        const int64_t id = ids ? ids[r] : r;
+        const bool live = (uint64_t)id < (uint64_t)n_table_rows;
+        const float wj = dN ? w[r] : 0.0f;
+        float acc = 0.0f;
+        for (int c = lane; c < nch; c += 32) {
+            float g[8], f[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) g[e] = (c * 8 + e < d) ? dM[p * ld_dm + c * 8 + e] : 0.0f;
+            uint4 v = make_uint4(0, 0, 0, 0);
+            if (live) v = ldg_nc_v4(table + id * ld + (int64_t)c * 8);
+            ElemTraits<__nv_bfloat16>::unpack(v, f);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) acc = fmaf(g[e], f[e], acc);
+            if (dN) {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) if (c * 8 + e < d) dN[r * ld_dn + c * 8 + e] = wj * g[e];
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xFFFFFFFFu, acc, o);
+        if (lane == 0) dw[r] = acc;
+    }
+}
+
+// softmax backwards + the score's two factors: ds = w (dw - <w, dw>);  dA[r, :] = ds_r * xa[p, :];  dXA[p, :] = sum_j ds_r * na[r, :]
+__global__ void __launch_bounds__(256) attention_softmax_bwd_kernel(const float* __restrict__ w, const float* __restrict__ dw,
+                                                                    const float* __restrict__ na, const float* __restrict__ xa, int H,
+                                                                    int64_t n_parents, int S, float* __restrict__ dA, float* __restrict__ dXA) {
+    const int lane = threadIdx.x & 31;
+    const int64_t p = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (p >= n_parents) return;
+    float dot = 0.0f;
+    for (int j = lane; j < S; j += 32) dot = fmaf(w[p * S + j], dw[p * S + j], dot);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) dot += __shfl_xor_sync(0xFFFFFFFFu, dot, o);
+    const float xav = lane < H ? xa[p * H + lane] : 0.0f;          // H <= 32: lane h holds xa[p, h]
+    float dxa = 0.0f;
+    for (int j = 0; j < S; ++j) {
+        const int64_t r = p * S + j;
+        const float ds = w[r] * (dw[r] - dot);
+        if (lane < H) {
+            dA[r * H + lane] = ds * xav;
+            dxa = fmaf(ds, na[r * H + lane], dxa);
+        }
+    }
+    if (lane < H) dXA[p * H + lane] = dxa;
+}
+
+// dpre = dt1 * (1 - t1^2)   (tanh', in place on dt1)
+__global__ void __launch_bounds__(256) tanh_bwd_kernel(float* __restrict__ dt1, const float* __restrict__ t1, int64_t n) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) { const float t = t1[i]; dt1[i] *= (1.0f - t * t); }
+}
+
+// dH[r, :] = (a[r, :] + b[r, :]) * act'(H[r, :]) for the two row ranges [0, n0) (self rows) and [n0, n0 + n1) (neighbour rows)
+__global__ void __launch_bounds__(256) sum_act_grad_kernel(const float* __restrict__ a0, const float* __restrict__ b0, const float* __restrict__ a1,
+                                                           const float* __restrict__ b1, const void* __restrict__ H, int h_dtype, int64_t ldh,
+                                                           int64_t n0, int64_t n1, int width, int act, void* __restrict__ dH, int dh_bf16) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (n0 + n1) * width) return;
+    const int64_t r = i / width;
+    const int c = (int)(i - r * width);
+    float g = r < n0 ? a0[r * width + c] + b0[r * width + c] : a1[(r - n0) * width + c] + b1[(r - n0) * width + c];
+    const float h = ld_any(H, h_dtype, r * ldh + c);
+    if (act == GSAGE_ACT_RELU) g = h > 0.0f ? g : 0.0f;
+    else if (act == GSAGE_ACT_TANH) g *= (1.0f - h * h);
+    if (dh_bf16) reinterpret_cast<__nv_bfloat16*>(dH)[i] = __float2bfloat16_rn(g);
+    else reinterpret_cast<float*>(dH)[i] = g;
+}
+
+int attention_dw_launch(const void* table, int64_t ld, int64_t n_table_rows, int d, const int64_t* ids, int64_t n_parents, int S,
+                        const float* dM, int64_t ld_dm, const float* w, float* dw, float* dN, int64_t ld_dn, cudaStream_t s) {
+    if (n_parents == 0) return GSAGE_OK;
+    attention_dw_kernel<<<(unsigned)ceil_div(n_parents, 8), 256, 0, s>>>((const __nv_bfloat16*)table, ld, n_table_rows, d, ids, n_parents, S, dM,
+                                                                        ld_dm, w, dw, dN, ld_dn);
+    GS_LAUNCHED();
+    return GSAGE_OK;
+}
+
+int attention_softmax_bwd_launch(const float* w, const float* dw, const float* na, const float* xa, int H, int64_t n_parents, int S,
+                                 float* dA, float* dXA, cudaStream_t s) {
+    GS_CHECK_ARG(H <= 32, "attention_softmax_bwd: attention width must be <= 32");
+    if (n_parents == 0) return GSAGE_OK;
+    attention_softmax_bwd_kernel<<<(unsigned)ceil_div(n_parents, 8), 256, 0, s>>>(w, dw, na, xa, H, n_parents, S, dA, dXA);
+    GS_LAUNCHED();
+    return GSAGE_OK;
+}
+
+int tanh_bwd_launch(float* dt1, const float* t1, int64_t n, cudaStream_t s) {
+    if (n == 0) return GSAGE_OK;
+    tanh_bwd_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, s>>>(dt1, t1, n);
+    GS_LAUNCHED();
+    return GSAGE_OK;
+}
+
+int sum_act_grad_launch(const float* a0, const float* b0, const float* a1, const float* b1, const void* H, int h_dtype, int64_t ldh,
+                        int64_t n0, int64_t n1, int width, int act, void* dH, int dh_dtype, cudaStream_t s) {
+    const int64_t total = (n0 + n1) * width;
+    if (total == 0) return GSAGE_OK;
+    sum_act_grad_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, s>>>(a0, b0, a1, b1, H, h_dtype, ldh, n0, n1, width, act, dH,
+                                                                      dh_dtype == GSAGE_BF16 ? 1 : 0);
+    GS_LAUNCHED();
+    return GSAGE_OK;
+}
+
 int wgrad_launch(const float* G, int64_t ldg, int O, const void* A, int a_dtype, int64_t lda, const int64_t* ids, int d,
                  int64_t n, float* dW, int64_t lddw, cudaStream_t s, bool accumulate) {
     if (!accumulate) GS_CUDA(cudaMemsetAsync(dW, 0, sizeof(float) * (size_t)O * lddw, s));

@@ -133,6 +133,10 @@ struct gsage_engine {
     WRef w_xT0;                         // pool + folded node_embedding backward (bf16): (Wx.Wp)^T (emb_dim x O1), K-major
     WRef w_x2T, w_n2T;                  // mean backward (bf16): layer-2 fc_x^T / fc_neib^T (2*O1 x O2), K-major, for the head's data gradients
     void* DZB = nullptr;                // bf16 copy of d loss / d z (operand of the tensor-core head gradients)
+    // attention backward (bf16, identity prep): d loss / d aggregated rows, d softmax weights, d a(n), d tanh input, d a(x), and
+    // the four partial input gradients of layer 2 (self / neighbour rows x direct / through-the-attention-MLP)
+    float* ADM = nullptr; float* ADW = nullptr; float* ADA = nullptr; float* ADT1 = nullptr; float* ADXA = nullptr; float* ADT1X = nullptr;
+    float* ASA = nullptr; float* ASB = nullptr; float* ANA = nullptr; float* ANB = nullptr;
     float* DP = nullptr;                // pool backward: d loss / d pooled rows, (n0 + n1) x H fp32
     void* DHID = nullptr;               // pool backward: d loss / d hidden rows, (n1 + n2) x H bf16
     float* DN2 = nullptr;               // pool backward: d loss / d (layer-2 neighbour rows), n1 x 2*O1 fp32
@@ -369,6 +373,13 @@ int gsage_engine_create(const gsage_engine_config* cfg, gsage_engine** out) {
     const int64_t o_DZN = carve(4 * 2 * O2 * e->n0), o_DZ = carve(4 * 2 * O2 * e->n0);
     const int64_t o_DH0 = carve(4 * 2 * O1 * e->n0), o_DM2 = carve(4 * 2 * O1 * e->n0);
     const int64_t o_DZB = carve(2 * 2 * O2 * e->n0);
+    const bool att_bwd = cfg->aggregator == GSAGE_AGG_ATTENTION && e->T == GSAGE_BF16 && cfg->prep == GSAGE_PREP_IDENTITY &&
+                         getenv("GSAGE_NO_ATTENTION_BACKWARD") == nullptr;
+    const int64_t o_ADM = att_bwd ? carve(4 * e->ld_m * (e->n0 + e->n1)) : -1, o_ADW = att_bwd ? carve(4 * e->n2) : -1;
+    const int64_t o_ADA = att_bwd ? carve(4 * (int64_t)e->hid * e->n2) : -1, o_ADT1 = att_bwd ? carve(4 * (int64_t)e->hid * e->n2) : -1;
+    const int64_t o_ADXA = att_bwd ? carve(4 * (int64_t)e->hid * e->n1) : -1, o_ADT1X = att_bwd ? carve(4 * (int64_t)e->hid * e->n1) : -1;
+    const int64_t o_ASA = att_bwd ? carve(4 * 2 * O1 * e->n0) : -1, o_ASB = att_bwd ? carve(4 * 2 * O1 * e->n0) : -1;
+    const int64_t o_ANA = att_bwd ? carve(4 * 2 * O1 * e->n1) : -1, o_ANB = att_bwd ? carve(4 * 2 * O1 * e->n1) : -1;
     const int64_t o_DH = carve(4 * 2 * O1 * (e->n0 + e->n1));
     // (n0 + n1) self rows for the mean recipe; the pool recipe also needs one row per sampled neighbour (n1 + n2)
     const int64_t o_DXE = e->fold_prep ? carve(4 * (int64_t)cfg->emb_dim * ((cfg->aggregator == GSAGE_AGG_MEAN ? 0 : e->n2) + e->n0 + e->n1)) : -1;
@@ -409,6 +420,9 @@ int gsage_engine_create(const gsage_engine_config* cfg, gsage_engine** out) {
     e->T1 = at(o_T1); e->NA = at(o_NA); e->T1x = at(o_T1x); e->XA = at(o_XA); e->AW = (float*)at(o_AW);
     e->H1 = at(o_H1); e->Z = (float*)at(o_Z); e->ZN = (float*)at(o_ZN); e->LG = (float*)at(o_LG);
     e->DXE = (float*)at(o_DXE); e->DZB = at(o_DZB);
+    e->ADM = (float*)at(o_ADM); e->ADW = (float*)at(o_ADW); e->ADA = (float*)at(o_ADA); e->ADT1 = (float*)at(o_ADT1);
+    e->ADXA = (float*)at(o_ADXA); e->ADT1X = (float*)at(o_ADT1X);
+    e->ASA = (float*)at(o_ASA); e->ASB = (float*)at(o_ASB); e->ANA = (float*)at(o_ANA); e->ANB = (float*)at(o_ANB);
     e->DP = (float*)at(o_DP); e->DHID = at(o_DHID); e->DN2 = (float*)at(o_DN2);
     e->DZN = (float*)at(o_DZN); e->DZ = (float*)at(o_DZ); e->DH0 = (float*)at(o_DH0); e->DM2 = (float*)at(o_DM2); e->DH = (float*)at(o_DH);
     *out = e;
@@ -528,6 +542,22 @@ int gsage_engine_set_weights(gsage_engine* e, const gsage_weights* w, void* stre
             GS_LAUNCHED();
             *it.dst = WRef{dst, GSAGE_BF16, ld};
             off += bytes;
+        }
+        if (att && e->T == GSAGE_BF16 && e->ADM) {
+            // attention backward: fc_neib^T (d_in x O) for d M = Gn . Wn, and the layer-2 fc_x^T for d h0 = Gx . Wx2
+            struct TItem { const float* src; int rows, cols; WRef* dst; } titems[2] = {
+                {w->layer[l].fc_neib, O, d_in, &e->w_nT[l]}, {l == 1 ? w->layer[1].fc_x : nullptr, O, d_in, &e->w_x2T}};
+            for (const TItem& it : titems) {
+                if (!it.src) continue;
+                const int64_t ld = pad_to(it.rows, 8);
+                const int64_t bytes = pad_to(2 * ld * it.cols, 256);
+                GS_CHECK_ARG(off + bytes <= e->wb_bytes, "engine_set_weights: bf16 weight arena too small (transposed copies)");
+                __nv_bfloat16* dst = (__nv_bfloat16*)(e->wb + off);
+                transpose_to_bf16_kernel<<<(unsigned)ceil_div((int64_t)it.cols * ld, 256), 256, 0, s>>>(it.src, it.rows, it.cols, dst, ld);
+                GS_LAUNCHED();
+                *it.dst = WRef{dst, GSAGE_BF16, ld};
+                off += bytes;
+            }
         }
         if (l == 1 && e->cfg.aggregator == GSAGE_AGG_MEAN && e->T == GSAGE_BF16) {
             // K-major transposed copies of the layer-2 weights: the head's data gradients d h0 = dz_x . Wx2, d m2 = dz_n . Wn2
@@ -1073,6 +1103,104 @@ int gsage_engine_backward_pool_embedding(gsage_engine* e, const float* dlogits, 
                                          const gsage_pool_embedding_grads* eg, void* stream) {
     GS_CHECK_ARG(eg, "engine_backward_pool_embedding: NULL argument");
     return backward_pool_impl(e, dlogits, g, pg, eg, stream);
+}
+
+// Full parameter-gradient pass for the attention aggregator (bf16 compute, identity prep; nn_modules.py:289-321).
+//   out = act([Wx x | Wn m]),  m_p = sum_j w_pj n_pj,  w_p = softmax_j <a(n_pj), a(x_p)>,  a(v) = W2 tanh(W1 v)
+// Per application the attention MLP's intermediates (tanh outputs, a(n), a(x), softmax weights) are RECOMPUTED with the
+// unfused forward kernels (the fused forward kernel keeps them on chip), then:
+//   dWx = Gx^T x, dWn = Gn^T m (tcgen05 split-K);  dM = Gn Wn (projection kernel, transposed weights);
+//   dw_pj = <dM_p, n_pj> (one more pass over the neighbour rows);  softmax', da(n) = ds xa, da(x) = sum_j ds a(n_pj);
+//   through W2 and tanh:  dW2 += da^T t1,  dpre = (da W2)(1 - t1^2),  dW1 += dpre^T rows  -- for the neighbour and the self side.
+// Layer 2 also returns the gradient of its input rows (w dM + dpre W1 for neighbours, Gx Wx + dpre_x W1 for self rows).
+int gsage_engine_backward_attention(gsage_engine* e, const float* dlogits, const gsage_grads* g, const gsage_attention_grads* ag, void* stream) {
+    GS_CHECK_ARG(e && e->have_weights && e->B > 0, "engine_backward_attention: run gsage_engine_forward first");
+    const gsage_engine_config& c = e->cfg;
+    GS_CHECK_ARG(c.aggregator == GSAGE_AGG_ATTENTION && c.prep == GSAGE_PREP_IDENTITY && e->T == GSAGE_BF16 && e->ADM,
+                 "engine_backward_attention: implemented for the attention aggregator with the identity prep in bf16 compute mode");
+    GS_CHECK_ARG(e->keep_activations, "engine_backward_attention: call gsage_engine_keep_activations(e, 1) before the forward");
+    GS_CHECK_ARG(dlogits && g && ag && g->fc_w && g->fc_b && g->fc_x[0] && g->fc_x[1] && g->fc_neib[0] && g->fc_neib[1] &&
+                 ag->att_w1[0] && ag->att_w1[1] && ag->att_w2[0] && ag->att_w2[1], "engine_backward_attention: NULL argument");
+    const int O1 = c.out_dim[0], O2 = c.out_dim[1], C = c.n_classes, S1 = c.fanout[0], S2 = c.fanout[1], H = e->hid, d1 = c.feats_dim;
+    GS_CHECK_ARG(O1 == 128 && O2 == 128 && H <= 32 && d1 % 16 == 0,
+                 "engine_backward_attention: needs output_dim 128, attention width <= 32 and a feature width that is a multiple of 16");
+    cudaStream_t s = as_stream(stream);
+    const int64_t n0 = e->B, n1 = n0 * S1, n2 = n1 * S2;
+    const int64_t es = (int64_t)dtype_size(e->T);
+    const int64_t* ids0 = e->ids; const int64_t* ids1 = ids0 + n0; const int64_t* ids2 = ids1 + n1;
+    (void)n2;
+
+    // one aggregator application, backwards.  G: (n, 2*O) bf16 pre-activation gradient.  `accumulate`: the layer's weights
+    // are shared with an earlier application.  in_self / in_nb (layer 2): where the two halves of the input-row gradient go.
+    auto app_bwd = [&](int layer, const RowSrc& x, const RowSrc& nb, int64_t n, int S, const void* Mrows, const __nv_bfloat16* G, bool accumulate,
+                       float* in_self_a, float* in_self_b, float* in_nb_a, float* in_nb_b) -> int {
+        const gsage_layer_weights& L = e->w.layer[layer];
+        const int O = c.out_dim[layer], d = x.d;
+        const int64_t ldg = 2 * (int64_t)O;
+        // recompute a(n), a(x), softmax weights (the unfused forward chain of apply_aggregator)
+        GS_TRY(linear_call(nb, e->w_att1[layer], H, e->b_att[layer], n * S, GSAGE_ACT_TANH, e->T1, GSAGE_F32, H, 0, 0, s));
+        RowSrc t1{e->T1, GSAGE_F32, H, n * S, nullptr, H};
+        GS_TRY(linear_call(t1, f32w(L.att_w2, H), H, nullptr, n * S, GSAGE_ACT_NONE, e->NA, GSAGE_F32, H, 0, 1, s));
+        GS_TRY(linear_call(x, e->w_att1[layer], H, e->b_att[layer], n, GSAGE_ACT_TANH, e->T1x, GSAGE_F32, H, 0, 0, s));
+        RowSrc t1x{e->T1x, GSAGE_F32, H, n, nullptr, H};
+        GS_TRY(linear_call(t1x, f32w(L.att_w2, H), H, nullptr, n, GSAGE_ACT_NONE, e->XA, GSAGE_F32, H, 0, 1, s));
+        GS_TRY(gsage_attention_weights(e->NA, e->XA, GSAGE_F32, H, H, n, S, e->AW, s));
+        // projection weights
+        WgradJob jobs[2] = {
+            {G, GSAGE_BF16, ldg, O, x.base, GSAGE_BF16, x.ld, x.ids, d, n, g->fc_x[layer], (int64_t)d, x.ids ? x.table_rows : 0},
+            {G + O, GSAGE_BF16, ldg, O, Mrows, GSAGE_BF16, e->ld_m, nullptr, d, n, g->fc_neib[layer], (int64_t)d, 0}};
+        GS_CHECK_ARG(wgrad_umma_eligible(jobs[0]) && wgrad_umma_eligible(jobs[1]), "engine_backward_attention: operands do not qualify for the "
+                     "tensor-core weight gradient");
+        GS_TRY(wgrad_umma_launch(jobs, 2, s, accumulate));
+        {   // dM = Gn . Wn  (n x O -> d)
+            LinearParams P;
+            P.n_segs = 1; P.n = n; P.act = GSAGE_ACT_NONE; P.out = e->ADM; P.out_dtype = GSAGE_F32; P.ld_out = e->ld_m;
+            P.seg[0] = LinearSeg{G + O, GSAGE_BF16, ldg, nullptr, e->w_nT[layer].p, GSAGE_BF16, e->w_nT[layer].ld, O, d, nullptr, 0};
+            GS_TRY(linear_dispatch(P, 0, s));
+        }
+        GS_TRY(attention_dw_launch(nb.base, nb.ld, nb.ids ? nb.table_rows : n * S, d, nb.ids, n, S, e->ADM, e->ld_m, e->AW, e->ADW,
+                                   in_nb_a, d, s));
+        GS_TRY(attention_softmax_bwd_launch(e->AW, e->ADW, (const float*)e->NA, (const float*)e->XA, H, n, S, e->ADA, e->ADXA, s));
+        // neighbour side of the attention MLP
+        GS_TRY(wgrad_launch(e->ADA, H, H, e->T1, GSAGE_F32, H, nullptr, H, n * S, ag->att_w2[layer], H, s, accumulate));       // dW2 += dA^T t1
+        GS_TRY(linear_trans_call(e->ADA, H, H, L.att_w2, H, H, n * S, e->ADT1, H, s));                                        // dA . W2
+        GS_TRY(tanh_bwd_launch(e->ADT1, (const float*)e->T1, n * S * H, s));
+        GS_TRY(wgrad_launch(e->ADT1, H, H, nb.base, nb.dtype, nb.ld, nb.ids, d, n * S, ag->att_w1[layer], d, s, accumulate)); // dW1 += dpre^T n
+        // self side
+        GS_TRY(wgrad_launch(e->ADXA, H, H, e->T1x, GSAGE_F32, H, nullptr, H, n, ag->att_w2[layer], H, s, true));
+        GS_TRY(linear_trans_call(e->ADXA, H, H, L.att_w2, H, H, n, e->ADT1X, H, s));
+        GS_TRY(tanh_bwd_launch(e->ADT1X, (const float*)e->T1x, n * H, s));
+        GS_TRY(wgrad_launch(e->ADT1X, H, H, x.base, x.dtype, x.ld, x.ids, d, n, ag->att_w1[layer], d, s, true));
+        if (in_self_a) {
+            // gradient of the input rows (layer 2): self = Gx . Wx + dpre_x . W1;  neighbours = w dM (written by attention_dw) + dpre . W1
+            LinearParams P;
+            P.n_segs = 1; P.n = n; P.act = GSAGE_ACT_NONE; P.out = in_self_a; P.out_dtype = GSAGE_F32; P.ld_out = d;
+            P.seg[0] = LinearSeg{G, GSAGE_BF16, ldg, nullptr, e->w_x2T.p, GSAGE_BF16, e->w_x2T.ld, O, d, nullptr, 0};
+            GS_TRY(linear_dispatch(P, 0, s));
+            GS_TRY(linear_trans_call(e->ADT1X, H, H, L.att_w1, d, d, n, in_self_b, d, s));
+            GS_TRY(linear_trans_call(e->ADT1, H, H, L.att_w1, d, d, n * S, in_nb_b, d, s));
+        }
+        return GSAGE_OK;
+    };
+
+    // ---- classifier + F.normalize --------------------------------------------------------------------------------------
+    GS_TRY(wgrad_launch(dlogits, C, C, e->ZN, GSAGE_F32, 2 * O2, nullptr, 2 * O2, n0, g->fc_w, 2 * O2, s));
+    GS_TRY(colsum_launch(dlogits, n0, C, g->fc_b, s));
+    GS_TRY(linear_trans_call(dlogits, C, C, e->w.fc_w, 2 * O2, 2 * O2, n0, e->DZN, 2 * O2, s));
+    GS_TRY(l2_normalize_bwd_launch(e->Z, e->DZN, n0, 2 * O2, c.act[1], e->DZ, s, e->DZB));
+    // ---- layer 2 on (h0, h1) -----------------------------------------------------------------------------------------------
+    RowSrc h{e->H1, e->T, e->ld_h1, n0 + n1, nullptr, 2 * O1};
+    const void* M2 = (const char*)e->M + (n0 + n1) * e->ld_m * es;
+    GS_TRY(app_bwd(1, h, h.shifted(n0), n0, S1, M2, (const __nv_bfloat16*)e->DZB, false, e->ASA, e->ASB, e->ANA, e->ANB));
+    GS_TRY(sum_act_grad_launch(e->ASA, e->ASB, e->ANA, e->ANB, e->H1, e->T, e->ld_h1, n0, n1, 2 * O1, c.act[0], e->DH, GSAGE_BF16, s));
+    // ---- layer 1 on (x0, x1) and (x1, x2), shared weights -----------------------------------------------------------------------
+    const __nv_bfloat16* dh = (const __nv_bfloat16*)e->DH;
+    RowSrc lvl{c.feats_dev, c.feats_dtype, c.feats_ld, c.feats_rows, ids0, d1};
+    GS_TRY(app_bwd(0, lvl, lvl.shifted(n0), n0, S1, e->M, dh, false, nullptr, nullptr, nullptr, nullptr));
+    GS_TRY(app_bwd(0, lvl.shifted(n0), lvl.shifted(n0 + n1), n1, S2, (const char*)e->M + n0 * e->ld_m * es, dh + n0 * 2 * (int64_t)O1, true,
+                   nullptr, nullptr, nullptr, nullptr));
+    (void)ids1; (void)ids2;
+    return mark_slot_done(e, s);
 }
 
 int gsage_engine_peek(gsage_engine* e, int what, const void** ptr, int64_t* rows, int64_t* cols, int64_t* ld, int* dtype) {

@@ -264,6 +264,18 @@ class GSSupervised(nn.Module):
         bucket = self._bucket()
         g = _lib.Grads()
         aggs = list(self.agg_layers.children())
+        if self._agg_name == 'attention':
+            ag = _lib.AttentionGrads()
+            for k in range(2):
+                g.fc_x[k] = bucket.grad_of(aggs[k].fc_x.weight).data_ptr()
+                g.fc_neib[k] = bucket.grad_of(aggs[k].fc_neib.weight).data_ptr()
+                ag.att_w1[k] = bucket.grad_of(aggs[k].att[0].weight).data_ptr()
+                ag.att_w2[k] = bucket.grad_of(aggs[k].att[2].weight).data_ptr()
+            g.fc_w, g.fc_b = bucket.grad_of(self.fc.weight).data_ptr(), bucket.grad_of(self.fc.bias).data_ptr()
+            dlogits = dlogits.contiguous().float()
+            check(lib().gsage_engine_backward_attention(self._last['h'], ops.ptr(dlogits), C.byref(g), C.byref(ag), ops.stream()))
+            bucket.all_reduce(grad_scale)
+            return bucket
         if self._agg_name in ('max_pool', 'mean_pool'):
             # one call computes every gradient (gsage_engine_backward_pool); no head / layer-1 split to overlap with
             pg = _lib.PoolGrads()

@@ -138,6 +138,42 @@ def test_pool_aggregator_gradients_match_autograd(g, agg):
         assert cos >= 0.995 and abs(ratio - 1.0) <= 2e-2, '%s: cosine %.5f, norm ratio %.4f' % (name, cos, ratio)
 
 
+def test_attention_aggregator_gradients_match_autograd(g):
+    """gsage_engine_backward_attention (bf16 compute, identity prep, output_dim 128): every parameter gradient -- fc_x, fc_neib,
+    att.0 and att.2 of both layers, fc -- against torch autograd through the CPU oracle on the same sampled ids, the
+    bf16-rounded table and bf16-rounded projection matrices.  Bar: cosine >= 0.995, norm within 3 % (bf16 activations;
+    the forward's scores use tanh.approx / __expf, the backward recomputes them with tanhf / expf)."""
+    from pytorch_graphsage_b200 import synth
+    prob = synth.make_problem('tiny', seed=1)
+    graph = g.GraphCSR.from_synth(prob['adj'])
+    torch.manual_seed(11)
+    model = g.GSSupervised(
+        input_dim=prob['feats_dim'], n_nodes=prob['n_nodes'], n_classes=prob['n_classes'],
+        layer_specs=[dict(n_train_samples=25, n_val_samples=25, output_dim=128, activation=F.relu),
+                     dict(n_train_samples=10, n_val_samples=10, output_dim=128, activation=lambda x: x)],
+        aggregator_class=g.aggregator_lookup['attention'], prep_class=g.prep_lookup['identity'],
+        sampler_class=g.sampler_lookup['sparse_uniform_neighbor_sampler'], adj=graph, train_adj=graph,
+        compute_dtype=torch.bfloat16).cuda()
+    ids0 = synth.seed_batch(prob, 48, seed=3)
+    targets = torch.from_numpy(np.random.RandomState(0).randint(0, prob['n_classes'], ids0.shape[0]))
+    g.set_seeds(31)
+    feats = torch.from_numpy(prob['feats'])
+    preds, loss = model.train_step(torch.from_numpy(ids0), feats, targets.cuda(), F.cross_entropy, optimizer=None, clip=None)
+    hop_ids = [torch.from_numpy(ids0), model.peek('ids1').cpu(), model.peek('ids2').cpu()]
+    ps = {k: (v.detach().cpu().to(torch.bfloat16).float() if v.dim() == 2 and not k.startswith('fc.') and '.att.2.' not in k
+              else v.detach().cpu().clone()).requires_grad_(True) for k, v in model.state_dict().items()}
+    logits = layers.forward_stack(hop_ids, feats.to(torch.bfloat16).float(), ps, aggregator='attention')
+    want_loss = F.cross_entropy(logits, targets)
+    want_loss.backward()
+    assert abs(loss.item() - want_loss.item()) < 5e-2
+    for name, p in model.named_parameters():
+        want = ps[name].grad.numpy().astype(np.float64)
+        got = p.grad.cpu().numpy().astype(np.float64)
+        cos = (got * want).sum() / (np.linalg.norm(got) * np.linalg.norm(want) + 1e-300)
+        ratio = np.linalg.norm(got) / (np.linalg.norm(want) + 1e-300)
+        assert cos >= 0.995 and abs(ratio - 1.0) <= 3e-2, '%s: cosine %.5f, norm ratio %.4f' % (name, cos, ratio)
+
+
 def test_pool_with_node_embedding_gradients_match_autograd(g):
     """BASELINE config C3's model (max pool + NodeEmbeddingPrep without features, bf16 compute): every parameter gradient incl.
     prep.fc and the dense embedding-table gradient, against autograd through the oracle at the bf16-rounded weights / table.
@@ -231,8 +267,8 @@ def test_train_step_with_the_dense_sampler(g):
 
 
 def test_backward_rejects_unsupported_plugins(g):
-    fix = util.load('model_attention_identity')
-    model = build_model(g, fix, 'attention', 'identity', True)
+    fix = util.load('model_mean_linear')
+    model = build_model(g, fix, 'mean', 'linear', True)
     g.set_seeds(1)
     preds = model(torch.from_numpy(fix['ids0']), torch.from_numpy(fix['feats']))
     with pytest.raises(ValueError):
