@@ -258,9 +258,16 @@ __global__ void __launch_bounds__(256) attention_softmax_bwd_kernel(const float*
 }
 
 // dpre = dt1 * (1 - t1^2)   (tanh', in place on dt1)
-__global__ void __launch_bounds__(256) tanh_bwd_kernel(float* __restrict__ dt1, const float* __restrict__ t1, int64_t n) {
+// `padded` (optional): bf16 copy with rows of 128 elements (columns H.. stay zero) = the operand of the tensor-core weight gradient
+__global__ void __launch_bounds__(256) tanh_bwd_kernel(float* __restrict__ dt1, const float* __restrict__ t1, int64_t n, int H,
+                                                       __nv_bfloat16* __restrict__ padded) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) { const float t = t1[i]; dt1[i] *= (1.0f - t * t); }
+    if (i < n) {
+        const float t = t1[i];
+        const float v = dt1[i] * (1.0f - t * t);
+        dt1[i] = v;
+        if (padded) padded[(i / H) * 128 + (i % H)] = __float2bfloat16_rn(v);
+    }
 }
 
 // dH[r, :] = (a[r, :] + b[r, :]) * act'(H[r, :]) for the two row ranges [0, n0) (self rows) and [n0, n0 + n1) (neighbour rows)
@@ -297,9 +304,9 @@ int attention_softmax_bwd_launch(const float* w, const float* dw, const float* n
     return GSAGE_OK;
 }
 
-int tanh_bwd_launch(float* dt1, const float* t1, int64_t n, cudaStream_t s) {
+int tanh_bwd_launch(float* dt1, const float* t1, int64_t n, cudaStream_t s, int H, void* padded_bf16) {
     if (n == 0) return GSAGE_OK;
-    tanh_bwd_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, s>>>(dt1, t1, n);
+    tanh_bwd_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, s>>>(dt1, t1, n, H > 0 ? H : 1, (__nv_bfloat16*)padded_bf16);
     GS_LAUNCHED();
     return GSAGE_OK;
 }

@@ -29,7 +29,7 @@ int attention_dw_launch(const void* table, int64_t ld, int64_t n_table_rows, int
                         const float* dM, int64_t ld_dm, const float* w, float* dw, float* dN, int64_t ld_dn, cudaStream_t s);
 int attention_softmax_bwd_launch(const float* w, const float* dw, const float* na, const float* xa, int H, int64_t n_parents, int S,
                                  float* dA, float* dXA, cudaStream_t s);
-int tanh_bwd_launch(float* dt1, const float* t1, int64_t n, cudaStream_t s);
+int tanh_bwd_launch(float* dt1, const float* t1, int64_t n, cudaStream_t s, int H = 0, void* padded_bf16 = nullptr);
 int sum_act_grad_launch(const float* a0, const float* b0, const float* a1, const float* b1, const void* H, int h_dtype, int64_t ldh,
                         int64_t n0, int64_t n1, int width, int act, void* dH, int dh_dtype, cudaStream_t s);
 // column sums of a bf16 (n, ld) matrix over its first d columns -> fp32

@@ -59,6 +59,11 @@ __global__ void __launch_bounds__(256) transpose_to_bf16_kernel(const float* __r
     dst[i] = __float2bfloat16_rn(r < rows ? src[(int64_t)r * cols + c] : 0.0f);
 }
 
+__global__ void __launch_bounds__(256) transpose_f32_kernel(const float* __restrict__ src, int rows, int cols, float* __restrict__ dst) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < rows * cols) dst[(i % cols) * rows + i / cols] = src[i];
+}
+
 __global__ void __launch_bounds__(256) axpy_kernel(float* y, const float* x, int n) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) y[i] += x[i];
@@ -137,6 +142,8 @@ struct gsage_engine {
     // the four partial input gradients of layer 2 (self / neighbour rows x direct / through-the-attention-MLP)
     float* ADM = nullptr; float* ADW = nullptr; float* ADA = nullptr; float* ADT1 = nullptr; float* ADXA = nullptr; float* ADT1X = nullptr;
     float* ASA = nullptr; float* ASB = nullptr; float* ANA = nullptr; float* ANB = nullptr;
+    float* AW2T[2] = {nullptr, nullptr};           // att.2.weight^T per layer (fp32, 32 x 32): d t1 = dA . W2 as a plain projection
+    void* ADPB = nullptr; float* AW1S = nullptr;   // d tanh input as bf16 rows of 128 (zero padded) + a (128, d) scratch for its weight gradient
     float* DP = nullptr;                // pool backward: d loss / d pooled rows, (n0 + n1) x H fp32
     void* DHID = nullptr;               // pool backward: d loss / d hidden rows, (n1 + n2) x H bf16
     float* DN2 = nullptr;               // pool backward: d loss / d (layer-2 neighbour rows), n1 x 2*O1 fp32
@@ -380,6 +387,8 @@ int gsage_engine_create(const gsage_engine_config* cfg, gsage_engine** out) {
     const int64_t o_ADXA = att_bwd ? carve(4 * (int64_t)e->hid * e->n1) : -1, o_ADT1X = att_bwd ? carve(4 * (int64_t)e->hid * e->n1) : -1;
     const int64_t o_ASA = att_bwd ? carve(4 * 2 * O1 * e->n0) : -1, o_ASB = att_bwd ? carve(4 * 2 * O1 * e->n0) : -1;
     const int64_t o_ANA = att_bwd ? carve(4 * 2 * O1 * e->n1) : -1, o_ANB = att_bwd ? carve(4 * 2 * O1 * e->n1) : -1;
+    const int64_t o_ADPB = att_bwd ? carve(2 * 128 * e->n2) : -1, o_AW1S = att_bwd ? carve(4 * 128 * e->ld_m) : -1;
+    const int64_t o_AW2T = att_bwd ? carve(4 * 2 * (int64_t)e->hid * e->hid) : -1;
     const int64_t o_DH = carve(4 * 2 * O1 * (e->n0 + e->n1));
     // (n0 + n1) self rows for the mean recipe; the pool recipe also needs one row per sampled neighbour (n1 + n2)
     const int64_t o_DXE = e->fold_prep ? carve(4 * (int64_t)cfg->emb_dim * ((cfg->aggregator == GSAGE_AGG_MEAN ? 0 : e->n2) + e->n0 + e->n1)) : -1;
@@ -422,6 +431,8 @@ int gsage_engine_create(const gsage_engine_config* cfg, gsage_engine** out) {
     e->DXE = (float*)at(o_DXE); e->DZB = at(o_DZB);
     e->ADM = (float*)at(o_ADM); e->ADW = (float*)at(o_ADW); e->ADA = (float*)at(o_ADA); e->ADT1 = (float*)at(o_ADT1);
     e->ADXA = (float*)at(o_ADXA); e->ADT1X = (float*)at(o_ADT1X);
+    e->ADPB = at(o_ADPB); e->AW1S = (float*)at(o_AW1S);
+    if (o_AW2T >= 0) { e->AW2T[0] = (float*)at(o_AW2T); e->AW2T[1] = e->AW2T[0] + (int64_t)e->hid * e->hid; }
     e->ASA = (float*)at(o_ASA); e->ASB = (float*)at(o_ASB); e->ANA = (float*)at(o_ANA); e->ANB = (float*)at(o_ANB);
     e->DP = (float*)at(o_DP); e->DHID = at(o_DHID); e->DN2 = (float*)at(o_DN2);
     e->DZN = (float*)at(o_DZN); e->DZ = (float*)at(o_DZ); e->DH0 = (float*)at(o_DH0); e->DM2 = (float*)at(o_DM2); e->DH = (float*)at(o_DH);
@@ -542,6 +553,10 @@ int gsage_engine_set_weights(gsage_engine* e, const gsage_weights* w, void* stre
             GS_LAUNCHED();
             *it.dst = WRef{dst, GSAGE_BF16, ld};
             off += bytes;
+        }
+        if (att && e->AW2T[l]) {
+            transpose_f32_kernel<<<(unsigned)ceil_div((int64_t)e->hid * e->hid, 256), 256, 0, s>>>(w->layer[l].att_w2, e->hid, e->hid, e->AW2T[l]);
+            GS_LAUNCHED();
         }
         if (att && e->T == GSAGE_BF16 && e->ADM) {
             // attention backward: fc_neib^T (d_in x O) for d M = Gn . Wn, and the layer-2 fc_x^T for d h0 = Gx . Wx2
@@ -1140,10 +1155,11 @@ int gsage_engine_backward_attention(gsage_engine* e, const float* dlogits, const
         // recompute a(n), a(x), softmax weights (the unfused forward chain of apply_aggregator)
         GS_TRY(linear_call(nb, e->w_att1[layer], H, e->b_att[layer], n * S, GSAGE_ACT_TANH, e->T1, GSAGE_F32, H, 0, 0, s));
         RowSrc t1{e->T1, GSAGE_F32, H, n * S, nullptr, H};
-        GS_TRY(linear_call(t1, f32w(L.att_w2, H), H, nullptr, n * S, GSAGE_ACT_NONE, e->NA, GSAGE_F32, H, 0, 1, s));
+        // (the 32 x 32 products run as TF32 on the tensor cores here: n*S rows each, the FFMA kernel spent 1.6 ms on them)
+        GS_TRY(linear_call(t1, f32w(L.att_w2, H), H, nullptr, n * S, GSAGE_ACT_NONE, e->NA, GSAGE_F32, H, 0, 0, s));
         GS_TRY(linear_call(x, e->w_att1[layer], H, e->b_att[layer], n, GSAGE_ACT_TANH, e->T1x, GSAGE_F32, H, 0, 0, s));
         RowSrc t1x{e->T1x, GSAGE_F32, H, n, nullptr, H};
-        GS_TRY(linear_call(t1x, f32w(L.att_w2, H), H, nullptr, n, GSAGE_ACT_NONE, e->XA, GSAGE_F32, H, 0, 1, s));
+        GS_TRY(linear_call(t1x, f32w(L.att_w2, H), H, nullptr, n, GSAGE_ACT_NONE, e->XA, GSAGE_F32, H, 0, 0, s));
         GS_TRY(gsage_attention_weights(e->NA, e->XA, GSAGE_F32, H, H, n, S, e->AW, s));
         // projection weights
         WgradJob jobs[2] = {
@@ -1163,9 +1179,22 @@ int gsage_engine_backward_attention(gsage_engine* e, const float* dlogits, const
         GS_TRY(attention_softmax_bwd_launch(e->AW, e->ADW, (const float*)e->NA, (const float*)e->XA, H, n, S, e->ADA, e->ADXA, s));
         // neighbour side of the attention MLP
         GS_TRY(wgrad_launch(e->ADA, H, H, e->T1, GSAGE_F32, H, nullptr, H, n * S, ag->att_w2[layer], H, s, accumulate));       // dW2 += dA^T t1
-        GS_TRY(linear_trans_call(e->ADA, H, H, L.att_w2, H, H, n * S, e->ADT1, H, s));                                        // dA . W2
-        GS_TRY(tanh_bwd_launch(e->ADT1, (const float*)e->T1, n * S * H, s));
-        GS_TRY(wgrad_launch(e->ADT1, H, H, nb.base, nb.dtype, nb.ld, nb.ids, d, n * S, ag->att_w1[layer], d, s, accumulate)); // dW1 += dpre^T n
+        {   // dA . W2 = dA . (W2^T)^T: a plain projection with the transposed copy (TF32 on the tensor cores)
+            RowSrc da{e->ADA, GSAGE_F32, H, n * S, nullptr, H};
+            GS_TRY(linear_call(da, f32w(e->AW2T[layer], H), H, nullptr, n * S, GSAGE_ACT_NONE, e->ADT1, GSAGE_F32, H, 0, 0, s));
+        }
+        GS_TRY(tanh_bwd_launch(e->ADT1, (const float*)e->T1, n * S * H, s, H, e->ADPB));
+        {   // dW1 += dpre^T n over all n*S neighbour rows: the 32 gradient columns ride in a zero-padded 128-column bf16 operand so
+            // that the split-K tcgen05 kernel takes it (the FFMA kernel needed 3 ms for this product at B = 8192)
+            WgradJob jw{e->ADPB, GSAGE_BF16, 128, 128, nb.base, GSAGE_BF16, nb.ld, nb.ids, d, n * S, e->AW1S, (int64_t)d, nb.ids ? nb.table_rows : 0};
+            if (wgrad_umma_eligible(jw)) {
+                GS_TRY(wgrad_umma_launch(&jw, 1, s));
+                if (accumulate) { axpy_kernel<<<(unsigned)ceil_div((int64_t)H * d, 256), 256, 0, s>>>(ag->att_w1[layer], e->AW1S, H * d); GS_LAUNCHED(); }
+                else GS_CUDA(cudaMemcpyAsync(ag->att_w1[layer], e->AW1S, sizeof(float) * (size_t)H * d, cudaMemcpyDeviceToDevice, s));
+            } else {
+                GS_TRY(wgrad_launch(e->ADT1, H, H, nb.base, nb.dtype, nb.ld, nb.ids, d, n * S, ag->att_w1[layer], d, s, accumulate));
+            }
+        }
         // self side
         GS_TRY(wgrad_launch(e->ADXA, H, H, e->T1x, GSAGE_F32, H, nullptr, H, n, ag->att_w2[layer], H, s, true));
         GS_TRY(linear_trans_call(e->ADXA, H, H, L.att_w2, H, H, n, e->ADT1X, H, s));
