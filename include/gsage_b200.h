@@ -261,9 +261,12 @@ int gsage_engine_sample_ahead(gsage_engine* e, gsage_graph* g, gsage_rng* rng, c
                               int64_t global_B, int64_t first, void* stream);
 int gsage_engine_sample_ahead_host(gsage_engine* e, gsage_graph* g, gsage_rng* rng, const int64_t* ids_host, int64_t B,
                                    void* stream);
-/* gsage_engine_forward_host that also queues the sample-ahead of the NEXT host batch (H2D of its ids + both hops) before
- * it blocks on its own logits: the end-to-end loop of a caller that knows its next batch (problem.py:141-153 does).
- * `next_ids_host` NULL = plain gsage_engine_forward_host. */
+/* gsage_engine_forward_host for a caller that knows its next batch (problem.py:141-153 does): before the call blocks on its
+ * own logits it queues the NEXT batch's H2D copy of the ids, its sampling (sampler stream) and its whole forward (`stream`),
+ * and the logits of THIS batch travel on a copy stream -- the GPU never idles across the host round trip.  The next call
+ * must then name that batch (same pointer and size); it finds its forward already queued and only collects the result.
+ * Draw order and results are those of the unpipelined calls.  `next_ids_host` NULL = plain gsage_engine_forward_host.
+ * While a forward is queued the engine's other entry points refuse to run, and gsage_engine_peek shows the queued batch. */
 int gsage_engine_forward_host_next(gsage_engine* e, gsage_graph* g, gsage_rng* rng, const int64_t* ids_host, int64_t B,
                                    const int64_t* next_ids_host, int64_t next_B, float* logits_host, void* stream);
 /* 1 while a sampled-ahead batch waits for its forward */

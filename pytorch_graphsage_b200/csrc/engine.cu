@@ -130,6 +130,11 @@ struct gsage_engine {
     void* T1 = nullptr; void* NA = nullptr; void* T1x = nullptr; void* XA = nullptr; float* AW = nullptr;   // attention
     void* H1 = nullptr;                 // layer-1 output (n0 + n1, 2*O1)
     float* Z = nullptr; float* ZN = nullptr; float* LG = nullptr;
+    // host-buffer entry, pipelined (gsage_engine_forward_host_next with a next batch): two logits buffers, a copy stream for
+    // the D2H of batch i while the forward of batch i+1 (queued before the call blocks) already runs
+    float* LG2[2] = {nullptr, nullptr}; int lg_cur = 0;
+    cudaStream_t cs = nullptr; cudaEvent_t ev_fwd = nullptr, ev_copy = nullptr; int* flags_host = nullptr;
+    struct Pre { bool valid = false; const void* src = nullptr; int64_t B = 0; int buf = 0; gsage_graph* g = nullptr; gsage_rng* rng = nullptr; } pre;
     int64_t ld_h1 = 0;
     // weights as the kernels read them (fp32 originals, or bf16 copies when compute dtype is bf16)
     char* wb = nullptr; int64_t wb_bytes = 0;
@@ -377,6 +382,7 @@ int gsage_engine_create(const gsage_engine_config* cfg, gsage_engine** out) {
     const int64_t o_Z = carve(4 * 2 * O2 * e->n0);
     const int64_t o_ZN = carve(4 * 2 * O2 * e->n0);
     const int64_t o_LG = carve(4 * (int64_t)cfg->n_classes * e->n0);
+    const int64_t o_LGb = carve(4 * (int64_t)cfg->n_classes * e->n0);
     const int64_t o_DZN = carve(4 * 2 * O2 * e->n0), o_DZ = carve(4 * 2 * O2 * e->n0);
     const int64_t o_DH0 = carve(4 * 2 * O1 * e->n0), o_DM2 = carve(4 * 2 * O1 * e->n0);
     const int64_t o_DZB = carve(2 * 2 * O2 * e->n0);
@@ -428,6 +434,7 @@ int gsage_engine_create(const gsage_engine_config* cfg, gsage_engine** out) {
     e->X = at(o_X); e->M = at(o_M); e->HN = at(o_HN); e->Pp = at(o_P);
     e->T1 = at(o_T1); e->NA = at(o_NA); e->T1x = at(o_T1x); e->XA = at(o_XA); e->AW = (float*)at(o_AW);
     e->H1 = at(o_H1); e->Z = (float*)at(o_Z); e->ZN = (float*)at(o_ZN); e->LG = (float*)at(o_LG);
+    e->LG2[0] = e->LG; e->LG2[1] = (float*)at(o_LGb);
     e->DXE = (float*)at(o_DXE); e->DZB = at(o_DZB);
     e->ADM = (float*)at(o_ADM); e->ADW = (float*)at(o_ADW); e->ADA = (float*)at(o_ADA); e->ADT1 = (float*)at(o_ADT1);
     e->ADXA = (float*)at(o_ADXA); e->ADT1X = (float*)at(o_ADT1X);
@@ -444,6 +451,10 @@ void gsage_engine_destroy(gsage_engine* e) {
     if (!e) return;
     for (cudaEvent_t ev : e->prof.pool) cudaEventDestroy(ev);
     if (e->ss) { cudaStreamSynchronize(e->ss); cudaStreamDestroy(e->ss); }
+    if (e->cs) { cudaStreamSynchronize(e->cs); cudaStreamDestroy(e->cs); }
+    if (e->ev_fwd) cudaEventDestroy(e->ev_fwd);
+    if (e->ev_copy) cudaEventDestroy(e->ev_copy);
+    if (e->flags_host) cudaFreeHost(e->flags_host);
     for (int i = 0; i < 2; ++i) if (e->ev_done[i]) cudaEventDestroy(e->ev_done[i]);
     if (e->ev_mid) cudaEventDestroy(e->ev_mid);
     if (e->ev_ahead) cudaEventDestroy(e->ev_ahead);
@@ -666,6 +677,7 @@ static int sample_ahead_impl(gsage_engine* e, gsage_graph* g, gsage_rng* rng, co
                              int64_t global_B, int64_t first, cudaStream_t main) {
     GS_TRY(check_batch_args(e, g, rng, ids_src, B, global_B, first));
     GS_CHECK_ARG(!e->ahead.valid, "engine_sample_ahead: a sampled-ahead batch is already pending (run its forward first)");
+    GS_CHECK_ARG(!e->pre.valid, "engine_sample_ahead: a host forward is already queued (gsage_engine_forward_host_next): collect it first");
     if (!e->ss) {
         int lo = 0, hi = 0;
         GS_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));          // hi = numerically lowest = greatest priority
@@ -702,11 +714,13 @@ static int forward_layers(gsage_engine* e, int64_t B, float* logits_dev, cudaStr
 
 int gsage_engine_forward(gsage_engine* e, gsage_graph* g, gsage_rng* rng, const int64_t* ids_dev, int64_t B,
                          float* logits_dev, void* stream) {
+    GS_CHECK_ARG(e && !e->pre.valid, "engine_forward: a host forward is already queued (gsage_engine_forward_host_next): collect it first");
     return forward_impl(e, g, rng, ids_dev, false, B, B, 0, logits_dev, as_stream(stream));
 }
 
 int gsage_engine_forward_sharded(gsage_engine* e, gsage_graph* g, gsage_rng* rng, const int64_t* ids_dev, int64_t B,
                                  int64_t global_B, int64_t first, float* logits_dev, void* stream) {
+    GS_CHECK_ARG(e && !e->pre.valid, "engine_forward_sharded: a host forward is already queued (gsage_engine_forward_host_next): collect it first");
     return forward_impl(e, g, rng, ids_dev, false, B, global_B, first, logits_dev, as_stream(stream));
 }
 
@@ -809,25 +823,57 @@ static int forward_layers(gsage_engine* e, int64_t B, float* logits_dev, cudaStr
 
 int gsage_engine_forward_host_next(gsage_engine* e, gsage_graph* g, gsage_rng* rng, const int64_t* ids_host, int64_t B,
                                    const int64_t* next_ids_host, int64_t next_B, float* logits_host, void* stream) {
-    GS_CHECK_ARG(e && ids_host && logits_host, "engine_forward_host: NULL argument");
+    GS_CHECK_ARG(e && g && rng && ids_host && logits_host, "engine_forward_host: NULL argument");
     GS_CHECK_ARG(B > 0 && B <= e->maxB, "engine_forward_host: batch outside (0, max_batch]");
+    GS_CHECK_ARG(!next_ids_host || (next_B > 0 && next_B <= e->maxB), "engine_forward_host: next batch outside (0, max_batch]");
     cudaStream_t s = as_stream(stream);
-    // the seed ids go straight into the hop-0 slot of the id buffer (H2D inside sample_hops, or already done by
-    // gsage_engine_sample_ahead_host); the logits come back from a dedicated view
-    float* logits_dev = e->LG;
-    int st = forward_impl(e, g, rng, ids_host, true, B, B, 0, logits_dev, s);
-    // the next batch's H2D + sampling are queued BEFORE this call blocks on its own result: they overlap the forward
-    if (st == GSAGE_OK && next_ids_host) st = sample_ahead_impl(e, g, rng, next_ids_host, true, next_B, next_B, 0, s);
-    if (st == GSAGE_OK) {
-        if (cudaMemcpyAsync(logits_host, logits_dev, 4 * B * e->cfg.n_classes, cudaMemcpyDeviceToHost, s) != cudaSuccess ||
-            cudaStreamSynchronize(s) != cudaSuccess) {
-            set_error("engine_forward_host: D2H copy failed: %s", cudaGetErrorString(cudaGetLastError()));
-            st = GSAGE_ERR_CUDA;
-        }
+    if (!e->cs) {
+        GS_CUDA(cudaStreamCreateWithFlags(&e->cs, cudaStreamNonBlocking));
+        GS_CUDA(cudaEventCreateWithFlags(&e->ev_fwd, cudaEventDisableTiming));
+        GS_CUDA(cudaEventCreateWithFlags(&e->ev_copy, cudaEventDisableTiming));
+        GS_CUDA(cudaHostAlloc((void**)&e->flags_host, 2 * sizeof(int), cudaHostAllocDefault));
     }
-    if (st == GSAGE_OK) st = gsage_rng_check(rng, stream);
-    if (st == GSAGE_OK) st = gsage_graph_check(g, stream);
-    return st;
+    // 1. this batch's forward: already queued by the previous call when that call was given this batch as its `next`
+    int buf;
+    if (e->pre.valid) {
+        GS_CHECK_ARG(e->pre.src == ids_host && e->pre.B == B && e->pre.g == g && e->pre.rng == rng,
+                     "engine_forward_host: the forward of a different batch is already queued (the previous call named it as its next batch)");
+        buf = e->pre.buf;
+        e->pre.valid = false;
+    } else {
+        buf = (e->lg_cur ^= 1);
+        // the seed ids go straight into the hop-0 slot of the id buffer (H2D inside sample_hops, or already done by a sample-ahead)
+        GS_TRY(forward_impl(e, g, rng, ids_host, true, B, B, 0, e->LG2[buf], s));
+        GS_CUDA(cudaEventRecord(e->ev_fwd, s));
+    }
+    // 2. its logits (and the two sticky error flags) travel on the copy stream, behind that forward only
+    GS_CUDA(cudaStreamWaitEvent(e->cs, e->ev_fwd, 0));
+    GS_CUDA(cudaMemcpyAsync(logits_host, e->LG2[buf], 4 * B * e->cfg.n_classes, cudaMemcpyDeviceToHost, e->cs));
+    GS_CUDA(cudaMemcpyAsync(e->flags_host, rng->err_flag, sizeof(int), cudaMemcpyDeviceToHost, e->cs));
+    GS_CUDA(cudaMemcpyAsync(e->flags_host + 1, g->err_flag, sizeof(int), cudaMemcpyDeviceToHost, e->cs));
+    GS_CUDA(cudaEventRecord(e->ev_copy, e->cs));
+    // 3. the next batch: H2D of its ids + sampling (sampler stream) AND its whole forward (caller's stream) are queued BEFORE
+    //    this call blocks on its own result -- the GPU never waits for the host round trip of the logits
+    if (next_ids_host) {
+        GS_TRY(sample_ahead_impl(e, g, rng, next_ids_host, true, next_B, next_B, 0, s));
+        const int nbuf = buf ^ 1;
+        GS_TRY(forward_impl(e, g, rng, next_ids_host, true, next_B, next_B, 0, e->LG2[nbuf], s));
+        GS_CUDA(cudaEventRecord(e->ev_fwd, s));
+        e->lg_cur = nbuf;
+        e->pre.valid = true; e->pre.src = next_ids_host; e->pre.B = next_B; e->pre.buf = nbuf; e->pre.g = g; e->pre.rng = rng;
+    }
+    // 4. block on THIS batch's copy only
+    if (cudaEventSynchronize(e->ev_copy) != cudaSuccess) {
+        set_error("engine_forward_host: D2H copy failed: %s", cudaGetErrorString(cudaGetLastError()));
+        return GSAGE_ERR_CUDA;
+    }
+    if (e->flags_host[0]) {
+        set_error("rng: the look-ahead window held fewer accepted draws than requested (12-sigma event) -- re-seed; results since the last "
+                  "check are invalid");
+        return GSAGE_ERR_RNG;
+    }
+    if (e->flags_host[1]) return gsage_graph_check(g, stream);     // reports (and clears) the out-of-range id like the device entry
+    return GSAGE_OK;
 }
 
 int gsage_engine_forward_host(gsage_engine* e, gsage_graph* g, gsage_rng* rng, const int64_t* ids_host, int64_t B,

@@ -205,3 +205,41 @@ def test_engine_with_the_dense_sampler_matches_reference(g, dtype, tol):
     assert np.array_equal(model.peek('ids1').cpu().numpy(), fix['ids1'].reshape(-1))
     assert np.array_equal(model.peek('ids2').cpu().numpy(), fix['ids2'].reshape(-1))
     np.testing.assert_allclose(logits.cpu().numpy(), fix['logits'], **tol)
+
+
+def test_pipelined_host_entry_equals_plain_host_entry(g):
+    """gsage_engine_forward_host_next with a next batch: that batch's H2D, sampling AND forward are queued before the call
+    blocks on its own logits (which travel on a copy stream).  Same draws in the same order: logits bit-identical to the
+    unpipelined calls, and the RNG stream ends at the same position."""
+    fix = util.load('model_mean_identity')
+    feats = torch.from_numpy(fix['feats'])
+    batches = [torch.from_numpy(b).pin_memory() for b in (fix['ids0'], fix['ids0'][::-1].copy(), fix['ids0'][:7].copy(), fix['ids0'])]
+    n_classes = fix['logits'].shape[1]
+    plain = build_model(g, fix, 'mean', 'identity', True)
+    g.set_seeds(int(fix['seed']))
+    want = []
+    for b in batches:
+        out = torch.empty((b.shape[0], n_classes), dtype=torch.float32).pin_memory()
+        plain.forward_host(b, feats, out)
+        want.append(out.numpy().copy())
+    state_plain = g.default_rng().get_state()
+    np.testing.assert_allclose(want[0], fix['logits'], rtol=1e-4, atol=1e-5)
+
+    model = build_model(g, fix, 'mean', 'identity', True)
+    g.set_seeds(int(fix['seed']))
+    for i, b in enumerate(batches):
+        out = torch.empty((b.shape[0], n_classes), dtype=torch.float32).pin_memory()
+        nxt = batches[i + 1] if i + 1 < len(batches) else None
+        model.forward_host(b, feats, out, next_ids_host=nxt)
+        np.testing.assert_array_equal(out.numpy(), want[i])
+    st = g.default_rng().get_state()
+    assert np.array_equal(st[1], state_plain[1]) and st[2] == state_plain[2]
+    # a queued forward must be collected before anything else runs on the engine
+    out = torch.empty((batches[0].shape[0], n_classes), dtype=torch.float32).pin_memory()
+    model.forward_host(batches[0], feats, out, next_ids_host=batches[1])
+    with pytest.raises(ValueError):
+        model(torch.from_numpy(fix['ids0']).cuda(), feats)
+    with pytest.raises(ValueError):
+        model.forward_host(batches[2], feats, out)
+    out1 = torch.empty((batches[1].shape[0], n_classes), dtype=torch.float32).pin_memory()
+    model.forward_host(batches[1], feats, out1)
