@@ -147,6 +147,8 @@ struct gsage_engine {
     // the four partial input gradients of layer 2 (self / neighbour rows x direct / through-the-attention-MLP)
     float* ADM = nullptr; float* ADW = nullptr; float* ADA = nullptr; float* ADT1 = nullptr; float* ADXA = nullptr; float* ADT1X = nullptr;
     float* ASA = nullptr; float* ASB = nullptr; float* ANA = nullptr; float* ANB = nullptr;
+    float* FCP = nullptr; int fc_pad = 0;          // classifier weights + bias zero-padded to a multiple of 16 rows (fp32): the bf16 engine
+                                                   // runs fc as a TF32 projection on the tensor cores and stores only n_classes columns
     float* AW2T[2] = {nullptr, nullptr};           // att.2.weight^T per layer (fp32, 32 x 32): d t1 = dA . W2 as a plain projection
     void* ADPB = nullptr; float* AW1S = nullptr;   // d tanh input as bf16 rows of 128 (zero padded) + a (128, d) scratch for its weight gradient
     float* DP = nullptr;                // pool backward: d loss / d pooled rows, (n0 + n1) x H fp32
@@ -461,6 +463,7 @@ void gsage_engine_destroy(gsage_engine* e) {
     cudaFree(e->ws);
     cudaFree(e->wb);
     cudaFree(e->fold);
+    cudaFree(e->FCP);
     delete e;
 }
 
@@ -618,6 +621,15 @@ int gsage_engine_set_weights(gsage_engine* e, const gsage_weights* w, void* stre
                 off += bytes;
             }
         }
+    }
+    if (e->T == GSAGE_BF16) {
+        // classifier: (n_classes, 2*O2) + bias padded with zero rows to a multiple of 16 (one small copy per set_weights)
+        const int C = e->cfg.n_classes, Cp = (C + 15) / 16 * 16, K = 2 * e->cfg.out_dim[1];
+        if (!e->FCP) GS_CUDA(cudaMalloc((void**)&e->FCP, sizeof(float) * (size_t)Cp * (K + 1)));
+        GS_CUDA(cudaMemsetAsync(e->FCP, 0, sizeof(float) * (size_t)Cp * (K + 1), s));
+        GS_CUDA(cudaMemcpyAsync(e->FCP, e->w.fc_w, sizeof(float) * (size_t)C * K, cudaMemcpyDeviceToDevice, s));
+        GS_CUDA(cudaMemcpyAsync(e->FCP + (size_t)Cp * K, e->w.fc_b, sizeof(float) * C, cudaMemcpyDeviceToDevice, s));
+        e->fc_pad = Cp;
     }
     e->have_weights = true;
     return GSAGE_OK;
@@ -814,6 +826,21 @@ static int forward_layers(gsage_engine* e, int64_t B, float* logits_dev, cudaStr
     // ---- normalise + classifier (models.py:90-91) -----------------------------------------------------------------
     GS_TRY(gsage_l2_normalize(e->Z, GSAGE_F32, 2 * O2, n0, 2 * O2, e->ZN, 2 * O2, s));
     RowSrc zn{e->ZN, GSAGE_F32, 2 * O2, n0, nullptr, 2 * O2};
+    if (T == GSAGE_BF16 && e->fc_pad > 0 && (2 * O2) % 4 == 0 && getenv("GSAGE_FC_EXACT") == nullptr) {
+        // bf16 mode: the classifier as a TF32 projection on the tensor cores (fp32 operands, 10-bit mantissa products, fp32
+        // accumulate -- well inside the mode's bf16 tolerance); the FFMA kernel took 40 us of a 1.5 ms step
+        LinearParams P;
+        P.n_segs = 1; P.n = n0; P.act = GSAGE_ACT_NONE; P.out = logits_dev; P.out_dtype = GSAGE_F32; P.ld_out = c.n_classes;
+        P.seg[0] = LinearSeg{e->ZN, GSAGE_F32, 2 * (int64_t)O2, nullptr, e->FCP, GSAGE_F32, 2 * (int64_t)O2, 2 * O2, e->fc_pad,
+                             e->FCP + (size_t)e->fc_pad * 2 * O2, 0};
+        P.seg[0].O_store = c.n_classes;
+        if (linear_ws_umma_eligible(P)) {
+            GS_TRY(linear_ws_umma_launch(P, s));
+            e->prof.end(p_all, s);
+            GS_TRY(mark_slot_done(e, s));
+            return GSAGE_OK;
+        }
+    }
     GS_TRY(linear_call(zn, f32w(e->w.fc_w, 2 * O2), c.n_classes, e->w.fc_b, n0, GSAGE_ACT_NONE, logits_dev, GSAGE_F32, c.n_classes,
                        0, 1, s));
     e->prof.end(p_all, s);

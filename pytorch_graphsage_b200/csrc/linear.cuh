@@ -10,6 +10,8 @@ struct LinearSeg {
     const float* bias; int64_t col0;
     int S = 1;      // > 1: A row r = mean_j A[ids[r*S + j]] (fused gather+mean)
     int w_trans = 0;   // 1: W is stored (d x O): element (o, k) at w[k * ldw + o]  (backward: dX = dY . W; FFMA kernel only)
+    int O_store = 0;      // > 0: only the first O_store of the O computed columns are stored (W rows O_store.. are padding:
+                          // the classifier's 41 classes ride in a 48-row operand on the tensor-core kernel)
     int64_t a_rows = 0;   // rows of the table behind `a` when known (> 0): ids outside it then read as ZERO rows in the TMA
                           // gathers (like gather_reduce.cu) instead of touching memory past the table
 };

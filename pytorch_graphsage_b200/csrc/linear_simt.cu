@@ -150,7 +150,13 @@ int linear_dispatch(const LinearParams& P, int exact, cudaStream_t s) {
         return linear_pool_umma_launch(P, s);
     }
     bool tc = !exact;
-    for (int i = 0; i < P.n_segs; ++i) tc = tc && !P.seg[i].w_trans;
+    for (int i = 0; i < P.n_segs; ++i) {
+        tc = tc && !P.seg[i].w_trans;
+        if (P.seg[i].O_store > 0 && P.seg[i].O_store < P.seg[i].O) {       // padded operand: only the weight-stationary kernel trims the store
+            GS_CHECK_ARG(!exact && linear_ws_umma_eligible(P), "linear: a padded projection (O_store < O) needs the weight-stationary tensor-core kernel");
+            return linear_ws_umma_launch(P, s);
+        }
+    }
     for (int i = 0; i < P.n_segs && tc; ++i) {
         LinearParams one = P;
         one.n_segs = 1; one.seg[0] = P.seg[i];

@@ -35,7 +35,7 @@ static constexpr int kSmemLimit = 227 * 1024;
 
 struct WsSeg {
     const void* a; int64_t lda; const int64_t* ids;
-    int d; int O; const float* bias; int64_t col0;
+    int d; int O; int O_store; const float* bias; int64_t col0;
     int kchunks;          // ceil(d / uk)
     int acc_col;          // first TMEM column of this segment's accumulator inside a buffer
     int w_off;            // byte offset of this segment's resident W inside the W area (kres slots of O x 128 B)
@@ -144,7 +144,8 @@ __global__ void __launch_bounds__(kWsThreads, 1) linear_ws_umma_kernel(const WsP
                         if (row < P.n) {
                             void* o = (char*)P.out + (row * P.ld_out + sg.col0 + c0) * (P.out_bf16 ? 2 : 4);
                             const float* bias = sg.bias ? sg.bias + c0 : nullptr;
-                            const int valid = min(32, sg.O - c0);
+                            const int valid = min(32, sg.O_store - c0);
+                            if (valid <= 0) continue;
                             if (P.act == GSAGE_ACT_RELU) ws_store32<GSAGE_ACT_RELU>(r, bias, valid, o, P.out_bf16);
                             else if (P.act == GSAGE_ACT_TANH) ws_store32<GSAGE_ACT_TANH>(r, bias, valid, o, P.out_bf16);
                             else ws_store32<GSAGE_ACT_NONE>(r, bias, valid, o, P.out_bf16);
@@ -400,6 +401,7 @@ int linear_ws_umma_launch(const LinearParams& P, cudaStream_t s) {
         const LinearSeg& g = P.seg[i];
         U.seg[i].a = g.a; U.seg[i].lda = g.lda; U.seg[i].ids = g.ids;
         U.seg[i].d = g.d; U.seg[i].O = g.O; U.seg[i].bias = g.bias; U.seg[i].col0 = g.col0;
+        U.seg[i].O_store = (g.O_store > 0 && g.O_store < g.O) ? g.O_store : g.O;
         U.seg[i].kchunks = (g.d + U.uk - 1) / U.uk;
         U.seg[i].kres = plan.kres[i];
     }
