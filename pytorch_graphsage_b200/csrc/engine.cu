@@ -120,7 +120,7 @@ struct gsage_engine {
     cudaEvent_t ev_done[2] = {nullptr, nullptr}; bool done_valid[2] = {false, false};   // last reader of each id slot (forward / backward) finished
     // mean aggregator: the sample-ahead stream starts AFTER the dominant (HBM-bound) gather+mean launch of the forward in
     // flight, so its kernels share the SMs with the projection / layer-2 tail instead of slowing the bandwidth-bound kernel
-    cudaEvent_t ev_mid = nullptr; bool mid_valid = false; int ahead_after_gather = 1;
+    cudaEvent_t ev_mid = nullptr; bool mid_valid = false; int ahead_after_gather = 1; int ahead_split = 0;   // split: draws before the gate (measured: step -1 %, gather kernel +2 %: off)
     struct Ahead { bool valid = false; const void* src = nullptr; int64_t B = 0, global_B = 0, first = 0;
                    gsage_graph* g = nullptr; gsage_rng* rng = nullptr; } ahead;
     void* X = nullptr;                  // materialised prepped rows (non-identity preps)
@@ -342,6 +342,7 @@ int gsage_engine_create(const gsage_engine_config* cfg, gsage_engine** out) {
     if (const char* f = getenv("GSAGE_CHUNK")) e->chunk_parents = atoll(f);
     if (const char* f = getenv("GSAGE_L2HINT")) e->l2_hint = atoi(f);
     if (const char* f = getenv("GSAGE_AHEAD_AFTER_GATHER")) e->ahead_after_gather = atoi(f);
+    if (const char* f = getenv("GSAGE_AHEAD_SPLIT")) e->ahead_split = atoi(f);
     const int64_t es = (int64_t)dtype_size(e->T);
     const int64_t vec = 16 / es;
     switch (cfg->prep) {
@@ -636,24 +637,29 @@ int gsage_engine_set_weights(gsage_engine* e, const gsage_weights* w, void* stre
 }
 
 // ---- sample: hop 0 draws first, then hop 1 (models.py:78-79), into `ids` = [ids0 | ids1 | ids2] -----------------
+// `gate` / `n_gate`: events the stream must wait for AFTER the draws and BEFORE anything touches `ids` (sample-ahead: the
+// draws do not depend on the ids, so they may start before the id slot is free)
 static int sample_hops(gsage_engine* e, gsage_graph* g, gsage_rng* rng, int64_t* ids, uint32_t* sel, const int64_t* ids_src,
-                       bool src_host, int64_t B, int64_t global_B, int64_t first, cudaStream_t s) {
+                       bool src_host, int64_t B, int64_t global_B, int64_t first, cudaStream_t s, cudaEvent_t* gate = nullptr, int n_gate = 0) {
     const int S1 = e->cfg.fanout[0], S2 = e->cfg.fanout[1];
     const int64_t n0 = B, n1 = B * S1, n2 = n1 * S2;
     const int p_smp = e->prof.begin(GSAGE_PROF_SAMPLE, s);
     int64_t* ids0 = ids; int64_t* ids1 = ids0 + n0; int64_t* ids2 = ids1 + n1;
-    if (ids_src != ids0) GS_CUDA(cudaMemcpyAsync(ids0, ids_src, 8 * n0, src_host ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, s));
     if (global_B == B) {
         // both hops draw from the same range [0, maxdeg) and the hop sizes do not depend on what was sampled, so the
         // n1 hop-0 draws followed by the n2 hop-1 draws are ONE bounded draw of n1 + n2 values from the stream (same words,
         // same order, same final position as two np.random.choice calls): one count / scan / scatter pass instead of two
         GS_TRY(rng_randint_internal(rng, (uint32_t)g->n_cols, n1 + n2, sel, s));
+        for (int i = 0; i < n_gate; ++i) GS_CUDA(cudaStreamWaitEvent(s, gate[i], 0));
+        if (ids_src != ids0) GS_CUDA(cudaMemcpyAsync(ids0, ids_src, 8 * n0, src_host ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, s));
         GS_TRY(sample_sparse_launch(g, ids0, n0, S1, sel, ids1, s));
         GS_TRY(sample_sparse_launch(g, ids1, n1, S2, sel + n1, ids2, s));
     } else {
         // seed-sharded, still bit-exact with the single-process run: every rank consumes the draws of the WHOLE
         // global batch (hop-0 block, then hop-1 block -- the cheap part) and uses the slice that belongs to its seeds;
         // the gather / aggregate / project work is what is sharded
+        for (int i = 0; i < n_gate; ++i) GS_CUDA(cudaStreamWaitEvent(s, gate[i], 0));
+        if (ids_src != ids0) GS_CUDA(cudaMemcpyAsync(ids0, ids_src, 8 * n0, src_host ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, s));
         const int64_t g1 = global_B * S1, g2 = g1 * S2;
         uint32_t* gsel = nullptr;
         GS_CUDA(cudaMallocAsync((void**)&gsel, sizeof(uint32_t) * g2, s));
@@ -699,9 +705,18 @@ static int sample_ahead_impl(gsage_engine* e, gsage_graph* g, gsage_rng* rng, co
     // the spare slot was last read by the forward (and backward) BEFORE the one in flight: wait for that one only, so
     // the draws run underneath the forward that was queued just before this call
     (void)main;
-    if (e->done_valid[e->cur ^ 1]) GS_CUDA(cudaStreamWaitEvent(e->ss, e->ev_done[e->cur ^ 1], 0));
-    if (e->mid_valid) { GS_CUDA(cudaStreamWaitEvent(e->ss, e->ev_mid, 0)); e->mid_valid = false; }
-    GS_TRY(sample_hops(e, g, rng, e->ids_slot[e->cur ^ 1], e->sel_ahead, ids_src, src_host, B, global_B, first, e->ss));
+    // the draws (count / scan / scatter of the RNG stream: no dependence on the ids) start right away; everything that reads or
+    // writes the id slot waits for the slot's last reader and -- mean aggregator -- for the dominant gather launch of the forward
+    // in flight, so that the random-access sample kernels share the SMs with the projection tail, not with that kernel
+    cudaEvent_t gate[2]; int n_gate = 0;
+    if (e->done_valid[e->cur ^ 1]) gate[n_gate++] = e->ev_done[e->cur ^ 1];
+    if (e->mid_valid) { gate[n_gate++] = e->ev_mid; e->mid_valid = false; }
+    if (e->ahead_split) {
+        GS_TRY(sample_hops(e, g, rng, e->ids_slot[e->cur ^ 1], e->sel_ahead, ids_src, src_host, B, global_B, first, e->ss, gate, n_gate));
+    } else {
+        for (int i = 0; i < n_gate; ++i) GS_CUDA(cudaStreamWaitEvent(e->ss, gate[i], 0));
+        GS_TRY(sample_hops(e, g, rng, e->ids_slot[e->cur ^ 1], e->sel_ahead, ids_src, src_host, B, global_B, first, e->ss));
+    }
     GS_CUDA(cudaEventRecord(e->ev_ahead, e->ss));
     e->ahead.valid = true; e->ahead.src = ids_src; e->ahead.B = B; e->ahead.global_B = global_B; e->ahead.first = first;
     e->ahead.g = g; e->ahead.rng = rng;
