@@ -155,8 +155,10 @@ int gsage_l2_normalize(const void* x_dev, int dtype, int64_t ld, int64_t n, int 
  * (nn_modules.py:150,166,200,224,228,307-308,317; models.py:91).
  *   out[:, col0 : col0+O] = act( A[ids] (n x d) . W^T (O x d, row-major, ldw) + bias )
  * `ids` NULL -> A read in place.  A / W / out dtypes independent (fp32 or bf16); fp32 accumulate.
- * `exact` != 0 forces the fp32 FFMA kernel; 0 lets bf16 operands (or fp32 operands, as TF32) run on the tcgen05
- * tensor-core kernel when they qualify (16-byte aligned rows, O % 16 == 0).
+ * `exact` == 1 forces the fp32 FFMA kernel; 0 lets bf16 operands (or fp32 operands, as TF32) run on the tcgen05
+ * tensor-core kernel when they qualify (16-byte aligned rows, O % 16 == 0); 2 = fp32 accuracy on the tensor cores: fp32
+ * operands whose weights fit in shared memory twice run as 3 x TF32 (a = a_hi + a_lo, w = w_hi + w_lo, the three leading
+ * products accumulated in fp32; ~1e-6 relative), anything else falls back to the FFMA kernel.
  * ------------------------------------------------------------------------------------------------ */
 typedef struct gsage_linear_seg {
     const void* a_dev; int a_dtype; int64_t lda; const int64_t* ids_dev;    /* A source (+ optional gather) */
@@ -194,8 +196,9 @@ typedef struct gsage_engine_config {
     int out_dim[2];                 /* O per layer (aggregator output is 2*O)                             */
     int act[2];                     /* gsage_act per layer (train.py:110,116: relu, identity)             */
     int n_classes;
-    int compute_dtype;              /* GSAGE_F32: every kernel fp32-exact.  GSAGE_BF16: bf16 tables/activations,
-                                       fp32 accumulate, tensor-core projections                           */
+    int compute_dtype;              /* GSAGE_F32: every kernel fp32-exact (projections: 3 x TF32 on the tensor cores where the
+                                       weights fit in shared memory, else FFMA; env GSAGE_FP32_FFMA=1 forces FFMA).
+                                       GSAGE_BF16: bf16 tables/activations, fp32 accumulate, tensor-core projections */
     /* node features (`feats`, problem.py:118-121); NULL for feats=None (Pokec) */
     const void* feats_dev; int feats_dtype; int64_t feats_ld; int feats_dim; int64_t feats_rows;
     /* NodeEmbeddingPrep (nn_modules.py:126-155): table (n_nodes+1, 64), fc 64x64 + bias; n_nodes = adj.shape[0] */

@@ -38,7 +38,7 @@ struct RowSrc {
 };
 
 // a weight matrix as a kernel will read it: the caller's fp32 tensor, or the engine's padded bf16 copy
-struct WRef { const void* p; int dtype; int64_t ld; };
+struct WRef { const void* p; int dtype; int64_t ld; const float* hi = nullptr; const float* lo = nullptr; };   // hi/lo: tf32-exact split (fp32-exact mode)
 
 // fp32 (rows, cols) -> bf16 (rows, ld) with zero padding (the tcgen05 kernel wants 16-byte aligned bf16 rows)
 __global__ void __launch_bounds__(256) to_bf16_padded_kernel(const float* __restrict__ src, int rows, int cols,
@@ -139,6 +139,7 @@ struct gsage_engine {
     // weights as the kernels read them (fp32 originals, or bf16 copies when compute dtype is bf16)
     char* wb = nullptr; int64_t wb_bytes = 0;
     WRef w_x[2], w_n[2], w_mlp[2], w_att1[2];
+    float* wsplit = nullptr; int64_t wsplit_floats = 0;      // fp32-exact mode: (hi, lo) tf32 halves of fc_x / fc_neib for the 3 x TF32 projection
     WRef w_nT[2], w_mlpT[2];            // pool backward (bf16): fc_neib^T (H x O) and mlp.0.weight^T (d_in x H), K-major
     WRef w_xT0;                         // pool + folded node_embedding backward (bf16): (Wx.Wp)^T (emb_dim x O1), K-major
     WRef w_x2T, w_n2T;                  // mean backward (bf16): layer-2 fc_x^T / fc_neib^T (2*O1 x O2), K-major, for the head's data gradients
@@ -176,7 +177,7 @@ struct gsage_engine {
 
 static int64_t pad_to(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
 
-static WRef f32w(const float* p, int64_t ld) { return WRef{p, GSAGE_F32, ld}; }
+static WRef f32w(const float* p, int64_t ld) { return WRef{p, GSAGE_F32, ld, nullptr, nullptr}; }
 
 static int linear_call(const RowSrc& a, const WRef& W, int O, const float* bias, int64_t n, int act,
                        void* out, int out_dtype, int64_t ld_out, int64_t col0, int exact, cudaStream_t s) {
@@ -184,6 +185,7 @@ static int linear_call(const RowSrc& a, const WRef& W, int O, const float* bias,
     P.n_segs = 1; P.n = n; P.act = act; P.out = out; P.out_dtype = out_dtype; P.ld_out = ld_out;
     P.seg[0] = LinearSeg{a.base, a.dtype, a.ld, a.ids, W.p, W.dtype, W.ld, a.d, O, bias, col0};
     P.seg[0].a_rows = a.ids ? a.table_rows : 0;
+    P.seg[0].w_hi = W.hi; P.seg[0].w_lo = W.lo;
     if (n == 0) return GSAGE_OK;
     return linear_dispatch(P, exact, s);
 }
@@ -197,6 +199,8 @@ static int combine_call(const RowSrc& x, const WRef& Wx, const RowSrc& m, const 
     P.seg[1] = LinearSeg{m.base, m.dtype, m.ld, m.ids, Wn.p, Wn.dtype, Wn.ld, m.d, O, bn, (int64_t)O};
     P.seg[0].a_rows = x.ids ? x.table_rows : 0;
     P.seg[1].a_rows = m.ids ? m.table_rows : 0;
+    P.seg[0].w_hi = Wx.hi; P.seg[0].w_lo = Wx.lo;
+    P.seg[1].w_hi = Wn.hi; P.seg[1].w_lo = Wn.lo;
     if (n == 0) return GSAGE_OK;
     return linear_dispatch(P, exact, s);
 }
@@ -464,6 +468,7 @@ void gsage_engine_destroy(gsage_engine* e) {
     cudaFree(e->ws);
     cudaFree(e->wb);
     cudaFree(e->fold);
+    cudaFree(e->wsplit);
     cudaFree(e->FCP);
     delete e;
 }
@@ -549,7 +554,16 @@ int gsage_engine_set_weights(gsage_engine* e, const gsage_weights* w, void* stre
     w = &eff;
     const bool pool = e->cfg.aggregator == GSAGE_AGG_MAX_POOL || e->cfg.aggregator == GSAGE_AGG_MEAN_POOL;
     const bool att = e->cfg.aggregator == GSAGE_AGG_ATTENTION;
-    int64_t off = 0;
+    int64_t off = 0, split_off = 0;
+    if (e->T == GSAGE_F32 && !e->cfg.allow_tf32 && !e->wsplit) {
+        int64_t need = 0;
+        for (int l = 0; l < 2; ++l) {
+            const int64_t d_in = l == 0 ? e->ld_prep : 2 * e->cfg.out_dim[0];
+            need += 2 * 2 * pad_to((int64_t)e->cfg.out_dim[l] * (d_in > e->hid ? d_in : e->hid), 64);      // fc_x, fc_neib: hi and lo
+        }
+        GS_CUDA(cudaMalloc((void**)&e->wsplit, need * sizeof(float)));
+        e->wsplit_floats = need;
+    }
     for (int l = 0; l < 2; ++l) {
         const int d_in = l == 0 ? e->d_prep : 2 * e->cfg.out_dim[0];
         const int d_nb = pool ? e->hid : d_in;
@@ -559,7 +573,17 @@ int gsage_engine_set_weights(gsage_engine* e, const gsage_weights* w, void* stre
             {pool ? w->layer[l].mlp_w : nullptr, e->hid, d_in, &e->w_mlp[l]}, {att ? w->layer[l].att_w1 : nullptr, e->hid, d_in, &e->w_att1[l]}};
         for (const Item& it : items) {
             if (!it.src) { *it.dst = WRef{nullptr, GSAGE_F32, 0}; continue; }
-            if (e->T != GSAGE_BF16) { *it.dst = f32w(it.src, it.cols); continue; }
+            if (e->T != GSAGE_BF16) {
+                *it.dst = f32w(it.src, it.cols);
+                const int64_t cnt = pad_to((int64_t)it.rows * it.cols, 64);
+                if (e->wsplit && (it.dst == &e->w_x[l] || it.dst == &e->w_n[l]) && split_off + 2 * cnt <= e->wsplit_floats) {
+                    float* hi = e->wsplit + split_off; float* lo = hi + cnt;
+                    GS_TRY(split_tf32_launch(it.src, (int64_t)it.rows * it.cols, hi, lo, s));
+                    it.dst->hi = hi; it.dst->lo = lo;
+                    split_off += 2 * cnt;
+                }
+                continue;
+            }
             const int64_t ld = pad_to(it.cols, 8);
             const int64_t bytes = pad_to(2 * ld * it.rows, 256);
             GS_CHECK_ARG(off + bytes <= e->wb_bytes, "engine_set_weights: bf16 weight arena too small");

@@ -10,6 +10,8 @@ struct LinearSeg {
     const float* bias; int64_t col0;
     int S = 1;      // > 1: A row r = mean_j A[ids[r*S + j]] (fused gather+mean)
     int w_trans = 0;   // 1: W is stored (d x O): element (o, k) at w[k * ldw + o]  (backward: dX = dY . W; FFMA kernel only)
+    const void* w_hi = nullptr; const void* w_lo = nullptr;   // fp32 operands only: tf32-exact split of W (w = w_hi + w_lo up to 2^-21): lets the
+                          // weight-stationary kernel run the projection as 3 x TF32 (fp32-level accuracy on the tensor cores)
     int O_store = 0;      // > 0: only the first O_store of the O computed columns are stored (W rows O_store.. are padding:
                           // the classifier's 41 classes ride in a 48-row operand on the tensor-core kernel)
     int64_t a_rows = 0;   // rows of the table behind `a` when known (> 0): ids outside it then read as ZERO rows in the TMA
@@ -31,6 +33,11 @@ int linear_umma_launch(const LinearParams& P, cudaStream_t s);
 // weight-stationary tcgen05 kernel (linear_ws_umma.cu): same operands, W of a phase resident in shared memory (preferred when it fits)
 bool linear_ws_umma_eligible(const LinearParams& P);
 int linear_ws_umma_launch(const LinearParams& P, cudaStream_t s);
+// 3 x TF32 variant (fp32 operands with w_hi / w_lo given, weights fully resident): same kernel, fp32-level accuracy
+bool linear_ws_umma_x3_eligible(const LinearParams& P);
+int linear_ws_umma_x3_launch(const LinearParams& P, cudaStream_t s);
+// w -> (w_hi, w_lo): w_hi = w with the 13 low mantissa bits cleared (exact in tf32), w_lo = the same of (w - w_hi)
+int split_tf32_launch(const float* w, int64_t n, float* w_hi, float* w_lo, cudaStream_t s);
 // pool aggregators: MLP + pool over the S rows of a parent in one tcgen05 kernel (linear_pool_umma.cu, swap-AB)
 bool linear_pool_umma_eligible(const LinearParams& P);
 int linear_pool_umma_launch(const LinearParams& P, cudaStream_t s);

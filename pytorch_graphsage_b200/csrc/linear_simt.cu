@@ -118,6 +118,24 @@ int linear_simt_launch(const LinearParams& P, cudaStream_t s) {
 
 using namespace gsage;
 
+// stream-ordered scratch for the (hi, lo) weight halves of exact == 2 calls: a private pool that keeps its memory between
+// calls (the default pool hands everything back to the driver at every synchronisation point)
+static cudaMemPool_t split_pool() {
+    static cudaMemPool_t pool = nullptr;
+    if (!pool) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaMemPoolProps props = {};
+        props.allocType = cudaMemAllocationTypePinned;
+        props.location.type = cudaMemLocationTypeDevice;
+        props.location.id = dev;
+        if (cudaMemPoolCreate(&pool, &props) != cudaSuccess) { cudaGetLastError(); cudaDeviceGetDefaultMemPool(&pool, dev); return pool; }
+        uint64_t keep = ~0ull;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+    return pool;
+}
+
 extern "C" int gsage_linear(const gsage_linear_seg* segs, int n_segs, int64_t n, int act, void* out_dev, int out_dtype,
                             int64_t ld_out, int exact, void* stream) {
     GS_CHECK_ARG(segs && (n_segs == 1 || n_segs == 2) && n >= 0 && out_dev, "linear: bad arguments");
@@ -135,13 +153,29 @@ extern "C" int gsage_linear(const gsage_linear_seg* segs, int n_segs, int64_t n,
         P.seg[i].a_rows = g.ids_dev ? g.a_rows : 0;
     }
     if (n == 0) return GSAGE_OK;
-    return linear_dispatch(P, exact, as_stream(stream));
+    cudaStream_t s = as_stream(stream);
+    if (exact != 2) return linear_dispatch(P, exact, s);
+    // exact == 2: fp32 accuracy on the tensor cores where the call qualifies (3 x TF32), the FFMA kernel where it does not.
+    // The (hi, lo) halves of the weights live in stream-ordered scratch for the duration of the call.
+    float* scratch[2] = {nullptr, nullptr};
+    for (int i = 0; i < n_segs; ++i) {
+        LinearSeg& g = P.seg[i];
+        if (g.a_dtype != GSAGE_F32 || g.w_dtype != GSAGE_F32 || g.w_trans) continue;
+        const int64_t cnt = (int64_t)g.O * g.ldw;
+        GS_CUDA(cudaMallocFromPoolAsync((void**)&scratch[i], 2 * cnt * sizeof(float), split_pool(), s));
+        GS_TRY(split_tf32_launch((const float*)g.w, cnt, scratch[i], scratch[i] + cnt, s));
+        g.w_hi = scratch[i]; g.w_lo = scratch[i] + cnt;
+    }
+    const int st = linear_dispatch(P, 1, s);
+    for (int i = 0; i < n_segs; ++i) if (scratch[i]) cudaFreeAsync(scratch[i], s);
+    return st;
 }
 
 namespace gsage {
 // bf16 x bf16 segments go to the tcgen05 kernel (<= 256 accumulator columns per launch: wide segments are
 // split into column blocks, two-segment calls that do not fit are issued one segment at a time);
-// anything else -- and everything when `exact` is set -- runs on the fp32 FFMA kernel.
+// anything else runs on the fp32 FFMA kernel -- and so does everything when `exact` is set, except fp32 calls that come with
+// the (hi, lo) tf32 halves of W and fit the weight-stationary kernel: those run as 3 x TF32 (GSAGE_FP32_FFMA=1 turns that off).
 int linear_dispatch(const LinearParams& P, int exact, cudaStream_t s) {
     if (P.pool_S > 1) {
         GS_CHECK_ARG(!exact && linear_pool_umma_eligible(P), "linear: the fused MLP+pool needs operands that qualify for the tensor-core kernel "
@@ -163,6 +197,7 @@ int linear_dispatch(const LinearParams& P, int exact, cudaStream_t s) {
         if (one.seg[0].O > 256) one.seg[0].O = 256;
         tc = linear_umma_eligible(one);
     }
+    if (exact && linear_ws_umma_x3_eligible(P)) return linear_ws_umma_x3_launch(P, s);     // fp32 accuracy on the tensor cores (3 x TF32)
     if (!tc) { GS_CHECK_ARG(P.pool_S <= 1, "linear: operands do not qualify for the tensor-core kernel (pooled epilogue)"); return linear_simt_launch(P, s); }
     if (linear_ws_umma_eligible(P)) return linear_ws_umma_launch(P, s);      // weights stationary in smem: half the L2 -> SM bytes
     if (linear_umma_eligible(P)) return linear_umma_launch(P, s);

@@ -28,7 +28,8 @@ namespace gsage {
 static constexpr int WM = 128;                 // rows per tile (UMMA M)
 static constexpr int kWsEpiWarps = 4;
 static constexpr int kWsTmaWarps = 8;             // producers: a lone warp issuing 32 gather4 per stage is the bottleneck (see below)
-static constexpr int kWsThreads = 32 * (kWsEpiWarps + 1 + kWsTmaWarps);
+static constexpr int kWsSplitWarps = 4;           // 3 x TF32 mode only: turn every landed fp32 A chunk into its (hi, lo) pair
+static constexpr int kWsThreads = 32 * (kWsEpiWarps + 1 + kWsTmaWarps + kWsSplitWarps);
 static constexpr int kWsABytes = WM * 128;     // one A stage: 128 rows x 128 bytes
 static constexpr int kWsMaxStages = 12;
 static constexpr int kSmemLimit = 227 * 1024;
@@ -38,7 +39,7 @@ struct WsSeg {
     int d; int O; int O_store; const float* bias; int64_t col0;
     int kchunks;          // ceil(d / uk)
     int acc_col;          // first TMEM column of this segment's accumulator inside a buffer
-    int w_off;            // byte offset of this segment's resident W inside the W area (kres slots of O x 128 B)
+    int w_off;            // byte offset of this segment's resident W inside the W area (kres slots of O x 128 B; x3: hi slots then lo slots)
     int kres;             // k-chunks of W resident in shared memory; chunks kres.. stream through the ring
 };
 
@@ -50,10 +51,11 @@ struct WsParams {
     int n_tiles; int stages; int w_area;      // bytes reserved for the resident weights
     int stage_bytes;                          // one ring slot: an A chunk (128 x 128 B) or a streamed W chunk (O x 128 B)
     int tf32; int uk;
+    int x3;                                   // 3 x TF32: D += A_hi W_hi^T + A_hi W_lo^T + A_lo W_hi^T (fp32 operands, W fully resident as hi + lo)
     int* err;
 };
 
-struct WsMaps { CUtensorMap w[2]; CUtensorMap a[2]; CUtensorMap g[2]; };
+struct WsMaps { CUtensorMap w[2]; CUtensorMap a[2]; CUtensorMap g[2]; CUtensorMap wl[2]; };   // wl: the lo halves of W (3 x TF32)
 
 template <int ACT>
 __device__ __forceinline__ void ws_store32(const uint32_t* r, const float* bias, int valid, void* out, int out_bf16) {
@@ -98,7 +100,7 @@ __global__ void __launch_bounds__(kWsThreads, 1) linear_ws_umma_kernel(const WsP
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint8_t* a_ring = smem + P.w_area;
     uint64_t* bars = (uint64_t*)(a_ring + (size_t)P.stages * P.stage_bytes);
-    uint32_t* tmem_slot = (uint32_t*)(bars + 2 * kWsMaxStages + 6);
+    uint32_t* tmem_slot = (uint32_t*)(bars + 3 * kWsMaxStages + 6);
     const uint32_t bar_base = smem_u32(bars);
     auto full_bar = [&](int s) { return bar_base + 8u * s; };
     auto empty_bar = [&](int s) { return bar_base + 8u * (kWsMaxStages + s); };
@@ -106,11 +108,12 @@ __global__ void __launch_bounds__(kWsThreads, 1) linear_ws_umma_kernel(const WsP
     auto tempty_bar = [&](int b) { return bar_base + 8u * (2 * kWsMaxStages + 2 + b); };
     const uint32_t wfull_bar = bar_base + 8u * (2 * kWsMaxStages + 4);
     const uint32_t wempty_bar = bar_base + 8u * (2 * kWsMaxStages + 5);
+    auto split_bar = [&](int s) { return bar_base + 8u * (2 * kWsMaxStages + 6 + s); };     // x3: the stage's lo tile is ready
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < P.stages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+        for (int s = 0; s < P.stages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); mbar_init(split_bar(s), 32 * kWsSplitWarps); }
         for (int b = 0; b < 2; ++b) { mbar_init(tfull_bar(b), 1); mbar_init(tempty_bar(b), 32 * kWsEpiWarps); }
         mbar_init(wfull_bar, 1);
         mbar_init(wempty_bar, 1);
@@ -186,7 +189,7 @@ __global__ void __launch_bounds__(kWsThreads, 1) linear_ws_umma_kernel(const WsP
                         uint64_t wdesc = desc_hi | (uint64_t)((smem_u32(smem + sg.w_off) & 0x3FFFF) >> 4);
                         const int kchunks = sg.kchunks, kres = sg.kres;
                         for (int kc = 0; kc < kchunks; ++kc) {
-                            mbar_wait(full_bar(stage), par, P.err);
+                            mbar_wait(P.x3 ? split_bar(stage) : full_bar(stage), par, P.err);
                             const uint32_t a_stage = stage;
                             const uint64_t adesc = desc_hi | (uint64_t)a16;
                             if (++stage == n_stages) { stage = 0; par ^= 1; a16 = ring16; } else a16 += sb16;
@@ -202,7 +205,16 @@ __global__ void __launch_bounds__(kWsThreads, 1) linear_ws_umma_kernel(const WsP
                                 wdesc += w_slot16;
                             }
                             tc_fence_after();
-                            if (P.tf32) {
+                            if (P.x3) {
+                                // a = a_hi + a_lo, w = w_hi + w_lo (each half exact in tf32): the three products that matter
+                                const uint64_t alo = adesc + (kWsABytes >> 4), wlo = bdesc + (uint64_t)(kchunks * w_slot16);
+#pragma unroll
+                                for (int k = 0; k < 4; ++k) {
+                                    umma_tf32(d_tmem, alo + 2 * k, bdesc + 2 * k, idesc, (kc | k) ? 1u : 0u);
+                                    umma_tf32(d_tmem, adesc + 2 * k, wlo + 2 * k, idesc, 1u);
+                                    umma_tf32(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, 1u);
+                                }
+                            } else if (P.tf32) {
 #pragma unroll
                                 for (int k = 0; k < 4; ++k) umma_tf32(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kc | k) ? 1u : 0u);
                             } else {
@@ -219,6 +231,44 @@ __global__ void __launch_bounds__(kWsThreads, 1) linear_ws_umma_kernel(const WsP
             }
         }
         __syncwarp();
+    } else if (warp >= kWsEpiWarps + 1 + kWsTmaWarps) {
+        // =========================== SPLITTERS (3 x TF32 only) ===========================
+        // every landed fp32 A chunk becomes a (hi, lo) pair in place: hi = the value with its 13 low mantissa bits cleared
+        // (exact in tf32 whatever rounding the tensor core applies to its inputs), lo = a - hi.  Elementwise, so the swizzled
+        // layout is irrelevant: the 128 threads sweep the 16 KB tile (and its twin 16 KB further up) in 8 passes of 2 KB,
+        // consecutive lanes on consecutive 16-byte units (a lane-per-row split would be a 32-way bank conflict: measured,
+        // 6900 cycles per stage instead of ~400).
+        if (P.x3) {
+            const int t = threadIdx.x - 32 * (kWsEpiWarps + 1 + kWsTmaWarps);
+            const uint32_t ring_u = smem_u32(a_ring), sb = (uint32_t)P.stage_bytes;
+            const uint32_t n_stages = (uint32_t)P.stages;
+            uint32_t stage = 0, par = 0, sa_u = ring_u;
+            for (int ph = 0; ph < P.n_phases; ++ph) {
+                const int s_first = P.phase_first[ph], s_count = P.phase_count[ph];
+                for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x) {
+                    for (int si = 0; si < s_count; ++si) {
+                        const int kchunks = P.seg[s_first + si].kchunks;
+                        for (int kc = 0; kc < kchunks; ++kc) {
+                            mbar_wait(full_bar(stage), par, P.err);
+                            const uint32_t at = sa_u + (uint32_t)t * 16u;
+#pragma unroll
+                            for (int q = 0; q < 8; ++q) {
+                                uint4 v;
+                                asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(at + 2048u * q));
+                                uint4 hi = make_uint4(v.x & 0xFFFFE000u, v.y & 0xFFFFE000u, v.z & 0xFFFFE000u, v.w & 0xFFFFE000u);
+                                uint4 lo = make_uint4(__float_as_uint(__uint_as_float(v.x) - __uint_as_float(hi.x)), __float_as_uint(__uint_as_float(v.y) - __uint_as_float(hi.y)),
+                                                      __float_as_uint(__uint_as_float(v.z) - __uint_as_float(hi.z)), __float_as_uint(__uint_as_float(v.w) - __uint_as_float(hi.w)));
+                                st_shared_v4(at + 2048u * q, hi);
+                                st_shared_v4(at + (uint32_t)kWsABytes + 2048u * q, lo);
+                            }
+                            fence_proxy_async();                     // generic-proxy stores -> visible to the tensor core
+                            mbar_arrive(split_bar(stage));
+                            if (++stage == n_stages) { stage = 0; par ^= 1; sa_u = ring_u; } else sa_u += sb;
+                        }
+                    }
+                }
+            }
+        }
     } else {
         // =========================== TMA PRODUCERS ===========================
         // Eight warps walk the same stage sequence.  Producer 0 (lane 0) posts every expect_tx and issues the one-instruction
@@ -241,7 +291,7 @@ __global__ void __launch_bounds__(kWsThreads, 1) linear_ws_umma_kernel(const WsP
                 uint32_t total = 0;
                 for (int si = 0; si < s_count; ++si) {
                     const WsSeg& sg = P.seg[s_first + si];
-                    total += (uint32_t)sg.kres * (uint32_t)sg.O * 128u;
+                    total += (uint32_t)sg.kres * (uint32_t)sg.O * 128u * (P.x3 ? 2u : 1u);
                 }
                 mbar_arrive_expect_tx(wfull_bar, total);
                 for (int si = 0; si < s_count; ++si) {
@@ -249,6 +299,9 @@ __global__ void __launch_bounds__(kWsThreads, 1) linear_ws_umma_kernel(const WsP
                     const uint32_t w_base = smem_u32(smem + sg.w_off);
                     for (int kc = 0; kc < sg.kres; ++kc)
                         tma_load_2d(w_base + (uint32_t)kc * (uint32_t)sg.O * 128u, &M.w[s_first + si], kc * uk, 0, wfull_bar);
+                    if (P.x3)
+                        for (int kc = 0; kc < sg.kres; ++kc)
+                            tma_load_2d(w_base + (uint32_t)(sg.kres + kc) * (uint32_t)sg.O * 128u, &M.wl[s_first + si], kc * uk, 0, wfull_bar);
                 }
             }
             for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x) {
@@ -333,17 +386,18 @@ struct WsPlan { int n_phases, w_area, stages, stage_bytes, kres[2]; };
 
 // plan the phases: both segments fully resident together when they fit next to a deep enough ring, else one segment per
 // phase with as many resident k-chunks as the ring leaves room for
-static bool ws_plan(const LinearParams& P, WsPlan* out) {
+static bool ws_plan(const LinearParams& P, bool x3, WsPlan* out) {
     const int fixed = 1024 /*align slack*/ + 512 /*barriers*/;
     int total = 0, cols = 0, maxO = 0;
     for (int i = 0; i < P.n_segs; ++i) {
-        total += ws_kchunks(P.seg[i]) * P.seg[i].O * 128;
+        total += ws_kchunks(P.seg[i]) * P.seg[i].O * 128 * (x3 ? 2 : 1);       // x3: hi and lo copies
         cols += (P.seg[i].O + 31) / 32 * 32;
         maxO = P.seg[i].O > maxO ? P.seg[i].O : maxO;
     }
     WsPlan p;
     p.stage_bytes = maxO * 128 > kWsABytes ? maxO * 128 : kWsABytes;
-    int min_stages = 6;
+    if (x3) p.stage_bytes = 2 * kWsABytes;                                      // the A chunk and its lo twin
+    int min_stages = x3 ? 3 : 6;
     if (const char* e = getenv("GSAGE_WS_STAGES")) min_stages = atoi(e);
     if (min_stages < 3) min_stages = 3;
     if (min_stages > kWsMaxStages) min_stages = kWsMaxStages;
@@ -352,6 +406,8 @@ static bool ws_plan(const LinearParams& P, WsPlan* out) {
     if (cols <= 256 && total <= avail) {
         p.n_phases = 1; p.w_area = total;
         for (int i = 0; i < P.n_segs; ++i) p.kres[i] = ws_kchunks(P.seg[i]);
+    } else if (x3) {
+        return false;                                                           // x3 streams no weights
     } else {
         p.n_phases = P.n_segs; p.w_area = 0;
         for (int i = 0; i < P.n_segs; ++i) {
@@ -383,18 +439,30 @@ bool linear_ws_umma_eligible(const LinearParams& P) {
         if (s.lda < (s.d + per - 1) / per * per || s.ldw < (s.d + per - 1) / per * per) return false;   // whole 16-byte chunks readable
     }
     WsPlan plan;
-    return ws_plan(P, &plan);
+    return ws_plan(P, false, &plan);
+}
+
+bool linear_ws_umma_x3_eligible(const LinearParams& P) {
+    if (getenv("GSAGE_FP32_FFMA")) return false;
+    for (int i = 0; i < P.n_segs; ++i) {
+        const LinearSeg& s = P.seg[i];
+        if (s.a_dtype != GSAGE_F32 || !s.w_hi || !s.w_lo || !ws_aligned16(s.w_hi) || !ws_aligned16(s.w_lo)) return false;
+    }
+    if (!linear_ws_umma_eligible(P)) return false;
+    WsPlan plan;
+    return ws_plan(P, true, &plan);
 }
 
 static int* g_ws_err = nullptr;
 
-int linear_ws_umma_launch(const LinearParams& P, cudaStream_t s) {
+static int ws_launch(const LinearParams& P, bool x3, cudaStream_t s) {
     WsParams U;
     memset(&U, 0, sizeof(U));
+    U.x3 = x3 ? 1 : 0;
     U.tf32 = P.seg[0].a_dtype == GSAGE_F32 ? 1 : 0;
     U.uk = U.tf32 ? 32 : 64;
     WsPlan plan;
-    GS_CHECK_ARG(ws_plan(P, &plan), "linear_ws_umma: operands do not fit in shared memory");
+    GS_CHECK_ARG(ws_plan(P, x3, &plan), "linear_ws_umma: operands do not fit in shared memory");
     const int n_phases = plan.n_phases;
     U.n_phases = n_phases; U.stages = plan.stages; U.w_area = plan.w_area; U.stage_bytes = plan.stage_bytes;
     for (int i = 0; i < P.n_segs; ++i) {
@@ -411,7 +479,7 @@ int linear_ws_umma_launch(const LinearParams& P, cudaStream_t s) {
         for (int i = 0; i < P.n_segs; ++i) {
             U.seg[i].acc_col = col; U.seg[i].w_off = off;
             col += (P.seg[i].O + 31) / 32 * 32;
-            off += plan.kres[i] * P.seg[i].O * 128;
+            off += plan.kres[i] * P.seg[i].O * 128 * (x3 ? 2 : 1);
         }
     } else {
         for (int i = 0; i < P.n_segs; ++i) { U.phase_first[i] = i; U.phase_count[i] = 1; U.seg[i].acc_col = 0; U.seg[i].w_off = 0; }
@@ -436,11 +504,32 @@ int linear_ws_umma_launch(const LinearParams& P, cudaStream_t s) {
     const int es = U.tf32 ? 4 : 2;
     for (int i = 0; i < P.n_segs; ++i) {
         const LinearSeg& g = P.seg[i];
-        GS_TRY(make_map(&maps.w[i], g.w, g.O, g.d, g.ldw, g.O, es));
+        GS_TRY(make_map(&maps.w[i], x3 ? g.w_hi : g.w, g.O, g.d, g.ldw, g.O, es));
+        if (x3) GS_TRY(make_map(&maps.wl[i], g.w_lo, g.O, g.d, g.ldw, g.O, es));
         if (!g.ids) GS_TRY(make_map(&maps.a[i], g.a, P.n, g.d, g.lda, WM, es));
         else GS_TRY(make_map(&maps.g[i], g.a, g.a_rows > 0 ? g.a_rows : 0x7FFFFFFF, g.d, g.lda, 1, es));       // rows by id
     }
     linear_ws_umma_kernel<<<grid, kWsThreads, smem, s>>>(U, maps);
+    GS_LAUNCHED();
+    return GSAGE_OK;
+}
+
+int linear_ws_umma_launch(const LinearParams& P, cudaStream_t s) { return ws_launch(P, false, s); }
+int linear_ws_umma_x3_launch(const LinearParams& P, cudaStream_t s) { return ws_launch(P, true, s); }
+
+__global__ void split_tf32_kernel(const float* __restrict__ w, int64_t n, float* __restrict__ hi, float* __restrict__ lo) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const float v = w[i];
+        const float h = __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
+        hi[i] = h;
+        lo[i] = __uint_as_float(__float_as_uint(v - h) & 0xFFFFE000u);
+    }
+}
+
+int split_tf32_launch(const float* w, int64_t n, float* w_hi, float* w_lo, cudaStream_t s) {
+    if (n <= 0) return GSAGE_OK;
+    const int grid = (int)(ceil_div(n, 256) < 1184 ? ceil_div(n, 256) : 1184);
+    split_tf32_kernel<<<grid, 256, 0, s>>>(w, n, w_hi, w_lo);
     GS_LAUNCHED();
     return GSAGE_OK;
 }

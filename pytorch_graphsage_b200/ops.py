@@ -116,7 +116,7 @@ def linear(segments, n, act=None, out=None, out_dtype=torch.float32, exact=True)
         width = max(width, sgm.get('col0', 0) + w.shape[0])
     if out is None:
         out = torch.empty((n, width), dtype=out_dtype, device=segments[0]['a'].device)
-    check(lib().gsage_linear(segs, len(segments), n, _lib.ACT[act], ptr(out), dt(out), _rows2d(out), 1 if exact else 0, stream()))
+    check(lib().gsage_linear(segs, len(segments), n, _lib.ACT[act], ptr(out), dt(out), _rows2d(out), 2 if exact == 'x3' else (1 if exact else 0), stream()))
     return out
 
 

@@ -33,11 +33,15 @@ class FlatGradBucket(object):
         head_ids = set(id(p) for p in head)
         order = [p for p in params if id(p) in head_ids] + [p for p in params if id(p) not in head_ids]
         device = device or order[0].device
-        self.flat = torch.zeros(sum(p.numel() for p in order), dtype=torch.float32, device=device)
-        self.views, off = {}, 0
+        # every slice starts on a 256-byte boundary (the kernels want 16-byte aligned rows, TMA wants more); the padding
+        # stays zero: it adds nothing to the gradient norm and an Adam update of (param 0, grad 0) is 0
+        pad = lambda n: (n + 63) // 64 * 64
+        self.flat = torch.zeros(sum(pad(p.numel()) for p in order), dtype=torch.float32, device=device)
+        self.views, self.offsets, off = {}, {}, 0
         for p in order:
             self.views[id(p)] = self.flat[off:off + p.numel()].view_as(p)
-            off += p.numel()
+            self.offsets[id(p)] = off
+            off += pad(p.numel())
             if id(p) in head_ids:
                 self.head_numel = off
         if not head_ids:
@@ -86,14 +90,12 @@ class FusedAdam(object):
         self.bucket = model._bucket()
         order = self.bucket.params
         dev = self.bucket.flat.device
-        self.flat = torch.empty(self.bucket.flat.numel(), dtype=torch.float32, device=dev)
-        off = 0
+        self.flat = torch.zeros(self.bucket.flat.numel(), dtype=torch.float32, device=dev)
         for p in order:
             assert p.dtype == torch.float32 and p.is_cuda, 'FusedAdam: fp32 CUDA parameters'
-            n = p.numel()
+            n, off = p.numel(), self.bucket.offsets[id(p)]
             self.flat[off:off + n].copy_(p.data.reshape(-1))
             p.data = self.flat[off:off + n].view_as(p)            # the parameter now lives inside the flat buffer
-            off += n
         self.m = torch.zeros_like(self.flat)
         self.v = torch.zeros_like(self.flat)
         self.scratch = torch.zeros(1, dtype=torch.float32, device=dev)

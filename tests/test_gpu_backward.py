@@ -241,6 +241,30 @@ def test_fused_clip_adam_equals_torch(g):
     np.testing.assert_allclose(lb.cpu().numpy(), la.cpu().numpy(), rtol=1e-4, atol=1e-5)
 
 
+def test_fused_adam_on_the_embedding_recipe_keeps_every_parameter_aligned(g):
+    """The Pokec recipe (mean + node_embedding, no features) under FusedAdam: the embedding table moves into the flat
+    parameter buffer behind odd-sized tensors (biases, the 41-class head), and the gather kernels need its rows 16-byte
+    aligned -- every slice of the flat buffers starts on a 256-byte boundary.  Three steps equal torch's clip + Adam."""
+    fix = util.load('model_mean_node_embedding_nofeats')
+    targets = torch.from_numpy(np.random.RandomState(1).randint(0, fix['logits'].shape[1], fix['ids0'].shape[0])).cuda()
+    ids = torch.from_numpy(fix['ids0'])
+    a = build_model(g, fix, 'mean', 'node_embedding', False)
+    b = build_model(g, fix, 'mean', 'node_embedding', False)
+    opt_a = torch.optim.Adam(a.parameters(), lr=0.01)
+    opt_b = g.FusedAdam(b, lr=0.01)
+    for p in b.parameters():
+        assert p.data_ptr() % 256 == 0
+    for step in range(3):
+        g.set_seeds(int(fix['seed']) + step)
+        a.train_step(ids, None, targets, F.cross_entropy, optimizer=opt_a, clip=5.0)
+        g.set_seeds(int(fix['seed']) + step)
+        b.train_step(ids, None, targets, F.cross_entropy, optimizer=opt_b, clip=5.0)
+        for (name, pa), (_, pb) in zip(a.named_parameters(), b.named_parameters()):
+            np.testing.assert_allclose(pb.detach().cpu().numpy(), pa.detach().cpu().numpy(), rtol=2e-4, atol=5e-6, err_msg='%s step %d' % (name, step))
+    for p in b.parameters():
+        assert p.grad.data_ptr() % 256 == 0
+
+
 def test_train_step_with_the_dense_sampler(g):
     """train.py's default configuration (dense sampler, mean, identity): gradients against autograd through the oracle."""
     fix = util.load('model_dense_mean_identity')

@@ -240,6 +240,33 @@ def test_umma_tf32_projection(g, n, d, O):
     np.testing.assert_allclose(exact.cpu().numpy(), want.numpy(), rtol=1e-4, atol=1e-5)
 
 
+@pytest.mark.parametrize('n,d,O', [(300, 64, 128), (128 * 200 + 5, 64, 128), (1000, 100, 64), (129, 256, 32), (777, 64, 16)])
+def test_three_tf32_projection_has_fp32_accuracy(g, n, d, O, monkeypatch):
+    """exact='x3': fp32 operands on the tensor cores as 3 x TF32 (a = a_hi + a_lo, w = w_hi + w_lo, three products, fp32
+    accumulate).  Same bar as the FFMA kernel (rtol 1e-4 / atol 1e-5 against float64), and it must be a different kernel
+    than both the FFMA one (GSAGE_FP32_FFMA=1) and the single-pass TF32 one (whose error is ~100x larger)."""
+    gen = torch.Generator().manual_seed(n + d)
+    table = torch.randn((n + 77, d), generator=gen)
+    m = torch.randn((n, d), generator=gen)
+    wx, wn = torch.randn((O, d), generator=gen) / d ** 0.5, torch.randn((O, d), generator=gen) / d ** 0.5
+    bias = torch.randn((O,), generator=gen)
+    ids = torch.randint(0, n + 77, (n,), generator=gen)
+    pad = lambda t: g.ops.pad_table(t, torch.float32)[0][:, :t.shape[1]]
+    segs = [dict(a=pad(table), ids=ids.cuda(), w=pad(wx), col0=0, bias=bias.cuda()), dict(a=pad(m), w=pad(wn), col0=O)]
+    want = torch.relu(torch.cat([table[ids].double() @ wx.double().t() + bias.double(), m.double() @ wn.double().t()], dim=1))
+    got = g.ops.linear(segs, n, act='relu', out_dtype=torch.float32, exact='x3').cpu()
+    np.testing.assert_allclose(got.numpy(), want.numpy(), rtol=1e-4, atol=1e-5)
+    err_x3 = (got.double() - want).abs().max().item()
+    tf32 = g.ops.linear(segs, n, act='relu', out_dtype=torch.float32, exact=False).cpu()
+    err_tf32 = (tf32.double() - want).abs().max().item()
+    assert err_x3 < err_tf32 / 20, (err_x3, err_tf32)
+    assert err_x3 < 4e-6 * d ** 0.5, err_x3
+    monkeypatch.setenv('GSAGE_FP32_FFMA', '1')
+    ffma = g.ops.linear(segs, n, act='relu', out_dtype=torch.float32, exact='x3').cpu()
+    np.testing.assert_allclose(ffma.numpy(), want.numpy(), rtol=1e-4, atol=1e-5)
+    assert not torch.equal(ffma, got)              # different summation order: the tensor-core path really ran
+
+
 @pytest.mark.parametrize('n,S,d,H', [(100, 10, 64, 512), (37, 25, 64, 512), (513, 3, 100, 32), (8, 128, 64, 48), (3000, 10, 256, 512),
                                      (257, 25, 256, 512), (1000, 10, 602, 512), (50, 64, 64, 200), (64, 2, 72, 136)])
 @pytest.mark.parametrize('reduce', ['max', 'mean'])

@@ -60,7 +60,7 @@ def test_shard_and_bucket_world2():
     seeds = res[0][1] + res[1][1]
     assert seeds == list(range(101)) and abs(len(res[0][1]) - len(res[1][1])) <= 1          # a partition of the batch
     assert all(r[2] for r in res), 'weighted all-reduce != single-process gradient of the global mean loss'
-    assert all(r[3] for r in res) and res[0][4] == 5 * 3 + 3                                   # head params lead the bucket
+    assert all(r[3] for r in res) and res[0][4] == 64 + 64                                   # head params lead the bucket
 
 
 def test_shard_seeds_partition_property():
