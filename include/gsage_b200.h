@@ -42,7 +42,7 @@ typedef enum gsage_dtype { GSAGE_F32 = 0, GSAGE_BF16 = 1 } gsage_dtype;
 typedef enum gsage_act { GSAGE_ACT_NONE = 0, GSAGE_ACT_RELU = 1, GSAGE_ACT_TANH = 2 } gsage_act;
 typedef enum gsage_reduce { GSAGE_RED_MEAN = 0, GSAGE_RED_MAX = 1, GSAGE_RED_SUM = 2 } gsage_reduce;
 typedef enum gsage_aggregator {
-    GSAGE_AGG_MEAN = 0, GSAGE_AGG_MAX_POOL = 1, GSAGE_AGG_MEAN_POOL = 2, GSAGE_AGG_ATTENTION = 3
+    GSAGE_AGG_MEAN = 0, GSAGE_AGG_MAX_POOL = 1, GSAGE_AGG_MEAN_POOL = 2, GSAGE_AGG_ATTENTION = 3, GSAGE_AGG_LSTM = 4
 } gsage_aggregator;
 typedef enum gsage_prep { GSAGE_PREP_IDENTITY = 0, GSAGE_PREP_NODE_EMBEDDING = 1, GSAGE_PREP_LINEAR = 2 } gsage_prep;
 
@@ -146,6 +146,13 @@ int gsage_attention_aggregate(const void* table_dev, int dtype, int64_t ld, int6
                               int64_t n_parents, int S,
                               const void* w1_dev, int w1_dtype, int64_t ldw, int H, const float* b1_dev, const float* w2_dev,
                               const float* xa_dev, void* out_dev, int out_dtype, int64_t ld_out, void* stream);
+/* One time step of the LSTM aggregator's cell (nn_modules.py:266,276-278: nn.LSTM, one layer, unidirectional, batch_first):
+ *   gates = gx + gh + b_ih + b_hh   (n x 4H fp32, torch's gate order i, f, g, o; gx = x_t . W_ih^T and gh = h_{t-1} . W_hh^T
+ *                                    come from gsage_linear)
+ *   c = sigmoid(f) c + sigmoid(i) tanh(g);   h = sigmoid(o) tanh(c)          (c fp32 in place, h fp32 or bf16)
+ * `first` != 0: zero initial state -- c is not read and gh is ignored (may be NULL). */
+int gsage_lstm_cell(const float* gx_dev, const float* gh_dev, int64_t ldg, const float* b_ih_dev, const float* b_hh_dev,
+                    float* c_dev, void* h_dev, int h_dtype, int64_t ldh, int64_t n, int H, int first, void* stream);
 /* F.normalize(dim=1, eps=1e-12) (models.py:90), fp32 out */
 int gsage_l2_normalize(const void* x_dev, int dtype, int64_t ld, int64_t n, int d, float* out_dev, int64_t ld_out,
                        void* stream);
@@ -203,7 +210,7 @@ typedef struct gsage_engine_config {
     const void* feats_dev; int feats_dtype; int64_t feats_ld; int feats_dim; int64_t feats_rows;
     /* NodeEmbeddingPrep (nn_modules.py:126-155): table (n_nodes+1, 64), fc 64x64 + bias; n_nodes = adj.shape[0] */
     const void* emb_dev; int emb_dtype; int64_t emb_ld; int emb_dim; int64_t n_nodes;
-    int hidden_dim;                 /* pool MLP width (512) / attention width (32)                        */
+    int hidden_dim;                 /* pool MLP width (512) / attention width (32) / LSTM state width (512) */
     int64_t max_batch;              /* workspace is sized for this many seeds                             */
     int allow_tf32;                 /* fp32 mode only: run the projections on the tensor cores as TF32 (10-bit mantissa
                                        products, fp32 accumulate; ~1e-3 relative) instead of the exact FFMA kernel */
@@ -217,6 +224,10 @@ typedef struct gsage_layer_weights {
     const float* mlp_b;             /* agg_layers.k.mlp.0.bias     (hidden)         pool                  */
     const float* att_w1;            /* agg_layers.k.att.0.weight   (hidden, d_in)   attention             */
     const float* att_w2;            /* agg_layers.k.att.2.weight   (hidden, hidden) attention             */
+    const float* lstm_w_ih;         /* agg_layers.k.lstm.weight_ih_l0 (4*hidden, d_in)   lstm             */
+    const float* lstm_w_hh;         /* agg_layers.k.lstm.weight_hh_l0 (4*hidden, hidden) lstm             */
+    const float* lstm_b_ih;         /* agg_layers.k.lstm.bias_ih_l0   (4*hidden)         lstm             */
+    const float* lstm_b_hh;         /* agg_layers.k.lstm.bias_hh_l0   (4*hidden)         lstm             */
 } gsage_layer_weights;
 
 typedef struct gsage_weights {

@@ -89,7 +89,26 @@ def agg_attention(x, neibs, params, prefix, act):
     return _combine(x, m, params, prefix, act)
 
 
+def agg_lstm(x, neibs, params, prefix, act):
+    """nn_modules.py:259-286: a one-layer unidirectional nn.LSTM (batch_first) over the S neighbour rows of every parent in
+    their sampled order, zero initial state, LAST hidden state -> fc_neib.  torch's cell (gate order i, f, g, o in the 4H rows
+    of weight_ih / weight_hh): c' = sigmoid(f) c + sigmoid(i) tanh(g), h' = sigmoid(o) tanh(c')."""
+    w_ih, w_hh = params[prefix + 'lstm.weight_ih_l0'], params[prefix + 'lstm.weight_hh_l0']
+    b = params[prefix + 'lstm.bias_ih_l0'] + params[prefix + 'lstm.bias_hh_l0']
+    n, H = x.shape[0], w_hh.shape[1]
+    seq = neibs.reshape(n, -1, neibs.shape[1])
+    h = torch.zeros((n, H), dtype=x.dtype)
+    c = torch.zeros((n, H), dtype=x.dtype)
+    for t in range(seq.shape[1]):
+        gates = seq[:, t] @ w_ih.t() + h @ w_hh.t() + b
+        i, f, g, o = gates[:, :H], gates[:, H:2 * H], gates[:, 2 * H:3 * H], gates[:, 3 * H:]
+        c = torch.sigmoid(f) * c + torch.sigmoid(i) * torch.tanh(g)
+        h = torch.sigmoid(o) * torch.tanh(c)
+    return _combine(x, h, params, prefix, act)
+
+
 AGGREGATORS = {
+    'lstm': agg_lstm,
     'mean': agg_mean,
     'max_pool': lambda *a, **k: agg_pool(*a, reducer='max', **k),
     'mean_pool': lambda *a, **k: agg_pool(*a, reducer='mean', **k),

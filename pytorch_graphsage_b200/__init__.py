@@ -13,7 +13,7 @@ from .graph import GraphCSR                                # noqa: F401
 from .rng import DeviceMT19937, default_rng, set_seeds     # noqa: F401
 from .operators import (sampler_lookup, prep_lookup, aggregator_lookup, UniformNeighborSampler,   # noqa: F401
                         SparseUniformNeighborSampler, IdentityPrep, NodeEmbeddingPrep, LinearPrep, MeanAggregator,
-                        PoolAggregator, MaxPoolAggregator, MeanPoolAggregator, AttentionAggregator)
+                        PoolAggregator, MaxPoolAggregator, MeanPoolAggregator, AttentionAggregator, LSTMAggregator)
 from .model import GSSupervised, FeatureTable             # noqa: F401
 from .parallel import FusedAdam, FlatGradBucket            # noqa: F401
 from . import ops, synth, problem                          # noqa: F401

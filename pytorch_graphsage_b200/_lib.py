@@ -12,7 +12,7 @@ LIB_PATH = os.path.join(HERE, 'libgsage_b200.so')
 F32, BF16 = 0, 1
 ACT = {'none': 0, None: 0, 'identity': 0, 'relu': 1, 'tanh': 2}
 REDUCE = {'mean': 0, 'max': 1, 'sum': 2}
-AGGREGATOR = {'mean': 0, 'max_pool': 1, 'mean_pool': 2, 'attention': 3}
+AGGREGATOR = {'mean': 0, 'max_pool': 1, 'mean_pool': 2, 'attention': 3, 'lstm': 4}
 PREP = {'identity': 0, 'node_embedding': 1, 'linear': 2}
 
 ERR_INVALID, ERR_CUDA, ERR_INDEX, ERR_RNG, ERR_NOMEM = -1, -2, -3, -4, -5
@@ -38,7 +38,8 @@ class EngineConfig(C.Structure):
 
 
 class LayerWeights(C.Structure):
-    _fields_ = [('fc_x', c_p), ('fc_neib', c_p), ('mlp_w', c_p), ('mlp_b', c_p), ('att_w1', c_p), ('att_w2', c_p)]
+    _fields_ = [('fc_x', c_p), ('fc_neib', c_p), ('mlp_w', c_p), ('mlp_b', c_p), ('att_w1', c_p), ('att_w2', c_p),
+                ('lstm_w_ih', c_p), ('lstm_w_hh', c_p), ('lstm_b_ih', c_p), ('lstm_b_hh', c_p)]
 
 
 class Grads(C.Structure):
@@ -96,6 +97,7 @@ _SIGNATURES = {
     'gsage_attention_weights': (C.c_int, [c_p, c_p, C.c_int, c_i64, C.c_int, c_i64, C.c_int, c_p, c_p]),
     'gsage_attention_aggregate': (C.c_int, [c_p, C.c_int, c_i64, c_i64, C.c_int, c_p, c_i64, C.c_int, c_p, C.c_int, c_i64, C.c_int, c_p, c_p, c_p, c_p,
                                             C.c_int, c_i64, c_p]),
+    'gsage_lstm_cell': (C.c_int, [c_p, c_p, c_i64, c_p, c_p, c_p, c_p, C.c_int, c_i64, c_i64, C.c_int, C.c_int, c_p]),
     'gsage_l2_normalize': (C.c_int, [c_p, C.c_int, c_i64, c_i64, C.c_int, c_p, c_i64, c_p]),
     'gsage_linear': (C.c_int, [C.POINTER(LinearSeg), C.c_int, c_i64, C.c_int, c_p, C.c_int, c_i64, C.c_int, c_p]),
     'gsage_linear_pooled': (C.c_int, [C.POINTER(LinearSeg), c_i64, C.c_int, C.c_int, C.c_int, c_p, C.c_int, c_i64, c_p]),

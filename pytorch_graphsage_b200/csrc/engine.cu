@@ -38,6 +38,8 @@ struct RowSrc {
 };
 
 // a weight matrix as a kernel will read it: the caller's fp32 tensor, or the engine's padded bf16 copy
+int transpose_ids_launch(const int64_t* ids, int64_t n, int S, int64_t* out, cudaStream_t s);      // lstm.cu
+
 struct WRef { const void* p; int dtype; int64_t ld; const float* hi = nullptr; const float* lo = nullptr; };   // hi/lo: tf32-exact split (fp32-exact mode)
 
 // fp32 (rows, cols) -> bf16 (rows, ld) with zero padding (the tcgen05 kernel wants 16-byte aligned bf16 rows)
@@ -138,7 +140,9 @@ struct gsage_engine {
     int64_t ld_h1 = 0;
     // weights as the kernels read them (fp32 originals, or bf16 copies when compute dtype is bf16)
     char* wb = nullptr; int64_t wb_bytes = 0;
-    WRef w_x[2], w_n[2], w_mlp[2], w_att1[2];
+    WRef w_x[2], w_n[2], w_mlp[2], w_att1[2], w_ih[2], w_hh[2];
+    // LSTM aggregator: gate pre-activations of the current step (x part, h part), cell / hidden state, per-step id lists
+    float* LGX = nullptr; float* LGH = nullptr; float* LC = nullptr; void* LH = nullptr; int64_t* LIDS = nullptr;
     float* wsplit = nullptr; int64_t wsplit_floats = 0;      // fp32-exact mode: (hi, lo) tf32 halves of fc_x / fc_neib for the 3 x TF32 projection
     WRef w_nT[2], w_mlpT[2];            // pool backward (bf16): fc_neib^T (H x O) and mlp.0.weight^T (d_in x H), K-major
     WRef w_xT0;                         // pool + folded node_embedding backward (bf16): (Wx.Wp)^T (emb_dim x O1), K-major
@@ -316,6 +320,26 @@ static int apply_aggregator(gsage_engine* e, int layer, const RowSrc& x, const R
         RowSrc m{Mb, T, ldm, n, nullptr, d};
         return combine_call(x, e->w_x[layer], m, e->w_n[layer], O, n, act, out, out_dtype, ld_out, exact, s, e->b_x[layer], e->b_n[layer]);
     }
+    case GSAGE_AGG_LSTM: {
+        // nn_modules.py:276-279: the S neighbour rows of a parent, in sampled order, through a one-layer LSTM; the last hidden
+        // state is the aggregate.  Every step = two projections on the tensor cores (x_t . W_ih^T, h . W_hh^T; 4H gate
+        // columns each, fp32 out) + the cell update (lstm.cu).  Step t's rows: ids transposed into S contiguous lists, or --
+        // rows read in place -- a view of every S-th row.
+        const int H = e->hid;
+        const int64_t G4 = 4 * (int64_t)H;
+        GS_CHECK_ARG(e->LGX && n <= e->n1 && n * S <= e->n2, "lstm aggregator: workspace too small for %lld parents x %d", (long long)n, S);
+        if (nb.ids) GS_TRY(transpose_ids_launch(nb.ids, n, S, e->LIDS, s));
+        RowSrc hrow{e->LH, T, H, n, nullptr, H};
+        for (int t = 0; t < S; ++t) {
+            RowSrc xt = nb;
+            if (nb.ids) xt.ids = e->LIDS + (int64_t)t * n;
+            else { xt.base = (const char*)nb.base + (int64_t)t * nb.ld * (int64_t)dtype_size(nb.dtype); xt.ld = nb.ld * S; xt.table_rows = n; }
+            GS_TRY(linear_call(xt, e->w_ih[layer], (int)G4, nullptr, n, GSAGE_ACT_NONE, e->LGX, GSAGE_F32, G4, 0, exact, s));
+            if (t > 0) GS_TRY(linear_call(hrow, e->w_hh[layer], (int)G4, nullptr, n, GSAGE_ACT_NONE, e->LGH, GSAGE_F32, G4, 0, exact, s));
+            GS_TRY(gsage_lstm_cell(e->LGX, e->LGH, G4, L.lstm_b_ih, L.lstm_b_hh, e->LC, e->LH, T, H, n, H, t == 0, s));
+        }
+        return combine_call(x, e->w_x[layer], hrow, e->w_n[layer], O, n, act, out, out_dtype, ld_out, exact, s, e->b_x[layer], nullptr);
+    }
     }
     set_error("engine: unknown aggregator %d", e->cfg.aggregator);
     return GSAGE_ERR_INVALID;
@@ -330,7 +354,7 @@ int gsage_engine_create(const gsage_engine_config* cfg, gsage_engine** out) {
     GS_CHECK_ARG(cfg->out_dim[0] > 0 && cfg->out_dim[1] > 0 && cfg->n_classes > 0, "engine_create: bad dims");
     GS_CHECK_ARG(cfg->max_batch > 0, "engine_create: max_batch must be > 0");
     GS_CHECK_ARG(cfg->compute_dtype == GSAGE_F32 || cfg->compute_dtype == GSAGE_BF16, "engine_create: bad compute dtype");
-    GS_CHECK_ARG(cfg->aggregator >= GSAGE_AGG_MEAN && cfg->aggregator <= GSAGE_AGG_ATTENTION, "engine_create: bad aggregator");
+    GS_CHECK_ARG(cfg->aggregator >= GSAGE_AGG_MEAN && cfg->aggregator <= GSAGE_AGG_LSTM, "engine_create: bad aggregator");
     GS_CHECK_ARG(cfg->prep >= GSAGE_PREP_IDENTITY && cfg->prep <= GSAGE_PREP_LINEAR, "engine_create: bad prep");
     const bool has_feats = cfg->feats_dev != nullptr;
     if (cfg->prep == GSAGE_PREP_IDENTITY || cfg->prep == GSAGE_PREP_LINEAR)
@@ -354,7 +378,7 @@ int gsage_engine_create(const gsage_engine_config* cfg, gsage_engine** out) {
     case GSAGE_PREP_LINEAR: e->d_prep = 32; break;            // overwritten by weights.prep_out_dim at set_weights
     case GSAGE_PREP_NODE_EMBEDDING: e->d_prep = (has_feats ? cfg->feats_dim : 0) + cfg->emb_dim; break;
     }
-    e->fold_prep = cfg->prep == GSAGE_PREP_NODE_EMBEDDING && !has_feats;
+    e->fold_prep = cfg->prep == GSAGE_PREP_NODE_EMBEDDING && !has_feats && cfg->aggregator != GSAGE_AGG_LSTM;   // the LSTM reads materialised rows
     if (const char* f = getenv("GSAGE_FOLD_PREP")) e->fold_prep = e->fold_prep && atoi(f) != 0;
     e->ld_prep = (int)pad_to(e->d_prep, vec * 2);
     e->hid = cfg->hidden_dim > 0 ? cfg->hidden_dim : (cfg->aggregator == GSAGE_AGG_ATTENTION ? 32 : 512);
@@ -384,6 +408,13 @@ int gsage_engine_create(const gsage_engine_config* cfg, gsage_engine** out) {
         o_T1 = carve(4 * e->hid * e->n2); o_NA = carve(4 * e->hid * e->n2);
         o_T1x = carve(4 * e->hid * e->n1); o_XA = carve(4 * e->hid * e->n1);
         o_AW = carve(4 * e->n2);
+    }
+    int64_t o_LGX = -1, o_LGH = -1, o_LC = -1, o_LH = -1, o_LIDS = -1;
+    if (cfg->aggregator == GSAGE_AGG_LSTM) {
+        GS_CHECK_ARG(e->hid % 8 == 0, "engine_create: the LSTM state width must be a multiple of 8");
+        o_LGX = carve(4 * 4 * (int64_t)e->hid * e->n1); o_LGH = carve(4 * 4 * (int64_t)e->hid * e->n1);
+        o_LC = carve(4 * (int64_t)e->hid * e->n1); o_LH = carve(es * (int64_t)e->hid * e->n1);
+        o_LIDS = carve(8 * e->n2);
     }
     const int64_t o_H1 = carve(es * e->ld_h1 * (e->n0 + e->n1));
     const int64_t o_Z = carve(4 * 2 * O2 * e->n0);
@@ -428,6 +459,7 @@ int gsage_engine_create(const gsage_engine_config* cfg, gsage_engine** out) {
     if (e->T == GSAGE_BF16) {                // arena for the padded bf16 weight copies the tensor-core kernel reads
         const int64_t dmax0 = std::max<int64_t>(e->ld_prep, 2 * O1) + 8;
         e->wb_bytes = 2 * (2 * 2 * ((O1 + O2) * 2 * (dmax0 + e->hid) + 2 * (int64_t)e->hid * dmax0) + 16 * 256);   // + the transposed copies
+        if (cfg->aggregator == GSAGE_AGG_LSTM) e->wb_bytes += 2 * 2 * 4 * (int64_t)e->hid * (dmax0 + e->hid + 16) + 8 * 256;   // W_ih, W_hh of both layers
         if (cudaMalloc((void**)&e->wb, (size_t)e->wb_bytes) != cudaSuccess) {
             set_error("engine_create: cudaMalloc of the weight arena failed");
             cudaFree(e->ws);
@@ -440,6 +472,7 @@ int gsage_engine_create(const gsage_engine_config* cfg, gsage_engine** out) {
     e->ids_slot[0] = e->ids; e->ids_slot[1] = (int64_t*)at(o_ids1); e->cur = 0; e->sel_ahead = (uint32_t*)at(o_sel1);
     e->X = at(o_X); e->M = at(o_M); e->HN = at(o_HN); e->Pp = at(o_P);
     e->T1 = at(o_T1); e->NA = at(o_NA); e->T1x = at(o_T1x); e->XA = at(o_XA); e->AW = (float*)at(o_AW);
+    e->LGX = (float*)at(o_LGX); e->LGH = (float*)at(o_LGH); e->LC = (float*)at(o_LC); e->LH = at(o_LH); e->LIDS = (int64_t*)at(o_LIDS);
     e->H1 = at(o_H1); e->Z = (float*)at(o_Z); e->ZN = (float*)at(o_ZN); e->LG = (float*)at(o_LG);
     e->LG2[0] = e->LG; e->LG2[1] = (float*)at(o_LGb);
     e->DXE = (float*)at(o_DXE); e->DZB = at(o_DZB);
@@ -514,6 +547,9 @@ int gsage_engine_set_weights(gsage_engine* e, const gsage_weights* w, void* stre
             GS_CHECK_ARG(w->layer[l].mlp_w && w->layer[l].mlp_b, "engine_set_weights: pool MLP missing (layer %d)", l);
         if (e->cfg.aggregator == GSAGE_AGG_ATTENTION)
             GS_CHECK_ARG(w->layer[l].att_w1 && w->layer[l].att_w2, "engine_set_weights: attention MLP missing (layer %d)", l);
+        if (e->cfg.aggregator == GSAGE_AGG_LSTM)
+            GS_CHECK_ARG(w->layer[l].lstm_w_ih && w->layer[l].lstm_w_hh && w->layer[l].lstm_b_ih && w->layer[l].lstm_b_hh,
+                         "engine_set_weights: LSTM weights missing (layer %d)", l);
     }
     GS_CHECK_ARG(w->fc_w && w->fc_b, "engine_set_weights: classifier missing");
     if (e->cfg.prep == GSAGE_PREP_NODE_EMBEDDING) GS_CHECK_ARG(w->prep_fc_w && w->prep_fc_b, "engine_set_weights: prep.fc missing");
@@ -566,11 +602,13 @@ int gsage_engine_set_weights(gsage_engine* e, const gsage_weights* w, void* stre
     }
     for (int l = 0; l < 2; ++l) {
         const int d_in = l == 0 ? e->d_prep : 2 * e->cfg.out_dim[0];
-        const int d_nb = pool ? e->hid : d_in;
+        const bool lstm = e->cfg.aggregator == GSAGE_AGG_LSTM;
+        const int d_nb = (pool || lstm) ? e->hid : d_in;
         const int O = e->cfg.out_dim[l];
-        struct Item { const float* src; int rows, cols; WRef* dst; } items[4] = {
+        struct Item { const float* src; int rows, cols; WRef* dst; } items[6] = {
             {w->layer[l].fc_x, O, d_in, &e->w_x[l]}, {w->layer[l].fc_neib, O, d_nb, &e->w_n[l]},
-            {pool ? w->layer[l].mlp_w : nullptr, e->hid, d_in, &e->w_mlp[l]}, {att ? w->layer[l].att_w1 : nullptr, e->hid, d_in, &e->w_att1[l]}};
+            {pool ? w->layer[l].mlp_w : nullptr, e->hid, d_in, &e->w_mlp[l]}, {att ? w->layer[l].att_w1 : nullptr, e->hid, d_in, &e->w_att1[l]},
+            {lstm ? w->layer[l].lstm_w_ih : nullptr, 4 * e->hid, d_in, &e->w_ih[l]}, {lstm ? w->layer[l].lstm_w_hh : nullptr, 4 * e->hid, e->hid, &e->w_hh[l]}};
         for (const Item& it : items) {
             if (!it.src) { *it.dst = WRef{nullptr, GSAGE_F32, 0}; continue; }
             if (e->T != GSAGE_BF16) {

@@ -19,14 +19,15 @@ from torch.nn import functional as F
 from . import _lib, ops
 from ._lib import check, lib
 from .graph import GraphCSR
-from .operators import (AttentionAggregator, MeanAggregator, MeanPoolAggregator, MaxPoolAggregator, NodeEmbeddingPrep,
+from .operators import (AttentionAggregator, LSTMAggregator, MeanAggregator, MeanPoolAggregator, MaxPoolAggregator, NodeEmbeddingPrep,
                         IdentityPrep, LinearPrep, SparseUniformNeighborSampler, UniformNeighborSampler, _act_name)
 from .rng import default_rng
 
 
 def _agg_name(cls):
+    cls = getattr(cls, 'func', cls)               # functools.partial(LSTMAggregator, hidden_dim=...) and the like
     for name, k in (('mean', MeanAggregator), ('max_pool', MaxPoolAggregator), ('mean_pool', MeanPoolAggregator),
-                    ('attention', AttentionAggregator)):
+                    ('attention', AttentionAggregator), ('lstm', LSTMAggregator)):
         if cls is k:
             return name
     raise ValueError('gsage engine: unsupported aggregator class %r' % (cls,))
@@ -128,7 +129,8 @@ class GSSupervised(nn.Module):
                 cfg.emb_dev, cfg.emb_dtype, cfg.emb_ld = emb.data_ptr(), _lib.F32, emb.stride(0)
             cfg.emb_dim, cfg.n_nodes = self.prep.embedding_dim, self.n_nodes
         agg0 = self.agg_layers[0]
-        cfg.hidden_dim = agg0.mlp[0].out_features if hasattr(agg0, 'mlp') else (agg0.att[0].out_features if hasattr(agg0, 'att') else 0)
+        cfg.hidden_dim = (agg0.mlp[0].out_features if hasattr(agg0, 'mlp') else agg0.att[0].out_features if hasattr(agg0, 'att') else
+                          agg0.lstm.hidden_size if hasattr(agg0, 'lstm') else 0)
         cfg.max_batch = max(batch, self.max_batch)
         cfg.allow_tf32 = 1 if self.allow_tf32 else 0
         h = C.c_void_p()
@@ -155,6 +157,9 @@ class GSSupervised(nn.Module):
                 w.layer[k].mlp_w, w.layer[k].mlp_b = p(agg.mlp[0].weight), p(agg.mlp[0].bias)
             if hasattr(agg, 'att'):
                 w.layer[k].att_w1, w.layer[k].att_w2 = p(agg.att[0].weight), p(agg.att[2].weight)
+            if hasattr(agg, 'lstm'):
+                w.layer[k].lstm_w_ih, w.layer[k].lstm_w_hh = p(agg.lstm.weight_ih_l0), p(agg.lstm.weight_hh_l0)
+                w.layer[k].lstm_b_ih, w.layer[k].lstm_b_hh = p(agg.lstm.bias_ih_l0), p(agg.lstm.bias_hh_l0)
         w.fc_w, w.fc_b = p(self.fc.weight), p(self.fc.bias)
         if self._prep_name == 'node_embedding':
             w.prep_fc_w, w.prep_fc_b = p(self.prep.fc.weight), p(self.prep.fc.bias)
@@ -261,6 +266,8 @@ class GSSupervised(nn.Module):
         ranks of the default process group.  `dlogits` = d loss / d logits (B, n_classes) fp32 on the GPU.
         `grad_scale` weights this rank's contribution (local_batch / global_batch for a mean loss).
         The head (fc + layer 2) is all-reduced on `overlap_stream` while layer 1's weight gradients are computed."""
+        if self._agg_name == 'lstm':
+            raise NotImplementedError('gsage: the LSTM aggregator is forward-only (no backward through the recurrence is built)')
         bucket = self._bucket()
         g = _lib.Grads()
         aggs = list(self.agg_layers.children())

@@ -287,10 +287,51 @@ class AttentionAggregator(nn.Module, AggregatorMixin):
         return self._combine(x, x_ids, agg, n)
 
 
+class LSTMAggregator(nn.Module, AggregatorMixin):
+    """nn_modules.py:259-286: the S neighbour rows of every parent through a one-layer nn.LSTM in their sampled order; the LAST
+    hidden state is the aggregate.  `self.lstm` is a stock nn.LSTM used as the parameter holder (same state_dict keys, same
+    init order as the reference); the recurrence runs on the library's kernels: per step two projections + gsage_lstm_cell."""
+
+    def forward(self, x, neibs):
+        """x (N, d), neibs (N*S, d) row-major grouped by parent -> (N, 2*output_dim)."""
+        return self._forward_rows(x, neibs)
+
+    def __init__(self, input_dim, output_dim, activation, hidden_dim=512, bidirectional=False, combine_fn=_cat):
+        super(LSTMAggregator, self).__init__()
+        assert not hidden_dim % 2, "LSTMAggregator: hiddem_dim % 2 != 0"
+        if bidirectional:
+            raise NotImplementedError('gsage: LSTMAggregator(bidirectional=True) is not built (the registry default is False)')
+        self.lstm = nn.LSTM(input_dim, hidden_dim, bidirectional=False, batch_first=True)
+        self.fc_x = nn.Linear(input_dim, output_dim, bias=False)
+        self.fc_neib = nn.Linear(hidden_dim, output_dim, bias=False)
+        self.output_dim_ = output_dim
+        self.activation = activation
+        self.combine_fn = combine_fn
+
+    def _run(self, x, x_ids, nb, nb_ids, n, S):
+        H, dev = self.lstm.hidden_size, x.device
+        w_ih, w_hh = self.lstm.weight_ih_l0.data, self.lstm.weight_hh_l0.data
+        b_ih, b_hh = self.lstm.bias_ih_l0.data.contiguous(), self.lstm.bias_hh_l0.data.contiguous()
+        gx = torch.empty((n, 4 * H), dtype=torch.float32, device=dev)
+        gh = torch.empty_like(gx)
+        c = torch.empty((n, H), dtype=torch.float32, device=dev)
+        h = torch.empty_like(c)
+        ids_t = nb_ids.view(n, S).t().contiguous() if nb_ids is not None else None        # (S, n): step t's ids are one list
+        for t in range(S):
+            if ids_t is not None:
+                ops.linear([dict(a=nb, ids=ids_t[t], w=w_ih)], n, out=gx)
+            else:
+                ops.linear([dict(a=nb.view(n, S, -1)[:, t], w=w_ih)], n, out=gx)            # every S-th row, read in place
+            if t > 0:
+                ops.linear([dict(a=h, w=w_hh)], n, out=gh)
+            ops.lstm_cell(gx, gh if t > 0 else None, b_ih, b_hh, c, h, first=(t == 0))
+        return self._combine(x, x_ids, h, n)
+
+
 aggregator_lookup = {
     "mean": MeanAggregator,
     "max_pool": MaxPoolAggregator,
     "mean_pool": MeanPoolAggregator,
     "attention": AttentionAggregator,
-    # "lstm": out of scope (sequential RNN over an arbitrary neighbour order, not a reduction)
+    "lstm": LSTMAggregator,
 }

@@ -38,6 +38,7 @@ from scipy.sparse import csr_matrix              # noqa: E402
 import nn_modules as ref_nn                      # noqa: E402  (the reference)
 import models as ref_models                      # noqa: E402  (the reference)
 from torch.nn import functional as F             # noqa: E402
+from functools import partial                    # noqa: E402
 
 ref_nn.to_numpy = lambda t: t.detach().cpu().numpy()
 warnings.filterwarnings('ignore')
@@ -110,7 +111,7 @@ def gen_sampler_dense():
     save('sampler_dense', adj=adj, ids0=ids0, out1=out1, out2=out2, perm1=perm1, perm2=perm2, seed=np.int64(123))
 
 
-def gen_model(agg, prep, fanout=(25, 10), batch=12, d=20, n_nodes=400, with_feats=True, out_dims=(16, 12)):
+def gen_model(agg, prep, fanout=(25, 10), batch=12, d=20, n_nodes=400, with_feats=True, out_dims=(16, 12), agg_kwargs=None):
     adj = synth.make_sparse_adjacency(n_nodes, n_nodes * 9, alpha=1.4, clip=45, seed=17, isolated_frac=0.05)
     trip = synth.triplets(adj)
     A = ref_parse_csr(trip)
@@ -123,7 +124,8 @@ def gen_model(agg, prep, fanout=(25, 10), batch=12, d=20, n_nodes=400, with_feat
             dict(n_train_samples=fanout[0], n_val_samples=fanout[0], output_dim=out_dims[0], activation=F.relu),
             dict(n_train_samples=fanout[1], n_val_samples=fanout[1], output_dim=out_dims[1], activation=lambda x: x),
         ],
-        aggregator_class=ref_nn.aggregator_lookup[agg], prep_class=ref_nn.prep_lookup[prep],
+        aggregator_class=(partial(ref_nn.aggregator_lookup[agg], **agg_kwargs) if agg_kwargs else ref_nn.aggregator_lookup[agg]),
+        prep_class=ref_nn.prep_lookup[prep],
         sampler_class=ref_nn.sampler_lookup['sparse_uniform_neighbor_sampler'], adj=A, train_adj=A)
     model.eval()
     ids0 = np.concatenate([[0], synth.seed_batch(dict(n_nodes=A.shape[0]), batch - 1, seed=4)]).astype(np.int64)
@@ -140,7 +142,6 @@ def gen_model(agg, prep, fanout=(25, 10), batch=12, d=20, n_nodes=400, with_feat
             hops.append(out.numpy().copy())
             return out
     spy = Spy()
-    from functools import partial
     model.train_sample_fns = [partial(spy, n_samples=s) for s in fanout]
     hooks = [m.register_forward_hook(lambda mod, inp, out: layer_outs.append(out.detach().numpy().copy()))
              for m in model.agg_layers.children()]
@@ -182,7 +183,6 @@ def gen_model_dense(agg='mean', prep='identity', fanout=(25, 10), batch=12, d=20
     ids0 = np.concatenate([[n], rs.randint(0, n, batch - 1)]).astype(np.int64)
     hops, layer_outs = [], []
     real_sampler = model.train_sampler
-    from functools import partial
 
     def spy(ids, n_samples):
         out = real_sampler(ids=ids, n_samples=n_samples)
@@ -216,3 +216,6 @@ if __name__ == '__main__':
     gen_model('max_pool', 'node_embedding', with_feats=False)   # BASELINE config C3
     gen_model('attention', 'node_embedding', with_feats=False)
     gen_model_dense('mean', 'identity')                          # BASELINE config C1: train.py's default sampler
+    # LSTMAggregator (nn_modules.py:259-286) with a 64-wide hidden state (the default 512 would make a 9 MB fixture)
+    gen_model('lstm', 'identity', agg_kwargs=dict(hidden_dim=64))
+    gen_model('lstm', 'node_embedding', with_feats=False, agg_kwargs=dict(hidden_dim=64))

@@ -66,12 +66,17 @@ def test_registries_mirror_the_reference():
     import pytorch_graphsage_b200 as g
     assert set(g.sampler_lookup) == {'uniform_neighbor_sampler', 'sparse_uniform_neighbor_sampler'}
     assert set(g.prep_lookup) == {'identity', 'node_embedding', 'linear'}
-    assert set(g.aggregator_lookup) == {'mean', 'max_pool', 'mean_pool', 'attention'}
+    assert set(g.aggregator_lookup) == {'mean', 'max_pool', 'mean_pool', 'lstm', 'attention'}          # nn_modules.py:324-330
     agg = g.aggregator_lookup['max_pool'](input_dim=12, output_dim=7, activation=F.relu)
     assert agg.output_dim == 14                                       # AggregatorMixin.output_dim, nn_modules.py:178-182
     assert sorted(agg.state_dict()) == ['fc_neib.weight', 'fc_x.weight', 'mlp.0.bias', 'mlp.0.weight']
     att = g.aggregator_lookup['attention'](input_dim=12, output_dim=7, activation=None)
     assert sorted(att.state_dict()) == ['att.0.weight', 'att.2.weight', 'fc_neib.weight', 'fc_x.weight']
+    lstm = g.aggregator_lookup['lstm'](input_dim=12, output_dim=7, activation=None, hidden_dim=64)
+    assert sorted(lstm.state_dict()) == ['fc_neib.weight', 'fc_x.weight', 'lstm.bias_hh_l0', 'lstm.bias_ih_l0', 'lstm.weight_hh_l0',
+                                         'lstm.weight_ih_l0'] and lstm.output_dim == 14 and lstm.fc_neib.in_features == 64
+    with pytest.raises(NotImplementedError):
+        g.aggregator_lookup['lstm'](input_dim=12, output_dim=7, activation=None, bidirectional=True)
     prep = g.prep_lookup['node_embedding'](input_dim=5, n_nodes=10)
     assert prep.output_dim == 69 and prep.embedding.weight.shape == (11, 64)
     assert g.prep_lookup['node_embedding'](input_dim=None, n_nodes=10).output_dim == 64

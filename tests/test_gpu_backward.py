@@ -265,6 +265,22 @@ def test_fused_adam_on_the_embedding_recipe_keeps_every_parameter_aligned(g):
         assert p.grad.data_ptr() % 256 == 0
 
 
+def test_lstm_aggregator_is_forward_only(g):
+    """The LSTM aggregator completes the registry for inference; its backward is not built and says so."""
+    fix = util.load('model_lstm_identity')
+    from functools import partial
+    model = g.GSSupervised(
+        input_dim=fix['feats'].shape[1], n_nodes=int(fix['n_nodes']), n_classes=fix['logits'].shape[1],
+        layer_specs=[dict(n_train_samples=25, n_val_samples=25, output_dim=int(fix['out_dims'][0]), activation=F.relu),
+                     dict(n_train_samples=10, n_val_samples=10, output_dim=int(fix['out_dims'][1]), activation=lambda x: x)],
+        aggregator_class=partial(g.aggregator_lookup['lstm'], hidden_dim=64), prep_class=g.prep_lookup['identity'],
+        sampler_class=g.sampler_lookup['sparse_uniform_neighbor_sampler'], adj=g.GraphCSR.from_triplets(fix['trip']),
+        train_adj=g.GraphCSR.from_triplets(fix['trip'])).cuda()
+    targets = torch.zeros(fix['ids0'].shape[0], dtype=torch.int64).cuda()
+    with pytest.raises(NotImplementedError):
+        model.train_step(torch.from_numpy(fix['ids0']), torch.from_numpy(fix['feats']), targets, F.cross_entropy, optimizer=None, clip=None)
+
+
 def test_train_step_with_the_dense_sampler(g):
     """train.py's default configuration (dense sampler, mean, identity): gradients against autograd through the oracle."""
     fix = util.load('model_dense_mean_identity')

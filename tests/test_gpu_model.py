@@ -29,7 +29,7 @@ def build_model(g, fix, agg, prep, with_feats, compute_dtype=torch.float32, **kw
         input_dim=d, n_nodes=int(fix['n_nodes']), n_classes=fix['logits'].shape[1],
         layer_specs=[dict(n_train_samples=S1, n_val_samples=S1, output_dim=O1, activation=F.relu),
                      dict(n_train_samples=S2, n_val_samples=S2, output_dim=O2, activation=lambda x: x)],
-        aggregator_class=g.aggregator_lookup[agg], prep_class=g.prep_lookup[prep],
+        aggregator_class=util.aggregator_class(g, fix, agg), prep_class=g.prep_lookup[prep],
         sampler_class=g.sampler_lookup['sparse_uniform_neighbor_sampler'], adj=graph, train_adj=graph,
         compute_dtype=compute_dtype, **kw)
     missing = model.load_state_dict(util.params_of(fix), strict=True)      # the reference's own state_dict
@@ -70,7 +70,8 @@ def test_narrow_operator_api_matches_reference(g, agg, prep, with_feats):
 
 
 @pytest.mark.parametrize('agg,prep,with_feats', [('mean', 'identity', True), ('max_pool', 'identity', True),
-                                                 ('attention', 'identity', True), ('mean', 'node_embedding', False)])
+                                                 ('attention', 'identity', True), ('mean', 'node_embedding', False),
+                                                 ('lstm', 'identity', True)])
 def test_engine_bf16_compute(g, agg, prep, with_feats):
     fix = util.load(util.case_name(agg, prep, with_feats))
     model = build_model(g, fix, agg, prep, with_feats, compute_dtype=torch.bfloat16)

@@ -9,6 +9,7 @@ Tolerances (stated, per op):
 import numpy as np
 import pytest
 import torch
+from torch.nn import functional as F
 
 pytestmark = pytest.mark.gpu
 
@@ -238,6 +239,51 @@ def test_umma_tf32_projection(g, n, d, O):
     assert err > 0 or d < 8                       # it really ran in reduced precision (the FFMA path would be ~1e-6)
     exact = g.ops.linear(segs, n, act='relu', out_dtype=torch.float32, exact=True)
     np.testing.assert_allclose(exact.cpu().numpy(), want.numpy(), rtol=1e-4, atol=1e-5)
+
+
+@pytest.mark.parametrize('n,H,h_dtype', [(1, 8, torch.float32), (37, 64, torch.float32), (1000, 512, torch.float32), (129, 64, torch.bfloat16)])
+def test_lstm_cell_equals_torch(g, n, H, h_dtype):
+    """gsage_lstm_cell against torch.nn.LSTMCell's arithmetic (gate order i, f, g, o), three chained steps from the zero state."""
+    gen = torch.Generator().manual_seed(n + H)
+    b_ih, b_hh = torch.randn((4 * H,), generator=gen), torch.randn((4 * H,), generator=gen)
+    c_ref, h_ref = torch.zeros((n, H), dtype=torch.float64), torch.zeros((n, H), dtype=torch.float64)
+    c = torch.full((n, H), 7.0, device='cuda')                          # garbage: the first step must not read it
+    h = torch.full((n, H), 7.0, device='cuda').to(h_dtype)
+    for t in range(3):
+        gx, gh = torch.randn((n, 4 * H), generator=gen), torch.randn((n, 4 * H), generator=gen)
+        gates = gx.double() + b_ih.double() + b_hh.double() + (gh.double() if t > 0 else 0.0)
+        i, f, gg, o = gates[:, :H], gates[:, H:2 * H], gates[:, 2 * H:3 * H], gates[:, 3 * H:]
+        c_ref = torch.sigmoid(f) * c_ref + torch.sigmoid(i) * torch.tanh(gg)
+        h_ref = torch.sigmoid(o) * torch.tanh(c_ref)
+        g.ops.lstm_cell(gx.cuda(), gh.cuda() if t > 0 else None, b_ih.cuda(), b_hh.cuda(), c, h, first=(t == 0))
+        np.testing.assert_allclose(c.cpu().numpy(), c_ref.numpy(), rtol=1e-5, atol=1e-6)
+        tol = dict(rtol=1e-5, atol=1e-6) if h_dtype == torch.float32 else dict(rtol=1e-2, atol=1e-2)
+        np.testing.assert_allclose(h.float().cpu().numpy(), h_ref.numpy(), **tol)
+
+
+@pytest.mark.parametrize('n,S,d,H,gather', [(40, 10, 20, 64, True), (33, 25, 64, 32, False), (5, 3, 7, 8, True)])
+def test_lstm_aggregator_equals_torch_lstm(g, n, S, d, H, gather):
+    """operators.LSTMAggregator (narrow and id-taking entries) against the stock nn.LSTM it holds its parameters in
+    (nn_modules.py:276-279: batch_first, last hidden state)."""
+    torch.manual_seed(n + S)
+    agg = g.aggregator_lookup['lstm'](input_dim=d, output_dim=16, activation=F.relu, hidden_dim=H)
+    table = torch.randn((n * S + 50, d))
+    x = torch.randn((n, d))
+    with torch.no_grad():
+        if gather:
+            ids_self = torch.randint(0, table.shape[0], (n,))
+            ids_nb = torch.randint(0, table.shape[0], (n * S,))
+            xs, nb = table[ids_self], table[ids_nb]
+        else:
+            xs, nb = x, table[:n * S]
+        seq, _ = agg.lstm(nb.view(n, S, d))
+        want = F.relu(torch.cat([agg.fc_x(xs), agg.fc_neib(seq[:, -1])], dim=1))
+    agg = agg.cuda()
+    if gather:
+        got = agg.forward_ids(table.cuda(), ids_self.cuda(), ids_nb.cuda(), S)
+    else:
+        got = agg(xs.cuda(), nb.cuda())
+    np.testing.assert_allclose(got.cpu().numpy(), want.numpy(), rtol=1e-4, atol=1e-5)
 
 
 @pytest.mark.parametrize('n,d,O', [(300, 64, 128), (128 * 200 + 5, 64, 128), (1000, 100, 64), (129, 256, 32), (777, 64, 16)])

@@ -14,11 +14,22 @@ MODEL_CASES = [
     ('attention', 'identity', True), ('mean', 'linear', True), ('mean', 'node_embedding', True),
     ('mean', 'node_embedding', False), ('max_pool', 'node_embedding', False),
     ('attention', 'node_embedding', False),
+    ('lstm', 'identity', True), ('lstm', 'node_embedding', False),          # hidden_dim = 64 (fixture size)
 ]
 
 
 def case_name(agg, prep, with_feats):
     return 'model_%s_%s%s' % (agg, prep, '' if with_feats else '_nofeats')
+
+
+def aggregator_class(g, fix, agg):
+    """The registry class for `agg`; the LSTM fixtures were made with a 64-wide state (hidden_dim is a constructor keyword of the
+    reference's class too), so the width is read back from the stored weights."""
+    cls = g.aggregator_lookup[agg]
+    if agg == 'lstm':
+        from functools import partial
+        return partial(cls, hidden_dim=int(fix['w:agg_layers.0.lstm.weight_hh_l0'].shape[1]))
+    return cls
 
 
 def load(name):
