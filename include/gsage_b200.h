@@ -324,6 +324,16 @@ int gsage_wgrad(const void* g_dev, int g_dtype, int64_t ldg, int O, const void* 
 typedef struct gsage_embedding_grads { float* gx_raw; float* gn_raw; float* csum; float* d_table; } gsage_embedding_grads;
 int gsage_engine_backward_layer1_embedding(gsage_engine* e, const gsage_embedding_grads* g, void* stream);
 
+/* Layer-1 gradients of a mean-aggregator model behind LinearPrep (nn_modules.py:158-166: X = F Wp^T, no bias).  The prep is
+ * linear, so layer 1 = act([F_self (Wx Wp)^T | mean_j F_nb (Wn Wp)^T]) and every gradient follows from two reductions against
+ * the RAW feature rows:
+ *   gx_raw (O1, feats_dim) = Gx^T . F[self ids]          gn_raw (O1, feats_dim) = Gn^T . mean_j F[neighbour ids]
+ * (G as above; the neighbour means of the raw rows are gathered here -- the forward only ever reduced the 32-wide X rows).
+ * The caller finishes with three small products: dWx = gx_raw.Wp^T, dWn = gn_raw.Wp^T, dWp = Wx^T.gx_raw + Wn^T.gn_raw.
+ * Call after gsage_engine_backward_head.  Buffers fp32, overwritten. */
+typedef struct gsage_linear_prep_grads { float* gx_raw; float* gn_raw; } gsage_linear_prep_grads;
+int gsage_engine_backward_layer1_linear(gsage_engine* e, const gsage_linear_prep_grads* g, void* stream);
+
 /* Every parameter gradient of a max / mean pool model (bf16 compute, identity prep, output_dim 128) in one call; replaces
  * the _head / _layer1 pair for such models (nn_modules.py:207-256 through loss.backward(), models.py:101).  `pg`: gradients
  * of agg_layers.k.mlp.0.weight (hidden, d_in) / .bias (hidden).  All buffers fp32, overwritten. */

@@ -62,6 +62,10 @@ class EmbeddingGrads(C.Structure):
     _fields_ = [('gx_raw', c_p), ('gn_raw', c_p), ('csum', c_p), ('d_table', c_p)]
 
 
+class LinearPrepGrads(C.Structure):
+    _fields_ = [('gx_raw', c_p), ('gn_raw', c_p)]
+
+
 class Weights(C.Structure):
     _fields_ = [('layer', LayerWeights * 2), ('fc_w', c_p), ('fc_b', c_p), ('prep_fc_w', c_p), ('prep_fc_b', c_p),
                 ('prep_out_dim', C.c_int)]
@@ -120,6 +124,7 @@ _SIGNATURES = {
     'gsage_engine_backward_attention': (C.c_int, [c_p, c_p, C.POINTER(Grads), C.POINTER(AttentionGrads), c_p]),
     'gsage_engine_backward_pool_embedding': (C.c_int, [c_p, c_p, C.POINTER(Grads), C.POINTER(PoolGrads), C.POINTER(PoolEmbeddingGrads), c_p]),
     'gsage_engine_backward_layer1_embedding': (C.c_int, [c_p, C.POINTER(EmbeddingGrads), c_p]),
+    'gsage_engine_backward_layer1_linear': (C.c_int, [c_p, C.POINTER(LinearPrepGrads), c_p]),
     'gsage_wgrad': (C.c_int, [c_p, C.c_int, c_i64, C.c_int, c_p, C.c_int, c_i64, c_i64, c_p, C.c_int, c_i64, c_p, c_i64, C.c_int, c_p]),
     'gsage_adam_step': (C.c_int, [c_p, c_p, c_p, c_p, c_i64, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, c_i64, C.c_float, c_p, c_p]),
     'gsage_engine_keep_activations': (C.c_int, [c_p, C.c_int]),

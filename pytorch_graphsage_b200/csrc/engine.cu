@@ -142,6 +142,7 @@ struct gsage_engine {
     char* wb = nullptr; int64_t wb_bytes = 0;
     WRef w_x[2], w_n[2], w_mlp[2], w_att1[2], w_ih[2], w_hh[2];
     // LSTM aggregator: gate pre-activations of the current step (x part, h part), cell / hidden state, per-step id lists
+    void* MF = nullptr;                 // mean + LinearPrep backward: neighbour means of the RAW feature rows, (n0 + n1) x feats_ld
     float* LGX = nullptr; float* LGH = nullptr; float* LC = nullptr; void* LH = nullptr; int64_t* LIDS = nullptr;
     float* wsplit = nullptr; int64_t wsplit_floats = 0;      // fp32-exact mode: (hi, lo) tf32 halves of fc_x / fc_neib for the 3 x TF32 projection
     WRef w_nT[2], w_mlpT[2];            // pool backward (bf16): fc_neib^T (H x O) and mlp.0.weight^T (d_in x H), K-major
@@ -411,11 +412,12 @@ int gsage_engine_create(const gsage_engine_config* cfg, gsage_engine** out) {
     }
     int64_t o_LGX = -1, o_LGH = -1, o_LC = -1, o_LH = -1, o_LIDS = -1;
     if (cfg->aggregator == GSAGE_AGG_LSTM) {
-        GS_CHECK_ARG(e->hid % 8 == 0, "engine_create: the LSTM state width must be a multiple of 8");
+        if (e->hid % 8 != 0) { set_error("engine_create: the LSTM state width must be a multiple of 8 (got %d)", e->hid); delete e; return GSAGE_ERR_INVALID; }
         o_LGX = carve(4 * 4 * (int64_t)e->hid * e->n1); o_LGH = carve(4 * 4 * (int64_t)e->hid * e->n1);
         o_LC = carve(4 * (int64_t)e->hid * e->n1); o_LH = carve(es * (int64_t)e->hid * e->n1);
         o_LIDS = carve(8 * e->n2);
     }
+    const int64_t o_MF = (cfg->aggregator == GSAGE_AGG_MEAN && cfg->prep == GSAGE_PREP_LINEAR) ? carve(es * cfg->feats_ld * (e->n0 + e->n1)) : -1;
     const int64_t o_H1 = carve(es * e->ld_h1 * (e->n0 + e->n1));
     const int64_t o_Z = carve(4 * 2 * O2 * e->n0);
     const int64_t o_ZN = carve(4 * 2 * O2 * e->n0);
@@ -472,6 +474,7 @@ int gsage_engine_create(const gsage_engine_config* cfg, gsage_engine** out) {
     e->ids_slot[0] = e->ids; e->ids_slot[1] = (int64_t*)at(o_ids1); e->cur = 0; e->sel_ahead = (uint32_t*)at(o_sel1);
     e->X = at(o_X); e->M = at(o_M); e->HN = at(o_HN); e->Pp = at(o_P);
     e->T1 = at(o_T1); e->NA = at(o_NA); e->T1x = at(o_T1x); e->XA = at(o_XA); e->AW = (float*)at(o_AW);
+    e->MF = at(o_MF);
     e->LGX = (float*)at(o_LGX); e->LGH = (float*)at(o_LGH); e->LC = (float*)at(o_LC); e->LH = at(o_LH); e->LIDS = (int64_t*)at(o_LIDS);
     e->H1 = at(o_H1); e->Z = (float*)at(o_Z); e->ZN = (float*)at(o_ZN); e->LG = (float*)at(o_LG);
     e->LG2[0] = e->LG; e->LG2[1] = (float*)at(o_LGb);
@@ -1019,9 +1022,10 @@ int gsage_engine_forward_dense(gsage_engine* e, const int64_t* adj_dev, int64_t 
 static int backward_supported(gsage_engine* e) {
     GS_CHECK_ARG(e && e->have_weights && e->B > 0, "engine_backward: run gsage_engine_forward first");
     GS_CHECK_ARG(e->cfg.aggregator == GSAGE_AGG_MEAN &&
-                 (e->cfg.prep == GSAGE_PREP_IDENTITY || (e->cfg.prep == GSAGE_PREP_NODE_EMBEDDING && e->fold_prep && e->T == GSAGE_F32)),
-                 "engine_backward: implemented for the mean aggregator with the identity prep, or with the node_embedding prep "
-                 "without features in fp32 (the Pokec recipe); the other plug-ins are forward-only");
+                 (e->cfg.prep == GSAGE_PREP_IDENTITY || e->cfg.prep == GSAGE_PREP_LINEAR ||
+                  (e->cfg.prep == GSAGE_PREP_NODE_EMBEDDING && e->fold_prep && e->T == GSAGE_F32)),
+                 "engine_backward: implemented for the mean aggregator with the identity or linear prep, or with the node_embedding "
+                 "prep without features in fp32 (the Pokec recipe); the other plug-ins are forward-only");
     GS_CHECK_ARG(!e->fuse_mean, "engine_backward: needs the reduced rows the fused (GSAGE_FUSE_MEAN) layer never writes");
     GS_CHECK_ARG(e->keep_activations || e->chunk_parents == 0, "engine_backward: call gsage_engine_keep_activations(e, 1) before the forward");
     return GSAGE_OK;
@@ -1095,6 +1099,36 @@ int gsage_engine_backward_layer1(gsage_engine* e, const gsage_grads* g, void* st
     GS_TRY(wgrad_launch(e->DH, 2 * O1, O1, c.feats_dev, c.feats_dtype, c.feats_ld, e->ids, d, n0 + n1, g->fc_x[0], d, s));
     GS_TRY(wgrad_launch(e->DH + O1, 2 * O1, O1, e->M, e->T, e->ld_m, nullptr, d, n0 + n1, g->fc_neib[0], d, s));
     return mark_slot_done(e, s);          // the weight gradients gather self rows by id: the slot is busy until here
+}
+
+// Layer-1 gradients behind LinearPrep (nn_modules.py:158-166): see gsage_b200.h.  Two reductions against the raw feature rows;
+// the neighbour means of the raw rows are gathered here (one more pass of the fused gather+mean kernel over the table).
+int gsage_engine_backward_layer1_linear(gsage_engine* e, const gsage_linear_prep_grads* g, void* stream) {
+    GS_TRY(backward_supported(e));
+    GS_CHECK_ARG(e->cfg.prep == GSAGE_PREP_LINEAR && e->MF, "engine_backward_layer1_linear: not a mean + LinearPrep model");
+    GS_CHECK_ARG(g && g->gx_raw && g->gn_raw, "engine_backward_layer1_linear: NULL argument");
+    cudaStream_t s = as_stream(stream);
+    const gsage_engine_config& c = e->cfg;
+    const int64_t n0 = e->B, n1 = n0 * c.fanout[0];
+    const int O1 = c.out_dim[0], d = c.feats_dim, S1 = c.fanout[0], S2 = c.fanout[1];
+    const int64_t es = (int64_t)dtype_size(e->T);
+    const int64_t* ids1 = e->ids + n0; const int64_t* ids2 = ids1 + n1;
+    GS_TRY(gather_reduce_launch(c.feats_dev, c.feats_dtype, c.feats_ld, c.feats_rows, d, ids1, n0, S1, GSAGE_RED_MEAN, nullptr, e->MF, e->T,
+                                c.feats_ld, s));
+    GS_TRY(gather_reduce_launch(c.feats_dev, c.feats_dtype, c.feats_ld, c.feats_rows, d, ids2, n1, S2, GSAGE_RED_MEAN, nullptr,
+                                (char*)e->MF + n0 * c.feats_ld * es, e->T, c.feats_ld, s));
+    if (layer1_wgrad_on_tensor_cores(e)) {               // the head wrote G as bf16 (layer1_grad_kernel)
+        const __nv_bfloat16* dh = (const __nv_bfloat16*)e->DH;
+        WgradJob jobs[2] = {
+            {dh, GSAGE_BF16, 2 * (int64_t)O1, O1, c.feats_dev, c.feats_dtype, c.feats_ld, e->ids, d, n0 + n1, g->gx_raw, d, c.feats_rows},
+            {dh + O1, GSAGE_BF16, 2 * (int64_t)O1, O1, e->MF, e->T, c.feats_ld, nullptr, d, n0 + n1, g->gn_raw, d}};
+        GS_CHECK_ARG(wgrad_umma_eligible(jobs[0]) && wgrad_umma_eligible(jobs[1]), "engine_backward_layer1_linear: operands do not qualify for the tensor-core weight gradient");
+        GS_TRY(wgrad_umma_launch(jobs, 2, s));
+        return mark_slot_done(e, s);
+    }
+    GS_TRY(wgrad_launch(e->DH, 2 * O1, O1, c.feats_dev, c.feats_dtype, c.feats_ld, e->ids, d, n0 + n1, g->gx_raw, d, s));
+    GS_TRY(wgrad_launch(e->DH + O1, 2 * O1, O1, e->MF, e->T, c.feats_ld, nullptr, d, n0 + n1, g->gn_raw, d, s));
+    return mark_slot_done(e, s);
 }
 
 // Layer-1 gradients of the Pokec recipe (mean aggregator, NodeEmbeddingPrep without features, nn_modules.py:126-155):

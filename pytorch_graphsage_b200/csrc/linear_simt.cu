@@ -121,10 +121,11 @@ using namespace gsage;
 // stream-ordered scratch for the (hi, lo) weight halves of exact == 2 calls: a private pool that keeps its memory between
 // calls (the default pool hands everything back to the driver at every synchronisation point)
 static cudaMemPool_t split_pool() {
-    static cudaMemPool_t pool = nullptr;
+    static cudaMemPool_t pools[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaMemPool_t& pool = pools[dev & 63];                     // one pool per device of the process
     if (!pool) {
-        int dev = 0;
-        cudaGetDevice(&dev);
         cudaMemPoolProps props = {};
         props.allocType = cudaMemAllocationTypePinned;
         props.location.type = cudaMemLocationTypeDevice;

@@ -328,6 +328,8 @@ class GSSupervised(nn.Module):
                 bucket.all_reduce_head(grad_scale)
         if self._prep_name == 'node_embedding':
             self._backward_layer1_embedding(bucket, aggs[0])
+        elif self._prep_name == 'linear':
+            self._backward_layer1_linear(bucket, aggs[0])
         else:
             check(lib().gsage_engine_backward_layer1(self._last['h'], C.byref(g), ops.stream()))
         if overlap_stream is None:
@@ -336,6 +338,19 @@ class GSSupervised(nn.Module):
             bucket.all_reduce_tail(grad_scale)
             main.wait_stream(overlap_stream)
         return bucket
+
+    def _backward_layer1_linear(self, bucket, agg0):
+        """mean + LinearPrep (nn_modules.py:158-166): the library reduces G against the raw feature rows (self rows and neighbour
+        means); the three small products that turn the two (O x d) reductions into parameter gradients are done here."""
+        O, d = agg0.fc_x.weight.shape[0], self.prep.fc.weight.shape[1]
+        raw = torch.empty((2, O, d), dtype=torch.float32, device='cuda')
+        lg = _lib.LinearPrepGrads()
+        lg.gx_raw, lg.gn_raw = raw[0].data_ptr(), raw[1].data_ptr()
+        check(lib().gsage_engine_backward_layer1_linear(self._last['h'], C.byref(lg), ops.stream()))
+        Wp, Wx, Wn = self.prep.fc.weight.data, agg0.fc_x.weight.data, agg0.fc_neib.weight.data
+        bucket.grad_of(agg0.fc_x.weight).copy_(raw[0] @ Wp.t())
+        bucket.grad_of(agg0.fc_neib.weight).copy_(raw[1] @ Wp.t())
+        bucket.grad_of(self.prep.fc.weight).copy_(Wx.t() @ raw[0] + Wn.t() @ raw[1])
 
     def _backward_layer1_embedding(self, bucket, agg0):
         """The Pokec recipe (mean + NodeEmbeddingPrep without features): the library reduces over the 26*B parent rows and

@@ -307,12 +307,40 @@ def test_train_step_with_the_dense_sampler(g):
 
 
 def test_backward_rejects_unsupported_plugins(g):
-    fix = util.load('model_mean_linear')
-    model = build_model(g, fix, 'mean', 'linear', True)
+    fix = util.load('model_mean_node_embedding')            # node_embedding WITH features (cat[feats, emb]): forward-only
+    model = build_model(g, fix, 'mean', 'node_embedding', True)
     g.set_seeds(1)
     preds = model(torch.from_numpy(fix['ids0']), torch.from_numpy(fix['feats']))
     with pytest.raises(ValueError):
         model.backward(torch.zeros_like(preds))
+
+
+@pytest.mark.parametrize('dtype,tol', [(torch.float32, dict(rtol=2e-3, atol=2e-5)), (torch.bfloat16, dict(rtol=6e-2, atol=3e-3))])
+def test_gradients_behind_the_linear_prep_match_autograd(g, dtype, tol):
+    """mean aggregator + LinearPrep (nn_modules.py:158-166): every parameter gradient, prep.fc.weight included, against torch
+    autograd through the CPU oracle on the same sampled ids (gsage_engine_backward_layer1_linear + three small products)."""
+    fix = util.load('model_mean_linear')
+    model = build_model(g, fix, 'mean', 'linear', True, compute_dtype=dtype)
+    feats = torch.from_numpy(fix['feats'])
+    targets = torch.from_numpy(np.random.RandomState(0).randint(0, fix['logits'].shape[1], fix['ids0'].shape[0]))
+    g.set_seeds(int(fix['seed']))
+    preds, loss = model.train_step(torch.from_numpy(fix['ids0']), feats, targets.cuda(), F.cross_entropy, optimizer=None, clip=None)
+    assert np.array_equal(model.peek('ids2').cpu().numpy(), fix['ids2'])
+    hop_ids = [torch.from_numpy(fix[k]) for k in ('ids0', 'ids1', 'ids2')]
+    ps = {k: v.clone().requires_grad_(True) for k, v in util.params_of(fix).items()}
+    want_loss = F.cross_entropy(layers.forward_stack(hop_ids, feats, ps, aggregator='mean', prep='linear'), targets)
+    want_loss.backward()
+    if dtype == torch.float32:
+        assert abs(loss.item() - want_loss.item()) < 1e-4
+    assert 'prep.fc.weight' in dict(model.named_parameters())
+    for name, p in model.named_parameters():
+        got, want = p.grad.cpu().numpy().astype(np.float64), ps[name].grad.numpy().astype(np.float64)
+        if dtype == torch.float32:
+            np.testing.assert_allclose(got, want, err_msg=name, **tol)
+        else:       # bf16 tables / activations: direction and size of every gradient tensor (the bar of the other bf16 recipes)
+            cos = (got * want).sum() / (np.linalg.norm(got) * np.linalg.norm(want) + 1e-300)
+            ratio = np.linalg.norm(got) / (np.linalg.norm(want) + 1e-300)
+            assert cos >= 0.995 and abs(ratio - 1.0) <= 3e-2, '%s: cosine %.5f, norm ratio %.4f' % (name, cos, ratio)
 
 
 # ---- tensor-core weight gradient (wgrad_umma.cu): dW = G^T . A[ids], both operands row-major = MN-major tiles --------
