@@ -50,6 +50,7 @@ WORKLOADS = {
     'reddit-maxpool': ('reddit', 'max_pool', 'identity', 'bf16', True),      # max-pool on the reddit shape (trainable: identity prep)
     'plaw2m-attention': ('plaw2m', 'attention', 'identity', 'bf16', True),   # configs[3]
     'big10m': ('big10m', 'mean', 'identity', 'bf16', True),                   # configs[4]
+    'reddit-lstm': ('reddit', 'lstm', 'identity', 'bf16', True),              # LSTM aggregator (forward only; use --batch 2048)
     'tiny': ('tiny', 'mean', 'identity', 'f32', True),
 }
 
@@ -232,6 +233,11 @@ def reference_params(prob, seed=123):
         if prob['aggregator'] in ('max_pool', 'mean_pool'):
             mlp = nn.Linear(d, 512)
             params[pre + 'mlp.0.weight'], params[pre + 'mlp.0.bias'] = mlp.weight.data, mlp.bias.data
+            hid = 512
+        if prob['aggregator'] == 'lstm':
+            lstm = nn.LSTM(d, 512, batch_first=True)
+            for name in ('weight_ih_l0', 'weight_hh_l0', 'bias_ih_l0', 'bias_hh_l0'):
+                params[pre + 'lstm.' + name] = getattr(lstm, name).data
             hid = 512
         if prob['aggregator'] == 'attention':
             params[pre + 'att.0.weight'] = nn.Linear(d, 32, bias=False).weight.data
