@@ -148,10 +148,11 @@ int gsage_attention_aggregate(const void* table_dev, int dtype, int64_t ld, int6
                               const float* xa_dev, void* out_dev, int out_dtype, int64_t ld_out, void* stream);
 /* One time step of the LSTM aggregator's cell (nn_modules.py:266,276-278: nn.LSTM, one layer, unidirectional, batch_first):
  *   gates = gx + gh + b_ih + b_hh   (n x 4H fp32, torch's gate order i, f, g, o; gx = x_t . W_ih^T and gh = h_{t-1} . W_hh^T
- *                                    come from gsage_linear)
+ *                                    come from gsage_linear; separate row strides, so gx may be step t of a (n, S, 4H) block
+ *                                    projected in one go: gx_dev = block + t*4H, ldgx = S*4H)
  *   c = sigmoid(f) c + sigmoid(i) tanh(g);   h = sigmoid(o) tanh(c)          (c fp32 in place, h fp32 or bf16)
  * `first` != 0: zero initial state -- c is not read and gh is ignored (may be NULL). */
-int gsage_lstm_cell(const float* gx_dev, const float* gh_dev, int64_t ldg, const float* b_ih_dev, const float* b_hh_dev,
+int gsage_lstm_cell(const float* gx_dev, int64_t ldgx, const float* gh_dev, int64_t ldgh, const float* b_ih_dev, const float* b_hh_dev,
                     float* c_dev, void* h_dev, int h_dtype, int64_t ldh, int64_t n, int H, int first, void* stream);
 /* F.normalize(dim=1, eps=1e-12) (models.py:90), fp32 out */
 int gsage_l2_normalize(const void* x_dev, int dtype, int64_t ld, int64_t n, int d, float* out_dev, int64_t ld_out,

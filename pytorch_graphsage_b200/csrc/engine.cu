@@ -38,8 +38,6 @@ struct RowSrc {
 };
 
 // a weight matrix as a kernel will read it: the caller's fp32 tensor, or the engine's padded bf16 copy
-int transpose_ids_launch(const int64_t* ids, int64_t n, int S, int64_t* out, cudaStream_t s);      // lstm.cu
-
 struct WRef { const void* p; int dtype; int64_t ld; const float* hi = nullptr; const float* lo = nullptr; };   // hi/lo: tf32-exact split (fp32-exact mode)
 
 // fp32 (rows, cols) -> bf16 (rows, ld) with zero padding (the tcgen05 kernel wants 16-byte aligned bf16 rows)
@@ -141,9 +139,10 @@ struct gsage_engine {
     // weights as the kernels read them (fp32 originals, or bf16 copies when compute dtype is bf16)
     char* wb = nullptr; int64_t wb_bytes = 0;
     WRef w_x[2], w_n[2], w_mlp[2], w_att1[2], w_ih[2], w_hh[2];
-    // LSTM aggregator: gate pre-activations of the current step (x part, h part), cell / hidden state, per-step id lists
     void* MF = nullptr;                 // mean + LinearPrep backward: neighbour means of the RAW feature rows, (n0 + n1) x feats_ld
-    float* LGX = nullptr; float* LGH = nullptr; float* LC = nullptr; void* LH = nullptr; int64_t* LIDS = nullptr;
+    // LSTM aggregator: input half of the gates for all S steps of a block of parents (lgx_rows rows x 4H), recurrent half of the
+    // current step, cell / hidden state
+    float* LGX = nullptr; float* LGH = nullptr; float* LC = nullptr; void* LH = nullptr; int64_t lgx_rows = 0;
     float* wsplit = nullptr; int64_t wsplit_floats = 0;      // fp32-exact mode: (hi, lo) tf32 halves of fc_x / fc_neib for the 3 x TF32 projection
     WRef w_nT[2], w_mlpT[2];            // pool backward (bf16): fc_neib^T (H x O) and mlp.0.weight^T (d_in x H), K-major
     WRef w_xT0;                         // pool + folded node_embedding backward (bf16): (Wx.Wp)^T (emb_dim x O1), K-major
@@ -323,22 +322,24 @@ static int apply_aggregator(gsage_engine* e, int layer, const RowSrc& x, const R
     }
     case GSAGE_AGG_LSTM: {
         // nn_modules.py:276-279: the S neighbour rows of a parent, in sampled order, through a one-layer LSTM; the last hidden
-        // state is the aggregate.  Every step = two projections on the tensor cores (x_t . W_ih^T, h . W_hh^T; 4H gate
-        // columns each, fp32 out) + the cell update (lstm.cu).  Step t's rows: ids transposed into S contiguous lists, or --
-        // rows read in place -- a view of every S-th row.
+        // state is the aggregate.  For a block of parents: ONE projection x . W_ih^T over all their S rows (4H gate columns,
+        // fp32), then per step h . W_hh^T and the cell update (lstm.cu), which reads step t of the block with a row stride of
+        // S * 4H.  Parents are independent, so blocks (<= 2 GiB of gate rows) run one after the other.
         const int H = e->hid;
-        const int64_t G4 = 4 * (int64_t)H;
-        GS_CHECK_ARG(e->LGX && n <= e->n1 && n * S <= e->n2, "lstm aggregator: workspace too small for %lld parents x %d", (long long)n, S);
-        if (nb.ids) GS_TRY(transpose_ids_launch(nb.ids, n, S, e->LIDS, s));
-        RowSrc hrow{e->LH, T, H, n, nullptr, H};
-        for (int t = 0; t < S; ++t) {
-            RowSrc xt = nb;
-            if (nb.ids) xt.ids = e->LIDS + (int64_t)t * n;
-            else { xt.base = (const char*)nb.base + (int64_t)t * nb.ld * (int64_t)dtype_size(nb.dtype); xt.ld = nb.ld * S; xt.table_rows = n; }
-            GS_TRY(linear_call(xt, e->w_ih[layer], (int)G4, nullptr, n, GSAGE_ACT_NONE, e->LGX, GSAGE_F32, G4, 0, exact, s));
-            if (t > 0) GS_TRY(linear_call(hrow, e->w_hh[layer], (int)G4, nullptr, n, GSAGE_ACT_NONE, e->LGH, GSAGE_F32, G4, 0, exact, s));
-            GS_TRY(gsage_lstm_cell(e->LGX, e->LGH, G4, L.lstm_b_ih, L.lstm_b_hh, e->LC, e->LH, T, H, n, H, t == 0, s));
+        const int64_t G4 = 4 * (int64_t)H, esT = (int64_t)dtype_size(T);
+        GS_CHECK_ARG(e->LGX && n <= e->n1 && S <= e->lgx_rows, "lstm aggregator: workspace too small for %lld parents x %d", (long long)n, S);
+        const int64_t np_max = e->lgx_rows / S;
+        for (int64_t p0 = 0; p0 < n; p0 += np_max) {
+            const int64_t np = std::min(np_max, n - p0);
+            GS_TRY(linear_call(nb.shifted(p0 * S), e->w_ih[layer], (int)G4, nullptr, np * S, GSAGE_ACT_NONE, e->LGX, GSAGE_F32, G4, 0, exact, s));
+            RowSrc hc{(char*)e->LH + p0 * H * esT, T, H, np, nullptr, H};
+            for (int t = 0; t < S; ++t) {
+                if (t > 0) GS_TRY(linear_call(hc, e->w_hh[layer], (int)G4, nullptr, np, GSAGE_ACT_NONE, e->LGH, GSAGE_F32, G4, 0, exact, s));
+                GS_TRY(gsage_lstm_cell(e->LGX + (int64_t)t * G4, (int64_t)S * G4, e->LGH, G4, L.lstm_b_ih, L.lstm_b_hh, e->LC + p0 * H,
+                                       (char*)e->LH + p0 * H * esT, T, H, np, H, t == 0, s));
+            }
         }
+        RowSrc hrow{e->LH, T, H, n, nullptr, H};
         return combine_call(x, e->w_x[layer], hrow, e->w_n[layer], O, n, act, out, out_dtype, ld_out, exact, s, e->b_x[layer], nullptr);
     }
     }
@@ -410,12 +411,16 @@ int gsage_engine_create(const gsage_engine_config* cfg, gsage_engine** out) {
         o_T1x = carve(4 * e->hid * e->n1); o_XA = carve(4 * e->hid * e->n1);
         o_AW = carve(4 * e->n2);
     }
-    int64_t o_LGX = -1, o_LGH = -1, o_LC = -1, o_LH = -1, o_LIDS = -1;
+    int64_t o_LGX = -1, o_LGH = -1, o_LC = -1, o_LH = -1;
     if (cfg->aggregator == GSAGE_AGG_LSTM) {
         if (e->hid % 8 != 0) { set_error("engine_create: the LSTM state width must be a multiple of 8 (got %d)", e->hid); delete e; return GSAGE_ERR_INVALID; }
-        o_LGX = carve(4 * 4 * (int64_t)e->hid * e->n1); o_LGH = carve(4 * 4 * (int64_t)e->hid * e->n1);
+        // x_t . W_ih^T for every step of a block of parents at once: at most 2 GiB of gate rows, at least one parent
+        const int64_t row_bytes = 4 * 4 * (int64_t)e->hid;
+        e->lgx_rows = std::min<int64_t>(e->n2, std::max<int64_t>((int64_t(2) << 30) / row_bytes, std::max(cfg->fanout[0], cfg->fanout[1])));
+        if (const char* f = getenv("GSAGE_LSTM_BLOCK_ROWS"))          // tests: force several blocks on a tiny batch
+            e->lgx_rows = std::min<int64_t>(e->n2, std::max<int64_t>(atoll(f), std::max(cfg->fanout[0], cfg->fanout[1])));
+        o_LGX = carve(row_bytes * e->lgx_rows); o_LGH = carve(row_bytes * e->n1);
         o_LC = carve(4 * (int64_t)e->hid * e->n1); o_LH = carve(es * (int64_t)e->hid * e->n1);
-        o_LIDS = carve(8 * e->n2);
     }
     const int64_t o_MF = (cfg->aggregator == GSAGE_AGG_MEAN && cfg->prep == GSAGE_PREP_LINEAR) ? carve(es * cfg->feats_ld * (e->n0 + e->n1)) : -1;
     const int64_t o_H1 = carve(es * e->ld_h1 * (e->n0 + e->n1));
@@ -475,7 +480,7 @@ int gsage_engine_create(const gsage_engine_config* cfg, gsage_engine** out) {
     e->X = at(o_X); e->M = at(o_M); e->HN = at(o_HN); e->Pp = at(o_P);
     e->T1 = at(o_T1); e->NA = at(o_NA); e->T1x = at(o_T1x); e->XA = at(o_XA); e->AW = (float*)at(o_AW);
     e->MF = at(o_MF);
-    e->LGX = (float*)at(o_LGX); e->LGH = (float*)at(o_LGH); e->LC = (float*)at(o_LC); e->LH = at(o_LH); e->LIDS = (int64_t*)at(o_LIDS);
+    e->LGX = (float*)at(o_LGX); e->LGH = (float*)at(o_LGH); e->LC = (float*)at(o_LC); e->LH = at(o_LH);
     e->H1 = at(o_H1); e->Z = (float*)at(o_Z); e->ZN = (float*)at(o_ZN); e->LG = (float*)at(o_LG);
     e->LG2[0] = e->LG; e->LG2[1] = (float*)at(o_LGb);
     e->DXE = (float*)at(o_DXE); e->DZB = at(o_DZB);

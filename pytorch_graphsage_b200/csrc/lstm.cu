@@ -1,6 +1,7 @@
 // lstm.cu -- the pointwise half of the LSTM aggregator (nn_modules.py:259-286).  The two matrix products of every time step
 // (x_t . W_ih^T and h_{t-1} . W_hh^T, 4H gate columns each) run on the projection kernels; this file holds what is left:
-// the cell update and the id transposition that turns "neighbour j of parent p" into S contiguous id lists.
+// the cell update.  The input half of the gates is computed for ALL S steps of a block of parents in one projection (the
+// rows of a parent are adjacent, so step t of parent p is row p*S + t: a row stride of S*4H for the cell kernel).
 #include "common.cuh"
 
 namespace gsage {
@@ -11,7 +12,7 @@ __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf
 //   c' = sigmoid(f) c + sigmoid(i) tanh(g),   h' = sigmoid(o) tanh(c')
 // one thread per (row, 4 hidden units): float4 loads of the four gate quarters of gx (+ gh) and of both biases
 template <typename HT>
-__global__ void __launch_bounds__(256) lstm_cell_kernel(const float* __restrict__ gx, const float* __restrict__ gh, int64_t ldg,
+__global__ void __launch_bounds__(256) lstm_cell_kernel(const float* __restrict__ gx, int64_t ldgx, const float* __restrict__ gh, int64_t ldgh,
                                                         const float* __restrict__ b_ih, const float* __restrict__ b_hh,
                                                         float* __restrict__ c, HT* __restrict__ h, int64_t ldh, int64_t n, int H,
                                                         int first) {
@@ -23,12 +24,12 @@ __global__ void __launch_bounds__(256) lstm_cell_kernel(const float* __restrict_
     float g4[4][4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-        const float4 a = *reinterpret_cast<const float4*>(gx + r * ldg + (int64_t)k * H + u);
+        const float4 a = *reinterpret_cast<const float4*>(gx + r * ldgx + (int64_t)k * H + u);
         const float4 bi = __ldg(reinterpret_cast<const float4*>(b_ih + k * H + u));
         const float4 bh = __ldg(reinterpret_cast<const float4*>(b_hh + k * H + u));
         g4[k][0] = a.x + bi.x + bh.x; g4[k][1] = a.y + bi.y + bh.y; g4[k][2] = a.z + bi.z + bh.z; g4[k][3] = a.w + bi.w + bh.w;
         if (!first) {
-            const float4 b = *reinterpret_cast<const float4*>(gh + r * ldg + (int64_t)k * H + u);
+            const float4 b = *reinterpret_cast<const float4*>(gh + r * ldgh + (int64_t)k * H + u);
             g4[k][0] += b.x; g4[k][1] += b.y; g4[k][2] += b.z; g4[k][3] += b.w;
         }
     }
@@ -45,31 +46,16 @@ __global__ void __launch_bounds__(256) lstm_cell_kernel(const float* __restrict_
     for (int j = 0; j < 4; ++j) ElemTraits<HT>::store(ho + j, hh[j]);
 }
 
-// out[t * n + p] = ids[p * S + t]: the ids of time step t become one contiguous list (what the projection's gather takes)
-__global__ void __launch_bounds__(256) transpose_ids_kernel(const int64_t* __restrict__ ids, int64_t n, int S, int64_t* __restrict__ out) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n * S) return;
-    const int64_t p = i / S;
-    const int t = (int)(i % S);
-    out[(int64_t)t * n + p] = ids[i];
-}
-
-int transpose_ids_launch(const int64_t* ids, int64_t n, int S, int64_t* out, cudaStream_t s) {
-    if (n * S <= 0) return GSAGE_OK;
-    transpose_ids_kernel<<<(unsigned)ceil_div(n * S, 256), 256, 0, s>>>(ids, n, S, out);
-    GS_LAUNCHED();
-    return GSAGE_OK;
-}
-
 }  // namespace gsage
 
 using namespace gsage;
 
-extern "C" int gsage_lstm_cell(const float* gx_dev, const float* gh_dev, int64_t ldg, const float* b_ih_dev, const float* b_hh_dev,
+extern "C" int gsage_lstm_cell(const float* gx_dev, int64_t ldgx, const float* gh_dev, int64_t ldgh, const float* b_ih_dev, const float* b_hh_dev,
                                float* c_dev, void* h_dev, int h_dtype, int64_t ldh, int64_t n, int H, int first, void* stream) {
     GS_CHECK_ARG(gx_dev && b_ih_dev && b_hh_dev && c_dev && h_dev && n >= 0 && H > 0, "lstm_cell: bad arguments");
     GS_CHECK_ARG(first || gh_dev, "lstm_cell: the recurrent gates are missing");
-    GS_CHECK_ARG(H % 4 == 0 && ldg % 4 == 0 && ldg >= 4 * (int64_t)H && ldh >= H, "lstm_cell: H and the gate row stride must be multiples of 4");
+    GS_CHECK_ARG(H % 4 == 0 && ldgx % 4 == 0 && ldgx >= 4 * (int64_t)H && ldh >= H, "lstm_cell: H and the gate row strides must be multiples of 4");
+    GS_CHECK_ARG(first || (ldgh % 4 == 0 && ldgh >= 4 * (int64_t)H), "lstm_cell: bad row stride of the recurrent gates");
     GS_CHECK_ARG(h_dtype == GSAGE_F32 || h_dtype == GSAGE_BF16, "lstm_cell: bad h dtype");
     GS_CHECK_ARG(((uintptr_t)gx_dev & 15) == 0 && ((uintptr_t)gh_dev & 15) == 0 && ((uintptr_t)c_dev & 15) == 0 &&
                  ((uintptr_t)b_ih_dev & 15) == 0 && ((uintptr_t)b_hh_dev & 15) == 0, "lstm_cell: operands must be 16-byte aligned");
@@ -77,9 +63,9 @@ extern "C" int gsage_lstm_cell(const float* gx_dev, const float* gh_dev, int64_t
     cudaStream_t s = as_stream(stream);
     const unsigned grid = (unsigned)ceil_div(n * (H / 4), 256);
     if (h_dtype == GSAGE_F32)
-        lstm_cell_kernel<float><<<grid, 256, 0, s>>>(gx_dev, gh_dev, ldg, b_ih_dev, b_hh_dev, c_dev, (float*)h_dev, ldh, n, H, first ? 1 : 0);
+        lstm_cell_kernel<float><<<grid, 256, 0, s>>>(gx_dev, ldgx, gh_dev, ldgh, b_ih_dev, b_hh_dev, c_dev, (float*)h_dev, ldh, n, H, first ? 1 : 0);
     else
-        lstm_cell_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(gx_dev, gh_dev, ldg, b_ih_dev, b_hh_dev, c_dev, (__nv_bfloat16*)h_dev, ldh, n, H,
+        lstm_cell_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(gx_dev, ldgx, gh_dev, ldgh, b_ih_dev, b_hh_dev, c_dev, (__nv_bfloat16*)h_dev, ldh, n, H,
                                                              first ? 1 : 0);
     GS_LAUNCHED();
     return GSAGE_OK;

@@ -312,19 +312,15 @@ class LSTMAggregator(nn.Module, AggregatorMixin):
         H, dev = self.lstm.hidden_size, x.device
         w_ih, w_hh = self.lstm.weight_ih_l0.data, self.lstm.weight_hh_l0.data
         b_ih, b_hh = self.lstm.bias_ih_l0.data.contiguous(), self.lstm.bias_hh_l0.data.contiguous()
-        gx = torch.empty((n, 4 * H), dtype=torch.float32, device=dev)
-        gh = torch.empty_like(gx)
+        # x . W_ih^T for all S steps of every parent in one projection; step t of parent p is row p*S + t
+        gx = ops.linear([dict(a=nb, ids=nb_ids, w=w_ih)], n * S).view(n, S, 4 * H)
+        gh = torch.empty((n, 4 * H), dtype=torch.float32, device=dev)
         c = torch.empty((n, H), dtype=torch.float32, device=dev)
         h = torch.empty_like(c)
-        ids_t = nb_ids.view(n, S).t().contiguous() if nb_ids is not None else None        # (S, n): step t's ids are one list
         for t in range(S):
-            if ids_t is not None:
-                ops.linear([dict(a=nb, ids=ids_t[t], w=w_ih)], n, out=gx)
-            else:
-                ops.linear([dict(a=nb.view(n, S, -1)[:, t], w=w_ih)], n, out=gx)            # every S-th row, read in place
             if t > 0:
                 ops.linear([dict(a=h, w=w_hh)], n, out=gh)
-            ops.lstm_cell(gx, gh if t > 0 else None, b_ih, b_hh, c, h, first=(t == 0))
+            ops.lstm_cell(gx[:, t], gh if t > 0 else None, b_ih, b_hh, c, h, first=(t == 0))
         return self._combine(x, x_ids, h, n)
 
 

@@ -150,12 +150,13 @@ def attention_weights(na, xa, n_parents, S):
 
 def lstm_cell(gx, gh, b_ih, b_hh, c, h, first):
     """One LSTM time step in place (gsage_lstm_cell): gates = gx + gh + b_ih + b_hh (n, 4H) fp32, torch gate order i, f, g, o;
-    c (n, H) fp32 and h (n, H) fp32 | bf16 are updated.  first=True: zero initial state (c not read, gh ignored)."""
+    c (n, H) fp32 and h (n, H) fp32 | bf16 are updated.  first=True: zero initial state (c not read, gh ignored).
+    gx may be a strided view (step t of an (n, S, 4H) block)."""
     _bind_device(gx)
     n, H = c.shape
     assert gx.dtype == torch.float32 and c.dtype == torch.float32 and gx.shape[1] == 4 * H
-    check(lib().gsage_lstm_cell(ptr(gx), ptr(gh) if gh is not None else None, _rows2d(gx), ptr(b_ih), ptr(b_hh), ptr(c), ptr(h), dt(h),
-                                _rows2d(h), n, H, 1 if first else 0, stream()))
+    check(lib().gsage_lstm_cell(ptr(gx), _rows2d(gx), ptr(gh) if gh is not None else None, _rows2d(gh) if gh is not None else 0,
+                                ptr(b_ih), ptr(b_hh), ptr(c), ptr(h), dt(h), _rows2d(h), n, H, 1 if first else 0, stream()))
     return h
 
 

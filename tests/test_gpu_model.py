@@ -82,6 +82,18 @@ def test_engine_bf16_compute(g, agg, prep, with_feats):
     np.testing.assert_allclose(logits.cpu().numpy(), fix['logits'], rtol=3e-2, atol=3e-2)
 
 
+def test_lstm_engine_in_blocks_of_parents(g, monkeypatch):
+    """The LSTM aggregator projects the input half of the gates for a BLOCK of parents at once (<= 2 GiB of gate rows); with a
+    60-row block the 12-seed fixture runs as 6 + 50 + 6 blocks and must give the same logits."""
+    monkeypatch.setenv('GSAGE_LSTM_BLOCK_ROWS', '60')
+    fix = util.load('model_lstm_identity')
+    model = build_model(g, fix, 'lstm', 'identity', True)
+    g.set_seeds(int(fix['seed']))
+    logits = model(torch.from_numpy(fix['ids0']), torch.from_numpy(fix['feats']), train=True)
+    np.testing.assert_allclose(model.peek('layer2').cpu().numpy(), fix['l2'], rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose(logits.cpu().numpy(), fix['logits'], rtol=1e-4, atol=1e-5)
+
+
 def test_host_buffer_entry_point(g):
     """gsage_engine_forward_host: pinned host ids in, pinned host logits out (the e2e path bench.py times)."""
     fix = util.load('model_mean_identity')
