@@ -146,6 +146,12 @@ int gsage_attention_aggregate(const void* table_dev, int dtype, int64_t ld, int6
                               int64_t n_parents, int S,
                               const void* w1_dev, int w1_dtype, int64_t ldw, int H, const float* b1_dev, const float* w2_dev,
                               const float* xa_dev, void* out_dev, int out_dtype, int64_t ld_out, void* stream);
+/* EXPERIMENTAL (refuses unless the environment has GSAGE_FUSED_LAYER=1): the neighbour half of the mean aggregator in one
+ * kernel -- out[p, col0 : col0+O] = act( mean_j table[ids[p*S + j]] . W^T + bias ) (nn_modules.py:197-200) -- the reduced rows
+ * never travel through HBM.  bf16 table and W (O x d, O <= 128), S <= 32. */
+int gsage_gather_mean_project(const void* table_dev, int dtype, int64_t ld, int64_t n_table_rows, int d, const int64_t* ids_dev,
+                              int64_t n_parents, int S, const void* w_dev, int w_dtype, int64_t ldw, int O, const float* bias_dev,
+                              int act, void* out_dev, int out_dtype, int64_t ld_out, int64_t col0, void* stream);
 /* One time step of the LSTM aggregator's cell (nn_modules.py:266,276-278: nn.LSTM, one layer, unidirectional, batch_first):
  *   gates = gx + gh + b_ih + b_hh   (n x 4H fp32, torch's gate order i, f, g, o; gx = x_t . W_ih^T and gh = h_{t-1} . W_hh^T
  *                                    come from gsage_linear; separate row strides, so gx may be step t of a (n, S, 4H) block

@@ -101,6 +101,8 @@ _SIGNATURES = {
     'gsage_attention_weights': (C.c_int, [c_p, c_p, C.c_int, c_i64, C.c_int, c_i64, C.c_int, c_p, c_p]),
     'gsage_attention_aggregate': (C.c_int, [c_p, C.c_int, c_i64, c_i64, C.c_int, c_p, c_i64, C.c_int, c_p, C.c_int, c_i64, C.c_int, c_p, c_p, c_p, c_p,
                                             C.c_int, c_i64, c_p]),
+    'gsage_gather_mean_project': (C.c_int, [c_p, C.c_int, c_i64, c_i64, C.c_int, c_p, c_i64, C.c_int, c_p, C.c_int, c_i64, C.c_int, c_p, C.c_int, c_p,
+                                            C.c_int, c_i64, c_i64, c_p]),
     'gsage_lstm_cell': (C.c_int, [c_p, c_i64, c_p, c_i64, c_p, c_p, c_p, c_p, C.c_int, c_i64, c_i64, C.c_int, C.c_int, c_p]),
     'gsage_l2_normalize': (C.c_int, [c_p, C.c_int, c_i64, c_i64, C.c_int, c_p, c_i64, c_p]),
     'gsage_linear': (C.c_int, [C.POINTER(LinearSeg), C.c_int, c_i64, C.c_int, c_p, C.c_int, c_i64, C.c_int, c_p]),

@@ -253,6 +253,26 @@ static int apply_aggregator(gsage_engine* e, int layer, const RowSrc& x, const R
         }
         // the stopwatch covers the dominant launch only (layer 1 on the (x1, x2) pair: n = B*S1 parents)
         const bool dominant = layer == 0 && n > e->B;
+        if (T == GSAGE_BF16 && !e->keep_activations && e->w_n[layer].dtype == GSAGE_BF16 && out_dtype == GSAGE_BF16 &&
+            gather_mean_project_eligible(nb.base, nb.dtype, nb.ld, d, S, e->w_n[layer].p, GSAGE_BF16, e->w_n[layer].ld, O)) {
+            // EXPERIMENTAL, GSAGE_FUSED_LAYER=1 (forward only: the reduced rows M are never written, so no backward): the
+            // neighbour half gather + mean + projection in one kernel, the self half as a one-segment projection
+            const int p_f = dominant ? e->prof.begin(GSAGE_PROF_REDUCE, s) : -1;
+            GS_TRY(gather_mean_project_launch(nb.base, nb.ld, nb.table_rows, d, nb.ids, n, S, e->w_n[layer].p, e->w_n[layer].ld, O,
+                                              e->b_n[layer], act, out, out_dtype, ld_out, O, s));
+            e->prof.end(p_f, s);
+            if (p_f >= 0) e->prof.bytes[GSAGE_PROF_REDUCE] += (double)n * ((double)S * d * dtype_size(nb.dtype) + (nb.ids ? 8.0 * S : 0.0) + (double)O * dtype_size(out_dtype));
+            if (dominant && e->ahead_after_gather) {
+                if (!e->ev_mid) GS_CUDA(cudaEventCreateWithFlags(&e->ev_mid, cudaEventDisableTiming));
+                GS_CUDA(cudaEventRecord(e->ev_mid, s));
+                e->mid_valid = true;
+            }
+            const int p_prj = dominant ? e->prof.begin(GSAGE_PROF_PROJECT, s) : -1;
+            const int st = linear_call(x, e->w_x[layer], O, e->b_x[layer], n, act, out, out_dtype, ld_out, 0, exact, s);
+            e->prof.end(p_prj, s);
+            if (p_prj >= 0) e->prof.bytes[GSAGE_PROF_PROJECT] += 2.0 * (double)n * d * O;
+            return st;
+        }
         const int p_red = dominant ? e->prof.begin(GSAGE_PROF_REDUCE, s) : -1;
         GS_TRY(gather_reduce_launch(nb.base, nb.dtype, nb.ld, nb.table_rows, d, nb.ids, n, S, GSAGE_RED_MEAN, nullptr, Mb, T, ldm, s,
                                     (e->l2_hint && !e->keep_activations) ? 1 : 0));

@@ -148,6 +148,17 @@ def attention_weights(na, xa, n_parents, S):
     return w
 
 
+def gather_mean_project(table, ids, n_parents, S, w, bias=None, act=None, out=None, col0=0, out_dtype=torch.bfloat16):
+    """EXPERIMENTAL (GSAGE_FUSED_LAYER=1): act(mean_j table[ids[p*S+j]] . w^T + bias) in one kernel (gsage_gather_mean_project)."""
+    _bind_device(table)
+    if out is None:
+        out = torch.empty((n_parents, col0 + w.shape[0]), dtype=out_dtype, device=table.device)
+    check(lib().gsage_gather_mean_project(ptr(table), dt(table), _rows2d(table), table.shape[0], table.shape[1], _ids_arg(ids), n_parents, S,
+                                          ptr(w), dt(w), _rows2d(w), w.shape[0], ptr(bias), _lib.ACT[act], ptr(out), dt(out), _rows2d(out),
+                                          col0, stream()))
+    return out
+
+
 def lstm_cell(gx, gh, b_ih, b_hh, c, h, first):
     """One LSTM time step in place (gsage_lstm_cell): gates = gx + gh + b_ih + b_hh (n, 4H) fp32, torch gate order i, f, g, o;
     c (n, H) fp32 and h (n, H) fp32 | bf16 are updated.  first=True: zero initial state (c not read, gh ignored).
