@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define GSAGE_ABI_VERSION 1
+#define GSAGE_ABI_VERSION 2   /* 2: gsage_layer_weights gained the LSTM weights, gsage_linear_seg.a_rows, new entry points */
 
 typedef enum gsage_status {
     GSAGE_OK = 0,

@@ -155,7 +155,7 @@ def lib():
             fn = getattr(handle, name)          # AttributeError if the header and the library disagree
             fn.restype = res
             fn.argtypes = args
-        if handle.gsage_abi_version() != 1:
+        if handle.gsage_abi_version() != 2:
             raise GsageError('libgsage_b200.so ABI mismatch')
         _lib = handle
     return _lib
