@@ -2,7 +2,7 @@
 """
 bench.py -- the headline measurement (BASELINE.json metric: sampled+aggregated nodes/sec; gather HBM GB/s vs peak).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload reddit] [--batch B]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload reddit] [--batch B] [--legs ...]
 
 A "step" is one pass of the hot path (sample both hops -> gather -> aggregate -> project, two layers, normalise,
 classifier) over one batch of B seed nodes per GPU on a synthetic problem of the named shape.  Default workload =
@@ -15,6 +15,10 @@ Ours (`--impl ours`):
   e2e     same metric through the host-buffer entry (pinned host ids in, pinned host logits out every step)
   roofline  the fused gather+aggregate kernel: algorithmic bytes / live CUDA-event time vs measured HBM peak
   cpu_baseline  the oracle port of the reference's CPU path, bounded sample, timed here on the host cores
+  configs the other BASELINE.json configs as short legs of the same run (`--legs`, default all): pokec-mean (the north-star
+          60 % target shape), pokec-maxpool (configs[2], bf16 and tf32), plaw2m-attention (configs[3]), big10m (configs[4]) --
+          each with value, ms/step, the dominant kernel's roofline and, where a backward exists, a train-step leg (forward +
+          loss + backward + gradient all-reduce over the N ranks + clip + Adam)
 Reference arm (`--impl reference`): the oracle port of the reference's CPU implementation (the reference is
 Python-2-era and cannot travel to the GPU box; oracle/ restates it and is pinned against it by the golden
 fixtures) timed on the host cores with all torch threads.
@@ -47,12 +51,19 @@ WORKLOADS = {
     'pokec-mean': ('pokec', 'mean', 'node_embedding', 'f32', False),  # north-star 60 % target shape
     'pokec-mean-tf32': ('pokec', 'mean', 'node_embedding', 'tf32', False),    # same, projections as TF32 on tcgen05
     'pokec-maxpool': ('pokec', 'max_pool', 'node_embedding', 'bf16', False),  # configs[2] (bf16 compute: the MLP is tensor-bound)
+    'pokec-maxpool-tf32': ('pokec', 'max_pool', 'node_embedding', 'tf32', False),   # configs[2] on fp32 tables (TF32 tensor-core products)
     'reddit-maxpool': ('reddit', 'max_pool', 'identity', 'bf16', True),      # max-pool on the reddit shape (trainable: identity prep)
     'plaw2m-attention': ('plaw2m', 'attention', 'identity', 'bf16', True),   # configs[3]
+    'plaw2m-attention-tf32': ('plaw2m', 'attention', 'identity', 'tf32', True),   # configs[3] on an fp32 table (TF32 products)
     'big10m': ('big10m', 'mean', 'identity', 'bf16', True),                   # configs[4]
     'reddit-lstm': ('reddit', 'lstm', 'identity', 'bf16', True),              # LSTM aggregator (forward only; use --batch 2048)
     'tiny': ('tiny', 'mean', 'identity', 'f32', True),
 }
+
+# the legs of the default run: (workload, seeds per step per GPU, timed steps); the first is the headline line
+DEFAULT_LEGS = [('pokec-mean', 32768, 40), ('pokec-maxpool', 16384, 40), ('plaw2m-attention', 16384, 40), ('big10m', 16384, 40)]
+# workloads whose feature table is generated on the device (a host copy would be 10 GB of fp32 for big10m)
+DEVICE_FEATS = ('plaw2m', 'big10m')
 
 
 def parse_args():
@@ -70,6 +81,8 @@ def parse_args():
     ap.add_argument('--torch-adam', action='store_true', help='train leg: torch.optim.Adam + clip_grad_norm_ instead of the fused native step')
     ap.add_argument('--no-ahead', action='store_true', help='sample inside each forward instead of one batch ahead on the sampler stream')
     ap.add_argument('--scale', type=float, default=1.0, help='shrink the graph (debug only; reported in config)')
+    ap.add_argument('--legs', default='default', help="'default' (the other BASELINE configs as short legs), 'none', or a comma list of "
+                                                      "workload[:batch[:steps]]; only with the default workload")
     return ap.parse_args()
 
 
@@ -84,25 +97,94 @@ def measured_peaks():
     return 6650.0, 'fallback (B200_PROFILING.md 6.65 TB/s)'
 
 
+def measured_tensor_peak():
+    """Dense bf16 TFLOP/s for a kernel timed inside a long step: the SUSTAINED cuBLAS figure of MEASURED_PEAKS.json."""
+    path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(path):
+        try:
+            p = json.load(open(path))
+            return float(p['bf16_tflops_sustained']), 'measured (MEASURED_PEAKS.json bf16_tflops_sustained)'
+        except Exception:
+            pass
+    return 1500.0, 'fallback (B200_PROFILING.md ~1.5 PFLOP/s sustained dense bf16)'
+
+
 class ClockSampler(object):
-    """nvidia-smi clocks + throttle reasons DURING the timed region (B200_PROFILING.md clocks line)."""
+    """SM clock + throttle reasons DURING the timed region (B200_PROFILING.md clocks line).  NVML from a thread of this process
+    (pynvml ships with the image): an `nvidia-smi -lms` child needs a second or more to come up on an 8-GPU box, longer than the
+    timed region under torchrun -- round 1's SCALE lines carried 0 samples for that reason.  Falls back to nvidia-smi."""
     Q = 'index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,' \
         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
 
-    def __init__(self, index):
-        self.index, self.proc, self.path = index, None, '/tmp/gsage_clocks_%d.csv' % os.getpid()
+    def __init__(self, uuid, index):
+        self.uuid, self.index = uuid, index
+        self.proc, self.thread, self.stop_flag = None, None, False
+        self.sm, self.reasons, self.power, self.sm_max = [], set(), [], None
+        self.path = '/tmp/gsage_clocks_%d.csv' % os.getpid()
+        self.how = None
+
+    def _nvml_handle(self):
+        import pynvml
+        pynvml.nvmlInit()
+        try:
+            return pynvml, pynvml.nvmlDeviceGetHandleByUUID(self.uuid.encode() if isinstance(self.uuid, str) else self.uuid)
+        except Exception:
+            return pynvml, pynvml.nvmlDeviceGetHandleByIndex(self.index)
+
+    def prepare(self):
+        """Everything slow (NVML init) happens here, before the barrier in front of the timed region."""
+        try:
+            self.nv, self.h = self._nvml_handle()
+            self.sm_max = float(self.nv.nvmlDeviceGetMaxClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+            self.how = 'nvml'
+        except Exception:
+            self.how = 'nvidia-smi'
+
+    def _loop(self):
+        nv, h = self.nv, self.h
+        names = (('hw_slowdown', getattr(nv, 'nvmlClocksEventReasonHwSlowdown', 0x8)),
+                 ('hw_thermal_slowdown', getattr(nv, 'nvmlClocksEventReasonHwThermalSlowdown', 0x40)),
+                 ('sw_thermal_slowdown', getattr(nv, 'nvmlClocksEventReasonSwThermalSlowdown', 0x20)),
+                 ('sw_power_cap', getattr(nv, 'nvmlClocksEventReasonSwPowerCap', 0x4)))
+        reasons_fn = getattr(nv, 'nvmlDeviceGetCurrentClocksEventReasons', None) or getattr(nv, 'nvmlDeviceGetCurrentClocksThrottleReasons')
+        while not self.stop_flag:
+            try:
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+                self.power.append(nv.nvmlDeviceGetPowerUsage(h) / 1e3)
+                bits = int(reasons_fn(h))
+                for name, bit in names:
+                    if bits & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.004)
 
     def start(self):
+        if self.how is None:
+            self.prepare()
+        if self.how == 'nvml':
+            import threading
+            self.stop_flag = False
+            self.thread = threading.Thread(target=self._loop, daemon=True)
+            self.thread.start()
+            return
         try:
             self.fh = open(self.path, 'w')
-            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q, '--format=csv,noheader,nounits',
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.uuid), '--query-gpu=' + self.Q, '--format=csv,noheader,nounits',
                                           '-lms', '20'], stdout=self.fh, stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
 
     def stop(self):
+        if self.how == 'nvml':
+            self.stop_flag = True
+            self.thread.join(timeout=2)
+            sm = sorted(self.sm)
+            return {'sm_mhz': (sm[len(sm) // 2] if sm else None), 'sm_max_mhz': self.sm_max,
+                    'power_w_max': (max(self.power) if self.power else None), 'samples': len(sm), 'reasons': sorted(self.reasons),
+                    'source': 'nvml thread, 4 ms period, inside the timed region'}
         if self.proc is None:
-            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable'], 'samples': 0}
         self.proc.terminate()
         try:
             self.proc.wait(timeout=5)
@@ -124,17 +206,39 @@ class ClockSampler(object):
         os.remove(self.path)
         sm.sort()
         return {'sm_mhz': (sm[len(sm) // 2] if sm else None), 'sm_max_mhz': (max(mx) if mx else None),
-                'power_w_max': (max(power) if power else None), 'samples': len(sm), 'reasons': sorted(reasons)}
+                'power_w_max': (max(power) if power else None), 'samples': len(sm), 'reasons': sorted(reasons), 'source': 'nvidia-smi -lms 20'}
 
 
 # ---------------------------------------------------------------------------------------------------
-def make_problem(args):
+def make_problem(workload, scale=1.0, host_feats=True):
+    """The synthetic problem of a workload.  `host_feats` False: the feature table of the big shapes is left out here and drawn
+    on the device (device_table) -- same distribution (N(0,1), row 0 = zeros), different generator."""
     from pytorch_graphsage_b200 import synth
-    shape, agg, prep, dtype, with_feats = WORKLOADS[args.workload]
+    shape, agg, prep, dtype, with_feats = WORKLOADS[workload]
     t0 = time.time()
-    prob = synth.make_problem(shape, seed=0, with_feats=with_feats, scale=args.scale)
-    prob.update(aggregator=agg, prep=prep, table_dtype=dtype, build_s=time.time() - t0)
+    on_device = with_feats and not host_feats and shape in DEVICE_FEATS
+    prob = synth.make_problem(shape, seed=0, with_feats=with_feats and not on_device, scale=scale)
+    if on_device:
+        prob['feats_dim'] = synth.SHAPES[shape]['d']
+    prob.update(aggregator=agg, prep=prep, table_dtype=dtype, build_s=time.time() - t0, feats_on_device=on_device, workload=workload)
     return prob
+
+
+def device_table(prob, dtype):
+    """(n_nodes, d) N(0,1) feature table drawn on the GPU in row chunks straight into the padded layout (row 0 = the dummy's zeros)."""
+    import torch
+    import pytorch_graphsage_b200 as g
+    rows, d = prob['n_nodes'], prob['feats_dim']
+    per = 16 // (2 if dtype == torch.bfloat16 else 4)
+    ld = (d + 2 * per - 1) // (2 * per) * (2 * per)
+    store = torch.zeros((rows, ld), dtype=dtype, device='cuda')
+    gen = torch.Generator(device='cuda').manual_seed(7919)
+    step = 1 << 20
+    for lo in range(0, rows, step):
+        hi = min(rows, lo + step)
+        store[lo:hi, :d] = torch.randn((hi - lo, d), generator=gen, device='cuda', dtype=torch.float32).to(dtype)
+    store[0].zero_()
+    return g.FeatureTable.from_store(store, d)
 
 
 def layer_specs():
@@ -143,19 +247,19 @@ def layer_specs():
             dict(n_train_samples=FANOUT[1], n_val_samples=FANOUT[1], output_dim=OUT_DIMS[1], activation=lambda x: x)]
 
 
-def workload_config(args, prob):
+def workload_config(workload, prob, batch, gpus, scale=1.0, ahead=True):
     s = prob['adj']
     return {'workload': '%s: %d nodes / %d edges / d=%s, %s aggregator, %s prep, fanout [25,10], out 128,128, %s table' %
-                        (args.workload, s['n_nodes'], s['nnz'], prob['feats_dim'] or 64, prob['aggregator'], prob['prep'],
+                        (workload, s['n_nodes'], s['nnz'], prob['feats_dim'] or 64, prob['aggregator'], prob['prep'],
                          prob['table_dtype']),
-            'batch_seeds_per_gpu': args.batch, 'rows_per_seed': ROWS_PER_SEED, 'graph_scale': args.scale,
+            'batch_seeds_per_gpu': batch, 'rows_per_seed': ROWS_PER_SEED, 'graph_scale': scale,
             'sampler': 'sparse_uniform_neighbor_sampler (device MT19937, bit-exact numpy legacy stream)',
             'l2_policy': 'inputs larger than L2 (table %.0f MB + per-step gather footprint); no flush' %
                          ((s['n_nodes'] + 1) * (prob['feats_dim'] or 64) * (2 if prob['table_dtype'] == 'bf16' else 4) / 1e6),
-            'pipeline': ('none: every forward samples its own batch' if getattr(args, 'no_ahead', False) else
+            'pipeline': ('none: every forward samples its own batch' if not ahead else
                          'sample-ahead: the draws + CSR lookups of batch i+1 run on a second stream under the aggregation of batch i; '
                          'every timed step still samples one batch and aggregates one batch'),
-            'parallelism': 'seed-sharded dp%d, graph+table replicated, no data-path collective' % max(1, args.gpus)}
+            'parallelism': 'seed-sharded dp%d, graph+table replicated, no data-path collective' % max(1, gpus)}
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -255,13 +359,14 @@ def run_reference(args):
     if RANK != 0:
         return
     import torch
-    prob = make_problem(args)
+    prob = make_problem(args.workload, args.scale, host_feats=True)
     value, ms, steps = cpu_reference_throughput(prob, args.cpu_batch, args.steps, args.warmup)
     cores = torch.get_num_threads()
     line = {'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': steps,
             'warmup': args.warmup, 'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
             'dtype': 'f32', 'data': 'synthetic',
-            'config': dict(workload_config(args, prob), batch_seeds_per_step=args.cpu_batch, pipeline='n/a (the reference\'s CPU path)'),
+            'config': dict(workload_config(args.workload, prob, args.batch, args.gpus, args.scale), batch_seeds_per_step=args.cpu_batch,
+                           pipeline='n/a (the reference\'s CPU path)'),
             'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': cores, 'kind': 'port',
                              'sample': '%d steps x %d seeds (oracle port of nn_modules.py/models.py CPU path, torch %d threads of %d cpus)' %
                                        (steps, args.cpu_batch, cores, os.cpu_count())},
@@ -271,25 +376,77 @@ def run_reference(args):
 
 
 # ---------------------------------------------------------------------------------------------------
-def run_ours(args):
+def barrier():
+    import torch
+    import torch.distributed as dist
+    torch.cuda.synchronize()
+    if WORLD > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+
+
+def max_over_ranks(x):
+    import torch
+    import torch.distributed as dist
+    if WORLD == 1:
+        return x
+    t = torch.tensor([x], dtype=torch.float64, device='cuda')
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def dominant_roofline(prob, prof, label_timed_in, traffic=None):
+    """The `roofline` object of a leg from the engine's live stopwatch (GSAGE_PROF_REDUCE = the dominant aggregate launch)."""
+    ms, n, byt, flo = prof['reduce']
+    if not n or ms <= 0:
+        return None
+    agg = prob['aggregator']
+    if agg in ('max_pool', 'mean_pool'):
+        peak, src = measured_tensor_peak()
+        dtype_note = ''
+        if prob['table_dtype'] != 'bf16':
+            peak, dtype_note = peak / 2.0, ' / 2 (TF32 runs at half the bf16 rate)'
+        achieved = (flo / 1e12) / (ms / 1e3)
+        return {'bound': 'tensor', 'kernel': 'linear_pool_ws_umma_kernel: relu(W1 n + b1) on tcgen05 + the pool over the S rows in the epilogue, '
+                                             'layer 1 on the (x1, x2) pair (B*25 parents, S=10)',
+                'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s', 'frac': achieved / peak, 'traffic': traffic,
+                'peak_source': src + dtype_note, 'launches': int(n), 'algorithmic_flops_per_launch_avg': flo / n,
+                'algorithmic_bytes_per_launch_avg': byt / n, 'hbm_gbs_algorithmic': (byt / 1e9) / (ms / 1e3), 'avg_launch_ms': ms / n,
+                'timed_in': label_timed_in}
+    peak, src = measured_peaks()
+    achieved = (byt / 1e9) / (ms / 1e3)
+    kernel = ('attention_fused_kernel: scores on tcgen05, softmax + weighted sum of the S neighbour rows on chip' if agg == 'attention'
+              else 'the fused gather+mean launch') + ', layer 1 on the (x1, x2) pair (B*25 parents, S=10)'
+    return {'bound': 'hbm', 'kernel': kernel, 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
+            'traffic': traffic, 'peak_source': src, 'launches': int(n), 'algorithmic_bytes_per_launch_avg': byt / n,
+            'avg_launch_ms': ms / n, 'timed_in': label_timed_in}
+
+
+def trainable(prob, dtype, tf32):
+    import torch
+    return (prob['aggregator'] == 'mean' and (prob['prep'] == 'identity' or (prob['prep'] == 'node_embedding' and dtype == torch.float32 and not tf32))) or \
+           (prob['aggregator'] in ('max_pool', 'mean_pool') and dtype == torch.bfloat16) or \
+           (prob['aggregator'] == 'attention' and prob['prep'] == 'identity' and dtype == torch.bfloat16)
+
+
+def run_leg(args, workload, B, steps, warmup, main):
+    """One workload on this rank's GPU: device-timed steps, (main leg only) the end-to-end host-buffer leg, the train-step leg.
+    Returns the leg's result dict on every rank (timings are max over ranks)."""
+    import gc
     import numpy as np
     import torch
     import torch.distributed as dist
     import pytorch_graphsage_b200 as g
     from pytorch_graphsage_b200 import synth
 
-    torch.cuda.set_device(LOCAL_RANK)                                         # one process per GPU
-    if WORLD > 1:
-        if os.environ.get('NCCL_DEBUG', '').upper() not in ('INFO', 'TRACE'):
-            os.environ['NCCL_DEBUG'] = 'WARN'                                  # keep stdout to the one JSON line
-        dist.init_process_group('nccl', device_id=torch.device('cuda', LOCAL_RANK))
-
-    prob = make_problem(args)
-    B = args.batch
+    prob = make_problem(workload, args.scale, host_feats=main)
     dtype = torch.bfloat16 if prob['table_dtype'] == 'bf16' else torch.float32
     tf32 = prob['table_dtype'] == 'tf32'
     graph = g.GraphCSR.from_synth(prob['adj'])
-    table = g.FeatureTable(prob['feats'], dtype) if prob['feats'] is not None else None
+    if prob['feats_on_device']:
+        table = device_table(prob, dtype)
+    else:
+        table = g.FeatureTable(prob['feats'], dtype) if prob['feats'] is not None else None
     model = g.GSSupervised(
         input_dim=prob['feats_dim'], n_nodes=prob['n_nodes'], n_classes=prob['n_classes'], layer_specs=layer_specs(),
         aggregator_class=g.aggregator_lookup[prob['aggregator']], prep_class=g.prep_lookup[prob['prep']],
@@ -301,61 +458,47 @@ def run_ours(args):
 
     n_batches = 8                                                               # rotate seed batches: no step reuses hot rows
     dev_ids = [torch.from_numpy(synth.seed_batch(prob, B, seed=17 * RANK + i)).cuda() for i in range(n_batches)]
-    host_ids = [torch.from_numpy(synth.seed_batch(prob, B, seed=17 * RANK + i)).pin_memory() for i in range(n_batches)]
-    host_out = torch.empty((B, prob['n_classes']), dtype=torch.float32).pin_memory()
 
-    def barrier():
-        torch.cuda.synchronize()
-        if WORLD > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def max_over_ranks(x):
-        if WORLD == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device='cuda')
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
-
-    # ---- device-resident timing -----------------------------------------------------------------------------
     ahead = not args.no_ahead
     step_no = [0]
 
     def step():
         i = step_no[0]
         step_no[0] += 1
-        out = model(dev_ids[i % n_batches], table)
-        if ahead:                                                                # batch i+1 is drawn while batch i aggregates
-            model.sample_ahead(dev_ids[(i + 1) % n_batches], table)
-        return out
+        # batch i+1 is drawn while batch i aggregates: its ids exist before this forward is queued (next_ids)
+        return model(dev_ids[i % n_batches], table, next_ids=dev_ids[(i + 1) % n_batches] if ahead else None)
 
     if ahead:
         model.sample_ahead(dev_ids[0], table)
-    for i in range(max(3, args.warmup)):
+    for i in range(max(3, warmup)):
         step()
     g.default_rng().check()
     graph.check()
     model.profile(True)
-    try:
-        gpu_sel = 'GPU-' + str(torch.cuda.get_device_properties(LOCAL_RANK).uuid)
-    except Exception:
-        gpu_sel = str(LOCAL_RANK)
-    clocks = ClockSampler(gpu_sel)
+    clocks = None
+    if main:
+        try:
+            uuid = 'GPU-' + str(torch.cuda.get_device_properties(LOCAL_RANK).uuid)
+        except Exception:
+            uuid = str(LOCAL_RANK)
+        clocks = ClockSampler(uuid, LOCAL_RANK)
+        clocks.prepare()
     barrier()
-    clocks.start()
+    if clocks:
+        clocks.start()
     launches0 = g.launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
-    for i in range(args.steps):
+    for i in range(steps):
         step()
     ev1.record()
     barrier()
     launches = g.launch_count() - launches0
-    clk = clocks.stop()
+    clk = clocks.stop() if clocks else None
     ms_total = max_over_ranks(ev0.elapsed_time(ev1))
     prof = model.profile_read()
     g.default_rng().check()
-    ms_step = ms_total / args.steps
+    ms_step = ms_total / steps
     value = WORLD * B * ROWS_PER_SEED / (ms_step / 1e3)
 
     # the dominant kernel alone: a few steps WITHOUT sample-ahead, so that no sampler kernel shares the SMs with it
@@ -366,40 +509,80 @@ def run_ours(args):
         step_no[0] += 1
         torch.cuda.synchronize()
         model.profile_read()
-        for i in range(20):
+        for i in range(10):
             model(dev_ids[(step_no[0] + i) % n_batches], table)
         torch.cuda.synchronize()
         prof_iso = model.profile_read()
-        step_no[0] += 20
+        step_no[0] += 10
     model.profile(False)
 
-    # ---- end to end through the host-buffer entry -----------------------------------------------------------------
-    def host_step(i):                                                          # synchronises every step (D2H of the logits)
-        nxt = host_ids[(i + 1) % n_batches] if ahead else None
-        model.forward_host(host_ids[i % n_batches], table, host_out, next_ids_host=nxt)
+    res = {'workload': workload, 'value': value, 'unit': UNIT, 'ms_per_step': ms_step, 'steps': steps, 'seeds_per_s': value / ROWS_PER_SEED,
+           'dtype': 'bf16' if dtype == torch.bfloat16 else ('tf32' if tf32 else 'f32'),
+           'config': workload_config(workload, prob, B, WORLD, args.scale, ahead), 'gpu_launches': int(launches) * WORLD,
+           'n_gpus': WORLD}
+    traffic, traffic_src = None, None
+    tpath = os.path.join(ROOT, 'profiles', 'traffic.json')
+    if os.path.exists(tpath):
+        tj = json.load(open(tpath))
+        traffic = tj.get('%s:%d' % (workload, B))
+        traffic_src = 'static: one `ncu --set full` capture of this kernel on this shape (profiles/traffic.json), not measured in this run'
+    timed_in = ('the pipelined steps above (its launches share the SMs with the next batch\'s sampling kernels)' if ahead
+                else 'the timed steps above')
+    res['roofline'] = dominant_roofline(prob, prof, timed_in, traffic)
+    if res['roofline'] is not None:
+        res['roofline']['traffic_source'] = traffic_src
+        if prof_iso is not None and prof_iso['reduce'][1]:
+            iso = dominant_roofline(prob, prof_iso, 'n/a')
+            res['roofline']['isolated'] = {'achieved': iso['achieved'], 'frac': iso['frac'], 'launches': iso['launches'],
+                                           'avg_launch_ms': iso['avg_launch_ms'],
+                                           'note': 'same kernel, same inputs, 10 steps without sample-ahead (nothing else on the SMs)'}
+    per = lambda k: prof[k][0] / steps
+    res['breakdown_ms_per_step'] = {
+        'forward': per('forward'), 'wait_for_sampled_batch': per('wait'), 'layer1_x0x1': per('app0'), 'dominant_aggregate': per('reduce'),
+        'project': per('project'), 'layer2': per('layer2'), 'normalize_classifier': per('head'),
+        'sample_on_sampler_stream': per('sample'),
+        'project_tflops': (prof['project'][3] / 1e12) / (prof['project'][0] / 1e3) if prof['project'][0] > 0 else None,
+        'project_gbs_algorithmic': (prof['project'][2] / 1e9) / (prof['project'][0] / 1e3) if prof['project'][0] > 0 else None}
+    # whole-step HBM roofline (algorithmic bytes per seed of the mean path)
+    if prob['aggregator'] == 'mean':
+        e = 2 if dtype == torch.bfloat16 else 4
+        d = prob['feats_dim'] or 64
+        per_seed = 276 * d * e + 26 * 16 + 275 * 8 + 275 * 16 + 26 * 2 * 128 * e + 27 * 2 * 128 * e
+        peak, _ = measured_peaks()
+        gbs = per_seed * B / (ms_step / 1e3) / 1e9                              # per GPU (every rank runs B seeds per step)
+        res['step_roofline'] = {'bound': 'hbm', 'algorithmic_bytes_per_seed': per_seed, 'achieved': gbs, 'peak': peak, 'unit': 'GB/s',
+                                'frac': gbs / peak, 'note': 'the WHOLE step against the HBM roofline (SURVEY.md 8d bytes per seed), per GPU'}
+    if clk is not None:
+        res['clocks'] = clk
 
-    for i in range(3):
-        host_step(i)
-    barrier()
-    t0 = time.perf_counter()
-    ev0.record()
-    for i in range(3, 3 + args.steps):
-        host_step(i)
-    ev1.record()
-    barrier()
-    if ahead:
-        model.forward_host(host_ids[(3 + args.steps) % n_batches], table, host_out)   # drain the pending batch
-    e2e_ms = max_over_ranks(max(ev0.elapsed_time(ev1), 0.0)) / args.steps
-    e2e_wall_ms = max_over_ranks((time.perf_counter() - t0) * 1e3) / args.steps
-    e2e_ms = max(e2e_ms, e2e_wall_ms)
-    e2e_value = WORLD * B * ROWS_PER_SEED / (e2e_ms / 1e3)
+    # ---- end to end through the host-buffer entry (main leg) ------------------------------------------------------
+    if main:
+        host_ids = [torch.from_numpy(synth.seed_batch(prob, B, seed=17 * RANK + i)).pin_memory() for i in range(n_batches)]
+        host_out = torch.empty((B, prob['n_classes']), dtype=torch.float32).pin_memory()
+
+        def host_step(i):                                                          # synchronises every step (D2H of the logits)
+            nxt = host_ids[(i + 1) % n_batches] if ahead else None
+            model.forward_host(host_ids[i % n_batches], table, host_out, next_ids_host=nxt)
+
+        for i in range(3):
+            host_step(i)
+        barrier()
+        t0 = time.perf_counter()
+        ev0.record()
+        for i in range(3, 3 + steps):
+            host_step(i)
+        ev1.record()
+        barrier()
+        if ahead:
+            model.forward_host(host_ids[(3 + steps) % n_batches], table, host_out)   # drain the pending batch
+        e2e_ms = max_over_ranks(max(ev0.elapsed_time(ev1), 0.0)) / steps
+        e2e_wall_ms = max_over_ranks((time.perf_counter() - t0) * 1e3) / steps
+        e2e_ms = max(e2e_ms, e2e_wall_ms)
+        res['e2e'] = {'value': WORLD * B * ROWS_PER_SEED / (e2e_ms / 1e3), 'unit': UNIT, 'h2d_bytes_per_step': 8 * B,
+                      'd2h_bytes_per_step': 4 * B * prob['n_classes'], 'ms_per_step': e2e_ms}
 
     # ---- one optimiser step per batch (forward + loss + backward + gradient all-reduce + clip + Adam) ---------------
-    train = None
-    trainable = (prob['aggregator'] == 'mean' and (prob['prep'] == 'identity' or (prob['prep'] == 'node_embedding' and dtype == torch.float32 and not tf32))) or \
-                (prob['aggregator'] in ('max_pool', 'mean_pool') and dtype == torch.bfloat16) or \
-                (prob['aggregator'] == 'attention' and prob['prep'] == 'identity' and dtype == torch.bfloat16)
-    if trainable and not args.no_train:
+    if trainable(prob, dtype, tf32) and not args.no_train:
         from torch.nn import functional as F
         if prob['task'] == 'regression_mae':                                       # problem.py:39-41: l1 loss on (B, 1) predictions
             tgt_all = torch.from_numpy(prob['targets']).cuda()
@@ -408,14 +591,19 @@ def run_ours(args):
             tgt_all = torch.from_numpy(prob['targets'].reshape(-1)).cuda()
             loss_fn = F.cross_entropy
         tgts = [tgt_all[i] for i in dev_ids]
-        # clip_grad_norm 5 + Adam as one native call over flat buffers (parallel.FusedAdam); --torch-adam: the stock pair
-        opt = torch.optim.Adam(model.parameters(), lr=0.01) if args.torch_adam else g.FusedAdam(model, lr=0.01)
+        # clip_grad_norm 5 + Adam as one native call over flat buffers (the model's own parallel.FusedAdam); --torch-adam: the stock pair
+        opt = torch.optim.Adam(model.parameters(), lr=0.01) if args.torch_adam else None
         side = torch.cuda.Stream()
-        k_train = max(3, min(args.steps, 30))
+        k_train = max(3, min(steps, 30))
+
         def train_step(i):
             model.train_step(dev_ids[i % n_batches], table, tgts[i % n_batches], loss_fn, optimizer=opt, grad_scale=1.0 / WORLD,
                              overlap_stream=side, next_ids=dev_ids[(i + 1) % n_batches] if ahead else None)
 
+        if ahead and model.optimizer.flat is None and opt is None:
+            model.optimizer._materialize()                                         # (re-creates the engines: before the first sample-ahead)
+        if ahead:
+            model.sample_ahead(dev_ids[0], table)
         for i in range(3):
             train_step(i)
         barrier()
@@ -427,53 +615,74 @@ def run_ours(args):
         if ahead:
             model(dev_ids[(3 + k_train) % n_batches], table)                       # drain the pending batch
         t_ms = max_over_ranks(ev0.elapsed_time(ev1)) / k_train
-        train = {'ms_per_step': t_ms, 'seeds_per_s': WORLD * B / (t_ms / 1e3), 'steps': k_train,
-                 'allreduce_bytes_per_step': int(model._bucket().flat.numel()) * 4,
-                 'collective': 'one flat fp32 gradient bucket, NCCL all-reduce in two pieces (fc + layer-2 head overlapped with the '
-                               'layer-1 weight-gradient kernels)' if WORLD > 1 else 'none (1 GPU)',
-                 'note': 'loss is stock torch; clip + Adam are ' + ('stock torch' if args.torch_adam else 'one native call (gsage_adam_step)')}
+        res['train'] = {'ms_per_step': t_ms, 'seeds_per_s': WORLD * B / (t_ms / 1e3), 'value': WORLD * B * ROWS_PER_SEED / (t_ms / 1e3), 'steps': k_train,
+                        'allreduce_bytes_per_step': int(model._bucket().flat.numel()) * 4,
+                        'collective': ('one flat fp32 gradient bucket, NCCL sum all-reduce over %d ranks (mean aggregator: in two pieces, the fc + '
+                                       'layer-2 head overlapped with the layer-1 weight-gradient kernels)' % WORLD) if WORLD > 1 else 'none (1 GPU)',
+                        'note': 'loss is stock torch; clip + Adam are ' + ('stock torch' if args.torch_adam else 'one native call (gsage_adam_step)')}
+    model.check()
+    del model, table, graph, dev_ids
+    gc.collect()
+    torch.cuda.empty_cache()
+    res['_prob'] = prob
+    return res
+
+
+def parse_legs(args):
+    if args.workload != 'reddit' or args.legs == 'none':
+        return []
+    if args.legs == 'default':
+        return list(DEFAULT_LEGS)
+    legs = []
+    for item in args.legs.split(','):
+        f = item.split(':')
+        legs.append((f[0], int(f[1]) if len(f) > 1 else 16384, int(f[2]) if len(f) > 2 else 40))
+    return legs
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    torch.cuda.set_device(LOCAL_RANK)                                         # one process per GPU
+    if WORLD > 1:
+        if os.environ.get('NCCL_DEBUG', '').upper() not in ('INFO', 'TRACE'):
+            os.environ['NCCL_DEBUG'] = 'WARN'                                  # keep stdout to the one JSON line
+        dist.init_process_group('nccl', device_id=torch.device('cuda', LOCAL_RANK))
+
+    main = run_leg(args, args.workload, args.batch, args.steps, args.warmup, main=True)
+    prob = main.pop('_prob')
+    legs = {}
+    for workload, B, steps in parse_legs(args):
+        t0 = time.time()
+        try:
+            leg = run_leg(args, workload, B, steps, 3, main=False)
+            leg.pop('_prob')
+            leg['wall_s_incl_setup'] = time.time() - t0
+        except Exception as exc:                                               # a leg that cannot run must not take the headline with it
+            if WORLD > 1:
+                raise
+            leg = {'workload': workload, 'error': '%s: %s' % (type(exc).__name__, exc)}
+        legs[workload] = leg
 
     if RANK != 0:
         if WORLD > 1:
             dist.destroy_process_group()
         return
 
-    peak, peak_src = measured_peaks()
-    red_ms, red_n, red_bytes = prof['reduce']
-    prj_ms, prj_n, prj_flops = prof['project']
-    achieved = (red_bytes / 1e9) / (red_ms / 1e3) if red_ms > 0 else None
-    traffic = None
-    tpath = os.path.join(ROOT, 'profiles', 'traffic.json')
-    if os.path.exists(tpath):
-        traffic = json.load(open(tpath)).get('%s:%d' % (args.workload, B))
     line = {
-        'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': WORLD, 'steps': args.steps, 'warmup': max(3, args.warmup),
-        'ms_per_step': ms_step, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
-        'dtype': 'bf16' if dtype == torch.bfloat16 else ('tf32' if tf32 else 'f32'), 'data': 'synthetic',
-        'config': workload_config(args, prob), 'clocks': clk,
-        'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': 8 * B, 'd2h_bytes_per_step': 4 * B * prob['n_classes'],
-                'ms_per_step': e2e_ms},
-        'gpu_launches': int(launches) * WORLD,
-        'seeds_per_s': value / ROWS_PER_SEED,
-        'roofline': {'bound': 'hbm', 'kernel': 'gather_reduce_kernel, the fused gather+mean launch of layer 1 on the (x1, x2) pair (B*25 parents, S=10)',
-                     'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': (achieved / peak if achieved else None),
-                     'traffic': traffic, 'peak_source': peak_src, 'launches': int(red_n),
-                     'algorithmic_bytes_per_launch_avg': (red_bytes / red_n if red_n else None),
-                     'avg_launch_ms': (red_ms / red_n if red_n else None),
-                     'timed_in': 'the pipelined steps above (its launches share the SMs with the next batch\'s sampling kernels)' if ahead
-                                 else 'the timed steps above'},
-        'breakdown_ms_per_step': {'forward': prof['forward'][0] / args.steps, 'sample': prof['sample'][0] / args.steps,
-                                  'gather_reduce': red_ms / args.steps, 'project': prj_ms / args.steps,
-                                  # fused build: the projection runs inside the gather+aggregate kernel (no time of its own)
-                                  'project_tflops': (prj_flops / 1e12) / ((prj_ms if prj_ms > 0 else red_ms) / 1e3) if (prj_ms + red_ms) > 0 else None},
+        'metric': METRIC, 'value': main['value'], 'unit': UNIT, 'n_gpus': WORLD, 'steps': args.steps, 'warmup': max(3, args.warmup),
+        'ms_per_step': main['ms_per_step'], 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+        'dtype': main['dtype'], 'data': 'synthetic', 'config': main['config'], 'clocks': main.get('clocks'),
+        'e2e': main['e2e'], 'gpu_launches': main['gpu_launches'], 'seeds_per_s': main['seeds_per_s'],
+        'roofline': main['roofline'], 'breakdown_ms_per_step': main['breakdown_ms_per_step'],
     }
-    if prof_iso is not None and prof_iso['reduce'][0] > 0:
-        ims, inn, iby = prof_iso['reduce']
-        line['roofline']['isolated'] = {'achieved': (iby / 1e9) / (ims / 1e3), 'frac': (iby / 1e9) / (ims / 1e3) / peak, 'launches': int(inn),
-                                        'avg_launch_ms': ims / inn,
-                                        'note': 'same kernel, same inputs, 20 steps without sample-ahead (nothing else on the SMs)'}
-    if train is not None:
-        line['train'] = train
+    if 'step_roofline' in main:
+        line['step_roofline'] = main['step_roofline']
+    if 'train' in main:
+        line['train'] = main['train']
+    if legs:
+        line['configs'] = legs
     if not args.no_cpu_baseline:
         v, ms, steps = cpu_reference_throughput(prob, args.cpu_batch, None, 2, seconds=args.cpu_seconds)
         line['cpu_baseline'] = {'value': v, 'unit': UNIT, 'cores': torch.get_num_threads(), 'kind': 'port',

@@ -27,7 +27,9 @@
 extern "C" {
 #endif
 
-#define GSAGE_ABI_VERSION 2   /* 2: gsage_layer_weights gained the LSTM weights, gsage_linear_seg.a_rows, new entry points */
+#define GSAGE_ABI_VERSION 3   /* 2: gsage_layer_weights gained the LSTM weights, gsage_linear_seg.a_rows, new entry points
+                               * 3: gsage_engine_profile_read reports bytes AND flops over 8 categories; gsage_engine_inputs_ready,
+                               *    gsage_engine_poll_errors, narrow-API backward kernels, metric kernels */
 
 typedef enum gsage_status {
     GSAGE_OK = 0,
@@ -292,6 +294,19 @@ int gsage_engine_forward_host_next(gsage_engine* e, gsage_graph* g, gsage_rng* r
                                    const int64_t* next_ids_host, int64_t next_B, float* logits_host, void* stream);
 /* 1 while a sampled-ahead batch waits for its forward */
 int gsage_engine_sample_ahead_pending(const gsage_engine* e);
+/* Ordering of gsage_engine_sample_ahead against the producer of `ids_dev` (e.g. the index kernel of problem.iterate,
+ * problem.py:149-152, or an H2D copy on `stream`): the sampler stream waits for an event on the caller's stream before it
+ * copies the ids.  By default that event is recorded when gsage_engine_sample_ahead is called -- always correct, but it also
+ * covers the forward queued just before, so nothing overlaps.  A caller that already holds the next batch's ids when it
+ * queues the CURRENT forward calls gsage_engine_inputs_ready first (ids complete on `stream` -> forward -> sample_ahead):
+ * the event is then the one recorded here and the sampling overlaps that forward.  One-shot: consumed by the next
+ * gsage_engine_sample_ahead. */
+int gsage_engine_inputs_ready(gsage_engine* e, void* stream);
+/* Non-blocking look at the sticky error flags (they live in mapped host memory) of the graph / rng of the last forward:
+ * GSAGE_ERR_INDEX if an earlier forward saw an id outside the adjacency (where `feats[ids]`, models.py:76, raises
+ * IndexError; cleared on report), GSAGE_ERR_RNG if the rng's look-ahead window ran short.  No synchronisation: it reports
+ * what has REACHED the host, i.e. typically the forward before the one in flight. */
+int gsage_engine_poll_errors(gsage_engine* e);
 /* device views of the last forward's intermediates (valid until the next forward): hop ids and layer outputs.
  * what: 0 ids0, 1 ids1, 2 ids2 (int64) ; 10 layer-1 output (26B x 2*O1) ; 11 layer-2 output (B x 2*O2) */
 int gsage_engine_peek(gsage_engine* e, int what, const void** ptr_dev, int64_t* rows, int64_t* cols, int64_t* ld,
@@ -368,17 +383,62 @@ typedef struct gsage_attention_grads { float* att_w1[2]; float* att_w2[2]; } gsa
 int gsage_engine_backward_attention(gsage_engine* e, const float* dlogits_dev, const gsage_grads* grads,
                                     const gsage_attention_grads* att_grads, void* stream);
 
+/* ---- gradients behind the NARROW plug-in API ------------------------------------------------------------------------
+ * The reference back-propagates through its plug-ins with torch autograd (models.py:100-101 -> nn_modules.py:196-204,
+ * 223-232, 305-321, 144-155).  operators.py wraps the narrow calls (`agg(x, neibs)`, `prep(ids, feats, layer_idx)`) in
+ * torch.autograd.Functions; their backward passes are gsage_wgrad (dW = G^T A), gsage_linear with a transposed weight
+ * (dA = G W) and the elementwise / segment kernels below.  Everything fp32, rows in place, buffers overwritten.
+ *   act_backward           dpre = dout * act'(out)  (out = the post-activation value)
+ *   segment_broadcast      dst[p*S + j, :] = scale * src[p, :]            (mean over S rows, backwards: scale = 1/S)
+ *   segment_max_backward   the first row attaining the maximum over the S rows of a parent receives dpooled (torch.max(dim))
+ *   attention_sum_backward m_p = sum_j w_j n_j, w = softmax_j <na_j, xa_p>: dn = w_j dM_p (direct path only), dna_j = ds_j xa_p,
+ *                          dxa_p = sum_j ds_j na_j with ds = softmax'(dw), dw_j = <dM_p, n_j>;  scratch: n*S floats
+ *   colsum                 out[c] = sum_r x[r, c]   (x contiguous)        (bias gradients)
+ *   embedding_backward     table_grad[ids[i], :] += drows[i, :]           (nn.Embedding's dense gradient; caller zeroes it)
+ *   l2_normalize_backward  F.normalize(z, dim=1) backwards (models.py:90; z, dzn, dz contiguous (n, d)) */
+int gsage_act_backward(const float* dout_dev, int64_t ld_dout, const float* out_dev, int64_t ld_out, int64_t n, int width, int act,
+                       float* dpre_dev, int64_t ld_dpre, void* stream);
+int gsage_segment_broadcast(const float* src_dev, int64_t ld_src, int64_t n, int d, int S, float scale, float* dst_dev, int64_t ld_dst,
+                            void* stream);
+int gsage_segment_max_backward(const float* h_dev, int64_t ld_h, const float* dpooled_dev, int64_t ld_dp, int64_t n, int S, int H,
+                               float* dh_dev, int64_t ld_dh, void* stream);
+int gsage_attention_sum_backward(const float* neibs_dev, int64_t ld_nb, int d, int64_t n, int S, const float* dm_dev, int64_t ld_dm,
+                                 const float* w_dev, const float* na_dev, const float* xa_dev, int H, float* dn_dev, int64_t ld_dn,
+                                 float* dna_dev, float* dxa_dev, float* scratch_dev, void* stream);
+int gsage_colsum(const float* x_dev, int64_t n, int d, float* out_dev, void* stream);
+int gsage_embedding_backward(const float* drows_dev, int64_t ld, int d, const int64_t* ids_dev, int64_t n_ids, float* table_grad_dev,
+                             int64_t ld_table, int64_t table_rows, void* stream);
+int gsage_l2_normalize_backward(const float* z_dev, const float* dzn_dev, int64_t n, int d, float* dz_dev, void* stream);
+
+/* ---- per-batch training metric on the device (train.py:150 `problem.metric_fn(to_numpy(targets), to_numpy(preds))`) -------
+ * gsage_metric_f1: sklearn micro / macro F1 as problem.py:44-58 computes them.  multilabel == 0 (`classification`):
+ *   `targets_dev` int64 (n), prediction = argmax of the n_classes logits (first maximum), macro averages over the labels
+ *   that occur in targets or predictions.  multilabel != 0: `targets_dev` float32 (n, ld_targets) of 0 / 1, prediction =
+ *   logit > 0, macro averages over all n_classes columns (empty label: F1 0).  `scratch_dev`: 3 * n_classes * 8 bytes.
+ *   out_dev[0] = micro, out_dev[1] = macro (double).
+ * gsage_metric_mae: mean |preds - targets| over n float32 elements (problem.py:60-64) -> out_dev[0] (double). */
+int gsage_metric_f1(const float* preds_dev, int64_t ld, const void* targets_dev, int64_t ld_targets, int64_t n, int n_classes,
+                    int multilabel, void* scratch_dev, double* out_dev, void* stream);
+int gsage_metric_mae(const float* preds_dev, const float* targets_dev, int64_t n, double* out_dev, void* stream);
+
 /* keep != 0: the next forwards keep every activation the backward pass needs (training).  0 (default): forward-only
  * streaming -- intermediates may be processed in L2-sized chunks that reuse their buffers. */
 int gsage_engine_keep_activations(gsage_engine* e, int keep);
 
 /* Live stopwatch (CUDA events on the launching stream) around kernel groups of the forward, for bench.py:
- *   FORWARD  the whole gsage_engine_forward        SAMPLE   rng draws + sample kernels, both hops
- *   REDUCE   the fused gather+aggregate launches   PROJECT  the concat-with-self projection launches
- * `work_out`: algorithmic bytes (REDUCE) / flops (PROJECT) of the recorded launches.  Reading synchronises. */
-enum { GSAGE_PROF_FORWARD = 0, GSAGE_PROF_SAMPLE = 1, GSAGE_PROF_REDUCE = 2, GSAGE_PROF_PROJECT = 3, GSAGE_PROF_CATS = 4 };
+ *   FORWARD  the whole gsage_engine_forward        SAMPLE   rng draws + sample kernels, both hops (on the stream they run on)
+ *   REDUCE   the DOMINANT aggregate launch: layer 1 on the (x1, x2) pair -- the fused gather+mean kernel, the pooled MLP
+ *            kernel (pool aggregators) or the fused attention kernel
+ *   PROJECT  the concat-with-self projection launch that follows it
+ *   APP0     layer 1 on the (x0, x1) pair, whole        LAYER2   layer 2, whole        HEAD   normalise + classifier
+ *   WAIT     the main stream waiting for the sampled-ahead batch (0 when the sampler stream finished first)
+ * `bytes_out` / `flops_out`: algorithmic bytes and flops of the recorded launches.  Arrays of
+ * GSAGE_PROF_CATS entries.  Reading synchronises. */
+enum { GSAGE_PROF_FORWARD = 0, GSAGE_PROF_SAMPLE = 1, GSAGE_PROF_REDUCE = 2, GSAGE_PROF_PROJECT = 3, GSAGE_PROF_APP0 = 4,
+       GSAGE_PROF_LAYER2 = 5, GSAGE_PROF_HEAD = 6, GSAGE_PROF_WAIT = 7, GSAGE_PROF_CATS = 8 };
 int gsage_engine_profile(gsage_engine* e, int enable);
-int gsage_engine_profile_read(gsage_engine* e, double* ms_out, int64_t* launches_out, double* work_out, void* stream);
+int gsage_engine_profile_read(gsage_engine* e, double* ms_out, int64_t* launches_out, double* bytes_out, double* flops_out,
+                              void* stream);
 
 #ifdef __cplusplus
 }

@@ -10,6 +10,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, 'libgsage_b200.so')
 
 F32, BF16 = 0, 1
+ABI_VERSION = 3
+PROF_CATS = ('forward', 'sample', 'reduce', 'project', 'app0', 'layer2', 'head', 'wait')
 ACT = {'none': 0, None: 0, 'identity': 0, 'relu': 1, 'tanh': 2}
 REDUCE = {'mean': 0, 'max': 1, 'sum': 2}
 AGGREGATOR = {'mean': 0, 'max_pool': 1, 'mean_pool': 2, 'attention': 3, 'lstm': 4}
@@ -118,6 +120,8 @@ _SIGNATURES = {
     'gsage_engine_sample_ahead': (C.c_int, [c_p, c_p, c_p, c_p, c_i64, c_i64, c_i64, c_p]),
     'gsage_engine_sample_ahead_host': (C.c_int, [c_p, c_p, c_p, c_p, c_i64, c_p]),
     'gsage_engine_sample_ahead_pending': (C.c_int, [c_p]),
+    'gsage_engine_inputs_ready': (C.c_int, [c_p, c_p]),
+    'gsage_engine_poll_errors': (C.c_int, [c_p]),
     'gsage_engine_peek': (C.c_int, [c_p, C.c_int, C.POINTER(c_p), C.POINTER(c_i64), C.POINTER(c_i64), C.POINTER(c_i64), C.POINTER(C.c_int)]),
     'gsage_engine_workspace_bytes': (c_i64, [c_p]),
     'gsage_engine_backward_head': (C.c_int, [c_p, c_p, C.POINTER(Grads), c_p]),
@@ -129,9 +133,18 @@ _SIGNATURES = {
     'gsage_engine_backward_layer1_linear': (C.c_int, [c_p, C.POINTER(LinearPrepGrads), c_p]),
     'gsage_wgrad': (C.c_int, [c_p, C.c_int, c_i64, C.c_int, c_p, C.c_int, c_i64, c_i64, c_p, C.c_int, c_i64, c_p, c_i64, C.c_int, c_p]),
     'gsage_adam_step': (C.c_int, [c_p, c_p, c_p, c_p, c_i64, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, c_i64, C.c_float, c_p, c_p]),
+    'gsage_act_backward': (C.c_int, [c_p, c_i64, c_p, c_i64, c_i64, C.c_int, C.c_int, c_p, c_i64, c_p]),
+    'gsage_segment_broadcast': (C.c_int, [c_p, c_i64, c_i64, C.c_int, C.c_int, C.c_float, c_p, c_i64, c_p]),
+    'gsage_segment_max_backward': (C.c_int, [c_p, c_i64, c_p, c_i64, c_i64, C.c_int, C.c_int, c_p, c_i64, c_p]),
+    'gsage_attention_sum_backward': (C.c_int, [c_p, c_i64, C.c_int, c_i64, C.c_int, c_p, c_i64, c_p, c_p, c_p, C.c_int, c_p, c_i64, c_p, c_p, c_p, c_p]),
+    'gsage_colsum': (C.c_int, [c_p, c_i64, C.c_int, c_p, c_p]),
+    'gsage_embedding_backward': (C.c_int, [c_p, c_i64, C.c_int, c_p, c_i64, c_p, c_i64, c_i64, c_p]),
+    'gsage_l2_normalize_backward': (C.c_int, [c_p, c_p, c_i64, C.c_int, c_p, c_p]),
+    'gsage_metric_f1': (C.c_int, [c_p, c_i64, c_p, c_i64, c_i64, C.c_int, C.c_int, c_p, c_p, c_p]),
+    'gsage_metric_mae': (C.c_int, [c_p, c_p, c_i64, c_p, c_p]),
     'gsage_engine_keep_activations': (C.c_int, [c_p, C.c_int]),
     'gsage_engine_profile': (C.c_int, [c_p, C.c_int]),
-    'gsage_engine_profile_read': (C.c_int, [c_p, C.POINTER(C.c_double), C.POINTER(c_i64), C.POINTER(C.c_double), c_p]),
+    'gsage_engine_profile_read': (C.c_int, [c_p, C.POINTER(C.c_double), C.POINTER(c_i64), C.POINTER(C.c_double), C.POINTER(C.c_double), c_p]),
 }
 
 EXPORTS = sorted(_SIGNATURES)
@@ -155,7 +168,7 @@ def lib():
             fn = getattr(handle, name)          # AttributeError if the header and the library disagree
             fn.restype = res
             fn.argtypes = args
-        if handle.gsage_abi_version() != 2:
+        if handle.gsage_abi_version() != ABI_VERSION:
             raise GsageError('libgsage_b200.so ABI mismatch')
         _lib = handle
     return _lib

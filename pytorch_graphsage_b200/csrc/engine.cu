@@ -85,7 +85,8 @@ struct EngineProf {
     struct Rec { int cat; int a, b; };
     std::vector<Rec> recs;
     int used = 0;
-    double bytes[GSAGE_PROF_CATS] = {0, 0, 0, 0};
+    double bytes[GSAGE_PROF_CATS] = {0}; double flops[GSAGE_PROF_CATS] = {0};
+    void work(int rec, int cat, double b, double f) { if (rec >= 0) { bytes[cat] += b; flops[cat] += f; } }
     int begin(int cat, cudaStream_t s) {
         if (!on) return -1;
         if (used + 2 > (int)pool.size()) {
@@ -123,6 +124,12 @@ struct gsage_engine {
     cudaEvent_t ev_mid = nullptr; bool mid_valid = false; int ahead_after_gather = 1; int ahead_split = 0;   // split: draws before the gate (measured: step -1 %, gather kernel +2 %: off)
     struct Ahead { bool valid = false; const void* src = nullptr; int64_t B = 0, global_B = 0, first = 0;
                    gsage_graph* g = nullptr; gsage_rng* rng = nullptr; } ahead;
+    // the producer of the NEXT batch's ids on the caller's stream: recorded by gsage_engine_inputs_ready (before the forward in
+    // flight was queued) or, failing that, at the entry of gsage_engine_sample_ahead; the sampler stream waits for it before it
+    // reads the ids
+    cudaEvent_t ev_src = nullptr; bool src_marked = false;
+    // whose sticky error flags gsage_engine_poll_errors looks at (the graph / rng of the last forward)
+    gsage_graph* last_g = nullptr; gsage_rng* last_rng = nullptr;
     void* X = nullptr;                  // materialised prepped rows (non-identity preps)
     void* M = nullptr;                  // reduced neighbour rows: [layer-1 app 1 (n0) | layer-1 app 2 (n1) | layer 2 (n0)] x ld_m
     int64_t ld_m = 0;                   // (kept after the forward: the backward pass reads them)
@@ -133,7 +140,7 @@ struct gsage_engine {
     // host-buffer entry, pipelined (gsage_engine_forward_host_next with a next batch): two logits buffers, a copy stream for
     // the D2H of batch i while the forward of batch i+1 (queued before the call blocks) already runs
     float* LG2[2] = {nullptr, nullptr}; int lg_cur = 0;
-    cudaStream_t cs = nullptr; cudaEvent_t ev_fwd = nullptr, ev_copy = nullptr; int* flags_host = nullptr;
+    cudaStream_t cs = nullptr; cudaEvent_t ev_fwd = nullptr, ev_copy = nullptr;
     struct Pre { bool valid = false; const void* src = nullptr; int64_t B = 0; int buf = 0; gsage_graph* g = nullptr; gsage_rng* rng = nullptr; } pre;
     int64_t ld_h1 = 0;
     // weights as the kernels read them (fp32 originals, or bf16 copies when compute dtype is bf16)
@@ -242,11 +249,10 @@ static int apply_aggregator(gsage_engine* e, int layer, const RowSrc& x, const R
                 const int p_f = e->prof.begin(GSAGE_PROF_REDUCE, s);
                 const int st = linear_umma_launch(P, s);
                 e->prof.end(p_f, s);
-                if (p_f >= 0) {
+                {
                     const double es_in = (double)dtype_size(nb.dtype), es_out = (double)dtype_size(out_dtype);
-                    e->prof.bytes[GSAGE_PROF_REDUCE] += (double)n * ((double)S * d * es_in + (nb.ids ? 8.0 * S : 0.0) + d * es_in +
-                                                                     (x.ids ? 8.0 : 0.0) + 2.0 * O * es_out);
-                    e->prof.bytes[GSAGE_PROF_PROJECT] += 4.0 * (double)n * d * O;
+                    e->prof.work(p_f, GSAGE_PROF_REDUCE, (double)n * ((double)S * d * es_in + (nb.ids ? 8.0 * S : 0.0) + d * es_in +
+                                                                      (x.ids ? 8.0 : 0.0) + 2.0 * O * es_out), 4.0 * (double)n * d * O);
                 }
                 return st;
             }
@@ -261,7 +267,8 @@ static int apply_aggregator(gsage_engine* e, int layer, const RowSrc& x, const R
             GS_TRY(gather_mean_project_launch(nb.base, nb.ld, nb.table_rows, d, nb.ids, n, S, e->w_n[layer].p, e->w_n[layer].ld, O,
                                               e->b_n[layer], act, out, out_dtype, ld_out, O, s));
             e->prof.end(p_f, s);
-            if (p_f >= 0) e->prof.bytes[GSAGE_PROF_REDUCE] += (double)n * ((double)S * d * dtype_size(nb.dtype) + (nb.ids ? 8.0 * S : 0.0) + (double)O * dtype_size(out_dtype));
+            e->prof.work(p_f, GSAGE_PROF_REDUCE, (double)n * ((double)S * d * dtype_size(nb.dtype) + (nb.ids ? 8.0 * S : 0.0) + (double)O * dtype_size(out_dtype)),
+                         2.0 * (double)n * d * O);
             if (dominant && e->ahead_after_gather) {
                 if (!e->ev_mid) GS_CUDA(cudaEventCreateWithFlags(&e->ev_mid, cudaEventDisableTiming));
                 GS_CUDA(cudaEventRecord(e->ev_mid, s));
@@ -270,7 +277,8 @@ static int apply_aggregator(gsage_engine* e, int layer, const RowSrc& x, const R
             const int p_prj = dominant ? e->prof.begin(GSAGE_PROF_PROJECT, s) : -1;
             const int st = linear_call(x, e->w_x[layer], O, e->b_x[layer], n, act, out, out_dtype, ld_out, 0, exact, s);
             e->prof.end(p_prj, s);
-            if (p_prj >= 0) e->prof.bytes[GSAGE_PROF_PROJECT] += 2.0 * (double)n * d * O;
+            e->prof.work(p_prj, GSAGE_PROF_PROJECT, (double)n * ((double)d * dtype_size(x.dtype) + (x.ids ? 8.0 : 0.0) + (double)O * dtype_size(out_dtype)),
+                         2.0 * (double)n * d * O);
             return st;
         }
         const int p_red = dominant ? e->prof.begin(GSAGE_PROF_REDUCE, s) : -1;
@@ -283,12 +291,14 @@ static int apply_aggregator(gsage_engine* e, int layer, const RowSrc& x, const R
             e->mid_valid = true;
         }
         // algorithmic bytes of the fused gather+mean launch: S rows + S ids in, one row out
-        if (p_red >= 0) e->prof.bytes[GSAGE_PROF_REDUCE] += (double)n * ((double)S * d * dtype_size(nb.dtype) + (nb.ids ? 8.0 * S : 0.0) + (double)d * dtype_size(T));
+        e->prof.work(p_red, GSAGE_PROF_REDUCE, (double)n * ((double)S * d * dtype_size(nb.dtype) + (nb.ids ? 8.0 * S : 0.0) + (double)d * dtype_size(T)),
+                     (double)n * S * d);
         RowSrc m{Mb, T, ldm, n, nullptr, d};
         const int p_prj = dominant ? e->prof.begin(GSAGE_PROF_PROJECT, s) : -1;
         const int st = combine_call(x, e->w_x[layer], m, e->w_n[layer], O, n, act, out, out_dtype, ld_out, exact, s, e->b_x[layer], e->b_n[layer]);
         e->prof.end(p_prj, s);
-        if (p_prj >= 0) e->prof.bytes[GSAGE_PROF_PROJECT] += 4.0 * (double)n * d * O;      // flops, not bytes
+        e->prof.work(p_prj, GSAGE_PROF_PROJECT, (double)n * ((double)d * dtype_size(x.dtype) + (x.ids ? 8.0 : 0.0) + (double)d * dtype_size(T) +
+                                                             2.0 * O * dtype_size(out_dtype)), 4.0 * (double)n * d * O);
         return st;
     }
     case GSAGE_AGG_MAX_POOL:
@@ -305,9 +315,20 @@ static int apply_aggregator(gsage_engine* e, int layer, const RowSrc& x, const R
             P.pool_S = S; P.pool_max = e->cfg.aggregator == GSAGE_AGG_MAX_POOL ? 1 : 0;
             P.seg[0].a_rows = nb.ids ? nb.table_rows : 0;
             if (linear_pool_umma_eligible(P)) {
+                // stopwatch: the dominant launch (layer 1 on the (x1, x2) pair) -- tensor-bound: 2*d*H flop per neighbour row
+                const bool dominant = layer == 0 && n > e->B;
+                const int p_red = dominant ? e->prof.begin(GSAGE_PROF_REDUCE, s) : -1;
                 GS_TRY(linear_dispatch(P, 0, s));
+                e->prof.end(p_red, s);
+                e->prof.work(p_red, GSAGE_PROF_REDUCE, (double)n * ((double)S * d * dtype_size(nb.dtype) + (nb.ids ? 8.0 * S : 0.0) + (double)H * dtype_size(T)),
+                             2.0 * (double)n * S * d * H);
                 RowSrc p{Pb, T, H, n, nullptr, H};
-                return combine_call(x, e->w_x[layer], p, e->w_n[layer], O, n, act, out, out_dtype, ld_out, exact, s, e->b_x[layer], nullptr);
+                const int p_prj = dominant ? e->prof.begin(GSAGE_PROF_PROJECT, s) : -1;
+                const int st = combine_call(x, e->w_x[layer], p, e->w_n[layer], O, n, act, out, out_dtype, ld_out, exact, s, e->b_x[layer], nullptr);
+                e->prof.end(p_prj, s);
+                e->prof.work(p_prj, GSAGE_PROF_PROJECT, (double)n * ((double)d * dtype_size(x.dtype) + (x.ids ? 8.0 : 0.0) + (double)H * dtype_size(T) +
+                                                                     2.0 * O * dtype_size(out_dtype)), 2.0 * (double)n * (d + H) * O);
+                return st;
             }
         }
         GS_TRY(linear_call(nb, e->w_mlp[layer], H, e->b_mlp[layer], n * S, GSAGE_ACT_RELU, e->HN, T, H, 0, exact, s));
@@ -327,10 +348,21 @@ static int apply_aggregator(gsage_engine* e, int layer, const RowSrc& x, const R
         if (!exact && attention_fused_eligible(nb.base, nb.dtype, nb.ld, d, e->w_att1[layer].p, e->w_att1[layer].dtype, e->w_att1[layer].ld, H, S,
                                                n, Mb, ldm, T)) {
             // bf16 mode: scores (tcgen05), softmax and the weighted sum in ONE kernel -- every neighbour row is read once
+            // stopwatch: the dominant launch (layer 1 on the (x1, x2) pair) -- HBM-bound by bytes: S rows + S ids + a(x) in, one row out
+            const bool dominant = layer == 0 && n > e->B;
+            const int p_red = dominant ? e->prof.begin(GSAGE_PROF_REDUCE, s) : -1;
             GS_TRY(attention_fused_launch(nb.base, nb.ld, nb.ids, d, e->w_att1[layer].p, e->w_att1[layer].ld, e->b_att[layer], L.att_w2,
                                           (const float*)e->XA, n, S, Mb, T, ldm, s, nb.ids ? nb.table_rows : 0));
+            e->prof.end(p_red, s);
+            e->prof.work(p_red, GSAGE_PROF_REDUCE, (double)n * ((double)S * d * dtype_size(nb.dtype) + (nb.ids ? 8.0 * S : 0.0) + 4.0 * H + (double)d * dtype_size(T)),
+                         (double)n * S * (2.0 * d * H + 2.0 * H * H + 2.0 * H + 2.0 * d));
             RowSrc mf{Mb, T, ldm, n, nullptr, d};
-            return combine_call(x, e->w_x[layer], mf, e->w_n[layer], O, n, act, out, out_dtype, ld_out, exact, s, e->b_x[layer], e->b_n[layer]);
+            const int p_prj = dominant ? e->prof.begin(GSAGE_PROF_PROJECT, s) : -1;
+            const int st = combine_call(x, e->w_x[layer], mf, e->w_n[layer], O, n, act, out, out_dtype, ld_out, exact, s, e->b_x[layer], e->b_n[layer]);
+            e->prof.end(p_prj, s);
+            e->prof.work(p_prj, GSAGE_PROF_PROJECT, (double)n * ((double)d * dtype_size(x.dtype) + (x.ids ? 8.0 : 0.0) + (double)d * dtype_size(T) +
+                                                                 2.0 * O * dtype_size(out_dtype)), 4.0 * (double)n * d * O);
+            return st;
         }
         GS_TRY(linear_call(nb, e->w_att1[layer], H, e->b_att[layer], n * S, GSAGE_ACT_TANH, e->T1, GSAGE_F32, H, 0, exact, s));
         RowSrc t1{e->T1, GSAGE_F32, H, n * S, nullptr, H};
@@ -522,7 +554,7 @@ void gsage_engine_destroy(gsage_engine* e) {
     if (e->cs) { cudaStreamSynchronize(e->cs); cudaStreamDestroy(e->cs); }
     if (e->ev_fwd) cudaEventDestroy(e->ev_fwd);
     if (e->ev_copy) cudaEventDestroy(e->ev_copy);
-    if (e->flags_host) cudaFreeHost(e->flags_host);
+    if (e->ev_src) cudaEventDestroy(e->ev_src);
     for (int i = 0; i < 2; ++i) if (e->ev_done[i]) cudaEventDestroy(e->ev_done[i]);
     if (e->ev_mid) cudaEventDestroy(e->ev_mid);
     if (e->ev_ahead) cudaEventDestroy(e->ev_ahead);
@@ -547,14 +579,15 @@ int gsage_engine_profile(gsage_engine* e, int enable) {
     e->prof.on = enable != 0;
     e->prof.recs.clear();
     e->prof.used = 0;
-    for (int i = 0; i < GSAGE_PROF_CATS; ++i) e->prof.bytes[i] = 0;
+    for (int i = 0; i < GSAGE_PROF_CATS; ++i) e->prof.bytes[i] = e->prof.flops[i] = 0;
     return GSAGE_OK;
 }
 
-int gsage_engine_profile_read(gsage_engine* e, double* ms_out, int64_t* launches_out, double* work_out, void* stream) {
-    GS_CHECK_ARG(e && ms_out && launches_out && work_out, "engine_profile_read: NULL argument");
+int gsage_engine_profile_read(gsage_engine* e, double* ms_out, int64_t* launches_out, double* bytes_out, double* flops_out, void* stream) {
+    GS_CHECK_ARG(e && ms_out && launches_out && bytes_out && flops_out, "engine_profile_read: NULL argument");
     GS_CUDA(cudaStreamSynchronize(as_stream(stream)));
-    for (int i = 0; i < GSAGE_PROF_CATS; ++i) { ms_out[i] = 0; launches_out[i] = 0; work_out[i] = e->prof.bytes[i]; }
+    if (e->ss) GS_CUDA(cudaStreamSynchronize(e->ss));          // SAMPLE records live on the sampler stream when sampling runs ahead
+    for (int i = 0; i < GSAGE_PROF_CATS; ++i) { ms_out[i] = 0; launches_out[i] = 0; bytes_out[i] = e->prof.bytes[i]; flops_out[i] = e->prof.flops[i]; }
     for (const EngineProf::Rec& r : e->prof.recs) {
         float ms = 0;
         GS_CUDA(cudaEventElapsedTime(&ms, e->prof.pool[r.a], e->prof.pool[r.b]));
@@ -563,7 +596,7 @@ int gsage_engine_profile_read(gsage_engine* e, double* ms_out, int64_t* launches
     }
     e->prof.recs.clear();
     e->prof.used = 0;
-    for (int i = 0; i < GSAGE_PROF_CATS; ++i) e->prof.bytes[i] = 0;
+    for (int i = 0; i < GSAGE_PROF_CATS; ++i) e->prof.bytes[i] = e->prof.flops[i] = 0;
     return GSAGE_OK;
 }
 
@@ -794,11 +827,19 @@ static int sample_ahead_impl(gsage_engine* e, gsage_graph* g, gsage_rng* rng, co
     }
     // the spare slot was last read by the forward (and backward) BEFORE the one in flight: wait for that one only, so
     // the draws run underneath the forward that was queued just before this call
-    (void)main;
     // the draws (count / scan / scatter of the RNG stream: no dependence on the ids) start right away; everything that reads or
     // writes the id slot waits for the slot's last reader and -- mean aggregator -- for the dominant gather launch of the forward
     // in flight, so that the random-access sample kernels share the SMs with the projection tail, not with that kernel
-    cudaEvent_t gate[2]; int n_gate = 0;
+    cudaEvent_t gate[3]; int n_gate = 0;
+    if (!src_host) {
+        // device ids: whatever produced them on the caller's stream must have finished before the sampler stream copies them.
+        // gsage_engine_inputs_ready marks that point BEFORE the forward in flight was queued (the overlap survives); without
+        // it the point is "now", i.e. behind that forward -- always correct, no overlap
+        if (!e->ev_src) GS_CUDA(cudaEventCreateWithFlags(&e->ev_src, cudaEventDisableTiming));
+        if (!e->src_marked) GS_CUDA(cudaEventRecord(e->ev_src, main));
+        e->src_marked = false;
+        gate[n_gate++] = e->ev_src;
+    }
     if (e->done_valid[e->cur ^ 1]) gate[n_gate++] = e->ev_done[e->cur ^ 1];
     if (e->mid_valid) { gate[n_gate++] = e->ev_mid; e->mid_valid = false; }
     if (e->ahead_split) {
@@ -825,6 +866,34 @@ int gsage_engine_sample_ahead_host(gsage_engine* e, gsage_graph* g, gsage_rng* r
 
 int gsage_engine_sample_ahead_pending(const gsage_engine* e) { return (e && e->ahead.valid) ? 1 : 0; }
 
+int gsage_engine_inputs_ready(gsage_engine* e, void* stream) {
+    GS_CHECK_ARG(e, "engine_inputs_ready: NULL engine");
+    if (!e->ev_src) GS_CUDA(cudaEventCreateWithFlags(&e->ev_src, cudaEventDisableTiming));
+    GS_CUDA(cudaEventRecord(e->ev_src, as_stream(stream)));
+    e->src_marked = true;
+    return GSAGE_OK;
+}
+
+// The sticky error flags (rng look-ahead window, out-of-range ids) live in mapped pinned host memory (graph.cu, mt19937.cu):
+// polling them costs neither a copy nor a synchronisation, so every forward can look at what the PREVIOUS forwards reported --
+// an error surfaces one call late instead of never.
+int gsage_engine_poll_errors(gsage_engine* e) {
+    GS_CHECK_ARG(e, "engine_poll_errors: NULL engine");
+    if (e->last_rng && *(volatile int*)e->last_rng->err_flag) {
+        set_error("rng: the look-ahead window held fewer accepted draws than requested (12-sigma event) -- re-seed; results since the last "
+                  "check are invalid");
+        return GSAGE_ERR_RNG;
+    }
+    if (e->last_g && *(volatile int*)e->last_g->err_flag) {
+        *(volatile int*)e->last_g->err_flag = 0;
+        set_error("index out of range: a seed or sampled id of an earlier forward lies outside the adjacency (%lld rows) -- "
+                  "`feats[ids]` (models.py:76) / scipy raise IndexError there; its samples were read as the dummy node",
+                  (long long)e->last_g->n_rows);
+        return GSAGE_ERR_INDEX;
+    }
+    return GSAGE_OK;
+}
+
 static int forward_impl(gsage_engine* e, gsage_graph* g, gsage_rng* rng, const int64_t* ids_src, bool src_host, int64_t B,
                         int64_t global_B, int64_t first, float* logits_dev, cudaStream_t s);
 static int forward_layers(gsage_engine* e, int64_t B, float* logits_dev, cudaStream_t s, int p_all);
@@ -845,6 +914,7 @@ static int forward_impl(gsage_engine* e, gsage_graph* g, gsage_rng* rng, const i
                         int64_t global_B, int64_t first, float* logits_dev, cudaStream_t s) {
     GS_TRY(check_batch_args(e, g, rng, ids_src, B, global_B, first));
     GS_CHECK_ARG(logits_dev, "engine_forward: NULL argument");
+    e->last_g = g; e->last_rng = rng;
     GS_CHECK_ARG(e->have_weights, "engine_forward: call gsage_engine_set_weights first");
 
     const int p_all = e->prof.begin(GSAGE_PROF_FORWARD, s);
@@ -854,7 +924,9 @@ static int forward_impl(gsage_engine* e, gsage_graph* g, gsage_rng* rng, const i
                      e->ahead.g == g && e->ahead.rng == rng,
                      "engine_forward: a different batch was sampled ahead (its draws are already consumed): run the forward of "
                      "that batch (same ids pointer, batch size, graph and rng) first");
+        const int p_wait = e->prof.begin(GSAGE_PROF_WAIT, s);
         GS_CUDA(cudaStreamWaitEvent(s, e->ev_ahead, 0));
+        e->prof.end(p_wait, s);
         e->cur ^= 1;
         e->ids = e->ids_slot[e->cur];
         e->ahead.valid = false;
@@ -913,7 +985,9 @@ static int forward_layers(gsage_engine* e, int64_t B, float* logits_dev, cudaStr
     const int O1 = c.out_dim[0], O2 = c.out_dim[1];
     x_seed = lvl;
     if (e->fold_prep) x_seed.ids = e->look0;
+    const int p_app0 = e->prof.begin(GSAGE_PROF_APP0, s);
     GS_TRY(apply_aggregator(e, 0, x_seed, lvl.shifted(n0), n0, S1, e->H1, T, ldh, 0, s));
+    e->prof.end(p_app0, s);
     if (!e->keep_activations && e->chunk_parents > 0 && c.aggregator == GSAGE_AGG_MEAN && n1 > e->chunk_parents) {
         for (int64_t p0 = 0; p0 < n1; p0 += e->chunk_parents) {
             const int64_t np = std::min(e->chunk_parents, n1 - p0);
@@ -926,9 +1000,12 @@ static int forward_layers(gsage_engine* e, int64_t B, float* logits_dev, cudaStr
 
     // ---- layer 2 on (h0, h1) ----------------------------------------------------------------------------------
     RowSrc h{e->H1, T, ldh, n0 + n1, nullptr, 2 * O1};
+    const int p_l2 = e->prof.begin(GSAGE_PROF_LAYER2, s);
     GS_TRY(apply_aggregator(e, 1, h, h.shifted(n0), n0, S1, e->Z, GSAGE_F32, 2 * O2, n0 + n1, s));
+    e->prof.end(p_l2, s);
 
     // ---- normalise + classifier (models.py:90-91) -----------------------------------------------------------------
+    const int p_head = e->prof.begin(GSAGE_PROF_HEAD, s);
     GS_TRY(gsage_l2_normalize(e->Z, GSAGE_F32, 2 * O2, n0, 2 * O2, e->ZN, 2 * O2, s));
     RowSrc zn{e->ZN, GSAGE_F32, 2 * O2, n0, nullptr, 2 * O2};
     if (T == GSAGE_BF16 && e->fc_pad > 0 && (2 * O2) % 4 == 0 && getenv("GSAGE_FC_EXACT") == nullptr) {
@@ -941,6 +1018,7 @@ static int forward_layers(gsage_engine* e, int64_t B, float* logits_dev, cudaStr
         P.seg[0].O_store = c.n_classes;
         if (linear_ws_umma_eligible(P)) {
             GS_TRY(linear_ws_umma_launch(P, s));
+            e->prof.end(p_head, s);
             e->prof.end(p_all, s);
             GS_TRY(mark_slot_done(e, s));
             return GSAGE_OK;
@@ -948,6 +1026,7 @@ static int forward_layers(gsage_engine* e, int64_t B, float* logits_dev, cudaStr
     }
     GS_TRY(linear_call(zn, f32w(e->w.fc_w, 2 * O2), c.n_classes, e->w.fc_b, n0, GSAGE_ACT_NONE, logits_dev, GSAGE_F32, c.n_classes,
                        0, 1, s));
+    e->prof.end(p_head, s);
     e->prof.end(p_all, s);
     GS_TRY(mark_slot_done(e, s));
     return GSAGE_OK;
@@ -963,7 +1042,6 @@ int gsage_engine_forward_host_next(gsage_engine* e, gsage_graph* g, gsage_rng* r
         GS_CUDA(cudaStreamCreateWithFlags(&e->cs, cudaStreamNonBlocking));
         GS_CUDA(cudaEventCreateWithFlags(&e->ev_fwd, cudaEventDisableTiming));
         GS_CUDA(cudaEventCreateWithFlags(&e->ev_copy, cudaEventDisableTiming));
-        GS_CUDA(cudaHostAlloc((void**)&e->flags_host, 2 * sizeof(int), cudaHostAllocDefault));
     }
     // 1. this batch's forward: already queued by the previous call when that call was given this batch as its `next`
     int buf;
@@ -981,8 +1059,6 @@ int gsage_engine_forward_host_next(gsage_engine* e, gsage_graph* g, gsage_rng* r
     // 2. its logits (and the two sticky error flags) travel on the copy stream, behind that forward only
     GS_CUDA(cudaStreamWaitEvent(e->cs, e->ev_fwd, 0));
     GS_CUDA(cudaMemcpyAsync(logits_host, e->LG2[buf], 4 * B * e->cfg.n_classes, cudaMemcpyDeviceToHost, e->cs));
-    GS_CUDA(cudaMemcpyAsync(e->flags_host, rng->err_flag, sizeof(int), cudaMemcpyDeviceToHost, e->cs));
-    GS_CUDA(cudaMemcpyAsync(e->flags_host + 1, g->err_flag, sizeof(int), cudaMemcpyDeviceToHost, e->cs));
     GS_CUDA(cudaEventRecord(e->ev_copy, e->cs));
     // 3. the next batch: H2D of its ids + sampling (sampler stream) AND its whole forward (caller's stream) are queued BEFORE
     //    this call blocks on its own result -- the GPU never waits for the host round trip of the logits
@@ -999,12 +1075,13 @@ int gsage_engine_forward_host_next(gsage_engine* e, gsage_graph* g, gsage_rng* r
         set_error("engine_forward_host: D2H copy failed: %s", cudaGetErrorString(cudaGetLastError()));
         return GSAGE_ERR_CUDA;
     }
-    if (e->flags_host[0]) {
+    // the sticky flags live in mapped host memory; this batch's kernels have all retired (its logits are here)
+    if (*(volatile int*)rng->err_flag) {
         set_error("rng: the look-ahead window held fewer accepted draws than requested (12-sigma event) -- re-seed; results since the last "
                   "check are invalid");
         return GSAGE_ERR_RNG;
     }
-    if (e->flags_host[1]) return gsage_graph_check(g, stream);     // reports (and clears) the out-of-range id like the device entry
+    if (*(volatile int*)g->err_flag) return gsage_graph_check(g, stream);     // reports (and clears) the out-of-range id like the device entry
     return GSAGE_OK;
 }
 

@@ -92,8 +92,10 @@ static int build(const int64_t* indptr, const int64_t* indices, const int64_t* d
         st = upload(c32.data(), sizeof(int32_t) * nnz, (void**)&g->col);
         if (st == GSAGE_OK) st = upload(deg.data(), sizeof(int32_t) * n_rows, (void**)&g->deg);
     }
-    if (st == GSAGE_OK) st = upload(nullptr, sizeof(int), (void**)&g->err_flag);
-    if (st == GSAGE_OK && cudaMemset(g->err_flag, 0, sizeof(int)) != cudaSuccess) st = GSAGE_ERR_CUDA;
+    // the sticky "id out of range" flag lives in MAPPED pinned host memory: kernels store to it through the unified address,
+    // the host polls it without a copy or a synchronisation (gsage_engine_poll_errors)
+    if (st == GSAGE_OK && cudaHostAlloc((void**)&g->err_flag, sizeof(int), cudaHostAllocMapped) != cudaSuccess) { g->err_flag = nullptr; st = GSAGE_ERR_NOMEM; }
+    if (st == GSAGE_OK) *g->err_flag = 0;
     if (st != GSAGE_OK) { gsage_graph_destroy(g); return st; }
     g->device_bytes = sizeof(int64_t) * (n_rows + 1) + (fits32 ? 4 : 8) * nnz + (fast ? 0 : 4 * nnz + 4 * n_rows);
     *out = g;
@@ -168,7 +170,7 @@ int gsage_graph_from_triplets(const int64_t* v, const int64_t* r, const int64_t*
 
 void gsage_graph_destroy(gsage_graph* g) {
     if (!g) return;
-    cudaFree(g->indptr); cudaFree(g->val); cudaFree(g->col); cudaFree(g->deg); cudaFree(g->err_flag);
+    cudaFree(g->indptr); cudaFree(g->val); cudaFree(g->col); cudaFree(g->deg); if (g->err_flag) cudaFreeHost(g->err_flag);
     delete g;
 }
 
@@ -191,11 +193,9 @@ int gsage_graph_degrees_host(const gsage_graph* g, int64_t* degrees_host) {
 
 int gsage_graph_check(gsage_graph* g, void* stream) {
     GS_CHECK_ARG(g, "graph_check: NULL graph");
-    int flag = 0;
-    GS_CUDA(cudaMemcpyAsync(&flag, g->err_flag, sizeof(int), cudaMemcpyDeviceToHost, as_stream(stream)));
     GS_CUDA(cudaStreamSynchronize(as_stream(stream)));
-    if (flag) {
-        GS_CUDA(cudaMemsetAsync(g->err_flag, 0, sizeof(int), as_stream(stream)));
+    if (*(volatile int*)g->err_flag) {
+        *(volatile int*)g->err_flag = 0;
         set_error("sampler: id out of range of the adjacency (%lld rows) -- scipy would raise IndexError",
                   (long long)g->n_rows);
         return GSAGE_ERR_INDEX;

@@ -232,7 +232,7 @@ __global__ void __launch_bounds__(1024) mt_scan_kernel(const int* __restrict__ t
         if (threadIdx.x == 1023) carry = before + x;
         __syncthreads();
     }
-    if (threadIdx.x == 0 && carry < count) atomicExch(err_flag, 1);   // window too short: never silently wrong
+    if (threadIdx.x == 0 && carry < count) { *(volatile int*)err_flag = 1; __threadfence_system(); }   // window too short: never silently wrong
 }
 
 // pass 3: stream compaction -- the q-th accepted word (q < count) goes to out[q]; the word after the
@@ -306,7 +306,7 @@ __global__ void __launch_bounds__(256) mt_permutation_kernel(const uint32_t* __r
         m |= m >> 1; m |= m >> 2; m |= m >> 4; m |= m >> 8; m |= m >> 16;
         uint32_t w;
         do {
-            if (c >= limit) { atomicExch(err_flag, 1); *cursor_out = c; return; }
+            if (c >= limit) { *(volatile int*)err_flag = 1; __threadfence_system(); *cursor_out = c; return; }
             w = mt_temper(ring[(uint64_t)c & cap_mask]) & m;
             ++c;
         } while (w > (uint32_t)i);
@@ -545,7 +545,8 @@ int gsage_rng_create(gsage_rng** out) {
     r->tiles_cap = (int)(r->cap / kTile + 2);
     cudaError_t e1 = cudaMalloc((void**)&r->ring, sizeof(uint32_t) * r->cap);
     cudaError_t e2 = cudaMalloc((void**)&r->cursor, sizeof(int64_t) * 2);
-    cudaError_t e3 = cudaMalloc((void**)&r->err_flag, sizeof(int));
+    cudaError_t e3 = cudaHostAlloc((void**)&r->err_flag, sizeof(int), cudaHostAllocMapped);   // mapped pinned: polled by the host without a copy
+    if (e3 == cudaSuccess) *r->err_flag = 0; else r->err_flag = nullptr;
     cudaError_t e4 = cudaMalloc((void**)&r->tile_count, sizeof(int) * r->tiles_cap);
     cudaError_t e5 = cudaMalloc((void**)&r->tile_off, sizeof(int64_t) * r->tiles_cap);
     if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess || e4 != cudaSuccess || e5 != cudaSuccess) {
@@ -577,7 +578,7 @@ int gsage_rng_create(gsage_rng** out) {
 
 void gsage_rng_destroy(gsage_rng* r) {
     if (!r) return;
-    cudaFree(r->ring); cudaFree(r->cursor); cudaFree(r->err_flag); cudaFree(r->tile_count); cudaFree(r->tile_off);
+    cudaFree(r->ring); cudaFree(r->cursor); if (r->err_flag) cudaFreeHost(r->err_flag); cudaFree(r->tile_count); cudaFree(r->tile_off);
     cudaFree(r->polys); cudaFree(r->partial);
     if (r->side) { cudaStreamSynchronize(r->side); cudaStreamDestroy(r->side); }
     if (r->ev_main) cudaEventDestroy(r->ev_main);
@@ -598,8 +599,8 @@ int gsage_rng_set_state(gsage_rng* r, const uint32_t* key, int pos, void* stream
     GS_CUDA(cudaMemcpyAsync(r->ring, key, sizeof(uint32_t) * kN, cudaMemcpyHostToDevice, s));
     const int64_t c[2] = {pos, pos};
     GS_CUDA(cudaMemcpyAsync(r->cursor, c, sizeof(c), cudaMemcpyHostToDevice, s));
-    GS_CUDA(cudaMemsetAsync(r->err_flag, 0, sizeof(int), s));
     GS_CUDA(cudaStreamSynchronize(s));                          // `key` / `c` are pageable host memory
+    *(volatile int*)r->err_flag = 0;                            // mapped host memory; every earlier consumer has retired
     r->gen_end = kN;
     r->gen_visible = kN;
     r->max_window = 0;
@@ -682,10 +683,8 @@ int gsage_rng_permutation(gsage_rng* r, int64_t n, int64_t* out_dev, void* strea
 
 int gsage_rng_check(gsage_rng* r, void* stream) {
     GS_CHECK_ARG(r, "rng_check: NULL rng");
-    int flag = 0;                       // sticky flag: reading it needs no ordering against the other consumer stream
-    GS_CUDA(cudaMemcpyAsync(&flag, r->err_flag, sizeof(int), cudaMemcpyDeviceToHost, as_stream(stream)));
-    GS_CUDA(cudaStreamSynchronize(as_stream(stream)));
-    if (flag) {
+    GS_CUDA(cudaStreamSynchronize(as_stream(stream)));   // sticky flag in mapped host memory: no ordering needed against the other consumer stream
+    if (*(volatile int*)r->err_flag) {
         set_error("rng: the look-ahead window held fewer accepted draws than requested (12-sigma event) -- "
                   "re-seed; results since the last check are invalid");
         return GSAGE_ERR_RNG;

@@ -10,6 +10,7 @@ the narrow operator API for parity debugging.
 """
 
 import ctypes as C
+import weakref
 from functools import partial
 
 import torch
@@ -22,6 +23,7 @@ from .graph import GraphCSR
 from .operators import (AttentionAggregator, LSTMAggregator, MeanAggregator, MeanPoolAggregator, MaxPoolAggregator, NodeEmbeddingPrep,
                         IdentityPrep, LinearPrep, SparseUniformNeighborSampler, UniformNeighborSampler, _act_name)
 from .rng import default_rng
+from .lr import LRSchedule
 
 
 def _agg_name(cls):
@@ -50,6 +52,16 @@ class FeatureTable(object):
         self.ld = self.store.shape[1]
         self.rows = self.store.shape[0]
         self.dtype = dtype
+
+    @classmethod
+    def from_store(cls, store, d):
+        """Wrap a device tensor that already has the layout (rows, ld >= d, zero padded, 32-byte rows)."""
+        assert store.is_cuda and store.dim() == 2 and store.stride(1) == 1 and (store.stride(0) * store.element_size()) % 32 == 0
+        self = cls.__new__(cls)
+        self.store, self.d = store, d
+        self.view = store[:, :d]
+        self.ld, self.rows, self.dtype = store.stride(0), store.shape[0], store.dtype
+        return self
 
 
 class GSSupervised(nn.Module):
@@ -88,6 +100,21 @@ class GSSupervised(nn.Module):
         self._agg_name, self._prep_name = _agg_name(aggregator_class), _prep_name(prep_class)
         self._engines = {}
         self._tables = {}
+        self._last = None
+        self.last_loss = None
+
+        # Optimiser (models.py:64-69): the schedule named by `lr_schedule` with `lr_init` bound, its value at progress 0, and an
+        # Adam over all parameters.  The Adam is parallel.FusedAdam -- clip_grad_norm 5 + the Adam update as one native call
+        # over flat buffers (models.py:102-103) -- built lazily because the reference constructs it before `model.cuda()`
+        from .parallel import FusedAdam
+        self.lr_scheduler = partial(getattr(LRSchedule, lr_schedule), lr_init=lr_init)
+        self.lr = self.lr_scheduler(0.0)
+        self.optimizer = FusedAdam(self, lr=self.lr, weight_decay=weight_decay, lazy=True)
+
+    def set_progress(self, progress):
+        """models.py:93-95: evaluate the schedule at `progress` (epochs) and hand the rate to the optimiser."""
+        self.lr = self.lr_scheduler(progress)
+        LRSchedule.set_lr(self.optimizer, self.lr)
 
     # -- engine plumbing --------------------------------------------------------------------------
     def _table(self, feats):
@@ -95,10 +122,20 @@ class GSSupervised(nn.Module):
             return None
         if isinstance(feats, FeatureTable):
             return feats
-        key = (feats.data_ptr() if torch.is_tensor(feats) else id(feats), self.compute_dtype)
-        if key not in self._tables:
-            self._tables[key] = FeatureTable(feats, self.compute_dtype)
-        return self._tables[key]
+        # the padded device copy is cached per tensor OBJECT and content version: an in-place update of `feats` (torch bumps
+        # `_version`) or a new tensor at a recycled address gets a fresh copy, a dead tensor drops its entry
+        key = (id(feats), self.compute_dtype)
+        version = feats._version if torch.is_tensor(feats) else None
+        hit = self._tables.get(key)
+        if hit is not None and hit[0]() is feats and hit[1] == version:
+            return hit[2]
+        table = FeatureTable(feats, self.compute_dtype)
+        try:
+            ref = weakref.ref(feats, lambda _r, k=key, t=self._tables: t.pop(k, None))
+        except TypeError:                                      # numpy arrays of some subclasses: keep the object alive instead
+            ref = (lambda o: (lambda: o))(feats)
+        self._tables[key] = (ref, version, table)
+        return table
 
     def _engine(self, table, fanout, batch):
         key = (None if table is None else table.store.data_ptr(), tuple(fanout))
@@ -180,20 +217,29 @@ class GSSupervised(nn.Module):
             eng['stamp'] = stamp
 
     # -- the reference's public surface ---------------------------------------------------------------
-    def forward(self, ids, feats, train=True, shard=None, keep_activations=False):
+    def forward(self, ids, feats, train=True, shard=None, keep_activations=False, next_ids=None, next_shard=None):
         """models.py:71-91.  `ids`: int64 tensor of seed ids (CUDA, or CPU -> copied); `feats`: the node feature
-        table (tensor / FeatureTable) or None.  Returns fp32 logits (B, n_classes) on the GPU."""
+        table (tensor / FeatureTable) or None.  Returns fp32 logits (B, n_classes) on the GPU.
+
+        `next_ids` (keyword extra): the batch after this one.  Its draws and CSR lookups are queued on the engine's sampler
+        stream right behind this forward (sample-ahead) and ordered after whatever produced `next_ids` on the current stream
+        BEFORE this call -- the next forward must then be given that same batch.  Out-of-range ids and rng window faults of
+        EARLIER forwards are raised here (IndexError / GsageError) from sticky flags polled without a synchronisation."""
         sampler = self.train_sampler if train else self.val_sampler
         fanout = [s['n_train_samples' if train else 'n_val_samples'] for s in self.layer_specs]
         ids = torch.as_tensor(ids).to(device='cuda', dtype=torch.int64).contiguous().view(-1)
         table = self._table(feats)
-        eng = self._engine(table, fanout, ids.shape[0])
+        eng = self._engine(table, fanout, max(ids.shape[0], 0 if next_ids is None else int(next_ids.shape[0])))
+        check(lib().gsage_engine_poll_errors(eng['h']))
         self._push_weights(eng)
         check(lib().gsage_engine_keep_activations(eng['h'], 1 if keep_activations else 0))
+        if next_ids is not None:
+            next_ids = torch.as_tensor(next_ids).to(device='cuda', dtype=torch.int64).contiguous().view(-1)
+            check(lib().gsage_engine_inputs_ready(eng['h'], ops.stream()))     # next_ids is complete on this stream HERE
         if isinstance(sampler, UniformNeighborSampler):
             # the dense 2-D edgelist sampler (train.py:55's default): one torch.randperm(K) per hop from the CPU generator,
             # hop 0 first -- exactly the draws nn_modules.py:44 makes -- then the same engine
-            assert shard is None, 'GSSupervised: seed sharding is implemented for the sparse sampler'
+            assert shard is None and next_ids is None, 'GSSupervised: seed sharding / sample-ahead are implemented for the sparse sampler'
             K = sampler.adj.size(1)
             perms = [torch.randperm(K).cuda() for _ in fanout]
             out = torch.empty((ids.shape[0], self.n_classes), dtype=torch.float32, device='cuda')
@@ -210,13 +256,24 @@ class GSSupervised(nn.Module):
             check(lib().gsage_engine_forward_sharded(eng['h'], sampler.graph._h, rng._h, ops.ptr(ids), ids.shape[0], int(shard[0]),
                                                      int(shard[1]), ops.ptr(out), ops.stream()))
         self._last = eng
+        if next_ids is not None:
+            self.sample_ahead(next_ids, feats, train=train, shard=next_shard)
         return out
 
+    def check(self):
+        """Synchronise and raise what the sticky device flags hold: IndexError for an id outside the adjacency (where the
+        reference's `feats[ids]` / scipy indexing raise, models.py:76), GsageError for an rng look-ahead fault."""
+        torch.cuda.synchronize()
+        if self._last is not None:
+            check(lib().gsage_engine_poll_errors(self._last['h']))
+
     def sample_ahead(self, ids, feats, train=True, shard=None, host=False):
-        """Draw and sample both hops of the NEXT batch now, on the engine's own stream, so that it overlaps the
-        aggregation of the batch whose forward is queued right after this call (gsage_engine_sample_ahead).  The next
+        """Draw and sample both hops of the NEXT batch now, on the engine's own stream (gsage_engine_sample_ahead).  The next
         `forward` / `forward_host` must be given the same `ids` tensor.  Draw order on the RNG stream = call order, so
-        the sampled ids are bit-identical with and without it."""
+        the sampled ids are bit-identical with and without it.  Called on its own, the sampler stream is ordered after
+        everything queued on the current stream so far (always correct; it then starts behind the forward in flight);
+        `forward(..., next_ids=)` / `train_step(..., next_ids=)` mark the ids as ready BEFORE they queue their forward, which
+        is what lets the sampling overlap it."""
         sampler = self.train_sampler if train else self.val_sampler
         fanout = [s['n_train_samples' if train else 'n_val_samples'] for s in self.layer_specs]
         if not host:
@@ -269,6 +326,7 @@ class GSSupervised(nn.Module):
         if self._agg_name == 'lstm':
             raise NotImplementedError('gsage: the LSTM aggregator is forward-only (no backward through the recurrence is built)')
         bucket = self._bucket()
+        bucket.attach()              # optimizer.zero_grad(set_to_none=True) (torch's default) drops p.grad: point it at the bucket again
         g = _lib.Grads()
         aggs = list(self.agg_layers.children())
         if self._agg_name == 'attention':
@@ -371,26 +429,36 @@ class GSSupervised(nn.Module):
         bucket.grad_of(self.prep.fc.weight).copy_(Wx.t() @ gx_raw + Wn.t() @ gn_raw)
         bucket.grad_of(self.prep.fc.bias).copy_(Wx.t() @ cx + Wn.t() @ cn)
 
-    def train_step(self, ids, feats, targets, loss_fn, optimizer=None, clip=5.0, grad_scale=1.0, overlap_stream=None, shard=None,
+    def train_step(self, ids, feats, targets, loss_fn, *, optimizer=None, clip=5.0, grad_scale=1.0, overlap_stream=None, shard=None,
                    next_ids=None, next_shard=None):
-        """models.py:97-104: forward, loss, backward, clip-norm 5, optimiser step.  The loss and the optimiser are
-        stock torch (out of scope); forward and parameter gradients run in the library.
-        `next_ids`: the next batch, sampled ahead underneath this step (the next call must be given the same tensor)."""
-        preds = self(ids, feats, train=True, shard=shard, keep_activations=True)
-        if next_ids is not None:
-            self.sample_ahead(next_ids, feats, train=True, shard=next_shard)
+        """models.py:97-104, same positional signature, same return value (`preds`): zero_grad, forward, loss, backward,
+        clip_grad_norm 5, optimiser step.  The loss is the caller's torch function (problem.py:26-41) evaluated on the
+        logits; its gradient enters the library's backward pass; clip + Adam are one native call on the model's own
+        optimiser (`self.optimizer`, models.py:69).  The scalar loss of the step is kept in `self.last_loss` (device tensor).
+
+        Keyword-only extras: `optimizer` (a torch optimiser to step instead of the model's own, or False for gradients only),
+        `clip`, `grad_scale`
+        (this rank's local/global batch weight under seed sharding), `overlap_stream` (all-reduce of the head gradients
+        under the layer-1 backward), `shard`, `next_ids` / `next_shard` (sample the next batch ahead, see `forward`)."""
+        opt = self.optimizer if optimizer is None else optimizer        # optimizer=False: gradients only, no update
+        if opt and getattr(opt, 'flat', 0) is None:
+            opt._materialize()                 # before the forward: building the flat buffers re-creates the engines
+        if opt:
+            opt.zero_grad()
+        preds = self(ids, feats, train=True, shard=shard, keep_activations=True, next_ids=next_ids, next_shard=next_shard)
         leaf = preds.detach().requires_grad_(True)
         loss = loss_fn(leaf, targets.squeeze())
         dlogits, = torch.autograd.grad(loss, leaf)
         self.backward(dlogits, grad_scale=grad_scale, overlap_stream=overlap_stream)
-        if getattr(optimizer, 'fused_clip', False):
-            optimizer.step(clip=clip)                              # clip + Adam in one native call (parallel.FusedAdam)
+        if opt and getattr(opt, 'fused_clip', False):
+            opt.step(clip=clip)                                    # clip + Adam in one native call (parallel.FusedAdam)
         else:
             if clip:
                 torch.nn.utils.clip_grad_norm_(self.parameters(), clip)
-            if optimizer is not None:
-                optimizer.step()
-        return preds, loss.detach()
+            if opt:
+                opt.step()
+        self.last_loss = loss.detach()
+        return preds
 
     def profile(self, enable=True):
         """Switch the engine's CUDA-event stopwatch on/off (all engines of this model)."""
@@ -398,11 +466,12 @@ class GSSupervised(nn.Module):
             check(lib().gsage_engine_profile(eng['h'], 1 if enable else 0))
 
     def profile_read(self):
-        """{category: (ms, launches, work)} accumulated since the last read, for the last-used engine; synchronises."""
-        ms, cnt, work = (C.c_double * 4)(), (C.c_int64 * 4)(), (C.c_double * 4)()
-        check(lib().gsage_engine_profile_read(self._last['h'], ms, cnt, work, ops.stream()))
-        names = ('forward', 'sample', 'reduce', 'project')
-        return {n: (ms[i], cnt[i], work[i]) for i, n in enumerate(names)}
+        """{category: (ms, launches, algorithmic bytes, flops)} accumulated since the last read, for the last-used engine
+        (categories: _lib.PROF_CATS); synchronises."""
+        n = len(_lib.PROF_CATS)
+        ms, cnt, byt, flo = (C.c_double * n)(), (C.c_int64 * n)(), (C.c_double * n)(), (C.c_double * n)()
+        check(lib().gsage_engine_profile_read(self._last['h'], ms, cnt, byt, flo, ops.stream()))
+        return {name: (ms[i], cnt[i], byt[i], flo[i]) for i, name in enumerate(_lib.PROF_CATS)}
 
     def peek(self, what):
         """Device view of an intermediate of the last forward: 'ids0' 'ids1' 'ids2' 'layer1' 'layer2'."""
@@ -414,7 +483,9 @@ class GSSupervised(nn.Module):
 
     def forward_reference_order(self, ids, feats, train=True):
         """The reference's own loop (models.py:71-91) over the narrow operator API: sample -> feats[ids] -> prep ->
-        aggregators on pre-gathered rows.  Slower (rows are materialised); exists for parity debugging."""
+        aggregators on pre-gathered rows.  Slower (rows are materialised), but every step is a plug-in call exactly where the
+        reference makes one, and the result is autograd-differentiable like the reference's: `loss.backward()` reaches every
+        parameter through the operators' autograd Functions (operators.py)."""
         sample_fns = self.train_sample_fns if train else self.val_sample_fns
         ids = torch.as_tensor(ids).to(device='cuda', dtype=torch.int64).contiguous().view(-1)
         table = self._table(feats)
@@ -426,8 +497,9 @@ class GSSupervised(nn.Module):
         for agg_layer in self.agg_layers.children():
             all_feats = [agg_layer(all_feats[k], all_feats[k + 1]) for k in range(len(all_feats) - 1)]
         assert len(all_feats) == 1, "len(all_feats) != 1"
-        out = ops.l2_normalize(all_feats[0])
-        return ops.linear([dict(a=out, w=self.fc.weight.data, bias=self.fc.bias.data)], out.shape[0])
+        from .operators import _L2Normalize, linear_fn
+        out = _L2Normalize.apply(all_feats[0])
+        return linear_fn(out, self.fc.weight, self.fc.bias)
 
     def __del__(self):
         try:

@@ -9,10 +9,14 @@ reference `state_dict` loads into these modules unchanged.
 
 Two entry points per aggregator:
   * `forward(x, neibs)`           -- the reference's narrow contract (rows already gathered): reduce + both
-                                     projections + concat + activation run in the library;
+                                     projections + concat + activation run in the library, and the call is
+                                     autograd-differentiable like the reference's (models.py:100-101 back-propagates
+                                     through nn_modules.py:196-204, 223-232, 305-321): every library call is wrapped in a
+                                     torch.autograd.Function whose backward pass is again library kernels
+                                     (gsage_wgrad, gsage_linear with a transposed weight, narrow_backward.cu);
   * `forward_ids(table, ids_self, ids_neib, S)` -- the wide contract: the gather is fused into the reduce
-                                     and projection kernels, neighbour rows are never materialised.
-These modules are inference/forward operators (no autograd graph is recorded through the library calls).
+                                     and projection kernels, neighbour rows are never materialised (forward only; the
+                                     engine owns the fused backward, model.GSSupervised.backward).
 """
 
 import numpy as np
@@ -52,6 +56,124 @@ def _cuda_ids(ids):
     was_cuda = ids.is_cuda
     ids = ids.to(device='cuda', dtype=torch.int64).contiguous().view(-1)
     return ids, was_cuda
+
+
+# --
+# autograd plumbing of the narrow API: forward and backward are both library calls, torch only records the graph
+
+def _f32(t):
+    t = t if torch.is_tensor(t) else torch.as_tensor(t)
+    return t.to(device='cuda', dtype=torch.float32)
+
+
+class _Linear(torch.autograd.Function):
+    """out = act([a0 . w0^T + b0 | a1 . w1^T]) -- one launch, one or two column ranges (nn.Linear / the concat-with-self)."""
+
+    @staticmethod
+    def forward(ctx, act, a0, w0, b0, a1, w1):
+        a0 = a0.contiguous()
+        segs = [dict(a=a0, w=w0, bias=b0, col0=0)]
+        if a1 is not None:
+            a1 = a1.contiguous()
+            segs.append(dict(a=a1, w=w1, col0=w0.shape[0]))
+        out = ops.linear(segs, a0.shape[0], act=act)
+        ctx.act, ctx.has_bias = act, b0 is not None
+        ctx.save_for_backward(a0, w0, a1, w1, out)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        a0, w0, a1, w1, out = ctx.saved_tensors
+        n, O0 = out.shape[0], w0.shape[0]
+        dpre = ops.act_backward(dout.contiguous(), out, ctx.act)
+        need = ctx.needs_input_grad
+        g0 = dpre[:, :O0]
+        da0 = ops.linear([dict(a=g0, w=w0, w_trans=True)], n) if need[1] else None
+        dw0 = ops.wgrad(g0, a0) if need[2] else None
+        db0 = ops.colsum(g0) if (ctx.has_bias and need[3]) else None
+        da1 = dw1 = None
+        if a1 is not None:
+            g1 = dpre[:, O0:]
+            da1 = ops.linear([dict(a=g1, w=w1, w_trans=True)], n) if need[4] else None
+            dw1 = ops.wgrad(g1, a1) if need[5] else None
+        return None, da0, dw0, db0, da1, dw1
+
+
+class _SegmentReduce(torch.autograd.Function):
+    """rows (n*S, d) grouped by parent -> (n, d): mean or max over the S rows (nn_modules.py:197-198, 225-226, 240, 252)."""
+
+    @staticmethod
+    def forward(ctx, rows, S, mode):
+        rows = rows.contiguous()
+        n = rows.shape[0] // S
+        out = ops.gather_reduce(rows, None, n, S, mode, out_dtype=torch.float32)
+        ctx.S, ctx.mode = S, mode
+        ctx.save_for_backward(rows)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        rows, = ctx.saved_tensors
+        dout = dout.contiguous()
+        if ctx.mode == 'mean':
+            return ops.segment_broadcast(dout, ctx.S, 1.0 / ctx.S), None, None
+        return ops.segment_max_backward(rows, dout, ctx.S), None, None
+
+
+class _AttentionSum(torch.autograd.Function):
+    """m_p = sum_j softmax_j(<na_pj, xa_p>) n_pj (nn_modules.py:309-315).  The gradient reaches `neibs` twice: directly (here)
+    and through na = att(neibs), which autograd routes through the _Linear calls that produced it."""
+
+    @staticmethod
+    def forward(ctx, neibs, na, xa, S):
+        neibs, na, xa = neibs.contiguous(), na.contiguous(), xa.contiguous()
+        n = xa.shape[0]
+        w = ops.attention_weights(na, xa, n, S)
+        out = ops.gather_reduce(neibs, None, n, S, 'sum', weights=w, out_dtype=torch.float32)
+        ctx.S = S
+        ctx.save_for_backward(neibs, na, xa, w)
+        return out
+
+    @staticmethod
+    def backward(ctx, dm):
+        neibs, na, xa, w = ctx.saved_tensors
+        dn, dna, dxa = ops.attention_sum_backward(neibs, dm.contiguous(), w, na, xa, ctx.S)
+        return dn, dna, dxa, None
+
+
+class _Embedding(torch.autograd.Function):
+    """weight[ids] (nn.Embedding, nn_modules.py:146,149) with its dense gradient."""
+
+    @staticmethod
+    def forward(ctx, weight, ids):
+        ctx.rows = weight.shape[0]
+        ctx.save_for_backward(ids)
+        return ops.gather_rows(weight, ids, out_dtype=torch.float32)
+
+    @staticmethod
+    def backward(ctx, drows):
+        ids, = ctx.saved_tensors
+        return ops.embedding_backward(drows.contiguous(), ids, ctx.rows), None
+
+
+class _L2Normalize(torch.autograd.Function):
+    """F.normalize(z, dim=1) (models.py:90)."""
+
+    @staticmethod
+    def forward(ctx, z):
+        z = z.contiguous()
+        ctx.save_for_backward(z)
+        return ops.l2_normalize(z)
+
+    @staticmethod
+    def backward(ctx, dzn):
+        z, = ctx.saved_tensors
+        return ops.l2_normalize_backward(z, dzn)
+
+
+def linear_fn(a, weight, bias=None, act=None):
+    """act(a . weight^T + bias) through the library, differentiable."""
+    return _Linear.apply(act, a, weight, bias, None, None)
 
 
 # --
@@ -153,13 +275,10 @@ class NodeEmbeddingPrep(nn.Module):
     def forward(self, ids, feats, layer_idx=0):
         ids, _ = _cuda_ids(ids)
         look = ids if layer_idx > 0 else torch.full_like(ids, self.n_nodes)
-        n, dfe = ids.shape[0], (self.input_dim or 0)
-        out = torch.empty((n, dfe + self.embedding_dim), dtype=torch.float32, device='cuda')
-        ops.linear([dict(a=self.embedding.weight.data, ids=look, w=self.fc.weight.data, bias=self.fc.bias.data, col0=dfe)],
-                   n, out=out)
+        embs = linear_fn(_Embedding.apply(self.embedding.weight, look), self.fc.weight, self.fc.bias)
         if self.input_dim:
-            out[:, :dfe] = feats
-        return out
+            return torch.cat([_f32(feats), embs], dim=1)
+        return embs
 
 
 class LinearPrep(nn.Module):
@@ -169,7 +288,7 @@ class LinearPrep(nn.Module):
         self.output_dim = output_dim
 
     def forward(self, ids, feats, layer_idx=0):
-        return ops.linear([dict(a=feats.contiguous(), w=self.fc.weight.data)], feats.shape[0])
+        return linear_fn(_f32(feats), self.fc.weight)
 
 
 prep_lookup = {
@@ -200,8 +319,13 @@ class AggregatorMixin(object):
                           n, act=_act_name(self.activation))
 
     def _forward_rows(self, x, neibs):
-        x, neibs = x.contiguous(), neibs.contiguous()
-        return self._run(x, None, neibs, None, x.size(0), neibs.size(0) // x.size(0))
+        """The narrow contract `agg(x, neibs)` (models.py:86), differentiable w.r.t. x, neibs and the parameters."""
+        if self.combine_fn is not _cat:
+            raise NotImplementedError('gsage: only the default concat combine_fn is fused')
+        x, neibs = _f32(x), _f32(neibs)
+        S = neibs.size(0) // x.size(0)
+        agg = self._reduce_rows(x, neibs, S)
+        return _Linear.apply(_act_name(self.activation), x, self.fc_x.weight, None, agg, self.fc_neib.weight)
 
     def forward_ids(self, table, ids_self, ids_neib, S):
         return self._run(table, ids_self, table, ids_neib, ids_self.shape[0], S)
@@ -219,6 +343,9 @@ class MeanAggregator(nn.Module, AggregatorMixin):
         self.output_dim_ = output_dim
         self.activation = activation
         self.combine_fn = combine_fn
+
+    def _reduce_rows(self, x, neibs, S):
+        return _SegmentReduce.apply(neibs, S, 'mean')
 
     def _run(self, x, x_ids, nb, nb_ids, n, S):
         agg = ops.gather_reduce(nb, nb_ids, n, S, 'mean', d=self.fc_neib.in_features, out_dtype=torch.float32)
@@ -239,6 +366,10 @@ class PoolAggregator(nn.Module, AggregatorMixin):
         self.activation = activation
         self.pool_fn = pool_fn                          # 'max' | 'mean' (the reference passes lambdas)
         self.combine_fn = combine_fn
+
+    def _reduce_rows(self, x, neibs, S):
+        h = linear_fn(neibs, self.mlp[0].weight, self.mlp[0].bias, act='relu')
+        return _SegmentReduce.apply(h, S, self.pool_fn)
 
     def _run(self, x, x_ids, nb, nb_ids, n, S):
         h = ops.linear([dict(a=nb, ids=nb_ids, w=self.mlp[0].weight.data, bias=self.mlp[0].bias.data)], n * S, act='relu')
@@ -280,6 +411,11 @@ class AttentionAggregator(nn.Module, AggregatorMixin):
         t = ops.linear([dict(a=a, ids=ids, w=self.att[0].weight.data)], n, act='tanh')
         return ops.linear([dict(a=t, w=self.att[2].weight.data)], n)
 
+    def _reduce_rows(self, x, neibs, S):
+        assert S > 1, 'AttentionAggregator: S must be > 1'
+        att = lambda rows: linear_fn(linear_fn(rows, self.att[0].weight, act='tanh'), self.att[2].weight)
+        return _AttentionSum.apply(neibs, att(neibs), att(x), S)
+
     def _run(self, x, x_ids, nb, nb_ids, n, S):
         assert S > 1, 'AttentionAggregator: S must be > 1'
         w = ops.attention_weights(self._att(nb, nb_ids, n * S), self._att(x, x_ids, n), n, S)
@@ -307,6 +443,12 @@ class LSTMAggregator(nn.Module, AggregatorMixin):
         self.output_dim_ = output_dim
         self.activation = activation
         self.combine_fn = combine_fn
+
+    def _forward_rows(self, x, neibs):
+        # forward only (no backward through the recurrence is built): the inputs are detached so that a caller who asks for
+        # gradients gets torch's "does not require grad" error instead of silently missing ones
+        x, neibs = _f32(x).detach().contiguous(), _f32(neibs).detach().contiguous()
+        return self._run(x, None, neibs, None, x.size(0), neibs.size(0) // x.size(0))
 
     def _run(self, x, x_ids, nb, nb_ids, n, S):
         H, dev = self.lstm.hidden_size, x.device

@@ -101,19 +101,21 @@ def gather_rows(table, ids, d=None, out_dtype=None):
 
 
 def linear(segments, n, act=None, out=None, out_dtype=torch.float32, exact=True):
-    """segments: list of dicts(a=, w=, ids=None, bias=None, col0=0, d=None, S=1).  One launch, <= 2 column ranges.
-    S > 1: row r of that segment's operand is mean_j a[ids[r*S + j]] (fused gather+mean)."""
+    """segments: list of dicts(a=, w=, ids=None, bias=None, col0=0, d=None, S=1, w_trans=False).  One launch, <= 2 column ranges.
+    S > 1: row r of that segment's operand is mean_j a[ids[r*S + j]] (fused gather+mean).
+    w_trans: out = a . w instead of a . w^T (w is (d, O): the data gradient of a Linear; fp32 FFMA kernel only)."""
     segs = (_lib.LinearSeg * len(segments))()
     width = 0
     for i, sgm in enumerate(segments):
         a, w = sgm['a'], sgm['w']
         _bind_device(a)
-        d = sgm.get('d') or w.shape[1]
+        d = sgm.get('d') or (w.shape[0] if sgm.get('w_trans') else w.shape[1])
         assert w.is_cuda and w.dim() == 2 and w.stride(1) == 1
         bias = sgm.get('bias')
         segs[i] = _lib.LinearSeg(ptr(a), dt(a), _rows2d(a), _ids_arg(sgm.get('ids')), ptr(w), dt(w), _rows2d(w), d,
-                                 w.shape[0], ptr(bias), sgm.get('col0', 0), int(sgm.get('S', 1)), 0, a.shape[0])
-        width = max(width, sgm.get('col0', 0) + w.shape[0])
+                                 (w.shape[1] if sgm.get('w_trans') else w.shape[0]), ptr(bias), sgm.get('col0', 0), int(sgm.get('S', 1)),
+                                 1 if sgm.get('w_trans') else 0, a.shape[0])
+        width = max(width, sgm.get('col0', 0) + (w.shape[1] if sgm.get('w_trans') else w.shape[0]))
     if out is None:
         out = torch.empty((n, width), dtype=out_dtype, device=segments[0]['a'].device)
     check(lib().gsage_linear(segs, len(segments), n, _lib.ACT[act], ptr(out), dt(out), _rows2d(out), 2 if exact == 'x3' else (1 if exact else 0), stream()))
@@ -139,6 +141,79 @@ def wgrad(g, a, ids=None, n=None, exact=True):
     check(lib().gsage_wgrad(ptr(g), dt(g), _rows2d(g), O, ptr(a), dt(a), _rows2d(a), a.shape[0], _ids_arg(ids), d, n, ptr(dw), d,
                             1 if exact else 0, stream()))
     return dw
+
+
+# ---- gradient kernels of the narrow plug-in API (narrow_backward.cu); everything fp32 ------------------------------
+def _f32c(t):
+    assert t.is_cuda and t.dtype == torch.float32 and t.dim() == 2 and t.stride(1) == 1, 'gsage: expected a row-major fp32 CUDA matrix'
+    return t
+
+
+def act_backward(dout, out, act):
+    """dout * act'(out) for act in (None, 'relu', 'tanh'); `out` is the post-activation value."""
+    if act is None:
+        return dout
+    dout, out = _f32c(dout), _f32c(out)
+    _bind_device(dout)
+    dpre = torch.empty(dout.shape, dtype=torch.float32, device=dout.device)
+    check(lib().gsage_act_backward(ptr(dout), _rows2d(dout), ptr(out), _rows2d(out), dout.shape[0], dout.shape[1], _lib.ACT[act],
+                                   ptr(dpre), _rows2d(dpre), stream()))
+    return dpre
+
+
+def segment_broadcast(src, S, scale=1.0):
+    src = _f32c(src)
+    _bind_device(src)
+    dst = torch.empty((src.shape[0] * S, src.shape[1]), dtype=torch.float32, device=src.device)
+    check(lib().gsage_segment_broadcast(ptr(src), _rows2d(src), src.shape[0], src.shape[1], S, float(scale), ptr(dst), _rows2d(dst), stream()))
+    return dst
+
+
+def segment_max_backward(h, dpooled, S):
+    h, dpooled = _f32c(h), _f32c(dpooled)
+    _bind_device(h)
+    dh = torch.empty(h.shape, dtype=torch.float32, device=h.device)
+    check(lib().gsage_segment_max_backward(ptr(h), _rows2d(h), ptr(dpooled), _rows2d(dpooled), dpooled.shape[0], S, h.shape[1], ptr(dh), _rows2d(dh),
+                                           stream()))
+    return dh
+
+
+def attention_sum_backward(neibs, dm, w, na, xa, S):
+    """-> (dneibs: the direct path w_j dM_p, dna, dxa)."""
+    neibs, dm, na, xa = _f32c(neibs), _f32c(dm), _f32c(na.contiguous()), _f32c(xa.contiguous())
+    _bind_device(neibs)
+    n, d, H = dm.shape[0], neibs.shape[1], na.shape[1]
+    dn = torch.empty((n * S, d), dtype=torch.float32, device=neibs.device)
+    dna, dxa = torch.empty_like(na), torch.empty_like(xa)
+    scratch = torch.empty((n * S,), dtype=torch.float32, device=neibs.device)
+    check(lib().gsage_attention_sum_backward(ptr(neibs), _rows2d(neibs), d, n, S, ptr(dm), _rows2d(dm), ptr(w), ptr(na), ptr(xa), H, ptr(dn), _rows2d(dn),
+                                             ptr(dna), ptr(dxa), ptr(scratch), stream()))
+    return dn, dna, dxa
+
+
+def colsum(x):
+    x = _f32c(x.contiguous())
+    _bind_device(x)
+    out = torch.empty((x.shape[1],), dtype=torch.float32, device=x.device)
+    check(lib().gsage_colsum(ptr(x), x.shape[0], x.shape[1], ptr(out), stream()))
+    return out
+
+
+def embedding_backward(drows, ids, table_rows):
+    drows = _f32c(drows)
+    _bind_device(drows)
+    grad = torch.zeros((table_rows, drows.shape[1]), dtype=torch.float32, device=drows.device)
+    check(lib().gsage_embedding_backward(ptr(drows), _rows2d(drows), drows.shape[1], _ids_arg(ids), ids.shape[0], ptr(grad), grad.shape[1], table_rows,
+                                         stream()))
+    return grad
+
+
+def l2_normalize_backward(z, dzn):
+    z, dzn = _f32c(z.contiguous()), _f32c(dzn.contiguous())
+    _bind_device(z)
+    dz = torch.empty_like(z)
+    check(lib().gsage_l2_normalize_backward(ptr(z), ptr(dzn), z.shape[0], z.shape[1], ptr(dz), stream()))
+    return dz
 
 
 def attention_weights(na, xa, n_parents, S):

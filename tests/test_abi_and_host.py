@@ -35,7 +35,7 @@ def test_library_exports_every_declared_symbol(built):
 def test_python_binding_covers_the_header(built):
     from pytorch_graphsage_b200 import _lib
     assert sorted(_lib.EXPORTS) == header_functions()
-    assert _lib.lib().gsage_abi_version() == 2
+    assert _lib.lib().gsage_abi_version() == 3
 
 
 def test_struct_layouts_match_the_header(built):

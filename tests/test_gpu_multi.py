@@ -38,7 +38,7 @@ def _worker(rank, world, port, q):
     first = int(sum(shard_seeds(ids, r, world).shape[0] for r in range(rank)))
     g.set_seeds(int(fix['seed']))                                  # every rank: the same stream as the single process
     side = torch.cuda.Stream()
-    preds, _ = model.train_step(mine, feats, tmine.cuda(), F.cross_entropy, optimizer=None, clip=None,
+    preds = model.train_step(mine, feats, tmine.cuda(), F.cross_entropy, optimizer=False, clip=None,
                                 grad_scale=mine.shape[0] / ids.shape[0], overlap_stream=side, shard=(ids.shape[0], first))
     torch.cuda.synchronize()
     st = g.default_rng().get_state()

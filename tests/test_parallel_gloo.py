@@ -35,10 +35,9 @@ def _worker(rank, world, port, out):
     grads = torch.autograd.grad(loss, params)
     for p, g in zip(params, grads):
         bucket.grad_of(p).copy_(g)
-    scale = mine.shape[0] / ids.shape[0]
-    bucket.flat.mul_(scale)                                    # weight BEFORE the sum == sum of (local/global) * local mean grads
-    bucket.all_reduce_head(1.0)
-    bucket.all_reduce_tail(1.0)
+    scale = mine.shape[0] / ids.shape[0]                       # 51/101 on rank 0, 50/101 on rank 1: uneven shards
+    bucket.all_reduce_head(scale)                              # the bucket weights BEFORE the sum: sum_r scale_r * g_r
+    bucket.all_reduce_tail(scale)
     ref = torch.autograd.grad(lin2(torch.relu(lin1(x))).pow(2).mean(), params)
     ok = all(torch.allclose(p.grad, r, rtol=1e-5, atol=1e-6) for p, r in zip(params, ref))
     head_first = bucket.params[0] is lin2.weight or bucket.params[0] is lin2.bias
