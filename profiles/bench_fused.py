@@ -1,8 +1,8 @@
 #!/usr/bin/env python
-"""Micro-benchmark for the EXPERIMENTAL fused kernel (gather_mean_project_umma.cu) against the two launches it replaces, on the
+"""Micro-benchmark for the fused kernel (gather_mean_project_umma.cu) against the two launches it replaces, on the
 layer-1 shape of the reddit workload: n parents x S = 10 neighbours, d = 602, O = 128, bf16.  CUDA-event timed, L2 flushed.
 
-    GSAGE_FUSED_LAYER=1 python profiles/bench_fused.py            (N=409600 by default; set N / S / D to change the shape)
+    python profiles/bench_fused.py            (N=409600 by default; set N / S / D to change the shape)
 
   unfused:  gather_reduce (mean rows -> HBM)  +  linear [fc_x(table[ids]) | fc_neib(M)]          (what the engine runs today)
   fused:    gather_mean_project (neighbour half, M never leaves the SM)  +  linear [fc_x(table[ids])]"""
@@ -53,10 +53,12 @@ def timed(fn, reps=10):
 
 t_u = timed(unfused)
 print('unfused: %.1f us' % (t_u * 1e3))
-if os.environ.get('GSAGE_FUSED_LAYER'):
-    t_f = timed(fused)
-    diff = (out_a.float() - out_b.float()).abs().max().item()
-    byt = n * (S * 608 * 2 + 8 * S + 608 * 2 + 8 + 2 * O * 2)
-    print('fused:   %.1f us  (%.0f GB/s algorithmic)   max |fused - unfused| = %.3g' % (t_f * 1e3, byt / t_f / 1e6, diff))
-else:
-    print('set GSAGE_FUSED_LAYER=1 to time the fused kernel')
+t_f = timed(fused)
+diff = (out_a.float() - out_b.float()).abs().max().item()
+ldb = (d + 15) // 16 * 16 * 2
+byt = n * (S * ldb + 8 * S + ldb + 8 + 2 * O * 2)
+print('fused:   %.1f us  (%.0f GB/s algorithmic)   max |fused - unfused| = %.3g' % (t_f * 1e3, byt / t_f / 1e6, diff))
+t_n = timed(lambda: g.ops.gather_mean_project(table, ids_nb, n, S, wn, act='relu', out=out_b, col0=O))
+t_g = timed(lambda: g.ops.gather_reduce(table, ids_nb, n, S, 'mean', d=d, out=m))
+print('neighbour half alone: fused kernel %.1f us (%.0f GB/s on S rows + ids + out)   gather_reduce %.1f us (%.0f GB/s)' %
+      (t_n * 1e3, n * (S * ldb + 8 * S + O * 2) / t_n / 1e6, t_g * 1e3, n * (S * ldb + 8 * S + ldb) / t_g / 1e6))

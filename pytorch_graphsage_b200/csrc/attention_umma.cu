@@ -10,9 +10,13 @@
 // rows themselves.  Here a tile of R = floor(128/S)*S neighbour rows (whole parents) lands in shared memory once, by TMA
 // (tile::gather4 for rows by id, all k-chunks of the tile), and everything else happens on chip:
 //   warp  8     MMA issue   D1[128 rows, 32] = tile . W1^T on tcgen05 (W1 resident in smem, accumulator in TMEM)
-//   warps 0-7   compute     tcgen05.ld -> +b1 -> tanh -> W2 (fp32 FFMA, W2 broadcast from smem) -> score against a(x_i)
+//   warps 0-7   compute     u_p = W2^T a(x_p) for the tile's parents (while the tile is still landing)
+//                           tcgen05.ld -> +b1 -> tanh -> score = <tanh(.), u_p>
 //                           -> softmax over the S rows of each parent (scores exchanged through smem)
 //                           -> weighted sum of the RAW rows, re-read from the swizzled smem tile -> m_i to HBM
+// The score is  <W2 t, a(x)> = <t, W2^T a(x)>: W2 moves from the N*S neighbour rows onto the N parents (32 x 32 FFMA per PARENT
+// instead of per row).  Round 1's kernel applied W2 per row -- 1024 FFMA + 128 LDS per row, and ncu showed it bound by FP32 issue
+// (tensor pipe 3 %, DRAM 9 %, 257 M instructions): 0.41 of the HBM peak.  Same value up to fp32 rounding (re-association).
 //   warps 9-12  producers   TMA loads of the next tile into the other buffer while this one is being reduced
 // a(x_i) (N x 32) is computed by the caller with the ordinary projection kernels: N rows, not N*S.
 // bf16 operands only (the fp32-exact engine keeps the unfused FFMA chain); attention width H == 32; tanh.approx.f32.
@@ -59,9 +63,10 @@ __global__ void __launch_bounds__(kAtThreads, 1) attention_fused_kernel(const At
     uint8_t* w1s = smem + (size_t)P.nbuf * P.buf_bytes;
     float* w2s = (float*)(w1s + (size_t)P.kchunks * kAtW1Chunk);
     float* b1s = w2s + AH * AH;
-    float* sc = b1s + AH;                                 // [2][128] partial scores (one per half of the W2 outputs)
+    float* sc = b1s + AH;                                 // [2][128] partial scores (one per half of the 32 attention units)
     float* wt = sc + 256;                                 // [128] softmax weights
-    uint64_t* bars = (uint64_t*)(wt + 128);
+    float* us = wt + 128;                                 // [64][32] u_p = W2^T a(x_p) of the tile's parents (PT <= 64)
+    uint64_t* bars = (uint64_t*)(us + 64 * AH);
     uint32_t* tmem_slot = (uint32_t*)(bars + 8);
     const uint32_t bar_base = smem_u32(bars);
     auto full_bar = [&](int b) { return bar_base + 8u * b; };          // tile b has landed (tx bytes)
@@ -101,42 +106,32 @@ __global__ void __launch_bounds__(kAtThreads, 1) attention_fused_kernel(const At
         for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x, ++it) {
             const int b = nbuf == 2 ? (it & 1) : 0;
             const uint32_t par = nbuf == 2 ? ((it >> 1) & 1) : (it & 1);
-            mbar_wait(dfull_bar(b), par, P.err);
-            tc_fence_after();
             const int64_t parent0 = (int64_t)tile * PT;
             const bool live = row < P.R && parent0 + my_parent < P.n_parents;
-            // ---- a(n) for this row: tanh(D1 + b1), then this half's 16 outputs of W2, dotted with a(x_parent) ----
-            uint32_t r[32];
-            tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(b * AH), r);
-            tmem_ld_wait();
-            float t[AH];
+            // ---- u_p = W2^T a(x_p) for the parents of this tile: u[p][k] = sum_o W2[o][k] xa[p][o]  (independent of the tile's
+            //      rows: runs while they are still landing / being multiplied) ----
+            for (int i = threadIdx.x; i < PT * AH; i += 32 * kAtComputeWarps) {
+                const int p = i >> 5, k = i & 31;
+                float acc = 0.0f;
+                if (parent0 + p < P.n_parents) {
+                    const float* xa = P.xa + (parent0 + p) * AH;
 #pragma unroll
-            for (int k = 0; k < AH; ++k) t[k] = tanh_approx(__uint_as_float(r[k]) + b1s[k]);
+                    for (int o = 0; o < AH; ++o) acc = fmaf(w2s[o * AH + k], __ldg(xa + o), acc);
+                }
+                us[i] = acc;
+            }
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            mbar_wait(dfull_bar(b), par, P.err);
+            tc_fence_after();
+            // ---- this half's 16 attention units of the row: tanh(D1 + b1) . u_parent ----
+            uint32_t r[16];
+            tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(b * AH + half * 16), r);
+            tmem_ld_wait();
             float part = 0.0f;
             if (live) {
-                const float4* xav = reinterpret_cast<const float4*>(P.xa + (parent0 + my_parent) * AH + half * 16);
-                float xa[16];
+                const float* u = us + my_parent * AH + half * 16;
 #pragma unroll
-                for (int q = 0; q < 4; ++q) { const float4 v = __ldg(xav + q); xa[4 * q] = v.x; xa[4 * q + 1] = v.y; xa[4 * q + 2] = v.z; xa[4 * q + 3] = v.w; }
-                // 16 independent accumulators (the first version ran one 32-long dependent FFMA chain per output and was
-                // latency-bound: 60 % of the kernel's samples); W2 rows come from smem as warp-uniform broadcast LDS.128
-                float acc[16];
-#pragma unroll
-                for (int o = 0; o < 16; ++o) acc[o] = 0.0f;
-                const uint32_t w2_u = smem_u32(w2s) + (uint32_t)(half * 16 * AH * 4);
-#pragma unroll
-                for (int q = 0; q < AH / 4; ++q) {
-#pragma unroll
-                    for (int o = 0; o < 16; ++o) {
-                        float4 w;
-                        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(w.x), "=f"(w.y), "=f"(w.z), "=f"(w.w)
-                                     : "r"(w2_u + (uint32_t)((o * AH + 4 * q) * 4)));
-                        acc[o] = fmaf(w.x, t[4 * q], acc[o]); acc[o] = fmaf(w.y, t[4 * q + 1], acc[o]);
-                        acc[o] = fmaf(w.z, t[4 * q + 2], acc[o]); acc[o] = fmaf(w.w, t[4 * q + 3], acc[o]);
-                    }
-                }
-#pragma unroll
-                for (int o = 0; o < 16; ++o) part = fmaf(acc[o], xa[o], part);
+                for (int k = 0; k < 16; ++k) part = fmaf(tanh_approx(__uint_as_float(r[k]) + b1s[half * 16 + k]), u[k], part);
             }
             sc[half * 128 + row] = part;
             asm volatile("bar.sync 1, 256;" ::: "memory");
@@ -267,7 +262,7 @@ bool attention_fused_eligible(const void* a, int a_dtype, int64_t lda, int d, co
     const int64_t es_out = out_dtype == GSAGE_BF16 ? 2 : 4;
     if ((ld_out * es_out) % 16 != 0 || ld_out < (d + 7) / 8 * 8) return false;           // whole 16-byte chunks are stored
     const int kchunks = (d + 63) / 64;
-    const int fixed = 1024 + kchunks * kAtW1Chunk + AH * AH * 4 + AH * 4 + 384 * 4 + 256;
+    const int fixed = 1024 + kchunks * kAtW1Chunk + AH * AH * 4 + AH * 4 + 384 * 4 + 64 * AH * 4 + 256;
     return kchunks * kAtChunk + fixed <= kAtSmemLimit && n_parents * (int64_t)S < (1LL << 31);
 }
 
@@ -284,7 +279,7 @@ int attention_fused_launch(const void* a, int64_t lda, const int64_t* ids, int d
     U.kchunks = (d + 63) / 64;
     U.n_tiles = (int)ceil_div(n_parents, U.PT);
     U.buf_bytes = U.kchunks * kAtChunk;
-    const int fixed = 1024 + U.kchunks * kAtW1Chunk + AH * AH * 4 + AH * 4 + 384 * 4 + 256;
+    const int fixed = 1024 + U.kchunks * kAtW1Chunk + AH * AH * 4 + AH * 4 + 384 * 4 + 64 * AH * 4 + 256;
     U.nbuf = (2 * U.buf_bytes + fixed <= kAtSmemLimit) ? 2 : 1;
     U.out = out; U.out_bf16 = out_dtype == GSAGE_BF16; U.ld_out = ld_out;
     if (!g_att_err) {

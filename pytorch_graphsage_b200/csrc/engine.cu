@@ -261,7 +261,7 @@ static int apply_aggregator(gsage_engine* e, int layer, const RowSrc& x, const R
         const bool dominant = layer == 0 && n > e->B;
         if (T == GSAGE_BF16 && !e->keep_activations && e->w_n[layer].dtype == GSAGE_BF16 && out_dtype == GSAGE_BF16 &&
             gather_mean_project_eligible(nb.base, nb.dtype, nb.ld, d, S, e->w_n[layer].p, GSAGE_BF16, e->w_n[layer].ld, O)) {
-            // EXPERIMENTAL, GSAGE_FUSED_LAYER=1 (forward only: the reduced rows M are never written, so no backward): the
+            // forward only (the reduced rows M are never written, so no backward; GSAGE_FUSED_LAYER=0 turns it off): the
             // neighbour half gather + mean + projection in one kernel, the self half as a one-segment projection
             const int p_f = dominant ? e->prof.begin(GSAGE_PROF_REDUCE, s) : -1;
             GS_TRY(gather_mean_project_launch(nb.base, nb.ld, nb.table_rows, d, nb.ids, n, S, e->w_n[layer].p, e->w_n[layer].ld, O,

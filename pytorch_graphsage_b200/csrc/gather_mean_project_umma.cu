@@ -1,5 +1,4 @@
-// gather_mean_project_umma.cu -- EXPERIMENTAL (off by default, GSAGE_FUSED_LAYER=1; not yet run on a GPU when committed):
-// the neighbour half of the mean aggregator in ONE kernel,
+// gather_mean_project_umma.cu -- the neighbour half of the mean aggregator in ONE kernel (GSAGE_FUSED_LAYER=0 turns it off),
 //     out[p, col0 : col0 + O] = act( (1/S) sum_j table[ids[p*S + j]] . Wn^T + bias )        (nn_modules.py:197-200)
 // so that the reduced rows M never travel to HBM and back (17 % of the bytes of a reddit step: DESIGN.md section 3).
 //
@@ -18,8 +17,17 @@
 //   * A is single-buffered.  A producer warp issues the loads of its first parent of tile i+1 BEFORE it waits for the MMAs of
 //     tile i to retire (the wait sits in front of the first shared-memory store), so the HBM pipe does not drain.
 //   warps 0-3   epilogue     tcgen05.ld -> bias / activation -> bf16 | fp32 -> HBM      (two TMEM buffers of O columns)
-//   warp  4     MMA issue    loads W once (TMA), then per tile nk x 4 tcgen05.mma M=128, N=O, K=16
-//   warps 5-24  producers    gather + mean -> swizzled A tile
+//   warp  4     MMA issue    loads W once (TMA), then per tile nk x 4 tcgen05.mma M=128, N=O, K=16   (warps 5-7: idle, they only
+//                            exist so that the issuer sits in a warpgroup of its own for setmaxnreg)
+//   warps 8-23  producers    gather + mean -> swizzled A tile
+// First measurement (round 2, 20 producer warps x 6 loads in flight per lane, 80 registers for everybody): 4.1 TB/s, warps 39 %
+// active, long-scoreboard bound -- 61 KB in flight per SM is not enough to cover HBM latency, and 48 parents over 20 warps leave
+// 20 % of the producers idle per tile.  Hence: the register file is re-balanced with setmaxnreg (epilogue 56, issuer group 24,
+// producers 96 registers -- the pool a warpgroup can grow from is what the OTHER warpgroups of the CTA released, so the three
+// budgets must fit in the 768 x 80 registers the CTA was launched with; a first version asked for 104 and dead-locked in
+// setmaxnreg.inc), 16 producers take exactly TR / 16 parents each, every lane keeps U x CPL = 10-12 loads in flight,
+// the fanout is a compile-time constant so that the rounds of a parent are unrolled and the next round's loads are issued while the
+// previous round is being accumulated, and the ids of the next parent are fetched one parent ahead.
 // The self half  act(table[ids_self] . Wx^T)  stays on linear_ws_umma_kernel (one segment).
 #include "linear.cuh"
 #include "umma_ptx.cuh"
@@ -29,8 +37,11 @@
 namespace gsage {
 
 static constexpr int kFgEpiWarps = 4;
-static constexpr int kFgGatherWarps = 20;
-static constexpr int kFgThreads = 32 * (kFgEpiWarps + 1 + kFgGatherWarps);     // 800: <= 80 registers per thread
+static constexpr int kFgIssueWarps = 4;        // warp 4 issues; 5-7 idle (one warpgroup: setmaxnreg is per warpgroup)
+static constexpr int kFgGatherWarps = 16;
+static constexpr int kFgThreads = 32 * (kFgEpiWarps + kFgIssueWarps + kFgGatherWarps);     // 768: launched with 80 registers per thread
+template <int N> __device__ __forceinline__ void setmaxnreg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
+template <int N> __device__ __forceinline__ void setmaxnreg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
 static constexpr int kFgSmemLimit = 227 * 1024;
 static constexpr int kFgMaxCPL = 4;            // 16-byte units per lane per row: rows up to 128 units = 1024 bf16
 
@@ -83,8 +94,8 @@ __device__ __forceinline__ void fg_store32(const uint32_t* r, const float* bias,
     }
 }
 
-// CPL = 16-byte units per lane per row (ceil(nk * 8 / 32)), U = neighbour rows in flight per lane
-template <int CPL, int U>
+// CPL = 16-byte units per lane per row (ceil(nk * 8 / 32)), U = neighbour rows in flight per lane, ST = fanout (0: run time)
+template <int CPL, int U, int ST>
 __global__ void __launch_bounds__(kFgThreads, 1) gather_mean_project_kernel(const FgParams P, const __grid_constant__ CUtensorMap w_map) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     // carve: [A tile: nk planes of TR x 128 B] [W: nk planes of O x 128 B] [barriers]   (A first: UMMA walks 128 rows per plane,
@@ -120,6 +131,7 @@ __global__ void __launch_bounds__(kFgThreads, 1) gather_mean_project_kernel(cons
 
     if (warp < kFgEpiWarps) {
         // =========================== EPILOGUE ===========================
+        setmaxnreg_dec<56>();
         const int row_in_tile = warp * 32 + lane;            // TMEM lane == tile row; only rows < TR carry a parent
         int it = 0;
         for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x, ++it) {
@@ -146,9 +158,10 @@ __global__ void __launch_bounds__(kFgThreads, 1) gather_mean_project_kernel(cons
             tc_fence_before();
             mbar_arrive(t_empty(buf));
         }
-    } else if (warp == kFgEpiWarps) {
-        // =========================== W LOAD + MMA ISSUER (one thread) ===========================
-        if (lane == 0) {
+    } else if (warp < kFgEpiWarps + kFgIssueWarps) {
+        // =========================== W LOAD + MMA ISSUER (one thread of warp 4) ===========================
+        setmaxnreg_dec<24>();
+        if (warp == kFgEpiWarps && lane == 0) {
             mbar_arrive_expect_tx(w_full, (uint32_t)P.nk * w_plane);
             for (int kc = 0; kc < P.nk; ++kc) tma_load_2d(smem_u32(w_area) + (uint32_t)kc * w_plane, &w_map, kc * 64, 0, w_full);
             mbar_wait(w_full, 0, P.err);
@@ -177,30 +190,42 @@ __global__ void __launch_bounds__(kFgThreads, 1) gather_mean_project_kernel(cons
         __syncwarp();
     } else {
         // =========================== PRODUCERS: gather + mean -> swizzled A tile ===========================
+        setmaxnreg_inc<96>();                                               // 128 x 56 + 128 x 24 + 512 x 96 <= 768 x 80
         constexpr int VEC = 8;                                             // bf16 per 16-byte unit
-        const int gw = warp - (kFgEpiWarps + 1);
+        const int gw = warp - (kFgEpiWarps + kFgIssueWarps);
         const uint32_t a_u = smem_u32(a_tile);
         const int units_tile = P.nk * 8;                                   // 16-byte units per A row (a multiple of 8 >= units_ld)
+        const int S = ST > 0 ? ST : P.S;
+        auto fetch_id = [&](int64_t parent) -> int64_t {                   // lane j holds the id of neighbour j of `parent`
+            if (parent >= P.n || lane >= S) return -1;
+            const int64_t at = parent * (int64_t)S + lane;
+            return P.ids ? __ldg(P.ids + at) : at;
+        };
         int it = 0;
+        int64_t next_id = fetch_id((int64_t)blockIdx.x * P.TR + gw);
         for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x, ++it) {
             bool may_store = (it == 0);                                    // tile 0: the A tile is free from the start
             for (int r = gw; r < P.TR; r += kFgGatherWarps) {
-                const int64_t parent = (int64_t)tile * P.TR + r;
+                const int64_t my_id = next_id;
+                {   // one parent ahead: the ids of this warp's next parent (next row of this tile, or its first row of the next tile)
+                    const bool wrap = r + kFgGatherWarps >= P.TR;
+                    const int64_t ntile = wrap ? (int64_t)tile + gridDim.x : (int64_t)tile;
+                    next_id = ntile < P.n_tiles ? fetch_id(ntile * P.TR + (wrap ? gw : r + kFgGatherWarps)) : -1;
+                }
                 float acc[CPL][VEC];
 #pragma unroll
                 for (int c = 0; c < CPL; ++c)
 #pragma unroll
                     for (int e = 0; e < VEC; ++e) acc[c][e] = 0.0f;
-                if (parent < P.n) {
-                    const int64_t first = parent * (int64_t)P.S;
-                    int64_t my_id = -1;
-                    if (lane < P.S) my_id = P.ids ? __ldg(P.ids + first + lane) : (first + lane);
-                    for (int jj = 0; jj < P.S; jj += U) {
+                {
+#pragma unroll
+                    for (int jj = 0; jj < (ST > 0 ? ST : 32); jj += U) {
+                        if (ST == 0 && jj >= S) break;
                         uint4 v[U][CPL];
 #pragma unroll
                         for (int u = 0; u < U; ++u) {
                             const int64_t id = __shfl_sync(0xFFFFFFFFu, my_id, min(jj + u, 31));
-                            const bool live = (jj + u < P.S) && ((uint64_t)id < (uint64_t)P.table_rows);
+                            const bool live = (jj + u < S) && ((uint64_t)id < (uint64_t)P.table_rows);
                             const __nv_bfloat16* row = P.table + id * P.ld;
 #pragma unroll
                             for (int c = 0; c < CPL; ++c) {
@@ -260,11 +285,12 @@ static int fg_tile_rows(int nk, int O) {
     const int left = kFgSmemLimit - fixed - nk * O * 128;
     if (left <= 0) return 0;
     int tr = left / (nk * 128) / 8 * 8;
+    if (tr >= kFgGatherWarps) tr = tr / kFgGatherWarps * kFgGatherWarps;     // every producer warp takes the same number of parents
     return tr > 128 ? 128 : tr;
 }
 
 bool gather_mean_project_eligible(const void* table, int dtype, int64_t ld, int d, int S, const void* w, int w_dtype, int64_t ldw, int O) {
-    if (!getenv("GSAGE_FUSED_LAYER")) return false;
+    if (const char* f = getenv("GSAGE_FUSED_LAYER")) { if (atoi(f) == 0) return false; }
     if (dtype != GSAGE_BF16 || w_dtype != GSAGE_BF16 || S < 1 || S > 32 || d < 1) return false;
     if (O % 16 != 0 || O < 16 || O > 128) return false;                     // one TMEM buffer = 128 columns
     if ((reinterpret_cast<uintptr_t>(table) & 15u) || (reinterpret_cast<uintptr_t>(w) & 15u) || ld % 8 != 0 || ldw % 8 != 0) return false;
@@ -303,19 +329,25 @@ int gather_mean_project_launch(const void* table, int64_t ld, int64_t table_rows
     GS_CHECK_ARG(smem <= (size_t)kFgSmemLimit, "gather_mean_project: %zu bytes of shared memory needed", smem);
     const int grid = P.n_tiles < sm_count() ? P.n_tiles : sm_count();
     const int cpl = (P.nk * 8 + 31) / 32;
-#define GS_FG(C, UU)                                                                                                        \
+#define GS_FG(C, UU, SS)                                                                                                    \
     do {                                                                                                                    \
         static bool attr_set = false;                                                                                       \
         if (!attr_set) {                                                                                                    \
-            GS_CUDA(cudaFuncSetAttribute(gather_mean_project_kernel<C, UU>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFgSmemLimit)); \
+            GS_CUDA(cudaFuncSetAttribute(gather_mean_project_kernel<C, UU, SS>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFgSmemLimit)); \
             attr_set = true;                                                                                                \
         }                                                                                                                   \
-        gather_mean_project_kernel<C, UU><<<grid, kFgThreads, smem, s>>>(P, w_map);                                         \
+        gather_mean_project_kernel<C, UU, SS><<<grid, kFgThreads, smem, s>>>(P, w_map);                                     \
     } while (0)
-    if (cpl == 1) GS_FG(1, 5);
-    else if (cpl == 2) GS_FG(2, 4);
-    else if (cpl == 3) GS_FG(3, 2);
-    else GS_FG(4, 2);
+    // U x CPL 16-byte loads in flight per lane: 10-12 (40-48 of the producers' 96 registers)
+#define GS_FG_S(C, UU)                                                                                                      \
+    do {                                                                                                                    \
+        if (S == 10) GS_FG(C, UU, 10); else if (S == 25) GS_FG(C, UU, 25); else GS_FG(C, UU, 0);                            \
+    } while (0)
+    if (cpl == 1) GS_FG_S(1, 10);             // rows <= 512 B: a whole fanout-10 parent in one round
+    else if (cpl == 2) GS_FG_S(2, 5);
+    else if (cpl == 3) GS_FG_S(3, 4);
+    else GS_FG_S(4, 3);
+#undef GS_FG_S
 #undef GS_FG
     GS_LAUNCHED();
     return GSAGE_OK;
@@ -331,7 +363,7 @@ extern "C" int gsage_gather_mean_project(const void* table_dev, int dtype, int64
     GS_CHECK_ARG(table_dev && w_dev && out_dev && n_parents >= 0 && col0 >= 0 && col0 + O <= ld_out, "gather_mean_project: bad arguments");
     GS_CHECK_ARG(out_dtype == GSAGE_F32 || out_dtype == GSAGE_BF16, "gather_mean_project: bad out dtype");
     GS_CHECK_ARG(gather_mean_project_eligible(table_dev, dtype, ld, d, S, w_dev, w_dtype, ldw, O),
-                 "gather_mean_project: experimental kernel -- needs GSAGE_FUSED_LAYER=1, a bf16 table and W with 16-byte aligned zero-padded "
+                 "gather_mean_project: needs a bf16 table and W with 16-byte aligned zero-padded "
                  "rows, S <= 32, O %% 16 == 0 and <= 128, and weights that fit in shared memory next to a tile of >= 16 parents");
     return gather_mean_project_launch(table_dev, ld, n_table_rows, d, ids_dev, n_parents, S, w_dev, ldw, O, bias_dev, act, out_dev, out_dtype,
                                       ld_out, col0, as_stream(stream));

@@ -36,7 +36,7 @@ int linear_ws_umma_launch(const LinearParams& P, cudaStream_t s);
 // 3 x TF32 variant (fp32 operands with w_hi / w_lo given, weights fully resident): same kernel, fp32-level accuracy
 bool linear_ws_umma_x3_eligible(const LinearParams& P);
 int linear_ws_umma_x3_launch(const LinearParams& P, cudaStream_t s);
-// EXPERIMENTAL (GSAGE_FUSED_LAYER=1): gather + mean + neighbour projection in one kernel (gather_mean_project_umma.cu)
+// gather + mean + neighbour projection in one kernel (gather_mean_project_umma.cu)
 bool gather_mean_project_eligible(const void* table, int dtype, int64_t ld, int d, int S, const void* w, int w_dtype, int64_t ldw, int O);
 int gather_mean_project_launch(const void* table, int64_t ld, int64_t table_rows, int d, const int64_t* ids, int64_t n, int S,
                                const void* w, int64_t ldw, int O, const float* bias, int act, void* out, int out_dtype, int64_t ld_out,

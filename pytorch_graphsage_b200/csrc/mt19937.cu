@@ -541,6 +541,7 @@ int gsage_rng_create(gsage_rng** out) {
     r->lanes = 32; r->lane_blocks = 256; r->lane_threshold = 128;
     if (const char* e = getenv("GSAGE_RNG_OVERLAP")) r->overlap = atoi(e) != 0;
     if (const char* e = getenv("GSAGE_RNG_LANES")) r->lanes = std::max(1, std::min(148, atoi(e)));
+    if (const char* e = getenv("GSAGE_RNG_LANE_BLOCKS")) r->lane_blocks = std::max(16, std::min(4096, atoi(e)));
     if ((int64_t)r->lanes * r->lane_blocks * kN > r->cap / 3) r->lanes = 1;
     r->tiles_cap = (int)(r->cap / kTile + 2);
     cudaError_t e1 = cudaMalloc((void**)&r->ring, sizeof(uint32_t) * r->cap);

@@ -224,7 +224,7 @@ def attention_weights(na, xa, n_parents, S):
 
 
 def gather_mean_project(table, ids, n_parents, S, w, bias=None, act=None, out=None, col0=0, out_dtype=torch.bfloat16):
-    """EXPERIMENTAL (GSAGE_FUSED_LAYER=1): act(mean_j table[ids[p*S+j]] . w^T + bias) in one kernel (gsage_gather_mean_project)."""
+    """act(mean_j table[ids[p*S+j]] . w^T + bias) in one kernel (gsage_gather_mean_project)."""
     _bind_device(table)
     if out is None:
         out = torch.empty((n_parents, col0 + w.shape[0]), dtype=out_dtype, device=table.device)

@@ -195,12 +195,15 @@ def test_feature_table_cache_follows_in_place_updates(g):
     ids = torch.from_numpy(fix['ids0'])
     g.set_seeds(int(fix['seed']))
     a = model(ids, feats).cpu().numpy()
-    feats.mul_(2.0)                                                             # in place: same data_ptr, new _version
+    feats[:, ::2].mul_(-1.0)                                                    # in place: same data_ptr, new _version (a plain rescale
+                                                                                # would be undone by the final F.normalize)
     g.set_seeds(int(fix['seed']))
     b = model(ids, feats).cpu().numpy()
     assert np.abs(a - b).max() > 1e-3
     g.set_seeds(int(fix['seed']))
-    c = model(ids, torch.from_numpy(fix['feats']) * 2.0).cpu().numpy()
+    fresh = torch.from_numpy(fix['feats']).clone()
+    fresh[:, ::2] *= -1.0
+    c = model(ids, fresh).cpu().numpy()
     np.testing.assert_allclose(b, c, rtol=1e-5, atol=1e-6)
 
 

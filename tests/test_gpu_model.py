@@ -66,7 +66,7 @@ def test_narrow_operator_api_matches_reference(g, agg, prep, with_feats):
     feats = torch.from_numpy(fix['feats']) if with_feats else None
     g.set_seeds(int(fix['seed']))
     logits = model.forward_reference_order(torch.from_numpy(fix['ids0']), feats, train=True)
-    np.testing.assert_allclose(logits.cpu().numpy(), fix['logits'], rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose(logits.detach().cpu().numpy(), fix['logits'], rtol=1e-4, atol=1e-5)
 
 
 @pytest.mark.parametrize('agg,prep,with_feats', [('mean', 'identity', True), ('max_pool', 'identity', True),
@@ -91,7 +91,7 @@ def test_lstm_engine_in_blocks_of_parents(g, monkeypatch):
     g.set_seeds(int(fix['seed']))
     logits = model(torch.from_numpy(fix['ids0']), torch.from_numpy(fix['feats']), train=True)
     np.testing.assert_allclose(model.peek('layer2').cpu().numpy(), fix['l2'], rtol=1e-4, atol=1e-5)
-    np.testing.assert_allclose(logits.cpu().numpy(), fix['logits'], rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose(logits.detach().cpu().numpy(), fix['logits'], rtol=1e-4, atol=1e-5)
 
 
 def test_host_buffer_entry_point(g):
