@@ -162,6 +162,14 @@ int gsage_gather_mean_project(const void* table_dev, int dtype, int64_t ld, int6
  * `first` != 0: zero initial state -- c is not read and gh is ignored (may be NULL). */
 int gsage_lstm_cell(const float* gx_dev, int64_t ldgx, const float* gh_dev, int64_t ldgh, const float* b_ih_dev, const float* b_hh_dev,
                     float* c_dev, void* h_dev, int h_dtype, int64_t ldh, int64_t n, int H, int first, void* stream);
+/* gsage_lstm_cell backwards: one step of back-propagation through time (nn.LSTM under loss.backward(), models.py:101).  The gate
+ * activations are recomputed from the pre-activations the forward saw (same gx / gh / biases) and c_{t-1}.
+ *   in : dh_dev = d loss / d h_t (n x H),  dc_dev = d loss / d c_t (n x H, in place -> d loss / d c_{t-1})
+ *   out: dgates_dev (n x 4H, row stride ldg) = d loss / d (gx + gh + b), gate order i, f, g, o.
+ * The caller turns dgates into dW_ih / dW_hh (gsage_wgrad), db (gsage_colsum), dx_t and dh_{t-1} (gsage_linear, transposed). */
+int gsage_lstm_cell_backward(const float* gx_dev, int64_t ldgx, const float* gh_dev, int64_t ldgh, const float* b_ih_dev,
+                             const float* b_hh_dev, const float* c_prev_dev, const float* dh_dev, float* dc_dev, float* dgates_dev,
+                             int64_t ldg, int64_t n, int H, int first, void* stream);
 /* F.normalize(dim=1, eps=1e-12) (models.py:90), fp32 out */
 int gsage_l2_normalize(const void* x_dev, int dtype, int64_t ld, int64_t n, int d, float* out_dev, int64_t ld_out,
                        void* stream);

@@ -106,6 +106,7 @@ _SIGNATURES = {
     'gsage_gather_mean_project': (C.c_int, [c_p, C.c_int, c_i64, c_i64, C.c_int, c_p, c_i64, C.c_int, c_p, C.c_int, c_i64, C.c_int, c_p, C.c_int, c_p,
                                             C.c_int, c_i64, c_i64, c_p]),
     'gsage_lstm_cell': (C.c_int, [c_p, c_i64, c_p, c_i64, c_p, c_p, c_p, c_p, C.c_int, c_i64, c_i64, C.c_int, C.c_int, c_p]),
+    'gsage_lstm_cell_backward': (C.c_int, [c_p, c_i64, c_p, c_i64, c_p, c_p, c_p, c_p, c_p, c_p, c_i64, c_i64, C.c_int, C.c_int, c_p]),
     'gsage_l2_normalize': (C.c_int, [c_p, C.c_int, c_i64, c_i64, C.c_int, c_p, c_i64, c_p]),
     'gsage_linear': (C.c_int, [C.POINTER(LinearSeg), C.c_int, c_i64, C.c_int, c_p, C.c_int, c_i64, C.c_int, c_p]),
     'gsage_linear_pooled': (C.c_int, [C.POINTER(LinearSeg), c_i64, C.c_int, C.c_int, C.c_int, c_p, C.c_int, c_i64, c_p]),

@@ -221,24 +221,35 @@ __global__ void __launch_bounds__(kFgThreads, 1) gather_mean_project_kernel(cons
 #pragma unroll
                     for (int jj = 0; jj < (ST > 0 ? ST : 32); jj += U) {
                         if (ST == 0 && jj >= S) break;
+                        // Every load is issued UNCONDITIONALLY from a clamped (always valid) address and masked afterwards.  The
+                        // obvious `ok ? ld : 0` compiles to a predicated load followed by a predicated MOV of zero into the same
+                        // register -- and a predicated-off MOV still waits on the scoreboard of the load in flight, which
+                        // serialised the loads of a round (ncu source view of v2: ~12 equally hot wait points per parent).
                         uint4 v[U][CPL];
+                        uint32_t okbits = 0;
 #pragma unroll
                         for (int u = 0; u < U; ++u) {
                             const int64_t id = __shfl_sync(0xFFFFFFFFu, my_id, min(jj + u, 31));
                             const bool live = (jj + u < S) && ((uint64_t)id < (uint64_t)P.table_rows);
-                            const __nv_bfloat16* row = P.table + id * P.ld;
+                            const __nv_bfloat16* row = P.table + (live ? id : 0) * P.ld;
 #pragma unroll
                             for (int c = 0; c < CPL; ++c) {
                                 const int ch = lane + 32 * c;
-                                v[u][c] = (live && ch < P.units_ld) ? ldg_nc_v4(row + (int64_t)ch * VEC) : make_uint4(0, 0, 0, 0);
+                                if (ST > 0 && jj + u >= ST) { v[u][c] = make_uint4(0, 0, 0, 0); continue; }     // compile-time dead rows: no load at all
+                                v[u][c] = ldg_nc_v4(row + (int64_t)min(ch, P.units_ld - 1) * VEC);
+                                okbits |= (live && ch < P.units_ld) ? (1u << (u * CPL + c)) : 0u;
                             }
                         }
 #pragma unroll
                         for (int u = 0; u < U; ++u)
 #pragma unroll
                             for (int c = 0; c < CPL; ++c) {
+                                if (ST > 0 && jj + u >= ST) continue;
+                                const uint32_t mask = 0u - ((okbits >> (u * CPL + c)) & 1u);
+                                uint4 w = v[u][c];
+                                w.x &= mask; w.y &= mask; w.z &= mask; w.w &= mask;
                                 float f[VEC];
-                                ElemTraits<__nv_bfloat16>::unpack(v[u][c], f);
+                                ElemTraits<__nv_bfloat16>::unpack(w, f);
 #pragma unroll
                                 for (int e = 0; e < VEC; ++e) acc[c][e] = fmaf(1.0f, f[e], acc[c][e]);      // same arithmetic as gather_reduce_kernel
                             }
@@ -290,7 +301,8 @@ static int fg_tile_rows(int nk, int O) {
 }
 
 bool gather_mean_project_eligible(const void* table, int dtype, int64_t ld, int d, int S, const void* w, int w_dtype, int64_t ldw, int O) {
-    if (const char* f = getenv("GSAGE_FUSED_LAYER")) { if (atoi(f) == 0) return false; }
+    // opt-in (GSAGE_FUSED_LAYER=1): measured slower than gather_reduce_kernel + the projection it replaces
+    { const char* f = getenv("GSAGE_FUSED_LAYER"); if (!f || atoi(f) == 0) return false; }
     if (dtype != GSAGE_BF16 || w_dtype != GSAGE_BF16 || S < 1 || S > 32 || d < 1) return false;
     if (O % 16 != 0 || O < 16 || O > 128) return false;                     // one TMEM buffer = 128 columns
     if ((reinterpret_cast<uintptr_t>(table) & 15u) || (reinterpret_cast<uintptr_t>(w) & 15u) || ld % 8 != 0 || ldw % 8 != 0) return false;

@@ -46,9 +46,56 @@ __global__ void __launch_bounds__(256) lstm_cell_kernel(const float* __restrict_
     for (int j = 0; j < 4; ++j) ElemTraits<HT>::store(ho + j, hh[j]);
 }
 
+// the cell, backwards (one time step of back-propagation through time).  Recomputes the gate activations from the same
+// pre-activations the forward saw (gx + gh + biases) and the previous cell state:
+//   do = dh tanh(c);  dc += dh o (1 - tanh(c)^2);  di = dc g;  dg = dc i;  df = dc c_prev;  dc_prev = dc f
+//   d(pre-activation) = (di i(1-i), df f(1-f), dg (1-g^2), do o(1-o))  -> dgates (n x 4H, same gate order)
+// dc holds d loss / d c_t on entry and d loss / d c_{t-1} on exit (in place).
+__global__ void __launch_bounds__(256) lstm_cell_backward_kernel(const float* __restrict__ gx, int64_t ldgx, const float* __restrict__ gh, int64_t ldgh,
+                                                                 const float* __restrict__ b_ih, const float* __restrict__ b_hh,
+                                                                 const float* __restrict__ c_prev, const float* __restrict__ dh,
+                                                                 float* __restrict__ dc, float* __restrict__ dgates, int64_t ldg, int64_t n, int H,
+                                                                 int first) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n * H) return;
+    const int64_t r = idx / H;
+    const int u = (int)(idx - r * H);
+    float a[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        a[k] = gx[r * ldgx + (int64_t)k * H + u] + b_ih[k * H + u] + b_hh[k * H + u];
+        if (!first) a[k] += gh[r * ldgh + (int64_t)k * H + u];
+    }
+    const float i = sigmoidf_(a[0]), f = sigmoidf_(a[1]), g = tanhf(a[2]), o = sigmoidf_(a[3]);
+    const float cp = first ? 0.0f : c_prev[r * (int64_t)H + u];
+    const float c = f * cp + i * g;
+    const float tc = tanhf(c);
+    const float dhv = dh[r * (int64_t)H + u];
+    const float dcv = dc[r * (int64_t)H + u] + dhv * o * (1.0f - tc * tc);
+    float* out = dgates + r * ldg + u;
+    out[0] = dcv * g * i * (1.0f - i);
+    out[H] = dcv * cp * f * (1.0f - f);
+    out[2 * (int64_t)H] = dcv * i * (1.0f - g * g);
+    out[3 * (int64_t)H] = dhv * tc * o * (1.0f - o);
+    dc[r * (int64_t)H + u] = dcv * f;
+}
+
 }  // namespace gsage
 
 using namespace gsage;
+
+extern "C" int gsage_lstm_cell_backward(const float* gx_dev, int64_t ldgx, const float* gh_dev, int64_t ldgh, const float* b_ih_dev,
+                                        const float* b_hh_dev, const float* c_prev_dev, const float* dh_dev, float* dc_dev, float* dgates_dev,
+                                        int64_t ldg, int64_t n, int H, int first, void* stream) {
+    GS_CHECK_ARG(gx_dev && b_ih_dev && b_hh_dev && dh_dev && dc_dev && dgates_dev && n >= 0 && H > 0, "lstm_cell_backward: bad arguments");
+    GS_CHECK_ARG(first || (gh_dev && c_prev_dev), "lstm_cell_backward: the recurrent gates / previous cell state are missing");
+    GS_CHECK_ARG(ldgx >= 4 * (int64_t)H && ldg >= 4 * (int64_t)H && (first || ldgh >= 4 * (int64_t)H), "lstm_cell_backward: bad row strides");
+    if (n == 0) return GSAGE_OK;
+    lstm_cell_backward_kernel<<<(unsigned)ceil_div(n * H, 256), 256, 0, as_stream(stream)>>>(gx_dev, ldgx, gh_dev, ldgh, b_ih_dev, b_hh_dev, c_prev_dev,
+                                                                                              dh_dev, dc_dev, dgates_dev, ldg, n, H, first ? 1 : 0);
+    GS_LAUNCHED();
+    return GSAGE_OK;
+}
 
 extern "C" int gsage_lstm_cell(const float* gx_dev, int64_t ldgx, const float* gh_dev, int64_t ldgh, const float* b_ih_dev, const float* b_hh_dev,
                                float* c_dev, void* h_dev, int h_dtype, int64_t ldh, int64_t n, int H, int first, void* stream) {

@@ -318,13 +318,28 @@ class GSSupervised(nn.Module):
             self._grad_bucket.attach()
         return self._grad_bucket
 
+    def has_fused_backward(self):
+        """Whether model.backward (the engine's hand-written gradient pass) covers this aggregator x prep x dtype; everything else
+        trains through the narrow plug-in API's autograd Functions (train_step picks automatically), the LSTM aggregator included."""
+        bf16 = self.compute_dtype == torch.bfloat16
+        with_feats = self.input_dim is not None
+        if self._agg_name == 'mean':
+            return self._prep_name in ('identity', 'linear') or (self._prep_name == 'node_embedding' and not with_feats and not bf16
+                                                                  and not self.allow_tf32)
+        if self._agg_name in ('max_pool', 'mean_pool'):
+            return bf16 and (self._prep_name == 'identity' or (self._prep_name == 'node_embedding' and not with_feats))
+        if self._agg_name == 'attention':
+            return bf16 and self._prep_name == 'identity'
+        return False
+
     def backward(self, dlogits, grad_scale=1.0, overlap_stream=None):
         """Parameter gradients of the last forward into the flat bucket (p.grad are views of it), summed over the
         ranks of the default process group.  `dlogits` = d loss / d logits (B, n_classes) fp32 on the GPU.
         `grad_scale` weights this rank's contribution (local_batch / global_batch for a mean loss).
         The head (fc + layer 2) is all-reduced on `overlap_stream` while layer 1's weight gradients are computed."""
-        if self._agg_name == 'lstm':
-            raise NotImplementedError('gsage: the LSTM aggregator is forward-only (no backward through the recurrence is built)')
+        if not self.has_fused_backward():
+            raise NotImplementedError('gsage: no fused backward for %s + %s in this dtype; train_step back-propagates through the narrow '
+                                      'plug-in API instead (forward_reference_order + loss.backward())' % (self._agg_name, self._prep_name))
         bucket = self._bucket()
         bucket.attach()              # optimizer.zero_grad(set_to_none=True) (torch's default) drops p.grad: point it at the bucket again
         g = _lib.Grads()
@@ -445,11 +460,27 @@ class GSSupervised(nn.Module):
             opt._materialize()                 # before the forward: building the flat buffers re-creates the engines
         if opt:
             opt.zero_grad()
-        preds = self(ids, feats, train=True, shard=shard, keep_activations=True, next_ids=next_ids, next_shard=next_shard)
-        leaf = preds.detach().requires_grad_(True)
-        loss = loss_fn(leaf, targets.squeeze())
-        dlogits, = torch.autograd.grad(loss, leaf)
-        self.backward(dlogits, grad_scale=grad_scale, overlap_stream=overlap_stream)
+        if not self.has_fused_backward():
+            # registry combinations the engine has no fused backward for (attention + node_embedding, node_embedding WITH
+            # features, pool / attention in fp32 or behind LinearPrep): the reference's own dataflow over the narrow plug-in
+            # API, whose calls are autograd Functions over library kernels (operators.py) -- slower (rows are materialised),
+            # same draws, same result
+            assert shard is None and next_ids is None, 'GSSupervised: seed sharding / sample-ahead need the fused backward'
+            bucket = self._bucket()
+            bucket.attach()
+            bucket.flat.zero_()
+            preds = self.forward_reference_order(ids, feats, train=True)
+            loss = loss_fn(preds, targets.squeeze())
+            loss.backward()                    # p.grad are views of the flat bucket: autograd accumulates into them in place
+            bucket.attach()
+            bucket.all_reduce(grad_scale)
+            preds = preds.detach()
+        else:
+            preds = self(ids, feats, train=True, shard=shard, keep_activations=True, next_ids=next_ids, next_shard=next_shard)
+            leaf = preds.detach().requires_grad_(True)
+            loss = loss_fn(leaf, targets.squeeze())
+            dlogits, = torch.autograd.grad(loss, leaf)
+            self.backward(dlogits, grad_scale=grad_scale, overlap_stream=overlap_stream)
         if opt and getattr(opt, 'fused_clip', False):
             opt.step(clip=clip)                                    # clip + Adam in one native call (parallel.FusedAdam)
         else:

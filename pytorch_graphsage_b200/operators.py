@@ -171,6 +171,55 @@ class _L2Normalize(torch.autograd.Function):
         return ops.l2_normalize_backward(z, dzn)
 
 
+class _LSTMLast(torch.autograd.Function):
+    """The S neighbour rows of every parent through a one-layer LSTM in their sampled order; the last hidden state is the
+    aggregate (nn_modules.py:276-279).  Forward = one projection x . W_ih^T over all steps + per step h . W_hh^T and
+    gsage_lstm_cell; backward = back-propagation through time over the saved states (gsage_lstm_cell_backward per step, then
+    ONE weight-gradient reduction per matrix over all steps).  Everything fp32; states are kept time-major."""
+
+    @staticmethod
+    def forward(ctx, neibs, w_ih, w_hh, b_ih, b_hh, S):
+        neibs = neibs.contiguous()
+        n, H, dev = neibs.shape[0] // S, w_hh.shape[1], neibs.device
+        gx = ops.linear([dict(a=neibs, w=w_ih)], n * S).view(n, S, 4 * H)         # step t of parent p is row p*S + t
+        hs = torch.zeros((S + 1, n, H), dtype=torch.float32, device=dev)          # hs[t + 1] = h_t, hs[0] = the zero initial state
+        cs = torch.zeros((S + 1, n, H), dtype=torch.float32, device=dev)
+        gh = torch.empty((n, 4 * H), dtype=torch.float32, device=dev)
+        c = torch.empty((n, H), dtype=torch.float32, device=dev)
+        b_ih, b_hh = b_ih.contiguous(), b_hh.contiguous()
+        for t in range(S):
+            if t > 0:
+                ops.linear([dict(a=hs[t], w=w_hh)], n, out=gh)
+            ops.lstm_cell(gx[:, t], gh if t > 0 else None, b_ih, b_hh, c, hs[t + 1], first=(t == 0))
+            cs[t + 1].copy_(c)
+        ctx.S = S
+        ctx.save_for_backward(neibs, w_ih, w_hh, b_ih, b_hh, gx, hs, cs)
+        return hs[S].clone()
+
+    @staticmethod
+    def backward(ctx, dh_last):
+        neibs, w_ih, w_hh, b_ih, b_hh, gx, hs, cs = ctx.saved_tensors
+        S = ctx.S
+        n, H, dev = hs.shape[1], hs.shape[2], hs.device
+        dg = torch.empty((S, n, 4 * H), dtype=torch.float32, device=dev)            # time-major: pairs with hs[:S] for dW_hh
+        gh = torch.empty((n, 4 * H), dtype=torch.float32, device=dev)
+        dh = dh_last.contiguous().clone()
+        dc = torch.zeros((n, H), dtype=torch.float32, device=dev)
+        for t in range(S - 1, -1, -1):
+            if t > 0:
+                ops.linear([dict(a=hs[t], w=w_hh)], n, out=gh)                      # the recurrent gates of step t, recomputed
+            ops.lstm_cell_backward(gx[:, t], gh if t > 0 else None, b_ih, b_hh, cs[t] if t > 0 else None, dh, dc, dg[t], first=(t == 0))
+            if t > 0:
+                dh = ops.linear([dict(a=dg[t], w=w_hh, w_trans=True)], n)           # d loss / d h_{t-1}
+        dg_tm = dg.view(S * n, 4 * H)
+        dw_hh = ops.wgrad(dg_tm, hs[:S].reshape(S * n, H))
+        dg_pm = dg.transpose(0, 1).contiguous().view(n * S, 4 * H)                  # parent-major: row p*S + t, like `neibs`
+        dw_ih = ops.wgrad(dg_pm, neibs)
+        db = ops.colsum(dg_pm)
+        dn = ops.linear([dict(a=dg_pm, w=w_ih, w_trans=True)], n * S) if ctx.needs_input_grad[0] else None
+        return dn, dw_ih, dw_hh, db, db.clone(), None
+
+
 def linear_fn(a, weight, bias=None, act=None):
     """act(a . weight^T + bias) through the library, differentiable."""
     return _Linear.apply(act, a, weight, bias, None, None)
@@ -444,11 +493,8 @@ class LSTMAggregator(nn.Module, AggregatorMixin):
         self.activation = activation
         self.combine_fn = combine_fn
 
-    def _forward_rows(self, x, neibs):
-        # forward only (no backward through the recurrence is built): the inputs are detached so that a caller who asks for
-        # gradients gets torch's "does not require grad" error instead of silently missing ones
-        x, neibs = _f32(x).detach().contiguous(), _f32(neibs).detach().contiguous()
-        return self._run(x, None, neibs, None, x.size(0), neibs.size(0) // x.size(0))
+    def _reduce_rows(self, x, neibs, S):
+        return _LSTMLast.apply(neibs, self.lstm.weight_ih_l0, self.lstm.weight_hh_l0, self.lstm.bias_ih_l0, self.lstm.bias_hh_l0, S)
 
     def _run(self, x, x_ids, nb, nb_ids, n, S):
         H, dev = self.lstm.hidden_size, x.device

@@ -246,6 +246,17 @@ def lstm_cell(gx, gh, b_ih, b_hh, c, h, first):
     return h
 
 
+def lstm_cell_backward(gx, gh, b_ih, b_hh, c_prev, dh, dc, dgates, first):
+    """One step of BPTT through the cell (gsage_lstm_cell_backward): dc is updated in place to d loss / d c_{t-1}, dgates
+    (n, 4H; may be a strided view) receives d loss / d pre-activation gates."""
+    _bind_device(gx)
+    n, H = dh.shape
+    check(lib().gsage_lstm_cell_backward(ptr(gx), _rows2d(gx), ptr(gh) if gh is not None else None, _rows2d(gh) if gh is not None else 0,
+                                         ptr(b_ih), ptr(b_hh), ptr(c_prev) if c_prev is not None else None, ptr(dh), ptr(dc), ptr(dgates),
+                                         _rows2d(dgates), n, H, 1 if first else 0, stream()))
+    return dgates
+
+
 def attention_aggregate(table, ids, n_parents, S, w1, w2, xa, b1=None, out_dtype=None):
     """sum_j softmax_j(<a(n_pj), xa[p]>) n_pj in one launch (gsage_attention_aggregate); returns (n_parents, d)."""
     _bind_device(table)

@@ -25,7 +25,7 @@ def g():
 @pytest.mark.parametrize('agg,prep,with_feats', [
     ('mean', 'identity', True), ('max_pool', 'identity', True), ('mean_pool', 'identity', True), ('attention', 'identity', True),
     ('mean', 'linear', True), ('mean', 'node_embedding', True), ('mean', 'node_embedding', False),
-    ('max_pool', 'node_embedding', False), ('attention', 'node_embedding', False)])
+    ('max_pool', 'node_embedding', False), ('attention', 'node_embedding', False), ('lstm', 'identity', True)])
 def test_loss_backward_through_the_plugins(g, agg, prep, with_feats):
     """models.py:97-104 as the reference runs it: forward through sampler / prep / aggregator plug-ins, loss, loss.backward(),
     every parameter gradient against the oracle's -- including the registry combinations the fused engine's backward does not
@@ -52,13 +52,14 @@ def test_loss_backward_through_the_plugins(g, agg, prep, with_feats):
         np.testing.assert_allclose(p.grad.cpu().numpy(), ps[name].grad.numpy(), err_msg=name, **TOL)
 
 
-@pytest.mark.parametrize('agg', ['mean', 'max_pool', 'mean_pool', 'attention'])
+@pytest.mark.parametrize('agg', ['mean', 'max_pool', 'mean_pool', 'attention', 'lstm'])
 def test_aggregator_call_is_differentiable_wrt_its_inputs(g, agg):
     """agg(x, neibs): gradients w.r.t. x and neibs (what lets layer 2 back-propagate into layer 1), vs the oracle's aggregator."""
     gen = torch.Generator().manual_seed(11)
     n, S, d, O = 37, 7, 20, 16
     torch.manual_seed(3)
-    mod = g.aggregator_lookup[agg](input_dim=d, output_dim=O, activation=F.relu).cuda()
+    kw = dict(hidden_dim=24) if agg == 'lstm' else {}
+    mod = g.aggregator_lookup[agg](input_dim=d, output_dim=O, activation=F.relu, **kw).cuda()
     x = torch.randn((n, d), generator=gen)
     nb = torch.randn((n * S, d), generator=gen)
     xg, nbg = x.cuda().requires_grad_(True), nb.cuda().requires_grad_(True)

@@ -270,20 +270,53 @@ def test_fused_adam_on_the_embedding_recipe_keeps_every_parameter_aligned(g):
         assert p.grad.data_ptr() % 256 == 0
 
 
-def test_lstm_aggregator_is_forward_only(g):
-    """The LSTM aggregator completes the registry for inference; its backward is not built and says so."""
-    fix = util.load('model_lstm_identity')
-    from functools import partial
-    model = g.GSSupervised(
-        input_dim=fix['feats'].shape[1], n_nodes=int(fix['n_nodes']), n_classes=fix['logits'].shape[1],
-        layer_specs=[dict(n_train_samples=25, n_val_samples=25, output_dim=int(fix['out_dims'][0]), activation=F.relu),
-                     dict(n_train_samples=10, n_val_samples=10, output_dim=int(fix['out_dims'][1]), activation=lambda x: x)],
-        aggregator_class=partial(g.aggregator_lookup['lstm'], hidden_dim=64), prep_class=g.prep_lookup['identity'],
-        sampler_class=g.sampler_lookup['sparse_uniform_neighbor_sampler'], adj=g.GraphCSR.from_triplets(fix['trip']),
-        train_adj=g.GraphCSR.from_triplets(fix['trip'])).cuda()
-    targets = torch.zeros(fix['ids0'].shape[0], dtype=torch.int64).cuda()
-    with pytest.raises(NotImplementedError):
-        model.train_step(torch.from_numpy(fix['ids0']), torch.from_numpy(fix['feats']), targets, F.cross_entropy, optimizer=False, clip=None)
+@pytest.mark.parametrize('case,prep,with_feats', [('model_lstm_identity', 'identity', True), ('model_lstm_node_embedding_nofeats', 'node_embedding', False)])
+def test_lstm_aggregator_trains_through_the_plugin_api(g, case, prep, with_feats):
+    """The LSTM aggregator (nn_modules.py:259-286) has no fused engine backward; train_step back-propagates through the narrow
+    plug-in API instead: back-propagation through time in operators._LSTMLast over gsage_lstm_cell_backward.  Every parameter
+    gradient (W_ih, W_hh, both biases, fc_x, fc_neib, the prep, fc) against torch autograd through the oracle's LSTM."""
+    fix = util.load(case)
+    model = build_model(g, fix, 'lstm', prep, with_feats)
+    assert not model.has_fused_backward()
+    feats = torch.from_numpy(fix['feats']) if with_feats else None
+    targets = torch.from_numpy(np.random.RandomState(0).randint(0, fix['logits'].shape[1], fix['ids0'].shape[0]))
+    g.set_seeds(int(fix['seed']))
+    preds = model.train_step(torch.from_numpy(fix['ids0']), feats, targets.cuda(), F.cross_entropy, optimizer=False, clip=None)
+    np.testing.assert_allclose(preds.cpu().numpy(), fix['logits'], rtol=1e-4, atol=1e-5)
+    hop_ids = [torch.from_numpy(fix[k]) for k in ('ids0', 'ids1', 'ids2')]
+    ps = {k: v.clone().requires_grad_(True) for k, v in util.params_of(fix).items()}
+    kw = dict(n_nodes=int(fix['n_nodes'])) if prep == 'node_embedding' else {}
+    want = F.cross_entropy(layers.forward_stack(hop_ids, feats, ps, aggregator='lstm', prep=prep, **kw), targets)
+    want.backward()
+    assert abs(model.last_loss.item() - want.item()) < 1e-4
+    for name, p in model.named_parameters():
+        np.testing.assert_allclose(p.grad.cpu().numpy(), ps[name].grad.numpy(), err_msg=name, rtol=2e-3, atol=2e-5)
+
+
+@pytest.mark.parametrize('agg,prep,with_feats,dtype', [('attention', 'node_embedding', False, torch.float32), ('max_pool', 'identity', True, torch.float32),
+                                                       ('mean', 'node_embedding', True, torch.float32)])
+def test_train_step_falls_back_to_the_plugin_api_where_no_fused_backward_exists(g, agg, prep, with_feats, dtype):
+    """Registry combinations without an engine backward train through forward_reference_order + loss.backward() (library kernels
+    behind autograd Functions), and one optimiser step moves every parameter like the oracle's Adam."""
+    fix = util.load(util.case_name(agg, prep, with_feats))
+    model = build_model(g, fix, agg, prep, with_feats, compute_dtype=dtype)
+    assert not model.has_fused_backward()
+    feats = torch.from_numpy(fix['feats']) if with_feats else None
+    targets = torch.from_numpy(np.random.RandomState(1).randint(0, fix['logits'].shape[1], fix['ids0'].shape[0]))
+    g.set_seeds(int(fix['seed']))
+    model.train_step(torch.from_numpy(fix['ids0']), feats, targets.cuda(), F.cross_entropy)          # the model's own optimiser
+    ref = {k: v.clone().requires_grad_(True) for k, v in util.params_of(fix).items()}
+    ropt = torch.optim.Adam(list(ref.values()), lr=0.01)
+    hop_ids = [torch.from_numpy(fix[k]) for k in ('ids0', 'ids1', 'ids2')]
+    kw = dict(n_nodes=int(fix['n_nodes'])) if prep == 'node_embedding' else {}
+    F.cross_entropy(layers.forward_stack(hop_ids, feats, ref, aggregator=agg, prep=prep, **kw), targets).backward()
+    torch.nn.utils.clip_grad_norm_(list(ref.values()), 5.0)
+    ropt.step()
+    for name, p in model.named_parameters():
+        got, want = p.detach().cpu().numpy(), ref[name].detach().numpy()
+        off = np.abs(got - want) > 1e-4 + 1e-3 * np.abs(want)
+        assert off.mean() <= 2e-3, '%s: %.3f %% of the elements differ' % (name, 100 * off.mean())     # (Adam on |g| ~ eps is rounding noise)
+        np.testing.assert_allclose(got, want, rtol=0, atol=0.011, err_msg=name)
 
 
 def test_train_step_with_the_dense_sampler(g):
