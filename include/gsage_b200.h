@@ -418,6 +418,18 @@ int gsage_embedding_backward(const float* drows_dev, int64_t ld, int d, const in
                              int64_t ld_table, int64_t table_rows, void* stream);
 int gsage_l2_normalize_backward(const float* z_dev, const float* dzn_dev, int64_t n, int d, float* dz_dev, void* stream);
 
+/* ---- the gradient all-reduce over NVLink peer memory (the path's one collective) --------------------------------
+ * One-shot sum all-reduce for small buffers (the 0.6-0.9 MB gradient bucket): every rank's bucket lives in symmetric memory
+ * (one allocation mapped into every process of the box; `peer_ptrs_host[p]` = rank p's bucket as seen from THIS process), and
+ * one kernel per rank reads all `world` buckets directly over NVLink, writes  out[i] = sum_p scale_p * bucket_p[i]  into the
+ * rank's own private buffer and accumulates sum(out^2) (the norm of clip_grad_norm, models.py:102) into `sumsq_dev` (may be NULL).
+ * Every rank calls it once per step with the same `epoch` (1, 2, ...); flags inside the symmetric buffers order the kernels
+ * of the ranks against each other (no host synchronisation, no NCCL).  The symmetric buffer of a rank must hold
+ * gsage_peer_allreduce_words(n) fp32 words, zero-initialised; n a multiple of 4. */
+int64_t gsage_peer_allreduce_words(int64_t n);
+int gsage_peer_allreduce(const uint64_t* peer_ptrs_host, int world, int rank, int64_t n, uint32_t epoch, float scale, float* out_dev,
+                         float* sumsq_dev, void* stream);
+
 /* ---- per-batch training metric on the device (train.py:150 `problem.metric_fn(to_numpy(targets), to_numpy(preds))`) -------
  * gsage_metric_f1: sklearn micro / macro F1 as problem.py:44-58 computes them.  multilabel == 0 (`classification`):
  *   `targets_dev` int64 (n), prediction = argmax of the n_classes logits (first maximum), macro averages over the labels

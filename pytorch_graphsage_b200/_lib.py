@@ -141,6 +141,8 @@ _SIGNATURES = {
     'gsage_colsum': (C.c_int, [c_p, c_i64, C.c_int, c_p, c_p]),
     'gsage_embedding_backward': (C.c_int, [c_p, c_i64, C.c_int, c_p, c_i64, c_p, c_i64, c_i64, c_p]),
     'gsage_l2_normalize_backward': (C.c_int, [c_p, c_p, c_i64, C.c_int, c_p, c_p]),
+    'gsage_peer_allreduce_words': (c_i64, [c_i64]),
+    'gsage_peer_allreduce': (C.c_int, [c_p, C.c_int, C.c_int, c_i64, C.c_uint32, C.c_float, c_p, c_p, c_p]),
     'gsage_metric_f1': (C.c_int, [c_p, c_i64, c_p, c_i64, c_i64, C.c_int, C.c_int, c_p, c_p, c_p]),
     'gsage_metric_mae': (C.c_int, [c_p, c_p, c_i64, c_p, c_p]),
     'gsage_engine_keep_activations': (C.c_int, [c_p, C.c_int]),

@@ -150,7 +150,7 @@ struct gsage_engine {
     // LSTM aggregator: input half of the gates for all S steps of a block of parents (lgx_rows rows x 4H), recurrent half of the
     // current step, cell / hidden state
     float* LGX = nullptr; float* LGH = nullptr; float* LC = nullptr; void* LH = nullptr; int64_t lgx_rows = 0;
-    float* wsplit = nullptr; int64_t wsplit_floats = 0;      // fp32-exact mode: (hi, lo) tf32 halves of fc_x / fc_neib for the 3 x TF32 projection
+    float* wsplit = nullptr; int64_t wsplit_floats = 0;      // fp32-exact mode: (hi, lo) tf32 halves of fc_x / fc_neib / mlp.0 / att.0 for the 3 x TF32 projections
     WRef w_nT[2], w_mlpT[2];            // pool backward (bf16): fc_neib^T (H x O) and mlp.0.weight^T (d_in x H), K-major
     WRef w_xT0;                         // pool + folded node_embedding backward (bf16): (Wx.Wp)^T (emb_dim x O1), K-major
     WRef w_x2T, w_n2T;                  // mean backward (bf16): layer-2 fc_x^T / fc_neib^T (2*O1 x O2), K-major, for the head's data gradients
@@ -331,12 +331,24 @@ static int apply_aggregator(gsage_engine* e, int layer, const RowSrc& x, const R
                 return st;
             }
         }
+        // fp32-exact mode (or operands the fused kernel does not take): the MLP as a projection (3 x TF32 in 128-column blocks when
+        // exact), the hidden rows through HBM, the pool as a segment reduce.  Stopwatch: MLP + pool of the dominant application.
+        const bool dominant = layer == 0 && n > e->B;
+        const int p_red = dominant ? e->prof.begin(GSAGE_PROF_REDUCE, s) : -1;
         GS_TRY(linear_call(nb, e->w_mlp[layer], H, e->b_mlp[layer], n * S, GSAGE_ACT_RELU, e->HN, T, H, 0, exact, s));
         GS_TRY(gather_reduce_launch(e->HN, T, H, n * S, H, nullptr, n, S,
                                     e->cfg.aggregator == GSAGE_AGG_MAX_POOL ? GSAGE_RED_MAX : GSAGE_RED_MEAN, nullptr,
                                     e->Pp, T, H, s));
+        e->prof.end(p_red, s);
+        e->prof.work(p_red, GSAGE_PROF_REDUCE, (double)n * ((double)S * d * dtype_size(nb.dtype) + (nb.ids ? 8.0 * S : 0.0) + (double)H * dtype_size(T)),
+                     2.0 * (double)n * S * d * H);
         RowSrc p{e->Pp, T, H, n, nullptr, H};
-        return combine_call(x, e->w_x[layer], p, e->w_n[layer], O, n, act, out, out_dtype, ld_out, exact, s, e->b_x[layer], nullptr);
+        const int p_prj = dominant ? e->prof.begin(GSAGE_PROF_PROJECT, s) : -1;
+        const int st = combine_call(x, e->w_x[layer], p, e->w_n[layer], O, n, act, out, out_dtype, ld_out, exact, s, e->b_x[layer], nullptr);
+        e->prof.end(p_prj, s);
+        e->prof.work(p_prj, GSAGE_PROF_PROJECT, (double)n * ((double)d * dtype_size(x.dtype) + (x.ids ? 8.0 : 0.0) + (double)H * dtype_size(T) +
+                                                             2.0 * O * dtype_size(out_dtype)), 2.0 * (double)n * (d + H) * O);
+        return st;
     }
     case GSAGE_AGG_ATTENTION: {
         const int H = e->hid;
@@ -364,13 +376,25 @@ static int apply_aggregator(gsage_engine* e, int layer, const RowSrc& x, const R
                                                                  2.0 * O * dtype_size(out_dtype)), 4.0 * (double)n * d * O);
             return st;
         }
+        // fp32-exact mode: the unfused chain -- a(n) for every neighbour row (W1 as 3 x TF32 when exact), scores + softmax, then the
+        // weighted gather+sum (the rows are read twice).  Stopwatch: the whole reduction of the dominant application.
+        const bool dominant = layer == 0 && n > e->B;
+        const int p_red = dominant ? e->prof.begin(GSAGE_PROF_REDUCE, s) : -1;
         GS_TRY(linear_call(nb, e->w_att1[layer], H, e->b_att[layer], n * S, GSAGE_ACT_TANH, e->T1, GSAGE_F32, H, 0, exact, s));
         RowSrc t1{e->T1, GSAGE_F32, H, n * S, nullptr, H};
         GS_TRY(linear_call(t1, f32w(L.att_w2, H), H, nullptr, n * S, GSAGE_ACT_NONE, e->NA, GSAGE_F32, H, 0, 1, s));
         GS_TRY(gsage_attention_weights(e->NA, e->XA, GSAGE_F32, H, H, n, S, e->AW, s));
         GS_TRY(gather_reduce_launch(nb.base, nb.dtype, nb.ld, nb.table_rows, d, nb.ids, n, S, GSAGE_RED_SUM, e->AW, Mb, T, ldm, s));
+        e->prof.end(p_red, s);
+        e->prof.work(p_red, GSAGE_PROF_REDUCE, (double)n * ((double)S * d * dtype_size(nb.dtype) + (nb.ids ? 8.0 * S : 0.0) + 4.0 * H + (double)d * dtype_size(T)),
+                     (double)n * S * (2.0 * d * H + 2.0 * H * H + 2.0 * H + 2.0 * d));
         RowSrc m{Mb, T, ldm, n, nullptr, d};
-        return combine_call(x, e->w_x[layer], m, e->w_n[layer], O, n, act, out, out_dtype, ld_out, exact, s, e->b_x[layer], e->b_n[layer]);
+        const int p_prj = dominant ? e->prof.begin(GSAGE_PROF_PROJECT, s) : -1;
+        const int st = combine_call(x, e->w_x[layer], m, e->w_n[layer], O, n, act, out, out_dtype, ld_out, exact, s, e->b_x[layer], e->b_n[layer]);
+        e->prof.end(p_prj, s);
+        e->prof.work(p_prj, GSAGE_PROF_PROJECT, (double)n * ((double)d * dtype_size(x.dtype) + (x.ids ? 8.0 : 0.0) + (double)d * dtype_size(T) +
+                                                             2.0 * O * dtype_size(out_dtype)), 4.0 * (double)n * d * O);
+        return st;
     }
     case GSAGE_AGG_LSTM: {
         // nn_modules.py:276-279: the S neighbour rows of a parent, in sampled order, through a one-layer LSTM; the last hidden
@@ -657,6 +681,7 @@ int gsage_engine_set_weights(gsage_engine* e, const gsage_weights* w, void* stre
         for (int l = 0; l < 2; ++l) {
             const int64_t d_in = l == 0 ? e->ld_prep : 2 * e->cfg.out_dim[0];
             need += 2 * 2 * pad_to((int64_t)e->cfg.out_dim[l] * (d_in > e->hid ? d_in : e->hid), 64);      // fc_x, fc_neib: hi and lo
+            if (pool || att) need += 2 * pad_to((int64_t)e->hid * d_in, 64);                                // mlp.0 / att.0: hi and lo
         }
         GS_CUDA(cudaMalloc((void**)&e->wsplit, need * sizeof(float)));
         e->wsplit_floats = need;
@@ -675,7 +700,8 @@ int gsage_engine_set_weights(gsage_engine* e, const gsage_weights* w, void* stre
             if (e->T != GSAGE_BF16) {
                 *it.dst = f32w(it.src, it.cols);
                 const int64_t cnt = pad_to((int64_t)it.rows * it.cols, 64);
-                if (e->wsplit && (it.dst == &e->w_x[l] || it.dst == &e->w_n[l]) && split_off + 2 * cnt <= e->wsplit_floats) {
+                if (e->wsplit && (it.dst == &e->w_x[l] || it.dst == &e->w_n[l] || it.dst == &e->w_mlp[l] || it.dst == &e->w_att1[l]) &&
+                    split_off + 2 * cnt <= e->wsplit_floats) {
                     float* hi = e->wsplit + split_off; float* lo = hi + cnt;
                     GS_TRY(split_tf32_launch(it.src, (int64_t)it.rows * it.cols, hi, lo, s));
                     it.dst->hi = hi; it.dst->lo = lo;

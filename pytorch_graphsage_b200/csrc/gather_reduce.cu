@@ -20,8 +20,12 @@ namespace gsage {
 
 enum { kRedSum = 0, kRedMax = 1 };
 
+// four CTAs per SM (<= 64 registers): the kernel lives on bytes in flight -- at 70 registers only three CTAs fit
+#ifndef GS_GR_MIN_CTAS
+#define GS_GR_MIN_CTAS 4
+#endif
 template <typename T, int LPR, int CPL, int RED>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, (CPL <= 3 ? GS_GR_MIN_CTAS : 2))
 gather_reduce_kernel(const T* __restrict__ table, int64_t ld, int64_t n_table_rows, int d,
                      const int64_t* __restrict__ ids, int64_t n_parents, int S, const float* __restrict__ weights,
                      float scale, void* __restrict__ out, int out_bf16, int64_t ld_out, int vec_store, int l2_hint) {

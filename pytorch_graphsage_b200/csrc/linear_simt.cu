@@ -199,6 +199,34 @@ int linear_dispatch(const LinearParams& P, int exact, cudaStream_t s) {
         tc = linear_umma_eligible(one);
     }
     if (exact && linear_ws_umma_x3_eligible(P)) return linear_ws_umma_x3_launch(P, s);     // fp32 accuracy on the tensor cores (3 x TF32)
+    if (exact) {
+        // 3 x TF32 needs W resident twice (hi + lo): a projection whose weights do not fit (the pool aggregators' 512-unit MLP, the
+        // d = 602 layer) runs in blocks of 128 output columns, each with its own slice of the weights -- the rows are re-read per
+        // block, which costs far less than the FFMA kernel this replaces (fp32-exact pool / attention / wide mean models)
+        bool all_split = true;
+        for (int i = 0; i < P.n_segs; ++i) all_split = all_split && P.seg[i].w_hi && P.seg[i].w_lo && !P.seg[i].w_trans && P.seg[i].S <= 1;
+        if (all_split && !getenv("GSAGE_FP32_FFMA")) {
+            bool any = false;
+            for (int i = 0; i < P.n_segs; ++i) {
+                const LinearSeg& g = P.seg[i];
+                for (int c = 0; c < g.O; c += 128) {
+                    LinearParams one = P;
+                    one.n_segs = 1;
+                    one.seg[0] = g;
+                    one.seg[0].O = g.O - c < 128 ? g.O - c : 128;
+                    one.seg[0].w = (const char*)g.w + (size_t)c * g.ldw * sizeof(float);
+                    one.seg[0].w_hi = (const char*)g.w_hi + (size_t)c * g.ldw * sizeof(float);
+                    one.seg[0].w_lo = (const char*)g.w_lo + (size_t)c * g.ldw * sizeof(float);
+                    one.seg[0].bias = g.bias ? g.bias + c : nullptr;
+                    one.seg[0].col0 = g.col0 + c;
+                    if (linear_ws_umma_x3_eligible(one)) { GS_TRY(linear_ws_umma_x3_launch(one, s)); any = true; }
+                    else GS_TRY(linear_simt_launch(one, s));
+                }
+            }
+            (void)any;
+            return GSAGE_OK;
+        }
+    }
     if (!tc) { GS_CHECK_ARG(P.pool_S <= 1, "linear: operands do not qualify for the tensor-core kernel (pooled epilogue)"); return linear_simt_launch(P, s); }
     if (linear_ws_umma_eligible(P)) return linear_ws_umma_launch(P, s);      // weights stationary in smem: half the L2 -> SM bytes
     if (linear_umma_eligible(P)) return linear_umma_launch(P, s);

@@ -93,29 +93,46 @@ __device__ __forceinline__ void mt_next_block(const uint32_t* o, uint32_t* n, in
 }
 
 // grid (lanes-1, kJumpSlices): partial[(lane-1)*kJumpSlices + slice][624]
+// x = the stream continuing the head window H: x[0..624) = H (the block before `start`), x[624 + j] = word start + j.  The same x
+// serves every lane, and its 33 blocks are simply the first 33 blocks of the refill -- so they are generated ONCE, by one CTA,
+// straight into the ring (mt_generate_kernel, queued right before this kernel), and every (lane, slice) CTA only loads the
+// 3120 words its slice touches.  (Round 1 regenerated up to 33 blocks sequentially in each of the 248 CTAs: the jump kernel cost
+// as much GPU time as generating the 5 M words themselves.)  The XOR itself takes four set bits per iteration: the loop is
+// bound by the latency of the shared-memory loads, four windows in flight cost the same as one; missing bits of the last group
+// point at a zero pad.
+static constexpr int kJumpPrefixBlocks = kSeqWords / kN;                 // 33
+static constexpr int kSliceSpan = kSliceWords * 32 + kN;                 // 3120 words of x per slice
+static constexpr int kZeroPad = 1024;
 __global__ void __launch_bounds__(256) mt_jump_kernel(const uint32_t* __restrict__ ring, uint64_t cap_mask, int64_t start,
                                                       const uint32_t* __restrict__ polys, uint32_t* __restrict__ partial) {
-    extern __shared__ uint32_t x[];                       // kSeqWords
+    __shared__ uint32_t xs[kSliceSpan + kZeroPad];
     __shared__ uint32_t gw[kSliceWords];
     const int tid = threadIdx.x, lane = blockIdx.x + 1, slice = blockIdx.y;
-    for (int i = tid; i < kN; i += 256) x[i] = ring[(uint64_t)(start - kN + i) & cap_mask];
+    const int64_t first = start - kN + (int64_t)slice * kSliceWords * 32;
+    for (int i = tid; i < kSliceSpan; i += 256) xs[i] = ring[(uint64_t)(first + i) & cap_mask];
+    for (int i = tid; i < kZeroPad; i += 256) xs[kSliceSpan + i] = 0u;
     if (tid < kSliceWords) gw[tid] = polys[(size_t)(lane - 1) * kN + slice * kSliceWords + tid];
     __syncthreads();
-    // this slice touches x[slice*2496 .. slice*2496 + 2496 + 624): generate just far enough
-    const int need = (slice + 1) * kSliceWords * 32 + kN;
-    for (int b = 0; (b + 1) * kN < need; ++b) mt_next_block(x + b * kN, x + (b + 1) * kN, tid);
     uint32_t a0 = 0, a1 = 0, a2 = 0;
-    const uint32_t* xs = x + slice * kSliceWords * 32;
     const bool third = tid + 512 < kN;
+    const int t2 = third ? tid + 512 : tid;                // (threads past the window's end re-read a word they already hold: a2 is dropped)
     for (int w = 0; w < kSliceWords; ++w) {
         uint32_t bits = gw[w];                             // uniform across the CTA: no divergence
+        const int base = w * 32;
         while (bits) {
-            const int b = __ffs(bits) - 1;
-            bits &= bits - 1;
-            const uint32_t* p = xs + w * 32 + b + tid;
-            a0 ^= p[0];
-            a1 ^= p[256];
-            if (third) a2 ^= p[512];
+            int off[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                if (bits) { off[k] = base + __ffs(bits) - 1; bits &= bits - 1; }
+                else off[k] = kSliceSpan;                  // the zero pad
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const uint32_t* p = xs + off[k];
+                a0 ^= p[tid];
+                a1 ^= p[tid + 256];
+                a2 ^= p[t2];
+            }
         }
     }
     uint32_t* out = partial + ((size_t)(lane - 1) * kJumpSlices + slice) * kN;
@@ -124,16 +141,18 @@ __global__ void __launch_bounds__(256) mt_jump_kernel(const uint32_t* __restrict
     if (third) out[tid + 512] = a2;
 }
 
-// grid (lanes): lane l writes stream words [start + l*K*624, start + (l+1)*K*624)
+// grid (lanes): lane l writes stream words [start + l*K*624, start + (l+1)*K*624).  Lane 0 continues after the
+// `skip0` blocks mt_generate_kernel already wrote (the jump kernel's x).
 __global__ void __launch_bounds__(256) mt_generate_lanes_kernel(uint32_t* __restrict__ ring, uint64_t cap_mask,
                                                                 int64_t start, int blocks_per_lane,
-                                                                const uint32_t* __restrict__ partial) {
+                                                                const uint32_t* __restrict__ partial, int skip0) {
     __shared__ uint32_t st[2][kN];
     const int tid = threadIdx.x, lane = blockIdx.x;
+    const int b0 = lane == 0 ? skip0 : 0;
     for (int i = tid; i < kN; i += 256) {
         uint32_t v;
         if (lane == 0) {
-            v = ring[(uint64_t)(start - kN + i) & cap_mask];
+            v = ring[(uint64_t)(start + (int64_t)(b0 - 1) * kN + i) & cap_mask];
         } else {
             v = 0;
             const uint32_t* p = partial + (size_t)(lane - 1) * kJumpSlices * kN + i;
@@ -145,7 +164,7 @@ __global__ void __launch_bounds__(256) mt_generate_lanes_kernel(uint32_t* __rest
     __syncthreads();
     int cur = 0;
     const int64_t base0 = start + (int64_t)lane * blocks_per_lane * kN;
-    for (int b = 0; b < blocks_per_lane; ++b) {
+    for (int b = b0; b < blocks_per_lane; ++b) {
         mt_next_block(st[cur], st[cur ^ 1], tid);
         const int64_t base = base0 + (int64_t)b * kN;
         for (int i = tid; i < kN; i += 256) ring[(uint64_t)(base + i) & cap_mask] = st[cur ^ 1][i];
@@ -417,11 +436,14 @@ static int rng_generate(gsage_rng* r, int64_t upto, cudaStream_t s, bool may_syn
         }
         if (use_lanes && blocks == lane_refill) {
             GS_TRY(rng_init_lanes(r));
-            mt_jump_kernel<<<dim3(r->lanes - 1, kJumpSlices), 256, sizeof(uint32_t) * kSeqWords, r->side_now>>>(
+            // x for the jumps = the first 33 blocks of the refill, generated once (one CTA, ~12 us), then read by every jump CTA
+            mt_generate_kernel<<<1, 256, 0, r->side_now>>>(r->ring, (uint64_t)(r->cap - 1), r->gen_end, kJumpPrefixBlocks);
+            GS_LAUNCHED();
+            mt_jump_kernel<<<dim3(r->lanes - 1, kJumpSlices), 256, 0, r->side_now>>>(
                 r->ring, (uint64_t)(r->cap - 1), r->gen_end, r->polys, r->partial);
             GS_LAUNCHED();
             mt_generate_lanes_kernel<<<r->lanes, 256, 0, r->side_now>>>(r->ring, (uint64_t)(r->cap - 1), r->gen_end, r->lane_blocks,
-                                                                    r->partial);
+                                                                    r->partial, kJumpPrefixBlocks);
             GS_LAUNCHED();
         } else {
             if (blocks < 0) blocks = std::min<int64_t>(need, (r->cap - (r->gen_end - (r->cursor_lb - kN))) / kN);
@@ -541,7 +563,7 @@ int gsage_rng_create(gsage_rng** out) {
     r->lanes = 32; r->lane_blocks = 256; r->lane_threshold = 128;
     if (const char* e = getenv("GSAGE_RNG_OVERLAP")) r->overlap = atoi(e) != 0;
     if (const char* e = getenv("GSAGE_RNG_LANES")) r->lanes = std::max(1, std::min(148, atoi(e)));
-    if (const char* e = getenv("GSAGE_RNG_LANE_BLOCKS")) r->lane_blocks = std::max(16, std::min(4096, atoi(e)));
+    if (const char* e = getenv("GSAGE_RNG_LANE_BLOCKS")) r->lane_blocks = std::max(64, std::min(4096, atoi(e)));      // (>= the 33 prefix blocks)
     if ((int64_t)r->lanes * r->lane_blocks * kN > r->cap / 3) r->lanes = 1;
     r->tiles_cap = (int)(r->cap / kTile + 2);
     cudaError_t e1 = cudaMalloc((void**)&r->ring, sizeof(uint32_t) * r->cap);

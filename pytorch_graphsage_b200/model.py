@@ -395,6 +395,8 @@ class GSSupervised(nn.Module):
         dlogits = dlogits.contiguous().float()
         check(lib().gsage_engine_backward_head(self._last['h'], ops.ptr(dlogits), C.byref(g), ops.stream()))
         main = torch.cuda.current_stream()
+        if bucket.one_shot:
+            overlap_stream = None            # one launch for the whole bucket after the last gradient kernel: nothing to split
         if overlap_stream is not None:
             overlap_stream.wait_stream(main)
             with torch.cuda.stream(overlap_stream):
@@ -473,6 +475,8 @@ class GSSupervised(nn.Module):
             loss = loss_fn(preds, targets.squeeze())
             loss.backward()                    # p.grad are views of the flat bucket: autograd accumulates into them in place
             bucket.attach()
+            if bucket.sym is not None:         # peers read this rank's LOCAL gradient from its symmetric buffer
+                bucket.sym[:bucket.flat.numel()].copy_(bucket.flat)
             bucket.all_reduce(grad_scale)
             preds = preds.detach()
         else:

@@ -5,6 +5,9 @@ parameter gradients, carried in one flat bucket so it is a single NCCL call (two
 the layer-1 weight gradients).  Works on any torch.distributed backend (NCCL on the GPUs, gloo in the CPU tests).
 """
 
+import ctypes as C
+import os
+
 import torch
 import torch.distributed as dist
 
@@ -26,7 +29,16 @@ class FlatGradBucket(object):
     """All parameter gradients of a model as views into ONE contiguous fp32 buffer.
 
     `head` parameters (the small late layers whose gradients exist first) sit at the front so that
-    `all_reduce_head()` can start while the big layer-1 weight gradients are still being computed."""
+    `all_reduce_head()` can start while the big layer-1 weight gradients are still being computed.
+
+    Under NCCL with more than one rank the bucket is TWO buffers: `sym`, the rank's slice of a symmetric-memory allocation
+    (mapped into every process of the box) that the backward kernels write and the PEERS read, and `flat`, the private buffer
+    the reduced gradient lands in (`p.grad` are views of it; the optimiser reads it).  `all_reduce` is then one launch of
+    gsage_peer_allreduce per rank: a one-shot all-reduce over NVLink peer memory fused with the gradient norm (peer_allreduce.cu),
+    no NCCL call.  Buckets too large for a one-shot (a learned embedding table's dense gradient), other backends (gloo in the
+    CPU tests) and `GSAGE_SYMM_ALLREDUCE=0` use torch.distributed's all_reduce on `flat` itself."""
+
+    ONE_SHOT_MAX_BYTES = 8 << 20
 
     def __init__(self, params, head=(), device=None):
         params = list(params)
@@ -36,10 +48,18 @@ class FlatGradBucket(object):
         # every slice starts on a 256-byte boundary (the kernels want 16-byte aligned rows, TMA wants more); the padding
         # stays zero: it adds nothing to the gradient norm and an Adam update of (param 0, grad 0) is 0
         pad = lambda n: (n + 63) // 64 * 64
-        self.flat = torch.zeros(sum(pad(p.numel()) for p in order), dtype=torch.float32, device=device)
-        self.views, self.offsets, off = {}, {}, 0
+        total = sum(pad(p.numel()) for p in order)
+        self.flat = torch.zeros(total, dtype=torch.float32, device=device)
+        self.sym, self.peer_ptrs, self.epoch, self.collective = None, None, 0, 'none (1 rank)'
+        self.sumsq = None
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            self.collective = 'torch.distributed all_reduce (%s)' % dist.get_backend()
+            self._try_symmetric(total, device)
+        src = self.sym if self.sym is not None else self.flat
+        self.views, self.pre, self.offsets, off = {}, {}, {}, 0
         for p in order:
-            self.views[id(p)] = self.flat[off:off + p.numel()].view_as(p)
+            self.views[id(p)] = self.flat[off:off + p.numel()].view_as(p)      # reduced gradient: what p.grad points at
+            self.pre[id(p)] = src[off:off + p.numel()].view_as(p)             # where the backward kernels write
             self.offsets[id(p)] = off
             off += pad(p.numel())
             if id(p) in head_ids:
@@ -48,35 +68,68 @@ class FlatGradBucket(object):
             self.head_numel = 0
         self.params = order
 
+    def _try_symmetric(self, total, device):
+        if os.environ.get('GSAGE_SYMM_ALLREDUCE', '1') == '0' or torch.device(device).type != 'cuda' or dist.get_backend() != 'nccl':
+            return
+        if total * 4 > self.ONE_SHOT_MAX_BYTES or dist.get_world_size() > 16:
+            self.collective += ' -- bucket of %.1f MB is too large for the one-shot peer all-reduce' % (total * 4 / 1e6)
+            return
+        try:
+            import torch.distributed._symmetric_memory as symm_mem
+            words = int(lib().gsage_peer_allreduce_words(total))
+            sym = symm_mem.empty(words, dtype=torch.float32, device=torch.device(device))
+            sym.zero_()
+            handle = symm_mem.rendezvous(sym, dist.group.WORLD)
+            ptrs = [int(x) for x in handle.buffer_ptrs]
+            assert len(ptrs) == dist.get_world_size() and ptrs[dist.get_rank()] == sym.data_ptr()
+            torch.cuda.synchronize()
+            dist.barrier()                                               # every rank's flags are zero before anybody's first call
+        except Exception as exc:                                         # no symmetric memory on this box: say so, use NCCL
+            self.collective += ' -- symmetric memory unavailable (%s: %s)' % (type(exc).__name__, str(exc)[:80])
+            return
+        self.sym, self._handle = sym, handle
+        self.peer_ptrs = (C.c_uint64 * len(ptrs))(*ptrs)
+        self.sumsq = torch.zeros(1, dtype=torch.float32, device=device)
+        self.collective = 'gsage_peer_allreduce: one-shot all-reduce over NVLink peer memory (symmetric memory), fused with the gradient norm'
+
     def grad_of(self, p):
-        return self.views[id(p)]
+        """Where the backward pass writes this parameter's LOCAL gradient (before the all-reduce)."""
+        return self.pre[id(p)]
 
     def attach(self):
         """Point every parameter's .grad at its slice (the optimiser then reads the reduced values in place)."""
         for p in self.params:
             p.grad = self.views[id(p)]
 
-    def _reduce(self, t, scale, async_op=False):
+    def _reduce(self, lo, hi, scale):
         # weight FIRST, then sum: shards may differ by one seed (shard_seeds follows np.array_split), so every rank has its
         # own local/global factor and the result must be sum_r scale_r * g_r -- scaling the sum would let replicas drift
+        if self.sym is not None:
+            assert lo == 0 and hi == self.flat.numel(), 'the one-shot peer all-reduce takes the whole bucket'
+            self.epoch += 1
+            check(lib().gsage_peer_allreduce(self.peer_ptrs, dist.get_world_size(), dist.get_rank(), self.flat.numel(), self.epoch,
+                                             float(scale), ops.ptr(self.flat), ops.ptr(self.sumsq), ops.stream()))
+            return
+        t = self.flat[lo:hi]
         if scale != 1.0:
             t.mul_(scale)
         if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
-            work = dist.all_reduce(t, op=dist.ReduceOp.SUM, async_op=async_op)
-            if async_op:
-                return work
-        return None
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+
+    @property
+    def one_shot(self):
+        return self.sym is not None
 
     def all_reduce(self, scale=1.0):
         """`scale` this rank's gradients (local/global batch weighting), then sum over ranks: the result equals the
         single-process gradient of the mean loss over the GLOBAL batch (problem.py:33)."""
-        self._reduce(self.flat, scale)
+        self._reduce(0, self.flat.numel(), scale)
 
     def all_reduce_head(self, scale=1.0):
-        self._reduce(self.flat[:self.head_numel], scale)
+        self._reduce(0, self.head_numel, scale)
 
     def all_reduce_tail(self, scale=1.0):
-        self._reduce(self.flat[self.head_numel:], scale)
+        self._reduce(self.head_numel, self.flat.numel(), scale)
 
 
 class FusedAdam(object):

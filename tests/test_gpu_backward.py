@@ -345,11 +345,12 @@ def test_train_step_with_the_dense_sampler(g):
 
 
 def test_backward_rejects_unsupported_plugins(g):
-    fix = util.load('model_mean_node_embedding')            # node_embedding WITH features (cat[feats, emb]): forward-only
-    model = build_model(g, fix, 'mean', 'node_embedding', True)
+    fix = util.load('model_mean_node_embedding')            # node_embedding WITH features (cat[feats, emb]): no FUSED backward --
+    model = build_model(g, fix, 'mean', 'node_embedding', True)     # train_step takes the plug-in autograd path instead
     g.set_seeds(1)
     preds = model(torch.from_numpy(fix['ids0']), torch.from_numpy(fix['feats']))
-    with pytest.raises(ValueError):
+    assert not model.has_fused_backward()
+    with pytest.raises(NotImplementedError):
         model.backward(torch.zeros_like(preds))
 
 

@@ -20,7 +20,7 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, q):
+def _worker(rank, world, port, q, skew=0):
     import torch.distributed as dist
     os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
     torch.cuda.set_device(rank)
@@ -34,8 +34,13 @@ def _worker(rank, world, port, q):
     feats = torch.from_numpy(fix['feats'])
     ids = torch.from_numpy(fix['ids0'])
     targets = torch.from_numpy(np.random.RandomState(0).randint(0, fix['logits'].shape[1], ids.shape[0]))
-    mine, tmine = shard_seeds(ids, rank, world), shard_seeds(targets, rank, world)
-    first = int(sum(shard_seeds(ids, r, world).shape[0] for r in range(rank)))
+    if skew:                                                          # uneven shards: rank 0 takes `skew` seeds more than half
+        cut = ids.shape[0] // 2 + skew
+        mine, tmine = (ids[:cut], targets[:cut]) if rank == 0 else (ids[cut:], targets[cut:])
+        first = 0 if rank == 0 else cut
+    else:
+        mine, tmine = shard_seeds(ids, rank, world), shard_seeds(targets, rank, world)
+        first = int(sum(shard_seeds(ids, r, world).shape[0] for r in range(rank)))
     g.set_seeds(int(fix['seed']))                                  # every rank: the same stream as the single process
     side = torch.cuda.Stream()
     preds = model.train_step(mine, feats, tmine.cuda(), F.cross_entropy, optimizer=False, clip=None,
@@ -43,13 +48,16 @@ def _worker(rank, world, port, q):
     torch.cuda.synchronize()
     st = g.default_rng().get_state()
     q.put((rank, first, model.peek('ids2').cpu().numpy(), preds.cpu().numpy(),
-           {n: p.grad.cpu().numpy() for n, p in model.named_parameters()}, st[1], st[2]))
+           {n: p.grad.cpu().numpy() for n, p in model.named_parameters()}, st[1], st[2], model._bucket().collective))
     dist.barrier()
     dist.destroy_process_group()
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason='needs 2 GPUs')
-def test_two_gpu_sharded_step_equals_single_gpu():
+@pytest.mark.parametrize('skew', [0, 5])
+def test_two_gpu_sharded_step_equals_single_gpu(skew):
+    """skew = 5: shards of different sizes -- every rank weights its gradient by ITS local/global batch before the sum
+    (scaling after the sum lets replicas drift)."""
     import torch.multiprocessing as mp
     from oracle import layers
     from tests import util
@@ -57,7 +65,7 @@ def test_two_gpu_sharded_step_equals_single_gpu():
     world, port = 2, _free_port()
     ctx = mp.get_context('spawn')
     q = ctx.Queue()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q, skew)) for r in range(world)]
     for p in procs:
         p.start()
     res = sorted([q.get(timeout=300) for _ in range(world)], key=lambda r: r[0])
@@ -78,3 +86,4 @@ def test_two_gpu_sharded_step_equals_single_gpu():
     for name, want in ps.items():
         for r in res:
             np.testing.assert_allclose(r[4][name], want.grad.numpy(), rtol=2e-3, atol=2e-5, err_msg=name)
+    print('collective:', res[0][7])

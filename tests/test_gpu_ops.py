@@ -94,10 +94,10 @@ def test_linear(g, a_dtype, n, d, O):
     for act, fn in ((None, lambda t: t), ('relu', torch.relu), ('tanh', torch.tanh)):
         want = fn(a[ids].double() @ w.double().t() + b.double())
         got = g.ops.linear([dict(a=a_dev, ids=ids.cuda(), w=w.cuda(), bias=b.cuda())], n, act=act)
-        np.testing.assert_allclose(got.cpu().numpy(), want.numpy(), rtol=1e-4, atol=1e-5)
+        np.testing.assert_allclose(got.detach().cpu().numpy(), want.numpy(), rtol=1e-4, atol=1e-5)
     want = a[:n].double() @ w.double().t()                       # no gather, no bias
     got = g.ops.linear([dict(a=a_dev, w=w.cuda())], n)
-    np.testing.assert_allclose(got.cpu().numpy(), want.numpy(), rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose(got.detach().cpu().numpy(), want.numpy(), rtol=1e-4, atol=1e-5)
 
 
 def test_linear_two_segments_concat(g):
@@ -109,7 +109,7 @@ def test_linear_two_segments_concat(g):
     got = g.ops.linear([dict(a=g.ops.aligned_rows(x.cuda()), w=wx.cuda(), col0=0),
                         dict(a=g.ops.aligned_rows(m.cuda()), w=wn.cuda(), col0=O)], n, act='relu')
     assert got.shape == (n, 2 * O)
-    np.testing.assert_allclose(got.cpu().numpy(), want.numpy(), rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose(got.detach().cpu().numpy(), want.numpy(), rtol=1e-4, atol=1e-5)
 
 
 def test_attention_weights_and_l2norm(g):
@@ -283,7 +283,7 @@ def test_lstm_aggregator_equals_torch_lstm(g, n, S, d, H, gather):
         got = agg.forward_ids(table.cuda(), ids_self.cuda(), ids_nb.cuda(), S)
     else:
         got = agg(xs.cuda(), nb.cuda())
-    np.testing.assert_allclose(got.cpu().numpy(), want.numpy(), rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose(got.detach().cpu().numpy(), want.numpy(), rtol=1e-4, atol=1e-5)
 
 
 @pytest.mark.parametrize('n,d,O', [(300, 64, 128), (128 * 200 + 5, 64, 128), (1000, 100, 64), (129, 256, 32), (777, 64, 16)])
