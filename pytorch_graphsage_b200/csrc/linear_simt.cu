@@ -209,17 +209,25 @@ int linear_dispatch(const LinearParams& P, int exact, cudaStream_t s) {
             bool any = false;
             for (int i = 0; i < P.n_segs; ++i) {
                 const LinearSeg& g = P.seg[i];
-                for (int c = 0; c < g.O; c += 128) {
+                // the widest column block whose (hi, lo) weights fit: 128, else 64 / 32 (layer 2's 256-wide rows), else FFMA
+                int blk = 0;
+                for (int cand = 128; cand >= 32 && !blk; cand >>= 1) {
+                    LinearParams probe = P;
+                    probe.n_segs = 1; probe.seg[0] = g; probe.seg[0].O = g.O < cand ? g.O : cand;
+                    if (linear_ws_umma_x3_eligible(probe)) blk = cand;
+                }
+                for (int c = 0; c < g.O; c += (blk ? blk : 128)) {
+                    const int width = blk ? blk : 128;
                     LinearParams one = P;
                     one.n_segs = 1;
                     one.seg[0] = g;
-                    one.seg[0].O = g.O - c < 128 ? g.O - c : 128;
+                    one.seg[0].O = g.O - c < width ? g.O - c : width;
                     one.seg[0].w = (const char*)g.w + (size_t)c * g.ldw * sizeof(float);
                     one.seg[0].w_hi = (const char*)g.w_hi + (size_t)c * g.ldw * sizeof(float);
                     one.seg[0].w_lo = (const char*)g.w_lo + (size_t)c * g.ldw * sizeof(float);
                     one.seg[0].bias = g.bias ? g.bias + c : nullptr;
                     one.seg[0].col0 = g.col0 + c;
-                    if (linear_ws_umma_x3_eligible(one)) { GS_TRY(linear_ws_umma_x3_launch(one, s)); any = true; }
+                    if (blk && linear_ws_umma_x3_eligible(one)) { GS_TRY(linear_ws_umma_x3_launch(one, s)); any = true; }
                     else GS_TRY(linear_simt_launch(one, s));
                 }
             }

@@ -33,6 +33,20 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* er
         }
     }
 }
+// the same for a waiter that is far AHEAD of what it waits for (a producer waiting for a free buffer): back off between polls,
+// so that the poll loop does not take issue slots from the warps doing the work (ncu on the attention kernel: 32 M polls, 90 % of
+// all executed instructions, from twelve producer lanes)
+__device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity, int* err) {
+    if (mbar_try(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try(bar, parity)) {
+        __nanosleep(256);
+        if (clock64() - t0 > 4000000000LL) {
+            if (err) atomicExch(err, 1);
+            __trap();
+        }
+    }
+}
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
 }

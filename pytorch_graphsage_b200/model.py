@@ -69,7 +69,9 @@ class GSSupervised(nn.Module):
                  adj, train_adj, lr_init=0.01, weight_decay=0.0, lr_schedule='constant', epochs=10,
                  compute_dtype=torch.float32, max_batch=512, rng=None, allow_tf32=False):
         super(GSSupervised, self).__init__()
-        assert len(layer_specs) == 2, 'GSSupervised: the engine implements the two-layer stack of train.py:105-118'
+        # the fused engine implements the two-layer stack train.py:105-118 hard-codes; any other depth (models.py:50-62,85-86 loop over
+        # whatever `layer_specs` holds) runs the reference's dataflow over the plug-in operators (forward_reference_order)
+        self.fused = len(layer_specs) == 2
         self.layer_specs = layer_specs
         self.n_nodes, self.n_classes = n_nodes, n_classes
         self.compute_dtype = compute_dtype
@@ -225,6 +227,10 @@ class GSSupervised(nn.Module):
         stream right behind this forward (sample-ahead) and ordered after whatever produced `next_ids` on the current stream
         BEFORE this call -- the next forward must then be given that same batch.  Out-of-range ids and rng window faults of
         EARLIER forwards are raised here (IndexError / GsageError) from sticky flags polled without a synchronisation."""
+        if not self.fused:
+            assert shard is None and next_ids is None, 'GSSupervised: seed sharding / sample-ahead need the two-layer engine'
+            with torch.no_grad():
+                return self.forward_reference_order(ids, feats, train=train)
         sampler = self.train_sampler if train else self.val_sampler
         fanout = [s['n_train_samples' if train else 'n_val_samples'] for s in self.layer_specs]
         ids = torch.as_tensor(ids).to(device='cuda', dtype=torch.int64).contiguous().view(-1)
@@ -323,6 +329,8 @@ class GSSupervised(nn.Module):
         trains through the narrow plug-in API's autograd Functions (train_step picks automatically), the LSTM aggregator included."""
         bf16 = self.compute_dtype == torch.bfloat16
         with_feats = self.input_dim is not None
+        if not self.fused:
+            return False
         if self._agg_name == 'mean':
             return self._prep_name in ('identity', 'linear') or (self._prep_name == 'node_embedding' and not with_feats and not bf16
                                                                   and not self.allow_tf32)

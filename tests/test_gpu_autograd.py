@@ -237,3 +237,43 @@ def test_device_metrics_match_sklearn(g, task):
             assert abs(got_dev - want) < 1e-4 * max(1.0, abs(want))
         else:
             assert abs(got_dev['micro'] - want['micro']) < 1e-9 and abs(got_dev['macro'] - want['macro']) < 1e-9
+
+
+def test_three_layer_stack_runs_over_the_plugin_operators(g):
+    """models.py:50-62,85-86 loop over however many `layer_specs` there are (train.py happens to pass two, which is what the fused
+    engine implements).  Any other depth takes the reference's dataflow over the plug-in operators: same draws, same logits, and it
+    trains.  Three layers, fanouts 4 / 3 / 2, against the oracle on ids re-sampled from the same MT19937 stream."""
+    from oracle import sampler as osampler
+    from oracle.mt19937 import MT19937Oracle
+    from pytorch_graphsage_b200 import synth
+    prob = synth.make_problem('tiny', seed=2)
+    adj = prob['adj']
+    graph = g.GraphCSR.from_synth(adj)
+    torch.manual_seed(9)
+    specs = [dict(n_train_samples=4, n_val_samples=4, output_dim=16, activation=F.relu),
+             dict(n_train_samples=3, n_val_samples=3, output_dim=16, activation=F.relu),
+             dict(n_train_samples=2, n_val_samples=2, output_dim=8, activation=lambda x: x)]
+    model = g.GSSupervised(input_dim=prob['feats_dim'], n_nodes=prob['n_nodes'], n_classes=prob['n_classes'], layer_specs=specs,
+                           aggregator_class=g.aggregator_lookup['mean'], prep_class=g.prep_lookup['identity'],
+                           sampler_class=g.sampler_lookup['sparse_uniform_neighbor_sampler'], adj=graph, train_adj=graph).cuda()
+    assert not model.fused and not model.has_fused_backward()
+    ids0 = synth.seed_batch(prob, 40, seed=5)
+    feats = torch.from_numpy(prob['feats'])
+    targets = torch.from_numpy(np.random.RandomState(3).randint(0, prob['n_classes'], ids0.shape[0]))
+    g.set_seeds(31)
+    before = {n: p.detach().clone() for n, p in model.named_parameters()}
+    preds = model.train_step(torch.from_numpy(ids0), feats, targets.cuda(), F.cross_entropy, optimizer=False, clip=None)
+
+    indptr, data, shape = adj['indptr'], adj['data'], adj['shape']
+    indices = np.arange(data.shape[0]) - np.repeat(indptr[:-1], np.diff(indptr))
+    deg = osampler.row_degrees(indptr, data)
+    rs = MT19937Oracle(31)
+    hops = [ids0]
+    for S in (4, 3, 2):
+        hops.append(osampler.sparse_sample(indptr, indices, data, shape, deg, hops[-1], S, rs.randint))
+    ps = {k: v.detach().cpu().clone().requires_grad_(True) for k, v in before.items()}
+    want = layers.forward_stack([torch.from_numpy(h) for h in hops], feats, ps, acts=('relu', 'relu', 'identity'))
+    np.testing.assert_allclose(preds.cpu().numpy(), want.detach().numpy(), rtol=1e-4, atol=1e-5)
+    F.cross_entropy(want, targets).backward()
+    for name, p in model.named_parameters():
+        np.testing.assert_allclose(p.grad.cpu().numpy(), ps[name].grad.numpy(), err_msg=name, **TOL)

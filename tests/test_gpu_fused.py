@@ -1,6 +1,6 @@
 """gather_mean_project_umma.cu: the neighbour half of the mean aggregator as ONE kernel (gather + mean + projection; the reduced rows
-never reach HBM).  It is the forward-only default of the bf16 engine (GSAGE_FUSED_LAYER=0 switches back to the two-kernel path,
-which training always uses because the backward reads the reduced rows).  GPU only.
+never reach HBM).  Opt-in (GSAGE_FUSED_LAYER=1): measured against the two kernels it replaces it wins on rows <= 512 bytes and loses on the 1216-byte
+reddit rows (profiles/README.md); training always uses the two-kernel path because the backward reads the reduced rows.  GPU only.
 
 Bars: the engine's bf16 logits with the fused kernel equal the two-kernel bf16 logits (same arithmetic order: expected
 bit-identical, asserted to 1e-3) and stay inside the bf16 bar (3e-2) against the fp32 reference fixture."""
@@ -43,6 +43,7 @@ def test_fused_gather_mean_project_equals_unfused(g, case, monkeypatch):
 
 @pytest.mark.parametrize('S,d', [(10, 602), (25, 602), (10, 256), (25, 64), (7, 100)])
 def test_fused_gather_mean_project_at_scale(g, S, d, monkeypatch):
+    monkeypatch.setenv('GSAGE_FUSED_LAYER', '1')
     """Many tiles per CTA (the A tile is single-buffered: tile i+1's stores wait for tile i's MMAs), ragged last tile, the
     compile-time fanouts (10, 25) and the run-time one, every row-width class (1-3 sixteen-byte units per lane)."""
     from pytorch_graphsage_b200 import ops

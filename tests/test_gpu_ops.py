@@ -367,7 +367,7 @@ def test_weight_stationary_kernel_equals_streaming_kernel(g, n, d, O, monkeypatc
 # the same bf16 operands: rtol 2e-2 / atol 2e-2 on unit-variance rows (measured ~3e-3).
 
 @pytest.mark.parametrize('n,S,d,gather', [(300, 10, 256, True), (77, 25, 256, False), (1000, 10, 602, True), (64, 2, 64, True),
-                                          (5, 128, 100, True), (513, 3, 8, False)])
+                                          (5, 128, 100, True), (513, 3, 8, False), (20000, 10, 256, True), (64, 8, 64, True), (5, 32, 100, True)])
 def test_fused_attention_aggregate(g, n, S, d, gather):
     gen = torch.Generator().manual_seed(n + S + d)
     H = 32
