@@ -1011,6 +1011,36 @@ static int forward_layers(gsage_engine* e, int64_t B, float* logits_dev, cudaStr
     const int O1 = c.out_dim[0], O2 = c.out_dim[1];
     x_seed = lvl;
     if (e->fold_prep) x_seed.ids = e->look0;
+    // mean aggregator: layer 1's two applications share their weights, the self rows of all n0 + n1 parents are the prefix
+    // [ids0 | ids1] of the id buffer and their reduced rows are adjacent in M -- so both reductions run first and ONE projection
+    // launch covers the 26*B parents (one launch, one pipeline fill and one tail instead of two; GSAGE_MERGE_L1=0 keeps them apart)
+    static const bool merge_l1 = [] { const char* f = getenv("GSAGE_MERGE_L1"); return !f || atoi(f) != 0; }();
+    const bool fused_mean_taken = T == GSAGE_BF16 && !e->keep_activations && getenv("GSAGE_FUSED_LAYER") != nullptr && atoi(getenv("GSAGE_FUSED_LAYER")) != 0;
+    if (merge_l1 && c.aggregator == GSAGE_AGG_MEAN && !e->fold_prep && !e->fuse_mean && !fused_mean_taken && e->chunk_parents == 0) {
+        const int exact = (T == GSAGE_F32 && !c.allow_tf32);
+        const int d = lvl.d;
+        const RowSrc nb0 = lvl.shifted(n0), nb1 = lvl.shifted(n0 + n1);
+        const int p_app0 = e->prof.begin(GSAGE_PROF_APP0, s);
+        GS_TRY(gather_reduce_launch(nb0.base, nb0.dtype, nb0.ld, nb0.table_rows, d, nb0.ids, n0, S1, GSAGE_RED_MEAN, nullptr, e->M, T, e->ld_m, s));
+        e->prof.end(p_app0, s);
+        const int p_red = e->prof.begin(GSAGE_PROF_REDUCE, s);
+        GS_TRY(gather_reduce_launch(nb1.base, nb1.dtype, nb1.ld, nb1.table_rows, d, nb1.ids, n1, S2, GSAGE_RED_MEAN, nullptr,
+                                    (char*)e->M + n0 * e->ld_m * es, T, e->ld_m, s));
+        e->prof.end(p_red, s);
+        e->prof.work(p_red, GSAGE_PROF_REDUCE, (double)n1 * ((double)S2 * d * dtype_size(nb1.dtype) + (nb1.ids ? 8.0 * S2 : 0.0) + (double)d * dtype_size(T)),
+                     (double)n1 * S2 * d);
+        if (e->ahead_after_gather) {
+            if (!e->ev_mid) GS_CUDA(cudaEventCreateWithFlags(&e->ev_mid, cudaEventDisableTiming));
+            GS_CUDA(cudaEventRecord(e->ev_mid, s));
+            e->mid_valid = true;
+        }
+        RowSrc m{e->M, T, e->ld_m, n0 + n1, nullptr, d};
+        const int p_prj = e->prof.begin(GSAGE_PROF_PROJECT, s);
+        GS_TRY(combine_call(lvl, e->w_x[0], m, e->w_n[0], O1, n0 + n1, c.act[0], e->H1, T, ldh, exact, s, e->b_x[0], e->b_n[0]));
+        e->prof.end(p_prj, s);
+        e->prof.work(p_prj, GSAGE_PROF_PROJECT, (double)(n0 + n1) * ((double)d * dtype_size(lvl.dtype) + (lvl.ids ? 8.0 : 0.0) + (double)d * dtype_size(T) +
+                                                                     2.0 * O1 * dtype_size(T)), 4.0 * (double)(n0 + n1) * d * O1);
+    } else {
     const int p_app0 = e->prof.begin(GSAGE_PROF_APP0, s);
     GS_TRY(apply_aggregator(e, 0, x_seed, lvl.shifted(n0), n0, S1, e->H1, T, ldh, 0, s));
     e->prof.end(p_app0, s);
@@ -1022,6 +1052,7 @@ static int forward_layers(gsage_engine* e, int64_t B, float* logits_dev, cudaStr
         }
     } else {
         GS_TRY(apply_aggregator(e, 0, lvl.shifted(n0), lvl.shifted(n0 + n1), n1, S2, (char*)e->H1 + n0 * ldh * es, T, ldh, n0, s));
+    }
     }
 
     // ---- layer 2 on (h0, h1) ----------------------------------------------------------------------------------

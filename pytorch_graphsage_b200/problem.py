@@ -1,13 +1,22 @@
 """
-Batch iterator of the reference (`NodeProblem.iterate`, /root/reference/problem.py:141-153) with the per-epoch
-shuffle drawn from the DEVICE MT19937 stream (`gsage_rng_permutation`), i.e. from the same global stream, at the
-same position, the reference's `np.random.permutation` would use -- so an epoch of seed batches followed by the
-sampler's draws stays bit-exact with the reference without a host round trip.  SURVEY.md 8(f) row 1.
+The problem side of the reference's training script (/root/reference/problem.py), device-resident:
+
+  * `iterate`        -- the batch iterator `NodeProblem.iterate` (problem.py:141-153) with the per-epoch shuffle drawn from the
+                        DEVICE MT19937 stream (`gsage_rng_permutation`), i.e. from the same global stream, at the same position,
+                        the reference's `np.random.permutation` would use -- an epoch of seed batches followed by the sampler's
+                        draws stays bit-exact with the reference without a host round trip;
+  * `ProblemLosses`  -- problem.py:26-41 (stock torch losses on the logits);
+  * `ProblemMetrics` -- problem.py:44-64 computed ON THE DEVICE (gsage_metric_f1 / gsage_metric_mae, csrc/metrics.cu);
+  * `NodeProblem`    -- the fields and methods train.py touches (problem.py:74-153) over in-memory arrays.
 """
 
 import numpy as np
 import torch
+from torch.nn import functional as _F
 
+from . import ops as _ops
+from ._lib import check as _check, lib as _lib_handle
+from .graph import GraphCSR as _GraphCSR
 from .rng import default_rng
 
 
@@ -33,15 +42,6 @@ def iterate(nodes, targets, batch_size=512, shuffle=False, rng=None):
 # (the h5 container itself is out of scope: h5py is not part of this stack; `problem.h5`'s keys map 1:1 onto the
 # arguments of `NodeProblem.from_arrays`, and the sparse adjacency travels as the file's 3 x nnz [v; r; c] array).
 # --------------------------------------------------------------------------------------------------------------------
-import ctypes as _C
-
-from torch.nn import functional as _F
-
-from . import ops as _ops
-from ._lib import check as _check, lib as _lib_handle
-from .graph import GraphCSR as _GraphCSR
-
-
 class ProblemLosses(object):
     """problem.py:26-41 -- stock torch losses on the logits (the loss itself is out of scope; its gradient w.r.t. the logits
     is what enters the library's backward pass)."""

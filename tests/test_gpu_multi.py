@@ -54,9 +54,9 @@ def _worker(rank, world, port, q, skew=0):
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason='needs 2 GPUs')
-@pytest.mark.parametrize('skew', [0, 5])
+@pytest.mark.parametrize('skew', [0, 2])
 def test_two_gpu_sharded_step_equals_single_gpu(skew):
-    """skew = 5: shards of different sizes -- every rank weights its gradient by ITS local/global batch before the sum
+    """skew = 2: shards of different sizes (8 and 4 of the fixture's 12 seeds) -- every rank weights its gradient by ITS local/global batch before the sum
     (scaling after the sum lets replicas drift)."""
     import torch.multiprocessing as mp
     from oracle import layers
