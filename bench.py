@@ -617,11 +617,17 @@ def run_leg(args, workload, B, steps, warmup, main):
         for i in range(3):
             train_step(i)
         barrier()
+        prof_train = os.environ.get('GSAGE_BENCH_PROFILE_TRAIN') == '1'           # ncu --profile-from-start off: the train steps only
+        if prof_train:
+            torch.cuda.synchronize()
+            torch.cuda.profiler.start()
         ev0.record()
         for i in range(3, 3 + k_train):
             train_step(i)
         ev1.record()
         barrier()
+        if prof_train:
+            torch.cuda.profiler.stop()
         if ahead:
             model(dev_ids[(3 + k_train) % n_batches], table)                       # drain the pending batch
         t_ms = max_over_ranks(ev0.elapsed_time(ev1)) / k_train

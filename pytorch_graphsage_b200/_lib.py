@@ -7,7 +7,8 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, 'libgsage_b200.so')
+# GSAGE_B200_LIB: load another build of the same library (profiles/scripts/build_timing_lib.sh: in-kernel cycle counters)
+LIB_PATH = os.environ.get('GSAGE_B200_LIB') or os.path.join(HERE, 'libgsage_b200.so')
 
 F32, BF16 = 0, 1
 ABI_VERSION = 3

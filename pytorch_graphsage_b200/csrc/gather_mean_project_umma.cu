@@ -161,7 +161,7 @@ __global__ void __launch_bounds__(kFgThreads, 1) gather_mean_project_kernel(cons
     } else if (warp < kFgEpiWarps + kFgIssueWarps) {
         // =========================== W LOAD + MMA ISSUER (one thread of warp 4) ===========================
         setmaxnreg_dec<24>();
-        if (warp == kFgEpiWarps && lane == 0) {
+        if (warp == kFgEpiWarps && elect_one()) {          // (elect_one, not lane == 0: umma_ptx.cuh)
             mbar_arrive_expect_tx(w_full, (uint32_t)P.nk * w_plane);
             for (int kc = 0; kc < P.nk; ++kc) tma_load_2d(smem_u32(w_area) + (uint32_t)kc * w_plane, &w_map, kc * 64, 0, w_full);
             mbar_wait(w_full, 0, P.err);

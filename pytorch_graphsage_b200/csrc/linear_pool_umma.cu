@@ -130,7 +130,7 @@ __global__ void __launch_bounds__(kPoolThreads, 1) linear_pool_umma_kernel(const
                 const int stage = item % P.stages;
                 mbar_wait(full_bar(stage), (item / P.stages) & 1, P.err);
                 tc_fence_after();
-                if (lane == 0) {
+                if (elect_one()) {                             // (not lane == 0: umma_ptx.cuh)
                     const uint32_t base = smem_u32(smem + (size_t)stage * P.stage_bytes);
                     const uint64_t bdesc = umma_desc(base + kHB * kMBytes);
                     for (int j = 0; j < nb; ++j) {
@@ -145,7 +145,7 @@ __global__ void __launch_bounds__(kPoolThreads, 1) linear_pool_umma_kernel(const
                 }
                 __syncwarp();
             }
-            if (lane == 0) umma_commit(tfull_bar);
+            if (elect_one()) umma_commit(tfull_bar);
             __syncwarp();
         }
     } else {
@@ -169,14 +169,20 @@ __global__ void __launch_bounds__(kPoolThreads, 1) linear_pool_umma_kernel(const
                 const int stage = item % P.stages;
                 mbar_wait(empty_bar(stage), ((item / P.stages) & 1) ^ 1, P.err);
                 const uint32_t base = smem_u32(smem + (size_t)stage * P.stage_bytes);
-                if (lane == 0) {
+                if (elect_one()) {
                     mbar_arrive_expect_tx(full_bar(stage), (uint32_t)(nb * kMBytes) + n_bytes);
                     for (int j = 0; j < nb; ++j) tma_load_2d(base + j * kMBytes, &M.w, kc * P.uk, (pass * kHB + j) * PM, full_bar(stage));
                     if (!P.ids) tma_load_2d(base + kHB * kMBytes, &M.a, kc * P.uk, (int)row0, full_bar(stage));
                 }
+                if (P.ids) {
+                    const bool elected = elect_one();
+                    for (int l = 0; l < groups; ++l) {                 // the ids of rows 4l .. 4l+3 live in lane l: hand them to the issuing lane
+                        const int a = __shfl_sync(0xFFFFFFFFu, rid[0], l), b = __shfl_sync(0xFFFFFFFFu, rid[1], l);
+                        const int c = __shfl_sync(0xFFFFFFFFu, rid[2], l), d = __shfl_sync(0xFFFFFFFFu, rid[3], l);
+                        if (elected) tma_gather4(base + kHB * kMBytes + l * 512, &M.g, kc * P.uk, a, b, c, d, full_bar(stage));
+                    }
+                }
                 __syncwarp();
-                if (P.ids && lane < groups)
-                    tma_gather4(base + kHB * kMBytes + lane * 512, &M.g, kc * P.uk, rid[0], rid[1], rid[2], rid[3], full_bar(stage));
             }
         }
     }

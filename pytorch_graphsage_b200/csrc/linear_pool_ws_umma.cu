@@ -40,12 +40,13 @@ struct QParams {
     const float* bias; int64_t col0;
     int d, H, S, R, PT;                           // R = PT * S rows of a tile are used
     int64_t n_rows, n_parents;
-    int n_tiles, h_blocks, bpp, n_phases, kchunks, uk, tf32;
+    int n_tiles, h_blocks, bpp, n_phases, kchunks, uk, tf32, dbg_skip;
     void* out; int out_bf16; int64_t ld_out;
     // backward mode: recompute the hidden rows and emit d loss / d hidden (bf16) from d loss / d pooled
     const float* dP; int64_t ld_dp; __nv_bfloat16* dhid; int64_t ld_dhid;
     float* db;                                    // += column sums of d hidden (the MLP bias gradient); may be NULL
     int* err;
+    long long* dbg;                               // GSAGE_POOL_TIMING builds only: per-role cycle counters of CTA 0
 };
 
 struct QMaps { CUtensorMap w; CUtensorMap a; };
@@ -84,6 +85,16 @@ __device__ __forceinline__ float q_backward_parent(const QParams& P, const float
     return total;
 }
 
+#ifdef GSAGE_POOL_TIMING
+#define QT_DECL long long qt_a = 0, qt_b = 0, qt_c = 0, qt_d = 0, qt_t = clock64()
+#define QT_LAP(x) do { const long long n_ = clock64(); (x) += n_ - qt_t; qt_t = n_; } while (0)
+#define QT_OUT(base, cond) do { if (P.dbg && blockIdx.x == 0 && (cond)) { P.dbg[(base)] = qt_a; P.dbg[(base) + 1] = qt_b; P.dbg[(base) + 2] = qt_c; P.dbg[(base) + 3] = qt_d; } } while (0)
+#else
+#define QT_DECL
+#define QT_LAP(x)
+#define QT_OUT(base, cond)
+#endif
+
 template <bool POOL_MAX, int S_CT, bool BWD>
 __global__ void __launch_bounds__(kQThreads, 1) linear_pool_ws_umma_kernel(const QParams P, const __grid_constant__ QMaps M) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -121,6 +132,7 @@ __global__ void __launch_bounds__(kQThreads, 1) linear_pool_ws_umma_kernel(const
         const int S = S_CT > 0 ? S_CT : P.S;
         const int PT = S_CT > 0 ? QN / S_CT : P.PT;
         int it = 0;
+        QT_DECL;
         for (int ph = 0; ph < P.n_phases; ++ph) {
             const int hb = ph * P.bpp + slot;
             const bool mine = slot < P.bpp && hb < P.h_blocks;
@@ -130,15 +142,22 @@ __global__ void __launch_bounds__(kQThreads, 1) linear_pool_ws_umma_kernel(const
             float bsum = 0.0f;                                 // backward: this hidden unit's bias gradient over the CTA's tiles
             for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x, ++it) {
                 const int buf = it & 1;
+                QT_LAP(qt_d);
                 mbar_wait(tfull_bar(buf), (it >> 1) & 1, P.err);
                 tc_fence_after();
+                QT_LAP(qt_a);
+#ifdef GSAGE_POOL_TIMING
+                if (mine && !P.dbg_skip) {
+#else
                 if (mine) {
+#endif
                     const int64_t parent0 = (int64_t)tile * PT;
                     const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * 256 + slot * QN);
                     uint32_t r0[32], r1[32];
                     tmem_ld32(taddr, r0);
                     tmem_ld32(taddr + 32, r1);
                     tmem_ld_wait();
+                    QT_LAP(qt_b);
                     if (BWD) {
                         // ---- backward: d hidden[row, h] from d pooled[parent, h] (the forward's MMAs recomputed) ----
                         float v[QN];
@@ -172,17 +191,44 @@ __global__ void __launch_bounds__(kQThreads, 1) linear_pool_ws_umma_kernel(const
                     } else
                     if (S_CT > 0) {
                         // static parent boundaries: element i of the tile belongs to parent i / S_CT
+                        constexpr int SS = S_CT > 0 ? S_CT : 1, NP = QN / SS;
+                        float acc[NP];
 #pragma unroll
-                        for (int p = 0; p < QN / (S_CT > 0 ? S_CT : 1); ++p) {
-                            float acc = POOL_MAX ? -3.0e38f : 0.0f;
+                        for (int p = 0; p < NP; ++p) {
+                            acc[p] = POOL_MAX ? -3.0e38f : 0.0f;
 #pragma unroll
-                            for (int j = 0; j < (S_CT > 0 ? S_CT : 1); ++j) {
-                                const int i = p * S_CT + j;
+                            for (int j = 0; j < SS; ++j) {
+                                const int i = p * SS + j;
                                 const float v = __uint_as_float(i < 32 ? r0[i & 31] : r1[i & 31]);
-                                if (POOL_MAX) acc = fmaxf(acc, v);
-                                else acc += fmaxf(v + bias, 0.0f);
+                                if (POOL_MAX) acc[p] = fmaxf(acc[p], v);
+                                else acc[p] += fmaxf(v + bias, 0.0f);
                             }
-                            if (h_ok && parent0 + p < P.n_parents) q_store<POOL_MAX>(P, parent0 + p, h, acc, bias);
+                            acc[p] = POOL_MAX ? fmaxf(acc[p] + bias, 0.0f) : acc[p] * (1.0f / (float)SS);
+                        }
+                        // stores: one base address per tile, a stride per parent; whole tiles (all but the last) skip the bounds checks.
+                        // (The first version rebuilt a 64-bit address and a bounds predicate per parent: ~110 of its ~140 instructions.)
+                        if (h_ok) {
+                            const int np = parent0 + NP <= P.n_parents ? NP : (int)(P.n_parents - parent0);
+                            const int64_t at = parent0 * P.ld_out + P.col0 + h;
+                            if (P.out_bf16) {
+                                __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(P.out) + at;
+                                if (np == NP) {
+#pragma unroll
+                                    for (int p = 0; p < NP; ++p) o[p * P.ld_out] = __float2bfloat16_rn(acc[p]);
+                                } else {
+#pragma unroll
+                                    for (int p = 0; p < NP; ++p) if (p < np) o[p * P.ld_out] = __float2bfloat16_rn(acc[p]);
+                                }
+                            } else {
+                                float* o = reinterpret_cast<float*>(P.out) + at;
+                                if (np == NP) {
+#pragma unroll
+                                    for (int p = 0; p < NP; ++p) o[p * P.ld_out] = acc[p];
+                                } else {
+#pragma unroll
+                                    for (int p = 0; p < NP; ++p) if (p < np) o[p * P.ld_out] = acc[p];
+                                }
+                            }
                         }
                     } else {
                         float acc = POOL_MAX ? -3.0e38f : 0.0f;
@@ -202,39 +248,54 @@ __global__ void __launch_bounds__(kQThreads, 1) linear_pool_ws_umma_kernel(const
                         }
                     }
                 }
+                QT_LAP(qt_c);
                 tc_fence_before();
                 mbar_arrive(tempty_bar(buf));
             }
             if (BWD && P.db && h_ok) atomicAdd(P.db + h, bsum);
         }
+        QT_OUT(0, threadIdx.x == 0);                           // wait tfull | tcgen05.ld + wait | pool + stores | arrive + loop
     } else if (warp == kQEpiWarps) {
-        // ============ MMA ISSUER: D[buf][blk][hidden, row] += W[blk][kc] . rows[kc]^T, one thread, lean loop ============
-        if (lane == 0) {
+        // ============ MMA ISSUER: D[buf][blk][hidden, row] += W[blk][kc] . rows[kc]^T, one elected thread, lean loop ============
+        // (elect_one, not lane == 0: see umma_ptx.cuh -- this loop was 2600 of the kernel's 2900 cycles per tile before)
+        if (elect_one()) {
             const uint32_t fmt = P.tf32 ? 2u : 1u;
             const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(QN >> 3) << 17) | ((uint32_t)(QM >> 4) << 24);
             const uint64_t desc_hi = umma_desc(0);
             const uint32_t ring16 = (smem_u32(ring) & 0x3FFFF) >> 4, w16 = (smem_u32(smem) & 0x3FFFF) >> 4;
             const int kchunks = P.kchunks;
+            const bool tf32 = P.tf32 != 0;
             uint32_t stage = 0, par = 0, b16 = ring16;
             int it = 0;
+            QT_DECL;
             for (int ph = 0; ph < P.n_phases; ++ph) {
                 const int nb = min(P.bpp, P.h_blocks - ph * P.bpp);
                 mbar_wait(wfull_bar, ph & 1, P.err);
                 for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x, ++it) {
                     const uint32_t buf = it & 1;
+                    QT_LAP(qt_c);
                     mbar_wait(tempty_bar(buf), ((it >> 1) & 1) ^ 1, P.err);
                     tc_fence_after();
+                    QT_LAP(qt_a);
                     const uint32_t d0 = tmem_base + buf * 256u;
                     for (int kc = 0; kc < kchunks; ++kc) {
                         mbar_wait(full_bar(stage), par, P.err);
                         tc_fence_after();
+                        QT_LAP(qt_b);
                         const uint64_t bdesc = desc_hi | (uint64_t)b16;
-                        for (int j = 0; j < nb; ++j) {
-                            const uint64_t adesc = desc_hi | (uint64_t)(w16 + (uint32_t)(j * kchunks + kc) * (kQWChunk >> 4));
+                        uint64_t adesc = desc_hi | (uint64_t)(w16 + (uint32_t)kc * (kQWChunk >> 4));
+                        const uint32_t acc = kc ? 1u : 0u;
+                        if (tf32) {
+                            for (int j = 0; j < nb; ++j, adesc += (uint64_t)(kchunks * (kQWChunk >> 4))) {
+                                umma_tf32(d0 + j * QN, adesc, bdesc, idesc, acc);
 #pragma unroll
-                            for (int k = 0; k < 4; ++k) {
-                                if (P.tf32) umma_tf32(d0 + j * QN, adesc + 2 * k, bdesc + 2 * k, idesc, (kc | k) ? 1u : 0u);
-                                else umma_bf16(d0 + j * QN, adesc + 2 * k, bdesc + 2 * k, idesc, (kc | k) ? 1u : 0u);
+                                for (int k = 1; k < 4; ++k) umma_tf32(d0 + j * QN, adesc + 2 * k, bdesc + 2 * k, idesc, 1u);
+                            }
+                        } else {
+                            for (int j = 0; j < nb; ++j, adesc += (uint64_t)(kchunks * (kQWChunk >> 4))) {
+                                umma_bf16(d0 + j * QN, adesc, bdesc, idesc, acc);
+#pragma unroll
+                                for (int k = 1; k < 4; ++k) umma_bf16(d0 + j * QN, adesc + 2 * k, bdesc + 2 * k, idesc, 1u);
                             }
                         }
                         umma_commit(empty_bar(stage));
@@ -244,57 +305,77 @@ __global__ void __launch_bounds__(kQThreads, 1) linear_pool_ws_umma_kernel(const
                 }
                 umma_commit(wempty_bar);
             }
+            QT_LAP(qt_c);
+            QT_OUT(4, true);                                   // wait tempty | wait full (rows landed) | issue MMAs + commits
         }
         __syncwarp();
     } else {
-        // ============ TMA PRODUCERS ============
+        // ============ TMA PRODUCERS: one elected lane per warp; producer pw owns tile rows 16 pw .. 16 pw + 15 ============
+        // The lane loads its 16 row ids one tile AHEAD (a dependent global load per tile would be exposed latency) and issues
+        // the four gather4 of a k-chunk back to back.
         const int pw = warp - (kQEpiWarps + 1);
-        const bool lead = pw == 0 && lane == 0;
-        const uint32_t ring_u = smem_u32(ring);
-        const int uk = P.uk, kchunks = P.kchunks;
-        const int my_row = 16 * pw + 4 * lane;                 // gather: lanes 0..3 of producer pw own tile rows my_row .. + 3
-        uint32_t stage = 0, par = 1, sa_u = ring_u;
-        for (int ph = 0; ph < P.n_phases; ++ph) {
-            if (lead) {
-                const int nb = min(P.bpp, P.h_blocks - ph * P.bpp);
-                mbar_wait(wempty_bar, (ph & 1) ^ 1, P.err);
-                mbar_arrive_expect_tx(wfull_bar, (uint32_t)(nb * kchunks * kQWChunk));
-                for (int j = 0; j < nb; ++j)
-                    for (int kc = 0; kc < kchunks; ++kc)
-                        tma_load_2d(smem_u32(smem) + (uint32_t)(j * kchunks + kc) * kQWChunk, &M.w, kc * uk, (ph * P.bpp + j) * QM, wfull_bar);
-            }
-            for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x) {
-                const int64_t row0 = (int64_t)tile * P.R;
+        if (elect_one()) {
+            const bool lead = pw == 0;
+            const uint32_t ring_u = smem_u32(ring);
+            const int uk = P.uk, kchunks = P.kchunks;
+            const int my_row = 16 * pw;
+            uint32_t stage = 0, par = 1, sa_u = ring_u;
+            QT_DECL;
+            auto load_ids = [&](int tile, int* r) {
+                const int64_t base = (int64_t)tile * P.R + my_row;
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {                 // unconditional loads from a clamped address, masked afterwards
+                    const int64_t at = base + i;
+                    const bool ok = tile < P.n_tiles && my_row + i < P.R && at < P.n_rows;
+                    const int v = (int)__ldg(P.ids + (ok ? at : 0));
+                    r[i] = ok ? v : 0;
+                }
+            };
+            for (int ph = 0; ph < P.n_phases; ++ph) {
+                if (lead) {
+                    const int nb = min(P.bpp, P.h_blocks - ph * P.bpp);
+                    mbar_wait(wempty_bar, (ph & 1) ^ 1, P.err);
+                    mbar_arrive_expect_tx(wfull_bar, (uint32_t)(nb * kchunks * kQWChunk));
+                    for (int j = 0; j < nb; ++j)
+                        for (int kc = 0; kc < kchunks; ++kc)
+                            tma_load_2d(smem_u32(smem) + (uint32_t)(j * kchunks + kc) * kQWChunk, &M.w, kc * uk, (ph * P.bpp + j) * QM, wfull_bar);
+                }
                 if (P.ids) {
-                    int r0 = 0, r1 = 0, r2 = 0, r3 = 0;
-                    const bool glane = lane < 4;
-                    if (glane) {
-                        const int64_t base = row0 + my_row;
-                        if (my_row + 0 < P.R && base + 0 < P.n_rows) r0 = (int)__ldg(P.ids + base + 0);
-                        if (my_row + 1 < P.R && base + 1 < P.n_rows) r1 = (int)__ldg(P.ids + base + 1);
-                        if (my_row + 2 < P.R && base + 2 < P.n_rows) r2 = (int)__ldg(P.ids + base + 2);
-                        if (my_row + 3 < P.R && base + 3 < P.n_rows) r3 = (int)__ldg(P.ids + base + 3);
+                    int cur[16], nxt[16];
+                    load_ids(blockIdx.x, cur);
+                    for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x) {
+                        load_ids(tile + (int)gridDim.x, nxt);
+                        const uint32_t row_off = (uint32_t)my_row * 128u;
+                        for (int kc = 0, col = 0; kc < kchunks; ++kc, col += uk) {
+                            QT_LAP(qt_c);
+                            mbar_wait(empty_bar(stage), par, P.err);
+                            QT_LAP(qt_a);
+                            const uint32_t fb = full_bar(stage);
+                            if (lead) mbar_arrive_expect_tx(fb, (uint32_t)kQRChunk);
+#pragma unroll
+                            for (int q = 0; q < 4; ++q)
+                                tma_gather4(sa_u + row_off + (uint32_t)q * 512u, &M.a, col, cur[4 * q], cur[4 * q + 1], cur[4 * q + 2], cur[4 * q + 3], fb);
+                            QT_LAP(qt_b);
+                            if (++stage == kQStages) { stage = 0; par ^= 1; sa_u = ring_u; } else sa_u += kQRChunk;
+                        }
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) cur[i] = nxt[i];
                     }
-                    const uint32_t row_off = (uint32_t)my_row * 128u;
-                    for (int kc = 0, col = 0; kc < kchunks; ++kc, col += uk) {
-                        mbar_wait(empty_bar(stage), par, P.err);
-                        const uint32_t fb = full_bar(stage);
-                        if (lead) mbar_arrive_expect_tx(fb, (uint32_t)kQRChunk);
-                        if (glane) tma_gather4(sa_u + row_off, &M.a, col, r0, r1, r2, r3, fb);
-                        if (++stage == kQStages) { stage = 0; par ^= 1; sa_u = ring_u; } else sa_u += kQRChunk;
-                    }
-                } else {
-                    for (int kc = 0, col = 0; kc < kchunks; ++kc, col += uk) {
-                        if (lead) {
+                } else if (lead) {
+                    for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x) {
+                        const int64_t row0 = (int64_t)tile * P.R;
+                        for (int kc = 0, col = 0; kc < kchunks; ++kc, col += uk) {
                             mbar_wait(empty_bar(stage), par, P.err);
                             mbar_arrive_expect_tx(full_bar(stage), (uint32_t)kQRChunk);
                             tma_load_2d(sa_u, &M.a, col, (int)row0, full_bar(stage));
+                            if (++stage == kQStages) { stage = 0; par ^= 1; sa_u = ring_u; } else sa_u += kQRChunk;
                         }
-                        if (++stage == kQStages) { stage = 0; par ^= 1; sa_u = ring_u; } else sa_u += kQRChunk;
                     }
                 }
             }
+            QT_OUT(8, lead);                                   // wait empty | expect_tx + gather4 issue | loop + id loads issued
         }
+        __syncwarp();
     }
 
     tc_fence_before();
@@ -350,6 +431,13 @@ static int q_launch(const LinearParams& P, const float* dP, int64_t ld_dp, void*
         GS_CUDA(cudaMemset(g_q_err, 0, sizeof(int)));
     }
     U.err = g_q_err;
+#ifdef GSAGE_POOL_TIMING
+    static long long* g_q_dbg = nullptr;
+    if (!g_q_dbg) { GS_CUDA(cudaMalloc((void**)&g_q_dbg, 16 * sizeof(long long))); }
+    GS_CUDA(cudaMemsetAsync(g_q_dbg, 0, 16 * sizeof(long long), s));
+    U.dbg = g_q_dbg;
+    U.dbg_skip = getenv("GSAGE_POOL_DBG_SKIP") ? atoi(getenv("GSAGE_POOL_DBG_SKIP")) : 0;   // 1: the epilogue only waits and arrives
+#endif
     const int es = U.tf32 ? 4 : 2;
     QMaps maps;
     memset(&maps, 0, sizeof(maps));
@@ -378,6 +466,17 @@ static int q_launch(const LinearParams& P, const float* dP, int64_t ld_dp, void*
     else GS_Q_PICK(0);
 #undef GS_Q_PICK
 #undef GS_Q_LAUNCH
+#ifdef GSAGE_POOL_TIMING
+    {
+        long long h[16];
+        GS_CUDA(cudaStreamSynchronize(s));
+        GS_CUDA(cudaMemcpy(h, g_q_dbg, sizeof(h), cudaMemcpyDeviceToHost));
+        const double t = (double)((U.n_tiles + grid - 1) / grid) * U.n_phases;
+        fprintf(stderr, "[pool timing] n_tiles %d (%.0f per CTA) skip %d | per tile, CTA 0:  epilogue warp 0: wait tfull %.0f, tcgen05.ld %.0f, pool+store %.0f, arrive %.0f | "
+                        "MMA thread: wait tempty %.0f, wait rows %.0f, issue %.0f | producer 0: wait empty %.0f, issue gather4 %.0f, ids+loop %.0f\n",
+                U.n_tiles, t, U.dbg_skip, h[0] / t, h[1] / t, h[2] / t, h[3] / t, h[4] / t, h[5] / t, h[6] / t, h[8] / t, h[9] / t, h[10] / t);
+    }
+#endif
     GS_LAUNCHED();
     return GSAGE_OK;
 }

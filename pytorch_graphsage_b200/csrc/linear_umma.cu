@@ -221,8 +221,9 @@ __global__ void __launch_bounds__(kThreads, 1) linear_umma_kernel(const UmmaPara
                     const int stage = item % P.stages;
                     mbar_wait(full_bar(stage), (item / P.stages) & 1, P.err);
                     tc_fence_after();
-                    if (lane == 0 && (P.debug & 4)) umma_commit(empty_bar(stage));
-                    if (lane == 0 && !(P.debug & 4)) {
+                    const bool elected = elect_one();                    // (not lane == 0: umma_ptx.cuh)
+                    if (elected && (P.debug & 4)) umma_commit(empty_bar(stage));
+                    if (elected && !(P.debug & 4)) {
                         const uint32_t a_addr = smem_u32(smem + (size_t)stage * P.stage_bytes);
                         const uint32_t b_addr = a_addr + kABytes;
                         const uint64_t adesc = umma_desc(a_addr), bdesc = umma_desc(b_addr);
@@ -236,7 +237,7 @@ __global__ void __launch_bounds__(kThreads, 1) linear_umma_kernel(const UmmaPara
                     __syncwarp();
                 }
             }
-            if (lane == 0) { umma_commit(tfull_bar(buf)); progress_publish(progress, it + 1); }   // accumulators of this tile complete
+            if (elect_one()) { umma_commit(tfull_bar(buf)); progress_publish(progress, it + 1); }   // accumulators of this tile complete
             __syncwarp();
         }
     } else if (warp == kTmaWarp) {
@@ -272,13 +273,20 @@ __global__ void __launch_bounds__(kThreads, 1) linear_umma_kernel(const UmmaPara
                         const int stage = item % P.stages;
                         mbar_wait(empty_bar(stage), ((item / P.stages) & 1) ^ 1, P.err);
                         const uint32_t sa_u = smem_u32(smem + (size_t)stage * P.stage_bytes);
-                        if (lane == 0) {
+                        const bool elected = elect_one();          // one lane issues everything (not lane == 0 / per-lane gather4: umma_ptx.cuh)
+                        if (elected) {
                             mbar_arrive_expect_tx(full_bar(stage), w_bytes + ((sg.ids && (P.debug & 1)) ? 0u : (uint32_t)kABytes));
                             tma_load_2d(sa_u + kABytes, &M.w[sidx], kc * P.uk, 0, full_bar(stage));
                             if (!sg.ids) tma_load_2d(sa_u, &M.a[sidx], kc * P.uk, tile * P.tile_rows, full_bar(stage));
                         }
-                        __syncwarp();                              // expect_tx is posted before any lane's copy can complete
-                        if (sg.ids && !(P.debug & 1)) tma_gather4(sa_u + lane * 512, &M.g[sidx], kc * P.uk, r0, r1, r2, r3, full_bar(stage));
+                        if (sg.ids && !(P.debug & 1)) {
+                            for (int l = 0; l < 32; ++l) {             // the ids of rows 4l .. 4l+3 live in lane l: hand them to the issuing lane
+                                const int a = __shfl_sync(0xFFFFFFFFu, r0, l), b = __shfl_sync(0xFFFFFFFFu, r1, l);
+                                const int c = __shfl_sync(0xFFFFFFFFu, r2, l), d = __shfl_sync(0xFFFFFFFFu, r3, l);
+                                if (elected) tma_gather4(sa_u + l * 512, &M.g[sidx], kc * P.uk, a, b, c, d, full_bar(stage));
+                            }
+                        }
+                        __syncwarp();
                     }
                 }
             }

@@ -10,6 +10,22 @@ namespace gsage {
 // ---- PTX helpers -----------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+// One lane of a CONVERGED warp (all 32 lanes must reach this together).  Guard single-thread issue loops (tcgen05.mma, TMA,
+// tcgen05.commit) with this instead of `lane == 0`: those instructions take uniform-register operands, and inside an
+// `if (lane == 0)` region ptxas cannot prove that a single lane is active, so it wraps EVERY one of them in an
+// ELECT / R2UR.BROADCAST / BRA.U.ANY loop over the active lanes (~60-160 cycles of dependent issue per instruction, measured:
+// profiles/r02_pool_phase_cycles.txt).  Under elect.sync it emits them back to back.
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred = 0;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "elect.sync _|p, 0xFFFFFFFF;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
 }
