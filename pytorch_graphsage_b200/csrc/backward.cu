@@ -185,10 +185,32 @@ __global__ void __launch_bounds__(256) embedding_scatter_kernel(const float* __r
     for (int c = lane; c < d; c += 32) atomicAdd(dst + c, src[c] * scale);
 }
 
+// the same with 16-byte vector reductions (red.global.add.v4.f32, sm_90+): a quarter of the L2 atomic requests.  A thread owns four
+// columns of one id; LPI = d / 4 threads per id (d = 64: two ids per warp).  Needs d % 4 == 0 and 16-byte aligned rows.
+__global__ void __launch_bounds__(256) embedding_scatter_v4_kernel(const float* __restrict__ rows, int64_t ld, int lpi,
+                                                                   const int64_t* __restrict__ ids, int64_t n_ids, int S, float scale,
+                                                                   float* __restrict__ table_grad, int64_t ld_table, int64_t table_rows) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t i = t / lpi;
+    if (i >= n_ids) return;
+    const int c = (int)(t - i * lpi) * 4;
+    const int64_t id = __ldg(ids + i);
+    if ((uint64_t)id >= (uint64_t)table_rows) return;
+    const float4 v = *reinterpret_cast<const float4*>(rows + (i / S) * ld + c);
+    float* dst = table_grad + id * ld_table + c;
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(v.x * scale), "f"(v.y * scale), "f"(v.z * scale), "f"(v.w * scale) : "memory");
+}
+
 int embedding_scatter_launch(const float* rows, int64_t ld, int d, const int64_t* ids, int64_t n_ids, int S, float scale,
                              float* table_grad, int64_t ld_table, int64_t table_rows, cudaStream_t s) {
     if (n_ids == 0) return GSAGE_OK;
-    embedding_scatter_kernel<<<(unsigned)ceil_div(n_ids, 8), 256, 0, s>>>(rows, ld, d, ids, n_ids, S, scale, table_grad, ld_table, table_rows);
+    const bool vec = d % 4 == 0 && ld % 4 == 0 && ld_table % 4 == 0 && ((uintptr_t)rows & 15) == 0 && ((uintptr_t)table_grad & 15) == 0;
+    if (vec) {
+        const int lpi = d / 4;
+        embedding_scatter_v4_kernel<<<(unsigned)ceil_div(n_ids * lpi, 256), 256, 0, s>>>(rows, ld, lpi, ids, n_ids, S, scale, table_grad, ld_table, table_rows);
+    } else {
+        embedding_scatter_kernel<<<(unsigned)ceil_div(n_ids, 8), 256, 0, s>>>(rows, ld, d, ids, n_ids, S, scale, table_grad, ld_table, table_rows);
+    }
     GS_LAUNCHED();
     return GSAGE_OK;
 }

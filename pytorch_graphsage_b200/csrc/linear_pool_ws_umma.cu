@@ -34,6 +34,8 @@ static constexpr int kQWChunk = QM * 128;         // 16 KB: one hidden block x o
 static constexpr int kQRChunk = QN * 128;         // 8 KB: one k-chunk of a row tile
 static constexpr int kQStages = 8;
 static constexpr int kQSmemLimit = 227 * 1024;
+static constexpr int kQIdBatch = 8;              // tiles per batch of row ids a producer warp stages in shared memory
+static constexpr int kQIdBytes = kQTmaWarps * kQIdBatch * 16 * 4;
 
 struct QParams {
     const void* a; int64_t lda; const int64_t* ids;
@@ -103,6 +105,7 @@ __global__ void __launch_bounds__(kQThreads, 1) linear_pool_ws_umma_kernel(const
     uint8_t* ring = smem + (size_t)P.bpp * P.kchunks * kQWChunk;
     uint64_t* bars = (uint64_t*)(ring + kQStages * kQRChunk);
     uint32_t* tmem_slot = (uint32_t*)(bars + 2 * kQStages + 6);
+    int* ids_s = (int*)(bars + 32);                           // [producer][tile of the batch][16 row ids]
     const uint32_t bar_base = smem_u32(bars);
     auto full_bar = [&](int s) { return bar_base + 8u * s; };
     auto empty_bar = [&](int s) { return bar_base + 8u * (kQStages + s); };
@@ -310,72 +313,88 @@ __global__ void __launch_bounds__(kQThreads, 1) linear_pool_ws_umma_kernel(const
         }
         __syncwarp();
     } else {
-        // ============ TMA PRODUCERS: one elected lane per warp; producer pw owns tile rows 16 pw .. 16 pw + 15 ============
-        // The lane loads its 16 row ids one tile AHEAD (a dependent global load per tile would be exposed latency) and issues
-        // the four gather4 of a k-chunk back to back.
+        // ============ TMA PRODUCERS: producer pw owns tile rows 16 pw .. 16 pw + 15 ============
+        // One elected lane per warp issues (its four gather4 of a k-chunk back to back).  The row ids are the catch: a global
+        // load per tile in that lane's loop is ~2000 cycles of exposed latency per tile (measured: the MMA thread waited
+        // 1060 cycles per tile for rows) -- so the WHOLE warp loads the ids of kQIdBatch tiles at once (4 per lane), one batch
+        // ahead, and parks them in shared memory, where the issuing lane picks up its 16 per tile.
         const int pw = warp - (kQEpiWarps + 1);
-        if (elect_one()) {
-            const bool lead = pw == 0;
-            const uint32_t ring_u = smem_u32(ring);
-            const int uk = P.uk, kchunks = P.kchunks;
-            const int my_row = 16 * pw;
-            uint32_t stage = 0, par = 1, sa_u = ring_u;
-            QT_DECL;
-            auto load_ids = [&](int tile, int* r) {
-                const int64_t base = (int64_t)tile * P.R + my_row;
+        const bool lead = pw == 0;
+        const uint32_t ring_u = smem_u32(ring);
+        const int uk = P.uk, kchunks = P.kchunks;
+        const int my_row = 16 * pw;
+        const uint32_t row_off = (uint32_t)my_row * 128u;
+        int* my_ids = ids_s + pw * (kQIdBatch * 16);
+        uint32_t stage = 0, par = 1, sa_u = ring_u;            // (only the elected lane's copy advances; elect.sync picks the same lane every time)
+        QT_DECL;
+        // lane -> (tile j of the batch, ids 4 i .. 4 i + 3 of my 16): unconditional loads from a clamped address, masked afterwards
+        const int bj = lane >> 2, bi = (lane & 3) * 4;
+        auto load_batch = [&](int k0, int* r) {
+            const int64_t tile = (int64_t)blockIdx.x + (int64_t)(k0 + bj) * gridDim.x;
+            const int64_t base = tile * P.R + my_row + bi;
 #pragma unroll
-                for (int i = 0; i < 16; ++i) {                 // unconditional loads from a clamped address, masked afterwards
-                    const int64_t at = base + i;
-                    const bool ok = tile < P.n_tiles && my_row + i < P.R && at < P.n_rows;
-                    const int v = (int)__ldg(P.ids + (ok ? at : 0));
-                    r[i] = ok ? v : 0;
-                }
-            };
-            for (int ph = 0; ph < P.n_phases; ++ph) {
-                if (lead) {
-                    const int nb = min(P.bpp, P.h_blocks - ph * P.bpp);
-                    mbar_wait(wempty_bar, (ph & 1) ^ 1, P.err);
-                    mbar_arrive_expect_tx(wfull_bar, (uint32_t)(nb * kchunks * kQWChunk));
-                    for (int j = 0; j < nb; ++j)
-                        for (int kc = 0; kc < kchunks; ++kc)
-                            tma_load_2d(smem_u32(smem) + (uint32_t)(j * kchunks + kc) * kQWChunk, &M.w, kc * uk, (ph * P.bpp + j) * QM, wfull_bar);
-                }
-                if (P.ids) {
-                    int cur[16], nxt[16];
-                    load_ids(blockIdx.x, cur);
-                    for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x) {
-                        load_ids(tile + (int)gridDim.x, nxt);
-                        const uint32_t row_off = (uint32_t)my_row * 128u;
-                        for (int kc = 0, col = 0; kc < kchunks; ++kc, col += uk) {
-                            QT_LAP(qt_c);
-                            mbar_wait(empty_bar(stage), par, P.err);
-                            QT_LAP(qt_a);
-                            const uint32_t fb = full_bar(stage);
-                            if (lead) mbar_arrive_expect_tx(fb, (uint32_t)kQRChunk);
+            for (int i = 0; i < 4; ++i) {
+                const bool ok = tile < P.n_tiles && my_row + bi + i < P.R && base + i < P.n_rows;
+                const int v = (int)__ldg(P.ids + (ok ? base + i : 0));
+                r[i] = ok ? v : 0;
+            }
+        };
+        for (int ph = 0; ph < P.n_phases; ++ph) {
+            if (lead && elect_one()) {
+                const int nb = min(P.bpp, P.h_blocks - ph * P.bpp);
+                mbar_wait(wempty_bar, (ph & 1) ^ 1, P.err);
+                mbar_arrive_expect_tx(wfull_bar, (uint32_t)(nb * kchunks * kQWChunk));
+                for (int j = 0; j < nb; ++j)
+                    for (int kc = 0; kc < kchunks; ++kc)
+                        tma_load_2d(smem_u32(smem) + (uint32_t)(j * kchunks + kc) * kQWChunk, &M.w, kc * uk, (ph * P.bpp + j) * QM, wfull_bar);
+            }
+            __syncwarp();
+            if (P.ids) {
+                int regs[4];
+                load_batch(0, regs);
+                for (int k0 = 0; (int64_t)blockIdx.x + (int64_t)k0 * gridDim.x < P.n_tiles; k0 += kQIdBatch) {
+                    *reinterpret_cast<int4*>(my_ids + bj * 16 + bi) = make_int4(regs[0], regs[1], regs[2], regs[3]);
+                    __syncwarp();
+                    load_batch(k0 + kQIdBatch, regs);
+                    if (elect_one()) {
+                        for (int j = 0; j < kQIdBatch; ++j) {
+                            if ((int64_t)blockIdx.x + (int64_t)(k0 + j) * gridDim.x >= P.n_tiles) break;
+                            int cur[16];
 #pragma unroll
-                            for (int q = 0; q < 4; ++q)
-                                tma_gather4(sa_u + row_off + (uint32_t)q * 512u, &M.a, col, cur[4 * q], cur[4 * q + 1], cur[4 * q + 2], cur[4 * q + 3], fb);
-                            QT_LAP(qt_b);
-                            if (++stage == kQStages) { stage = 0; par ^= 1; sa_u = ring_u; } else sa_u += kQRChunk;
+                            for (int q = 0; q < 4; ++q) {
+                                const int4 v = *reinterpret_cast<const int4*>(my_ids + j * 16 + 4 * q);
+                                cur[4 * q] = v.x; cur[4 * q + 1] = v.y; cur[4 * q + 2] = v.z; cur[4 * q + 3] = v.w;
+                            }
+                            for (int kc = 0, col = 0; kc < kchunks; ++kc, col += uk) {
+                                QT_LAP(qt_c);
+                                mbar_wait(empty_bar(stage), par, P.err);
+                                QT_LAP(qt_a);
+                                const uint32_t fb = full_bar(stage);
+                                if (lead) mbar_arrive_expect_tx(fb, (uint32_t)kQRChunk);
+#pragma unroll
+                                for (int q = 0; q < 4; ++q)
+                                    tma_gather4(sa_u + row_off + (uint32_t)q * 512u, &M.a, col, cur[4 * q], cur[4 * q + 1], cur[4 * q + 2], cur[4 * q + 3], fb);
+                                QT_LAP(qt_b);
+                                if (++stage == kQStages) { stage = 0; par ^= 1; sa_u = ring_u; } else sa_u += kQRChunk;
+                            }
                         }
-#pragma unroll
-                        for (int i = 0; i < 16; ++i) cur[i] = nxt[i];
                     }
-                } else if (lead) {
-                    for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x) {
-                        const int64_t row0 = (int64_t)tile * P.R;
-                        for (int kc = 0, col = 0; kc < kchunks; ++kc, col += uk) {
-                            mbar_wait(empty_bar(stage), par, P.err);
-                            mbar_arrive_expect_tx(full_bar(stage), (uint32_t)kQRChunk);
-                            tma_load_2d(sa_u, &M.a, col, (int)row0, full_bar(stage));
-                            if (++stage == kQStages) { stage = 0; par ^= 1; sa_u = ring_u; } else sa_u += kQRChunk;
-                        }
+                    __syncwarp();
+                }
+            } else if (lead && elect_one()) {
+                for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x) {
+                    const int64_t row0 = (int64_t)tile * P.R;
+                    for (int kc = 0, col = 0; kc < kchunks; ++kc, col += uk) {
+                        mbar_wait(empty_bar(stage), par, P.err);
+                        mbar_arrive_expect_tx(full_bar(stage), (uint32_t)kQRChunk);
+                        tma_load_2d(sa_u, &M.a, col, (int)row0, full_bar(stage));
+                        if (++stage == kQStages) { stage = 0; par ^= 1; sa_u = ring_u; } else sa_u += kQRChunk;
                     }
                 }
             }
-            QT_OUT(8, lead);                                   // wait empty | expect_tx + gather4 issue | loop + id loads issued
+            __syncwarp();
         }
-        __syncwarp();
+        QT_OUT(8, lead && lane == 0);                          // wait empty | expect_tx + gather4 issue | loop + ids from smem
     }
 
     tc_fence_before();
@@ -390,7 +409,7 @@ static int q_blocks_per_phase(const LinearParams& P) {
     const LinearSeg& s = P.seg[0];
     const int es = s.a_dtype == GSAGE_BF16 ? 2 : 4, uk = 128 / es;
     const int kchunks = (s.d + uk - 1) / uk;
-    const int budget = kQSmemLimit - 2048 - kQStages * kQRChunk;
+    const int budget = kQSmemLimit - 2048 - kQIdBytes - kQStages * kQRChunk;
     int bpp = budget / (kchunks * kQWChunk);
     const int h_blocks = (s.O + QM - 1) / QM;
     if (bpp > kQMaxBlocks) bpp = kQMaxBlocks;
@@ -444,7 +463,7 @@ static int q_launch(const LinearParams& P, const float* dP, int64_t ld_dp, void*
     GS_TRY(make_map(&maps.w, g.w, g.O, g.d, g.ldw, QM, es));
     if (g.ids) GS_TRY(make_map(&maps.a, g.a, g.a_rows > 0 ? g.a_rows : 0x7FFFFFFF, g.d, g.lda, 1, es));
     else GS_TRY(make_map(&maps.a, g.a, P.n, g.d, g.lda, QN, es));
-    const size_t smem = (size_t)U.bpp * U.kchunks * kQWChunk + (size_t)kQStages * kQRChunk + 1024 + 512;
+    const size_t smem = (size_t)U.bpp * U.kchunks * kQWChunk + (size_t)kQStages * kQRChunk + 1024 + 512 + kQIdBytes;
     const int grid = U.n_tiles < sm_count() ? U.n_tiles : sm_count();
 #define GS_Q_LAUNCH(MX, SCT, BW)                                                                                                   \
     do {                                                                                                                           \

@@ -306,6 +306,23 @@ __global__ void __launch_bounds__(kWsThreads, 1) linear_ws_umma_kernel(const WsP
                             tma_load_2d(w_base + (uint32_t)(sg.kres + kc) * (uint32_t)sg.O * 128u, &M.wl[s_first + si], kc * uk, 0, wfull_bar);
                 }
             }
+            // the row ids of a gathered (tile, segment) are loaded one item AHEAD: a dependent global load at the top of every
+            // item is ~1-2 us of latency the ring has to hide (measured in the pool kernel: profiles/r02_pool_phase_cycles.txt)
+            constexpr int kRowsPerProducer = WM / kWsTmaWarps, kGatherLanes = kRowsPerProducer / 4;
+            const int my_row = kRowsPerProducer * pw + 4 * lane;
+            int n0 = 0, n1 = 0, n2 = 0, n3 = 0;
+            auto load_ids = [&](int tile, int sidx) {             // unconditional loads from a clamped address, masked afterwards
+                const int64_t* ids = tile < P.n_tiles ? P.seg[sidx].ids : nullptr;
+                n0 = n1 = n2 = n3 = 0;
+                if (ids && lane < kGatherLanes) {
+                    const int64_t base = (int64_t)tile * WM + my_row, last = P.n - 1;
+                    const int v0 = (int)__ldg(ids + min(base + 0, last)), v1 = (int)__ldg(ids + min(base + 1, last));
+                    const int v2 = (int)__ldg(ids + min(base + 2, last)), v3 = (int)__ldg(ids + min(base + 3, last));
+                    n0 = base + 0 <= last ? v0 : 0; n1 = base + 1 <= last ? v1 : 0;
+                    n2 = base + 2 <= last ? v2 : 0; n3 = base + 3 <= last ? v3 : 0;
+                }
+            };
+            load_ids(blockIdx.x, s_first);
             for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x) {
                 for (int si = 0; si < s_count; ++si) {
                     const int sidx = s_first + si;
@@ -316,18 +333,10 @@ __global__ void __launch_bounds__(kWsThreads, 1) linear_ws_umma_kernel(const WsP
                     const CUtensorMap* map_a = ids ? &M.g[sidx] : &M.a[sidx];
                     const CUtensorMap* map_w = &M.w[sidx];
                     const int tile_row = tile * WM;
+                    const int r0 = n0, r1 = n1, r2 = n2, r3 = n3;
+                    if (si + 1 < s_count) load_ids(tile, sidx + 1); else load_ids(tile + (int)gridDim.x, s_first);
                     if (ids) {
                         // ---- gathered operand: the first lanes of producer pw own tile rows kRowsPerProducer pw + 4 lane .. + 3 ----
-                        constexpr int kRowsPerProducer = WM / kWsTmaWarps, kGatherLanes = kRowsPerProducer / 4;
-                        int r0 = 0, r1 = 0, r2 = 0, r3 = 0;
-                        const int my_row = kRowsPerProducer * pw + 4 * lane;
-                        if (lane < kGatherLanes) {
-                            const int64_t base = (int64_t)tile_row + my_row;
-                            if (base + 0 < P.n) r0 = (int)__ldg(ids + base + 0);
-                            if (base + 1 < P.n) r1 = (int)__ldg(ids + base + 1);
-                            if (base + 2 < P.n) r2 = (int)__ldg(ids + base + 2);
-                            if (base + 3 < P.n) r3 = (int)__ldg(ids + base + 3);
-                        }
                         const uint32_t row_off = (uint32_t)my_row * 128u;
                         for (int kc = 0, col = 0; kc < kchunks; ++kc, col += uk) {
                             mbar_wait(empty_bar(stage), par, P.err);

@@ -262,8 +262,8 @@ def attention_aggregate(table, ids, n_parents, S, w1, w2, xa, b1=None, out_dtype
     _bind_device(table)
     d = table.shape[1]
     out_dtype = out_dtype or table.dtype
-    store, _ = pad_table(torch.zeros((n_parents, d), dtype=torch.float32), out_dtype)
-    out = store[:, :d]
+    per = 32 // (2 if out_dtype == torch.bfloat16 else 4)          # rows of whole 32-byte sectors, zero padding (as pad_table lays them out)
+    out = torch.zeros((n_parents, (d + per - 1) // per * per), dtype=out_dtype, device=table.device)[:, :d]
     check(lib().gsage_attention_aggregate(ptr(table), dt(table), _rows2d(table), table.shape[0], d, _ids_arg(ids), n_parents, S, ptr(w1), dt(w1), _rows2d(w1),
                                           w1.shape[0], ptr(b1), ptr(w2), ptr(xa), ptr(out), dt(out), _rows2d(out), stream()))
     return out
