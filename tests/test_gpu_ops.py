@@ -336,6 +336,252 @@ def test_umma_pooled_epilogue(g, n, S, d, H, reduce):
     np.testing.assert_allclose(got.float().cpu().numpy(), want.numpy(), rtol=1e-2, atol=1e-2)
 
 
+@pytest.mark.parametrize('n,S,d,H,dtype', [(40003, 10, 64, 512, 'bf16'), (20011, 25, 64, 384, 'bf16'), (30001, 10, 128, 200, 'bf16'),
+                                           (25000, 10, 64, 512, 'f32')])
+def test_pool_kernel_many_tiles_per_cta(g, n, S, d, H, dtype):
+    """linear_pool_ws_umma.cu over many tiles per CTA (ring wrap-around, accumulator-buffer parities, several staged id batches, a
+    ragged last tile, an id outside the table), rows by id and rows in place; against fp64 on the same operands."""
+    gen = torch.Generator().manual_seed(n + S + d)
+    rows = 50000
+    tdt = torch.bfloat16 if dtype == 'bf16' else torch.float32
+    rnd = (lambda t: _bf16(t)) if dtype == 'bf16' else (lambda t: t)
+    table = rnd(torch.randn((rows, d), generator=gen))
+    w, b = rnd(torch.randn((H, d), generator=gen) / d ** 0.5), torch.randn((H,), generator=gen)
+    ids = torch.randint(0, rows, (n * S,), generator=gen)
+    ids[5] = rows + 7                                          # outside the table: reads as a zero row
+    pad = lambda t: g.ops.pad_table(t.float(), tdt)[0][:, :t.shape[1]]
+    rows_d = table[ids.clamp(max=rows - 1)].double()
+    rows_d[5] = 0
+    tol = 2e-4 if dtype == 'bf16' else 5e-3                    # fp32 operands run as TF32 products here
+    for reduce in ('max', 'mean'):
+        h = torch.relu(rows_d @ w.double().t() + b.double()).view(n, S, H)
+        want = h.max(dim=1)[0] if reduce == 'max' else h.mean(dim=1)
+        got = g.ops.linear_pooled(pad(table), pad(w), n, S, reduce, ids=ids.cuda(), bias=b.cuda())
+        np.testing.assert_allclose(got.cpu().numpy(), want.numpy(), rtol=tol, atol=tol)
+    nb = rnd(torch.randn((n * S, d), generator=gen))
+    h = torch.relu(nb.double() @ w.double().t() + b.double()).view(n, S, H)
+    got = g.ops.linear_pooled(pad(nb), pad(w), n, S, 'max', bias=b.cuda())
+    np.testing.assert_allclose(got.cpu().numpy(), h.max(dim=1)[0].numpy(), rtol=tol, atol=tol)
+
+
+@pytest.mark.parametrize('n,d,O', [(777, 602, 128), (128 * 150 + 3, 64, 64), (50, 256, 128)])
+def test_umma_concat_with_self(g, n, d, O):
+    """[fc_x(table[ids]) | fc_neib(m)] + relu in one tensor-core launch (two TMEM accumulators per tile)."""
+    gen = torch.Generator().manual_seed(n)
+    table = _bf16(torch.randn((n + 99, d), generator=gen))
+    m = _bf16(torch.randn((n, d), generator=gen))
+    wx, wn = _bf16(torch.randn((O, d), generator=gen) / d ** 0.5), _bf16(torch.randn((O, d), generator=gen) / d ** 0.5)
+    ids = torch.randint(0, n + 99, (n,), generator=gen)
+    pad = lambda t: g.ops.pad_table(t.float(), torch.bfloat16)[0][:, :t.shape[1]]
+    want = torch.relu(torch.cat([table[ids].double() @ wx.double().t(), m.double() @ wn.double().t()], dim=1))
+    got = g.ops.linear([dict(a=pad(table), ids=ids.cuda(), w=pad(wx), col0=0), dict(a=pad(m), w=pad(wn), col0=O)], n,
+                       act='relu', out_dtype=torch.float32, exact=False)
+    assert got.shape == (n, 2 * O)
+    np.testing.assert_allclose(got.cpu().numpy(), want.numpy(), rtol=2e-4, atol=2e-4)
+
+
+def test_umma_wide_output_is_split(g):
+    """O = 512 (the pool MLP) does not fit one 256-column accumulator: the dispatcher issues column blocks."""
+    n, d, O = 1500, 64, 512
+    gen = torch.Generator().manual_seed(3)
+    a, w, b = _bf16(torch.randn((n, d), generator=gen)), _bf16(torch.randn((O, d), generator=gen) / 8), torch.randn((O,), generator=gen)
+    pad = lambda t: g.ops.pad_table(t.float(), torch.bfloat16)[0][:, :t.shape[1]]
+    want = torch.relu(a.double() @ w.double().t() + b.double())
+    got = g.ops.linear([dict(a=pad(a), w=pad(w), bias=b.cuda())], n, act='relu', exact=False)
+    np.testing.assert_allclose(got.cpu().numpy(), want.numpy(), rtol=2e-4, atol=2e-4)
+
+
+@pytest.mark.parametrize('n,d,O,S', [(300, 602, 128, 10), (129, 64, 64, 25), (1000, 256, 128, 3), (50, 100, 16, 40)])
+def test_fused_gather_mean_projection(g, n, d, O, S):
+    """[fc_x(table[ids]) | fc_neib(mean_j table[nb_ids])]: the gather+mean happens inside the projection kernel's
+    operand load (tcgen05 path, bf16) -- compared with fp64 on the same bf16 operands, and with the fp32 FFMA path."""
+    gen = torch.Generator().manual_seed(n + S)
+    rows = 2000
+    table = _bf16(torch.randn((rows, d), generator=gen))
+    wx, wn = _bf16(torch.randn((O, d), generator=gen) / d ** 0.5), _bf16(torch.randn((O, d), generator=gen) / d ** 0.5)
+    ids = torch.randint(0, rows, (n,), generator=gen)
+    nb = torch.randint(0, rows, (n * S,), generator=gen)
+    pad = lambda t: g.ops.pad_table(t.float(), torch.bfloat16)[0][:, :t.shape[1]]
+    mean = table[nb].float().view(n, S, d).sum(dim=1) * (1.0 / S)               # fp32 sum in j order, like the kernel
+    mean_bf16 = mean.to(torch.bfloat16)                                         # the kernel rounds the mean to bf16 in smem
+    want = torch.relu(torch.cat([table[ids].double() @ wx.double().t(), mean_bf16.double() @ wn.double().t()], dim=1))
+    segs = [dict(a=pad(table), ids=ids.cuda(), w=pad(wx), col0=0), dict(a=pad(table), ids=nb.cuda(), w=pad(wn), col0=O, S=S)]
+    got = g.ops.linear(segs, n, act='relu', out_dtype=torch.float32, exact=False)
+    # bf16 rounding of the mean can flip by one ulp vs the torch emulation (summation order): 2^-8 relative on that operand
+    np.testing.assert_allclose(got.cpu().numpy(), want.numpy(), rtol=2e-3, atol=2e-3)
+    exact = torch.relu(torch.cat([table[ids].double() @ wx.double().t(),
+                                  table[nb].double().view(n, S, d).mean(dim=1) @ wn.double().t()], dim=1))
+    got32 = g.ops.linear(segs, n, act='relu', out_dtype=torch.float32, exact=True)   # FFMA path: mean kept in fp32
+    np.testing.assert_allclose(got32.cpu().numpy(), exact.numpy(), rtol=1e-4, atol=1e-5)
+
+
+def test_fused_contiguous_mean_projection(g):
+    """ids=None, S>1: the layer-2 case -- neighbours are rows r*S+j of the previous layer's output."""
+    n, d, O, S = 200, 256, 128, 25
+    gen = torch.Generator().manual_seed(8)
+    h = _bf16(torch.randn((n + n * S, d), generator=gen))
+    wx, wn = _bf16(torch.randn((O, d), generator=gen) / 16), _bf16(torch.randn((O, d), generator=gen) / 16)
+    pad = lambda t: g.ops.pad_table(t.float(), torch.bfloat16)[0][:, :t.shape[1]]
+    hd = pad(h)
+    mean = (h[n:].float().view(n, S, d).sum(dim=1) * (1.0 / S)).to(torch.bfloat16)
+    want = torch.cat([h[:n].double() @ wx.double().t(), mean.double() @ wn.double().t()], dim=1)
+    got = g.ops.linear([dict(a=hd[:n], w=pad(wx), col0=0), dict(a=hd[n:], w=pad(wn), col0=O, S=S)], n, exact=False)
+    np.testing.assert_allclose(got.cpu().numpy(), want.numpy(), rtol=2e-3, atol=2e-3)
+
+
+@pytest.mark.parametrize('n,d,O', [(300, 64, 128), (1000, 256, 64), (129, 100, 16)])
+def test_umma_tf32_projection(g, n, d, O):
+    """fp32 operands on the tensor cores as TF32 (exact=False): products carry a 10-bit mantissa, fp32 accumulate.
+    Stated tolerance: 2e-3 * sqrt(d) absolute on unit-variance operands (measured errors are ~10x smaller)."""
+    gen = torch.Generator().manual_seed(d)
+    table = torch.randn((n + 77, d), generator=gen)
+    m = torch.randn((n, d), generator=gen)
+    wx, wn = torch.randn((O, d), generator=gen) / d ** 0.5, torch.randn((O, d), generator=gen) / d ** 0.5
+    ids = torch.randint(0, n + 77, (n,), generator=gen)
+    pad = lambda t: g.ops.pad_table(t, torch.float32)[0][:, :t.shape[1]]
+    segs = [dict(a=pad(table), ids=ids.cuda(), w=pad(wx), col0=0), dict(a=pad(m), w=pad(wn), col0=O)]
+    want = torch.relu(torch.cat([table[ids].double() @ wx.double().t(), m.double() @ wn.double().t()], dim=1))
+    got = g.ops.linear(segs, n, act='relu', out_dtype=torch.float32, exact=False)
+    err = (got.cpu().double() - want).abs().max().item()
+    assert err < 2e-3 * d ** 0.5, err
+    assert err > 0 or d < 8                       # it really ran in reduced precision (the FFMA path would be ~1e-6)
+    exact = g.ops.linear(segs, n, act='relu', out_dtype=torch.float32, exact=True)
+    np.testing.assert_allclose(exact.cpu().numpy(), want.numpy(), rtol=1e-4, atol=1e-5)
+
+
+@pytest.mark.parametrize('n,H,h_dtype', [(1, 8, torch.float32), (37, 64, torch.float32), (1000, 512, torch.float32), (129, 64, torch.bfloat16)])
+def test_lstm_cell_equals_torch(g, n, H, h_dtype):
+    """gsage_lstm_cell against torch.nn.LSTMCell's arithmetic (gate order i, f, g, o), three chained steps from the zero state."""
+    gen = torch.Generator().manual_seed(n + H)
+    b_ih, b_hh = torch.randn((4 * H,), generator=gen), torch.randn((4 * H,), generator=gen)
+    c_ref, h_ref = torch.zeros((n, H), dtype=torch.float64), torch.zeros((n, H), dtype=torch.float64)
+    c = torch.full((n, H), 7.0, device='cuda')                          # garbage: the first step must not read it
+    h = torch.full((n, H), 7.0, device='cuda').to(h_dtype)
+    for t in range(3):
+        gx, gh = torch.randn((n, 4 * H), generator=gen), torch.randn((n, 4 * H), generator=gen)
+        gates = gx.double() + b_ih.double() + b_hh.double() + (gh.double() if t > 0 else 0.0)
+        i, f, gg, o = gates[:, :H], gates[:, H:2 * H], gates[:, 2 * H:3 * H], gates[:, 3 * H:]
+        c_ref = torch.sigmoid(f) * c_ref + torch.sigmoid(i) * torch.tanh(gg)
+        h_ref = torch.sigmoid(o) * torch.tanh(c_ref)
+        g.ops.lstm_cell(gx.cuda(), gh.cuda() if t > 0 else None, b_ih.cuda(), b_hh.cuda(), c, h, first=(t == 0))
+        np.testing.assert_allclose(c.cpu().numpy(), c_ref.numpy(), rtol=1e-5, atol=1e-6)
+        tol = dict(rtol=1e-5, atol=1e-6) if h_dtype == torch.float32 else dict(rtol=1e-2, atol=1e-2)
+        np.testing.assert_allclose(h.float().cpu().numpy(), h_ref.numpy(), **tol)
+
+
+@pytest.mark.parametrize('n,S,d,H,gather', [(40, 10, 20, 64, True), (33, 25, 64, 32, False), (5, 3, 7, 8, True)])
+def test_lstm_aggregator_equals_torch_lstm(g, n, S, d, H, gather):
+    """operators.LSTMAggregator (narrow and id-taking entries) against the stock nn.LSTM it holds its parameters in
+    (nn_modules.py:276-279: batch_first, last hidden state)."""
+    torch.manual_seed(n + S)
+    agg = g.aggregator_lookup['lstm'](input_dim=d, output_dim=16, activation=F.relu, hidden_dim=H)
+    table = torch.randn((n * S + 50, d))
+    x = torch.randn((n, d))
+    with torch.no_grad():
+        if gather:
+            ids_self = torch.randint(0, table.shape[0], (n,))
+            ids_nb = torch.randint(0, table.shape[0], (n * S,))
+            xs, nb = table[ids_self], table[ids_nb]
+        else:
+            xs, nb = x, table[:n * S]
+        seq, _ = agg.lstm(nb.view(n, S, d))
+        want = F.relu(torch.cat([agg.fc_x(xs), agg.fc_neib(seq[:, -1])], dim=1))
+    agg = agg.cuda()
+    if gather:
+        got = agg.forward_ids(table.cuda(), ids_self.cuda(), ids_nb.cuda(), S)
+    else:
+        got = agg(xs.cuda(), nb.cuda())
+    np.testing.assert_allclose(got.detach().cpu().numpy(), want.numpy(), rtol=1e-4, atol=1e-5)
+
+
+@pytest.mark.parametrize('n,d,O', [(300, 64, 128), (128 * 200 + 5, 64, 128), (1000, 100, 64), (129, 256, 32), (777, 64, 16)])
+def test_three_tf32_projection_has_fp32_accuracy(g, n, d, O, monkeypatch):
+    """exact='x3': fp32 operands on the tensor cores as 3 x TF32 (a = a_hi + a_lo, w = w_hi + w_lo, three products, fp32
+    accumulate).  Same bar as the FFMA kernel (rtol 1e-4 / atol 1e-5 against float64), and it must be a different kernel
+    than both the FFMA one (GSAGE_FP32_FFMA=1) and the single-pass TF32 one (whose error is ~100x larger)."""
+    gen = torch.Generator().manual_seed(n + d)
+    table = torch.randn((n + 77, d), generator=gen)
+    m = torch.randn((n, d), generator=gen)
+    wx, wn = torch.randn((O, d), generator=gen) / d ** 0.5, torch.randn((O, d), generator=gen) / d ** 0.5
+    bias = torch.randn((O,), generator=gen)
+    ids = torch.randint(0, n + 77, (n,), generator=gen)
+    pad = lambda t: g.ops.pad_table(t, torch.float32)[0][:, :t.shape[1]]
+    segs = [dict(a=pad(table), ids=ids.cuda(), w=pad(wx), col0=0, bias=bias.cuda()), dict(a=pad(m), w=pad(wn), col0=O)]
+    want = torch.relu(torch.cat([table[ids].double() @ wx.double().t() + bias.double(), m.double() @ wn.double().t()], dim=1))
+    got = g.ops.linear(segs, n, act='relu', out_dtype=torch.float32, exact='x3').cpu()
+    np.testing.assert_allclose(got.numpy(), want.numpy(), rtol=1e-4, atol=1e-5)
+    err_x3 = (got.double() - want).abs().max().item()
+    tf32 = g.ops.linear(segs, n, act='relu', out_dtype=torch.float32, exact=False).cpu()
+    err_tf32 = (tf32.double() - want).abs().max().item()
+    assert err_x3 < err_tf32 / 20, (err_x3, err_tf32)
+    assert err_x3 < 4e-6 * d ** 0.5, err_x3
+    monkeypatch.setenv('GSAGE_FP32_FFMA', '1')
+    ffma = g.ops.linear(segs, n, act='relu', out_dtype=torch.float32, exact='x3').cpu()
+    np.testing.assert_allclose(ffma.numpy(), want.numpy(), rtol=1e-4, atol=1e-5)
+    assert not torch.equal(ffma, got)              # different summation order: the tensor-core path really ran
+
+
+@pytest.mark.parametrize('n,S,d,H', [(100, 10, 64, 512), (37, 25, 64, 512), (513, 3, 100, 32), (8, 128, 64, 48), (3000, 10, 256, 512),
+                                     (257, 25, 256, 512), (1000, 10, 602, 512), (50, 64, 64, 200), (64, 2, 72, 136)])
+@pytest.mark.parametrize('reduce', ['max', 'mean'])
+def test_umma_pooled_epilogue(g, n, S, d, H, reduce):
+    """relu(MLP) on tcgen05 with the max / mean over the S neighbour rows of each parent done in the epilogue."""
+    gen = torch.Generator().manual_seed(n * S + d)
+    rows = 3000
+    table = _bf16(torch.randn((rows, d), generator=gen))
+    w, b = _bf16(torch.randn((H, d), generator=gen) / d ** 0.5), torch.randn((H,), generator=gen)
+    ids = torch.randint(0, rows, (n * S,), generator=gen)
+    pad = lambda t: g.ops.pad_table(t.float(), torch.bfloat16)[0][:, :t.shape[1]]
+    h = torch.relu(table[ids].double() @ w.double().t() + b.double()).view(n, S, H)
+    want = h.max(dim=1)[0] if reduce == 'max' else h.mean(dim=1)
+    got = g.ops.linear_pooled(pad(table), pad(w), n, S, reduce, ids=ids.cuda(), bias=b.cuda())
+    np.testing.assert_allclose(got.cpu().numpy(), want.numpy(), rtol=2e-4, atol=2e-4)
+    # contiguous neighbours (ids=None): rows p*S+j of the operand itself
+    nb = _bf16(torch.randn((n * S, d), generator=gen))
+    h = torch.relu(nb.double() @ w.double().t() + b.double()).view(n, S, H)
+    want = h.max(dim=1)[0] if reduce == 'max' else h.mean(dim=1)
+    got = g.ops.linear_pooled(pad(nb), pad(w), n, S, reduce, bias=b.cuda(), out_dtype=torch.bfloat16)
+    np.testing.assert_allclose(got.float().cpu().numpy(), want.numpy(), rtol=1e-2, atol=1e-2)
+
+
+@pytest.mark.parametrize('n,S,d,H,dtype', [(40003, 10, 64, 512, 'bf16'), (20011, 25, 64, 384, 'bf16'), (30001, 10, 128, 200, 'bf16'),
+                                           (25000, 10, 64, 512, 'f32')])
+@pytest.mark.parametrize('fill', ['lsu', 'tma'])
+def test_pool_kernel_128_column_tiles(g, n, S, d, H, dtype, fill, monkeypatch):
+    """linear_pool_n128_umma.cu over many tiles per CTA (ring wrap-around, accumulator-slot parities, several id batches, a ragged
+    last tile), rows by id through either fill path and rows in place; against fp64 on the same operands, and bit-for-bit against
+    the 64-column kernel (same MMAs in the same k order)."""
+    monkeypatch.setenv('GSAGE_POOL_FILL', fill)
+    gen = torch.Generator().manual_seed(n + S + d)
+    rows = 50000
+    tdt = torch.bfloat16 if dtype == 'bf16' else torch.float32
+    rnd = (lambda t: _bf16(t)) if dtype == 'bf16' else (lambda t: t)
+    table = rnd(torch.randn((rows, d), generator=gen))
+    w, b = rnd(torch.randn((H, d), generator=gen) / d ** 0.5), torch.randn((H,), generator=gen)
+    ids = torch.randint(0, rows, (n * S,), generator=gen)
+    ids[5] = rows + 7                                          # outside the table: reads as a zero row
+    pad = lambda t: g.ops.pad_table(t.float(), tdt)[0][:, :t.shape[1]]
+    rows_d = table[ids.clamp(max=rows - 1)].double()
+    rows_d[5] = 0
+    tol = 2e-4 if dtype == 'bf16' else 5e-3                    # fp32 operands run as TF32 products here
+    for reduce in ('max', 'mean'):
+        h = torch.relu(rows_d @ w.double().t() + b.double()).view(n, S, H)
+        want = h.max(dim=1)[0] if reduce == 'max' else h.mean(dim=1)
+        got = g.ops.linear_pooled(pad(table), pad(w), n, S, reduce, ids=ids.cuda(), bias=b.cuda())
+        np.testing.assert_allclose(got.cpu().numpy(), want.numpy(), rtol=tol, atol=tol)
+        monkeypatch.setenv('GSAGE_NO_POOL_N128', '1')
+        ref = g.ops.linear_pooled(pad(table), pad(w), n, S, reduce, ids=ids.cuda(), bias=b.cuda())
+        monkeypatch.delenv('GSAGE_NO_POOL_N128')
+        if reduce == 'max':
+            assert torch.equal(got, ref)                       # (the mean sums the S rows in the same order too, but fma contraction may differ)
+        else:
+            np.testing.assert_allclose(got.cpu().numpy(), ref.cpu().numpy(), rtol=1e-6, atol=1e-6)
+    nb = rnd(torch.randn((n * S, d), generator=gen))
+    h = torch.relu(nb.double() @ w.double().t() + b.double()).view(n, S, H)
+    got = g.ops.linear_pooled(pad(nb), pad(w), n, S, 'max', bias=b.cuda())
+    np.testing.assert_allclose(got.cpu().numpy(), h.max(dim=1)[0].numpy(), rtol=tol, atol=tol)
+
+
 @pytest.mark.parametrize('n,d,O', [(777, 602, 128), (128 * 150 + 3, 64, 64), (50, 256, 128), (128 * 300 + 1, 602, 128), (3000, 256, 256)])
 def test_weight_stationary_kernel_equals_streaming_kernel(g, n, d, O, monkeypatch):
     """linear_ws_umma.cu (W of a phase resident in shared memory; d=602 runs as two phases, one segment each) against
