@@ -26,7 +26,8 @@
 namespace gsage {
 
 static constexpr int WM = 128;                 // rows per tile (UMMA M)
-static constexpr int kWsEpiWarps = 4;
+static constexpr int kWsEpiWarps = 8;             // two per TMEM lane quarter: they take the 32-column chunks of a tile in turn (with four,
+                                                  // the epilogue -- ~3000 cycles per tile -- outlasted the MMAs of every shape with d <= 256)
 static constexpr int kWsTmaWarps = 8;             // producers: a lone warp issuing 32 gather4 per stage is the bottleneck (see below)
 static constexpr int kWsSplitWarps = 4;           // 3 x TF32 mode only: turn every landed fp32 A chunk into its (hi, lo) pair
 static constexpr int kWsThreads = 32 * (kWsEpiWarps + 1 + kWsTmaWarps + kWsSplitWarps);
@@ -130,7 +131,8 @@ __global__ void __launch_bounds__(kWsThreads, 1) linear_ws_umma_kernel(const WsP
 
     if (warp < kWsEpiWarps) {
         // =========================== EPILOGUE ===========================
-        const int row_in_tile = warp * 32 + lane;            // TMEM lane == tile row
+        const int quarter = warp & 3, turn = warp >> 2;      // TMEM lane quarter; which of every two 32-column chunks is mine
+        const int row_in_tile = quarter * 32 + lane;         // TMEM lane == tile row
         int it = 0;
         for (int ph = 0; ph < P.n_phases; ++ph) {
             for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x, ++it) {
@@ -138,11 +140,13 @@ __global__ void __launch_bounds__(kWsThreads, 1) linear_ws_umma_kernel(const WsP
                 mbar_wait(tfull_bar(buf), (it >> 1) & 1, P.err);
                 tc_fence_after();
                 const int64_t row = (int64_t)tile * WM + row_in_tile;
+                int chunk = 0;
                 for (int si = 0; si < P.phase_count[ph]; ++si) {
                     const WsSeg& sg = P.seg[P.phase_first[ph] + si];
-                    for (int c0 = 0; c0 < sg.O; c0 += 32) {
+                    for (int c0 = 0; c0 < sg.O; c0 += 32, ++chunk) {
+                        if ((chunk & 1) != turn) continue;
                         uint32_t r[32];
-                        tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(buf * 256 + sg.acc_col + c0), r);
+                        tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * 256 + sg.acc_col + c0), r);
                         tmem_ld_wait();
                         if (row < P.n) {
                             void* o = (char*)P.out + (row * P.ld_out + sg.col0 + c0) * (P.out_bf16 ? 2 : 4);
