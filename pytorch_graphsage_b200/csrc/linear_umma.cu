@@ -77,42 +77,6 @@ struct UmmaParams {
 struct UmmaMaps { CUtensorMap w[2]; CUtensorMap a[2]; CUtensorMap g[2]; };   // g: 64 x 1 box for tile::gather4 (rows by id)
 
 // 32 accumulator columns of one row: bias, activation (compile-time), convert, 16-byte stores when aligned
-template <int ACT>
-__device__ __forceinline__ void epilogue_store(const uint32_t* r, const float* bias, int valid, void* out, int out_bf16) {
-    float v[32];
-#pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-    if (bias) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) if (j < valid) v[j] += __ldg(bias + j);
-    }
-#pragma unroll
-    for (int j = 0; j < 32; ++j) {
-        if (ACT == GSAGE_ACT_RELU) v[j] = fmaxf(v[j], 0.0f);
-        if (ACT == GSAGE_ACT_TANH) v[j] = tanhf(v[j]);
-    }
-    const bool vec = valid == 32 && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
-    if (out_bf16) {
-        if (vec) {
-#pragma unroll
-            for (int q = 0; q < 4; ++q)
-                reinterpret_cast<uint4*>(out)[q] = make_uint4(pack_bf16(v[8 * q], v[8 * q + 1]), pack_bf16(v[8 * q + 2], v[8 * q + 3]),
-                                                              pack_bf16(v[8 * q + 4], v[8 * q + 5]), pack_bf16(v[8 * q + 6], v[8 * q + 7]));
-        } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) if (j < valid) reinterpret_cast<__nv_bfloat16*>(out)[j] = __float2bfloat16_rn(v[j]);
-        }
-    } else {
-        if (vec) {
-#pragma unroll
-            for (int q = 0; q < 8; ++q)
-                reinterpret_cast<float4*>(out)[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
-        } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) if (j < valid) reinterpret_cast<float*>(out)[j] = v[j];
-        }
-    }
-}
 
 // ---- the kernel ----------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kThreads, 1) linear_umma_kernel(const UmmaParams P, const __grid_constant__ UmmaMaps M) {
@@ -195,9 +159,9 @@ __global__ void __launch_bounds__(kThreads, 1) linear_umma_kernel(const UmmaPara
                         void* o = (char*)P.out + (row * P.ld_out + sg.col0 + c0) * (P.out_bf16 ? 2 : 4);
                         const float* bias = sg.bias ? sg.bias + c0 : nullptr;
                         const int valid = min(32, sg.O - c0);
-                        if (P.act == GSAGE_ACT_RELU) epilogue_store<GSAGE_ACT_RELU>(r, bias, valid, o, P.out_bf16);
-                        else if (P.act == GSAGE_ACT_TANH) epilogue_store<GSAGE_ACT_TANH>(r, bias, valid, o, P.out_bf16);
-                        else epilogue_store<GSAGE_ACT_NONE>(r, bias, valid, o, P.out_bf16);
+                        if (P.act == GSAGE_ACT_RELU) epilogue_store32<GSAGE_ACT_RELU>(r, bias, valid, o, P.out_bf16);
+                        else if (P.act == GSAGE_ACT_TANH) epilogue_store32<GSAGE_ACT_TANH>(r, bias, valid, o, P.out_bf16);
+                        else epilogue_store32<GSAGE_ACT_NONE>(r, bias, valid, o, P.out_bf16);
                     }
                 }
             }

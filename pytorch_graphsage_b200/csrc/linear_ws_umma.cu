@@ -54,46 +54,21 @@ struct WsParams {
     int tf32; int uk;
     int x3;                                   // 3 x TF32: D += A_hi W_hi^T + A_hi W_lo^T + A_lo W_hi^T (fp32 operands, W fully resident as hi + lo)
     int* err;
+    long long* dbg;                           // GSAGE_WS_TIMING builds only: per-role cycle counters of CTA 0
 };
 
 struct WsMaps { CUtensorMap w[2]; CUtensorMap a[2]; CUtensorMap g[2]; CUtensorMap wl[2]; };   // wl: the lo halves of W (3 x TF32)
 
-template <int ACT>
-__device__ __forceinline__ void ws_store32(const uint32_t* r, const float* bias, int valid, void* out, int out_bf16) {
-    float v[32];
-#pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-    if (bias) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) if (j < valid) v[j] += __ldg(bias + j);
-    }
-#pragma unroll
-    for (int j = 0; j < 32; ++j) {
-        if (ACT == GSAGE_ACT_RELU) v[j] = fmaxf(v[j], 0.0f);
-        if (ACT == GSAGE_ACT_TANH) v[j] = tanhf(v[j]);
-    }
-    const bool vec = valid == 32 && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
-    if (out_bf16) {
-        if (vec) {
-#pragma unroll
-            for (int q = 0; q < 4; ++q)
-                reinterpret_cast<uint4*>(out)[q] = make_uint4(pack_bf16(v[8 * q], v[8 * q + 1]), pack_bf16(v[8 * q + 2], v[8 * q + 3]),
-                                                              pack_bf16(v[8 * q + 4], v[8 * q + 5]), pack_bf16(v[8 * q + 6], v[8 * q + 7]));
-        } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) if (j < valid) reinterpret_cast<__nv_bfloat16*>(out)[j] = __float2bfloat16_rn(v[j]);
-        }
-    } else {
-        if (vec) {
-#pragma unroll
-            for (int q = 0; q < 8; ++q)
-                reinterpret_cast<float4*>(out)[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
-        } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) if (j < valid) reinterpret_cast<float*>(out)[j] = v[j];
-        }
-    }
-}
+
+#ifdef GSAGE_WS_TIMING
+#define WT_DECL long long wt_a = 0, wt_b = 0, wt_c = 0, wt_t = clock64()
+#define WT_LAP(x) do { const long long n_ = clock64(); (x) += n_ - wt_t; wt_t = n_; } while (0)
+#define WT_OUT(base, cond) do { if (P.dbg && blockIdx.x == 0 && (cond)) { P.dbg[(base)] = wt_a; P.dbg[(base) + 1] = wt_b; P.dbg[(base) + 2] = wt_c; } } while (0)
+#else
+#define WT_DECL
+#define WT_LAP(x)
+#define WT_OUT(base, cond)
+#endif
 
 __global__ void __launch_bounds__(kWsThreads, 1) linear_ws_umma_kernel(const WsParams P, const __grid_constant__ WsMaps M) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -131,14 +106,18 @@ __global__ void __launch_bounds__(kWsThreads, 1) linear_ws_umma_kernel(const WsP
 
     if (warp < kWsEpiWarps) {
         // =========================== EPILOGUE ===========================
+        // (twelve warps -- the idle splitter warps of the non-x3 modes as a third turn -- measured 4-8 % slower than eight)
         const int quarter = warp & 3, turn = warp >> 2;      // TMEM lane quarter; which of every two 32-column chunks is mine
         const int row_in_tile = quarter * 32 + lane;         // TMEM lane == tile row
         int it = 0;
+        WT_DECL;
         for (int ph = 0; ph < P.n_phases; ++ph) {
             for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x, ++it) {
                 const int buf = it & 1;
+                WT_LAP(wt_c);
                 mbar_wait(tfull_bar(buf), (it >> 1) & 1, P.err);
                 tc_fence_after();
+                WT_LAP(wt_a);
                 const int64_t row = (int64_t)tile * WM + row_in_tile;
                 int chunk = 0;
                 for (int si = 0; si < P.phase_count[ph]; ++si) {
@@ -153,16 +132,18 @@ __global__ void __launch_bounds__(kWsThreads, 1) linear_ws_umma_kernel(const WsP
                             const float* bias = sg.bias ? sg.bias + c0 : nullptr;
                             const int valid = min(32, sg.O_store - c0);
                             if (valid <= 0) continue;
-                            if (P.act == GSAGE_ACT_RELU) ws_store32<GSAGE_ACT_RELU>(r, bias, valid, o, P.out_bf16);
-                            else if (P.act == GSAGE_ACT_TANH) ws_store32<GSAGE_ACT_TANH>(r, bias, valid, o, P.out_bf16);
-                            else ws_store32<GSAGE_ACT_NONE>(r, bias, valid, o, P.out_bf16);
+                            if (P.act == GSAGE_ACT_RELU) epilogue_store32<GSAGE_ACT_RELU>(r, bias, valid, o, P.out_bf16);
+                            else if (P.act == GSAGE_ACT_TANH) epilogue_store32<GSAGE_ACT_TANH>(r, bias, valid, o, P.out_bf16);
+                            else epilogue_store32<GSAGE_ACT_NONE>(r, bias, valid, o, P.out_bf16);
                         }
                     }
                 }
+                WT_LAP(wt_b);
                 tc_fence_before();
                 mbar_arrive(tempty_bar(buf));
             }
         }
+        WT_OUT(0, threadIdx.x == 0);                         // wait tfull | tcgen05.ld + act + stores | arrive + loop
     } else if (warp == kWsEpiWarps) {
         // =========================== MMA ISSUER ===========================
         // ONE thread runs this loop, and it is the critical path of the kernel: every instruction between two stages is
@@ -179,13 +160,16 @@ __global__ void __launch_bounds__(kWsThreads, 1) linear_ws_umma_kernel(const WsP
             const uint32_t n_stages = (uint32_t)P.stages;
             uint32_t stage = 0, par = 0, a16 = ring16;           // ring slot, its parity, its address / 16
             int it = 0;
+            WT_DECL;
             for (int ph = 0; ph < P.n_phases; ++ph) {
                 mbar_wait(wfull_bar, ph & 1, P.err);             // this phase's resident weights have landed
                 const int s_first = P.phase_first[ph], s_count = P.phase_count[ph];
                 for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x, ++it) {
                     const uint32_t buf = it & 1;
+                    WT_LAP(wt_c);
                     mbar_wait(tempty_bar(buf), ((it >> 1) & 1) ^ 1, P.err);     // first use of each buffer passes immediately
                     tc_fence_after();
+                    WT_LAP(wt_a);
                     for (int si = 0; si < s_count; ++si) {
                         const WsSeg& sg = P.seg[s_first + si];
                         // instruction descriptor: D = f32, A = B = bf16 | tf32, both K-major, N = O, M = 128
@@ -195,7 +179,9 @@ __global__ void __launch_bounds__(kWsThreads, 1) linear_ws_umma_kernel(const WsP
                         uint64_t wdesc = desc_hi | (uint64_t)((smem_u32(smem + sg.w_off) & 0x3FFFF) >> 4);
                         const int kchunks = sg.kchunks, kres = sg.kres;
                         for (int kc = 0; kc < kchunks; ++kc) {
+                            WT_LAP(wt_c);
                             mbar_wait(P.x3 ? split_bar(stage) : full_bar(stage), par, P.err);
+                            WT_LAP(wt_b);
                             const uint32_t a_stage = stage;
                             const uint64_t adesc = desc_hi | (uint64_t)a16;
                             if (++stage == n_stages) { stage = 0; par ^= 1; a16 = ring16; } else a16 += sb16;
@@ -235,6 +221,8 @@ __global__ void __launch_bounds__(kWsThreads, 1) linear_ws_umma_kernel(const WsP
                 }
                 umma_commit(wempty_bar);                                 // every MMA that reads this phase's W has retired
             }
+            WT_LAP(wt_c);
+            WT_OUT(4, true);                                     // wait tempty | wait for the stage (rows landed / split) | issue
         }
         __syncwarp();
     } else if (warp >= kWsEpiWarps + 1 + kWsTmaWarps) {
@@ -249,13 +237,16 @@ __global__ void __launch_bounds__(kWsThreads, 1) linear_ws_umma_kernel(const WsP
             const uint32_t ring_u = smem_u32(a_ring), sb = (uint32_t)P.stage_bytes;
             const uint32_t n_stages = (uint32_t)P.stages;
             uint32_t stage = 0, par = 0, sa_u = ring_u;
+            WT_DECL;
             for (int ph = 0; ph < P.n_phases; ++ph) {
                 const int s_first = P.phase_first[ph], s_count = P.phase_count[ph];
                 for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x) {
                     for (int si = 0; si < s_count; ++si) {
                         const int kchunks = P.seg[s_first + si].kchunks;
                         for (int kc = 0; kc < kchunks; ++kc) {
+                            WT_LAP(wt_c);
                             mbar_wait(full_bar(stage), par, P.err);
+                            WT_LAP(wt_a);
                             const uint32_t at = sa_u + (uint32_t)t * 16u;
 #pragma unroll
                             for (int q = 0; q < 8; ++q) {
@@ -269,11 +260,13 @@ __global__ void __launch_bounds__(kWsThreads, 1) linear_ws_umma_kernel(const WsP
                             }
                             fence_proxy_async();                     // generic-proxy stores -> visible to the tensor core
                             mbar_arrive(split_bar(stage));
+                            WT_LAP(wt_b);
                             if (++stage == n_stages) { stage = 0; par ^= 1; sa_u = ring_u; } else sa_u += sb;
                         }
                     }
                 }
             }
+            WT_OUT(8, t == 0);                                   // wait for the rows | split + fence + arrive | loop
         }
     } else {
         // =========================== TMA PRODUCERS ===========================
@@ -506,6 +499,12 @@ static int ws_launch(const LinearParams& P, bool x3, cudaStream_t s) {
         GS_CUDA(cudaMemset(g_ws_err, 0, sizeof(int)));
     }
     U.err = g_ws_err;
+#ifdef GSAGE_WS_TIMING
+    static long long* g_ws_dbg = nullptr;
+    if (!g_ws_dbg) { GS_CUDA(cudaMalloc((void**)&g_ws_dbg, 16 * sizeof(long long))); }
+    GS_CUDA(cudaMemsetAsync(g_ws_dbg, 0, 16 * sizeof(long long), s));
+    U.dbg = g_ws_dbg;
+#endif
     const size_t smem = (size_t)U.w_area + (size_t)U.stages * U.stage_bytes + 1024 /*align slack*/ + 512 /*barriers*/;
     GS_CHECK_ARG(smem <= (size_t)kSmemLimit, "linear_ws_umma: %zu bytes of shared memory needed", smem);
     static bool attr_set = false;
@@ -525,6 +524,20 @@ static int ws_launch(const LinearParams& P, bool x3, cudaStream_t s) {
         else GS_TRY(make_map(&maps.g[i], g.a, g.a_rows > 0 ? g.a_rows : 0x7FFFFFFF, g.d, g.lda, 1, es));       // rows by id
     }
     linear_ws_umma_kernel<<<grid, kWsThreads, smem, s>>>(U, maps);
+#ifdef GSAGE_WS_TIMING
+    if (U.n_tiles >= 8 * grid) {                                 // (big launches only)
+        long long h[16];
+        GS_CUDA(cudaStreamSynchronize(s));
+        GS_CUDA(cudaMemcpy(h, g_ws_dbg, sizeof(h), cudaMemcpyDeviceToHost));
+        const double t = (double)((U.n_tiles + grid - 1) / grid) * U.n_phases;
+        int stages_per_tile = 0;
+        for (int i = 0; i < P.n_segs; ++i) stages_per_tile += U.seg[i].kchunks;
+        fprintf(stderr, "[ws timing] n %lld tiles/CTA %.0f phases %d x3 %d tf32 %d ring %d x %d B, %d A stages per tile | per tile, CTA 0:  epilogue warp 0: wait tfull %.0f, "
+                        "ld+act+store %.0f, arrive %.0f | MMA thread: wait tempty %.0f, wait stage %.0f, issue %.0f | splitter 0: wait rows %.0f, split %.0f, loop %.0f\n",
+                (long long)U.n, t, U.n_phases, U.x3, U.tf32, U.stages, U.stage_bytes, stages_per_tile, h[0] / t, h[1] / t, h[2] / t, h[4] / t, h[5] / t, h[6] / t,
+                h[8] / t, h[9] / t, h[10] / t);
+    }
+#endif
     GS_LAUNCHED();
     return GSAGE_OK;
 }

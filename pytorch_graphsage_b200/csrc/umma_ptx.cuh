@@ -198,4 +198,65 @@ static int make_map(CUtensorMap* m, const void* base, int64_t rows, int64_t cols
 }
 
 
+// one 32-byte store (a whole DRAM sector per thread; st.global.v8.b32 needs sm_100+)
+__device__ __forceinline__ void st_global_v8(void* p, uint32_t a, uint32_t b, uint32_t c, uint32_t d, uint32_t e, uint32_t f, uint32_t g, uint32_t h) {
+    asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(a), "r"(b), "r"(c), "r"(d), "r"(e), "r"(f), "r"(g), "r"(h) : "memory");
+}
+
+// The projection kernels' epilogue for one thread: 32 accumulator columns of ONE output row (TMEM lane = row) -> + bias -> ACT -> HBM.
+// A thread owns a row segment, so every warp-wide store touches 32 different lines and the LSU takes them one by one: the
+// stores, not the MMAs, set the pace of the weight-stationary kernel whenever d <= 256 (cycle counters:
+// profiles/r02_linear_ws_phase_cycles.txt).  32-byte stores halve the number of requests (bf16, d = 64: 186 -> 124 us); staging
+// the chunk through shared memory to store along the rows was slower on every shape (the tensor core's operand reads already
+// use the shared-memory bandwidth: 8 KB per 67-cycle MMA).
+template <int ACT>
+__device__ __forceinline__ void epilogue_store32(const uint32_t* r, const float* bias, int valid, void* out, int out_bf16) {
+    float v[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+    if (bias) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) if (j < valid) v[j] += __ldg(bias + j);
+    }
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+        if (ACT == GSAGE_ACT_RELU) v[j] = fmaxf(v[j], 0.0f);
+        if (ACT == GSAGE_ACT_TANH) v[j] = tanhf(v[j]);
+    }
+    const bool vec = valid == 32 && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
+    const bool vec32 = vec && ((reinterpret_cast<uintptr_t>(out) & 31) == 0);
+    if (out_bf16) {
+        if (vec32) {
+#pragma unroll
+            for (int q = 0; q < 2; ++q)
+                st_global_v8(reinterpret_cast<char*>(out) + 32 * q, pack_bf16(v[16 * q], v[16 * q + 1]), pack_bf16(v[16 * q + 2], v[16 * q + 3]),
+                             pack_bf16(v[16 * q + 4], v[16 * q + 5]), pack_bf16(v[16 * q + 6], v[16 * q + 7]), pack_bf16(v[16 * q + 8], v[16 * q + 9]),
+                             pack_bf16(v[16 * q + 10], v[16 * q + 11]), pack_bf16(v[16 * q + 12], v[16 * q + 13]), pack_bf16(v[16 * q + 14], v[16 * q + 15]));
+        } else if (vec) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                reinterpret_cast<uint4*>(out)[q] = make_uint4(pack_bf16(v[8 * q], v[8 * q + 1]), pack_bf16(v[8 * q + 2], v[8 * q + 3]),
+                                                              pack_bf16(v[8 * q + 4], v[8 * q + 5]), pack_bf16(v[8 * q + 6], v[8 * q + 7]));
+        } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) if (j < valid) reinterpret_cast<__nv_bfloat16*>(out)[j] = __float2bfloat16_rn(v[j]);
+        }
+    } else {
+        if (vec32) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                st_global_v8(reinterpret_cast<char*>(out) + 32 * q, __float_as_uint(v[8 * q]), __float_as_uint(v[8 * q + 1]), __float_as_uint(v[8 * q + 2]),
+                             __float_as_uint(v[8 * q + 3]), __float_as_uint(v[8 * q + 4]), __float_as_uint(v[8 * q + 5]), __float_as_uint(v[8 * q + 6]),
+                             __float_as_uint(v[8 * q + 7]));
+        } else if (vec) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+                reinterpret_cast<float4*>(out)[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+        } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) if (j < valid) reinterpret_cast<float*>(out)[j] = v[j];
+        }
+    }
+}
+
 }  // namespace gsage
