@@ -1,7 +1,8 @@
 #!/usr/bin/env python
 """DRAM bytes of ONE launch of each workload's dominant kernel (`roofline.traffic` of bench.py), from ncu:
 
-    python profiles/capture_traffic.py OUTDIR            (on a GPU box; writes OUTDIR/traffic.json + the raw CSVs)
+    python profiles/capture_traffic.py OUTDIR [WORKLOAD ...]     (on a GPU box; writes OUTDIR/traffic.json + the raw CSVs;
+                                                                  workloads given: only those)
 
 For every workload: `ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum` over a 3-step bench run,
 the launches of the dominant kernel are filtered by name and the LONGEST one (layer 1 on the (x1, x2) pair) is taken."""
@@ -21,7 +22,10 @@ def main(out):
     res = {'_note': 'dram__bytes_read.sum + dram__bytes_write.sum of the LONGEST launch of the dominant kernel of each workload '
                     '(layer 1 on the (x1, x2) pair), ncu --metrics pass over `bench.py --workload W --batch B --steps 3`; '
                     'made by profiles/capture_traffic.py'}
+    only = sys.argv[2:]
     for wl, B, kern in WORK:
+        if only and wl not in only:
+            continue
         log = os.path.join(out, 'traffic_%s.csv' % wl)
         cmd = ['ncu', '--metrics', 'dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum', '--clock-control', 'none',
                '-k', 'regex:' + kern, '-c', '40', '--csv', '--log-file', log,
