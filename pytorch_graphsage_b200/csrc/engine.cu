@@ -25,6 +25,9 @@ int sample_sparse_launch(gsage_graph* g, const int64_t* ids, int64_t n, int S, c
 int gather_reduce_launch(const void* table, int dtype, int64_t ld, int64_t rows, int d, const int64_t* ids,
                          int64_t n_parents, int S, int reduce, const float* weights, void* out, int out_dtype,
                          int64_t ld_out, cudaStream_t s, int l2_hint = 0);
+bool head_fused_eligible(int d, int n_classes);
+int head_fused_launch(const float* z, int64_t ld, int64_t n, int d, const float* w, const float* b, int n_classes, float* zn, int64_t ld_zn,
+                      float* logits, int64_t ld_logits, cudaStream_t s);
 
 // a set of rows some kernel will read: either (table, ids) gathered on the fly or a materialised buffer
 struct RowSrc {
@@ -1063,6 +1066,13 @@ static int forward_layers(gsage_engine* e, int64_t B, float* logits_dev, cudaStr
 
     // ---- normalise + classifier (models.py:90-91) -----------------------------------------------------------------
     const int p_head = e->prof.begin(GSAGE_PROF_HEAD, s);
+    if (head_fused_eligible(2 * O2, c.n_classes)) {           // few classes: normalise + classifier as one launch, fp32 FFMA (gather_reduce.cu)
+        GS_TRY(head_fused_launch(e->Z, 2 * O2, n0, 2 * O2, e->w.fc_w, e->w.fc_b, c.n_classes, e->ZN, 2 * O2, logits_dev, c.n_classes, s));
+        e->prof.end(p_head, s);
+        e->prof.end(p_all, s);
+        GS_TRY(mark_slot_done(e, s));
+        return GSAGE_OK;
+    }
     GS_TRY(gsage_l2_normalize(e->Z, GSAGE_F32, 2 * O2, n0, 2 * O2, e->ZN, 2 * O2, s));
     RowSrc zn{e->ZN, GSAGE_F32, 2 * O2, n0, nullptr, 2 * O2};
     if (T == GSAGE_BF16 && e->fc_pad > 0 && (2 * O2) % 4 == 0 && getenv("GSAGE_FC_EXACT") == nullptr) {

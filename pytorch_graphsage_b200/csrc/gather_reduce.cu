@@ -211,6 +211,90 @@ __global__ void __launch_bounds__(256) l2_normalize_kernel(const T* __restrict__
     for (int c = lane; c < d; c += 32) out[r * ld_out + c] = ElemTraits<T>::load(x + r * ld + c) * inv;
 }
 
+// --------------------------------------------------------------------------------------------------
+// normalise + classifier in one launch (models.py:90-91): zn = F.normalize(z, dim=1); logits = fc(zn).
+// The head is 16 K rows x 256 -> 41 classes: two launches of nothing, but under the sample-ahead pipeline each of them
+// queues behind the next batch's sampling kernels (0.06-0.07 ms of a 0.7-1.4 ms step, 0.024 alone).  One warp takes kHeadRows
+// rows: a lane keeps VPL = D / 32 values of each, reads its VPL values of a classifier row once for all of them, and the
+// class's dot products are reduced by shuffles.  fp32 FFMA throughout (exact mode and bf16 mode alike); zn is written for the
+// backward pass.
+// --------------------------------------------------------------------------------------------------
+static constexpr int kHeadRows = 4;
+
+template <int VPL>
+__global__ void __launch_bounds__(256) head_kernel(const float* __restrict__ z, int64_t ld, int64_t n, const float* __restrict__ w,
+                                                   const float* __restrict__ b, int n_classes, float* __restrict__ zn, int64_t ld_zn,
+                                                   float* __restrict__ logits, int64_t ld_logits) {
+    constexpr int D = 32 * VPL;
+    const int lane = threadIdx.x & 31;
+    const int64_t r0 = ((int64_t)blockIdx.x * 8 + (threadIdx.x >> 5)) * kHeadRows;
+    if (r0 >= n) return;
+    float x[kHeadRows][VPL];
+#pragma unroll
+    for (int i = 0; i < kHeadRows; ++i) {
+        const int64_t r = r0 + i < n ? r0 + i : n - 1;          // (a ragged last group repeats its last row; nothing of it is stored)
+        float ss = 0.0f;
+#pragma unroll
+        for (int v = 0; v < VPL; ++v) { x[i][v] = z[r * ld + lane + 32 * v]; ss = fmaf(x[i][v], x[i][v], ss); }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xFFFFFFFFu, ss, o);
+        const float inv = 1.0f / fmaxf(sqrtf(ss), 1e-12f);
+#pragma unroll
+        for (int v = 0; v < VPL; ++v) {
+            x[i][v] *= inv;
+            if (r0 + i < n) zn[(r0 + i) * ld_zn + lane + 32 * v] = x[i][v];
+        }
+    }
+    for (int c = 0; c < n_classes; ++c) {
+        float wv[VPL], acc[kHeadRows];
+#pragma unroll
+        for (int v = 0; v < VPL; ++v) wv[v] = __ldg(w + (int64_t)c * D + lane + 32 * v);
+#pragma unroll
+        for (int i = 0; i < kHeadRows; ++i) {
+            acc[i] = 0.0f;
+#pragma unroll
+            for (int v = 0; v < VPL; ++v) acc[i] = fmaf(x[i][v], wv[v], acc[i]);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+            for (int i = 0; i < kHeadRows; ++i) acc[i] += __shfl_xor_sync(0xFFFFFFFFu, acc[i], o);
+        }
+        if (lane < kHeadRows && r0 + lane < n) {
+            float mine = acc[0];
+#pragma unroll
+            for (int i = 1; i < kHeadRows; ++i) mine = lane == i ? acc[i] : mine;
+            logits[(r0 + lane) * ld_logits + c] = mine + __ldg(b + c);
+        }
+    }
+}
+
+// few classes only: with 41 the per-class shuffle reductions make it slower than the two launches it replaces (reddit head 0.068 ->
+// 0.098 ms, big10m 0.070 -> 0.101; pokec regression, 1 output: 0.079 -> 0.021)
+bool head_fused_eligible(int d, int n_classes) {
+    return d % 32 == 0 && d >= 32 && d <= 256 && n_classes <= 8 && getenv("GSAGE_NO_FUSED_HEAD") == nullptr;
+}
+
+int head_fused_launch(const float* z, int64_t ld, int64_t n, int d, const float* w, const float* b, int n_classes, float* zn, int64_t ld_zn,
+                      float* logits, int64_t ld_logits, cudaStream_t s) {
+    if (n == 0) return GSAGE_OK;
+    const unsigned grid = (unsigned)ceil_div(ceil_div(n, (int64_t)kHeadRows), 8);
+#define GS_HEAD(V) head_kernel<V><<<grid, 256, 0, s>>>(z, ld, n, w, b, n_classes, zn, ld_zn, logits, ld_logits)
+    switch (d / 32) {
+        case 1: GS_HEAD(1); break;
+        case 2: GS_HEAD(2); break;
+        case 3: GS_HEAD(3); break;
+        case 4: GS_HEAD(4); break;
+        case 5: GS_HEAD(5); break;
+        case 6: GS_HEAD(6); break;
+        case 7: GS_HEAD(7); break;
+        default: GS_HEAD(8); break;
+    }
+#undef GS_HEAD
+    GS_LAUNCHED();
+    return GSAGE_OK;
+}
+
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 int gather_reduce_launch(const void* table, int dtype, int64_t ld, int64_t rows, int d, const int64_t* ids,
