@@ -303,7 +303,11 @@ int attention_fused_launch(const void* a, int64_t lda, const int64_t* ids, int d
         GS_CUDA(cudaFuncSetAttribute(attention_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAtSmemLimit));
         attr_set = true;
     }
-    const int grid = U.n_tiles < sm_count() ? U.n_tiles : sm_count();
+    // grid = waves x SMs, one CTA resident per SM at a time (profiling knob): > 1 hands the tiles out in smaller static shares; measured slower for this kernel
+    // (profiles/r02_persistent_waves.txt), unlike the single-phase projections (linear_ws_umma.cu)
+    static const int waves = getenv("GSAGE_ATT_WAVES") ? atoi(getenv("GSAGE_ATT_WAVES")) : 1;
+    const int slots = sm_count() * (waves < 1 ? 1 : waves);
+    const int grid = U.n_tiles < slots ? U.n_tiles : slots;
     attention_fused_kernel<<<grid, kAtThreads, smem, s>>>(U, maps);
     GS_LAUNCHED();
     return GSAGE_OK;

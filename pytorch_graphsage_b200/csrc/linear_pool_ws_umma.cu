@@ -464,7 +464,11 @@ static int q_launch(const LinearParams& P, const float* dP, int64_t ld_dp, void*
     if (g.ids) GS_TRY(make_map(&maps.a, g.a, g.a_rows > 0 ? g.a_rows : 0x7FFFFFFF, g.d, g.lda, 1, es));
     else GS_TRY(make_map(&maps.a, g.a, P.n, g.d, g.lda, QN, es));
     const size_t smem = (size_t)U.bpp * U.kchunks * kQWChunk + (size_t)kQStages * kQRChunk + 1024 + 512 + kQIdBytes;
-    const int grid = U.n_tiles < sm_count() ? U.n_tiles : sm_count();
+    // grid = waves x SMs, one CTA resident per SM at a time (profiling knob): > 1 hands the tiles out in smaller static shares; measured slower for this kernel
+    // (profiles/r02_persistent_waves.txt), unlike the single-phase projections (linear_ws_umma.cu)
+    static const int waves = getenv("GSAGE_POOL_WAVES") ? atoi(getenv("GSAGE_POOL_WAVES")) : 1;
+    const int slots = sm_count() * (waves < 1 ? 1 : waves);
+    const int grid = U.n_tiles < slots ? U.n_tiles : slots;
 #define GS_Q_LAUNCH(MX, SCT, BW)                                                                                                   \
     do {                                                                                                                           \
         static bool attr_set = false;                                                                                              \

@@ -517,7 +517,14 @@ static int ws_launch(const LinearParams& P, bool x3, cudaStream_t s) {
         GS_CUDA(cudaFuncSetAttribute(linear_ws_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
         attr_set = true;
     }
-    const int grid = U.n_tiles < sm_count() ? U.n_tiles : sm_count();
+    // grid = waves x SMs, one CTA resident per SM at a time (profiling knob): > 1 hands the tiles out in smaller static shares, so an
+    // SM that starts late (the next batch's sampling kernels run underneath) ends up with fewer of them, at the price of one more
+    // weight load and pipeline ramp per CTA.  Two calls disagreed on the sign for the single-phase projections (-29 % / +10 %:
+    // profiles/r02_persistent_waves.txt), the two-phase d = 602 projection and the pool / attention kernels were slower: default 1
+    static const int env_waves = getenv("GSAGE_WS_WAVES") ? atoi(getenv("GSAGE_WS_WAVES")) : 0;
+    const int waves = env_waves > 0 ? env_waves : 1;
+    const int slots = sm_count() * waves;
+    const int grid = U.n_tiles < slots ? U.n_tiles : slots;
     WsMaps maps;
     memset(&maps, 0, sizeof(maps));
     const int es = U.tf32 ? 4 : 2;
