@@ -124,7 +124,7 @@ struct gsage_engine {
     cudaEvent_t ev_done[2] = {nullptr, nullptr}; bool done_valid[2] = {false, false};   // last reader of each id slot (forward / backward) finished
     // mean aggregator: the sample-ahead stream starts AFTER the dominant (HBM-bound) gather+mean launch of the forward in
     // flight, so its kernels share the SMs with the projection / layer-2 tail instead of slowing the bandwidth-bound kernel
-    cudaEvent_t ev_mid = nullptr; bool mid_valid = false; int ahead_after_gather = 1; int ahead_split = 0;   // split: draws before the gate (measured: step -1 %, gather kernel +2 %: off)
+    cudaEvent_t ev_mid = nullptr; bool mid_valid = false; int ahead_after_gather = 1; int ahead_split = 0;   // split: the RNG draws of the next batch run ahead of the gate, i.e. under the dominant launch (measured twice: off)
     struct Ahead { bool valid = false; const void* src = nullptr; int64_t B = 0, global_B = 0, first = 0;
                    gsage_graph* g = nullptr; gsage_rng* rng = nullptr; } ahead;
     // the producer of the NEXT batch's ids on the caller's stream: recorded by gsage_engine_inputs_ready (before the forward in
@@ -451,6 +451,9 @@ int gsage_engine_create(const gsage_engine_config* cfg, gsage_engine** out) {
     if (const char* f = getenv("GSAGE_CHUNK")) e->chunk_parents = atoll(f);
     if (const char* f = getenv("GSAGE_L2HINT")) e->l2_hint = atoi(f);
     if (const char* f = getenv("GSAGE_AHEAD_AFTER_GATHER")) e->ahead_after_gather = atoi(f);
+    // GSAGE_AHEAD_SPLIT=1: the next batch's RNG draws (count / scan / scatter, refill included) under the dominant launch instead of
+    // under the projection tail.  Two calls on the final build (profiles/r02_ahead_split.txt): step -1.8 % then +-0 on reddit, the
+    // gather kernel 2 % slower both times (0.986 -> 0.966 of the copy peak), the attention kernel 11 % slower: off
     if (const char* f = getenv("GSAGE_AHEAD_SPLIT")) e->ahead_split = atoi(f);
     const int64_t es = (int64_t)dtype_size(e->T);
     const int64_t vec = 16 / es;
